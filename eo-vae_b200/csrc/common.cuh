@@ -1,0 +1,89 @@
+// Shared device/host helpers for the eo-vae sm_100a kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+// ---------------------------------------------------------------- error reporting (C-ABI: eovae_last_error)
+namespace eovae {
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+}  // namespace eovae
+
+#define EOVAE_CHECK(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      eovae::set_error(__VA_ARGS__);      \
+      return -1;                          \
+    }                                     \
+  } while (0)
+
+#define EOVAE_CUDA(call)                                  \
+  do {                                                    \
+    if (eovae::check_cuda((call), #call) != 0) return -2; \
+  } while (0)
+
+#define EOVAE_LAUNCH_CHECK() EOVAE_CUDA(cudaGetLastError())
+
+// dtype codes used across the C-ABI
+enum : int { EOVAE_BF16 = 0, EOVAE_F16 = 1, EOVAE_F32 = 2 };  // == EOVAE_DT_* in include/eovae.h
+
+// ---------------------------------------------------------------- 16-bit <-> float helpers
+template <typename T>
+struct T16;
+template <>
+struct T16<__nv_bfloat16> {
+  using v2 = __nv_bfloat162;
+  static __device__ __forceinline__ float2 to_f2(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+  }
+  static __device__ __forceinline__ uint32_t from_f2(float a, float b) {
+    __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <>
+struct T16<__half> {
+  using v2 = __half2;
+  static __device__ __forceinline__ float2 to_f2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  }
+  static __device__ __forceinline__ uint32_t from_f2(float a, float b) {
+    __half2 r = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+
+__device__ __forceinline__ float2 unpack16(uint32_t u, int dtype) {
+  return dtype == EOVAE_BF16 ? T16<__nv_bfloat16>::to_f2(u) : T16<__half>::to_f2(u);
+}
+__device__ __forceinline__ uint32_t pack16(float a, float b, int dtype) {
+  return dtype == EOVAE_BF16 ? T16<__nv_bfloat16>::from_f2(a, b) : T16<__half>::from_f2(a, b);
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+int eovae_num_sms();

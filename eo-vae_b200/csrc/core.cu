@@ -1,0 +1,121 @@
+// Library plumbing (error slot, device query) and weight-packing kernels.
+#include "../../include/eovae.h"
+#include "common.cuh"
+
+namespace eovae {
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return -2;
+}
+}  // namespace eovae
+
+int eovae_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+namespace {
+
+template <typename T>
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int taps,
+                                        int kpt, long long total) {
+  // out[o][tap][c] (c < kpt), zero for o >= cout or c >= cin
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % kpt);
+  long long t = i / kpt;
+  const int tap = static_cast<int>(t % taps);
+  const int o = static_cast<int>(t / taps);
+  float v = 0.f;
+  if (o < cout && c < cin) v = w[(static_cast<long long>(o) * cin + c) * taps + tap];
+  out[i] = T16<T>::from_f(v);
+}
+
+template <typename T>
+__global__ void pack_dyn_weight_kernel(const float* __restrict__ wk, int c, int embed, int decoder, float scale,
+                                       T* __restrict__ packed, int kpt, int rows_pad, float* __restrict__ oihw,
+                                       const float* __restrict__ bias_raw, float bias_scale,
+                                       float* __restrict__ bias_out, int nbias) {
+  if (blockIdx.x == 0 && bias_out != nullptr)
+    for (int i = threadIdx.x; i < nbias; i += blockDim.x) bias_out[i] = bias_raw[i] * bias_scale;
+  // wk: [c][9*embed], flat (tap*embed + e).  Encoder conv weight W[e][band][tap]; decoder W[band][e][tap].
+  const int rows = decoder ? c : embed;  // Cout
+  const int cin = decoder ? embed : c;
+  const long long total = static_cast<long long>(rows_pad) * 9 * kpt;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % kpt);
+    long long t = i / kpt;
+    const int tap = static_cast<int>(t % 9);
+    const int o = static_cast<int>(t / 9);
+    float v = 0.f;
+    if (o < rows && ci < cin) {
+      const int band = decoder ? o : ci;
+      const int e = decoder ? ci : o;
+      v = wk[static_cast<long long>(band) * 9 * embed + tap * embed + e] * scale;
+      if (oihw != nullptr) oihw[(static_cast<long long>(o) * cin + ci) * 9 + tap] = v;
+    }
+    packed[i] = T16<T>::from_f(v);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int eovae_version(void) { return EOVAE_ABI_VERSION; }
+const char* eovae_last_error(void) { return eovae::g_err; }
+
+int eovae_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, int kh, int kw, int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK((kh == 3 && kw == 3) || (kh == 1 && kw == 1), "pack_conv_weight: only 3x3 and 1x1 kernels");
+  const int taps = kh * kw;
+  const int kpt = eovae_conv_k_per_tap(cin);
+  const long long total = static_cast<long long>(round_up(cout, 16)) * taps * kpt;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == EOVAE_BF16)
+    pack_conv_weight_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, taps, kpt, total);
+  else if (dtype == EOVAE_F16)
+    pack_conv_weight_kernel<__half><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, taps, kpt, total);
+  else
+    EOVAE_CHECK(false, "pack_conv_weight: bad dtype %d", dtype);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_pack_dyn_weight(const float* wk, int c, int embed, int decoder, float scale, void* packed, int dtype,
+                          int k_per_tap, int rows_pad, float* oihw_out, const float* bias_raw, float bias_scale,
+                          float* bias_out, int nbias, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int rows = decoder ? c : embed;
+  const int cin = decoder ? embed : c;
+  EOVAE_CHECK(rows_pad >= rows && k_per_tap >= cin, "pack_dyn_weight: padding smaller than extent");
+  const long long total = static_cast<long long>(rows_pad) * 9 * k_per_tap;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  if (dtype == EOVAE_BF16)
+    pack_dyn_weight_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(wk, c, embed, decoder, scale, static_cast<__nv_bfloat16*>(packed), k_per_tap, rows_pad, oihw_out, bias_raw, bias_scale, bias_out, nbias);
+  else if (dtype == EOVAE_F16)
+    pack_dyn_weight_kernel<__half><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(wk, c, embed, decoder, scale, static_cast<__half*>(packed), k_per_tap, rows_pad, oihw_out, bias_raw, bias_scale, bias_out, nbias);
+  else
+    EOVAE_CHECK(false, "pack_dyn_weight: bad dtype %d", dtype);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

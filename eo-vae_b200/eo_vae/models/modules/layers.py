@@ -1,0 +1,170 @@
+"""Flux2-AE building blocks on the sm_100a kernels.
+
+Mirrors the reference interface of ``eo_vae/models/modules/layers.py`` (Normalize :14, swish :21, Downsample :25,
+Upsample :40, ResnetBlock :53, AttnBlock :117): same constructor arguments, parameter names and shapes (OIHW fp32
+master weights), same forward signatures.  Forward math runs in: GroupNorm statistics (warp-shuffle reduction) ->
+normalise+affine+SiLU -> tcgen05 implicit-GEMM conv with bias / residual fused in the epilogue.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from ... import ops
+from ...settings import compute_dtype
+
+
+def Normalize(in_channels: int, num_groups: int = 32) -> nn.Module:
+    return GroupNormSM100(num_groups=num_groups, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+def swish(x: Tensor) -> Tensor:
+    """x * sigmoid(x).  Inside the blocks SiLU is fused into the GroupNorm-apply kernel; this free function only
+    exists for API parity and works on any tensor."""
+    return x * torch.sigmoid(x)
+
+
+class GroupNormSM100(nn.GroupNorm):
+    """nn.GroupNorm parameter container whose forward runs eovae_gn_stats + eovae_gn_apply."""
+
+    def forward(self, x: Tensor, silu: bool = False) -> Tensor:  # noqa: D102
+        x = ops.to_act(x, compute_dtype())
+        return ops.group_norm(x, self.weight, self.bias, silu, self.num_groups, self.eps)
+
+
+class Conv2dSM100(nn.Conv2d):
+    """nn.Conv2d parameter container (same init, same state_dict keys) executed by eovae_conv2d.
+
+    The K-major 16-bit operand is a derived cache keyed on the parameter version, so optimiser steps and
+    ``load_state_dict`` invalidate it automatically."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0):
+        super().__init__(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding)
+        k = self.kernel_size[0]
+        if (k, self.stride[0], self.padding[0]) == (3, 1, 1):
+            self._mode = ops.CONV_3X3
+        elif (k, self.stride[0], self.padding[0]) == (1, 1, 0):
+            self._mode = ops.CONV_1X1
+        elif (k, self.stride[0], self.padding[0]) == (3, 2, 0):
+            self._mode = ops.CONV_3X3_S2  # caller semantics: F.pad(0,1,0,1) first (Downsample)
+        else:
+            raise ValueError("Conv2dSM100 supports 3x3/s1/p1, 1x1 and the Downsample 3x3/s2/p0 convolution only")
+        self._packed = None
+        self._packed_key = None
+
+    def packed_weight(self, dtype) -> Tensor:
+        key = (self.weight._version, self.weight.data_ptr(), dtype)
+        if self._packed is None or self._packed_key != key:
+            self._packed = ops.pack_conv_weight(self.weight, dtype)
+            self._packed_key = key
+        return self._packed
+
+    def bias_f32(self):
+        return None if self.bias is None else self.bias.detach()
+
+    def forward(self, x: Tensor, residual: Tensor | None = None, out_dtype=None) -> Tensor:  # noqa: D102
+        x = ops.to_act(x, compute_dtype())
+        return ops.conv2d(x, self.packed_weight(x.dtype), self.bias_f32(), self.out_channels, self._mode,
+                          residual=residual, out_dtype=out_dtype)
+
+
+class Downsample(nn.Module):
+    """layers.py:25-37: zero pad right/bottom by one, 3x3 stride-2 conv.  The pad is never materialised: the four
+    stride-2 sub-lattices are separate TMA maps and the missing row/column is TMA out-of-bounds zero fill."""
+
+    def __init__(self, in_channels: int):
+        super().__init__()
+        self.conv = Conv2dSM100(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.conv(x)
+
+
+class Upsample(nn.Module):
+    """layers.py:40-50: nearest x2 then 3x3 conv."""
+
+    def __init__(self, in_channels: int):
+        super().__init__()
+        self.conv = Conv2dSM100(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
+
+    def forward(self, x: Tensor) -> Tensor:
+        x = ops.to_act(x, compute_dtype())
+        return self.conv(ops.upsample2x(x))
+
+
+class ResnetBlock(nn.Module):
+    """layers.py:53-114: GN -> SiLU -> conv3x3 -> GN -> SiLU -> conv3x3 (+ 1x1 shortcut) + x."""
+
+    def __init__(self, in_channels: int, out_channels: int, cond_dim: int = None):
+        super().__init__()
+        self.in_channels = in_channels
+        out_channels = in_channels if out_channels is None else out_channels
+        self.out_channels = out_channels
+        self.cond_dim = cond_dim
+        self.norm1 = GroupNormSM100(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+        self.conv1 = Conv2dSM100(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        if self.cond_dim is not None:  # AdaIN projection: parameters kept for checkpoint parity
+            self.emb_proj = nn.Linear(cond_dim, out_channels * 2)
+            nn.init.zeros_(self.emb_proj.bias)
+            self.emb_proj.weight.data.zero_()
+            self.emb_proj.bias.data[:out_channels] = 1.0
+        self.norm2 = GroupNormSM100(num_groups=32, num_channels=out_channels, eps=1e-6, affine=True)
+        self.conv2 = Conv2dSM100(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        if self.in_channels != self.out_channels:
+            self.nin_shortcut = Conv2dSM100(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
+
+    def forward(self, x: Tensor, emb: Tensor | None = None) -> Tensor:
+        if self.cond_dim is not None and emb is not None:
+            raise NotImplementedError("AdaIN-conditioned ResnetBlock (use_adain) is outside the built hot path")
+        x = ops.to_act(x, compute_dtype())
+        h = self.conv1(self.norm1(x, silu=True))
+        h = self.norm2(h, silu=True)
+        shortcut = self.nin_shortcut(x) if self.in_channels != self.out_channels else x
+        return self.conv2(h, residual=shortcut)  # residual add fused in the conv epilogue
+
+
+class AttnBlock(nn.Module):
+    """layers.py:117-142: GN -> q,k,v 1x1 -> softmax(q k^T / sqrt(C)) v (single head, d = C) -> proj 1x1 -> + x.
+
+    q, k and v come from ONE fused 1x1 implicit GEMM (Cout = 3C) and are consumed in place as channel slices; the
+    reference's three ``rearrange(...).contiguous()`` copies do not exist here (NHWC is already [L, C])."""
+
+    def __init__(self, in_channels: int):
+        super().__init__()
+        self.in_channels = in_channels
+        self.norm = GroupNormSM100(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+        self.q = Conv2dSM100(in_channels, in_channels, kernel_size=1)
+        self.k = Conv2dSM100(in_channels, in_channels, kernel_size=1)
+        self.v = Conv2dSM100(in_channels, in_channels, kernel_size=1)
+        self.proj_out = Conv2dSM100(in_channels, in_channels, kernel_size=1)
+        self._qkv = None
+        self._qkv_key = None
+
+    def _qkv_operands(self, dtype):
+        key = tuple((m.weight._version, m.weight.data_ptr(), m.bias._version) for m in (self.q, self.k, self.v)) + (dtype,)
+        if self._qkv is None or self._qkv_key != key:
+            w = torch.cat([m.packed_weight(dtype) for m in (self.q, self.k, self.v)], dim=0)
+            b = torch.cat([m.bias.detach() for m in (self.q, self.k, self.v)], dim=0).contiguous()
+            self._qkv, self._qkv_key = (w, b), key
+        return self._qkv
+
+    def forward(self, x: Tensor) -> Tensor:
+        x = ops.to_act(x, compute_dtype())
+        n, c, hh, ww = x.shape
+        if c % 16 != 0:
+            raise RuntimeError("AttnBlock: channel count must be a multiple of 16 on the sm_100a path")
+        L = hh * ww
+        h = self.norm(x, silu=False)
+        wqkv, bqkv = self._qkv_operands(x.dtype)
+        qkv = ops.conv2d(h, wqkv, bqkv, 3 * c, ops.CONV_1X1)  # NHWC [n, L, 3c]
+        flat = qkv.permute(0, 2, 3, 1).reshape(n, L, 3 * c)     # view: pixel-major rows, pitch 3c
+        q, k, v = flat[:, :, :c], flat[:, :, c:2 * c], flat[:, :, 2 * c:]
+        scores = ops.gemm_tn_batched(q, k, torch.float32, scale=1.0 / math.sqrt(c))  # [n, L, L] fp32
+        probs = ops.softmax_rows(scores, x.dtype)
+        vt = ops.transpose16(v)                                   # [n, c, L]
+        o = ops.gemm_tn_batched(probs, vt, x.dtype)               # [n, L, c]
+        o = o.view(n, hh, ww, c).permute(0, 3, 1, 2)
+        return self.proj_out(o, residual=x)

@@ -1,0 +1,293 @@
+"""Torch-tensor front end of the C ABI (include/eovae.h): allocation, stream and argument marshalling only.
+
+Activations are ordinary ``torch.Tensor`` objects of logical shape [N, C, H, W] stored channels-last (NHWC in
+memory) in a 16-bit dtype, so every module boundary stays a plain tensor while the kernels see pixel-major data.
+Nothing here computes: each function forwards to one hand-written sm_100a kernel and raises on failure.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _C
+from ._C import BF16, CONV_1X1, CONV_3X3, CONV_3X3_S2, F16, F32  # noqa: F401
+
+DT = {torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("eo_vae: tensors must live on a CUDA device - this path has no CPU implementation")
+
+
+def nhwc_empty(n: int, c: int, h: int, w: int, dtype, device) -> torch.Tensor:
+    """Uninitialised logical-NCHW tensor with NHWC storage."""
+    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def pix_stride(t: torch.Tensor) -> int:
+    """Elements between consecutive pixels of an NHWC-stored [N, C, H, W] view (channel slices allowed)."""
+    n, c, h, w = t.shape
+    ps = t.stride(3)
+    ok = (c == 1 or t.stride(1) == 1) and (h == 1 or t.stride(2) == w * ps) and (n == 1 or t.stride(0) == h * w * ps)
+    if not ok or ps < c:
+        raise RuntimeError(f"eo_vae: expected channels-last storage, got shape {tuple(t.shape)} strides {t.stride()}")
+    return ps
+
+
+def to_act(x: torch.Tensor, dtype) -> torch.Tensor:
+    """Bring an arbitrary [N, C, H, W] tensor to the internal activation form (edge use only)."""
+    _need_cuda(x)
+    if x.dtype == dtype and x.dim() == 4:
+        try:
+            pix_stride(x)
+            return x
+        except RuntimeError:
+            pass
+    return x.to(dtype=dtype, memory_format=torch.channels_last)
+
+
+# ------------------------------------------------------------------------------------------------ conv / gemm
+def conv_k_per_tap(cin: int) -> int:
+    return _C.lib().eovae_conv_k_per_tap(cin)
+
+
+def pack_conv_weight(w: torch.Tensor, dtype) -> torch.Tensor:
+    """OIHW fp32 -> K-major 16-bit [round_up(cout,16)][taps][k_per_tap] (derived cache, never persisted)."""
+    _need_cuda(w)
+    cout, cin, kh, kw = w.shape
+    wf = w.detach().to(torch.float32).contiguous()
+    rows = (cout + 15) // 16 * 16
+    out = torch.empty((rows, kh * kw, conv_k_per_tap(cin)), dtype=dtype, device=w.device)
+    _C.check(_C.lib().eovae_pack_conv_weight(_ptr(wf), _ptr(out), cout, cin, kh, kw, DT[dtype], _stream()),
+             "eovae_pack_conv_weight")
+    return out
+
+
+def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, residual=None, out_dtype=None,
+           scale: float = 1.0) -> torch.Tensor:
+    _need_cuda(x, w_packed, bias, residual)
+    n, cin, h, w = x.shape
+    ho, wo = (h, w) if mode != CONV_3X3_S2 else ((h - 2) // 2 + 1, (w - 2) // 2 + 1)
+    out_dtype = out_dtype or x.dtype
+    # pixel pitch padded to 16 channels so every row stays 16-byte aligned (e.g. a 12-band reconstruction)
+    out = nhwc_empty(n, (cout + 15) // 16 * 16, ho, wo, out_dtype, x.device)[:, :cout]
+    res_dt, res_ps = 0, 0
+    if residual is not None:
+        if tuple(residual.shape) != (n, cout, ho, wo):
+            raise RuntimeError("eo_vae.conv2d: residual shape mismatch")
+        res_dt, res_ps = DT[residual.dtype], pix_stride(residual)
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != cout):
+        raise RuntimeError("eo_vae.conv2d: bias must be fp32 [cout]")
+    rc = _C.lib().eovae_conv2d(_ptr(x), n, h, w, cin, pix_stride(x), mode, _ptr(w_packed), cout, _ptr(bias),
+                              _ptr(residual), res_dt, res_ps, _ptr(out), DT[out_dtype], pix_stride(out), DT[x.dtype],
+                              float(scale), _stream())
+    _C.check(rc, "eovae_conv2d")
+    return out
+
+
+def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 1.0) -> torch.Tensor:
+    """c[i] = scale * a[i] @ b[i].T ; a [B, M, K], b [B, N, K]; row pitches may exceed K (channel slices)."""
+    _need_cuda(a, b)
+    bsz, m, k = a.shape
+    n = b.shape[1]
+    if b.shape[0] != bsz or b.shape[2] != k or a.stride(2) != 1 or b.stride(2) != 1 or a.dtype != b.dtype:
+        raise RuntimeError("eo_vae.gemm_tn_batched: bad operand layout")
+    if a.stride(0) != m * a.stride(1):
+        raise RuntimeError("eo_vae.gemm_tn_batched: A batches must be contiguous")
+    c = torch.empty((bsz, m, n), dtype=out_dtype, device=a.device)
+    rc = _C.lib().eovae_gemm_tn_batched(_ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1), b.stride(0), _ptr(c),
+                                       DT[out_dtype], n, bsz, m, n, k, DT[a.dtype], float(scale), _stream())
+    _C.check(rc, "eovae_gemm_tn_batched")
+    return c
+
+
+# ------------------------------------------------------------------------------------------------ group norm
+def gn_stats(x: torch.Tensor, groups: int = 32, eps: float = 1e-6) -> torch.Tensor:
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x.device)
+    ws_bytes = _C.lib().eovae_gn_stats_workspace_bytes(n, h * w, c, groups)
+    ws = torch.empty((max(ws_bytes // 8, 1),), dtype=torch.float64, device=x.device)
+    rc = _C.lib().eovae_gn_stats(_ptr(x), DT[x.dtype], n, h * w, c, pix_stride(x), groups, float(eps), _ptr(stats),
+                                _ptr(ws), ws.numel() * 8, _stream())
+    _C.check(rc, "eovae_gn_stats")
+    return stats
+
+
+def gn_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool,
+             groups: int = 32, out_dtype=None) -> torch.Tensor:
+    _need_cuda(x, stats, gamma, beta)
+    n, c, h, w = x.shape
+    y = nhwc_empty(n, c, h, w, out_dtype or x.dtype, x.device)
+    rc = _C.lib().eovae_gn_apply(_ptr(x), DT[x.dtype], pix_stride(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(y),
+                                DT[y.dtype], pix_stride(y), n, h * w, c, groups, 1 if silu else 0, _stream())
+    _C.check(rc, "eovae_gn_apply")
+    return y
+
+
+def group_norm(x, gamma, beta, silu: bool, groups: int = 32, eps: float = 1e-6):
+    return gn_apply(x, gn_stats(x, groups, eps), gamma, beta, silu, groups)
+
+
+# ------------------------------------------------------------------------------------------------ edges
+def nchw_to_act(x: torch.Tensor, c_pad: int, dtype) -> torch.Tensor:
+    """fp32 NCHW image batch -> internal activation with channels zero-padded to c_pad."""
+    _need_cuda(x)
+    x = x.to(torch.float32).contiguous()
+    n, c, h, w = x.shape
+    out = nhwc_empty(n, c_pad, h, w, dtype, x.device)
+    _C.check(_C.lib().eovae_nchw_to_nhwc16(_ptr(x), _ptr(out), n, c, h, w, c_pad, DT[dtype], _stream()),
+             "eovae_nchw_to_nhwc16")
+    return out
+
+
+def act_to_nchw_f32(x: torch.Tensor, channels: int | None = None) -> torch.Tensor:
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    c = channels or c
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _C.check(_C.lib().eovae_nhwc_to_nchw_f32(_ptr(x), DT[x.dtype], pix_stride(x), _ptr(out), n, c, h, w, _stream()),
+             "eovae_nhwc_to_nchw_f32")
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    if pix_stride(x) != c:
+        raise RuntimeError("eo_vae.upsample2x: dense channels-last input required")
+    out = nhwc_empty(n, c, 2 * h, 2 * w, x.dtype, x.device)
+    _C.check(_C.lib().eovae_upsample2x(_ptr(x), _ptr(out), n, h, w, c, _stream()), "eovae_upsample2x")
+    return out
+
+
+def softmax_rows(s: torch.Tensor, out_dtype) -> torch.Tensor:
+    _need_cuda(s)
+    if not s.is_contiguous():
+        raise RuntimeError("eo_vae.softmax_rows: contiguous input required")
+    cols = s.shape[-1]
+    rows = s.numel() // cols
+    p = torch.empty(s.shape, dtype=out_dtype, device=s.device)
+    _C.check(_C.lib().eovae_softmax_rows(_ptr(s), DT[s.dtype], _ptr(p), DT[out_dtype], rows, cols, _stream()),
+             "eovae_softmax_rows")
+    return p
+
+
+def transpose16(x: torch.Tensor) -> torch.Tensor:
+    """[B, R, C] (row pitch may exceed C) 16-bit -> dense [B, C, R]."""
+    _need_cuda(x)
+    b, r, c = x.shape
+    if x.stride(2) != 1 or x.stride(0) != r * x.stride(1) or x.element_size() != 2:
+        raise RuntimeError("eo_vae.transpose16: bad layout")
+    out = torch.empty((b, c, r), dtype=x.dtype, device=x.device)
+    _C.check(_C.lib().eovae_transpose16(_ptr(x), x.stride(1), _ptr(out), b, r, c, _stream()), "eovae_transpose16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ latent glue
+def _strides4(t: torch.Tensor):
+    return (ctypes.c_longlong * 4)(*t.stride())
+
+
+def latent_norm(moments: torch.Tensor, running_mean, running_var, eps: float, zc: int) -> torch.Tensor:
+    """moments: fp32 logical [N, 2zc, H, W] (any strides) -> normalised spatial latent NCHW fp32 [N, zc, H, W]."""
+    _need_cuda(moments, running_mean, running_var)
+    n, c2, h, w = moments.shape
+    if moments.dtype != torch.float32 or c2 != 2 * zc:
+        raise RuntimeError("eo_vae.latent_norm: bad moments tensor")
+    z = torch.empty((n, zc, h, w), dtype=torch.float32, device=moments.device)
+    rc = _C.lib().eovae_latent_norm(_ptr(moments), _strides4(moments), _ptr(running_mean), _ptr(running_var), float(eps),
+                                   _ptr(z), n, h, w, zc, _stream())
+    _C.check(rc, "eovae_latent_norm")
+    return z
+
+
+def latent_denorm(z: torch.Tensor, running_mean, running_var, eps: float, dtype) -> torch.Tensor:
+    """normalised spatial latent NCHW fp32 -> inverse BN -> decoder input activation (NHWC 16-bit)."""
+    _need_cuda(z, running_mean, running_var)
+    z = z.to(torch.float32).contiguous()
+    n, zc, h, w = z.shape
+    out = nhwc_empty(n, zc, h, w, dtype, z.device)
+    rc = _C.lib().eovae_latent_denorm(_ptr(z), _ptr(running_mean), _ptr(running_var), float(eps), _ptr(out), DT[dtype], n,
+                                     h, w, zc, _stream())
+    _C.check(rc, "eovae_latent_denorm")
+    return out
+
+
+def kl_reparam(moments: torch.Tensor, eps, zc: int, want_z: bool = True):
+    """moments fp32 logical [N, 2zc, H, W] (any strides) -> (z NCHW fp32 or None, kl [N])."""
+    _need_cuda(moments, eps)
+    n, c2, h, w = moments.shape
+    if moments.dtype != torch.float32 or c2 != 2 * zc:
+        raise RuntimeError("eo_vae.kl_reparam: bad moments tensor")
+    z = torch.empty((n, zc, h, w), dtype=torch.float32, device=moments.device) if want_z else None
+    kl = torch.empty((n,), dtype=torch.float32, device=moments.device)
+    if eps is not None:
+        eps = eps.to(device=moments.device, dtype=torch.float32).contiguous()
+    rc = _C.lib().eovae_kl_reparam(_ptr(moments), _strides4(moments), _ptr(eps), _ptr(z), _ptr(kl), n, h, w, zc, _stream())
+    _C.check(rc, "eovae_kl_reparam")
+    return z, kl
+
+
+def l1_charbonnier(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-3):
+    """-> fp32 tensor [2] = (mean |a-b|, mean sqrt((a-b)^2 + eps^2))."""
+    _need_cuda(a, b)
+    a = a.to(torch.float32).contiguous()
+    b = b.to(torch.float32).contiguous()
+    out = torch.empty((2,), dtype=torch.float32, device=a.device)
+    ws = torch.empty((2,), dtype=torch.float64, device=a.device)
+    _C.check(_C.lib().eovae_l1_charbonnier(_ptr(a), _ptr(b), a.numel(), float(eps), _ptr(out), _ptr(ws), 16, _stream()),
+             "eovae_l1_charbonnier")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ hypernetwork
+def hypernet_forward(wvs: torch.Tensor, params: list, num_layers: int, d: int, heads: int, ff: int, embed: int,
+                     decoder: bool):
+    """-> (wk [C, 9*embed], bias_raw [embed] | [C]) fp32, unscaled (see eovae_hypernet_forward)."""
+    _need_cuda(wvs, *params)
+    wvs = wvs.to(torch.float32).contiguous()
+    c = wvs.numel()
+    lib = _C.lib()
+    ws_bytes = lib.eovae_hypernet_workspace_bytes(c, d, ff, embed)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=wvs.device)
+    wk = torch.empty((c, 9 * embed), dtype=torch.float32, device=wvs.device)
+    bias = torch.empty((c if decoder else embed,), dtype=torch.float32, device=wvs.device)
+    arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    rc = lib.eovae_hypernet_forward(_ptr(wvs), c, arr, num_layers, d, heads, ff, embed, 1 if decoder else 0, _ptr(wk),
+                                    _ptr(bias), _ptr(ws), ws_bytes, _stream())
+    _C.check(rc, "eovae_hypernet_forward")
+    return wk, bias
+
+
+def pack_dyn_weight(wk: torch.Tensor, bias_raw: torch.Tensor, c: int, embed: int, decoder: bool, scale: float,
+                    bias_scale: float, dtype, want_oihw: bool):
+    """generated kernel -> (igemm B operand, scaled bias, optional fp32 OIHW weight)."""
+    _need_cuda(wk, bias_raw)
+    rows, cin = (c, embed) if decoder else (embed, c)
+    rows_pad = (rows + 15) // 16 * 16
+    kpt = conv_k_per_tap(dyn_cin_pad(cin))
+    packed = torch.empty((rows_pad, 9, kpt), dtype=dtype, device=wk.device)
+    oihw = torch.empty((rows, cin, 3, 3), dtype=torch.float32, device=wk.device) if want_oihw else None
+    bias = torch.empty_like(bias_raw)
+    rc = _C.lib().eovae_pack_dyn_weight(_ptr(wk), c, embed, 1 if decoder else 0, float(scale), _ptr(packed), DT[dtype],
+                                       kpt, rows_pad, _ptr(oihw), _ptr(bias_raw), float(bias_scale), _ptr(bias),
+                                       bias.numel(), _stream())
+    _C.check(rc, "eovae_pack_dyn_weight")
+    return packed, bias, oihw
+
+
+def dyn_cin_pad(cin: int) -> int:
+    """channel padding of the NHWC operand of a dynamic conv (16 = one 32-byte TMA/UMMA K-chunk)."""
+    return (cin + 15) // 16 * 16

@@ -1,0 +1,127 @@
+/*
+ * eovae.h - C ABI of libeovae_sm100.so: the sm_100a (B200) kernels behind the EOFluxVAE hot path.
+ *
+ * The reference (nilsleh/eo-vae) is pure Python/PyTorch and has NO FFI of its own: its "operator API" for this
+ * path is the set of torch library calls made by the nn.Modules listed below.  Each entry point here replaces
+ * one of those call sites (paths relative to the reference root); the Python package eo-vae_b200/eo_vae binds
+ * them with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch caching allocator); nothing is retained
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*); no internal device sync
+ *   - return 0 on success, negative on error; eovae_last_error() returns a thread-local message
+ *   - activations are NHWC ("pixel-major"), 16-bit (EOVAE_BF16 / EOVAE_F16) unless stated; `*_pix_stride`
+ *     is the distance between consecutive pixels in ELEMENTS (>= channels) so ops can read or write a channel
+ *     slice of a wider tensor
+ *   - unsupported shapes / dtypes are errors: there is no CPU or library fallback
+ */
+#ifndef EOVAE_H_
+#define EOVAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EOVAE_ABI_VERSION 1
+
+/* dtype codes */
+#define EOVAE_DT_BF16 0
+#define EOVAE_DT_F16 1
+#define EOVAE_DT_F32 2
+
+/* conv modes */
+#define EOVAE_CONV_3X3 0    /* 3x3, stride 1, zero pad 1                  (nn.Conv2d, layers.py:64,81)            */
+#define EOVAE_CONV_1X1 1    /* 1x1                                        (layers.py:85,123-126; model.py:165,236) */
+#define EOVAE_CONV_3X3_S2 2 /* F.pad(0,1,0,1) + 3x3 stride 2 pad 0        (Downsample, layers.py:33-37)            */
+
+int eovae_version(void);
+const char* eovae_last_error(void);
+int eovae_num_sms(void);
+
+/* ---- weight packing (derived, non-persistent caches of the OIHW fp32 master parameters) -------------------- */
+/* channels per K-chunk (in bytes: 32/64/128) and padded channels per tap chosen for a given Cin */
+int eovae_conv_chunk_bytes(int cin);
+int eovae_conv_k_per_tap(int cin);
+/* OIHW fp32 [cout][cin][kh][kw] -> K-major 16-bit [round_up(cout,16)][kh*kw][k_per_tap(cin)], zero padded */
+int eovae_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, int kh, int kw, int dtype, void* stream);
+
+/* ---- tcgen05 implicit-GEMM convolution: replaces cuDNN conv2d at layers.py:64,81,85,123-126,33-37 and
+ *      model.py:162,165,236,260.   out = scale * conv(x, w) + bias + residual                                   */
+int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_stride, int mode, const void* w_packed,
+                 int cout, const float* bias, const void* residual, int res_dtype, long long res_pix_stride, void* out,
+                 int out_dtype, long long out_pix_stride, int act_dtype, float scale, void* stream);
+
+/* ---- batched C[b] = scale * A[b] (m x k) * B[b]^T (n x k): the q k^T and p v products of AttnBlock
+ *      (F.scaled_dot_product_attention, layers.py:134-141)                                                      */
+int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride, const void* b, long long ldb,
+                          long long b_batch_stride, void* c, int c_dtype, long long ldc, int batch, int m, int n, int k,
+                          int ab_dtype, float scale, void* stream);
+
+/* ---- GroupNorm(32, eps) statistics + normalise/affine(/SiLU): replaces ATen group_norm + x*sigmoid(x)
+ *      (layers.py:61,78,120; layers.py:21-22; model.py:159,193-194,295,349-350)
+ *      stats: float [n][groups][2] = (mean, rstd);  workspace: eovae_gn_stats_workspace_bytes(...) bytes.
+ *      Deterministic (fixed-order partial sums, no atomics).                                                    */
+size_t eovae_gn_stats_workspace_bytes(int n, long long hw, int c, int groups);
+int eovae_gn_stats(const void* x, int x_dtype, int n, long long hw, int c, long long pix_stride, int groups, float eps,
+                   float* stats, void* workspace, size_t workspace_bytes, void* stream);
+int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const float* stats, const float* gamma,
+                   const float* beta, void* y, int y_dtype, long long y_pix_stride, int n, long long hw, int c, int groups,
+                   int apply_silu, void* stream);
+
+/* ---- layout / edge kernels ----------------------------------------------------------------------------------- */
+/* NCHW fp32 image batch -> NHWC 16-bit with channels zero-padded to c_pad (input edge of DynamicConv) */
+int eovae_nchw_to_nhwc16(const float* x, void* out, int n, int c, int h, int w, int c_pad, int out_dtype, void* stream);
+/* NHWC (fp32 or 16-bit) -> NCHW fp32 (output edge: moments / reconstructions) */
+int eovae_nhwc_to_nchw_f32(const void* x, int x_dtype, long long x_pix_stride, float* out, int n, int c, int h, int w,
+                           void* stream);
+/* nearest-neighbour x2 upsample, NHWC 16-bit (F.interpolate, layers.py:48) */
+int eovae_upsample2x(const void* x, void* out, int n, int h, int w, int c, void* stream);
+/* row softmax: s [rows][cols] (fp32 or 16-bit) -> p 16-bit */
+int eovae_softmax_rows(const void* s, int s_dtype, void* p, int p_dtype, long long rows, int cols, void* stream);
+/* batched transpose of 16-bit matrices: in [batch][rows][in_ld>=cols] -> out [batch][cols][rows] */
+int eovae_transpose16(const void* in, long long in_ld, void* out, int batch, int rows, int cols, void* stream);
+
+/* ---- posterior + latent glue (distributions.py:20-67, new_autoencoder.py:466-469,533-543,730-738) ------------ */
+/* moments fp32, logical [n][2*zc][h][w] with HOST array mstrides[4] = element strides (n, c, y, x)
+ * -> z_norm NCHW fp32 [n][zc][h][w]:
+ *   pixel-unshuffle(2) -> BatchNorm2d(eval, running stats, eps) -> pixel-shuffle(2) collapses to a per
+ *   (channel, row parity, col parity) affine on the posterior mean                                               */
+int eovae_latent_norm(const float* moments, const long long* mstrides, const float* running_mean,
+                      const float* running_var, float eps, float* z, int n, int h, int w, int zc, void* stream);
+/* z (spatial, normalised) NCHW fp32 -> inverse BN (running stats, eps) -> NHWC 16-bit decoder input */
+int eovae_latent_denorm(const float* z, const float* running_mean, const float* running_var, float eps, void* out,
+                        int out_dtype, int n, int h, int w, int zc, void* stream);
+/* fused reparameterisation + KL: z = mean + exp(0.5*clamp(logvar)) * eps ; kl[n] = 0.5*sum(mean^2+var-1-logvar)
+ * moments fp32 with host strides as above; eps, z NCHW fp32 (eps NULL -> z = mean; z NULL -> KL only)          */
+int eovae_kl_reparam(const float* moments, const long long* mstrides, const float* eps, float* z, float* kl, int n,
+                     int h, int w, int zc, void* stream);
+
+/* ---- wavelength hypernetwork (dynamic_conv.py:37-59,110-130,162-183,352-366,499-525,666-697), all fp32 -------- */
+/* params: host array of device pointers: 0 omega[d/2] (sincos frequencies) | 1 weight_tokens | 2 bias_token |
+ *   3,4 fclayer.w1 (w,b) | 5,6 fclayer.w2 | 7,8 fc_weight | 9,10 fc_bias | then 12 per transformer layer:
+ *   in_proj (w,b), out_proj (w,b), linear1 (w,b), linear2 (w,b), norm1 (g,b), norm2 (g,b)
+ * wk_out  : [C][9*embed] raw fc_weight output (unscaled)
+ * bias_out: encoder [embed], decoder [C]  (raw fc_bias output, unscaled)
+ * workspace: eovae_hypernet_workspace_bytes(...) bytes                                                           */
+size_t eovae_hypernet_workspace_bytes(int c, int d, int ff, int embed);
+int eovae_hypernet_forward(const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads,
+                           int ff, int embed, int decoder, float* wk_out, float* bias_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* generated kernel -> igemm B operand (16-bit, K-major, zero padded), optional fp32 OIHW copy (both scaled by
+ * `scale`), and bias_out[i] = bias_raw[i] * bias_scale (nbias entries)                                          */
+int eovae_pack_dyn_weight(const float* wk, int c, int embed, int decoder, float scale, void* packed, int dtype,
+                          int k_per_tap, int rows_pad, float* oihw_out, const float* bias_raw, float bias_scale,
+                          float* bias_out, int nbias, void* stream);
+
+/* ---- losses (consistency_loss.py:12-21,418; 24-37 via torchmetrics MS-SSIM) ---------------------------------- */
+/* out[0] = mean |a-b| , out[1] = mean sqrt((a-b)^2 + eps^2); a, b fp32, any layout (elementwise) */
+int eovae_l1_charbonnier(const float* a, const float* b, long long count, float eps, float* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EOVAE_H_ */

@@ -1,0 +1,192 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point against a plain PyTorch fp32 statement of the same op
+on the same (already 16-bit-rounded) operands, so the tolerances only cover accumulation order and the output
+rounding.  Everything goes through eo_vae.ops -> ctypes -> libeovae_sm100.so."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))
+
+
+def _act(n, c, h, w, dev, dtype=torch.bfloat16, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn((n, c, h, w), generator=g).to(dev)
+    return x.to(dtype=dtype, memory_format=torch.channels_last)
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout
+    (2, 32, 32, 64, 64),
+    (1, 64, 64, 128, 128),
+    (2, 16, 16, 512, 512),
+    (1, 256, 256, 128, 128),
+    (3, 24, 24, 32, 64),     # 64-byte K chunks
+    (2, 8, 8, 16, 32),       # 32-byte K chunks, several images per tile
+    (1, 48, 40, 64, 256),    # ragged tiles
+    (2, 32, 32, 256, 512),
+    (5, 4, 4, 64, 16),       # tiny maps, Cout 16
+    (2, 16, 16, 8, 32),      # Cin below one K chunk (TMA channel OOB fill)
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_CASES)
+@pytest.mark.parametrize("mode", ["3x3", "1x1", "s2"])
+def test_conv2d(cuda, n, h, w, cin, cout, mode):
+    from eo_vae import ops
+    torch.manual_seed(1)
+    x = _act(n, cin, h, w, cuda, seed=n * 7 + h)
+    k = 1 if mode == "1x1" else 3
+    wgt = (torch.randn(cout, cin, k, k) / math.sqrt(cin * k * k)).to(cuda)
+    bias = torch.randn(cout).to(cuda)
+    wp = ops.pack_conv_weight(wgt, torch.bfloat16)
+    m = {"3x3": ops.CONV_3X3, "1x1": ops.CONV_1X1, "s2": ops.CONV_3X3_S2}[mode]
+    w16 = wgt.bfloat16().float()
+    xf = x.float()
+    if mode == "3x3":
+        ref = F.conv2d(xf, w16, bias, padding=1)
+    elif mode == "1x1":
+        ref = F.conv2d(xf, w16, bias)
+    else:
+        ref = F.conv2d(F.pad(xf, (0, 1, 0, 1)), w16, bias, stride=2)
+    out = ops.conv2d(x, wp, bias, cout, m, out_dtype=torch.float32)
+    assert out.shape == ref.shape
+    assert _rel(out, ref) < 2e-5, f"fp32-out conv mismatch {_rel(out, ref)}"
+    # fused residual + 16-bit output
+    res = _act(*ref.shape[:2], *ref.shape[2:], cuda, seed=99).contiguous(memory_format=torch.channels_last)
+    out2 = ops.conv2d(x, wp, bias, cout, m, residual=res)
+    assert out2.dtype == torch.bfloat16
+    assert _rel(out2, ref + res.float()) < 4e-3
+
+
+def test_conv2d_fp16_operands(cuda):
+    from eo_vae import ops
+    x = _act(2, 64, 16, 16, cuda, dtype=torch.float16)
+    wgt = (torch.randn(64, 64, 3, 3) / 24).to(cuda)
+    wp = ops.pack_conv_weight(wgt, torch.float16)
+    out = ops.conv2d(x, wp, None, 64, ops.CONV_3X3, out_dtype=torch.float32)
+    ref = F.conv2d(x.float(), wgt.half().float(), None, padding=1)
+    assert _rel(out, ref) < 2e-5
+
+
+def test_conv2d_channel_slices(cuda):
+    """A conv may read a channel slice of a wider NHWC tensor and write into one."""
+    from eo_vae import ops
+    big = _act(2, 192, 16, 16, cuda)
+    x = big[:, 64:128]
+    wgt = (torch.randn(32, 64, 1, 1) / 8).to(cuda)
+    wp = ops.pack_conv_weight(wgt, torch.bfloat16)
+    out = ops.conv2d(x, wp, None, 32, ops.CONV_1X1, out_dtype=torch.float32)
+    ref = F.conv2d(x.float(), wgt.bfloat16().float())
+    assert _rel(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("b,m,n,k", [(2, 256, 256, 64), (3, 1024, 1024, 512), (1, 100, 72, 32), (4, 64, 512, 1024)])
+def test_gemm_tn_batched(cuda, b, m, n, k):
+    from eo_vae import ops
+    torch.manual_seed(2)
+    a = torch.randn(b, m, k, device=cuda).bfloat16()
+    bb = torch.randn(b, n, k, device=cuda).bfloat16()
+    c = ops.gemm_tn_batched(a, bb, torch.float32, scale=0.125)
+    ref = 0.125 * torch.einsum("bmk,bnk->bmn", a.float(), bb.float())
+    assert _rel(c, ref) < 2e-5
+
+
+@pytest.mark.parametrize("n,c,h,w", [(2, 128, 32, 32), (3, 512, 8, 8), (1, 256, 64, 64), (2, 32, 16, 16), (2, 64, 12, 20)])
+def test_group_norm(cuda, n, c, h, w):
+    from eo_vae import ops
+    x = _act(n, c, h, w, cuda, seed=5) * 3 + 1.5
+    gamma = (1 + 0.1 * torch.randn(c)).to(cuda)
+    beta = (0.1 * torch.randn(c)).to(cuda)
+    stats = ops.gn_stats(x)
+    xf = x.float().reshape(n, 32, -1)
+    assert torch.allclose(stats[..., 0], xf.mean(-1), atol=1e-4)
+    assert torch.allclose(stats[..., 1], 1 / torch.sqrt(xf.var(-1, unbiased=False) + 1e-6), rtol=1e-4)
+    for silu in (False, True):
+        y = ops.gn_apply(x, stats, gamma, beta, silu)
+        ref = F.group_norm(x.float(), 32, gamma, beta, eps=1e-6)
+        if silu:
+            ref = ref * torch.sigmoid(ref)
+        assert _rel(y, ref) < 4e-3
+
+
+def test_softmax_transpose_upsample(cuda):
+    from eo_vae import ops
+    s = torch.randn(3, 200, 1024, device=cuda) * 4
+    p = ops.softmax_rows(s, torch.bfloat16)
+    assert _rel(p, torch.softmax(s, -1)) < 4e-3
+    s2 = torch.randn(2, 8, 5000, device=cuda)
+    assert _rel(ops.softmax_rows(s2, torch.bfloat16), torch.softmax(s2, -1)) < 4e-3
+    t = torch.randn(3, 70, 96 * 3, device=cuda).bfloat16()
+    v = t[:, :, 96:192]
+    assert torch.equal(ops.transpose16(v), v.transpose(1, 2).contiguous())
+    x = _act(2, 64, 6, 10, cuda)
+    up = ops.upsample2x(x)
+    assert torch.equal(up, F.interpolate(x.float(), scale_factor=2.0, mode="nearest").to(x.dtype))
+
+
+def test_layout_edges(cuda):
+    from eo_vae import ops
+    x = torch.randn(3, 12, 20, 28, device=cuda)
+    a = ops.nchw_to_act(x, 16, torch.bfloat16)
+    assert a.shape == (3, 16, 20, 28)
+    assert torch.equal(a[:, :12].float(), x.bfloat16().float())
+    assert float(a[:, 12:].abs().max()) == 0.0
+    back = ops.act_to_nchw_f32(a, 12)
+    assert back.is_contiguous() and torch.equal(back, x.bfloat16().float())
+
+
+def test_latent_glue(cuda):
+    from eo_vae import ops
+    from oracle import eovae_oracle as O
+    n, zc, h, w = 3, 8, 6, 10
+    moments = torch.randn(n, 2 * zc, h, w, device=cuda)
+    moments_cl = moments.contiguous(memory_format=torch.channels_last)
+    sd = {"bn.running_mean": torch.randn(4 * zc), "bn.running_var": torch.rand(4 * zc) + 0.5}
+    rm, rv = sd["bn.running_mean"].to(cuda), sd["bn.running_var"].to(cuda)
+    ref = O.pixel_shuffle2(O.bn_eval(sd, O.pixel_unshuffle2(moments.cpu()[:, :zc])))
+    for mom in (moments, moments_cl):
+        z = ops.latent_norm(mom, rm, rv, 1e-5, zc)
+        assert torch.allclose(z.cpu(), ref, atol=1e-5, rtol=1e-5)
+    eps = torch.randn(n, zc, h, w)
+    zs, kl = ops.kl_reparam(moments_cl, eps.to(cuda), zc)
+    assert torch.allclose(zs.cpu(), O.posterior_sample(moments.cpu(), eps), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(kl.cpu(), O.posterior_kl(moments.cpu()), rtol=1e-5)
+    zn = torch.randn(n, zc, h, w, device=cuda)
+    d = ops.latent_denorm(zn, rm, rv, 1e-4, torch.bfloat16)
+    ref_d = O.pixel_shuffle2(O.bn_inverse(sd, O.pixel_unshuffle2(zn.cpu())))
+    assert _rel(d.cpu(), ref_d) < 4e-3
+
+
+def test_pixel_losses(cuda):
+    from eo_vae import ops
+    a = torch.randn(2, 12, 33, 47, device=cuda)
+    b = torch.randn(2, 12, 33, 47, device=cuda)
+    out = ops.l1_charbonnier(a, b, 1e-3).cpu()
+    assert abs(float(out[0]) - float((a - b).abs().mean())) < 1e-5
+    assert abs(float(out[1]) - float(torch.sqrt((a - b) ** 2 + 1e-6).mean())) < 1e-5
+
+
+@pytest.mark.parametrize("modality", ["S2RGB", "S1RTC", "S2L2A", "S2L1C"])
+@pytest.mark.parametrize("cfg_name", ["tiny", "full"])
+def test_hypernet(cuda, modality, cfg_name):
+    """Generated conv kernels vs the CPU oracle (fp32 both sides)."""
+    import __graft_entry__ as g
+    from oracle import eovae_oracle as O
+    from oracle.weights import FULL_CONFIG, TINY_CONFIG, WAVELENGTHS, make_state_dict
+    cfg = TINY_CONFIG if cfg_name == "tiny" else FULL_CONFIG
+    sd = make_state_dict(cfg, 1)
+    model = g._model(cfg, sd, cuda)
+    wvs = torch.tensor(WAVELENGTHS[modality])
+    w_ref, b_ref = O.hypernet(sd, "encoder.conv_in", wvs, False, cfg["hyper_heads"])
+    w, b = model.encoder.conv_in.get_distillation_weight(wvs.to(cuda))
+    assert _rel(w.cpu(), w_ref) < 2e-4 and _rel(b.cpu(), b_ref) < 2e-4
+    w_ref, b_ref = O.hypernet(sd, "decoder.conv_out", wvs, True, cfg["hyper_heads"])
+    w, b = model.decoder.conv_out.get_distillation_weight(wvs.to(cuda))
+    assert _rel(w.cpu(), w_ref) < 2e-4
+    assert _rel(b.cpu(), b_ref * 10.0) < 2e-4  # get_distillation_weight scales the bias once (x0.1), forward twice

@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Headline benchmark: EOFluxVAE.encode_spatial_normalized on synthetic S2L2A 12-band 256x256 patches
+(BASELINE.json configs[1]: batch 64 per GPU, bf16 operands, -> 32x32x32 latents), patches/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch (hypernetwork included - nothing is cached across steps).
+* value   : device-resident inputs, CUDA events on the launching stream, max over ranks
+* e2e     : the same call with HOST (pinned) inputs and a host copy of the latents, H2D/D2H inside the timed region
+* roofline: the tcgen05 implicit-GEMM family (all conv / attention-GEMM launches of a step), algorithmic FLOPs
+            (2*MACs of the reference formulation) / summed CUDA-event launch durations
+* cpu_baseline / --impl reference: the CPU oracle port of the reference path on the box's host cores (bounded sample)
+Multi-GPU: patches are independent, each rank encodes its own batch, no data-path collective ("weak" scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "eo-vae_b200"))
+
+BATCH = 64
+BANDS, SIZE = 12, 256
+GF_PER_PATCH_ENCODE = 274.62  # SURVEY.md section 8d (algorithmic, 2*MACs), + ~1.5 GF hypernet per call
+METRIC = "S2L2A 256x256 patches/sec (EOFluxVAE encode_spatial_normalized)"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tensor=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), hbm=float(p["hbm_gbs"]),
+                    source="MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)")
+    return dict(tensor=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md: ~1.4 PF sustained, 6.65 TB/s)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples taken DURING the timed region."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []  # upper half = samples under load
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_throughput(target_seconds: float = 15.0):
+    """Reference path (CPU oracle port, fp32, all host threads) on a bounded sample of the same workload."""
+    import torch
+    from oracle import eovae_oracle as O
+    from oracle.weights import FULL_CONFIG, WAVELENGTHS, make_state_dict, synthetic_patches
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_state_dict(FULL_CONFIG, 0)
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"])
+    with torch.no_grad():
+        x1 = synthetic_patches(1, BANDS, SIZE, seed=11)
+        O.encode_spatial_normalized(sd, x1, wvs)  # warm-up (thread pools, allocator)
+        t0 = time.perf_counter()
+        O.encode_spatial_normalized(sd, x1, wvs)
+        one = time.perf_counter() - t0
+        n = int(max(2, min(16, target_seconds / max(one, 1e-3))))
+        x = synthetic_patches(n, BANDS, SIZE, seed=12)
+        t0 = time.perf_counter()
+        O.encode_spatial_normalized(sd, x, wvs)
+        dt = time.perf_counter() - t0
+    return n / dt, cores, f"{n} patches of 12x256x256 in one batch, fp32, torch {torch.__version__} CPU, 1 warm-up"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    times, sample, cores = [], "", 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        v, cores, sample = cpu_reference_throughput(target_seconds=6.0)
+        if i >= args.warmup:
+            times.append(v)
+    v = statistics.mean(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "EOFluxVAE.encode_spatial_normalized S2L2A 12x256x256 (bounded CPU sample per step)"},
+        "cpu_baseline": {"value": v, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+    from oracle.weights import FULL_CONFIG, WAVELENGTHS, make_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if not os.path.exists(g.LIB):
+        raise RuntimeError("libeovae_sm100.so missing - run __graft_entry__.build() first")
+    import eo_vae
+    from eo_vae import ops
+    eo_vae.set_compute_dtype(torch.bfloat16)
+
+    model = g._model(FULL_CONFIG, make_state_dict(FULL_CONFIG, 0), dev)
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"], dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x_dev = torch.randn((BATCH, BANDS, SIZE, SIZE), generator=gen, device=dev).clamp_(-2.0, 6.0)  # 201 MB > 126 MB L2
+    x_host = x_dev.cpu().pin_memory()
+    z_host = torch.empty((BATCH, 32, SIZE // 8, SIZE // 8), dtype=torch.float32).pin_memory()
+
+    def step_device():
+        return model.encode_spatial_normalized(x_dev, wvs)
+
+    def step_e2e():
+        z = model.encode_spatial_normalized(x_host.to(dev, non_blocking=True), wvs)
+        z_host.copy_(z, non_blocking=True)
+        return z
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = ops.launch_count()
+        ms_total = timed(step_device, args.steps)
+        launches = ops.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+
+        # --- kernel-family timing for the roofline (same process, after the headline loop; events per launch)
+        roof = None
+        if rank == 0:
+            ops.PROFILE = []
+            for _ in range(min(args.steps, 5)):
+                step_device()
+            torch.cuda.synchronize()
+            fam = {}
+            for family, flops, s, e in ops.PROFILE:
+                t, f, c = fam.get(family, (0.0, 0.0, 0))
+                fam[family] = (t + s.elapsed_time(e), f + flops, c + 1)
+            ops.PROFILE = None
+            peaks = load_peaks()
+            t_ms = sum(v[0] for v in fam.values())
+            flops = sum(v[1] for v in fam.values())
+            n_launch = sum(v[2] for v in fam.values())
+            achieved = flops / (t_ms * 1e-3) / 1e12
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "igemm_traffic.json")
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            roof = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM: all conv + attention GEMM launches)",
+                    "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
+                    "traffic": traffic, "peak_source": peaks["source"],
+                    "avg_launch_ms": t_ms / n_launch, "launches_per_step": n_launch / min(args.steps, 5),
+                    "algorithmic_gflop_per_launch": flops / n_launch / 1e9,
+                    "share_of_step": (t_ms / min(args.steps, 5)) / (ms_total / args.steps)}
+
+    if rank == 0:
+        patches = BATCH * world * args.steps
+        value = patches / (ms_total * 1e-3)
+        e2e_v = patches / (ms_e2e * 1e-3)
+        cpu_v, cores, sample = (None, None, None)
+        if world == 1:
+            cpu_v, cores, sample = cpu_reference_throughput()
+        line = {
+            "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "EOFluxVAE.encode_spatial_normalized, S2L2A 12x256x256, batch 64 per GPU, "
+                                   "random-init reference architecture (ch128, mult 1-2-4-4, z32), -> 32x32x32 latents",
+                       "batch_per_gpu": BATCH, "parallelism": f"dp{world} (patches sharded by rank, no collective)",
+                       "l2": "inputs (201 MB/step) and every level-0/1 activation exceed the 126 MB L2"},
+            "tensor_tflops": value * (GF_PER_PATCH_ENCODE / 1000.0),
+            "e2e": {"value": e2e_v, "unit": "patches/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": z_host.numel() * 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        }
+        if cpu_v is not None:
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,7 @@
 namespace eovae {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+extern unsigned long long g_launches;
 }  // namespace eovae
 
 #define EOVAE_CHECK(cond, ...)            \
@@ -28,7 +29,12 @@ int check_cuda(cudaError_t e, const char* what);
     if (eovae::check_cuda((call), #call) != 0) return -2; \
   } while (0)
 
-#define EOVAE_LAUNCH_CHECK() EOVAE_CUDA(cudaGetLastError())
+// every kernel launch goes through this macro: it also feeds eovae_launch_count() (bench.py "gpu_launches")
+#define EOVAE_LAUNCH_CHECK()              \
+  do {                                    \
+    ++eovae::g_launches;                  \
+    EOVAE_CUDA(cudaGetLastError());       \
+  } while (0)
 
 // dtype codes used across the C-ABI
 enum : int { EOVAE_BF16 = 0, EOVAE_F16 = 1, EOVAE_F32 = 2 };  // == EOVAE_DT_* in include/eovae.h

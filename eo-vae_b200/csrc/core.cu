@@ -4,6 +4,7 @@
 
 namespace eovae {
 static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -80,6 +81,7 @@ extern "C" {
 
 int eovae_version(void) { return EOVAE_ABI_VERSION; }
 const char* eovae_last_error(void) { return eovae::g_err; }
+unsigned long long eovae_launch_count(void) { return eovae::g_launches; }
 
 int eovae_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, int kh, int kw, int dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -134,13 +134,14 @@ int gn_block_threads(int c) {
   return t < vpp ? 0 : t;
 }
 
-void gn_grid(int n, long long hw, int rows, int* bpi, int* ppb) {
-  long long want = (4LL * eovae_num_sms() + n - 1) / n;  // ~4 waves of blocks over the whole batch
-  long long max_b = (hw + rows - 1) / rows;               // at least one pixel row-set per block
-  if (want > max_b) want = max_b;
-  if (want < 1) want = 1;
-  long long per = (hw + want - 1) / want;
+// Pixel partition of one image: depends on (hw, c) only - never on the batch size - so that a patch's statistics
+// (hence its latents) are bit-identical whatever batch it is encoded in.
+void gn_grid(int n, long long hw, int c, int rows, int* bpi, int* ppb) {
+  (void)n;
+  long long per = 32768 / c;  // ~64 KB of 16-bit data per block
+  if (per < rows) per = rows;
   per = (per + rows - 1) / rows * rows;
+  if (per > hw) per = (hw + rows - 1) / rows * rows;
   *ppb = static_cast<int>(per);
   *bpi = static_cast<int>((hw + per - 1) / per);
 }
@@ -388,7 +389,7 @@ size_t eovae_gn_stats_workspace_bytes(int n, long long hw, int c, int groups) {
   const int threads = gn_block_threads(c);
   if (threads <= 0) return 0;
   int bpi, ppb;
-  gn_grid(n, hw, threads / (c / 8), &bpi, &ppb);
+  gn_grid(n, hw, c, threads / (c / 8), &bpi, &ppb);
   return sizeof(double) * 2 * static_cast<size_t>(n) * bpi * groups;
 }
 
@@ -403,7 +404,7 @@ int eovae_gn_stats(const void* x, int x_dtype, int n, long long hw, int c, long 
   EOVAE_CHECK(workspace_bytes >= eovae_gn_stats_workspace_bytes(n, hw, c, groups), "gn_stats: workspace too small");
   const int rows = threads / (c / 8);
   int bpi, ppb;
-  gn_grid(n, hw, rows, &bpi, &ppb);
+  gn_grid(n, hw, c, rows, &bpi, &ppb);
   double* ws = static_cast<double*>(workspace);
   dim3 grid(bpi, n);
   const size_t smem = sizeof(float) * 2 * c * rows;
@@ -429,7 +430,7 @@ int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const flo
   const int threads = gn_block_threads(c);
   EOVAE_CHECK(threads > 0, "gn_apply: C too large (%d)", c);
   int bpi, ppb;
-  gn_grid(n, hw, threads / (c / 8), &bpi, &ppb);
+  gn_grid(n, hw, c, threads / (c / 8), &bpi, &ppb);
   dim3 grid(bpi, n);
 #define EOVAE_GN_APPLY(TI, TO, S)                                                                                        \
   gn_apply_kernel<TI, TO, S><<<grid, threads, 0, stream>>>(static_cast<const TI*>(x), x_pix_stride, stats, gamma, beta, \

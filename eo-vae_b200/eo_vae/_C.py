@@ -21,6 +21,7 @@ SIGNATURES = {
     "eovae_version": (_i, []),
     "eovae_last_error": (C.c_char_p, []),
     "eovae_num_sms": (_i, []),
+    "eovae_launch_count": (C.c_ulonglong, []),
     "eovae_conv_chunk_bytes": (_i, [_i]),
     "eovae_conv_k_per_tap": (_i, [_i]),
     "eovae_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

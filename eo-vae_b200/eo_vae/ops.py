@@ -16,6 +16,26 @@ from ._C import BF16, CONV_1X1, CONV_3X3, CONV_3X3_S2, F16, F32  # noqa: F401
 DT = {torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32}
 
 
+# bench.py sets this to a list to collect (family, algorithmic flops, start event, end event) per tensor-core launch
+PROFILE = None
+
+
+def _timed(family: str, flops: float, call):
+    if PROFILE is None:
+        return call()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    rc = call()
+    end.record()
+    PROFILE.append((family, flops, start, end))
+    return rc
+
+
+def launch_count() -> int:
+    """Kernels launched so far by libeovae_sm100.so in this process."""
+    return int(_C.lib().eovae_launch_count())
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -75,7 +95,7 @@ def pack_conv_weight(w: torch.Tensor, dtype) -> torch.Tensor:
 
 
 def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, residual=None, out_dtype=None,
-           scale: float = 1.0) -> torch.Tensor:
+           scale: float = 1.0, algo_cin: int | None = None) -> torch.Tensor:
     _need_cuda(x, w_packed, bias, residual)
     n, cin, h, w = x.shape
     ho, wo = (h, w) if mode != CONV_3X3_S2 else ((h - 2) // 2 + 1, (w - 2) // 2 + 1)
@@ -89,9 +109,10 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, 
         res_dt, res_ps = DT[residual.dtype], pix_stride(residual)
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != cout):
         raise RuntimeError("eo_vae.conv2d: bias must be fp32 [cout]")
-    rc = _C.lib().eovae_conv2d(_ptr(x), n, h, w, cin, pix_stride(x), mode, _ptr(w_packed), cout, _ptr(bias),
-                              _ptr(residual), res_dt, res_ps, _ptr(out), DT[out_dtype], pix_stride(out), DT[x.dtype],
-                              float(scale), _stream())
+    flops = 2.0 * n * ho * wo * cout * (algo_cin or cin) * (1 if mode == CONV_1X1 else 9)
+    rc = _timed("conv", flops, lambda: _C.lib().eovae_conv2d(
+        _ptr(x), n, h, w, cin, pix_stride(x), mode, _ptr(w_packed), cout, _ptr(bias), _ptr(residual), res_dt, res_ps,
+        _ptr(out), DT[out_dtype], pix_stride(out), DT[x.dtype], float(scale), _stream()))
     _C.check(rc, "eovae_conv2d")
     return out
 
@@ -106,8 +127,9 @@ def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 
     if a.stride(0) != m * a.stride(1):
         raise RuntimeError("eo_vae.gemm_tn_batched: A batches must be contiguous")
     c = torch.empty((bsz, m, n), dtype=out_dtype, device=a.device)
-    rc = _C.lib().eovae_gemm_tn_batched(_ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1), b.stride(0), _ptr(c),
-                                       DT[out_dtype], n, bsz, m, n, k, DT[a.dtype], float(scale), _stream())
+    rc = _timed("attn_gemm", 2.0 * bsz * m * n * k, lambda: _C.lib().eovae_gemm_tn_batched(
+        _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1), b.stride(0), _ptr(c), DT[out_dtype], n, bsz, m, n, k,
+        DT[a.dtype], float(scale), _stream()))
     _C.check(rc, "eovae_gemm_tn_batched")
     return c
 

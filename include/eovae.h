@@ -40,6 +40,8 @@ extern "C" {
 int eovae_version(void);
 const char* eovae_last_error(void);
 int eovae_num_sms(void);
+/* number of kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
+unsigned long long eovae_launch_count(void);
 
 /* ---- weight packing (derived, non-persistent caches of the OIHW fp32 master parameters) -------------------- */
 /* channels per K-chunk (in bytes: 32/64/128) and padded channels per tap chosen for a given Cin */

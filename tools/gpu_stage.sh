@@ -6,10 +6,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --for
 rc=0
 for t in "$@"; do
   name=$(echo "$t" | tr '/:[]' '____')
-  timeout 900 python -m pytest "$t" -m gpu -q -x --no-header -p no:cacheprovider > "gpurun_out/stage_${name}.log" 2>&1
+  timeout 900 python -m pytest "$t" -m gpu -q --no-header -rA -p no:cacheprovider > "gpurun_out/stage_${name}.log" 2>&1
   r=$?
   echo "stage $t rc=$r"
-  tail -n 25 "gpurun_out/stage_${name}.log"
+  grep -E "PARITY|passed|failed|Error" "gpurun_out/stage_${name}.log" | tail -n 40
   [ $r -ne 0 ] && rc=$r
 done
 exit $rc

@@ -96,6 +96,37 @@ int pick_block_n(int cout_pad) {
   return 16;
 }
 
+// stats[n][g] = (mean, rstd) from the per-tile partial sums written by the igemm epilogue; one warp per (n, g),
+// fixed summation order (deterministic).
+__global__ void gn_tiles_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int pairs, int groups,
+                                         int slots_per_img, double count, float eps) {
+  const int pair = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pair >= pairs) return;
+  const int n = pair / groups, g = pair % groups;
+  const float* base = partial + (static_cast<long long>(n) * slots_per_img * groups + g) * 2;
+  double s = 0.0, q = 0.0;
+  for (int t = lane; t < slots_per_img; t += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(base + static_cast<long long>(t) * groups * 2);
+    s += v.x;
+    q += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * pair] = static_cast<float>(mean);
+    stats[2 * pair + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+void m_tiling(int n, int ho, int wo, bool batched, int* bw, int* bh, int* bn);
+
 struct ASpec {       // activation-side operand: NHWC tensor view
   const void* ptr;
   int N, H, W, C;    // logical extent (C = channels visible to the contraction)
@@ -105,7 +136,8 @@ struct ASpec {       // activation-side operand: NHWC tensor view
 int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chunk_bytes, int cout, long long w_rows,
                  long long w_row_stride, long long w_batch_stride, int w_batches, const float* bias, const void* res, int res_dtype,
                  long long res_pix_stride, void* out, int out_dtype, long long out_pix_stride, int act_dtype,
-                 float scale, cudaStream_t stream) {
+                 float scale, cudaStream_t stream, float* gn_stats = nullptr, int gn_groups = 0, float gn_eps = 0.f,
+                 void* gn_ws = nullptr, size_t gn_ws_bytes = 0) {
   EOVAE_CHECK(act_dtype == EOVAE_BF16 || act_dtype == EOVAE_F16, "igemm: operand dtype must be bf16/f16");
   EOVAE_CHECK(chunk_bytes == 32 || chunk_bytes == 64 || chunk_bytes == 128, "igemm: bad chunk bytes %d", chunk_bytes);
   EOVAE_CHECK(a.pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ptr) % 16) == 0,
@@ -126,13 +158,7 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     Wo = (a.W - 2) / 2 + 1;
   }
   // --- M tile = one TMA box of pixels
-  p.box_w = Wo < 128 ? Wo : 128;
-  p.box_h = 128 / p.box_w;
-  if (p.box_h > Ho) p.box_h = Ho;
-  p.box_n = 128 / (p.box_w * p.box_h);
-  if (p.box_n > a.N) p.box_n = a.N;
-  if (w_batches > 1) p.box_n = 1;
-  if (p.box_n < 1) p.box_n = 1;
+  m_tiling(a.N, Ho, Wo, w_batches > 1, &p.box_w, &p.box_h, &p.box_n);
   p.tiles_w = ceil_div(Wo, p.box_w);
   p.tiles_h = ceil_div(Ho, p.box_h);
   p.tiles_n = ceil_div(a.N, p.box_n);
@@ -207,11 +233,39 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   }
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   if (total_tiles == 0) return 0;
-  switch (chunk_bytes) {
-    case 128: return launch_n<128>(block_n, p, total_tiles, stream);
-    case 64: return launch_n<64>(block_n, p, total_tiles, stream);
-    default: return launch_n<32>(block_n, p, total_tiles, stream);
+  if (gn_stats != nullptr) {
+    EOVAE_CHECK(p.box_n == 1 && cout % 32 == 0 && gn_groups > 0 && cout % gn_groups == 0 && 32 % (cout / gn_groups) == 0 &&
+                    block_n >= 32,
+                "igemm: fused GroupNorm statistics unsupported for this shape (query eovae_conv2d_gn_workspace_bytes)");
+    const size_t need = sizeof(float) * 2 * 4 * static_cast<size_t>(p.tiles_w) * p.tiles_h * p.tiles_n * gn_groups;
+    EOVAE_CHECK(gn_ws != nullptr && gn_ws_bytes >= need, "igemm: GroupNorm workspace too small");
+    p.gn_partial = static_cast<float*>(gn_ws);
+    p.gn_groups = gn_groups;
+    p.gn_cpg = cout / gn_groups;
   }
+  int rc;
+  switch (chunk_bytes) {
+    case 128: rc = launch_n<128>(block_n, p, total_tiles, stream); break;
+    case 64: rc = launch_n<64>(block_n, p, total_tiles, stream); break;
+    default: rc = launch_n<32>(block_n, p, total_tiles, stream); break;
+  }
+  if (rc != 0 || gn_stats == nullptr) return rc;
+  const int pairs = p.Nimg * gn_groups;
+  gn_tiles_finalize_kernel<<<ceil_div(pairs, 4), 128, 0, stream>>>(p.gn_partial, gn_stats, pairs, gn_groups,
+                                                                   p.tiles_w * p.tiles_h * 4,
+                                                                   static_cast<double>(Ho) * Wo * p.gn_cpg, gn_eps);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// shape rule shared by launch_igemm and the workspace query
+void m_tiling(int n, int ho, int wo, bool batched, int* bw, int* bh, int* bn) {
+  *bw = wo < 128 ? wo : 128;
+  *bh = 128 / *bw;
+  if (*bh > ho) *bh = ho;
+  *bn = 128 / (*bw * *bh);
+  if (*bn > n) *bn = n;
+  if (batched || *bn < 1) *bn = 1;
 }
 
 }  // namespace
@@ -229,9 +283,22 @@ int eovae_conv_k_per_tap(int cin) {
   return round_up(cin, ch);
 }
 
+size_t eovae_conv2d_gn_workspace_bytes(int n, int h, int w, int mode, int cout, int groups) {
+  int ho = h, wo = w;
+  if (mode == EOVAE_CONV_3X3_S2) {
+    ho = (h - 2) / 2 + 1;
+    wo = (w - 2) / 2 + 1;
+  }
+  int bw, bh, bn;
+  m_tiling(n, ho, wo, false, &bw, &bh, &bn);
+  if (bn != 1 || groups <= 0 || cout % 32 != 0 || cout % groups != 0 || 32 % (cout / groups) != 0) return 0;
+  return sizeof(float) * 2 * 4 * static_cast<size_t>(ceil_div(wo, bw)) * ceil_div(ho, bh) * n * groups;
+}
+
 int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_stride, int mode, const void* w_packed,
                  int cout, const float* bias, const void* residual, int res_dtype, long long res_pix_stride, void* out,
-                 int out_dtype, long long out_pix_stride, int act_dtype, float scale, void* stream) {
+                 int out_dtype, long long out_pix_stride, int act_dtype, float scale, float* gn_stats, int gn_groups,
+                 float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, void* stream) {
   EOVAE_CHECK(mode == EOVAE_CONV_3X3 || mode == EOVAE_CONV_1X1 || mode == EOVAE_CONV_3X3_S2, "conv2d: bad mode %d", mode);
   EOVAE_CHECK(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "conv2d: empty shape");
   EOVAE_CHECK(cin % 8 == 0, "conv2d: Cin (%d) must be a multiple of 8", cin);
@@ -240,7 +307,8 @@ int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_st
   const int kpt = eovae_conv_k_per_tap(cin);
   return launch_igemm(a, mode, w_packed, kpt, cb, cout, round_up(cout, 16),
                       static_cast<long long>(mode == EOVAE_CONV_1X1 ? 1 : 9) * kpt, 0, 1, bias, residual, res_dtype,
-                      res_pix_stride, out, out_dtype, out_pix_stride, act_dtype, scale, static_cast<cudaStream_t>(stream));
+                      res_pix_stride, out, out_dtype, out_pix_stride, act_dtype, scale, static_cast<cudaStream_t>(stream),
+                      gn_stats, gn_groups, gn_eps, gn_workspace, gn_workspace_bytes);
 }
 
 int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride, const void* b, long long ldb,

@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA implicit-GEMM kernel for sm_100a.
 //
-//   D[m, n] = sum_{tap, c} A_tap[m, c] * Wp[n, tap*Kc + c]      (+ bias[n]) (+ residual[m, n]) (* scale)
+//   D[m, n] = scale * sum_{tap, c} A_tap[m, c] * Wp[n, tap*Kc + c]   (+ bias[n]) (+ residual[m, n])
 //
 // m runs over output pixels (image n, row y, col x) of an NHWC activation tensor, A_tap is the same tensor
 // shifted by the filter tap; every A tile is ONE 4-D TMA box (channels, x, y, image) whose out-of-bounds
@@ -8,17 +8,21 @@
 // nothing is ever im2col'ed or padded in HBM.  B tiles are 3-D TMA boxes (k, cout, batch) of the packed
 // K-major weight matrix (batch = 0 for convolutions, = image for the attention batched GEMMs).
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0      : TMA producer (one elected lane), STAGES-deep smem ring, mbarrier full/empty
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (one lane); accumulators double-buffered in TMEM
-//   warps 2..5  : epilogue - tcgen05.ld (32 lanes x 32 bit), bias / residual / scale, 16-byte stores
+//   warps 2..9  : epilogue - two warps per TMEM sub-partition, each owning half of the tile's columns:
+//                 tcgen05.ld 32 lanes x 32 columns, bias from shared memory, residual (L2-prefetched one mainloop
+//                 ahead), 16-byte stores, and optionally the GroupNorm partial sums of the tile (warp-shuffle
+//                 reduce-scatter over the 32 rows, fixed-slot writes -> deterministic, no atomics)
 #pragma once
 #include "common.cuh"
 
 namespace igemm {
 
 constexpr int BLOCK_M = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int MAX_TAPS = 9;
 
 struct Params {
@@ -42,6 +46,11 @@ struct Params {
   const float* bias;
   float out_scale;
   uint32_t idesc;
+  // fused GroupNorm statistics of the OUTPUT tensor (nullptr = off; needs box_n == 1, Cout % 32 == 0):
+  // gn_partial[((m_tile * 4 + sub) * groups + g) * 2 + {0,1}] = (sum, sum of squares) over the 32 rows of the warp
+  float* gn_partial;
+  int gn_cpg;                     // channels per group (1, 2, 4, 8, 16 or 32)
+  int gn_groups;                  // Cout / gn_cpg
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -94,6 +103,9 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -109,7 +121,7 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -118,6 +130,9 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the 256 epilogue threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+}
 
 // K-major operand tile in shared memory: rows of CHUNK_BYTES (32/64/128) bytes, hardware swizzle of the same
 // width, 8-row groups CHUNK_BYTES*8 apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell).
@@ -142,77 +157,64 @@ struct Config {
   static constexpr int BUDGET = 200 * 1024;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias, double buffered*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + AUX_BYTES;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 };
 
-// Epilogue for 16 accumulator columns of one output pixel.
-__device__ __forceinline__ void epilogue16(const Params& p, const uint32_t (&acc)[16], long long pix, int n0,
-                                           bool valid_pix) {
-  if (!valid_pix || n0 >= p.Cout) return;
-  float v[16];
-  const bool full = (n0 + 16 <= p.Cout);
+// Warp-level reduce-scatter of NV per-lane values over the 32 lanes: afterwards lane l holds in vals[0] the
+// total of value index (l >> (5 - log2 NV))... see gn_reduce() for the index formula.  NV shuffles instead of 5*NV.
+template <int NV>
+__device__ __forceinline__ void reduce_scatter(float (&vals)[NV], int lane) {
+  int nv = NV;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * p.out_scale;
-  if (p.bias != nullptr) {
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (nv > 1) {
+      const int half = nv >> 1;
+      const bool upper = (lane & off) != 0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (full || n0 + j < p.Cout) v[j] += __ldg(p.bias + n0 + j);
-  }
-  if (p.res != nullptr) {
-    if (p.res_dtype == EOVAE_F32) {
-      const float* r = reinterpret_cast<const float*>(p.res) + pix * p.res_pix_stride + n0;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 t = *reinterpret_cast<const float4*>(r + j);
-          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      for (int i = 0; i < NV / 2; ++i) {
+        if (i < half) {
+          const float send = upper ? vals[i] : vals[i + half];
+          const float keep = upper ? vals[i + half] : vals[i];
+          vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
-      } else {
-        for (int j = 0; j < 16 && n0 + j < p.Cout; ++j) v[j] += r[j];
       }
+      nv = half;
     } else {
-      const uint16_t* r = reinterpret_cast<const uint16_t*>(p.res) + pix * p.res_pix_stride + n0;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-          uint4 t = *reinterpret_cast<const uint4*>(r + j);
-          float2 a = unpack16(t.x, p.res_dtype), b = unpack16(t.y, p.res_dtype);
-          float2 c = unpack16(t.z, p.res_dtype), d = unpack16(t.w, p.res_dtype);
-          v[j] += a.x; v[j + 1] += a.y; v[j + 2] += b.x; v[j + 3] += b.y;
-          v[j + 4] += c.x; v[j + 5] += c.y; v[j + 6] += d.x; v[j + 7] += d.y;
-        }
-      } else {
-        for (int j = 0; j < 16 && n0 + j < p.Cout; ++j) {
-          uint32_t u = r[j];
-          v[j] += unpack16(u, p.res_dtype).x;
-        }
-      }
+      vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
     }
   }
-  if (p.out_dtype == EOVAE_F32) {
-    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + n0;
-    if (full) {
+}
+
+// GroupNorm partial sums of one 32-column chunk: v = final fp32 outputs of this thread's row (zero for invalid rows).
+template <int CPG>
+__device__ __forceinline__ void gn_chunk(const float (&v)[32], int lane, float* dst /* [32/CPG groups][2] */) {
+  constexpr int G = 32 / CPG;
+  constexpr int NV = 2 * G;
+  float vals[NV];
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-      for (int j = 0; j < 16 && n0 + j < p.Cout; ++j) o[j] = v[j];
-    }
-  } else {
-    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.out_pix_stride + n0;
-    if (full) {
+  for (int g = 0; g < G; ++g) {
+    float s = 0.f, q = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; j += 8) {
-        uint4 t;
-        t.x = pack16(v[j], v[j + 1], p.out_dtype);
-        t.y = pack16(v[j + 2], v[j + 3], p.out_dtype);
-        t.z = pack16(v[j + 4], v[j + 5], p.out_dtype);
-        t.w = pack16(v[j + 6], v[j + 7], p.out_dtype);
-        *reinterpret_cast<uint4*>(o + j) = t;
-      }
-    } else {
-      for (int j = 0; j < 16 && n0 + j < p.Cout; ++j) o[j] = static_cast<uint16_t>(pack16(v[j], 0.f, p.out_dtype) & 0xFFFF);
+    for (int j = 0; j < CPG; ++j) {
+      const float t = v[g * CPG + j];
+      s += t;
+      q = fmaf(t, t, q);
     }
+    vals[g] = s;          // sums in the lower half, squares in the upper half
+    vals[G + g] = q;
+  }
+  reduce_scatter<NV>(vals, lane);
+  // after log2(NV) halving steps (offsets 16, 8, ...) lane l owns value index = top log2(NV) bits of l
+  constexpr int LOG = (NV == 64) ? 6 : (NV == 32) ? 5 : (NV == 16) ? 4 : (NV == 8) ? 3 : (NV == 4) ? 2 : 1;
+  // value index i < G is the sum of group i, i >= G the sum of squares of group i - G
+  auto put = [&](int idx, float val) { dst[(idx < G ? idx : idx - G) * 2 + (idx < G ? 0 : 1)] = val; };
+  if constexpr (NV <= 32) {
+    if ((lane & ((1 << (5 - LOG)) - 1)) == 0) put(lane >> (5 - LOG), vals[0]);
+  } else {  // NV == 64: five halvings leave two consecutive indices per lane
+    put(2 * lane, vals[0]);
+    put(2 * lane + 1, vals[1]);
   }
 }
 
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -322,13 +325,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..5
-    const int sub = warp & 3;  // TMEM sub-partition this warp may access: lanes [32*sub, 32*sub+32)
+    // ------------------------------------------------------------------ epilogue warps 2..9
+    const int ew = warp - 2;
+    const int sub = warp & 3;    // TMEM sub-partition this warp may access: lanes [32*sub, 32*sub+32)
+    const int half = ew >> 2;    // which half of the tile's columns this warp owns
+    const int et = threadIdx.x - 64;  // 0..255
+    constexpr int HALF_N = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;  // narrow tiles: only half 0 works
+    const bool has_cols = (BLOCK_N >= 64) || (half == 0);
+    const int col_begin = (BLOCK_N >= 64) ? half * HALF_N : 0;
     const int row = sub * 32 + lane;
     const int box_pix = p.box_w * p.box_h * p.box_n;
     const int wi = row % p.box_w;
     const int hi = (row / p.box_w) % p.box_h;
     const int ni = row / (p.box_w * p.box_h);
+    const bool out16 = p.out_dtype != EOVAE_F32;
+    const bool has_res = p.res != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -341,24 +352,131 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
       const int ox = tw * p.box_w + wi, oy = th * p.box_h + hi, on = tn * p.box_n + ni;
       const bool valid = row < box_pix && ox < p.Wo && oy < p.Ho && on < p.Nimg;
       const long long pix = (static_cast<long long>(on) * p.Ho + oy) * p.Wo + ox;
+      const int n_tile0 = nt * BLOCK_N;
+      // stage this tile's bias in shared memory (double buffered by tile parity)
+      float* bs = bias_s + acc * BLOCK_N;
+      if (et < BLOCK_N) bs[et] = (p.bias != nullptr && n_tile0 + et < p.Cout) ? __ldg(p.bias + n_tile0 + et) : 0.f;
+      // pull this thread's residual row segment into L2 while the mainloop of this tile is still running
+      if (has_res && valid && has_cols) {
+        const int esz = p.res_dtype == EOVAE_F32 ? 4 : 2;
+        const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + n_tile0 + col_begin) * esz;
+        for (int b = 0; b < HALF_N * esz; b += 128) prefetch_l2(rp + b);
+      }
+      epi_bar_sync();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
-      if constexpr (BLOCK_N >= 32) {
+      if (has_cols) {
+        constexpr int CW = BLOCK_N >= 32 ? 32 : 16;  // chunk width
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t v0[16], v1[16];
-          tc_ld16(taddr + c, v0);
-          tc_ld16(taddr + c + 16, v1);
+        for (int c = col_begin; c < col_begin + HALF_N; c += CW) {
+          uint32_t raw[32];
+          tc_ld16(taddr + c, raw);
+          if constexpr (CW == 32) tc_ld16(taddr + c + 16, raw + 16);
+          const int n0 = n_tile0 + c;
+          const bool full = n0 + CW <= p.Cout;
+          // residual loads are issued before the TMEM wait so both latencies overlap
+          uint4 r16[4];
+          float4 r32[8];
+          if (has_res && valid && full) {
+            if (p.res_dtype == EOVAE_F32) {
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + pix * p.res_pix_stride + n0);
+#pragma unroll
+              for (int j = 0; j < CW / 4; ++j) r32[j] = __ldg(rp + j);
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res) + pix * p.res_pix_stride + n0);
+#pragma unroll
+              for (int j = 0; j < CW / 8; ++j) r16[j] = __ldg(rp + j);
+            }
+          }
           tc_wait_ld();
-          epilogue16(p, v0, pix, nt * BLOCK_N + c, valid);
-          epilogue16(p, v1, pix, nt * BLOCK_N + c + 16, valid);
+          float v[32];
+          const float4* b4 = reinterpret_cast<const float4*>(bs + c);
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) {
+            const float4 bq = b4[j];
+            v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), p.out_scale, bq.x);
+            v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), p.out_scale, bq.y);
+            v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), p.out_scale, bq.z);
+            v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), p.out_scale, bq.w);
+          }
+          if constexpr (CW == 16) {
+#pragma unroll
+            for (int j = 16; j < 32; ++j) v[j] = 0.f;
+          }
+          if (has_res && valid) {
+            if (full) {
+              if (p.res_dtype == EOVAE_F32) {
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                  v[4 * j] += r32[j].x; v[4 * j + 1] += r32[j].y; v[4 * j + 2] += r32[j].z; v[4 * j + 3] += r32[j].w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CW / 8; ++j) {
+                  const float2 a = unpack16(r16[j].x, p.res_dtype), b = unpack16(r16[j].y, p.res_dtype);
+                  const float2 cc = unpack16(r16[j].z, p.res_dtype), d = unpack16(r16[j].w, p.res_dtype);
+                  v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b.x; v[8 * j + 3] += b.y;
+                  v[8 * j + 4] += cc.x; v[8 * j + 5] += cc.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
+                }
+              }
+            } else {
+              for (int j = 0; j < CW && n0 + j < p.Cout; ++j) {
+                if (p.res_dtype == EOVAE_F32) {
+                  v[j] += reinterpret_cast<const float*>(p.res)[pix * p.res_pix_stride + n0 + j];
+                } else {
+                  const uint32_t u = reinterpret_cast<const uint16_t*>(p.res)[pix * p.res_pix_stride + n0 + j];
+                  v[j] += unpack16(u, p.res_dtype).x;
+                }
+              }
+            }
+          }
+          if (valid && n0 < p.Cout) {
+            if (full) {
+              if (out16) {
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + pix * p.out_pix_stride + n0);
+#pragma unroll
+                for (int j = 0; j < CW / 8; ++j) {
+                  uint4 t;
+                  t.x = pack16(v[8 * j], v[8 * j + 1], p.out_dtype);
+                  t.y = pack16(v[8 * j + 2], v[8 * j + 3], p.out_dtype);
+                  t.z = pack16(v[8 * j + 4], v[8 * j + 5], p.out_dtype);
+                  t.w = pack16(v[8 * j + 6], v[8 * j + 7], p.out_dtype);
+                  o[j] = t;
+                }
+              } else {
+                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + n0);
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+            } else {
+              for (int j = 0; j < CW && n0 + j < p.Cout; ++j) {
+                if (out16)
+                  reinterpret_cast<uint16_t*>(p.out)[pix * p.out_pix_stride + n0 + j] =
+                      static_cast<uint16_t>(pack16(v[j], 0.f, p.out_dtype) & 0xFFFF);
+                else
+                  reinterpret_cast<float*>(p.out)[pix * p.out_pix_stride + n0 + j] = v[j];
+              }
+            }
+          }
+          if constexpr (CW == 32) {
+            if (p.gn_partial != nullptr && full) {  // warp-uniform
+              if (!valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              }
+              float* dst = p.gn_partial + ((static_cast<long long>(mt) * 4 + sub) * p.gn_groups + n0 / p.gn_cpg) * 2;
+              switch (p.gn_cpg) {
+                case 1: gn_chunk<1>(v, lane, dst); break;
+                case 2: gn_chunk<2>(v, lane, dst); break;
+                case 4: gn_chunk<4>(v, lane, dst); break;
+                case 8: gn_chunk<8>(v, lane, dst); break;
+                case 16: gn_chunk<16>(v, lane, dst); break;
+                default: gn_chunk<32>(v, lane, dst); break;
+              }
+            }
+          }
         }
-      } else {
-        uint32_t v0[16];
-        tc_ld16(taddr, v0);
-        tc_wait_ld();
-        epilogue16(p, v0, pix, nt * BLOCK_N, valid);
       }
       tc_fence_before();
       __syncwarp();

@@ -150,7 +150,7 @@ class Decoder(nn.Module):
 
     def forward_act(self, z: Tensor, wvs: Tensor = None) -> Tensor:
         """z: activation (NHWC 16-bit) or any [B, z, h, w] tensor -> fp32 NHWC-stored reconstruction."""
-        h = self.conv_in(self.post_quant_conv(z))
+        h = self.conv_in(self.post_quant_conv(z), gn_next=True)
         h = self.mid.block_1(h)
         h = self.mid.attn_1(h)
         h = self.mid.block_2(h)

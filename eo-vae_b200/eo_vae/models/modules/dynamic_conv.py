@@ -178,7 +178,7 @@ class DynamicConv(_DynamicBase):
         wk, b_raw = self._generate(wvs)
         packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, self.embed_dim, False, self.scaler, self.scaler, dt, False)
         x = ops.nchw_to_act(img_feat, ops.dyn_cin_pad(c), dt)
-        return ops.conv2d(x, packed, bias, self.embed_dim, ops.CONV_3X3, algo_cin=c)
+        return ops.conv2d(x, packed, bias, self.embed_dim, ops.CONV_3X3, algo_cin=c, gn_groups=32, gn_eps=1e-6)
 
 
 class DynamicConv_decoder(_DynamicBase):

@@ -65,10 +65,11 @@ class Conv2dSM100(nn.Conv2d):
     def bias_f32(self):
         return None if self.bias is None else self.bias.detach()
 
-    def forward(self, x: Tensor, residual: Tensor | None = None, out_dtype=None) -> Tensor:  # noqa: D102
+    def forward(self, x: Tensor, residual: Tensor | None = None, out_dtype=None, gn_next: bool = False) -> Tensor:  # noqa: D102
+        """gn_next: the output feeds a GroupNorm(32, eps 1e-6) next, so let the epilogue produce its statistics."""
         x = ops.to_act(x, compute_dtype())
         return ops.conv2d(x, self.packed_weight(x.dtype), self.bias_f32(), self.out_channels, self._mode,
-                          residual=residual, out_dtype=out_dtype)
+                          residual=residual, out_dtype=out_dtype, gn_groups=32 if gn_next else 0, gn_eps=1e-6)
 
 
 class Downsample(nn.Module):
@@ -80,7 +81,7 @@ class Downsample(nn.Module):
         self.conv = Conv2dSM100(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
 
     def forward(self, x: Tensor) -> Tensor:
-        return self.conv(x)
+        return self.conv(x, gn_next=True)
 
 
 class Upsample(nn.Module):
@@ -92,7 +93,7 @@ class Upsample(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         x = ops.to_act(x, compute_dtype())
-        return self.conv(ops.upsample2x(x))
+        return self.conv(ops.upsample2x(x), gn_next=True)
 
 
 class ResnetBlock(nn.Module):
@@ -120,10 +121,10 @@ class ResnetBlock(nn.Module):
         if self.cond_dim is not None and emb is not None:
             raise NotImplementedError("AdaIN-conditioned ResnetBlock (use_adain) is outside the built hot path")
         x = ops.to_act(x, compute_dtype())
-        h = self.conv1(self.norm1(x, silu=True))
+        h = self.conv1(self.norm1(x, silu=True), gn_next=True)
         h = self.norm2(h, silu=True)
         shortcut = self.nin_shortcut(x) if self.in_channels != self.out_channels else x
-        return self.conv2(h, residual=shortcut)  # residual add fused in the conv epilogue
+        return self.conv2(h, residual=shortcut, gn_next=True)  # residual add + next GN's statistics in the epilogue
 
 
 class AttnBlock(nn.Module):
@@ -167,4 +168,4 @@ class AttnBlock(nn.Module):
         vt = ops.transpose16(v)                                   # [n, c, L]
         o = ops.gemm_tn_batched(probs, vt, x.dtype)               # [n, L, c]
         o = o.view(n, hh, ww, c).permute(0, 3, 1, 2)
-        return self.proj_out(o, residual=x)
+        return self.proj_out(o, residual=x, gn_next=True)

@@ -95,7 +95,9 @@ def pack_conv_weight(w: torch.Tensor, dtype) -> torch.Tensor:
 
 
 def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, residual=None, out_dtype=None,
-           scale: float = 1.0, algo_cin: int | None = None) -> torch.Tensor:
+           scale: float = 1.0, algo_cin: int | None = None, gn_groups: int = 0, gn_eps: float = 1e-6) -> torch.Tensor:
+    """out = scale * conv(x) + bias + residual.  With gn_groups > 0 the epilogue also produces the GroupNorm statistics
+    of the output; they ride along as ``out._gn_stats = (stats, groups, eps)`` for the next GroupNormSM100."""
     _need_cuda(x, w_packed, bias, residual)
     n, cin, h, w = x.shape
     ho, wo = (h, w) if mode != CONV_3X3_S2 else ((h - 2) // 2 + 1, (w - 2) // 2 + 1)
@@ -109,11 +111,21 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, 
         res_dt, res_ps = DT[residual.dtype], pix_stride(residual)
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != cout):
         raise RuntimeError("eo_vae.conv2d: bias must be fp32 [cout]")
+    stats = ws = None
+    ws_bytes = 0
+    if gn_groups > 0:
+        ws_bytes = _C.lib().eovae_conv2d_gn_workspace_bytes(n, h, w, mode, cout, gn_groups)
+        if ws_bytes > 0:
+            stats = torch.empty((n, gn_groups, 2), dtype=torch.float32, device=x.device)
+            ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=x.device)
     flops = 2.0 * n * ho * wo * cout * (algo_cin or cin) * (1 if mode == CONV_1X1 else 9)
     rc = _timed("conv", flops, lambda: _C.lib().eovae_conv2d(
         _ptr(x), n, h, w, cin, pix_stride(x), mode, _ptr(w_packed), cout, _ptr(bias), _ptr(residual), res_dt, res_ps,
-        _ptr(out), DT[out_dtype], pix_stride(out), DT[x.dtype], float(scale), _stream()))
+        _ptr(out), DT[out_dtype], pix_stride(out), DT[x.dtype], float(scale), _ptr(stats), gn_groups, float(gn_eps),
+        _ptr(ws), ws_bytes, _stream()))
     _C.check(rc, "eovae_conv2d")
+    if stats is not None:
+        out._gn_stats = (stats, gn_groups, float(gn_eps))
     return out
 
 
@@ -159,7 +171,13 @@ def gn_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: to
 
 
 def group_norm(x, gamma, beta, silu: bool, groups: int = 32, eps: float = 1e-6):
-    return gn_apply(x, gn_stats(x, groups, eps), gamma, beta, silu, groups)
+    """GroupNorm (+SiLU).  Statistics come from the producing conv's epilogue when it left them on the tensor."""
+    fused = getattr(x, "_gn_stats", None)
+    if fused is not None and fused[1] == groups and fused[2] == float(eps):
+        stats = fused[0]
+    else:
+        stats = gn_stats(x, groups, eps)
+    return gn_apply(x, stats, gamma, beta, silu, groups)
 
 
 # ------------------------------------------------------------------------------------------------ edges

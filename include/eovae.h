@@ -52,9 +52,15 @@ int eovae_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, in
 
 /* ---- tcgen05 implicit-GEMM convolution: replaces cuDNN conv2d at layers.py:64,81,85,123-126,33-37 and
  *      model.py:162,165,236,260.   out = scale * conv(x, w) + bias + residual                                   */
+/*      Optional fused GroupNorm statistics of the OUTPUT (what the next GroupNorm of the network needs): when
+ *      gn_stats != NULL the epilogue also emits per-tile partial sums (fixed slots, no atomics -> deterministic) and a
+ *      tiny second kernel reduces them to gn_stats[n][gn_groups][2] = (mean, rstd).  eovae_conv2d_gn_workspace_bytes
+ *      returns the workspace size, or 0 when the shape does not support the fusion (use eovae_gn_stats instead).     */
+size_t eovae_conv2d_gn_workspace_bytes(int n, int h, int w, int mode, int cout, int groups);
 int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_stride, int mode, const void* w_packed,
                  int cout, const float* bias, const void* residual, int res_dtype, long long res_pix_stride, void* out,
-                 int out_dtype, long long out_pix_stride, int act_dtype, float scale, void* stream);
+                 int out_dtype, long long out_pix_stride, int act_dtype, float scale, float* gn_stats, int gn_groups,
+                 float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, void* stream);
 
 /* ---- batched C[b] = scale * A[b] (m x k) * B[b]^T (n x k): the q k^T and p v products of AttnBlock
  *      (F.scaled_dot_product_attention, layers.py:134-141)                                                      */

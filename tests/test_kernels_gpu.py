@@ -64,6 +64,37 @@ def test_conv2d(cuda, n, h, w, cin, cout, mode):
     assert _rel(out2, ref + res.float()) < 4e-3
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 64, 128), (1, 64, 64, 128, 256), (3, 16, 16, 128, 512),
+                                            (2, 24, 40, 32, 64), (2, 16, 16, 16, 32), (1, 256, 256, 16, 128)])
+@pytest.mark.parametrize("mode", ["3x3", "s2"])
+def test_conv2d_fused_gn_stats(cuda, n, h, w, cin, cout, mode):
+    """The epilogue's GroupNorm statistics of the conv OUTPUT (incl. bias + residual) match a two-pass fp32 statement
+    and are bit-reproducible."""
+    from eo_vae import ops
+    x = _act(n, cin, h, w, cuda, seed=3)
+    wgt = (torch.randn(cout, cin, 3, 3) / math.sqrt(cin * 9)).to(cuda)
+    bias = torch.randn(cout).to(cuda)
+    wp = ops.pack_conv_weight(wgt, torch.bfloat16)
+    m = ops.CONV_3X3 if mode == "3x3" else ops.CONV_3X3_S2
+    xf, w16 = x.float(), wgt.bfloat16().float()
+    ref = F.conv2d(xf, w16, bias, padding=1) if mode == "3x3" else F.conv2d(F.pad(xf, (0, 1, 0, 1)), w16, bias, stride=2)
+    res = _act(*ref.shape, cuda, seed=11)
+    ref = ref + res.float()
+    out = ops.conv2d(x, wp, bias, cout, m, residual=res, gn_groups=32)
+    assert hasattr(out, "_gn_stats"), "fused statistics were not produced for a supported shape"
+    stats = out._gn_stats[0]
+    rf = ref.reshape(ref.shape[0], 32, -1)
+    assert torch.allclose(stats[..., 0], rf.mean(-1), atol=2e-4)
+    assert torch.allclose(stats[..., 1], 1 / torch.sqrt(rf.var(-1, unbiased=False) + 1e-6), rtol=2e-4)
+    out2 = ops.conv2d(x, wp, bias, cout, m, residual=res, gn_groups=32)
+    assert torch.equal(out2._gn_stats[0], stats) and torch.equal(out2, out)
+    # group_norm() consumes them: same result as recomputing from the stored tensor up to the 16-bit rounding
+    gamma, beta = torch.ones(cout, device=cuda), torch.zeros(cout, device=cuda)
+    y = ops.group_norm(out, gamma, beta, True)
+    y_ref = F.group_norm(ref, 32, gamma, beta, eps=1e-6)
+    assert _rel(y, y_ref * torch.sigmoid(y_ref)) < 6e-3
+
+
 def test_conv2d_fp16_operands(cuda):
     from eo_vae import ops
     x = _act(2, 64, 16, 16, cuda, dtype=torch.float16)

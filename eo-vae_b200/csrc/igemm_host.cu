@@ -8,6 +8,9 @@
 
 namespace {
 
+int g_debug_mode = 0;
+int g_force_ctas = 0;  // 0 = auto, 1 / 2 = forced (tests, tools/igemm_bench.py)
+
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -58,31 +61,44 @@ int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const ui
   return 0;
 }
 
-template <int BLOCK_N, int CHUNK_BYTES>
-int launch_t(const igemm::Params& p, int total_tiles, cudaStream_t stream) {
-  using Cfg = igemm::Config<BLOCK_N, CHUNK_BYTES>;
-  auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES>;
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS>
+int launch_t(const igemm::Params& p, int total_work, cudaStream_t stream) {
+  using Cfg = igemm::Config<BLOCK_N, CHUNK_BYTES, CTAS>;
+  auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES, CTAS>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
     EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  int grid = total_tiles < eovae_num_sms() ? total_tiles : eovae_num_sms();
-  kern<<<grid, igemm::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  const int max_groups = eovae_num_sms() / CTAS;  // one CTA (pair) per SM (pair), persistent over the work items
+  const int groups = total_work < max_groups ? total_work : max_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CTAS);
+  cfg.blockDim = dim3(igemm::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EOVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   EOVAE_LAUNCH_CHECK();
   return 0;
 }
 
-template <int CHUNK_BYTES>
-int launch_n(int block_n, const igemm::Params& p, int total_tiles, cudaStream_t stream) {
+template <int CHUNK_BYTES, int CTAS>
+int launch_n(int block_n, const igemm::Params& p, int total_work, cudaStream_t stream) {
   switch (block_n) {
-    case 16: return launch_t<16, CHUNK_BYTES>(p, total_tiles, stream);
-    case 32: return launch_t<32, CHUNK_BYTES>(p, total_tiles, stream);
-    case 64: return launch_t<64, CHUNK_BYTES>(p, total_tiles, stream);
-    case 128: return launch_t<128, CHUNK_BYTES>(p, total_tiles, stream);
-    case 256: return launch_t<256, CHUNK_BYTES>(p, total_tiles, stream);
+    case 16: if constexpr (CTAS == 1) return launch_t<16, CHUNK_BYTES, 1>(p, total_work, stream); break;
+    case 32: return launch_t<32, CHUNK_BYTES, CTAS>(p, total_work, stream);
+    case 64: return launch_t<64, CHUNK_BYTES, CTAS>(p, total_work, stream);
+    case 128: return launch_t<128, CHUNK_BYTES, CTAS>(p, total_work, stream);
+    case 256: return launch_t<256, CHUNK_BYTES, CTAS>(p, total_work, stream);
   }
-  eovae::set_error("igemm: unsupported BLOCK_N %d", block_n);
+  eovae::set_error("igemm: unsupported BLOCK_N %d for a %d-CTA group", block_n, CTAS);
   return -1;
 }
 
@@ -177,12 +193,20 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   p.res_pix_stride = res_pix_stride;
   p.bias = bias;
   p.out_scale = scale;
+  p.debug_mode = g_debug_mode;
   const int block_n = pick_block_n(round_up(cout, 16));
   p.n_tiles = ceil_div(cout, block_n);
+  // CTA pairs (cta_group::2, UMMA M = 256) whenever there are at least two m-tiles to pair; a batched B operand
+  // additionally needs both tiles of a pair inside one image.
+  const int m_tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
+  int ctas = (block_n >= 32 && m_tiles_total >= 2) ? 2 : 1;
+  if (w_batches > 1 && (p.tiles_w * p.tiles_h) % 2 != 0) ctas = 1;
+  if (g_force_ctas == 1) ctas = 1;
+  if (g_force_ctas == 2 && block_n >= 32 && !(w_batches > 1 && (p.tiles_w * p.tiles_h) % 2 != 0)) ctas = 2;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B = bf16|f16, K-major both, N>>3, M>>4
   const uint32_t fmt = act_dtype == EOVAE_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) |
-            (static_cast<uint32_t>(igemm::BLOCK_M >> 4) << 24);
+            (static_cast<uint32_t>((igemm::BLOCK_M * ctas) >> 4) << 24);
 
   // --- A maps
   const uint32_t box[4] = {static_cast<uint32_t>(ch), static_cast<uint32_t>(p.box_w), static_cast<uint32_t>(p.box_h),
@@ -227,11 +251,11 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     uint64_t dims[3] = {ktot, static_cast<uint64_t>(w_rows), static_cast<uint64_t>(w_batches)};
     uint64_t strides[2] = {static_cast<uint64_t>(w_row_stride) * es, static_cast<uint64_t>(w_batch_stride) * es};
     if (w_batches <= 1) strides[1] = static_cast<uint64_t>(w_row_stride) * static_cast<uint64_t>(w_rows) * es;
-    const uint32_t bbox[3] = {static_cast<uint32_t>(ch), static_cast<uint32_t>(block_n), 1};
+    const uint32_t bbox[3] = {static_cast<uint32_t>(ch), static_cast<uint32_t>(block_n / ctas), 1};
     int rc = encode_map(&p.b_map, act_dtype, 3, w, dims, strides, bbox, chunk_bytes);
     if (rc) return rc;
   }
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int total_tiles = ceil_div(m_tiles_total, ctas) * p.n_tiles;  // work items
   if (total_tiles == 0) return 0;
   if (gn_stats != nullptr) {
     EOVAE_CHECK(p.box_n == 1 && cout % 32 == 0 && gn_groups > 0 && cout % gn_groups == 0 && 32 % (cout / gn_groups) == 0 &&
@@ -244,10 +268,18 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     p.gn_cpg = cout / gn_groups;
   }
   int rc;
-  switch (chunk_bytes) {
-    case 128: rc = launch_n<128>(block_n, p, total_tiles, stream); break;
-    case 64: rc = launch_n<64>(block_n, p, total_tiles, stream); break;
-    default: rc = launch_n<32>(block_n, p, total_tiles, stream); break;
+  if (ctas == 2) {
+    switch (chunk_bytes) {
+      case 128: rc = launch_n<128, 2>(block_n, p, total_tiles, stream); break;
+      case 64: rc = launch_n<64, 2>(block_n, p, total_tiles, stream); break;
+      default: rc = launch_n<32, 2>(block_n, p, total_tiles, stream); break;
+    }
+  } else {
+    switch (chunk_bytes) {
+      case 128: rc = launch_n<128, 1>(block_n, p, total_tiles, stream); break;
+      case 64: rc = launch_n<64, 1>(block_n, p, total_tiles, stream); break;
+      default: rc = launch_n<32, 1>(block_n, p, total_tiles, stream); break;
+    }
   }
   if (rc != 0 || gn_stats == nullptr) return rc;
   const int pairs = p.Nimg * gn_groups;
@@ -271,6 +303,11 @@ void m_tiling(int n, int ho, int wo, bool batched, int* bw, int* bh, int* bn) {
 }  // namespace
 
 extern "C" {
+
+void eovae_set_debug_mode(int mode) {
+  g_debug_mode = mode & 0xFF;       // low byte: pipeline actor switched off (igemm_sm100.cuh)
+  g_force_ctas = (mode >> 8) & 3;   // bits 8-9: force 1- or 2-CTA groups (0 = automatic)
+}
 
 int eovae_conv_chunk_bytes(int cin) {
   if (cin % 64 == 0) return 128;

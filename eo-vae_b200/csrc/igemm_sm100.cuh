@@ -8,6 +8,11 @@
 // nothing is ever im2col'ed or padded in HBM.  B tiles are 3-D TMA boxes (k, cout, batch) of the packed
 // K-major weight matrix (batch = 0 for convolutions, = image for the attention batched GEMMs).
 //
+// CTAS = 2 runs the mainloop on CTA PAIRS (tcgen05 cta_group::2, cluster of 2): one UMMA covers 256 pixels x BLOCK_N,
+// each CTA stages its own 128-pixel A tile and HALF of the B tile, so the shared-memory operand traffic per MMA
+// drops from (128 + N) to (128 + N/2) rows - the single-CTA SS-mode MMA is smem-read bound (measured: 157 / 187
+// cycles per 128xNx16 MMA at N = 128 / 256 against 64 / 128 cycles of math).
+//
 // Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0      : TMA producer (one elected lane), STAGES-deep smem ring, mbarrier full/empty
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (one lane); accumulators double-buffered in TMEM
@@ -51,6 +56,7 @@ struct Params {
   float* gn_partial;
   int gn_cpg;                     // channels per group (1, 2, 4, 8, 16 or 32)
   int gn_groups;                  // Cout / gn_cpg
+  int debug_mode;                 // 0 normal | 1 no epilogue work | 2 no MMA issue | 3 no TMA (tools/igemm_bench.py)
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -121,6 +127,53 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants.  A shared::cta address is a valid shared::cluster address of the executing
+// CTA; clearing bit 24 (cute::Sm100MmaPeerBitMask) addresses the same offset in the even (leader) CTA of the pair.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit_mc(uint64_t* bar) {  // arrive on `bar` in BOTH CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tc2_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -148,10 +201,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <int BLOCK_N, int CHUNK_BYTES>
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS>
 struct Config {
   static constexpr int A_BYTES = BLOCK_M * CHUNK_BYTES;
-  static constexpr int B_BYTES_RAW = BLOCK_N * CHUNK_BYTES;
+  static constexpr int B_ROWS = BLOCK_N / CTAS;  // rows of the B tile staged by each CTA
+  static constexpr int B_BYTES_RAW = B_ROWS * CHUNK_BYTES;
   static constexpr int B_BYTES = (B_BYTES_RAW + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BUDGET = 200 * 1024;
@@ -218,9 +272,13 @@ __device__ __forceinline__ void gn_chunk(const float (&v)[32], int lane, float* 
   }
 }
 
-template <int BLOCK_N, int CHUNK_BYTES>
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_constant__ Params p) {
-  using Cfg = Config<BLOCK_N, CHUNK_BYTES>;
+  using Cfg = Config<BLOCK_N, CHUNK_BYTES, CTAS>;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int group_id = CTAS == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_groups = CTAS == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CH_ELEMS = CHUNK_BYTES / 2;  // 16-bit elements per k-chunk
   constexpr int K_STEPS = CHUNK_BYTES / 32;  // UMMA_K = 16 elements = 32 bytes
@@ -240,68 +298,90 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_work = ((m_tiles + CTAS - 1) / CTAS) * p.n_tiles;  // work item = CTAS adjacent m-tiles x one n-tile
   const int num_kb = p.num_taps * p.chunks_per_tap;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&p.a_map[i]);
     prefetch_tmap(&p.b_map);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], CTAS);   // one producer arrive per CTA of the group (the leader's copy is the live one)
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS * CTAS);  // one arrive per epilogue warp of every CTA of the group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (every CTA of the group)
     if (lane == 0) {
       const uint32_t a_box_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * CHUNK_BYTES;
-      const uint32_t tx_bytes = a_box_bytes + Cfg::B_BYTES_RAW;
+      const uint32_t tx_bytes = (a_box_bytes + Cfg::B_BYTES_RAW) * CTAS;  // bytes landing in ALL CTAs of the group
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int mt = tile / p.n_tiles;
+      for (int work = group_id; work < total_work; work += num_groups) {
+        const int nt = work % p.n_tiles;
+        const int mt = (work / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tn = mt / (p.tiles_w * p.tiles_h);
+        const int tn = mt / (p.tiles_w * p.tiles_h);  // == tiles_n for the padding tile of an odd tail: fully OOB -> zeros
         const int x0 = tw * p.box_w, y0 = th * p.box_h, img0 = tn * p.box_n;
         const int bb = p.b_batched ? img0 : 0;
+        const int b_row0 = nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / p.chunks_per_tap;
           const int cc = kb - tap * p.chunks_per_tap;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_4d(&p.a_map[p.tap_map[tap]], &full_bar[stage], smem_a + stage * Cfg::A_BYTES, cc * CH_ELEMS,
-                      x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], img0);
-          tma_load_3d(&p.b_map, &full_bar[stage], smem_b + stage * Cfg::B_BYTES, tap * p.k_per_tap + cc * CH_ELEMS,
-                      nt * BLOCK_N, bb);
+          if (p.debug_mode == 3) {
+            if (leader) mbar_arrive(&full_bar[stage]); else mbar_arrive_leader(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          void* sa = smem_a + stage * Cfg::A_BYTES;
+          void* sb = smem_b + stage * Cfg::B_BYTES;
+          const int k0 = tap * p.k_per_tap + cc * CH_ELEMS;
+          if constexpr (CTAS == 2) {
+            if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes); else mbar_arrive_leader(&full_bar[stage]);
+            tma2_load_4d(&p.a_map[p.tap_map[tap]], &full_bar[stage], sa, cc * CH_ELEMS, x0 + p.tap_dx[tap],
+                         y0 + p.tap_dy[tap], img0);
+            tma2_load_3d(&p.b_map, &full_bar[stage], sb, k0, b_row0, bb);
+          } else {
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(&p.a_map[p.tap_map[tap]], &full_bar[stage], sa, cc * CH_ELEMS, x0 + p.tap_dx[tap],
+                        y0 + p.tap_dy[tap], img0);
+            tma_load_3d(&p.b_map, &full_bar[stage], sb, k0, b_row0, bb);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of the group only)
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int work = group_id; work < total_work; work += num_groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -314,14 +394,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
           const uint64_t db = make_smem_desc<CHUNK_BYTES>(smem_u32(smem_b + stage * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < K_STEPS; ++k) {
+            if (p.debug_mode == 2) break;
             // advance the 14-bit start-address field by k*32 bytes (>>4)
-            tc_mma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc,
-                       (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CTAS == 2)
+              tc2_mma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+            else
+              tc_mma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc,
+                         (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in every CTA of the group) when these MMAs retire
+          if constexpr (CTAS == 2) tc2_commit_mc(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);  // accumulator complete
+        if constexpr (CTAS == 2) tc2_commit_mc(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);  // accumulator complete
       }
     }
   } else {
@@ -341,16 +427,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     const bool out16 = p.out_dtype != EOVAE_F32;
     const bool has_res = p.res != nullptr;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int work = group_id; work < total_work; work += num_groups, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = tile % p.n_tiles;
-      const int mt = tile / p.n_tiles;
+      const int nt = work % p.n_tiles;
+      const int mt = (work / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tn = mt / (p.tiles_w * p.tiles_h);
       const int ox = tw * p.box_w + wi, oy = th * p.box_h + hi, on = tn * p.box_n + ni;
-      const bool valid = row < box_pix && ox < p.Wo && oy < p.Ho && on < p.Nimg;
+      const bool valid = mt < m_tiles && row < box_pix && ox < p.Wo && oy < p.Ho && on < p.Nimg;
       const long long pix = (static_cast<long long>(on) * p.Ho + oy) * p.Wo + ox;
       const int n_tile0 = nt * BLOCK_N;
       // stage this tile's bias in shared memory (double buffered by tile parity)
@@ -366,7 +452,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
-      if (has_cols) {
+      if (has_cols && p.debug_mode != 1) {
         constexpr int CW = BLOCK_N >= 32 ? 32 : 16;  // chunk width
 #pragma unroll 1
         for (int c = col_begin; c < col_begin + HALF_N; c += CW) {
@@ -460,7 +546,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
             }
           }
           if constexpr (CW == 32) {
-            if (p.gn_partial != nullptr && full) {  // warp-uniform
+            if (p.gn_partial != nullptr && full && mt < m_tiles) {  // warp-uniform
               if (!valid) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -480,15 +566,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_leader(&tmem_empty[acc]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    if constexpr (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
   }
 }
 

@@ -42,6 +42,10 @@ const char* eovae_last_error(void);
 int eovae_num_sms(void);
 /* number of kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
 unsigned long long eovae_launch_count(void);
+/* test / profiling aid: low byte 0 normal | 1 skip epilogue work | 2 skip MMA issue | 3 skip TMA loads (these produce
+ * garbage by design, tools/igemm_bench.py only); bits 8-9: 0 automatic | 1 force single-CTA | 2 force CTA-pair
+ * (cta_group::2) implicit GEMM (tests run both).  Nothing in the product path ever sets it.                         */
+void eovae_set_debug_mode(int mode);
 
 /* ---- weight packing (derived, non-persistent caches of the OIHW fp32 master parameters) -------------------- */
 /* channels per K-chunk (in bytes: 32/64/128) and padded channels per tap chosen for a given Cin */

@@ -35,9 +35,19 @@ CONV_CASES = [
 ]
 
 
+@pytest.fixture(params=[1, 2], ids=["1cta", "2cta"])
+def cta_group(request, cuda):
+    """Run the implicit GEMM as single CTAs and as CTA pairs (tcgen05 cta_group::2); shapes that cannot pair fall
+    back to single CTAs inside the library."""
+    from eo_vae import _C
+    _C.lib().eovae_set_debug_mode(request.param << 8)
+    yield request.param
+    _C.lib().eovae_set_debug_mode(0)
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout", CONV_CASES)
 @pytest.mark.parametrize("mode", ["3x3", "1x1", "s2"])
-def test_conv2d(cuda, n, h, w, cin, cout, mode):
+def test_conv2d(cuda, cta_group, n, h, w, cin, cout, mode):
     from eo_vae import ops
     torch.manual_seed(1)
     x = _act(n, cin, h, w, cuda, seed=n * 7 + h)
@@ -67,7 +77,7 @@ def test_conv2d(cuda, n, h, w, cin, cout, mode):
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 64, 128), (1, 64, 64, 128, 256), (3, 16, 16, 128, 512),
                                             (2, 24, 40, 32, 64), (2, 16, 16, 16, 32), (1, 256, 256, 16, 128)])
 @pytest.mark.parametrize("mode", ["3x3", "s2"])
-def test_conv2d_fused_gn_stats(cuda, n, h, w, cin, cout, mode):
+def test_conv2d_fused_gn_stats(cuda, cta_group, n, h, w, cin, cout, mode):
     """The epilogue's GroupNorm statistics of the conv OUTPUT (incl. bias + residual) match a two-pass fp32 statement
     and are bit-reproducible."""
     from eo_vae import ops
@@ -81,6 +91,10 @@ def test_conv2d_fused_gn_stats(cuda, n, h, w, cin, cout, mode):
     res = _act(*ref.shape, cuda, seed=11)
     ref = ref + res.float()
     out = ops.conv2d(x, wp, bias, cout, m, residual=res, gn_groups=32)
+    from eo_vae import _C
+    if _C.lib().eovae_conv2d_gn_workspace_bytes(n, h, w, m, cout, 32) == 0:
+        assert not hasattr(out, "_gn_stats")  # several images per tile: the caller falls back to eovae_gn_stats
+        return
     assert hasattr(out, "_gn_stats"), "fused statistics were not produced for a supported shape"
     stats = out._gn_stats[0]
     rf = ref.reshape(ref.shape[0], 32, -1)
@@ -118,7 +132,7 @@ def test_conv2d_channel_slices(cuda):
 
 
 @pytest.mark.parametrize("b,m,n,k", [(2, 256, 256, 64), (3, 1024, 1024, 512), (1, 100, 72, 32), (4, 64, 512, 1024)])
-def test_gemm_tn_batched(cuda, b, m, n, k):
+def test_gemm_tn_batched(cuda, cta_group, b, m, n, k):
     from eo_vae import ops
     torch.manual_seed(2)
     a = torch.randn(b, m, k, device=cuda).bfloat16()

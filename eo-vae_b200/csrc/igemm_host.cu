@@ -10,6 +10,7 @@ namespace {
 
 int g_debug_mode = 0;
 int g_force_ctas = 0;  // 0 = auto, 1 / 2 = forced (tests, tools/igemm_bench.py)
+int g_force_kch1 = 0;  // 1 = always one K-chunk per stage
 
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -61,10 +62,11 @@ int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const ui
   return 0;
 }
 
-template <int BLOCK_N, int CHUNK_BYTES, int CTAS>
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH = 1>
 int launch_t(const igemm::Params& p, int total_work, cudaStream_t stream) {
-  using Cfg = igemm::Config<BLOCK_N, CHUNK_BYTES, CTAS>;
-  auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES, CTAS>;
+  using Cfg = igemm::Config<BLOCK_N, CHUNK_BYTES, CTAS, KCH>;
+  static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
+  auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES, CTAS, KCH>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
     EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -268,7 +270,14 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     p.gn_cpg = cout / gn_groups;
   }
   int rc;
-  if (ctas == 2) {
+  // two K-chunks (128 channels) per pipeline stage where the shapes allow >= 3 stages of shared memory
+  const bool kch2 = chunk_bytes == 128 && p.chunks_per_tap % 2 == 0 && !g_force_kch1 &&
+                    (block_n == 128 || (block_n == 256 && ctas == 2));
+  if (kch2) {
+    if (block_n == 128 && ctas == 2) rc = launch_t<128, 128, 2, 2>(p, total_tiles, stream);
+    else if (block_n == 128) rc = launch_t<128, 128, 1, 2>(p, total_tiles, stream);
+    else rc = launch_t<256, 128, 2, 2>(p, total_tiles, stream);
+  } else if (ctas == 2) {
     switch (chunk_bytes) {
       case 128: rc = launch_n<128, 2>(block_n, p, total_tiles, stream); break;
       case 64: rc = launch_n<64, 2>(block_n, p, total_tiles, stream); break;
@@ -307,6 +316,7 @@ extern "C" {
 void eovae_set_debug_mode(int mode) {
   g_debug_mode = mode & 0xFF;       // low byte: pipeline actor switched off (igemm_sm100.cuh)
   g_force_ctas = (mode >> 8) & 3;   // bits 8-9: force 1- or 2-CTA groups (0 = automatic)
+  g_force_kch1 = (mode >> 10) & 1;  // bit 10: force 64-channel pipeline stages
 }
 
 int eovae_conv_chunk_bytes(int cin) {

@@ -56,7 +56,7 @@ struct Params {
   float* gn_partial;
   int gn_cpg;                     // channels per group (1, 2, 4, 8, 16 or 32)
   int gn_groups;                  // Cout / gn_cpg
-  int debug_mode;                 // 0 normal | 1 no epilogue work | 2 no MMA issue | 3 no TMA (tools/igemm_bench.py)
+  int debug_mode;                 // bit mask: 1 no epilogue work | 2 no MMA issue | 4 no TMA (tools/igemm_bench.py)
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -140,8 +140,9 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
-               : "memory");
+  // default (.release.cta) semantics as in cutlass::arch::ClusterBarrier::arrive: a cluster-scope release here costs
+  // an L1 invalidate + ~1e3 cycles per call and serialised the peer's producer (measured: 1800 cycles per k-block)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                              int c3) {
@@ -201,12 +202,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <int BLOCK_N, int CHUNK_BYTES, int CTAS>
+// KCH = K-chunks (of CHUNK_BYTES) per pipeline stage.  The single producer / MMA threads pay ~300 cycles of serial
+// latency per stage (mbarrier try_wait, tcgen05.commit, TMA issue): measured 0.65 ms of pure handshake on a 1.3 ms
+// 128->128 conv with 64-channel stages, so wide-channel layers use two chunks (K = 128) per stage.
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH>
 struct Config {
-  static constexpr int A_BYTES = BLOCK_M * CHUNK_BYTES;
+  static constexpr int A_CHUNK_BYTES = BLOCK_M * CHUNK_BYTES;
+  static constexpr int A_BYTES = A_CHUNK_BYTES * KCH;
   static constexpr int B_ROWS = BLOCK_N / CTAS;  // rows of the B tile staged by each CTA
   static constexpr int B_BYTES_RAW = B_ROWS * CHUNK_BYTES;
-  static constexpr int B_BYTES = (B_BYTES_RAW + 1023) / 1024 * 1024;
+  static constexpr int B_CHUNK_BYTES = (B_BYTES_RAW + 1023) / 1024 * 1024;
+  static constexpr int B_BYTES = B_CHUNK_BYTES * KCH;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BUDGET = 200 * 1024;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
@@ -272,9 +278,9 @@ __device__ __forceinline__ void gn_chunk(const float (&v)[32], int lane, float* 
   }
 }
 
-template <int BLOCK_N, int CHUNK_BYTES, int CTAS>
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH>
 __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_constant__ Params p) {
-  using Cfg = Config<BLOCK_N, CHUNK_BYTES, CTAS>;
+  using Cfg = Config<BLOCK_N, CHUNK_BYTES, CTAS, KCH>;
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int group_id = CTAS == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -299,7 +305,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   const int lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_work = ((m_tiles + CTAS - 1) / CTAS) * p.n_tiles;  // work item = CTAS adjacent m-tiles x one n-tile
-  const int num_kb = p.num_taps * p.chunks_per_tap;
+  const int stages_per_tap = p.chunks_per_tap / KCH;  // host guarantees divisibility
+  const int num_kb = p.num_taps * stages_per_tap;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&p.a_map[i]);
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     // ------------------------------------------------------------------ TMA producer (every CTA of the group)
     if (lane == 0) {
       const uint32_t a_box_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * CHUNK_BYTES;
-      const uint32_t tx_bytes = (a_box_bytes + Cfg::B_BYTES_RAW) * CTAS;  // bytes landing in ALL CTAs of the group
+      const uint32_t tx_bytes = (a_box_bytes + Cfg::B_BYTES_RAW) * CTAS * KCH;  // bytes landing in ALL CTAs of the group
       int stage = 0;
       uint32_t phase = 0;
       for (int work = group_id; work < total_work; work += num_groups) {
@@ -349,27 +356,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         const int bb = p.b_batched ? img0 : 0;
         const int b_row0 = nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.chunks_per_tap;
-          const int cc = kb - tap * p.chunks_per_tap;
+          const int tap = kb / stages_per_tap;
+          const int cc = (kb - tap * stages_per_tap) * KCH;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (p.debug_mode == 3) {
+          if (p.debug_mode & 4) {
             if (leader) mbar_arrive(&full_bar[stage]); else mbar_arrive_leader(&full_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          void* sa = smem_a + stage * Cfg::A_BYTES;
-          void* sb = smem_b + stage * Cfg::B_BYTES;
+          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
           const int k0 = tap * p.k_per_tap + cc * CH_ELEMS;
+          const CUtensorMap* amap = &p.a_map[p.tap_map[tap]];
+          const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
           if constexpr (CTAS == 2) {
             if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes); else mbar_arrive_leader(&full_bar[stage]);
-            tma2_load_4d(&p.a_map[p.tap_map[tap]], &full_bar[stage], sa, cc * CH_ELEMS, x0 + p.tap_dx[tap],
-                         y0 + p.tap_dy[tap], img0);
-            tma2_load_3d(&p.b_map, &full_bar[stage], sb, k0, b_row0, bb);
+#pragma unroll
+            for (int j = 0; j < KCH; ++j) {
+              tma2_load_4d(amap, &full_bar[stage], sa + j * Cfg::A_CHUNK_BYTES, (cc + j) * CH_ELEMS, ax, ay, img0);
+              tma2_load_3d(&p.b_map, &full_bar[stage], sb + j * Cfg::B_CHUNK_BYTES, k0 + j * CH_ELEMS, b_row0, bb);
+            }
           } else {
             mbar_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(&p.a_map[p.tap_map[tap]], &full_bar[stage], sa, cc * CH_ELEMS, x0 + p.tap_dx[tap],
-                        y0 + p.tap_dy[tap], img0);
-            tma_load_3d(&p.b_map, &full_bar[stage], sb, k0, b_row0, bb);
+#pragma unroll
+            for (int j = 0; j < KCH; ++j) {
+              tma_load_4d(amap, &full_bar[stage], sa + j * Cfg::A_CHUNK_BYTES, (cc + j) * CH_ELEMS, ax, ay, img0);
+              tma_load_3d(&p.b_map, &full_bar[stage], sb + j * Cfg::B_CHUNK_BYTES, k0 + j * CH_ELEMS, b_row0, bb);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -390,18 +403,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_smem_desc<CHUNK_BYTES>(smem_u32(smem_a + stage * Cfg::A_BYTES));
-          const uint64_t db = make_smem_desc<CHUNK_BYTES>(smem_u32(smem_b + stage * Cfg::B_BYTES));
 #pragma unroll
-          for (int k = 0; k < K_STEPS; ++k) {
-            if (p.debug_mode == 2) break;
-            // advance the 14-bit start-address field by k*32 bytes (>>4)
-            if constexpr (CTAS == 2)
-              tc2_mma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc,
-                          (kb | k) != 0 ? 1u : 0u);
-            else
-              tc_mma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+          for (int j = 0; j < KCH; ++j) {
+            const uint64_t da = make_smem_desc<CHUNK_BYTES>(smem_u32(smem_a + stage * Cfg::A_BYTES + j * Cfg::A_CHUNK_BYTES));
+            const uint64_t db = make_smem_desc<CHUNK_BYTES>(smem_u32(smem_b + stage * Cfg::B_BYTES + j * Cfg::B_CHUNK_BYTES));
+#pragma unroll
+            for (int k = 0; k < K_STEPS; ++k) {
+              if (p.debug_mode & 2) break;
+              // advance the 14-bit start-address field by k*32 bytes (>>4)
+              if constexpr (CTAS == 2)
+                tc2_mma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc,
+                            (kb | j | k) != 0 ? 1u : 0u);
+              else
+                tc_mma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc,
+                           (kb | j | k) != 0 ? 1u : 0u);
+            }
           }
           // frees the smem slot (in every CTA of the group) when these MMAs retire
           if constexpr (CTAS == 2) tc2_commit_mc(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
@@ -452,7 +468,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
-      if (has_cols && p.debug_mode != 1) {
+      if (has_cols && !(p.debug_mode & 1)) {
         constexpr int CW = BLOCK_N >= 32 ? 32 : 16;  // chunk width
 #pragma unroll 1
         for (int c = col_begin; c < col_begin + HALF_N; c += CW) {

@@ -22,7 +22,11 @@ SHAPES = [  # name, n, h, w, cin, cout, residual, gn
     ("dyn 16->128 @256", 64, 256, 256, 16, 128, False, True),
 ]
 modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["0", "1", "2", "3"])]
+ctas = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # bits: 1/2 = forced CTA group size, +4 = force 64-channel stages
+only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
 for name, n, h, w, cin, cout, res, gn in SHAPES:
+    if only and not any(name.startswith(o) for o in only):
+        continue
     x = torch.randn((n, h, w, cin), device=dev).bfloat16().permute(0, 3, 1, 2)
     wgt = (torch.randn(cout, cin, 3, 3, device=dev) / math.sqrt(9 * cin))
     wp = ops.pack_conv_weight(wgt, torch.bfloat16)
@@ -31,7 +35,7 @@ for name, n, h, w, cin, cout, res, gn in SHAPES:
     flops = 2.0 * n * h * w * cout * cin * 9
     line = f"{name:30s}"
     for mode in modes:
-        _C.lib().eovae_set_debug_mode(mode)
+        _C.lib().eovae_set_debug_mode(mode | (ctas << 8))
         for gflag in ((True, False) if (mode == 0 and gn) else (False,)):
             f = lambda: ops.conv2d(x, wp, bias, cout, ops.CONV_3X3, residual=r, gn_groups=32 if gflag else 0)
             for _ in range(2):

@@ -210,7 +210,18 @@ def run_ours(args):
             for family, flops, s, e in ops.PROFILE:
                 t, f, c = fam.get(family, (0.0, 0.0, 0))
                 fam[family] = (t + s.elapsed_time(e), f + flops, c + 1)
+            prof = ops.PROFILE
             ops.PROFILE = None
+            if os.environ.get("EOVAE_BENCH_DUMP"):
+                nsteps = min(args.steps, 5)
+                per = len(prof) // nsteps
+                rows = []
+                for i in range(per):
+                    ms = sum(prof[k * per + i][2].elapsed_time(prof[k * per + i][3]) for k in range(nsteps)) / nsteps
+                    rows.append({"i": i, "family": prof[i][0], "gflop": prof[i][1] / 1e9, "ms": ms,
+                                 "tflops": prof[i][1] / ms / 1e9})
+                with open(os.environ["EOVAE_BENCH_DUMP"], "w") as f:
+                    json.dump(rows, f, indent=1)
             peaks = load_peaks()
             t_ms = sum(v[0] for v in fam.values())
             flops = sum(v[1] for v in fam.values())

@@ -21,52 +21,69 @@ __global__ void sincos_kernel(const float* __restrict__ wvs_um, const float* __r
 }
 
 // Y[s][n] = act(sum_k X[s][k] * W[n][k] + b[n]) + R[s][n]
-constexpr int LBM = 32, LBN = 64, LBK = 16;
-__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
-                                                     const float* __restrict__ b, const float* __restrict__ r, int ldr,
-                                                     float* __restrict__ y, int ldy, int s, int n, int k, int act) {
-  __shared__ float xs[LBK][LBM + 1];
-  __shared__ float ws[LBK][LBN + 1];
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // 16 x 16 threads -> 4 cols x 2 rows each
+// Skinny GEMM (s <= 142 rows): 64 x 64 output tiles, 4 x 4 outputs per thread, K split across blockIdx.z so that
+// even the N = 256 layers fill the 148 SMs; split partials go to a workspace and are reduced in FIXED order by
+// linear_reduce_kernel (deterministic - no atomics), which also applies bias / activation / residual.
+constexpr int LBM = 64, LBN = 64, LBK = 16;
+__global__ void __launch_bounds__(256) linear_partial_kernel(const float* __restrict__ x, int ldx,
+                                                             const float* __restrict__ w, float* __restrict__ part,
+                                                             int s, int n, int k, int k_per_split) {
+  __shared__ float xs[LBK][LBM + 4];
+  __shared__ float ws[LBK][LBN + 4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int row0 = blockIdx.y * LBM, col0 = blockIdx.x * LBN;
-  float acc[2][4] = {};
-  for (int k0 = 0; k0 < k; k0 += LBK) {
-    for (int i = threadIdx.x; i < LBM * LBK; i += 256) {
-      const int rr = i / LBK, kk = i % LBK;
-      xs[kk][rr] = (row0 + rr < s && k0 + kk < k) ? x[static_cast<long long>(row0 + rr) * ldx + k0 + kk] : 0.f;
-    }
-    for (int i = threadIdx.x; i < LBN * LBK; i += 256) {
-      const int cc = i / LBK, kk = i % LBK;
-      ws[kk][cc] = (col0 + cc < n && k0 + kk < k) ? __ldg(&w[static_cast<long long>(col0 + cc) * k + k0 + kk]) : 0.f;
+  const int kb = blockIdx.z * k_per_split;
+  const int ke = min(k, kb + k_per_split);
+  float acc[4][4] = {};
+  for (int k0 = kb; k0 < ke; k0 += LBK) {
+    {  // 64 rows x 16 k: one float4 per thread for each operand
+      const int rr = threadIdx.x / 4, kk = (threadIdx.x % 4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + rr < s && k0 + kk < ke) v = *reinterpret_cast<const float4*>(&x[static_cast<long long>(row0 + rr) * ldx + k0 + kk]);
+      xs[kk][rr] = v.x; xs[kk + 1][rr] = v.y; xs[kk + 2][rr] = v.z; xs[kk + 3][rr] = v.w;
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col0 + rr < n && k0 + kk < ke) u = __ldg(reinterpret_cast<const float4*>(&w[static_cast<long long>(col0 + rr) * k + k0 + kk]));
+      ws[kk][rr] = u.x; ws[kk + 1][rr] = u.y; ws[kk + 2][rr] = u.z; ws[kk + 3][rr] = u.w;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < LBK; ++kk) {
-      const float a0 = xs[kk][ty * 2], a1 = xs[kk][ty * 2 + 1];
+      const float4 a = *reinterpret_cast<const float4*>(&xs[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&ws[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float bv = ws[kk][tx * 4 + j];
-        acc[0][j] = fmaf(a0, bv, acc[0][j]);
-        acc[1][j] = fmaf(a1, bv, acc[1][j]);
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
+  float* pz = part + static_cast<long long>(blockIdx.z) * s * n;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int rr = row0 + ty * 2 + i;
+  for (int i = 0; i < 4; ++i) {
+    const int rr = row0 + ty * 4 + i;
     if (rr >= s) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int cc = col0 + tx * 4 + j;
-      if (cc >= n) continue;
-      float v = acc[i][j] + (b != nullptr ? b[cc] : 0.f);
-      if (act == ACT_RELU) v = fmaxf(v, 0.f);
-      if (act == ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-      if (r != nullptr) v += r[static_cast<long long>(rr) * ldr + cc];
-      y[static_cast<long long>(rr) * ldy + cc] = v;
+      if (cc < n) pz[static_cast<long long>(rr) * n + cc] = acc[i][j];
     }
   }
+}
+
+__global__ void linear_reduce_kernel(const float* __restrict__ part, int splits, const float* __restrict__ b,
+                                     const float* __restrict__ r, int ldr, float* __restrict__ y, int ldy, int s, int n,
+                                     int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s * n) return;
+  const int rr = i / n, cc = i % n;
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += part[static_cast<long long>(z) * s * n + i];
+  if (b != nullptr) v += b[cc];
+  if (act == ACT_RELU) v = fmaxf(v, 0.f);
+  if (act == ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (r != nullptr) v += r[static_cast<long long>(rr) * ldr + cc];
+  y[static_cast<long long>(rr) * ldy + cc] = v;
 }
 
 // y[row] = LayerNorm(x[row]) * g + b ; one warp per row
@@ -136,10 +153,24 @@ __global__ void add_rows_kernel(const float* __restrict__ a, const float* __rest
   y[i] = a[i] + b[bcast ? (i % d) : i];
 }
 
+constexpr size_t kLinearPartFloats = static_cast<size_t>(32) * 192 * 2048;  // upper bound used by the workspace query
+
 int linear(const float* x, int ldx, const float* w, const float* b, const float* r, int ldr, float* y, int ldy, int s,
-           int n, int k, int act, cudaStream_t st) {
-  dim3 grid(ceil_div(n, LBN), ceil_div(s, LBM));
-  linear_kernel<<<grid, 256, 0, st>>>(x, ldx, w, b, r, ldr, y, ldy, s, n, k, act);
+           int n, int k, int act, float* part, cudaStream_t st) {
+  EOVAE_CHECK(k % 4 == 0 && ldx % 4 == 0, "hypernet linear: K and ldx must be multiples of 4");
+  const int tiles = ceil_div(n, LBN) * ceil_div(s, LBM);
+  int splits = ceil_div(2 * eovae_num_sms(), tiles);          // aim at ~2 blocks per SM
+  const int max_splits = ceil_div(k, 4 * LBK);                // at least 64 k per split
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 32) splits = 32;
+  if (splits < 1) splits = 1;
+  int kps = round_up(ceil_div(k, splits), LBK);
+  splits = ceil_div(k, kps);
+  EOVAE_CHECK(static_cast<size_t>(splits) * s * n <= kLinearPartFloats, "hypernet linear: partial buffer too small");
+  dim3 grid(ceil_div(n, LBN), ceil_div(s, LBM), splits);
+  linear_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, w, part, s, n, k, kps);
+  EOVAE_LAUNCH_CHECK();
+  linear_reduce_kernel<<<ceil_div(s * n, 256), 256, 0, st>>>(part, splits, b, r, ldr, y, ldy, s, n, act);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -151,7 +182,7 @@ extern "C" {
 size_t eovae_hypernet_workspace_bytes(int c, int d, int ff, int embed) {
   const size_t s = 128 + c + 1;
   (void)embed;
-  const size_t floats = 5 * static_cast<size_t>(c) * d + 3 * s * d + s * 3 * d + s * ff + 64;
+  const size_t floats = 5 * static_cast<size_t>(c) * d + 3 * s * d + s * 3 * d + s * ff + 64 + kLinearPartFloats;
   return floats * sizeof(float);
 }
 
@@ -177,6 +208,7 @@ int eovae_hypernet_forward(const float* wvs_um, int c, const float* const* param
   float* tmp = ws; ws += s * d;
   float* qkv = ws; ws += s * 3 * d;
   float* ffh = ws; ws += static_cast<size_t>(s) * ff;
+  float* part = ws;
   const float* omega = params[0];
   const float* wtok = params[1];
   const float* btok = params[2];
@@ -184,35 +216,35 @@ int eovae_hypernet_forward(const float* wvs_um, int c, const float* const* param
   sincos_kernel<<<ceil_div(c * d / 2, 128), 128, 0, st>>>(wvs_um, omega, emb, c, d);
   EOVAE_LAUNCH_CHECK();
   // FCResLayer: waves = emb + relu(W2 relu(W1 emb + b1) + b2)
-  if (linear(emb, d, params[3], params[4], nullptr, 0, t1, d, c, d, d, ACT_RELU, st)) return -1;
-  if (linear(t1, d, params[5], params[6], emb, d, waves, d, c, d, d, ACT_RELU, st)) return -1;
+  if (linear(emb, d, params[3], params[4], nullptr, 0, t1, d, c, d, d, ACT_RELU, part, st)) return -1;
+  if (linear(t1, d, params[5], params[6], emb, d, waves, d, c, d, d, ACT_RELU, part, st)) return -1;
   // token sequence [weight_tokens; waves; bias_token]
   EOVAE_CUDA(cudaMemcpyAsync(x, wtok, sizeof(float) * 128 * d, cudaMemcpyDeviceToDevice, st));
   EOVAE_CUDA(cudaMemcpyAsync(x + 128 * d, waves, sizeof(float) * c * d, cudaMemcpyDeviceToDevice, st));
   EOVAE_CUDA(cudaMemcpyAsync(x + (128 + c) * d, btok, sizeof(float) * d, cudaMemcpyDeviceToDevice, st));
   for (int l = 0; l < num_layers; ++l) {
     const float* const* lp = params + 11 + 12 * l;
-    if (linear(x, d, lp[0], lp[1], nullptr, 0, qkv, 3 * d, s, 3 * d, d, ACT_NONE, st)) return -1;
+    if (linear(x, d, lp[0], lp[1], nullptr, 0, qkv, 3 * d, s, 3 * d, d, ACT_NONE, part, st)) return -1;
     mha_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(qkv, att, s, d, heads);
     EOVAE_LAUNCH_CHECK();
-    if (linear(att, d, lp[2], lp[3], x, d, tmp, d, s, d, d, ACT_NONE, st)) return -1;
+    if (linear(att, d, lp[2], lp[3], x, d, tmp, d, s, d, d, ACT_NONE, part, st)) return -1;
     layernorm_kernel<<<ceil_div(s, 4), 128, 0, st>>>(tmp, lp[8], lp[9], x, s, d, 1e-5f);
     EOVAE_LAUNCH_CHECK();
-    if (linear(x, d, lp[4], lp[5], nullptr, 0, ffh, ff, s, ff, d, ACT_GELU, st)) return -1;
-    if (linear(ffh, ff, lp[6], lp[7], x, d, tmp, d, s, d, ff, ACT_NONE, st)) return -1;
+    if (linear(x, d, lp[4], lp[5], nullptr, 0, ffh, ff, s, ff, d, ACT_GELU, part, st)) return -1;
+    if (linear(ffh, ff, lp[6], lp[7], x, d, tmp, d, s, d, ff, ACT_NONE, part, st)) return -1;
     layernorm_kernel<<<ceil_div(s, 4), 128, 0, st>>>(tmp, lp[10], lp[11], x, s, d, 1e-5f);
     EOVAE_LAUNCH_CHECK();
   }
   // heads
   add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(x + 128 * d, waves, headin, c, d, 0);
   EOVAE_LAUNCH_CHECK();
-  if (linear(headin, d, params[7], params[8], nullptr, 0, wk_out, 9 * embed, c, 9 * embed, d, ACT_NONE, st)) return -1;
+  if (linear(headin, d, params[7], params[8], nullptr, 0, wk_out, 9 * embed, c, 9 * embed, d, ACT_NONE, part, st)) return -1;
   if (decoder) {
     add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(x + 128 * d, btok, headin2, c, d, 1);
     EOVAE_LAUNCH_CHECK();
-    if (linear(headin2, d, params[9], params[10], nullptr, 0, bias_out, 1, c, 1, d, ACT_NONE, st)) return -1;
+    if (linear(headin2, d, params[9], params[10], nullptr, 0, bias_out, 1, c, 1, d, ACT_NONE, part, st)) return -1;
   } else {
-    if (linear(x + (128 + c) * d, d, params[9], params[10], nullptr, 0, bias_out, embed, 1, embed, d, ACT_NONE, st)) return -1;
+    if (linear(x + (128 + c) * d, d, params[9], params[10], nullptr, 0, bias_out, embed, 1, embed, d, ACT_NONE, part, st)) return -1;
   }
   return 0;
 }

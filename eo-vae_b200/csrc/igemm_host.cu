@@ -155,7 +155,7 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
                  long long w_row_stride, long long w_batch_stride, int w_batches, const float* bias, const void* res, int res_dtype,
                  long long res_pix_stride, void* out, int out_dtype, long long out_pix_stride, int act_dtype,
                  float scale, cudaStream_t stream, float* gn_stats = nullptr, int gn_groups = 0, float gn_eps = 0.f,
-                 void* gn_ws = nullptr, size_t gn_ws_bytes = 0) {
+                 void* gn_ws = nullptr, size_t gn_ws_bytes = 0, const ASpec* extra = nullptr) {
   EOVAE_CHECK(act_dtype == EOVAE_BF16 || act_dtype == EOVAE_F16, "igemm: operand dtype must be bf16/f16");
   EOVAE_CHECK(chunk_bytes == 32 || chunk_bytes == 64 || chunk_bytes == 128, "igemm: bad chunk bytes %d", chunk_bytes);
   EOVAE_CHECK(a.pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ptr) % 16) == 0,
@@ -182,6 +182,16 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   p.tiles_n = ceil_div(a.N, p.box_n);
   p.chunks_per_tap = k_per_tap / ch;
   p.k_per_tap = k_per_tap;
+  int extra_k = 0;
+  if (extra != nullptr) {
+    EOVAE_CHECK(mode != EOVAE_CONV_3X3_S2, "igemm: a fused 1x1 operand needs a stride-1 convolution");
+    EOVAE_CHECK(extra->N == a.N && extra->H == a.H && extra->W == a.W, "igemm: fused 1x1 operand shape mismatch");
+    EOVAE_CHECK(extra->C % ch == 0 && extra->pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(extra->ptr) % 16) == 0,
+                "igemm: fused 1x1 operand must have a multiple of %d channels and 16-byte aligned pixels", ch);
+    p.extra_chunks = extra->C / ch;
+    p.extra_map = 1;
+    extra_k = extra->C;
+  }
   p.Wo = Wo;
   p.Ho = Ho;
   p.Nimg = a.N;
@@ -241,6 +251,15 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     int rc = encode_map(&p.a_map[0], act_dtype, 4, a.ptr, dims, strides, box, chunk_bytes);
     if (rc) return rc;
     p.a_map[1] = p.a_map[2] = p.a_map[3] = p.a_map[0];
+    if (extra != nullptr) {
+      uint64_t edims[4] = {static_cast<uint64_t>(extra->C), static_cast<uint64_t>(extra->W),
+                           static_cast<uint64_t>(extra->H), static_cast<uint64_t>(extra->N)};
+      uint64_t estr[3] = {static_cast<uint64_t>(extra->pix_stride) * es,
+                          static_cast<uint64_t>(extra->W) * extra->pix_stride * es,
+                          static_cast<uint64_t>(extra->H) * extra->W * extra->pix_stride * es};
+      rc = encode_map(&p.a_map[1], act_dtype, 4, extra->ptr, edims, estr, box, chunk_bytes);
+      if (rc) return rc;
+    }
     for (int t = 0; t < p.num_taps; ++t) {
       p.tap_map[t] = 0;
       p.tap_dy[t] = (mode == EOVAE_CONV_1X1) ? 0 : t / 3 - 1;
@@ -249,7 +268,7 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   }
   // --- B map: [batch][rows][K] K-major
   {
-    const uint64_t ktot = static_cast<uint64_t>(p.num_taps) * k_per_tap;
+    const uint64_t ktot = static_cast<uint64_t>(p.num_taps) * k_per_tap + extra_k;
     uint64_t dims[3] = {ktot, static_cast<uint64_t>(w_rows), static_cast<uint64_t>(w_batches)};
     uint64_t strides[2] = {static_cast<uint64_t>(w_row_stride) * es, static_cast<uint64_t>(w_batch_stride) * es};
     if (w_batches <= 1) strides[1] = static_cast<uint64_t>(w_row_stride) * static_cast<uint64_t>(w_rows) * es;
@@ -271,9 +290,14 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   }
   int rc;
   // two K-chunks (128 channels) per pipeline stage where the shapes allow >= 3 stages of shared memory
-  const bool kch2 = chunk_bytes == 128 && p.chunks_per_tap % 2 == 0 && !g_force_kch1 &&
+  const int k_items = p.num_taps * p.chunks_per_tap + p.extra_chunks;
+  const bool kch2 = chunk_bytes == 128 && k_items % 2 == 0 && !g_force_kch1 &&
                     (block_n == 128 || (block_n == 256 && ctas == 2));
-  if (kch2) {
+  // narrow-channel inputs (the dynamic input conv: 16 channels = one 32-byte chunk per tap): three taps per stage
+  const bool kch3 = chunk_bytes == 32 && k_items % 3 == 0 && !g_force_kch1 && block_n == 128 && ctas == 2;
+  if (kch3) {
+    rc = launch_t<128, 32, 2, 3>(p, total_tiles, stream);
+  } else if (kch2) {
     if (block_n == 128 && ctas == 2) rc = launch_t<128, 128, 2, 2>(p, total_tiles, stream);
     else if (block_n == 128) rc = launch_t<128, 128, 1, 2>(p, total_tiles, stream);
     else rc = launch_t<256, 128, 2, 2>(p, total_tiles, stream);
@@ -345,17 +369,23 @@ size_t eovae_conv2d_gn_workspace_bytes(int n, int h, int w, int mode, int cout, 
 int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_stride, int mode, const void* w_packed,
                  int cout, const float* bias, const void* residual, int res_dtype, long long res_pix_stride, void* out,
                  int out_dtype, long long out_pix_stride, int act_dtype, float scale, float* gn_stats, int gn_groups,
-                 float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, void* stream) {
+                 float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, const void* x2, int cin2,
+                 long long x2_pix_stride, void* stream) {
   EOVAE_CHECK(mode == EOVAE_CONV_3X3 || mode == EOVAE_CONV_1X1 || mode == EOVAE_CONV_3X3_S2, "conv2d: bad mode %d", mode);
   EOVAE_CHECK(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "conv2d: empty shape");
   EOVAE_CHECK(cin % 8 == 0, "conv2d: Cin (%d) must be a multiple of 8", cin);
   ASpec a{x, n, h, w, cin, x_pix_stride};
+  ASpec e{x2, n, h, w, cin2, x2_pix_stride};
   const int cb = eovae_conv_chunk_bytes(cin);
   const int kpt = eovae_conv_k_per_tap(cin);
+  const int taps = mode == EOVAE_CONV_1X1 ? 1 : 9;
+  if (x2 != nullptr)
+    EOVAE_CHECK(eovae_conv_chunk_bytes(cin2) == cb && eovae_conv_k_per_tap(cin2) == cin2,
+                "conv2d: fused 1x1 operand needs Cin2 (%d) compatible with the %d-byte K chunks of Cin (%d)", cin2, cb, cin);
   return launch_igemm(a, mode, w_packed, kpt, cb, cout, round_up(cout, 16),
-                      static_cast<long long>(mode == EOVAE_CONV_1X1 ? 1 : 9) * kpt, 0, 1, bias, residual, res_dtype,
+                      static_cast<long long>(taps) * kpt + (x2 != nullptr ? cin2 : 0), 0, 1, bias, residual, res_dtype,
                       res_pix_stride, out, out_dtype, out_pix_stride, act_dtype, scale, static_cast<cudaStream_t>(stream),
-                      gn_stats, gn_groups, gn_eps, gn_workspace, gn_workspace_bytes);
+                      gn_stats, gn_groups, gn_eps, gn_workspace, gn_workspace_bytes, x2 != nullptr ? &e : nullptr);
 }
 
 int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride, const void* b, long long ldb,

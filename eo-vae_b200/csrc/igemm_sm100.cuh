@@ -36,8 +36,10 @@ struct Params {
   int box_w, box_h, box_n;        // pixels per A box (box_w*box_h*box_n <= 128)
   int tiles_w, tiles_h, tiles_n;  // m-tile grid
   int n_tiles;                    // tiles along Cout
-  int num_taps, chunks_per_tap;   // K loop length = num_taps * chunks_per_tap
+  int num_taps, chunks_per_tap;   // main K items = num_taps * chunks_per_tap
   int k_per_tap;                  // padded channels per tap in the packed weight matrix
+  int extra_chunks;               // K items of a fused 1x1 operand read through a_map[extra_map] at the output pixel
+  int extra_map;                  //   (ResnetBlock nin_shortcut folded into conv2); its weights follow the taps in K
   int tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
   int Wo, Ho, Nimg;               // output extent
   int Cout;                       // valid output channels
@@ -305,8 +307,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   const int lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_work = ((m_tiles + CTAS - 1) / CTAS) * p.n_tiles;  // work item = CTAS adjacent m-tiles x one n-tile
-  const int stages_per_tap = p.chunks_per_tap / KCH;  // host guarantees divisibility
-  const int num_kb = p.num_taps * stages_per_tap;
+  const int main_items = p.num_taps * p.chunks_per_tap;
+  const int num_kb = (main_items + p.extra_chunks) / KCH;  // host guarantees divisibility
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&p.a_map[i]);
@@ -356,8 +358,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         const int bb = p.b_batched ? img0 : 0;
         const int b_row0 = nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / stages_per_tap;
-          const int cc = (kb - tap * stages_per_tap) * KCH;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p.debug_mode & 4) {
             if (leader) mbar_arrive(&full_bar[stage]); else mbar_arrive_leader(&full_bar[stage]);
@@ -366,22 +366,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
           }
           uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
-          const int k0 = tap * p.k_per_tap + cc * CH_ELEMS;
-          const CUtensorMap* amap = &p.a_map[p.tap_map[tap]];
-          const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
           if constexpr (CTAS == 2) {
             if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes); else mbar_arrive_leader(&full_bar[stage]);
-#pragma unroll
-            for (int j = 0; j < KCH; ++j) {
-              tma2_load_4d(amap, &full_bar[stage], sa + j * Cfg::A_CHUNK_BYTES, (cc + j) * CH_ELEMS, ax, ay, img0);
-              tma2_load_3d(&p.b_map, &full_bar[stage], sb + j * Cfg::B_CHUNK_BYTES, k0 + j * CH_ELEMS, b_row0, bb);
-            }
           } else {
             mbar_expect_tx(&full_bar[stage], tx_bytes);
+          }
 #pragma unroll
-            for (int j = 0; j < KCH; ++j) {
-              tma_load_4d(amap, &full_bar[stage], sa + j * Cfg::A_CHUNK_BYTES, (cc + j) * CH_ELEMS, ax, ay, img0);
-              tma_load_3d(&p.b_map, &full_bar[stage], sb + j * Cfg::B_CHUNK_BYTES, k0 + j * CH_ELEMS, b_row0, bb);
+          for (int j = 0; j < KCH; ++j) {
+            // K item -> (tensor map, pixel shift, channel chunk, weight column)
+            const int item = kb * KCH + j;
+            const CUtensorMap* amap;
+            int ax, ay, c0, k0;
+            if (item < main_items) {
+              const int tap = item / p.chunks_per_tap;
+              c0 = (item - tap * p.chunks_per_tap) * CH_ELEMS;
+              amap = &p.a_map[p.tap_map[tap]];
+              ax = x0 + p.tap_dx[tap];
+              ay = y0 + p.tap_dy[tap];
+              k0 = tap * p.k_per_tap + c0;
+            } else {
+              c0 = (item - main_items) * CH_ELEMS;
+              amap = &p.a_map[p.extra_map];
+              ax = x0;
+              ay = y0;
+              k0 = p.num_taps * p.k_per_tap + c0;
+            }
+            if constexpr (CTAS == 2) {
+              tma2_load_4d(amap, &full_bar[stage], sa + j * Cfg::A_CHUNK_BYTES, c0, ax, ay, img0);
+              tma2_load_3d(&p.b_map, &full_bar[stage], sb + j * Cfg::B_CHUNK_BYTES, k0, b_row0, bb);
+            } else {
+              tma_load_4d(amap, &full_bar[stage], sa + j * Cfg::A_CHUNK_BYTES, c0, ax, ay, img0);
+              tma_load_3d(&p.b_map, &full_bar[stage], sb + j * Cfg::B_CHUNK_BYTES, k0, b_row0, bb);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -464,12 +479,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + n_tile0 + col_begin) * esz;
         for (int b = 0; b < HALF_N * esz; b += 128) prefetch_l2(rp + b);
       }
+      constexpr int CW = BLOCK_N >= 32 ? 32 : 16;  // chunk width
+      // 16-bit residual rows travel through registers one chunk ahead of their use; the first chunk is requested
+      // here, before the wait for the accumulator, so its latency hides behind the mainloop
+      const bool res16 = has_res && p.res_dtype != EOVAE_F32;
+      const uint16_t* res_row = reinterpret_cast<const uint16_t*>(p.res) + pix * p.res_pix_stride;
+      uint4 r16[4], r16n[4];
+      if (res16 && valid && has_cols && n_tile0 + col_begin + CW <= p.Cout) {
+        const uint4* rp = reinterpret_cast<const uint4*>(res_row + n_tile0 + col_begin);
+#pragma unroll
+        for (int j = 0; j < CW / 8; ++j) r16[j] = __ldg(rp + j);
+      }
       epi_bar_sync();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
       if (has_cols && !(p.debug_mode & 1)) {
-        constexpr int CW = BLOCK_N >= 32 ? 32 : 16;  // chunk width
 #pragma unroll 1
         for (int c = col_begin; c < col_begin + HALF_N; c += CW) {
           uint32_t raw[32];
@@ -477,19 +502,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
           if constexpr (CW == 32) tc_ld16(taddr + c + 16, raw + 16);
           const int n0 = n_tile0 + c;
           const bool full = n0 + CW <= p.Cout;
-          // residual loads are issued before the TMEM wait so both latencies overlap
-          uint4 r16[4];
           float4 r32[8];
-          if (has_res && valid && full) {
-            if (p.res_dtype == EOVAE_F32) {
-              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + pix * p.res_pix_stride + n0);
+          if (has_res && valid && full && !res16) {
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + pix * p.res_pix_stride + n0);
 #pragma unroll
-              for (int j = 0; j < CW / 4; ++j) r32[j] = __ldg(rp + j);
-            } else {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res) + pix * p.res_pix_stride + n0);
+            for (int j = 0; j < CW / 4; ++j) r32[j] = __ldg(rp + j);
+          }
+          if (res16 && valid && c + CW < col_begin + HALF_N && n0 + 2 * CW <= p.Cout) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res_row + n0 + CW);
 #pragma unroll
-              for (int j = 0; j < CW / 8; ++j) r16[j] = __ldg(rp + j);
-            }
+            for (int j = 0; j < CW / 8; ++j) r16n[j] = __ldg(rp + j);
           }
           tc_wait_ld();
           float v[32];
@@ -578,6 +600,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
               }
             }
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r16[j] = r16n[j];
         }
       }
       tc_fence_before();

@@ -116,6 +116,20 @@ class ResnetBlock(nn.Module):
         self.conv2 = Conv2dSM100(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
         if self.in_channels != self.out_channels:
             self.nin_shortcut = Conv2dSM100(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
+        self._fused = None
+        self._fused_key = None
+
+    def _conv2_with_shortcut(self, dtype):
+        """conv2 and nin_shortcut as ONE implicit GEMM: [W2 | Wnin] along K, b2 + bnin (derived cache)."""
+        c2, sc = self.conv2, self.nin_shortcut
+        key = (c2.weight._version, c2.weight.data_ptr(), sc.weight._version, sc.weight.data_ptr(), c2.bias._version,
+               sc.bias._version, dtype)
+        if self._fused is None or self._fused_key != key:
+            w2, w1 = c2.packed_weight(dtype), sc.packed_weight(dtype)
+            w = torch.cat([w2.reshape(w2.shape[0], -1), w1.reshape(w1.shape[0], -1)], dim=1).contiguous()
+            b = (c2.bias.detach() + sc.bias.detach()).contiguous()
+            self._fused, self._fused_key = (w, b), key
+        return self._fused
 
     def forward(self, x: Tensor, emb: Tensor | None = None) -> Tensor:
         if self.cond_dim is not None and emb is not None:
@@ -123,8 +137,13 @@ class ResnetBlock(nn.Module):
         x = ops.to_act(x, compute_dtype())
         h = self.conv1(self.norm1(x, silu=True), gn_next=True)
         h = self.norm2(h, silu=True)
-        shortcut = self.nin_shortcut(x) if self.in_channels != self.out_channels else x
-        return self.conv2(h, residual=shortcut, gn_next=True)  # residual add + next GN's statistics in the epilogue
+        if self.in_channels == self.out_channels:
+            return self.conv2(h, residual=x, gn_next=True)  # residual add + next GN's statistics in the epilogue
+        if self.in_channels % 64 == 0 and self.out_channels % 64 == 0:
+            # 1x1 shortcut folded into conv2's K loop: no shortcut tensor is written or re-read
+            w, b = self._conv2_with_shortcut(x.dtype)
+            return ops.conv2d(h, w, b, self.out_channels, ops.CONV_3X3, gn_groups=32, gn_eps=1e-6, x2=x)
+        return self.conv2(h, residual=self.nin_shortcut(x), gn_next=True)
 
 
 class AttnBlock(nn.Module):

@@ -95,9 +95,11 @@ def pack_conv_weight(w: torch.Tensor, dtype) -> torch.Tensor:
 
 
 def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, residual=None, out_dtype=None,
-           scale: float = 1.0, algo_cin: int | None = None, gn_groups: int = 0, gn_eps: float = 1e-6) -> torch.Tensor:
+           scale: float = 1.0, algo_cin: int | None = None, gn_groups: int = 0, gn_eps: float = 1e-6,
+           x2: torch.Tensor | None = None) -> torch.Tensor:
     """out = scale * conv(x) + bias + residual.  With gn_groups > 0 the epilogue also produces the GroupNorm statistics
-    of the output; they ride along as ``out._gn_stats = (stats, groups, eps)`` for the next GroupNormSM100."""
+    of the output; they ride along as ``out._gn_stats = (stats, groups, eps)`` for the next GroupNormSM100.  ``x2``: a second
+    activation whose 1x1 convolution is accumulated in the same mainloop (weights appended along K in ``w_packed``)."""
     _need_cuda(x, w_packed, bias, residual)
     n, cin, h, w = x.shape
     ho, wo = (h, w) if mode != CONV_3X3_S2 else ((h - 2) // 2 + 1, (w - 2) // 2 + 1)
@@ -119,10 +121,17 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, 
             stats = torch.empty((n, gn_groups, 2), dtype=torch.float32, device=x.device)
             ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=x.device)
     flops = 2.0 * n * ho * wo * cout * (algo_cin or cin) * (1 if mode == CONV_1X1 else 9)
+    cin2, x2_ps = 0, 0
+    if x2 is not None:
+        _need_cuda(x2)
+        if x2.dtype != x.dtype or tuple(x2.shape[0:1] + x2.shape[2:]) != (n, h, w):
+            raise RuntimeError("eo_vae.conv2d: fused 1x1 operand must match the main input's batch / size / dtype")
+        cin2, x2_ps = x2.shape[1], pix_stride(x2)
+        flops += 2.0 * n * ho * wo * cout * cin2
     rc = _timed("conv", flops, lambda: _C.lib().eovae_conv2d(
         _ptr(x), n, h, w, cin, pix_stride(x), mode, _ptr(w_packed), cout, _ptr(bias), _ptr(residual), res_dt, res_ps,
         _ptr(out), DT[out_dtype], pix_stride(out), DT[x.dtype], float(scale), _ptr(stats), gn_groups, float(gn_eps),
-        _ptr(ws), ws_bytes, _stream()))
+        _ptr(ws), ws_bytes, _ptr(x2), cin2, x2_ps, _stream()))
     _C.check(rc, "eovae_conv2d")
     if stats is not None:
         out._gn_stats = (stats, gn_groups, float(gn_eps))

@@ -64,7 +64,12 @@ size_t eovae_conv2d_gn_workspace_bytes(int n, int h, int w, int mode, int cout, 
 int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_stride, int mode, const void* w_packed,
                  int cout, const float* bias, const void* residual, int res_dtype, long long res_pix_stride, void* out,
                  int out_dtype, long long out_pix_stride, int act_dtype, float scale, float* gn_stats, int gn_groups,
-                 float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, void* stream);
+                 float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, const void* x2, int cin2,
+                 long long x2_pix_stride, void* stream);
+/*      Optional fused 1x1 operand (x2 != NULL, stride-1 modes): out += conv1x1(x2, w2) computed in the SAME mainloop -
+ *      the ResnetBlock nin_shortcut (layers.py:85,111-112) folded into conv2.  w_packed then holds, per output row,
+ *      the taps*k_per_tap(cin) columns of the main kernel followed by cin2 columns of the 1x1 kernel, and `bias` the
+ *      sum of both biases.                                                                                           */
 
 /* ---- batched C[b] = scale * A[b] (m x k) * B[b]^T (n x k): the q k^T and p v products of AttnBlock
  *      (F.scaled_dot_product_attention, layers.py:134-141)                                                      */

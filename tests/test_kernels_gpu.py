@@ -109,6 +109,25 @@ def test_conv2d_fused_gn_stats(cuda, cta_group, n, h, w, cin, cout, mode):
     assert _rel(y, y_ref * torch.sigmoid(y_ref)) < 6e-3
 
 
+@pytest.mark.parametrize("n,h,w,cin2,c", [(2, 32, 32, 128, 256), (1, 64, 64, 256, 512), (3, 16, 16, 64, 128), (2, 8, 8, 64, 64)])
+def test_conv2d_fused_shortcut(cuda, cta_group, n, h, w, cin2, c):
+    """ResnetBlock tail as one implicit GEMM: conv3x3(h) + conv1x1(x) + biases (+ GroupNorm statistics)."""
+    from eo_vae import ops
+    hh = _act(n, c, h, w, cuda, seed=21)
+    x = _act(n, cin2, h, w, cuda, seed=22)
+    w3 = (torch.randn(c, c, 3, 3) / math.sqrt(9 * c)).to(cuda)
+    w1 = (torch.randn(c, cin2, 1, 1) / math.sqrt(cin2)).to(cuda)
+    b3, b1 = torch.randn(c).to(cuda), torch.randn(c).to(cuda)
+    p3, p1 = ops.pack_conv_weight(w3, torch.bfloat16), ops.pack_conv_weight(w1, torch.bfloat16)
+    wf = torch.cat([p3.reshape(p3.shape[0], -1), p1.reshape(p1.shape[0], -1)], dim=1).contiguous()
+    out = ops.conv2d(hh, wf, (b3 + b1).contiguous(), c, ops.CONV_3X3, out_dtype=torch.float32, x2=x, gn_groups=32)
+    ref = F.conv2d(hh.float(), w3.bfloat16().float(), b3, padding=1) + F.conv2d(x.float(), w1.bfloat16().float(), b1)
+    assert _rel(out, ref) < 2e-5
+    if hasattr(out, "_gn_stats"):
+        rf = ref.reshape(n, 32, -1)
+        assert torch.allclose(out._gn_stats[0][..., 0], rf.mean(-1), atol=2e-4)
+
+
 def test_conv2d_fp16_operands(cuda):
     from eo_vae import ops
     x = _act(2, 64, 16, 16, cuda, dtype=torch.float16)

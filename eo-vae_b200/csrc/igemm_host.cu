@@ -11,6 +11,7 @@ namespace {
 int g_debug_mode = 0;
 int g_force_ctas = 0;  // 0 = auto, 1 / 2 = forced (tests, tools/igemm_bench.py)
 int g_force_kch1 = 0;  // 1 = always one K-chunk per stage
+int g_no_tma_store = 0;  // 1 = epilogue writes with per-thread 16-byte stores instead of bulk tensor stores
 
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -31,7 +32,7 @@ EncodeFn get_encode_fn() {
 
 // rank-`rank` tiled map over 16-bit elements; strides in BYTES for dims 1..rank-1.
 int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
-               const uint32_t* box, int chunk_bytes) {
+               const uint32_t* box, int chunk_bytes, bool promote = true) {
   EncodeFn fn = get_encode_fn();
   EOVAE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
   cuuint64_t gdim[5];
@@ -48,7 +49,8 @@ int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const ui
                                              : (chunk_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMapDataType dt = dtype == EOVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = fn(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promote ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     eovae::set_error(
         "cuTensorMapEncodeTiled failed (%d): rank %d base %p dims [%llu %llu %llu %llu] strides [%llu %llu %llu] box [%u %u %u %u] chunk %d",
@@ -276,6 +278,32 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     int rc = encode_map(&p.b_map, act_dtype, 3, w, dims, strides, bbox, chunk_bytes);
     if (rc) return rc;
   }
+  // --- output map for the TMA-store epilogue: each epilogue warp owns 32 consecutive tile rows; they must form a
+  //     rectangular (w, h, image) sub-box of the tile
+  if (out_dtype != EOVAE_F32 && block_n >= 32 && !g_no_tma_store) {
+    int sw = 0, sh = 0, sn = 0;
+    if (p.box_w >= 32) {
+      if (p.box_w % 32 == 0) { sw = 32; sh = 1; sn = 1; }
+    } else if (32 % p.box_w == 0) {
+      const int rows = 32 / p.box_w;
+      if (p.box_h >= rows) {
+        if (p.box_h % rows == 0) { sw = p.box_w; sh = rows; sn = 1; }
+      } else if (rows % p.box_h == 0 && p.box_n >= rows / p.box_h && p.box_n % (rows / p.box_h) == 0) {
+        sw = p.box_w; sh = p.box_h; sn = rows / p.box_h;
+      }
+    }
+    if ((p.box_w * p.box_h * p.box_n) % 32 != 0) sw = 0;  // every warp entirely inside or outside the pixel box
+    if (sw > 0) {
+      uint64_t odims[4] = {static_cast<uint64_t>(cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                           static_cast<uint64_t>(a.N)};
+      uint64_t ostr[3] = {static_cast<uint64_t>(out_pix_stride) * es, static_cast<uint64_t>(Wo) * out_pix_stride * es,
+                          static_cast<uint64_t>(Ho) * Wo * out_pix_stride * es};
+      const uint32_t obox[4] = {32u, static_cast<uint32_t>(sw), static_cast<uint32_t>(sh), static_cast<uint32_t>(sn)};
+      int rc0 = encode_map(&p.out_map, out_dtype, 4, out, odims, ostr, obox, 64, false);
+      if (rc0) return rc0;
+      p.out_tma = 1;
+    }
+  }
   const int total_tiles = ceil_div(m_tiles_total, ctas) * p.n_tiles;  // work items
   if (total_tiles == 0) return 0;
   if (gn_stats != nullptr) {
@@ -341,6 +369,7 @@ void eovae_set_debug_mode(int mode) {
   g_debug_mode = mode & 0xFF;       // low byte: pipeline actor switched off (igemm_sm100.cuh)
   g_force_ctas = (mode >> 8) & 3;   // bits 8-9: force 1- or 2-CTA groups (0 = automatic)
   g_force_kch1 = (mode >> 10) & 1;  // bit 10: force 64-channel pipeline stages
+  g_no_tma_store = (mode >> 11) & 1;  // bit 11: disable the TMA-store epilogue
 }
 
 int eovae_conv_chunk_bytes(int cin) {

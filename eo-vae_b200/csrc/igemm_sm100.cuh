@@ -59,6 +59,8 @@ struct Params {
   int gn_cpg;                     // channels per group (1, 2, 4, 8, 16 or 32)
   int gn_groups;                  // Cout / gn_cpg
   int debug_mode;                 // bit mask: 1 no epilogue work | 2 no MMA issue | 4 no TMA (tools/igemm_bench.py)
+  CUtensorMap out_map;            // 16-bit output, box = (32 channels, the 32 pixels of one epilogue warp), 64 B swizzle
+  int out_tma;                    // 1: epilogue stores through out_map (shared-memory staging + bulk tensor store)
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -186,9 +188,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the 256 epilogue threads only
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
-}
 
 // K-major operand tile in shared memory: rows of CHUNK_BYTES (32/64/128) bytes, hardware swizzle of the same
 // width, 8-row groups CHUNK_BYTES*8 apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell).
@@ -216,11 +215,13 @@ struct Config {
   static constexpr int B_CHUNK_BYTES = (B_BYTES_RAW + 1023) / 1024 * 1024;
   static constexpr int B_BYTES = B_CHUNK_BYTES * KCH;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * 2 * 32 * 64;  // per-warp double-buffered TMA-store staging
+  static constexpr int AUX_BYTES = 1024;                          // barriers + tmem slot (keeps the staging 1 KB aligned)
+  static constexpr int MAX_SMEM = 232448;                         // 227 KB per CTA on sm_100
+  static constexpr int BUDGET = MAX_SMEM - 1024 /*align slack*/ - AUX_BYTES - EPI_BYTES;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias, double buffered*/;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + AUX_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + AUX_BYTES + EPI_BYTES;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 };
 
@@ -301,7 +302,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][BLOCK_N]
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 1024;  // TMA-store staging: 8 warps x 2 x 2 KB, 1 KB aligned
+  constexpr int EPI_BUF_BYTES = 32 * 64;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -313,6 +315,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&p.a_map[i]);
     prefetch_tmap(&p.b_map);
+    if (p.out_tma) prefetch_tmap(&p.out_map);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], CTAS);   // one producer arrive per CTA of the group (the leader's copy is the live one)
       mbar_init(&empty_bar[i], 1);
@@ -446,8 +449,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     const int ew = warp - 2;
     const int sub = warp & 3;    // TMEM sub-partition this warp may access: lanes [32*sub, 32*sub+32)
     const int half = ew >> 2;    // which half of the tile's columns this warp owns
-    const int et = threadIdx.x - 64;  // 0..255
     constexpr int HALF_N = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;  // narrow tiles: only half 0 works
+    constexpr int CW = BLOCK_N >= 32 ? 32 : 16;                    // chunk width (columns per tcgen05.ld round)
     const bool has_cols = (BLOCK_N >= 64) || (half == 0);
     const int col_begin = (BLOCK_N >= 64) ? half * HALF_N : 0;
     const int row = sub * 32 + lane;
@@ -455,8 +458,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     const int wi = row % p.box_w;
     const int hi = (row / p.box_w) % p.box_h;
     const int ni = row / (p.box_w * p.box_h);
+    // first pixel of this warp's 32 rows inside the tile (origin of its TMA-store sub-box)
+    const int w_wi = (sub * 32) % p.box_w, w_hi = ((sub * 32) / p.box_w) % p.box_h, w_ni = (sub * 32) / (p.box_w * p.box_h);
     const bool out16 = p.out_dtype != EOVAE_F32;
+    const bool out_bf16 = p.out_dtype == EOVAE_BF16;
     const bool has_res = p.res != nullptr;
+    const bool res16 = has_res && p.res_dtype != EOVAE_F32;
+    const bool res_bf16 = p.res_dtype == EOVAE_BF16;
+    const bool use_tma_store = (CW == 32) && p.out_tma != 0;
+    uint8_t* stage_buf = epi_smem + ew * (2 * EPI_BUF_BYTES);  // two 32-row x 32-column 16-bit buffers per warp
+    int sbuf = 0;
     int it = 0;
     for (int work = group_id; work < total_work; work += num_groups, ++it) {
       const int acc = it & 1;
@@ -470,19 +481,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
       const bool valid = mt < m_tiles && row < box_pix && ox < p.Wo && oy < p.Ho && on < p.Nimg;
       const long long pix = (static_cast<long long>(on) * p.Ho + oy) * p.Wo + ox;
       const int n_tile0 = nt * BLOCK_N;
-      // stage this tile's bias in shared memory (double buffered by tile parity)
-      float* bs = bias_s + acc * BLOCK_N;
-      if (et < BLOCK_N) bs[et] = (p.bias != nullptr && n_tile0 + et < p.Cout) ? __ldg(p.bias + n_tile0 + et) : 0.f;
       // pull this thread's residual row segment into L2 while the mainloop of this tile is still running
       if (has_res && valid && has_cols) {
         const int esz = p.res_dtype == EOVAE_F32 ? 4 : 2;
         const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + n_tile0 + col_begin) * esz;
         for (int b = 0; b < HALF_N * esz; b += 128) prefetch_l2(rp + b);
       }
-      constexpr int CW = BLOCK_N >= 32 ? 32 : 16;  // chunk width
       // 16-bit residual rows travel through registers one chunk ahead of their use; the first chunk is requested
       // here, before the wait for the accumulator, so its latency hides behind the mainloop
-      const bool res16 = has_res && p.res_dtype != EOVAE_F32;
       const uint16_t* res_row = reinterpret_cast<const uint16_t*>(p.res) + pix * p.res_pix_stride;
       uint4 r16[4], r16n[4];
       if (res16 && valid && has_cols && n_tile0 + col_begin + CW <= p.Cout) {
@@ -490,7 +496,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < CW / 8; ++j) r16[j] = __ldg(rp + j);
       }
-      epi_bar_sync();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
@@ -502,6 +507,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
           if constexpr (CW == 32) tc_ld16(taddr + c + 16, raw + 16);
           const int n0 = n_tile0 + c;
           const bool full = n0 + CW <= p.Cout;
+          // bias: warp-uniform 16-byte loads (one L1 line per instruction), in flight together with the TMEM load
+          float4 bq[CW / 4];
+          if (p.bias != nullptr && full) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) bq[j] = __ldg(bp + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) {
+              bq[j].x = (p.bias != nullptr && n0 + 4 * j < p.Cout) ? __ldg(p.bias + n0 + 4 * j) : 0.f;
+              bq[j].y = (p.bias != nullptr && n0 + 4 * j + 1 < p.Cout) ? __ldg(p.bias + n0 + 4 * j + 1) : 0.f;
+              bq[j].z = (p.bias != nullptr && n0 + 4 * j + 2 < p.Cout) ? __ldg(p.bias + n0 + 4 * j + 2) : 0.f;
+              bq[j].w = (p.bias != nullptr && n0 + 4 * j + 3 < p.Cout) ? __ldg(p.bias + n0 + 4 * j + 3) : 0.f;
+            }
+          }
           float4 r32[8];
           if (has_res && valid && full && !res16) {
             const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + pix * p.res_pix_stride + n0);
@@ -515,14 +535,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
           }
           tc_wait_ld();
           float v[32];
-          const float4* b4 = reinterpret_cast<const float4*>(bs + c);
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) {
-            const float4 bq = b4[j];
-            v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), p.out_scale, bq.x);
-            v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), p.out_scale, bq.y);
-            v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), p.out_scale, bq.z);
-            v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), p.out_scale, bq.w);
+            v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), p.out_scale, bq[j].x);
+            v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), p.out_scale, bq[j].y);
+            v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), p.out_scale, bq[j].z);
+            v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), p.out_scale, bq[j].w);
           }
           if constexpr (CW == 16) {
 #pragma unroll
@@ -530,16 +548,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
           }
           if (has_res && valid) {
             if (full) {
-              if (p.res_dtype == EOVAE_F32) {
+              if (!res16) {
 #pragma unroll
                 for (int j = 0; j < CW / 4; ++j) {
                   v[4 * j] += r32[j].x; v[4 * j + 1] += r32[j].y; v[4 * j + 2] += r32[j].z; v[4 * j + 3] += r32[j].w;
                 }
+              } else if (res_bf16) {
+#pragma unroll
+                for (int j = 0; j < CW / 8; ++j) {
+                  const float2 a = T16<__nv_bfloat16>::to_f2(r16[j].x), b = T16<__nv_bfloat16>::to_f2(r16[j].y);
+                  const float2 cc = T16<__nv_bfloat16>::to_f2(r16[j].z), d = T16<__nv_bfloat16>::to_f2(r16[j].w);
+                  v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b.x; v[8 * j + 3] += b.y;
+                  v[8 * j + 4] += cc.x; v[8 * j + 5] += cc.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < CW / 8; ++j) {
-                  const float2 a = unpack16(r16[j].x, p.res_dtype), b = unpack16(r16[j].y, p.res_dtype);
-                  const float2 cc = unpack16(r16[j].z, p.res_dtype), d = unpack16(r16[j].w, p.res_dtype);
+                  const float2 a = T16<__half>::to_f2(r16[j].x), b = T16<__half>::to_f2(r16[j].y);
+                  const float2 cc = T16<__half>::to_f2(r16[j].z), d = T16<__half>::to_f2(r16[j].w);
                   v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b.x; v[8 * j + 3] += b.y;
                   v[8 * j + 4] += cc.x; v[8 * j + 5] += cc.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
                 }
@@ -555,31 +581,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
               }
             }
           }
-          if (valid && n0 < p.Cout) {
-            if (full) {
-              if (out16) {
-                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + pix * p.out_pix_stride + n0);
+          if (n0 < p.Cout) {
+            if (out16 && (use_tma_store || (valid && full))) {
+              uint32_t pk[CW / 2];
+              if (out_bf16) {
 #pragma unroll
-                for (int j = 0; j < CW / 8; ++j) {
-                  uint4 t;
-                  t.x = pack16(v[8 * j], v[8 * j + 1], p.out_dtype);
-                  t.y = pack16(v[8 * j + 2], v[8 * j + 3], p.out_dtype);
-                  t.z = pack16(v[8 * j + 4], v[8 * j + 5], p.out_dtype);
-                  t.w = pack16(v[8 * j + 6], v[8 * j + 7], p.out_dtype);
-                  o[j] = t;
+                for (int j = 0; j < CW / 2; ++j) pk[j] = T16<__nv_bfloat16>::from_f2(v[2 * j], v[2 * j + 1]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) pk[j] = T16<__half>::from_f2(v[2 * j], v[2 * j + 1]);
+              }
+              if (use_tma_store) {
+                if constexpr (CW == 32) {
+                  // 32 rows x 64 bytes, 64-byte swizzle (16-byte piece j of row r lives at piece j ^ ((r >> 1) & 3)):
+                  // conflict-free st.shared, then ONE bulk tensor store per warp and chunk - coalesced by the TMA
+                  // unit, clipped at the tensor bounds (ragged tiles, channel tails), asynchronous
+                  uint8_t* buf = stage_buf + sbuf * EPI_BUF_BYTES;
+                  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer's last store drained
+                  __syncwarp();
+                  const uint32_t rbase = smem_u32(buf) + lane * 64;
+                  const int sw = (lane >> 1) & 3;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((j ^ sw) << 4)), "r"(pk[4 * j]),
+                                 "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                                 : "memory");
+                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                  __syncwarp();
+                  if (lane == 0 && mt < m_tiles && sub * 32 < box_pix) {  // warps past the box hold no pixels
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                            reinterpret_cast<uint64_t>(&p.out_map)),
+                        "r"(smem_u32(buf)), "r"(n0), "r"(tw * p.box_w + w_wi), "r"(th * p.box_h + w_hi),
+                        "r"(tn * p.box_n + w_ni)
+                        : "memory");
+                  }
+                  if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                  sbuf ^= 1;
                 }
               } else {
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + pix * p.out_pix_stride + n0);
+#pragma unroll
+                for (int j = 0; j < CW / 8; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              }
+            } else if (valid) {
+              if (full) {  // fp32 output
                 float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + n0);
 #pragma unroll
                 for (int j = 0; j < CW / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              }
-            } else {
-              for (int j = 0; j < CW && n0 + j < p.Cout; ++j) {
-                if (out16)
-                  reinterpret_cast<uint16_t*>(p.out)[pix * p.out_pix_stride + n0 + j] =
-                      static_cast<uint16_t>(pack16(v[j], 0.f, p.out_dtype) & 0xFFFF);
-                else
-                  reinterpret_cast<float*>(p.out)[pix * p.out_pix_stride + n0 + j] = v[j];
+              } else {
+                for (int j = 0; j < CW && n0 + j < p.Cout; ++j) {
+                  if (out16)
+                    reinterpret_cast<uint16_t*>(p.out)[pix * p.out_pix_stride + n0 + j] =
+                        static_cast<uint16_t>(pack16(v[j], 0.f, p.out_dtype) & 0xFFFF);
+                  else
+                    reinterpret_cast<float*>(p.out)[pix * p.out_pix_stride + n0 + j] = v[j];
+                }
               }
             }
           }
@@ -610,6 +667,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         if (leader) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_leader(&tmem_empty[acc]);
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp complete
   }
 
   tc_fence_before();

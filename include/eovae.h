@@ -44,7 +44,8 @@ int eovae_num_sms(void);
 unsigned long long eovae_launch_count(void);
 /* test / profiling aid: low byte = bit mask 1 skip epilogue work | 2 skip MMA issue | 4 skip TMA loads (these produce
  * garbage by design, tools/igemm_bench.py only); bits 8-9: 0 automatic | 1 force single-CTA | 2 force CTA-pair
- * (cta_group::2) implicit GEMM; bit 10: force one K-chunk per stage (tests run all).  The product path never sets it.                         */
+ * (cta_group::2) implicit GEMM; bit 10: force one K-chunk per stage; bit 11: per-thread stores instead of the TMA-store epilogue (tests run all).
+ * The product path never sets it.                         */
 void eovae_set_debug_mode(int mode);
 
 /* ---- weight packing (derived, non-persistent caches of the OIHW fp32 master parameters) -------------------- */

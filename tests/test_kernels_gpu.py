@@ -35,7 +35,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.fixture(params=[1, 2, 5, 6], ids=["1cta", "2cta", "1cta-k64", "2cta-k64"])
+@pytest.fixture(params=[1, 2, 5, 6, 10], ids=["1cta", "2cta", "1cta-k64", "2cta-k64", "2cta-stg"])
 def cta_group(request, cuda):
     """Run the implicit GEMM as single CTAs and as CTA pairs (tcgen05 cta_group::2); shapes that cannot pair fall
     back to single CTAs inside the library."""

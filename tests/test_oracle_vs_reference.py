@@ -1,0 +1,78 @@
+"""CPU suite, part 2 (build container only): the oracle and the drop-in package's checkpoint layout against the
+unmodified reference executed from /root/reference.  Skipped where the reference tree does not exist (GPU box)."""
+import pytest
+import torch
+
+from oracle import eovae_oracle as O
+from oracle import ref_shim
+from oracle.weights import FULL_CONFIG, TINY_CONFIG, WAVELENGTHS, make_state_dict, state_dict_spec, synthetic_patches
+
+pytestmark = pytest.mark.skipif(ref_shim.reference_root() is None, reason="reference tree not available")
+
+
+@pytest.mark.parametrize("cfg", [TINY_CONFIG, FULL_CONFIG], ids=["tiny", "full"])
+def test_state_dict_layout(cfg):
+    model = ref_shim.build_reference_model(cfg)
+    ref_sd = model.state_dict()
+    spec = state_dict_spec(cfg)
+    assert list(ref_sd.keys()) == list(spec.keys())
+    for k, shape in spec.items():
+        assert tuple(ref_sd[k].shape) == tuple(shape), k
+
+
+@pytest.mark.parametrize("modality", ["S2RGB", "S1RTC", "S2L2A"])
+def test_oracle_equals_reference_live(modality):
+    cfg = TINY_CONFIG
+    sd = make_state_dict(cfg, 5)
+    model = ref_shim.build_reference_model(cfg, sd, train=False)
+    wvs = torch.tensor(WAVELENGTHS[modality])
+    x = synthetic_patches(2, len(wvs), 32, seed=77)
+    with torch.no_grad():
+        z_ref = model.encode_spatial_normalized(x, wvs)
+        r_ref = model.reconstruct(x, wvs)
+        post = model.encode(x, wvs)
+        z = O.encode_spatial_normalized(sd, x, wvs, cfg["hyper_heads"])
+        r = O.reconstruct(sd, x, wvs, cfg["hyper_heads"])
+        m = O.encoder_forward(sd, x, wvs, cfg["hyper_heads"])
+    assert torch.allclose(z, z_ref, atol=2e-5) and torch.allclose(r, r_ref, atol=5e-5)
+    assert torch.allclose(O.posterior_kl(m), post.kl(), rtol=1e-5)
+    assert torch.allclose(O.posterior(m)[1], post.logvar, atol=2e-5)
+
+
+def test_train_mode_forward_matches_reference():
+    """Sampled, train-mode forward (batch-statistics BN, inverse BN on running stats) with the noise passed in."""
+    cfg = TINY_CONFIG
+    sd = make_state_dict(cfg, 6)
+    model = ref_shim.build_reference_model(cfg, sd, train=True)
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"])
+    x = synthetic_patches(3, 12, 32, seed=78)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        recon_ref, post = model(x, wvs)          # draws eps with the CPU generator (distributions.py:44)
+        torch.manual_seed(123)
+        eps = torch.randn(post.mean.shape)
+        recon, _ = O.forward(sd, x, wvs, eps=eps, train=True, heads=cfg["hyper_heads"])
+    assert torch.allclose(recon, recon_ref, atol=1e-4)
+
+
+def test_dropin_package_has_reference_checkpoint_layout():
+    """eo_vae (this repo) registers exactly the reference's parameters/buffers: a reference checkpoint loads strictly."""
+    import __graft_entry__ as g
+    import sys
+    if g.PKG not in sys.path:
+        sys.path.insert(0, g.PKG)
+    from eo_vae.models import Decoder, Encoder, EOFluxVAE
+    cfg = TINY_CONFIG
+    dyn = dict(num_layers=cfg["hyper_layers"], wv_planes=cfg["wv_planes"], num_heads=cfg["hyper_heads"])
+    enc = Encoder(resolution=64, in_channels=3, ch=cfg["ch"], ch_mult=list(cfg["ch_mult"]), num_res_blocks=1,
+                  z_channels=cfg["z_channels"], use_dynamic_ops=True, dynamic_conv_kwargs=dict(dyn))
+    dec = Decoder(ch=cfg["ch"], out_ch=3, ch_mult=list(cfg["ch_mult"]), num_res_blocks=1, resolution=64,
+                  z_channels=cfg["z_channels"], use_dynamic_ops=True, dynamic_conv_kwargs=dict(dyn))
+    ours = EOFluxVAE(enc, dec, torch.nn.Identity(), freeze_body=False)
+    ref = ref_shim.build_reference_model(cfg, make_state_dict(cfg, 2))
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    # same trainable set after freezing the body (new_autoencoder.py:274-293)
+    frozen = EOFluxVAE(enc, dec, torch.nn.Identity(), freeze_body=True)
+    names = {n for n, p in frozen.named_parameters() if p.requires_grad}
+    assert names and all(n.startswith(("encoder.conv_in.", "decoder.conv_out.")) for n in names)

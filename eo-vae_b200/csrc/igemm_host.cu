@@ -12,6 +12,7 @@ int g_debug_mode = 0;
 int g_force_ctas = 0;  // 0 = auto, 1 / 2 = forced (tests, tools/igemm_bench.py)
 int g_force_kch1 = 0;  // 1 = always one K-chunk per stage
 int g_no_tma_store = 0;  // 1 = epilogue writes with per-thread 16-byte stores instead of bulk tensor stores
+int g_no_halo = 0;       // 1 = never use the halo-reuse mainloop
 
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -64,11 +65,11 @@ int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const ui
   return 0;
 }
 
-template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH = 1>
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH = 1, bool HALO = false>
 int launch_t(const igemm::Params& p, int total_work, cudaStream_t stream) {
-  using Cfg = igemm::Config<BLOCK_N, CHUNK_BYTES, CTAS, KCH>;
+  using Cfg = igemm::Config<BLOCK_N, CHUNK_BYTES, CTAS, KCH, HALO>;
   static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
-  auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES, CTAS, KCH>;
+  auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES, CTAS, KCH, HALO>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
     EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -323,7 +324,20 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
                     (block_n == 128 || (block_n == 256 && ctas == 2));
   // narrow-channel inputs (the dynamic input conv: 16 channels = one 32-byte chunk per tap): three taps per stage
   const bool kch3 = chunk_bytes == 32 && k_items % 3 == 0 && !g_force_kch1 && block_n == 128 && ctas == 2;
-  if (kch3) {
+  // halo reuse of the A tile across the three horizontal taps: m-tile = 128 consecutive pixels of one image row
+  const bool halo = mode == EOVAE_CONV_3X3 && chunk_bytes == 128 && ctas == 2 && p.extra_chunks == 0 && p.box_w == 128 &&
+                    p.box_h == 1 && p.box_n == 1 && (block_n == 128 || block_n == 256) && !g_no_halo;
+  if (halo) {
+    uint64_t dims[4] = {static_cast<uint64_t>(a.C), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
+                        static_cast<uint64_t>(a.N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(a.pix_stride) * es, static_cast<uint64_t>(a.W) * a.pix_stride * es,
+                           static_cast<uint64_t>(a.H) * a.W * a.pix_stride * es};
+    const uint32_t hbox[4] = {static_cast<uint32_t>(ch), static_cast<uint32_t>(igemm::HALO_ROWS), 1u, 1u};
+    rc = encode_map(&p.a_map[3], act_dtype, 4, a.ptr, dims, strides, hbox, chunk_bytes);
+    if (rc) return rc;
+    if (block_n == 128) rc = launch_t<128, 128, 2, 1, true>(p, total_tiles, stream);
+    else rc = launch_t<256, 128, 2, 1, true>(p, total_tiles, stream);
+  } else if (kch3) {
     rc = launch_t<128, 32, 2, 3>(p, total_tiles, stream);
   } else if (kch2) {
     if (block_n == 128 && ctas == 2) rc = launch_t<128, 128, 2, 2>(p, total_tiles, stream);
@@ -370,6 +384,7 @@ void eovae_set_debug_mode(int mode) {
   g_force_ctas = (mode >> 8) & 3;   // bits 8-9: force 1- or 2-CTA groups (0 = automatic)
   g_force_kch1 = (mode >> 10) & 1;  // bit 10: force 64-channel pipeline stages
   g_no_tma_store = (mode >> 11) & 1;  // bit 11: disable the TMA-store epilogue
+  g_no_halo = (mode >> 12) & 1;       // bit 12: disable the halo-reuse mainloop
 }
 
 int eovae_conv_chunk_bytes(int cin) {

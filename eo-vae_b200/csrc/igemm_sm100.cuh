@@ -192,9 +192,9 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // K-major operand tile in shared memory: rows of CHUNK_BYTES (32/64/128) bytes, hardware swizzle of the same
 // width, 8-row groups CHUNK_BYTES*8 apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell).
 template <int CHUNK_BYTES>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t base_offset = 0) {
   constexpr uint64_t layout = CHUNK_BYTES == 128 ? 2 : (CHUNK_BYTES == 64 ? 4 : 6);
-  uint64_t d = 0;
+  uint64_t d = static_cast<uint64_t>(base_offset & 7) << 49;        // matrix base offset  bits [49,52)
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);            // start address      bits [0,14)
   d |= static_cast<uint64_t>(1) << 16;                               // leading byte off.  bits [16,30) (unused for swizzled K-major)
   d |= static_cast<uint64_t>((CHUNK_BYTES * 8) >> 4) << 32;          // stride byte offset bits [32,46)
@@ -206,14 +206,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // KCH = K-chunks (of CHUNK_BYTES) per pipeline stage.  The single producer / MMA threads pay ~300 cycles of serial
 // latency per stage (mbarrier try_wait, tcgen05.commit, TMA issue): measured 0.65 ms of pure handshake on a 1.3 ms
 // 128->128 conv with 64-channel stages, so wide-channel layers use two chunks (K = 128) per stage.
-template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH>
+//
+// HALO (3x3 stride-1 convs whose m-tile is 128 consecutive pixels of ONE image row, 128-byte chunks): a stage holds
+// one (kernel row, 64-channel chunk): the input row segment is loaded ONCE with a one-pixel halo on each side (130
+// pixels) and the three horizontal taps are three UMMA views of the same shared-memory tile, shifted by one 128-byte
+// row each (descriptor start address + matrix base offset) - A traffic through L2 drops 3x.
+constexpr int HALO_ROWS = 130;
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH, bool HALO = false>
 struct Config {
-  static constexpr int A_CHUNK_BYTES = BLOCK_M * CHUNK_BYTES;
-  static constexpr int A_BYTES = A_CHUNK_BYTES * KCH;
+  static constexpr int A_CHUNK_BYTES = HALO ? ((HALO_ROWS * CHUNK_BYTES + 1023) / 1024 * 1024) : BLOCK_M * CHUNK_BYTES;
+  static constexpr int A_BYTES = A_CHUNK_BYTES * (HALO ? 1 : KCH);
   static constexpr int B_ROWS = BLOCK_N / CTAS;  // rows of the B tile staged by each CTA
   static constexpr int B_BYTES_RAW = B_ROWS * CHUNK_BYTES;
   static constexpr int B_CHUNK_BYTES = (B_BYTES_RAW + 1023) / 1024 * 1024;
-  static constexpr int B_BYTES = B_CHUNK_BYTES * KCH;
+  static constexpr int B_PER_STAGE = HALO ? 3 : KCH;
+  static constexpr int B_BYTES = B_CHUNK_BYTES * B_PER_STAGE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = NUM_EPI_WARPS * 2 * 32 * 64;  // per-warp double-buffered TMA-store staging
   static constexpr int AUX_BYTES = 1024;                          // barriers + tmem slot (keeps the staging 1 KB aligned)
@@ -281,9 +288,9 @@ __device__ __forceinline__ void gn_chunk(const float (&v)[32], int lane, float* 
   }
 }
 
-template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH>
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH, bool HALO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_constant__ Params p) {
-  using Cfg = Config<BLOCK_N, CHUNK_BYTES, CTAS, KCH>;
+  using Cfg = Config<BLOCK_N, CHUNK_BYTES, CTAS, KCH, HALO>;
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int group_id = CTAS == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -310,7 +317,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_work = ((m_tiles + CTAS - 1) / CTAS) * p.n_tiles;  // work item = CTAS adjacent m-tiles x one n-tile
   const int main_items = p.num_taps * p.chunks_per_tap;
-  const int num_kb = (main_items + p.extra_chunks) / KCH;  // host guarantees divisibility
+  // pipeline stages per tile; HALO: one stage per (kernel row, channel chunk), else KCH K-items per stage
+  const int num_kb = HALO ? 3 * p.chunks_per_tap : (main_items + p.extra_chunks) / KCH;  // host guarantees divisibility
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&p.a_map[i]);
@@ -348,7 +356,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     // ------------------------------------------------------------------ TMA producer (every CTA of the group)
     if (lane == 0) {
       const uint32_t a_box_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * CHUNK_BYTES;
-      const uint32_t tx_bytes = (a_box_bytes + Cfg::B_BYTES_RAW) * CTAS * KCH;  // bytes landing in ALL CTAs of the group
+      const uint32_t tx_bytes = HALO ? (HALO_ROWS * CHUNK_BYTES + 3 * Cfg::B_BYTES_RAW) * CTAS
+                                     : (a_box_bytes + Cfg::B_BYTES_RAW) * CTAS * KCH;  // bytes landing in ALL CTAs of the group
       int stage = 0;
       uint32_t phase = 0;
       for (int work = group_id; work < total_work; work += num_groups) {
@@ -373,6 +382,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
             if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes); else mbar_arrive_leader(&full_bar[stage]);
           } else {
             mbar_expect_tx(&full_bar[stage], tx_bytes);
+          }
+          if constexpr (HALO) {
+            const int kh = kb / p.chunks_per_tap;
+            const int c0 = (kb - kh * p.chunks_per_tap) * CH_ELEMS;
+            // one input row segment with its halo: pixels [x0 - 1, x0 + 128], row y0 + kh - 1 (OOB -> zeros)
+            tma2_load_4d(&p.a_map[3], &full_bar[stage], sa, c0, x0 - 1, y0 + kh - 1, img0);
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              tma2_load_3d(&p.b_map, &full_bar[stage], sb + kw * Cfg::B_CHUNK_BYTES, (kh * 3 + kw) * p.k_per_tap + c0,
+                           b_row0, bb);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
           }
 #pragma unroll
           for (int j = 0; j < KCH; ++j) {
@@ -421,6 +442,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if constexpr (HALO) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              // tap kw = the halo tile shifted by kw pixels = kw 128-byte rows.  The 128-byte swizzle is a function of
+              // the absolute shared-memory address bits (TMA wrote it that way), so a row-shifted start address needs
+              // NO matrix-base-offset (verified on B200: base offset = kw gives garbage, 0 is bit-exact)
+              const uint64_t da = make_smem_desc<CHUNK_BYTES>(smem_u32(smem_a + stage * Cfg::A_BYTES + kw * CHUNK_BYTES));
+              const uint64_t db = make_smem_desc<CHUNK_BYTES>(smem_u32(smem_b + stage * Cfg::B_BYTES + kw * Cfg::B_CHUNK_BYTES));
+#pragma unroll
+              for (int k = 0; k < K_STEPS; ++k) {
+                if (p.debug_mode & 2) break;
+                tc2_mma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc,
+                            (kb | kw | k) != 0 ? 1u : 0u);
+              }
+            }
+            tc2_commit_mc(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < KCH; ++j) {
             const uint64_t da = make_smem_desc<CHUNK_BYTES>(smem_u32(smem_a + stage * Cfg::A_BYTES + j * Cfg::A_CHUNK_BYTES));

@@ -32,10 +32,13 @@ CONV_CASES = [
     (2, 32, 32, 256, 512),
     (5, 4, 4, 64, 16),       # tiny maps, Cout 16
     (2, 16, 16, 8, 32),      # Cin below one K chunk (TMA channel OOB fill)
+    (1, 6, 128, 64, 128),    # m-tile = one image row: halo-reuse mainloop (three taps from one shared-memory tile)
+    (2, 4, 256, 128, 256),
+    (1, 3, 200, 64, 128),    # halo mainloop with a ragged right edge
 ]
 
 
-@pytest.fixture(params=[1, 2, 5, 6, 10], ids=["1cta", "2cta", "1cta-k64", "2cta-k64", "2cta-stg"])
+@pytest.fixture(params=[1, 2, 5, 6, 10, 18], ids=["1cta", "2cta", "1cta-k64", "2cta-k64", "2cta-stg", "2cta-nohalo"])
 def cta_group(request, cuda):
     """Run the implicit GEMM as single CTAs and as CTA pairs (tcgen05 cta_group::2); shapes that cannot pair fall
     back to single CTAs inside the library."""

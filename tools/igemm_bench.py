@@ -22,7 +22,7 @@ SHAPES = [  # name, n, h, w, cin, cout, residual, gn
     ("dyn 16->128 @256", 64, 256, 256, 16, 128, False, True),
 ]
 modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["0", "1", "2", "3"])]
-ctas = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # bits: 1/2 = forced CTA group size, +4 = force 64-channel stages
+ctas = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # bits: 1/2 = forced CTA group size, +4 = 64-channel stages, +8 = no TMA store, +16 = no halo
 only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
 for name, n, h, w, cin, cout, res, gn in SHAPES:
     if only and not any(name.startswith(o) for o in only):

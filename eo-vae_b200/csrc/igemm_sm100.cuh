@@ -530,18 +530,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
       // 16-bit residual rows travel through registers one chunk ahead of their use; the first chunk is requested
       // here, before the wait for the accumulator, so its latency hides behind the mainloop
       const uint16_t* res_row = reinterpret_cast<const uint16_t*>(p.res) + pix * p.res_pix_stride;
-      uint4 r16[4], r16n[4];
-      if (res16 && valid && has_cols && n_tile0 + col_begin + CW <= p.Cout) {
-        const uint4* rp = reinterpret_cast<const uint4*>(res_row + n_tile0 + col_begin);
+      uint4 rbuf_a[4], rbuf_b[4];
+      auto res_fetch = [&](uint4 (&rb)[4], int c) {  // residual columns [n_tile0 + c, + CW) of this thread's pixel
+        if (res16 && valid && c < col_begin + HALF_N && n_tile0 + c + CW <= p.Cout) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res_row + n_tile0 + c);
 #pragma unroll
-        for (int j = 0; j < CW / 8; ++j) r16[j] = __ldg(rp + j);
+          for (int j = 0; j < CW / 8; ++j) rb[j] = __ldg(rp + j);
+        }
+      };
+      if (has_cols) {
+        res_fetch(rbuf_a, col_begin);
+        res_fetch(rbuf_b, col_begin + CW);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
       if (has_cols && !(p.debug_mode & 1)) {
-#pragma unroll 1
-        for (int c = col_begin; c < col_begin + HALF_N; c += CW) {
+        auto process = [&](const int c, uint4 (&r16)[4]) {
           uint32_t raw[32];
           tc_ld16(taddr + c, raw);
           if constexpr (CW == 32) tc_ld16(taddr + c + 16, raw + 16);
@@ -562,17 +567,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
               bq[j].w = (p.bias != nullptr && n0 + 4 * j + 3 < p.Cout) ? __ldg(p.bias + n0 + 4 * j + 3) : 0.f;
             }
           }
-          float4 r32[8];
-          if (has_res && valid && full && !res16) {
-            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + pix * p.res_pix_stride + n0);
-#pragma unroll
-            for (int j = 0; j < CW / 4; ++j) r32[j] = __ldg(rp + j);
-          }
-          if (res16 && valid && c + CW < col_begin + HALF_N && n0 + 2 * CW <= p.Cout) {
-            const uint4* rp = reinterpret_cast<const uint4*>(res_row + n0 + CW);
-#pragma unroll
-            for (int j = 0; j < CW / 8; ++j) r16n[j] = __ldg(rp + j);
-          }
           tc_wait_ld();
           float v[32];
 #pragma unroll
@@ -587,13 +581,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
             for (int j = 16; j < 32; ++j) v[j] = 0.f;
           }
           if (has_res && valid) {
-            if (full) {
-              if (!res16) {
-#pragma unroll
-                for (int j = 0; j < CW / 4; ++j) {
-                  v[4 * j] += r32[j].x; v[4 * j + 1] += r32[j].y; v[4 * j + 2] += r32[j].z; v[4 * j + 3] += r32[j].w;
-                }
-              } else if (res_bf16) {
+            if (full && res16) {
+              if (res_bf16) {
 #pragma unroll
                 for (int j = 0; j < CW / 8; ++j) {
                   const float2 a = T16<__nv_bfloat16>::to_f2(r16[j].x), b = T16<__nv_bfloat16>::to_f2(r16[j].y);
@@ -697,8 +686,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
               }
             }
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) r16[j] = r16n[j];
+          res_fetch(r16, c + 2 * CW);  // this buffer's next use is two chunks ahead
+        };
+#pragma unroll 1
+        for (int c = col_begin; c < col_begin + HALF_N; c += 2 * CW) {
+          process(c, rbuf_a);
+          if (c + CW < col_begin + HALF_N) process(c + CW, rbuf_b);
         }
       }
       tc_fence_before();

@@ -109,22 +109,34 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const TI* __restri
   if (p1 > hw) p1 = hw;
   const TI* xb = x + (static_cast<long long>(n) * hw) * x_pix_stride + v * 8;
   TO* yb = y + (static_cast<long long>(n) * hw) * y_pix_stride + v * 8;
-  for (long long p = p0 + r; p < p1; p += rows) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + p * x_pix_stride));
-    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o[4];
+  // four independent 16-byte loads in flight per thread (the kernel is pure HBM streaming: 1 read + 1 write)
+  constexpr int UNROLL = 4;
+  for (long long p = p0 + r; p < p1; p += static_cast<long long>(rows) * UNROLL) {
+    uint4 u[UNROLL];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = T16<TI>::to_f2(w4[j]);
-      float h0 = fmaf(f.x, a[2 * j], b[2 * j]);
-      float h1 = fmaf(f.y, a[2 * j + 1], b[2 * j + 1]);
-      if (SILU) {
-        h0 = silu_f(h0);
-        h1 = silu_f(h1);
-      }
-      o[j] = T16<TO>::from_f2(h0, h1);
+    for (int k = 0; k < UNROLL; ++k) {
+      const long long pk = p + static_cast<long long>(k) * rows;
+      if (pk < p1) u[k] = __ldcs(reinterpret_cast<const uint4*>(xb + pk * x_pix_stride));
     }
-    *reinterpret_cast<uint4*>(yb + p * y_pix_stride) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) {
+      const long long pk = p + static_cast<long long>(k) * rows;
+      if (pk >= p1) break;
+      const uint32_t w4[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = T16<TI>::to_f2(w4[j]);
+        float h0 = fmaf(f.x, a[2 * j], b[2 * j]);
+        float h1 = fmaf(f.y, a[2 * j + 1], b[2 * j + 1]);
+        if (SILU) {
+          h0 = silu_f(h0);
+          h1 = silu_f(h1);
+        }
+        o[j] = T16<TO>::from_f2(h0, h1);
+      }
+      *reinterpret_cast<uint4*>(yb + pk * y_pix_stride) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 

@@ -13,6 +13,7 @@ from oracle.weights import FULL_CONFIG, WAVELENGTHS, make_state_dict  # noqa: E4
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+what = sys.argv[3] if len(sys.argv) > 3 else "encode"  # encode | reconstruct
 dev = torch.device("cuda:0")
 model = g._model(FULL_CONFIG, make_state_dict(FULL_CONFIG, 0), dev)
 wvs = torch.tensor(WAVELENGTHS["S2L2A"], device=dev)
@@ -22,7 +23,7 @@ with torch.no_grad():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        z = model.encode_spatial_normalized(x, wvs)
+        z = model.encode_spatial_normalized(x, wvs) if what == "encode" else model.reconstruct(x, wvs)
         e1.record()
         torch.cuda.synchronize()
-        print(f"step {i}: {e0.elapsed_time(e1):.3f} ms, latents {tuple(z.shape)} finite={bool(torch.isfinite(z).all())}")
+        print(f"step {i}: {e0.elapsed_time(e1):.3f} ms, {what} out {tuple(z.shape)} finite={bool(torch.isfinite(z).all())}")

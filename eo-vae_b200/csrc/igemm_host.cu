@@ -97,7 +97,7 @@ int launch_t(const igemm::Params& p, int total_work, cudaStream_t stream) {
 template <int CHUNK_BYTES, int CTAS>
 int launch_n(int block_n, const igemm::Params& p, int total_work, cudaStream_t stream) {
   switch (block_n) {
-    case 16: if constexpr (CTAS == 1) return launch_t<16, CHUNK_BYTES, 1>(p, total_work, stream); break;
+    case 16: return launch_t<16, CHUNK_BYTES, CTAS>(p, total_work, stream);
     case 32: return launch_t<32, CHUNK_BYTES, CTAS>(p, total_work, stream);
     case 64: return launch_t<64, CHUNK_BYTES, CTAS>(p, total_work, stream);
     case 128: return launch_t<128, CHUNK_BYTES, CTAS>(p, total_work, stream);
@@ -214,10 +214,10 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   // CTA pairs (cta_group::2, UMMA M = 256) whenever there are at least two m-tiles to pair; a batched B operand
   // additionally needs both tiles of a pair inside one image.
   const int m_tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
-  int ctas = (block_n >= 32 && m_tiles_total >= 2) ? 2 : 1;
+  int ctas = (m_tiles_total >= 2) ? 2 : 1;
   if (w_batches > 1 && (p.tiles_w * p.tiles_h) % 2 != 0) ctas = 1;
   if (g_force_ctas == 1) ctas = 1;
-  if (g_force_ctas == 2 && block_n >= 32 && !(w_batches > 1 && (p.tiles_w * p.tiles_h) % 2 != 0)) ctas = 2;
+  if (g_force_ctas == 2 && !(w_batches > 1 && (p.tiles_w * p.tiles_h) % 2 != 0)) ctas = 2;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B = bf16|f16, K-major both, N>>3, M>>4
   const uint32_t fmt = act_dtype == EOVAE_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) |
@@ -326,7 +326,7 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   const bool kch3 = chunk_bytes == 32 && k_items % 3 == 0 && !g_force_kch1 && block_n == 128 && ctas == 2;
   // halo reuse of the A tile across the three horizontal taps: m-tile = 128 consecutive pixels of one image row
   const bool halo = mode == EOVAE_CONV_3X3 && chunk_bytes == 128 && ctas == 2 && p.extra_chunks == 0 && p.box_w == 128 &&
-                    p.box_h == 1 && p.box_n == 1 && (block_n == 128 || block_n == 256) && !g_no_halo;
+                    p.box_h == 1 && p.box_n == 1 && (block_n == 16 || block_n == 128 || block_n == 256) && !g_no_halo;
   if (halo) {
     uint64_t dims[4] = {static_cast<uint64_t>(a.C), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
                         static_cast<uint64_t>(a.N)};
@@ -336,6 +336,7 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     rc = encode_map(&p.a_map[3], act_dtype, 4, a.ptr, dims, strides, hbox, chunk_bytes);
     if (rc) return rc;
     if (block_n == 128) rc = launch_t<128, 128, 2, 1, true>(p, total_tiles, stream);
+    else if (block_n == 16) rc = launch_t<16, 128, 2, 1, true>(p, total_tiles, stream);  // skinny-N: dynamic output conv
     else rc = launch_t<256, 128, 2, 1, true>(p, total_tiles, stream);
   } else if (kch3) {
     rc = launch_t<128, 32, 2, 3>(p, total_tiles, stream);

@@ -45,6 +45,8 @@ SIGNATURES = {
     "eovae_hypernet_forward": (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "eovae_pack_dyn_weight": (_i, [_vp, _i, _i, _i, _f, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp]),
     "eovae_l1_charbonnier": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _sz, _vp]),
+    "eovae_msssim_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "eovae_msssim": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

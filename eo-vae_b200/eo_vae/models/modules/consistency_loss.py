@@ -23,6 +23,17 @@ class CharbonnierLoss(nn.Module):
         return ops.l1_charbonnier(pred, target, self.eps)[1]
 
 
+class SSIMLoss(nn.Module):
+    """1 - MS-SSIM (data_range 6, 5 scales) on the fused per-scale kernels (reference :24-37 via torchmetrics)."""
+
+    def __init__(self, channels=12):
+        super().__init__()
+        self.data_range = 6.0
+
+    def forward(self, pred, target):
+        return 1.0 - ops.msssim(pred, target, self.data_range)[0][0]
+
+
 class EOConsistencyLoss(nn.Module):
     def __init__(self, pixel_weight: float = 1.0, rec_loss_type: str = 'l1', spectral_weight: float = 0.0,
                  spatial_weight: float = 0.0, freq_weight: float = 0.0, feature_weight: float = 0.0,
@@ -42,6 +53,7 @@ class EOConsistencyLoss(nn.Module):
         self.weights = {'pixel': pixel_weight, 'spectral': spectral_weight, 'spatial': spatial_weight,
                         'freq': freq_weight, 'feature': feature_weight, 'msssim': msssim_weight}
         self.char_loss = CharbonnierLoss()
+        self.msssim_loss = SSIMLoss()
 
     def forward(self, inputs: torch.Tensor, wvs: torch.Tensor, reconstructions: torch.Tensor, global_step: int = 0,
                 split: str = 'train', **kwargs):
@@ -53,6 +65,8 @@ class EOConsistencyLoss(nn.Module):
             total = total + self.weights['pixel'] * l_rec
             logs[f'{split}/loss_rec'] = l_rec.detach()
         if self.weights['msssim'] > 0 and global_step >= self.starts['msssim']:
-            raise NotImplementedError('MS-SSIM kernel not built yet')
+            l_msssim = self.msssim_loss(reconstructions, inputs)
+            total = total + self.weights['msssim'] * l_msssim
+            logs[f'{split}/loss_msssim'] = l_msssim.detach()
         logs[f'{split}/loss_total'] = total.detach()
         return total, logs

@@ -301,6 +301,22 @@ def l1_charbonnier(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-3):
     return out
 
 
+def msssim(pred: torch.Tensor, target: torch.Tensor, data_range: float = 6.0):
+    """-> (mean MS-SSIM over the batch [1], per-sample MS-SSIM [B]); fp32 NCHW inputs."""
+    _need_cuda(pred, target)
+    pred = pred.to(torch.float32).contiguous()
+    target = target.to(torch.float32).contiguous()
+    b, c, h, w = pred.shape
+    lib = _C.lib()
+    ws_bytes = lib.eovae_msssim_workspace_bytes(b, c, h, w)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=pred.device)
+    out = torch.empty((1,), dtype=torch.float32, device=pred.device)
+    per = torch.empty((b,), dtype=torch.float32, device=pred.device)
+    _C.check(lib.eovae_msssim(_ptr(pred), _ptr(target), b, c, h, w, float(data_range), _ptr(out), _ptr(per), _ptr(ws),
+                              ws_bytes, _stream()), "eovae_msssim")
+    return out, per
+
+
 # ------------------------------------------------------------------------------------------------ hypernetwork
 def hypernet_forward(wvs: torch.Tensor, params: list, num_layers: int, d: int, heads: int, ff: int, embed: int,
                      decoder: bool):

@@ -139,6 +139,14 @@ int eovae_pack_dyn_weight(const float* wk, int c, int embed, int decoder, float 
 int eovae_l1_charbonnier(const float* a, const float* b, long long count, float eps, float* out, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* mean multi-scale SSIM over the batch (out[0]) and per sample (per_sample[b], may be NULL); pred, target fp32 NCHW
+ * [b][c][h][w], h and w multiples of 16 and >= 176; 5 scales, 11-tap sigma-1.5 Gaussian, reflect padding, relu
+ * normalisation, betas (0.0448, 0.2856, 0.3001, 0.2363, 0.1333): torchmetrics' algorithm as called by the reference
+ * (consistency_loss.py:24-37).  loss = 1 - out[0].                                                                  */
+size_t eovae_msssim_workspace_bytes(int b, int c, int h, int w);
+int eovae_msssim(const float* pred, const float* target, int b, int c, int h, int w, float data_range, float* out,
+                 float* per_sample, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

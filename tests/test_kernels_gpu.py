@@ -239,6 +239,33 @@ def test_pixel_losses(cuda):
     assert abs(float(out[1]) - float(torch.sqrt((a - b) ** 2 + 1e-6).mean())) < 1e-5
 
 
+@pytest.mark.parametrize("b,c,h,w", [(2, 12, 256, 256), (3, 2, 192, 176), (1, 3, 512, 256)])
+def test_msssim_and_consistency_loss(cuda, b, c, h, w):
+    """MS-SSIM kernels and the EOConsistencyLoss forward against the CPU oracle (1e-3 relative, BASELINE tolerance)."""
+    from eo_vae import ops
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from oracle import eovae_oracle as O
+    g = torch.Generator().manual_seed(b * h)
+    x = torch.randn((b, c, h, w), generator=g).clamp_(-2, 6)
+    r = x + 0.4 * torch.randn((b, c, h, w), generator=g)
+    ref = float(O.ms_ssim(r, x))
+    out, per = ops.msssim(r.to(cuda), x.to(cuda))
+    assert abs(float(out) - ref) / ref < 1e-4
+    assert per.shape == (b,) and abs(float(per.mean()) - ref) / ref < 1e-4
+    assert abs(float(ops.msssim(x.to(cuda), x.to(cuda))[0]) - 1.0) < 1e-5
+    for kind in ("l1", "char"):
+        loss = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type=kind, msssim_weight=1.0, msssim_start_step=0)
+        total, logs = loss(x.to(cuda), None, r.to(cuda), global_step=3, split="train")
+        t_ref, rec_ref, ms_ref = O.consistency_loss(x, r, kind, 1.0, 1.0, 3, 0)
+        assert abs(float(total) - float(t_ref)) / float(t_ref) < 1e-3
+        assert abs(float(logs["train/loss_rec"]) - float(rec_ref)) / float(rec_ref) < 1e-3
+        assert abs(float(logs["train/loss_msssim"]) - float(ms_ref)) / float(ms_ref) < 1e-3
+        assert set(logs) == {"train/loss_rec", "train/loss_msssim", "train/loss_total"}
+    gated = EOConsistencyLoss(pixel_weight=1.0, msssim_weight=1.0, msssim_start_step=2000)
+    _, logs = gated(x.to(cuda), None, r.to(cuda), global_step=10)
+    assert "train/loss_msssim" not in logs
+
+
 @pytest.mark.parametrize("modality", ["S2RGB", "S1RTC", "S2L2A", "S2L1C"])
 @pytest.mark.parametrize("cfg_name", ["tiny", "full"])
 def test_hypernet(cuda, modality, cfg_name):

@@ -112,3 +112,22 @@ def test_full_size_properties(cuda):
     assert torch.equal(z_all, z_again), "encode is not deterministic"
     assert torch.equal(z_all[2:3], z_one), "a patch's latent depends on its batch neighbours"
     assert torch.isfinite(z_all).all()
+
+
+def test_config5_512px_13band(cuda):
+    """BASELINE configs[4] shape: S2L1C 13-band 512x512 (attention over L = 4096 tokens), parity against the oracle."""
+    import __graft_entry__ as g
+    from oracle import eovae_oracle as O
+    from oracle.weights import FULL_CONFIG, WAVELENGTHS, make_state_dict, synthetic_patches
+    sd = make_state_dict(FULL_CONFIG, 1)
+    model = g._model(FULL_CONFIG, sd, cuda)
+    wvs = torch.tensor(WAVELENGTHS["S2L1C"])
+    x = synthetic_patches(2, 13, 512, seed=21)
+    with torch.no_grad():
+        z = model.encode_spatial_normalized(x.to(cuda), wvs.to(cuda))
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        z_ref = O.encode_spatial_normalized(sd, x[:1], wvs, FULL_CONFIG["hyper_heads"])
+    assert z.shape == (2, 32, 64, 64)
+    e = _rel(z[:1].cpu(), z_ref)
+    print(f"PARITY config5 512px bf16: latent {e:.3e}")
+    assert e < BOUNDS[torch.bfloat16][0]

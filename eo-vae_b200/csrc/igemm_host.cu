@@ -65,11 +65,11 @@ int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const ui
   return 0;
 }
 
-template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH = 1, bool HALO = false>
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH = 1, bool HALO = false, bool GNP = false>
 int launch_t(const igemm::Params& p, int total_work, cudaStream_t stream) {
   using Cfg = igemm::Config<BLOCK_N, CHUNK_BYTES, CTAS, KCH, HALO>;
   static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
-  auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES, CTAS, KCH, HALO>;
+  auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES, CTAS, KCH, HALO, GNP>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
     EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -79,7 +79,7 @@ int launch_t(const igemm::Params& p, int total_work, cudaStream_t stream) {
   const int groups = total_work < max_groups ? total_work : max_groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * CTAS);
-  cfg.blockDim = dim3(igemm::NUM_THREADS);
+  cfg.blockDim = dim3(GNP ? igemm::NUM_THREADS_GNP : igemm::NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -146,7 +146,27 @@ __global__ void gn_tiles_finalize_kernel(const float* __restrict__ partial, floa
   }
 }
 
+// per-(image, channel) affine of GroupNorm folded for the fused prologue: silu(z) = h + h * tanh(h), h = z / 2
+__global__ void gn_ab_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float2* __restrict__ ab, int c, int groups, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = i / c, ch = i % c;
+  const int g = ch / (c / groups);
+  const float mean = stats[(n * groups + g) * 2], rstd = stats[(n * groups + g) * 2 + 1];
+  const float a = gamma[ch] * rstd;
+  ab[i] = make_float2(0.5f * a, 0.5f * (beta[ch] - mean * a));
+}
+
 void m_tiling(int n, int ho, int wo, bool batched, int* bw, int* bh, int* bn);
+
+struct GnPrologue {  // GroupNorm(+SiLU) of the conv INPUT, applied inside the mainloop (halo kernels only)
+  const float* stats;
+  const float* gamma;
+  const float* beta;
+  int groups;
+  void* workspace;  // >= N * Cin * 8 bytes
+};
 
 struct ASpec {       // activation-side operand: NHWC tensor view
   const void* ptr;
@@ -158,7 +178,8 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
                  long long w_row_stride, long long w_batch_stride, int w_batches, const float* bias, const void* res, int res_dtype,
                  long long res_pix_stride, void* out, int out_dtype, long long out_pix_stride, int act_dtype,
                  float scale, cudaStream_t stream, float* gn_stats = nullptr, int gn_groups = 0, float gn_eps = 0.f,
-                 void* gn_ws = nullptr, size_t gn_ws_bytes = 0, const ASpec* extra = nullptr) {
+                 void* gn_ws = nullptr, size_t gn_ws_bytes = 0, const ASpec* extra = nullptr,
+                 const GnPrologue* gnp = nullptr) {
   EOVAE_CHECK(act_dtype == EOVAE_BF16 || act_dtype == EOVAE_F16, "igemm: operand dtype must be bf16/f16");
   EOVAE_CHECK(chunk_bytes == 32 || chunk_bytes == 64 || chunk_bytes == 128, "igemm: bad chunk bytes %d", chunk_bytes);
   EOVAE_CHECK(a.pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ptr) % 16) == 0,
@@ -327,6 +348,19 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   // halo reuse of the A tile across the three horizontal taps: m-tile = 128 consecutive pixels of one image row
   const bool halo = mode == EOVAE_CONV_3X3 && chunk_bytes == 128 && ctas == 2 && p.extra_chunks == 0 && p.box_w == 128 &&
                     p.box_h == 1 && p.box_n == 1 && (block_n == 16 || block_n == 128 || block_n == 256) && !g_no_halo;
+  EOVAE_CHECK(gnp == nullptr || (halo && block_n != 16 && a.C % 64 == 0 && a.C % gnp->groups == 0),
+              "igemm: fused GroupNorm prologue unsupported for this shape (query eovae_conv2d_gn_prologue_ok)");
+  if (gnp != nullptr) {
+    const int total = a.N * a.C;
+    gn_ab_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(gnp->stats, gnp->gamma, gnp->beta,
+                                                           static_cast<float2*>(gnp->workspace), a.C, gnp->groups, total);
+    EOVAE_LAUNCH_CHECK();
+    p.gnp_ab = static_cast<const float2*>(gnp->workspace);
+    p.gnp_cin = a.C;
+    p.gnp_h = a.H;
+    p.gnp_w = a.W;
+    p.gnp_bf16 = act_dtype == EOVAE_BF16;
+  }
   if (halo) {
     uint64_t dims[4] = {static_cast<uint64_t>(a.C), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
                         static_cast<uint64_t>(a.N)};
@@ -335,7 +369,9 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     const uint32_t hbox[4] = {static_cast<uint32_t>(ch), static_cast<uint32_t>(igemm::HALO_ROWS), 1u, 1u};
     rc = encode_map(&p.a_map[3], act_dtype, 4, a.ptr, dims, strides, hbox, chunk_bytes);
     if (rc) return rc;
-    if (block_n == 128) rc = launch_t<128, 128, 2, 1, true>(p, total_tiles, stream);
+    if (gnp != nullptr && block_n == 128) rc = launch_t<128, 128, 2, 1, true, true>(p, total_tiles, stream);
+    else if (gnp != nullptr) rc = launch_t<256, 128, 2, 1, true, true>(p, total_tiles, stream);
+    else if (block_n == 128) rc = launch_t<128, 128, 2, 1, true>(p, total_tiles, stream);
     else if (block_n == 16) rc = launch_t<16, 128, 2, 1, true>(p, total_tiles, stream);  // skinny-N: dynamic output conv
     else rc = launch_t<256, 128, 2, 1, true>(p, total_tiles, stream);
   } else if (kch3) {
@@ -411,11 +447,23 @@ size_t eovae_conv2d_gn_workspace_bytes(int n, int h, int w, int mode, int cout, 
   return sizeof(float) * 2 * 4 * static_cast<size_t>(ceil_div(wo, bw)) * ceil_div(ho, bh) * n * groups;
 }
 
+int eovae_conv2d_gn_prologue_ok(int n, int h, int w, int cin, int cout, int mode, int groups) {
+  if (mode != EOVAE_CONV_3X3 || g_no_halo || g_force_ctas == 1 || groups <= 0) return 0;
+  if (cin % 64 != 0 || cin % groups != 0) return 0;
+  int bw, bh, bn;
+  m_tiling(n, h, w, false, &bw, &bh, &bn);
+  if (bw != 128 || bh != 1 || bn != 1) return 0;
+  const int block_n = pick_block_n(round_up(cout, 16));
+  if (block_n != 128 && block_n != 256) return 0;
+  return ceil_div(w, bw) * h * n >= 2 ? 1 : 0;
+}
+
 int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_stride, int mode, const void* w_packed,
                  int cout, const float* bias, const void* residual, int res_dtype, long long res_pix_stride, void* out,
                  int out_dtype, long long out_pix_stride, int act_dtype, float scale, float* gn_stats, int gn_groups,
                  float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, const void* x2, int cin2,
-                 long long x2_pix_stride, void* stream) {
+                 long long x2_pix_stride, const float* in_gn_stats, const float* in_gn_gamma, const float* in_gn_beta,
+                 int in_gn_groups, void* in_gn_workspace, size_t in_gn_workspace_bytes, void* stream) {
   EOVAE_CHECK(mode == EOVAE_CONV_3X3 || mode == EOVAE_CONV_1X1 || mode == EOVAE_CONV_3X3_S2, "conv2d: bad mode %d", mode);
   EOVAE_CHECK(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "conv2d: empty shape");
   EOVAE_CHECK(cin % 8 == 0, "conv2d: Cin (%d) must be a multiple of 8", cin);
@@ -427,10 +475,19 @@ int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_st
   if (x2 != nullptr)
     EOVAE_CHECK(eovae_conv_chunk_bytes(cin2) == cb && eovae_conv_k_per_tap(cin2) == cin2,
                 "conv2d: fused 1x1 operand needs Cin2 (%d) compatible with the %d-byte K chunks of Cin (%d)", cin2, cb, cin);
+  GnPrologue gp{in_gn_stats, in_gn_gamma, in_gn_beta, in_gn_groups, in_gn_workspace};
+  if (in_gn_stats != nullptr) {
+    EOVAE_CHECK(x2 == nullptr, "conv2d: the fused GroupNorm prologue cannot be combined with a fused 1x1 operand");
+    EOVAE_CHECK(in_gn_gamma != nullptr && in_gn_beta != nullptr && in_gn_workspace != nullptr &&
+                    in_gn_workspace_bytes >= sizeof(float) * 2 * static_cast<size_t>(n) * cin,
+                "conv2d: GroupNorm prologue needs gamma, beta and a workspace of N*Cin*8 bytes");
+    EOVAE_CHECK(x_pix_stride == cin, "conv2d: GroupNorm prologue needs a dense NHWC input");
+  }
   return launch_igemm(a, mode, w_packed, kpt, cb, cout, round_up(cout, 16),
                       static_cast<long long>(taps) * kpt + (x2 != nullptr ? cin2 : 0), 0, 1, bias, residual, res_dtype,
                       res_pix_stride, out, out_dtype, out_pix_stride, act_dtype, scale, static_cast<cudaStream_t>(stream),
-                      gn_stats, gn_groups, gn_eps, gn_workspace, gn_workspace_bytes, x2 != nullptr ? &e : nullptr);
+                      gn_stats, gn_groups, gn_eps, gn_workspace, gn_workspace_bytes, x2 != nullptr ? &e : nullptr,
+                      in_gn_stats != nullptr ? &gp : nullptr);
 }
 
 int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride, const void* b, long long ldb,

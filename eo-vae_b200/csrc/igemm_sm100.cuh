@@ -28,6 +28,8 @@ namespace igemm {
 constexpr int BLOCK_M = 128;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+// GroupNorm-prologue variant: 4 warpgroups = {TMA, MMA, 2 idle} | 4 epilogue | 4 epilogue | 4 transform warps
+constexpr int NUM_THREADS_GNP = 512;
 constexpr int MAX_TAPS = 9;
 
 struct Params {
@@ -59,6 +61,11 @@ struct Params {
   int gn_cpg;                     // channels per group (1, 2, 4, 8, 16 or 32)
   int gn_groups;                  // Cout / gn_cpg
   int debug_mode;                 // bit mask: 1 no epilogue work | 2 no MMA issue | 4 no TMA (tools/igemm_bench.py)
+  // fused GroupNorm + SiLU of the INPUT (GNP kernels): A operand = silu(x * a[n][c] + b[n][c]), zero outside the image
+  const float2* gnp_ab;           // [Nimg][Cin] (0.5 * gamma * rstd, 0.5 * (beta - mean * gamma * rstd))
+  int gnp_cin;                    // channels of the input tensor
+  int gnp_h, gnp_w;               // input extent (padding mask)
+  int gnp_bf16;                   // activation element type of the A operand
   CUtensorMap out_map;            // 16-bit output, box = (32 channels, the 32 pixels of one epilogue warp), 64 B swizzle
   int out_tma;                    // 1: epilogue stores through out_map (shared-memory staging + bulk tensor store)
 };
@@ -288,9 +295,12 @@ __device__ __forceinline__ void gn_chunk(const float (&v)[32], int lane, float* 
   }
 }
 
-template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH, bool HALO = false>
-__global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_constant__ Params p) {
+template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH, bool HALO = false, bool GNP = false>
+__global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_kernel(const __grid_constant__ Params p) {
+  static_assert(!GNP || (HALO && CTAS == 2), "the GroupNorm prologue lives in the CTA-pair halo mainloop");
   using Cfg = Config<BLOCK_N, CHUNK_BYTES, CTAS, KCH, HALO>;
+  constexpr int EPI_WARP0 = GNP ? 4 : 2;   // first epilogue warp
+  constexpr int XF_WARP0 = 12;             // first transform warp (GNP)
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int group_id = CTAS == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -309,6 +319,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* a_full = bars + 2 * STAGES + 6;       // GNP: this CTA's raw A tile has landed (local)
+  uint64_t* ready_bar = bars + 3 * STAGES + 6;    // GNP: A tiles of the whole group are transformed (leader's copy)
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 1024;  // TMA-store staging: 8 warps x 2 x 2 KB, 1 KB aligned
   constexpr int EPI_BUF_BYTES = 32 * 64;
 
@@ -332,6 +344,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], NUM_EPI_WARPS * CTAS);  // one arrive per epilogue warp of every CTA of the group
     }
+    if constexpr (GNP) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&ready_bar[i], 4 * CTAS);  // one arrive per transform warp of every CTA of the group
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -352,6 +370,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // GNP: 512 threads start with 128 registers each; every warpgroup re-sizes its budget at the top of ITS branch
+  // (ptxas allocates registers per region dominated by a setmaxnreg): 56 | 184 | 184 | 88 = 512 * 128 / 128.
+  if (warp < EPI_WARP0) {
+  if constexpr (GNP) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (every CTA of the group)
     if (lane == 0) {
@@ -378,7 +400,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
           }
           uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
-          if constexpr (CTAS == 2) {
+          if constexpr (GNP) {
+            // raw A tile -> this CTA's own barrier (its transform warps wait there); B tiles -> the leader's barrier
+            mbar_expect_tx(&a_full[stage], HALO_ROWS * CHUNK_BYTES);
+            if (leader) mbar_expect_tx(&full_bar[stage], 3 * Cfg::B_BYTES_RAW * CTAS); else mbar_arrive_leader(&full_bar[stage]);
+          } else if constexpr (CTAS == 2) {
             if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes); else mbar_arrive_leader(&full_bar[stage]);
           } else {
             mbar_expect_tx(&full_bar[stage], tx_bytes);
@@ -387,7 +413,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
             const int kh = kb / p.chunks_per_tap;
             const int c0 = (kb - kh * p.chunks_per_tap) * CH_ELEMS;
             // one input row segment with its halo: pixels [x0 - 1, x0 + 128], row y0 + kh - 1 (OOB -> zeros)
-            tma2_load_4d(&p.a_map[3], &full_bar[stage], sa, c0, x0 - 1, y0 + kh - 1, img0);
+            if constexpr (GNP) tma_load_4d(&p.a_map[3], &a_full[stage], sa, c0, x0 - 1, y0 + kh - 1, img0);
+            else tma2_load_4d(&p.a_map[3], &full_bar[stage], sa, c0, x0 - 1, y0 + kh - 1, img0);
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
               tma2_load_3d(&p.b_map, &full_bar[stage], sb + kw * Cfg::B_CHUNK_BYTES, (kh * 3 + kw) * p.k_per_tap + c0,
@@ -441,6 +468,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if constexpr (GNP) mbar_wait(&ready_bar[stage], phase);
           tc_fence_after();
           if constexpr (HALO) {
 #pragma unroll
@@ -484,9 +512,72 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         if constexpr (CTAS == 2) tc2_commit_mc(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);  // accumulator complete
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps 2..9
-    const int ew = warp - 2;
+  }
+  } else if (GNP && warp >= XF_WARP0) {
+    // ------------------------------------------------------------------ transform warps (GroupNorm + SiLU prologue)
+    if constexpr (GNP) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // The raw halo tile is normalised IN PLACE before the MMA reads it: y = silu(x * a + b) per (image, channel),
+    // pixels outside the image stay zero (conv padding applies to the normalised tensor).  Each thread owns one
+    // 16-byte piece column (8 channels) and walks the 130 rows in steps of 16.
+    if constexpr (GNP) {
+      const int tl = threadIdx.x - XF_WARP0 * 32;  // 0..127
+      const int j = tl & 7, rg = tl >> 3;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = group_id; work < total_work; work += num_groups) {
+        const int mt = (work / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tn = mt / (p.tiles_w * p.tiles_h);
+        const int x0 = tw * p.box_w, y0 = th * p.box_h;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int kh = kb / p.chunks_per_tap;
+          const int c0 = (kb - kh * p.chunks_per_tap) * CH_ELEMS + j * 8;
+          const int y = y0 + kh - 1;
+          mbar_wait(&a_full[stage], phase);
+          if (mt < m_tiles && y >= 0 && y < p.gnp_h) {
+            const float4* abp = reinterpret_cast<const float4*>(p.gnp_ab + static_cast<long long>(tn) * p.gnp_cin + c0);
+            float ca[8], cb[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 f = __ldg(abp + q);
+              ca[2 * q] = f.x; cb[2 * q] = f.y; ca[2 * q + 1] = f.z; cb[2 * q + 1] = f.w;
+            }
+            const uint32_t tile = smem_u32(smem_a + stage * Cfg::A_BYTES);
+#pragma unroll 3
+            for (int r = rg; r < HALO_ROWS; r += 16) {
+              const int x = x0 - 1 + r;
+              if (x < 0 || x >= p.gnp_w) continue;
+              const uint32_t addr = tile + r * 128 + ((j ^ (r & 7)) << 4);
+              uint32_t v[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = p.gnp_bf16 ? T16<__nv_bfloat16>::to_f2(v[q]) : T16<__half>::to_f2(v[q]);
+                // silu(z) = z * sigmoid(z) = h + h * tanh(h) with h = z / 2 (the 1/2 is folded into a, b)
+                const float h0 = fmaf(f.x, ca[2 * q], cb[2 * q]), h1 = fmaf(f.y, ca[2 * q + 1], cb[2 * q + 1]);
+                float t0, t1;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                const float o0 = fmaf(h0, t0, h0), o1 = fmaf(h1, t1, h1);
+                v[q] = p.gnp_bf16 ? T16<__nv_bfloat16>::from_f2(o0, o1) : T16<__half>::from_f2(o0, o1);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(&ready_bar[stage]); else mbar_arrive_leader(&ready_bar[stage]);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + NUM_EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue warps
+    if constexpr (GNP) asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+    const int ew = warp - EPI_WARP0;
     const int sub = warp & 3;    // TMEM sub-partition this warp may access: lanes [32*sub, 32*sub+32)
     const int half = ew >> 2;    // which half of the tile's columns this warp owns
     constexpr int HALF_N = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;  // narrow tiles: only half 0 works

@@ -65,11 +65,26 @@ class Conv2dSM100(nn.Conv2d):
     def bias_f32(self):
         return None if self.bias is None else self.bias.detach()
 
-    def forward(self, x: Tensor, residual: Tensor | None = None, out_dtype=None, gn_next: bool = False) -> Tensor:  # noqa: D102
-        """gn_next: the output feeds a GroupNorm(32, eps 1e-6) next, so let the epilogue produce its statistics."""
+    def forward(self, x: Tensor, residual: Tensor | None = None, out_dtype=None, gn_next: bool = False,
+                pre_norm: 'GroupNormSM100 | None' = None) -> Tensor:  # noqa: D102
+        """gn_next: the output feeds a GroupNorm(32, eps 1e-6) next, so let the epilogue produce its statistics.
+        pre_norm: compute conv(silu(pre_norm(x))); the normalisation runs inside the conv's mainloop when the shape
+        allows it (no normalised tensor in HBM), otherwise as the separate GroupNorm-apply kernel."""
         x = ops.to_act(x, compute_dtype())
+        in_gn = None
+        if pre_norm is not None:
+            if ops.gn_prologue_ok(x, self.out_channels, self._mode, pre_norm.num_groups):
+                fused = getattr(x, "_gn_stats", None)
+                if fused is not None and fused[1] == pre_norm.num_groups and fused[2] == float(pre_norm.eps):
+                    stats = fused[0]
+                else:
+                    stats = ops.gn_stats(x, pre_norm.num_groups, pre_norm.eps)
+                in_gn = (stats, pre_norm.weight.detach(), pre_norm.bias.detach(), pre_norm.num_groups)
+            else:
+                x = pre_norm(x, silu=True)
         return ops.conv2d(x, self.packed_weight(x.dtype), self.bias_f32(), self.out_channels, self._mode,
-                          residual=residual, out_dtype=out_dtype, gn_groups=32 if gn_next else 0, gn_eps=1e-6)
+                          residual=residual, out_dtype=out_dtype, gn_groups=32 if gn_next else 0, gn_eps=1e-6,
+                          in_gn=in_gn)
 
 
 class Downsample(nn.Module):
@@ -135,10 +150,11 @@ class ResnetBlock(nn.Module):
         if self.cond_dim is not None and emb is not None:
             raise NotImplementedError("AdaIN-conditioned ResnetBlock (use_adain) is outside the built hot path")
         x = ops.to_act(x, compute_dtype())
-        h = self.conv1(self.norm1(x, silu=True), gn_next=True)
-        h = self.norm2(h, silu=True)
+        h = self.conv1(x, gn_next=True, pre_norm=self.norm1)  # GN1 + SiLU inside the conv where the shape allows
         if self.in_channels == self.out_channels:
-            return self.conv2(h, residual=x, gn_next=True)  # residual add + next GN's statistics in the epilogue
+            # GN2 + SiLU in the prologue, residual add + next GN's statistics in the epilogue
+            return self.conv2(h, residual=x, gn_next=True, pre_norm=self.norm2)
+        h = self.norm2(h, silu=True)
         if self.in_channels % 64 == 0 and self.out_channels % 64 == 0:
             # 1x1 shortcut folded into conv2's K loop: no shortcut tensor is written or re-read
             w, b = self._conv2_with_shortcut(x.dtype)

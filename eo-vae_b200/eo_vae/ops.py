@@ -96,10 +96,12 @@ def pack_conv_weight(w: torch.Tensor, dtype) -> torch.Tensor:
 
 def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, residual=None, out_dtype=None,
            scale: float = 1.0, algo_cin: int | None = None, gn_groups: int = 0, gn_eps: float = 1e-6,
-           x2: torch.Tensor | None = None) -> torch.Tensor:
+           x2: torch.Tensor | None = None, in_gn=None) -> torch.Tensor:
     """out = scale * conv(x) + bias + residual.  With gn_groups > 0 the epilogue also produces the GroupNorm statistics
     of the output; they ride along as ``out._gn_stats = (stats, groups, eps)`` for the next GroupNormSM100.  ``x2``: a second
-    activation whose 1x1 convolution is accumulated in the same mainloop (weights appended along K in ``w_packed``)."""
+    activation whose 1x1 convolution is accumulated in the same mainloop (weights appended along K in ``w_packed``).
+    ``in_gn = (stats, gamma, beta, groups)``: x is a RAW tensor and GroupNorm + SiLU is applied to the operand tiles
+    inside the mainloop (only where ``gn_prologue_ok`` says so)."""
     _need_cuda(x, w_packed, bias, residual)
     n, cin, h, w = x.shape
     ho, wo = (h, w) if mode != CONV_3X3_S2 else ((h - 2) // 2 + 1, (w - 2) // 2 + 1)
@@ -128,14 +130,27 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, 
             raise RuntimeError("eo_vae.conv2d: fused 1x1 operand must match the main input's batch / size / dtype")
         cin2, x2_ps = x2.shape[1], pix_stride(x2)
         flops += 2.0 * n * ho * wo * cout * cin2
+    g_stats = g_gamma = g_beta = g_ws = None
+    g_groups, g_ws_bytes = 0, 0
+    if in_gn is not None:
+        g_stats, g_gamma, g_beta, g_groups = in_gn
+        g_ws = torch.empty((n * cin * 2,), dtype=torch.float32, device=x.device)
+        g_ws_bytes = g_ws.numel() * 4
     rc = _timed("conv", flops, lambda: _C.lib().eovae_conv2d(
         _ptr(x), n, h, w, cin, pix_stride(x), mode, _ptr(w_packed), cout, _ptr(bias), _ptr(residual), res_dt, res_ps,
         _ptr(out), DT[out_dtype], pix_stride(out), DT[x.dtype], float(scale), _ptr(stats), gn_groups, float(gn_eps),
-        _ptr(ws), ws_bytes, _ptr(x2), cin2, x2_ps, _stream()))
+        _ptr(ws), ws_bytes, _ptr(x2), cin2, x2_ps, _ptr(g_stats), _ptr(g_gamma), _ptr(g_beta), g_groups, _ptr(g_ws),
+        g_ws_bytes, _stream()))
     _C.check(rc, "eovae_conv2d")
     if stats is not None:
         out._gn_stats = (stats, gn_groups, float(gn_eps))
     return out
+
+
+def gn_prologue_ok(x: torch.Tensor, cout: int, mode: int, groups: int = 32) -> bool:
+    """Can eovae_conv2d apply GroupNorm + SiLU to this input inside its mainloop?"""
+    n, cin, h, w = x.shape
+    return pix_stride(x) == cin and bool(_C.lib().eovae_conv2d_gn_prologue_ok(n, h, w, cin, cout, mode, groups))
 
 
 def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 1.0) -> torch.Tensor:

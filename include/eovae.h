@@ -62,12 +62,19 @@ int eovae_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, in
  *      tiny second kernel reduces them to gn_stats[n][gn_groups][2] = (mean, rstd).  eovae_conv2d_gn_workspace_bytes
  *      returns the workspace size, or 0 when the shape does not support the fusion (use eovae_gn_stats instead).     */
 size_t eovae_conv2d_gn_workspace_bytes(int n, int h, int w, int mode, int cout, int groups);
+int eovae_conv2d_gn_prologue_ok(int n, int h, int w, int cin, int cout, int mode, int groups);
 int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_stride, int mode, const void* w_packed,
                  int cout, const float* bias, const void* residual, int res_dtype, long long res_pix_stride, void* out,
                  int out_dtype, long long out_pix_stride, int act_dtype, float scale, float* gn_stats, int gn_groups,
                  float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, const void* x2, int cin2,
-                 long long x2_pix_stride, void* stream);
-/*      Optional fused 1x1 operand (x2 != NULL, stride-1 modes): out += conv1x1(x2, w2) computed in the SAME mainloop -
+                 long long x2_pix_stride, const float* in_gn_stats, const float* in_gn_gamma, const float* in_gn_beta,
+                 int in_gn_groups, void* in_gn_workspace, size_t in_gn_workspace_bytes, void* stream);
+/*      Optional fused GroupNorm + SiLU of the INPUT (in_gn_stats != NULL): x is the RAW tensor and the mainloop
+ *      normalises every operand tile in shared memory before the MMA reads it, i.e. out = conv(silu(GN(x))) without the
+ *      normalised tensor ever touching HBM (layers.py:93-95,106-108).  in_gn_stats = [n][groups][2] (mean, rstd) of x,
+ *      gamma / beta = the GroupNorm affine, workspace >= n*cin*8 bytes.  Only for shapes where
+ *      eovae_conv2d_gn_prologue_ok(...) returns 1 (3x3 stride 1, image rows of >= 128 pixels, Cin % 64 == 0).
+ *      Optional fused 1x1 operand (x2 != NULL, stride-1 modes): out += conv1x1(x2, w2) computed in the SAME mainloop -
  *      the ResnetBlock nin_shortcut (layers.py:85,111-112) folded into conv2.  w_packed then holds, per output row,
  *      the taps*k_per_tap(cin) columns of the main kernel followed by cin2 columns of the 1x1 kernel, and `bias` the
  *      sum of both biases.                                                                                           */

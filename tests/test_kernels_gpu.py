@@ -131,6 +131,36 @@ def test_conv2d_fused_shortcut(cuda, cta_group, n, h, w, cin2, c):
         assert torch.allclose(out._gn_stats[0][..., 0], rf.mean(-1), atol=2e-4)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 6, 128, 64, 128), (2, 5, 256, 128, 128), (2, 4, 128, 256, 256),
+                                            (1, 3, 200, 128, 256), (3, 2, 384, 64, 128)])
+def test_conv2d_gn_prologue(cuda, n, h, w, cin, cout, dtype):
+    """conv3x3(silu(GroupNorm(x))) with the normalisation applied to the operand tiles inside the mainloop (transform
+    warps) vs the fp32 statement and vs the unfused kernels; also with residual + next-GN statistics in the epilogue."""
+    from eo_vae import ops
+    x = (_act(n, cin, h, w, cuda, dtype=dtype, seed=31) * 2.5 + 0.7).contiguous(memory_format=torch.channels_last)
+    gamma = (1 + 0.2 * torch.randn(cin)).to(cuda)
+    beta = (0.3 * torch.randn(cin)).to(cuda)
+    wgt = (torch.randn(cout, cin, 3, 3) / math.sqrt(9 * cin)).to(cuda)
+    bias = torch.randn(cout).to(cuda)
+    wp = ops.pack_conv_weight(wgt, dtype)
+    assert ops.gn_prologue_ok(x, cout, ops.CONV_3X3)
+    stats = ops.gn_stats(x)
+    res = _act(n, cout, h, w, cuda, dtype=dtype, seed=32)
+    fused = ops.conv2d(x, wp, bias, cout, ops.CONV_3X3, residual=res, out_dtype=torch.float32, gn_groups=32,
+                       in_gn=(stats, gamma, beta, 32))
+    y = F.group_norm(x.float(), 32, gamma, beta, eps=1e-6)
+    y = (y * torch.sigmoid(y)).to(dtype).float()
+    ref = F.conv2d(y, wgt.to(dtype).float(), bias, padding=1) + res.float()
+    unfused = ops.conv2d(ops.gn_apply(x, stats, gamma, beta, True), wp, bias, cout, ops.CONV_3X3, residual=res,
+                         out_dtype=torch.float32)
+    tol = 3e-3 if dtype == torch.bfloat16 else 6e-4   # rounding of the normalised operand may differ by one ulp
+    assert _rel(fused, ref) < tol, _rel(fused, ref)
+    assert _rel(fused, unfused) < tol
+    rf = ref.reshape(n, 32, -1)
+    assert torch.allclose(fused._gn_stats[0][..., 0], rf.mean(-1), atol=3e-3)
+
+
 def test_conv2d_fp16_operands(cuda):
     from eo_vae import ops
     x = _act(2, 64, 16, 16, cuda, dtype=torch.float16)

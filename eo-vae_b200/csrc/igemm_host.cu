@@ -146,7 +146,7 @@ __global__ void gn_tiles_finalize_kernel(const float* __restrict__ partial, floa
   }
 }
 
-// per-(image, channel) affine of GroupNorm folded for the fused prologue: silu(z) = h + h * tanh(h), h = z / 2
+// per-(image, channel) affine of GroupNorm for the fused prologue: z = x * a + b
 __global__ void gn_ab_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float2* __restrict__ ab, int c, int groups, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,7 +155,7 @@ __global__ void gn_ab_kernel(const float* __restrict__ stats, const float* __res
   const int g = ch / (c / groups);
   const float mean = stats[(n * groups + g) * 2], rstd = stats[(n * groups + g) * 2 + 1];
   const float a = gamma[ch] * rstd;
-  ab[i] = make_float2(0.5f * a, 0.5f * (beta[ch] - mean * a));
+  ab[i] = make_float2(a, beta[ch] - mean * a);
 }
 
 void m_tiling(int n, int ho, int wo, bool batched, int* bw, int* bh, int* bn);

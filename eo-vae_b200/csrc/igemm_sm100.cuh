@@ -28,8 +28,9 @@ namespace igemm {
 constexpr int BLOCK_M = 128;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-// GroupNorm-prologue variant: 4 warpgroups = {TMA, MMA, 2 idle} | 4 epilogue | 4 epilogue | 4 transform warps
-constexpr int NUM_THREADS_GNP = 512;
+// GroupNorm-prologue variant: 5 warpgroups = {TMA, MMA, 2 idle} | 4 + 4 epilogue warps | 4 + 4 transform warps
+constexpr int NUM_XF_WARPS = 8;
+constexpr int NUM_THREADS_GNP = 128 + 32 * NUM_EPI_WARPS + 32 * NUM_XF_WARPS;
 constexpr int MAX_TAPS = 9;
 
 struct Params {
@@ -62,7 +63,7 @@ struct Params {
   int gn_groups;                  // Cout / gn_cpg
   int debug_mode;                 // bit mask: 1 no epilogue work | 2 no MMA issue | 4 no TMA (tools/igemm_bench.py)
   // fused GroupNorm + SiLU of the INPUT (GNP kernels): A operand = silu(x * a[n][c] + b[n][c]), zero outside the image
-  const float2* gnp_ab;           // [Nimg][Cin] (0.5 * gamma * rstd, 0.5 * (beta - mean * gamma * rstd))
+  const float2* gnp_ab;           // [Nimg][Cin] (gamma * rstd, beta - mean * gamma * rstd)
   int gnp_cin;                    // channels of the input tensor
   int gnp_h, gnp_w;               // input extent (padding mask)
   int gnp_bf16;                   // activation element type of the A operand
@@ -99,7 +100,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 21)) __trap();  // ~10 s of polling: far beyond any legitimate wait
   }
 }
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
     if constexpr (GNP) {
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(&a_full[i], 1);
-        mbar_init(&ready_bar[i], 4 * CTAS);  // one arrive per transform warp of every CTA of the group
+        mbar_init(&ready_bar[i], NUM_XF_WARPS * CTAS);  // one arrive per transform warp of every CTA of the group
       }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -370,10 +371,12 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // GNP: 512 threads start with 128 registers each; every warpgroup re-sizes its budget at the top of ITS branch
-  // (ptxas allocates registers per region dominated by a setmaxnreg): 56 | 184 | 184 | 88 = 512 * 128 / 128.
+  // GNP: 640 threads start with 96 registers each (61440 in the CTA's pool - setmaxnreg.inc can only take what the
+  // CTA's own warps released, so the new budgets must sum to <= 61440 or the kernel deadlocks); every warpgroup
+  // re-sizes at the top of ITS branch (ptxas allocates per region dominated by a setmaxnreg):
+  // 40 | 168 | 168 | 48 | 48 registers x 128 threads = 60416.
   if (warp < EPI_WARP0) {
-  if constexpr (GNP) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if constexpr (GNP) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (every CTA of the group)
     if (lane == 0) {
@@ -515,12 +518,16 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
   }
   } else if (GNP && warp >= XF_WARP0) {
     // ------------------------------------------------------------------ transform warps (GroupNorm + SiLU prologue)
-    if constexpr (GNP) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if constexpr (GNP) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    // STATUS: correct (tests/test_kernels_gpu.py::test_conv2d_gn_prologue) but NOT used by default: with the 48
+    // registers the CTA's register pool leaves them, the 8 transform warps reach an IPC of ~0.75 and need ~3400 cycles
+    // per (kernel row, chunk) stage against ~1150 cycles of MMA - the fused conv is 1.95 ms where gn_apply (0.41 ms,
+    // 80 % of HBM peak) + conv (1.10 ms) take 1.51 ms (profiles/r1_gn_prologue_experiment.md).
     // The raw halo tile is normalised IN PLACE before the MMA reads it: y = silu(x * a + b) per (image, channel),
     // pixels outside the image stay zero (conv padding applies to the normalised tensor).  Each thread owns one
-    // 16-byte piece column (8 channels) and walks the 130 rows in steps of 16.
+    // 16-byte piece column (8 channels) and walks the 130 rows in steps of 32.
     if constexpr (GNP) {
-      const int tl = threadIdx.x - XF_WARP0 * 32;  // 0..127
+      const int tl = threadIdx.x - XF_WARP0 * 32;  // 0..255
       const int j = tl & 7, rg = tl >> 3;
       int stage = 0;
       uint32_t phase = 0;
@@ -535,7 +542,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
           const int c0 = (kb - kh * p.chunks_per_tap) * CH_ELEMS + j * 8;
           const int y = y0 + kh - 1;
           mbar_wait(&a_full[stage], phase);
-          if (mt < m_tiles && y >= 0 && y < p.gnp_h) {
+          if (mt < m_tiles && y >= 0 && y < p.gnp_h && !(p.debug_mode & 16)) {
             const float4* abp = reinterpret_cast<const float4*>(p.gnp_ab + static_cast<long long>(tn) * p.gnp_cin + c0);
             float ca[8], cb[8];
 #pragma unroll
@@ -544,8 +551,8 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
               ca[2 * q] = f.x; cb[2 * q] = f.y; ca[2 * q + 1] = f.z; cb[2 * q + 1] = f.w;
             }
             const uint32_t tile = smem_u32(smem_a + stage * Cfg::A_BYTES);
-#pragma unroll 3
-            for (int r = rg; r < HALO_ROWS; r += 16) {
+#pragma unroll 2
+            for (int r = rg; r < HALO_ROWS; r += 4 * NUM_XF_WARPS) {
               const int x = x0 - 1 + r;
               if (x < 0 || x >= p.gnp_w) continue;
               const uint32_t addr = tile + r * 128 + ((j ^ (r & 7)) << 4);
@@ -554,8 +561,9 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float2 f = p.gnp_bf16 ? T16<__nv_bfloat16>::to_f2(v[q]) : T16<__half>::to_f2(v[q]);
-                // silu(z) = z * sigmoid(z) = h + h * tanh(h) with h = z / 2 (the 1/2 is folded into a, b)
-                const float h0 = fmaf(f.x, ca[2 * q], cb[2 * q]), h1 = fmaf(f.y, ca[2 * q + 1], cb[2 * q + 1]);
+                // silu(z) = z * sigmoid(z) = h + h * tanh(h) with h = z / 2: one MUFU op per element (an
+                // ex2.f16x2 + 2 x rcp formulation measured 1.4x slower here)
+                const float h0 = 0.5f * fmaf(f.x, ca[2 * q], cb[2 * q]), h1 = 0.5f * fmaf(f.y, ca[2 * q + 1], cb[2 * q + 1]);
                 float t0, t1;
                 asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
                 asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
@@ -576,7 +584,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
     }
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + NUM_EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue warps
-    if constexpr (GNP) asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+    if constexpr (GNP) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int ew = warp - EPI_WARP0;
     const int sub = warp & 3;    // TMEM sub-partition this warp may access: lanes [32*sub, 32*sub+32)
     const int half = ew >> 2;    // which half of the tile's columns this warp owns

@@ -73,7 +73,7 @@ class Conv2dSM100(nn.Conv2d):
         x = ops.to_act(x, compute_dtype())
         in_gn = None
         if pre_norm is not None:
-            if ops.gn_prologue_ok(x, self.out_channels, self._mode, pre_norm.num_groups):
+            if ops.USE_GN_PROLOGUE and ops.gn_prologue_ok(x, self.out_channels, self._mode, pre_norm.num_groups):
                 fused = getattr(x, "_gn_stats", None)
                 if fused is not None and fused[1] == pre_norm.num_groups and fused[2] == float(pre_norm.eps):
                     stats = fused[0]

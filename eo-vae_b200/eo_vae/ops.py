@@ -147,6 +147,10 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, 
     return out
 
 
+# The in-mainloop GroupNorm prologue is correct but slower than gn_apply + conv on B200 (see igemm_sm100.cuh): opt-in.
+USE_GN_PROLOGUE = False
+
+
 def gn_prologue_ok(x: torch.Tensor, cout: int, mode: int, groups: int = 32) -> bool:
     """Can eovae_conv2d apply GroupNorm + SiLU to this input inside its mainloop?"""
     n, cin, h, w = x.shape

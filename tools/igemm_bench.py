@@ -34,6 +34,27 @@ for name, n, h, w, cin, cout, res, gn in SHAPES:
     r = torch.randn((n, h, w, cout), device=dev).bfloat16().permute(0, 3, 1, 2) if res else None
     flops = 2.0 * n * h * w * cout * cin * 9
     line = f"{name:30s}"
+    if os.environ.get("GNP") and ops.gn_prologue_ok(x, cout, ops.CONV_3X3):
+        st = ops.gn_stats(x)
+        gam, bet = torch.ones(cin, device=dev), torch.zeros(cin, device=dev)
+        dm = int(os.environ.get("GNP_DEBUG", "0"))
+        _C.lib().eovae_set_debug_mode(dm)
+        for label, fn in ((f"fused GN prologue dbg{dm}", lambda: ops.conv2d(x, wp, bias, cout, ops.CONV_3X3, residual=r, gn_groups=32, in_gn=(st, gam, bet, 32))),
+                          ("gn_apply + conv  ", lambda: ops.conv2d(ops.gn_apply(x, st, gam, bet, True), wp, bias, cout, ops.CONV_3X3, residual=r, gn_groups=32))):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            line += f" | {label} {ms:7.3f} ms {flops / ms / 1e9:7.1f} TF"
+        _C.lib().eovae_set_debug_mode(0)
+        print(line, flush=True)
+        continue
     for mode in modes:
         _C.lib().eovae_set_debug_mode(mode | (ctas << 8))
         for gflag in ((True, False) if (mode == 0 and gn) else (False,)):

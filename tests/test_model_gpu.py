@@ -131,3 +131,20 @@ def test_config5_512px_13band(cuda):
     e = _rel(z[:1].cpu(), z_ref)
     print(f"PARITY config5 512px bf16: latent {e:.3e}")
     assert e < BOUNDS[torch.bfloat16][0]
+
+
+def test_cuda_graph_replay_is_bit_identical(cuda):
+    """eo_vae.graphs.GraphedEncoder: the ~120 launches of an encode captured once, replayed with new inputs."""
+    import __graft_entry__ as g
+    from eo_vae.graphs import GraphedEncoder
+    from oracle.weights import FULL_CONFIG, WAVELENGTHS, make_state_dict, synthetic_patches
+    model = g._model(FULL_CONFIG, make_state_dict(FULL_CONFIG, 0), cuda)
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"]).to(cuda)
+    x1 = synthetic_patches(2, 12, 256, seed=31).to(cuda)
+    x2 = synthetic_patches(2, 12, 256, seed=32).to(cuda)
+    with torch.no_grad():
+        ref1 = model.encode_spatial_normalized(x1, wvs).clone()
+        ref2 = model.encode_spatial_normalized(x2, wvs).clone()
+        ge = GraphedEncoder(model, x1, wvs)
+        assert torch.equal(ge(x1), ref1)
+        assert torch.equal(ge(x2), ref2)

@@ -148,3 +148,25 @@ def test_cuda_graph_replay_is_bit_identical(cuda):
         ge = GraphedEncoder(model, x1, wvs)
         assert torch.equal(ge(x1), ref1)
         assert torch.equal(ge(x2), ref2)
+
+
+@pytest.mark.parametrize("modality,size,batch", [("S2RGB", 224, 1), ("S1RTC", 96, 3), ("S2L2A", 144, 2)])
+def test_forward_like_reference_test(cuda, modality, size, batch):
+    """The reference's own test (tests/test_model.py:19-27: x = randn(1, 3, 224, 224), recon.shape == x.shape) plus
+    numerical parity with the oracle, on sizes that are NOT multiples of the 128-pixel tile (ragged tiles)."""
+    import __graft_entry__ as g
+    from oracle import eovae_oracle as O
+    from oracle.weights import FULL_CONFIG, WAVELENGTHS, make_state_dict, synthetic_patches
+    sd = make_state_dict(FULL_CONFIG, 4)
+    model = g._model(FULL_CONFIG, sd, cuda)
+    wvs = torch.tensor(WAVELENGTHS[modality])
+    x = synthetic_patches(batch, len(wvs), size, seed=41)
+    with torch.no_grad():
+        recon, posterior = model(x.to(cuda), wvs.to(cuda), sample_posterior=False)
+        assert isinstance(recon, torch.Tensor) and recon.shape == x.shape
+        assert posterior.mean.shape == (batch, 32, size // 8, size // 8)
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        ref = O.reconstruct(sd, x, wvs, FULL_CONFIG["hyper_heads"])
+    e = _rel(recon.cpu(), ref)
+    print(f"PARITY forward {modality} {size}px bf16: recon {e:.3e}")
+    assert e < BOUNDS[torch.bfloat16][1]

@@ -215,11 +215,13 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 
 // ------------------------------------------------------------------------------------------------- softmax
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(128) softmax_rows_kernel(const TI* __restrict__ s, TO* __restrict__ p, int cols) {
+__global__ void __launch_bounds__(128) softmax_rows_kernel(const TI* __restrict__ s, TO* __restrict__ p, int cols,
+                                                           long long s_ld, long long p_ld) {
   constexpr int MAXV = 32;  // cached values per thread (cols <= 4096)
   const long long row = blockIdx.x;
-  const TI* sr = s + row * cols;
-  TO* pr = p + row * cols;
+  const TI* sr = s + row * s_ld;
+  TO* pr = p + row * p_ld;
+  for (long long cidx = cols + threadIdx.x; cidx < p_ld; cidx += 128) pr[cidx] = T16<TO>::from_f(0.f);  // K padding
   __shared__ float red[4];
   float v[MAXV];
   float m = -INFINITY;
@@ -265,12 +267,12 @@ __global__ void __launch_bounds__(128) softmax_rows_kernel(const TI* __restrict_
   }
 }
 
-__global__ void transpose16_kernel(const uint16_t* __restrict__ in, long long in_ld, uint16_t* __restrict__ out, int rows,
-                                   int cols) {
+__global__ void transpose16_kernel(const uint16_t* __restrict__ in, long long in_ld, uint16_t* __restrict__ out,
+                                   long long out_ld, int rows, int cols) {
   __shared__ uint16_t tile[32][34];
   const long long b = blockIdx.z;
   const uint16_t* ib = in + b * rows * in_ld;
-  uint16_t* ob = out + b * static_cast<long long>(rows) * cols;
+  uint16_t* ob = out + b * static_cast<long long>(cols) * out_ld;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int r = r0 + j, cc = c0 + threadIdx.x;
@@ -279,7 +281,7 @@ __global__ void transpose16_kernel(const uint16_t* __restrict__ in, long long in
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int cc = c0 + j, r = r0 + threadIdx.x;
-    if (r < rows && cc < cols) ob[static_cast<long long>(cc) * rows + r] = tile[threadIdx.x][j];
+    if (cc < cols && r < out_ld) ob[static_cast<long long>(cc) * out_ld + r] = r < rows ? tile[threadIdx.x][j] : uint16_t(0);
   }
 }
 
@@ -503,11 +505,12 @@ int eovae_upsample2x(const void* x, void* out, int n, int h, int w, int c, void*
   return 0;
 }
 
-int eovae_softmax_rows(const void* s, int s_dtype, void* p, int p_dtype, long long rows, int cols, void* stream_) {
+int eovae_softmax_rows(const void* s, int s_dtype, long long s_ld, void* p, int p_dtype, long long p_ld, long long rows,
+                       int cols, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  EOVAE_CHECK(rows > 0 && cols > 0 && rows < (1LL << 31), "softmax_rows: bad shape");
+  EOVAE_CHECK(rows > 0 && cols > 0 && rows < (1LL << 31) && s_ld >= cols && p_ld >= cols, "softmax_rows: bad shape");
   const unsigned grid = static_cast<unsigned>(rows);
-#define EOVAE_SM(TI, TO) softmax_rows_kernel<TI, TO><<<grid, 128, 0, stream>>>(static_cast<const TI*>(s), static_cast<TO*>(p), cols)
+#define EOVAE_SM(TI, TO) softmax_rows_kernel<TI, TO><<<grid, 128, 0, stream>>>(static_cast<const TI*>(s), static_cast<TO*>(p), cols, s_ld, p_ld)
   if (s_dtype == EOVAE_F32 && p_dtype == EOVAE_BF16) EOVAE_SM(float, __nv_bfloat16);
   else if (s_dtype == EOVAE_F32 && p_dtype == EOVAE_F16) EOVAE_SM(float, __half);
   else if (s_dtype == EOVAE_BF16 && p_dtype == EOVAE_BF16) EOVAE_SM(__nv_bfloat16, __nv_bfloat16);
@@ -518,11 +521,13 @@ int eovae_softmax_rows(const void* s, int s_dtype, void* p, int p_dtype, long lo
   return 0;
 }
 
-int eovae_transpose16(const void* in, long long in_ld, void* out, int batch, int rows, int cols, void* stream_) {
+int eovae_transpose16(const void* in, long long in_ld, void* out, long long out_ld, int batch, int rows, int cols,
+                      void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), batch);
+  EOVAE_CHECK(out_ld >= rows && in_ld >= cols, "transpose16: pitches smaller than extents");
+  dim3 grid(ceil_div(cols, 32), ceil_div(static_cast<int>(out_ld), 32), batch);
   dim3 block(32, 8);
-  transpose16_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(in), in_ld, static_cast<uint16_t*>(out), rows, cols);
+  transpose16_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(in), in_ld, static_cast<uint16_t*>(out), out_ld, rows, cols);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

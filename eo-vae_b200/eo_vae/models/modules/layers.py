@@ -198,9 +198,10 @@ class AttnBlock(nn.Module):
         qkv = ops.conv2d(h, wqkv, bqkv, 3 * c, ops.CONV_1X1)  # NHWC [n, L, 3c]
         flat = qkv.permute(0, 2, 3, 1).reshape(n, L, 3 * c)     # view: pixel-major rows, pitch 3c
         q, k, v = flat[:, :, :c], flat[:, :, c:2 * c], flat[:, :, 2 * c:]
+        lp = (L + 15) // 16 * 16  # key extent padded to the MMA K step (zero probabilities / zero values)
         scores = ops.gemm_tn_batched(q, k, torch.float32, scale=1.0 / math.sqrt(c))  # [n, L, L] fp32
-        probs = ops.softmax_rows(scores, x.dtype)
-        vt = ops.transpose16(v)                                   # [n, c, L]
+        probs = ops.softmax_rows(scores, x.dtype, cols=L, out_cols=lp)               # [n, L, lp]
+        vt = ops.transpose16(v, out_rows=lp)                      # [n, c, lp]
         o = ops.gemm_tn_batched(probs, vt, x.dtype)               # [n, L, c]
         o = o.view(n, hh, ww, c).permute(0, 3, 1, 2)
         return self.proj_out(o, residual=x, gn_next=True)

@@ -339,6 +339,15 @@ class EOFluxVAE(LightningModule):
         return (optimizers, schedulers) if schedulers else optimizers
 
     def training_step(self, batch, batch_idx):
+        """Mirror of the reference step (:587-690): forward (sampled posterior) -> loss -> manual backward -> clip ->
+        Adam -> scheduler -> log.  The forward and loss kernels exist; the BACKWARD kernels (conv dgrad / wgrad,
+        GroupNorm, attention, hypernetwork, MS-SSIM adjoints) are not built yet, and this path never falls back to
+        torch autograd over library ops - so the step raises instead of silently training nothing."""
+        if not getattr(ops, "HAVE_BACKWARD", False):
+            raise NotImplementedError(
+                "EOFluxVAE.training_step: the sm_100a backward kernels are not part of this build (see DESIGN.md "
+                "section 7); inference paths (encode / decode / reconstruct / encode_spatial_normalized / "
+                "validation_step) are complete")
         opts = self.optimizers()
         opt_gen = opts[0] if isinstance(opts, list) else opts
         schs = self.lr_schedulers()

@@ -240,26 +240,32 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def softmax_rows(s: torch.Tensor, out_dtype) -> torch.Tensor:
+def softmax_rows(s: torch.Tensor, out_dtype, cols: int | None = None, out_cols: int | None = None) -> torch.Tensor:
+    """softmax over the first ``cols`` entries of every row of s [..., ld]; output [..., out_cols] with zeros beyond
+    ``cols`` (K padding for the following GEMM)."""
     _need_cuda(s)
     if not s.is_contiguous():
         raise RuntimeError("eo_vae.softmax_rows: contiguous input required")
-    cols = s.shape[-1]
-    rows = s.numel() // cols
-    p = torch.empty(s.shape, dtype=out_dtype, device=s.device)
-    _C.check(_C.lib().eovae_softmax_rows(_ptr(s), DT[s.dtype], _ptr(p), DT[out_dtype], rows, cols, _stream()),
-             "eovae_softmax_rows")
+    ld = s.shape[-1]
+    cols = cols or ld
+    out_cols = out_cols or cols
+    rows = s.numel() // ld
+    p = torch.empty(s.shape[:-1] + (out_cols,), dtype=out_dtype, device=s.device)
+    _C.check(_C.lib().eovae_softmax_rows(_ptr(s), DT[s.dtype], ld, _ptr(p), DT[out_dtype], out_cols, rows, cols,
+                                         _stream()), "eovae_softmax_rows")
     return p
 
 
-def transpose16(x: torch.Tensor) -> torch.Tensor:
-    """[B, R, C] (row pitch may exceed C) 16-bit -> dense [B, C, R]."""
+def transpose16(x: torch.Tensor, out_rows: int | None = None) -> torch.Tensor:
+    """[B, R, C] (row pitch may exceed C) 16-bit -> dense [B, C, out_rows >= R], zero padded."""
     _need_cuda(x)
     b, r, c = x.shape
+    out_rows = out_rows or r
     if x.stride(2) != 1 or x.stride(0) != r * x.stride(1) or x.element_size() != 2:
         raise RuntimeError("eo_vae.transpose16: bad layout")
-    out = torch.empty((b, c, r), dtype=x.dtype, device=x.device)
-    _C.check(_C.lib().eovae_transpose16(_ptr(x), x.stride(1), _ptr(out), b, r, c, _stream()), "eovae_transpose16")
+    out = torch.empty((b, c, out_rows), dtype=x.dtype, device=x.device)
+    _C.check(_C.lib().eovae_transpose16(_ptr(x), x.stride(1), _ptr(out), out_rows, b, r, c, _stream()),
+             "eovae_transpose16")
     return out
 
 

@@ -104,10 +104,13 @@ int eovae_nhwc_to_nchw_f32(const void* x, int x_dtype, long long x_pix_stride, f
                            void* stream);
 /* nearest-neighbour x2 upsample, NHWC 16-bit (F.interpolate, layers.py:48) */
 int eovae_upsample2x(const void* x, void* out, int n, int h, int w, int c, void* stream);
-/* row softmax: s [rows][cols] (fp32 or 16-bit) -> p 16-bit */
-int eovae_softmax_rows(const void* s, int s_dtype, void* p, int p_dtype, long long rows, int cols, void* stream);
-/* batched transpose of 16-bit matrices: in [batch][rows][in_ld>=cols] -> out [batch][cols][rows] */
-int eovae_transpose16(const void* in, long long in_ld, void* out, int batch, int rows, int cols, void* stream);
+/* row softmax: s [rows][s_ld >= cols] (fp32 or 16-bit) -> p [rows][p_ld >= cols] 16-bit, columns >= cols zeroed
+ * (lets the p*v GEMM run on a K extent padded to the 16-element MMA step) */
+int eovae_softmax_rows(const void* s, int s_dtype, long long s_ld, void* p, int p_dtype, long long p_ld, long long rows,
+                       int cols, void* stream);
+/* batched transpose of 16-bit matrices: in [batch][rows][in_ld>=cols] -> out [batch][cols][out_ld>=rows], zero padded */
+int eovae_transpose16(const void* in, long long in_ld, void* out, long long out_ld, int batch, int rows, int cols,
+                      void* stream);
 
 /* ---- posterior + latent glue (distributions.py:20-67, new_autoencoder.py:466-469,533-543,730-738) ------------ */
 /* moments fp32, logical [n][2*zc][h][w] with HOST array mstrides[4] = element strides (n, c, y, x)

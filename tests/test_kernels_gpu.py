@@ -219,6 +219,12 @@ def test_softmax_transpose_upsample(cuda):
     assert _rel(p, torch.softmax(s, -1)) < 4e-3
     s2 = torch.randn(2, 8, 5000, device=cuda)
     assert _rel(ops.softmax_rows(s2, torch.bfloat16), torch.softmax(s2, -1)) < 4e-3
+    s3 = torch.randn(2, 50, 324, device=cuda)
+    p3 = ops.softmax_rows(s3, torch.bfloat16, cols=324, out_cols=336)
+    assert p3.shape == (2, 50, 336) and float(p3[..., 324:].abs().max()) == 0.0
+    assert _rel(p3[..., :324], torch.softmax(s3, -1)) < 4e-3
+    vt = ops.transpose16(torch.randn(2, 324, 64, device=cuda).bfloat16(), out_rows=336)
+    assert vt.shape == (2, 64, 336) and float(vt[..., 324:].abs().max()) == 0.0
     t = torch.randn(3, 70, 96 * 3, device=cuda).bfloat16()
     v = t[:, :, 96:192]
     assert torch.equal(ops.transpose16(v), v.transpose(1, 2).contiguous())

@@ -1,0 +1,402 @@
+// Backward-pass kernels of the HBM-bound ops (first part of the training path): GroupNorm (+SiLU) backward,
+// stride-2 gradient scatter, 2x2 gradient pooling (nearest-upsample adjoint), per-channel bias gradient.
+// Data gradients of the convolutions reuse the implicit-GEMM kernel with transposed / flipped weight operands
+// (eovae_pack_conv_weight_dgrad); weight gradients are in wgrad_sm100.cu.
+#include "../../include/eovae.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float silu_grad(float z) {  // d/dz [z * sigmoid(z)]
+  const float s = 1.0f / (1.0f + __expf(-z));
+  return s * (1.0f + z * (1.0f - s));
+}
+
+// Pass 1: per (image, channel) sums  A = sum dz,  B = sum dz * xhat   with dz = g * silu'(z) (or g when !SILU),
+// z = xhat * gamma + beta, xhat = (x - mean) * rstd.  grid (blocks_per_image, n); fixed-slot partials (deterministic).
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ g,
+                                                                  const float* __restrict__ stats,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, long long hw, int c,
+                                                                  int groups, float* __restrict__ partial,
+                                                                  int pix_per_block) {
+  extern __shared__ float sm[];  // [rows][2][c]
+  const int vpp = c >> 3;
+  const int rows = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
+  const int n = blockIdx.y;
+  const int cpg = c / groups;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
+  if (r < rows) {
+    float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = v * 8 + j, gi = ch / cpg;
+      mean[j] = stats[(n * groups + gi) * 2];
+      rstd[j] = stats[(n * groups + gi) * 2 + 1];
+      ga[j] = gamma[ch];
+      be[j] = beta[ch];
+    }
+    const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+    long long p1 = p0 + pix_per_block;
+    if (p1 > hw) p1 = hw;
+    const T* xb = x + (static_cast<long long>(n) * hw) * c + v * 8;
+    const T* gb = g + (static_cast<long long>(n) * hw) * c + v * 8;
+    for (long long p = p0 + r; p < p1; p += rows) {
+      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(xb + p * c));
+      const uint4 ug = __ldg(reinterpret_cast<const uint4*>(gb + p * c));
+      const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fx = T16<T>::to_f2(wx[j]), fg = T16<T>::to_f2(wg[j]);
+        const float xh0 = (fx.x - mean[2 * j]) * rstd[2 * j], xh1 = (fx.y - mean[2 * j + 1]) * rstd[2 * j + 1];
+        float d0 = fg.x, d1 = fg.y;
+        if (SILU) {
+          d0 *= silu_grad(fmaf(xh0, ga[2 * j], be[2 * j]));
+          d1 *= silu_grad(fmaf(xh1, ga[2 * j + 1], be[2 * j + 1]));
+        }
+        sa[2 * j] += d0; sb[2 * j] = fmaf(d0, xh0, sb[2 * j]);
+        sa[2 * j + 1] += d1; sb[2 * j + 1] = fmaf(d1, xh1, sb[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sm[(r * 2) * c + v * 8 + j] = sa[j];
+      sm[(r * 2 + 1) * c + v * 8 + j] = sb[j];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; ++rr) {
+      a += sm[(rr * 2) * c + ch];
+      b += sm[(rr * 2 + 1) * c + ch];
+    }
+    float* o = partial + ((static_cast<long long>(n) * gridDim.x + blockIdx.x) * c + ch) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+}
+
+// Pass 2 (tiny): per (image, channel) totals -> per-(image, group) s1 = sum dz*gamma, s2 = sum dz*gamma*xhat and the
+// parameter gradients dgamma[c] += sum_n B, dbeta[c] += sum_n A.   One block per image for the group sums.
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma, int n_img, int bpi,
+                                       int c, int groups, float* __restrict__ gsum /*[n][groups][2]*/,
+                                       float* __restrict__ chsum /*[n][c][2]*/) {
+  const int n = blockIdx.x;
+  extern __shared__ float tot[];  // [c][2]
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < bpi; ++k) {
+      const float* o = partial + ((static_cast<long long>(n) * bpi + k) * c + ch) * 2;
+      a += o[0];
+      b += o[1];
+    }
+    tot[2 * ch] = static_cast<float>(a);
+    tot[2 * ch + 1] = static_cast<float>(b);
+    chsum[(static_cast<long long>(n) * c + ch) * 2] = static_cast<float>(a);
+    chsum[(static_cast<long long>(n) * c + ch) * 2 + 1] = static_cast<float>(b);
+  }
+  __syncthreads();
+  const int cpg = c / groups;
+  for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      const int ch = gi * cpg + j;
+      s1 += static_cast<double>(tot[2 * ch]) * gamma[ch];
+      s2 += static_cast<double>(tot[2 * ch + 1]) * gamma[ch];
+    }
+    gsum[(n * groups + gi) * 2] = static_cast<float>(s1);
+    gsum[(n * groups + gi) * 2 + 1] = static_cast<float>(s2);
+  }
+}
+
+__global__ void gn_bwd_param_kernel(const float* __restrict__ chsum, int n_img, int c, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int accumulate) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double a = 0.0, b = 0.0;
+  for (int n = 0; n < n_img; ++n) {
+    a += chsum[(static_cast<long long>(n) * c + ch) * 2];
+    b += chsum[(static_cast<long long>(n) * c + ch) * 2 + 1];
+  }
+  dbeta[ch] = (accumulate ? dbeta[ch] : 0.f) + static_cast<float>(a);
+  dgamma[ch] = (accumulate ? dgamma[ch] : 0.f) + static_cast<float>(b);
+}
+
+// Pass 3: dx = rstd * (dz*gamma - (s1 + xhat*s2) / M) (+ optional accumulation into an existing gradient)
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ g,
+                                                                 const float* __restrict__ stats,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta,
+                                                                 const float* __restrict__ gsum, const T* __restrict__ add,
+                                                                 T* __restrict__ dx, long long hw, int c, int groups,
+                                                                 int pix_per_block) {
+  const int vpp = c >> 3;
+  const int rows = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
+  const int n = blockIdx.y;
+  if (r >= rows) return;
+  const int cpg = c / groups;
+  const float inv_m = 1.0f / (static_cast<float>(hw) * cpg);
+  float mean[8], rstd[8], ga[8], be[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = v * 8 + j, gi = ch / cpg;
+    mean[j] = stats[(n * groups + gi) * 2];
+    rstd[j] = stats[(n * groups + gi) * 2 + 1];
+    ga[j] = gamma[ch];
+    be[j] = beta[ch];
+    k1[j] = gsum[(n * groups + gi) * 2] * inv_m;
+    k2[j] = gsum[(n * groups + gi) * 2 + 1] * inv_m;
+  }
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > hw) p1 = hw;
+  const long long base = (static_cast<long long>(n) * hw) * c + v * 8;
+  for (long long p = p0 + r; p < p1; p += rows) {
+    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + base + p * c));
+    const uint4 ug = __ldg(reinterpret_cast<const uint4*>(g + base + p * c));
+    uint4 ua = make_uint4(0, 0, 0, 0);
+    if (add != nullptr) ua = __ldg(reinterpret_cast<const uint4*>(add + base + p * c));
+    const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w}, wa[4] = {ua.x, ua.y, ua.z, ua.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fx = T16<T>::to_f2(wx[j]), fg = T16<T>::to_f2(wg[j]);
+      float2 fa = make_float2(0.f, 0.f);
+      if (add != nullptr) fa = T16<T>::to_f2(wa[j]);
+      const float xh0 = (fx.x - mean[2 * j]) * rstd[2 * j], xh1 = (fx.y - mean[2 * j + 1]) * rstd[2 * j + 1];
+      float d0 = fg.x, d1 = fg.y;
+      if (SILU) {
+        d0 *= silu_grad(fmaf(xh0, ga[2 * j], be[2 * j]));
+        d1 *= silu_grad(fmaf(xh1, ga[2 * j + 1], be[2 * j + 1]));
+      }
+      const float r0 = rstd[2 * j] * (d0 * ga[2 * j] - k1[2 * j] - xh0 * k2[2 * j]) + fa.x;
+      const float r1 = rstd[2 * j + 1] * (d1 * ga[2 * j + 1] - k1[2 * j + 1] - xh1 * k2[2 * j + 1]) + fa.y;
+      o[j] = T16<T>::from_f2(r0, r1);
+    }
+    *reinterpret_cast<uint4*>(dx + base + p * c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+void bwd_grid(long long hw, int c, int rows, int* bpi, int* ppb) {
+  long long per = 16384 / c;
+  if (per < rows) per = rows;
+  per = (per + rows - 1) / rows * rows;
+  if (per > hw) per = (hw + rows - 1) / rows * rows;
+  *ppb = static_cast<int>(per);
+  *bpi = static_cast<int>((hw + per - 1) / per);
+}
+
+// dY [n][ho][wo][c] -> Z [n][h][w][c], zero except Z[2i+1][2j+1] = dY[i][j]: turns the data gradient of the
+// pad(0,1,0,1) + stride-2 conv into a stride-1 pad-1 conv with the flipped kernel.
+__global__ void scatter_s2_kernel(const uint4* __restrict__ dy, uint4* __restrict__ z, int ho, int wo, int h, int w, int c8,
+                                  long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % c8);
+  long long t = i / c8;
+  const int x = static_cast<int>(t % w);
+  t /= w;
+  const int y = static_cast<int>(t % h);
+  const long long n = t / h;
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if ((x & 1) && (y & 1) && (x >> 1) < wo && (y >> 1) < ho) val = __ldg(&dy[((n * ho + (y >> 1)) * wo + (x >> 1)) * c8 + v]);
+  z[i] = val;
+}
+
+// adjoint of nearest x2 upsampling: out[n][i][j][c] = sum of the 2x2 block of g
+template <typename T>
+__global__ void pool2x2_sum_kernel(const T* __restrict__ g, T* __restrict__ out, int h, int w, int c8, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % c8);
+  long long t = i / c8;
+  const int x = static_cast<int>(t % w);
+  t /= w;
+  const int y = static_cast<int>(t % h);
+  const long long n = t / h;
+  float acc[8] = {};
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(g) + ((n * 2 * h + 2 * y + dy) * 2 * w + 2 * x + dx) * c8 + v);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = T16<T>::to_f2(w4[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  uint4 o;
+  o.x = T16<T>::from_f2(acc[0], acc[1]);
+  o.y = T16<T>::from_f2(acc[2], acc[3]);
+  o.z = T16<T>::from_f2(acc[4], acc[5]);
+  o.w = T16<T>::from_f2(acc[6], acc[7]);
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+// per-channel sum over all pixels of an NHWC 16-bit tensor (bias gradient); fixed-slot partials
+template <typename T>
+__global__ void __launch_bounds__(kThreads) colsum_partial_kernel(const T* __restrict__ g, long long pixels, int c,
+                                                                   float* __restrict__ partial, long long pix_per_block) {
+  extern __shared__ float sm[];  // [rows][c]
+  const int vpp = c >> 3;
+  const int rows = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
+  float s[8] = {};
+  if (r < rows) {
+    const long long p0 = blockIdx.x * pix_per_block;
+    long long p1 = p0 + pix_per_block;
+    if (p1 > pixels) p1 = pixels;
+    for (long long p = p0 + r; p < p1; p += rows) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + p * c + v * 8));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = T16<T>::to_f2(w4[j]);
+        s[2 * j] += f.x;
+        s[2 * j + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[r * c + v * 8 + j] = s[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += sm[rr * c + ch];
+    partial[static_cast<long long>(blockIdx.x) * c + ch] = a;
+  }
+}
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ out,
+                                       int accumulate) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double a = 0.0;
+  for (int b = 0; b < blocks; ++b) a += partial[static_cast<long long>(b) * c + ch];
+  out[ch] = (accumulate ? out[ch] : 0.f) + static_cast<float>(a);
+}
+
+int block_threads(int c) {
+  const int vpp = c / 8;
+  const int t = (kThreads / vpp) * vpp;
+  return t < vpp ? 0 : t;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t eovae_gn_backward_workspace_bytes(int n, long long hw, int c, int groups) {
+  const int threads = block_threads(c);
+  if (threads <= 0) return 0;
+  int bpi, ppb;
+  bwd_grid(hw, c, threads / (c / 8), &bpi, &ppb);
+  return sizeof(float) * (2 * static_cast<size_t>(n) * bpi * c + 2 * static_cast<size_t>(n) * groups +
+                          2 * static_cast<size_t>(n) * c + 64);
+}
+
+int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const float* stats, const float* gamma,
+                      const float* beta, int n, long long hw, int c, int groups, int with_silu, const void* grad_add,
+                      void* grad_x, float* dgamma, float* dbeta, int accumulate_params, void* workspace,
+                      size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c % 8 == 0 && c % groups == 0, "gn_backward: C (%d) must be a multiple of 8 and of groups (%d)", c, groups);
+  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "gn_backward: 16-bit tensors only");
+  const int threads = block_threads(c);
+  EOVAE_CHECK(threads > 0, "gn_backward: C too large (%d)", c);
+  EOVAE_CHECK(workspace_bytes >= eovae_gn_backward_workspace_bytes(n, hw, c, groups), "gn_backward: workspace too small");
+  const int rows = threads / (c / 8);
+  int bpi, ppb;
+  bwd_grid(hw, c, rows, &bpi, &ppb);
+  float* partial = static_cast<float*>(workspace);
+  float* gsum = partial + 2 * static_cast<size_t>(n) * bpi * c;
+  float* chsum = gsum + 2 * static_cast<size_t>(n) * groups;
+  dim3 grid(bpi, n);
+  const size_t smem = sizeof(float) * 2 * c * rows;
+#define EOVAE_GNB_R(T, S)                                                                                             \
+  gn_bwd_reduce_kernel<T, S><<<grid, threads, smem, stream>>>(static_cast<const T*>(x), static_cast<const T*>(grad_out), \
+                                                             stats, gamma, beta, hw, c, groups, partial, ppb)
+#define EOVAE_GNB_A(T, S)                                                                                            \
+  gn_bwd_apply_kernel<T, S><<<grid, threads, 0, stream>>>(static_cast<const T*>(x), static_cast<const T*>(grad_out),  \
+                                                          stats, gamma, beta, gsum, static_cast<const T*>(grad_add),  \
+                                                          static_cast<T*>(grad_x), hw, c, groups, ppb)
+  if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_R(__nv_bfloat16, true); else EOVAE_GNB_R(__nv_bfloat16, false); }
+  else { if (with_silu) EOVAE_GNB_R(__half, true); else EOVAE_GNB_R(__half, false); }
+  EOVAE_LAUNCH_CHECK();
+  gn_bwd_finalize_kernel<<<n, 256, sizeof(float) * 2 * c, stream>>>(partial, gamma, n, bpi, c, groups, gsum, chsum);
+  EOVAE_LAUNCH_CHECK();
+  if (dgamma != nullptr && dbeta != nullptr) {
+    gn_bwd_param_kernel<<<ceil_div(c, 128), 128, 0, stream>>>(chsum, n, c, dgamma, dbeta, accumulate_params);
+    EOVAE_LAUNCH_CHECK();
+  }
+  if (grad_x != nullptr) {
+    if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_A(__nv_bfloat16, true); else EOVAE_GNB_A(__nv_bfloat16, false); }
+    else { if (with_silu) EOVAE_GNB_A(__half, true); else EOVAE_GNB_A(__half, false); }
+    EOVAE_LAUNCH_CHECK();
+  }
+#undef EOVAE_GNB_R
+#undef EOVAE_GNB_A
+  return 0;
+}
+
+int eovae_scatter_stride2(const void* dy, void* z, int n, int ho, int wo, int h, int w, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c % 8 == 0, "scatter_stride2: C must be a multiple of 8");
+  const long long total = static_cast<long long>(n) * h * w * (c / 8);
+  scatter_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const uint4*>(dy), static_cast<uint4*>(z), ho, wo, h, w, c / 8, total);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_pool2x2_sum(const void* g, void* out, int dtype, int n, int h, int w, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c % 8 == 0, "pool2x2_sum: C must be a multiple of 8");
+  const long long total = static_cast<long long>(n) * h * w * (c / 8);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == EOVAE_BF16)
+    pool2x2_sum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(out), h, w, c / 8, total);
+  else
+    pool2x2_sum_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(g), static_cast<__half*>(out), h, w, c / 8, total);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t eovae_bias_grad_workspace_bytes(long long pixels, int c) {
+  return sizeof(float) * static_cast<size_t>((pixels + 4095) / 4096 + 1) * c;
+}
+
+int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, float* dbias, int accumulate, void* workspace,
+                    size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c % 8 == 0, "bias_grad: C must be a multiple of 8");
+  EOVAE_CHECK(workspace_bytes >= eovae_bias_grad_workspace_bytes(pixels, c), "bias_grad: workspace too small");
+  const int threads = block_threads(c);
+  EOVAE_CHECK(threads > 0, "bias_grad: C too large");
+  const int rows = threads / (c / 8);
+  const long long ppb = 4096;
+  const int blocks = static_cast<int>((pixels + ppb - 1) / ppb);
+  float* partial = static_cast<float*>(workspace);
+  const size_t smem = sizeof(float) * rows * c;
+  if (dtype == EOVAE_BF16)
+    colsum_partial_kernel<__nv_bfloat16><<<blocks, threads, smem, stream>>>(static_cast<const __nv_bfloat16*>(grad_out), pixels, c, partial, ppb);
+  else
+    colsum_partial_kernel<__half><<<blocks, threads, smem, stream>>>(static_cast<const __half*>(grad_out), pixels, c, partial, ppb);
+  EOVAE_LAUNCH_CHECK();
+  colsum_finalize_kernel<<<ceil_div(c, 128), 128, 0, stream>>>(partial, blocks, c, dbias, accumulate);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -47,6 +47,22 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restri
   out[i] = T16<T>::from_f(v);
 }
 
+// dgrad operand: the data gradient of y = conv(x, W) is conv(dy, W') with W'[ci][co][kh][kw] = W[co][ci][K-1-kh][K-1-kw]
+template <typename T>
+__global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int taps,
+                                              int kpt, long long total) {
+  // out[ci][tap][co] (co < kpt = padded Cout), rows padded to round_up(cin, 16)
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % kpt);
+  long long t = i / kpt;
+  const int tap = static_cast<int>(t % taps);
+  const int ci = static_cast<int>(t / taps);
+  float v = 0.f;
+  if (ci < cin && co < cout) v = w[(static_cast<long long>(co) * cin + ci) * taps + (taps - 1 - tap)];
+  out[i] = T16<T>::from_f(v);
+}
+
 template <typename T>
 __global__ void pack_dyn_weight_kernel(const float* __restrict__ wk, int c, int embed, int decoder, float scale,
                                        T* __restrict__ packed, int kpt, int rows_pad, float* __restrict__ oihw,
@@ -96,6 +112,24 @@ int eovae_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, in
     pack_conv_weight_kernel<__half><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, taps, kpt, total);
   else
     EOVAE_CHECK(false, "pack_conv_weight: bad dtype %d", dtype);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_pack_conv_weight_dgrad(const float* w_oihw, void* out, int cout, int cin, int kh, int kw, int dtype,
+                                 void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK((kh == 3 && kw == 3) || (kh == 1 && kw == 1), "pack_conv_weight_dgrad: only 3x3 and 1x1 kernels");
+  const int taps = kh * kw;
+  const int kpt = eovae_conv_k_per_tap(round_up(cout, 8));
+  const long long total = static_cast<long long>(round_up(cin, 16)) * taps * kpt;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == EOVAE_BF16)
+    pack_conv_weight_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, taps, kpt, total);
+  else if (dtype == EOVAE_F16)
+    pack_conv_weight_dgrad_kernel<__half><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, taps, kpt, total);
+  else
+    EOVAE_CHECK(false, "pack_conv_weight_dgrad: bad dtype %d", dtype);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

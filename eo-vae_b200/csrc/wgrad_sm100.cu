@@ -1,0 +1,277 @@
+// Weight gradient of the 3x3 (stride 1, pad 1) and 1x1 convolutions on tcgen05:
+//
+//   dW[co][ci][kh][kw] = sum_{n, y, x} dY[n, y, x, co] * X[n, y + kh - 1, x + kw - 1, ci]
+//
+// i.e. per tap a GEMM  D[co, ci] = A[co, p] * B[ci, p]^T  contracted over the pixels p.  Both operands are read from
+// CHANNEL-MAJOR copies (dY^T, X^T: [n][channels][h][w], produced by eovae_transpose16) so that a 64-pixel K chunk of 128
+// output channels / up to 256 input channels is ONE 4-D TMA box (x, y, channel, image) - K-major, 128-byte swizzled, and
+// the tap shift of X is just a shifted box whose out-of-image part the TMA unit zero-fills (= the conv padding).
+// Work item = (tap, 128-row Cout tile, Cin tile, K split); every CTA accumulates its pixel range in TMEM and writes one
+// fp32 partial tile, a second kernel reduces the K splits in fixed order (deterministic) into OIHW fp32.
+#include "../../include/eovae.h"
+#include "igemm_sm100.cuh"
+
+namespace {
+
+using namespace igemm;
+
+constexpr int WG_THREADS = 192;  // TMA warp, MMA warp, 4 epilogue warps
+constexpr int WG_STAGES = 4;
+
+struct WgradParams {
+  CUtensorMap a_map;   // dY^T: dims (W, H, Cout, N), box (bw, bh, 128, 1)
+  CUtensorMap b_map;   // X^T : dims (W, H, Cin, N),  box (bw, bh, BN, 1)
+  int H, W, N;
+  int bw, bh;          // pixels per K chunk = bw * bh = 64
+  int taps;            // 9 or 1
+  int cout, cin;
+  int co_tiles, ci_tiles, ksplit;
+  int chunks_total;    // N * H * W / 64
+  int chunks_per_split;
+  float* partial;      // [ksplit][taps][cout][cin]
+  uint32_t idesc;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * STAGE);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WG_STAGES;
+  uint64_t* done_bar = bars + 2 * WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item decode
+  int item = blockIdx.x;
+  const int ks = item % p.ksplit; item /= p.ksplit;
+  const int cit = item % p.ci_tiles; item /= p.ci_tiles;
+  const int cot = item % p.co_tiles; item /= p.co_tiles;
+  const int tap = item;
+  const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+  const int chunk0 = ks * p.chunks_per_split;
+  int chunk1 = chunk0 + p.chunks_per_split;
+  if (chunk1 > p.chunks_total) chunk1 = p.chunks_total;
+  const int nchunks = chunk1 > chunk0 ? chunk1 - chunk0 : 0;
+  const int chunks_w = p.W / p.bw, chunks_h = p.H / p.bh;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.a_map);
+    prefetch_tmap(&p.b_map);
+    for (int i = 0; i < WG_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int chunk = chunk0 + c;
+        const int cx = chunk % chunks_w;
+        const int cy = (chunk / chunks_w) % chunks_h;
+        const int n = chunk / (chunks_w * chunks_h);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+        tma_load_4d(&p.a_map, &full_bar[stage], smem + stage * STAGE, cx * p.bw, cy * p.bh, cot * 128, n);
+        tma_load_4d(&p.b_map, &full_bar[stage], smem + stage * STAGE + A_BYTES, cx * p.bw + dx, cy * p.bh + dy, cit * BN, n);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc<128>(smem_u32(smem + stage * STAGE));
+        const uint64_t db = make_smem_desc<128>(smem_u32(smem + stage * STAGE + A_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tmem_base, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc, (c | k) != 0 ? 1u : 0u);
+        tc_commit(&empty_bar[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(done_bar);
+    }
+  } else {
+    const int sub = warp & 3;
+    const int co = cot * 128 + sub * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* dst = p.partial + ((static_cast<long long>(ks) * p.taps + tap) * p.cout + co) * p.cin + cit * BN;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t raw[16];
+      tc_ld16(taddr + c, raw);
+      tc_wait_ld();
+      if (co < p.cout && nchunks > 0) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          if (cit * BN + c + j < p.cin)
+            *reinterpret_cast<float4*>(dst + c + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
+                                                                  __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
+      } else if (co < p.cout) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          if (cit * BN + c + j < p.cin) *reinterpret_cast<float4*>(dst + c + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// dW[co][ci][tap] (OIHW, taps innermost) (+)= sum_ks partial[ks][tap][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ksplit, int taps, int cout,
+                                    int cin, int accumulate, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // over (tap, co, ci), ci fastest
+  if (i >= total) return;
+  const int ci = static_cast<int>(i % cin);
+  long long t = i / cin;
+  const int co = static_cast<int>(t % cout);
+  const int tap = static_cast<int>(t / cout);
+  double acc = 0.0;
+  for (int k = 0; k < ksplit; ++k) acc += partial[static_cast<long long>(k) * total + i];
+  float* o = dw + (static_cast<long long>(co) * cin + ci) * taps + tap;
+  *o = (accumulate ? *o : 0.f) + static_cast<float>(acc);
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* m, int dtype, const void* base, int w, int h, int c, int n, int bw, int bh, int rows) {
+  EncodeFn fn = encode_fn();
+  EOVAE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(w) * 2, static_cast<cuuint64_t>(w) * h * 2, static_cast<cuuint64_t>(w) * h * c * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(rows), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, dtype == EOVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                  const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EOVAE_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled failed (%d) w %d h %d c %d n %d box %d %d %d", (int)r, w, h, c, n, bw, bh, rows);
+  return 0;
+}
+
+int pick_bn(int cin) {
+  if (cin >= 256) return 256;
+  if (cin >= 128) return 128;
+  if (cin >= 64) return 64;
+  if (cin >= 32) return 32;
+  return 16;
+}
+
+void plan(int n, int h, int w, int cin, int cout, int taps, int* bn, int* co_tiles, int* ci_tiles, int* ksplit, int* cps,
+          int* chunks_total) {
+  *bn = pick_bn(cin);
+  *co_tiles = ceil_div(cout, 128);
+  *ci_tiles = ceil_div(cin, *bn);
+  *chunks_total = static_cast<int>(static_cast<long long>(n) * h * w / 64);
+  const int base = taps * *co_tiles * *ci_tiles;
+  int ks = ceil_div(4 * eovae_num_sms(), base);
+  int max_ks = *chunks_total / 16;  // at least 16 K chunks (1024 pixels) per item
+  if (max_ks < 1) max_ks = 1;
+  if (ks > max_ks) ks = max_ks;
+  if (ks < 1) ks = 1;
+  *cps = ceil_div(*chunks_total, ks);
+  *ksplit = ceil_div(*chunks_total, *cps);
+}
+
+template <int BN>
+int launch(const WgradParams& p, int items, cudaStream_t stream) {
+  constexpr int SMEM = WG_STAGES * (128 * 128 + BN * 128) + 1024 + 256;
+  auto kern = wgrad_kernel<BN>;
+  static bool set = false;
+  if (!set) {
+    EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    set = true;
+  }
+  kern<<<items, WG_THREADS, SMEM, stream>>>(p);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t eovae_conv2d_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize) {
+  int bn, cot, cit, ks, cps, ct;
+  plan(n, h, w, cin, cout, ksize * ksize, &bn, &cot, &cit, &ks, &cps, &ct);
+  return sizeof(float) * static_cast<size_t>(ks) * ksize * ksize * cout * cin;
+}
+
+int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int n, int h, int w, int cin, int cout, int ksize,
+                       float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad: kernel size must be 3 or 1");
+  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "conv2d_wgrad: 16-bit operands only");
+  EOVAE_CHECK(w % 8 == 0 && cin % 16 == 0 && cin % 4 == 0, "conv2d_wgrad: W %% 8 and Cin %% 16 required (W %d, Cin %d)", w, cin);
+  const int bw = w >= 64 ? 64 : w;
+  EOVAE_CHECK(64 % bw == 0 && w % bw == 0, "conv2d_wgrad: W (%d) must be a power of two below 64 or a multiple of 64", w);
+  const int bh = 64 / bw;
+  EOVAE_CHECK(h % bh == 0, "conv2d_wgrad: H (%d) must be a multiple of %d", h, bh);
+  EOVAE_CHECK(workspace_bytes >= eovae_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, ksize), "conv2d_wgrad: workspace too small");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int bn;
+  plan(n, h, w, cin, cout, ksize * ksize, &bn, &p.co_tiles, &p.ci_tiles, &p.ksplit, &p.chunks_per_split, &p.chunks_total);
+  p.H = h; p.W = w; p.N = n; p.bw = bw; p.bh = bh; p.taps = ksize * ksize; p.cout = cout; p.cin = cin;
+  p.partial = static_cast<float*>(workspace);
+  const uint32_t fmt = dtype == EOVAE_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  if (make_map(&p.a_map, dtype, dy_t, w, h, cout, n, bw, bh, 128)) return -3;
+  if (make_map(&p.b_map, dtype, x_t, w, h, cin, n, bw, bh, bn)) return -3;
+  const int items = p.taps * p.co_tiles * p.ci_tiles * p.ksplit;
+  int rc;
+  switch (bn) {
+    case 256: rc = launch<256>(p, items, stream); break;
+    case 128: rc = launch<128>(p, items, stream); break;
+    case 64: rc = launch<64>(p, items, stream); break;
+    case 32: rc = launch<32>(p, items, stream); break;
+    default: rc = launch<16>(p, items, stream); break;
+  }
+  if (rc) return rc;
+  const long long total = static_cast<long long>(p.taps) * cout * cin;
+  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p.partial, dw_oihw, p.ksplit, p.taps, cout,
+                                                                                      cin, accumulate, total);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

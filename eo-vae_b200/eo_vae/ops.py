@@ -342,6 +342,93 @@ def msssim(pred: torch.Tensor, target: torch.Tensor, data_range: float = 6.0):
     return out, per
 
 
+# ------------------------------------------------------------------------------------------------ backward pieces
+def pack_conv_weight_dgrad(w: torch.Tensor, dtype) -> torch.Tensor:
+    """OIHW fp32 -> operand of the data-gradient conv (flipped taps, in/out channels swapped)."""
+    _need_cuda(w)
+    cout, cin, kh, kw = w.shape
+    wf = w.detach().to(torch.float32).contiguous()
+    out = torch.empty(((cin + 15) // 16 * 16, kh * kw, conv_k_per_tap((cout + 7) // 8 * 8)), dtype=dtype, device=w.device)
+    _C.check(_C.lib().eovae_pack_conv_weight_dgrad(_ptr(wf), _ptr(out), cout, cin, kh, kw, DT[dtype], _stream()),
+             "eovae_pack_conv_weight_dgrad")
+    return out
+
+
+def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, mode: int, in_hw=None, grad_add=None) -> torch.Tensor:
+    """Data gradient of eovae_conv2d (w: OIHW fp32 master weight) as another implicit GEMM; ``grad_add`` (same shape
+    as the result) is accumulated in the epilogue (gradient fan-in of a residual branch)."""
+    cout, cin = w.shape[0], w.shape[1]
+    wp = pack_conv_weight_dgrad(w, dy.dtype)
+    if mode == CONV_3X3_S2:
+        n, _, ho, wo = dy.shape
+        h, wd = in_hw
+        z = nhwc_empty(n, cout, h, wd, dy.dtype, dy.device)
+        _C.check(_C.lib().eovae_scatter_stride2(_ptr(dy), _ptr(z), n, ho, wo, h, wd, cout, _stream()),
+                 "eovae_scatter_stride2")
+        return conv2d(z, wp, None, cin, CONV_3X3, residual=grad_add)
+    return conv2d(dy, wp, None, cin, mode, residual=grad_add)
+
+
+def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor | None = None) -> torch.Tensor:
+    """Weight gradient [cout, cin, k, k] fp32 of a stride-1 conv (x: its NHWC 16-bit input, dy: output gradient)."""
+    _need_cuda(x, dy)
+    n, cin, h, w = x.shape
+    cout = dy.shape[1]
+    xt = transpose16(x.permute(0, 2, 3, 1).reshape(n, h * w, pix_stride(x))[:, :, :cin])    # [n, cin, h*w]
+    dyt = transpose16(dy.permute(0, 2, 3, 1).reshape(n, h * w, pix_stride(dy))[:, :, :cout])
+    lib = _C.lib()
+    ws_bytes = lib.eovae_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, ksize)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=x.device)
+    acc = dw is not None
+    if dw is None:
+        dw = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    _C.check(lib.eovae_conv2d_wgrad(_ptr(xt), _ptr(dyt), DT[x.dtype], n, h, w, cin, cout, ksize, _ptr(dw), 1 if acc else 0,
+                                    _ptr(ws), ws_bytes, _stream()), "eovae_conv2d_wgrad")
+    return dw
+
+
+def bias_grad(dy: torch.Tensor) -> torch.Tensor:
+    _need_cuda(dy)
+    n, c, h, w = dy.shape
+    if pix_stride(dy) != c:
+        raise RuntimeError("eo_vae.bias_grad: dense channels-last gradient required")
+    lib = _C.lib()
+    ws_bytes = lib.eovae_bias_grad_workspace_bytes(n * h * w, c)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=dy.device)
+    out = torch.empty((c,), dtype=torch.float32, device=dy.device)
+    _C.check(lib.eovae_bias_grad(_ptr(dy), DT[dy.dtype], n * h * w, c, _ptr(out), 0, _ptr(ws), ws_bytes, _stream()),
+             "eovae_bias_grad")
+    return out
+
+
+def gn_backward(x: torch.Tensor, grad_out: torch.Tensor, stats, gamma, beta, silu: bool, groups: int = 32,
+                grad_add=None):
+    """-> (grad_x, dgamma, dbeta) of y = [silu](GroupNorm(x))."""
+    _need_cuda(x, grad_out, stats, gamma, beta, grad_add)
+    n, c, h, w = x.shape
+    if pix_stride(x) != c or pix_stride(grad_out) != c or (grad_add is not None and pix_stride(grad_add) != c):
+        raise RuntimeError("eo_vae.gn_backward: dense channels-last tensors required")
+    lib = _C.lib()
+    ws_bytes = lib.eovae_gn_backward_workspace_bytes(n, h * w, c, groups)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=x.device)
+    gx = nhwc_empty(n, c, h, w, x.dtype, x.device)
+    dg = torch.empty((c,), dtype=torch.float32, device=x.device)
+    db = torch.empty((c,), dtype=torch.float32, device=x.device)
+    _C.check(lib.eovae_gn_backward(_ptr(x), _ptr(grad_out), DT[x.dtype], _ptr(stats), _ptr(gamma), _ptr(beta), n, h * w, c,
+                                   groups, 1 if silu else 0, _ptr(grad_add), _ptr(gx), _ptr(dg), _ptr(db), 0, _ptr(ws),
+                                   ws_bytes, _stream()), "eovae_gn_backward")
+    return gx, dg, db
+
+
+def pool2x2_sum(g: torch.Tensor) -> torch.Tensor:
+    _need_cuda(g)
+    n, c, h2, w2 = g.shape
+    out = nhwc_empty(n, c, h2 // 2, w2 // 2, g.dtype, g.device)
+    _C.check(_C.lib().eovae_pool2x2_sum(_ptr(g), _ptr(out), DT[g.dtype], n, h2 // 2, w2 // 2, c, _stream()),
+             "eovae_pool2x2_sum")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ hypernetwork
 def hypernet_forward(wvs: torch.Tensor, params: list, num_layers: int, d: int, heads: int, ff: int, embed: int,
                      decoder: bool):

@@ -157,6 +157,33 @@ size_t eovae_msssim_workspace_bytes(int b, int c, int h, int w);
 int eovae_msssim(const float* pred, const float* target, int b, int c, int h, int w, float data_range, float* out,
                  float* per_sample, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- backward pass (first kernels of the training path, new_autoencoder.py:648 manual_backward) ------------------ */
+/* dgrad operand: conv data gradient = eovae_conv2d(dy, pack_dgrad(W), Cout' = Cin) with the flipped / transposed kernel:
+ * OIHW fp32 [cout][cin][kh][kw] -> [round_up(cin,16)][kh*kw][k_per_tap(round_up(cout,8))]                            */
+int eovae_pack_conv_weight_dgrad(const float* w_oihw, void* out, int cout, int cin, int kh, int kw, int dtype,
+                                 void* stream);
+/* GroupNorm(+SiLU) backward (dense NHWC 16-bit x, grad_out): grad_x = dL/dx (+ grad_add if not NULL),
+ * dgamma/dbeta fp32 [c] (optionally accumulated); grad_x or the parameter outputs may be NULL                      */
+size_t eovae_gn_backward_workspace_bytes(int n, long long hw, int c, int groups);
+int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const float* stats, const float* gamma,
+                      const float* beta, int n, long long hw, int c, int groups, int with_silu, const void* grad_add,
+                      void* grad_x, float* dgamma, float* dbeta, int accumulate_params, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* dy [n][ho][wo][c] -> z [n][h][w][c] = 0 except z[2i+1][2j+1] = dy[i][j] (adjoint of the Downsample stride-2 gather) */
+int eovae_scatter_stride2(const void* dy, void* z, int n, int ho, int wo, int h, int w, int c, void* stream);
+/* out [n][h][w][c] = sum over the 2x2 blocks of g [n][2h][2w][c] (adjoint of nearest x2 upsampling) */
+int eovae_pool2x2_sum(const void* g, void* out, int dtype, int n, int h, int w, int c, void* stream);
+/* weight gradient of a 3x3 (stride 1, pad 1) or 1x1 convolution on tcgen05, contracted over the pixels:
+ * x_t, dy_t: CHANNEL-MAJOR 16-bit copies [n][cin][h][w] / [n][cout][h][w] (eovae_transpose16 of the NHWC tensors);
+ * dw_oihw fp32 [cout][cin][k][k] (optionally accumulated).  Deterministic (fixed-order split-K reduction).          */
+size_t eovae_conv2d_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize);
+int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int n, int h, int w, int cin, int cout, int ksize,
+                       float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* dbias[c] (+)= sum over pixels of grad_out [pixels][c] (16-bit) */
+size_t eovae_bias_grad_workspace_bytes(long long pixels, int c);
+int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, float* dbias, int accumulate, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

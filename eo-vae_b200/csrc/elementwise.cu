@@ -285,6 +285,33 @@ __global__ void transpose16_kernel(const uint16_t* __restrict__ in, long long in
   }
 }
 
+// out[d][b][c][y*w + x] = in[b][y*w + x + d - 1][c] when 0 <= x + d - 1 < w, else 0 (d = 0, 1, 2): the three x-shifted
+// channel-major copies the weight-gradient GEMM reads (TMA cannot shift the innermost coordinate by one element).
+__global__ void transpose16_xshift3_kernel(const uint16_t* __restrict__ in, long long in_ld, uint16_t* __restrict__ out,
+                                           int rows, int w, int cols, long long copy_stride) {
+  __shared__ uint16_t tile[34][33];
+  const long long b = blockIdx.z;
+  const uint16_t* ib = in + b * rows * in_ld;
+  uint16_t* ob = out + b * static_cast<long long>(cols) * rows;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 34; j += blockDim.y) {
+    const int r = r0 + j - 1, cc = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r >= 0 && r < rows && cc < cols) ? ib[static_cast<long long>(r) * in_ld + cc] : uint16_t(0);
+  }
+  __syncthreads();
+  const int r = r0 + threadIdx.x;
+  const int x = r % w;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int cc = c0 + j;
+    if (cc >= cols || r >= rows) continue;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int xs = x + d - 1;
+      ob[d * copy_stride + static_cast<long long>(cc) * rows + r] = (xs >= 0 && xs < w) ? tile[threadIdx.x + d][j] : uint16_t(0);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- latent glue
 struct Strides4 { long long n, c, y, x; };  // element strides of a logical [N, C, H, W] tensor
 
@@ -528,6 +555,18 @@ int eovae_transpose16(const void* in, long long in_ld, void* out, long long out_
   dim3 grid(ceil_div(cols, 32), ceil_div(static_cast<int>(out_ld), 32), batch);
   dim3 block(32, 8);
   transpose16_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(in), in_ld, static_cast<uint16_t*>(out), out_ld, rows, cols);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_transpose16_xshift3(const void* in, long long in_ld, void* out, int batch, int h, int w, int cols, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(in_ld >= cols, "transpose16_xshift3: pitch smaller than extent");
+  const int rows = h * w;
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), batch);
+  dim3 block(32, 8);
+  transpose16_xshift3_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(in), in_ld, static_cast<uint16_t*>(out), rows, w,
+                                                         cols, static_cast<long long>(batch) * cols * rows);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -3,9 +3,11 @@
 //   dW[co][ci][kh][kw] = sum_{n, y, x} dY[n, y, x, co] * X[n, y + kh - 1, x + kw - 1, ci]
 //
 // i.e. per tap a GEMM  D[co, ci] = A[co, p] * B[ci, p]^T  contracted over the pixels p.  Both operands are read from
-// CHANNEL-MAJOR copies (dY^T, X^T: [n][channels][h][w], produced by eovae_transpose16) so that a 64-pixel K chunk of 128
-// output channels / up to 256 input channels is ONE 4-D TMA box (x, y, channel, image) - K-major, 128-byte swizzled, and
-// the tap shift of X is just a shifted box whose out-of-image part the TMA unit zero-fills (= the conv padding).
+// CHANNEL-MAJOR copies (dY^T, X^T: [n][channels][h*w]) so that a 64-pixel K chunk of 128 output channels / up to 256 input
+// channels is ONE 3-D TMA box (pixel, channel, image) - K-major, 128-byte swizzled.  The vertical tap shift of X is a box
+// shifted by +-W pixels whose out-of-image part the TMA unit zero-fills (= the conv padding); the horizontal shift cannot be
+// a TMA coordinate (the innermost start must stay 16-byte aligned - a one-element shift faults), so X^T comes as three
+// x-shifted copies with the row borders already zeroed (eovae_transpose16_xshift3), stacked along the image dimension.
 // Work item = (tap, 128-row Cout tile, Cin tile, K split); every CTA accumulates its pixel range in TMEM and writes one
 // fp32 partial tile, a second kernel reduces the K splits in fixed order (deterministic) into OIHW fp32.
 #include "../../include/eovae.h"
@@ -19,10 +21,10 @@ constexpr int WG_THREADS = 192;  // TMA warp, MMA warp, 4 epilogue warps
 constexpr int WG_STAGES = 4;
 
 struct WgradParams {
-  CUtensorMap a_map;   // dY^T: dims (W, H, Cout, N), box (bw, bh, 128, 1)
-  CUtensorMap b_map;   // X^T : dims (W, H, Cin, N),  box (bw, bh, BN, 1)
+  CUtensorMap a_map;   // dY^T: dims (H*W, Cout, N),       box (64, 128, 1)
+  CUtensorMap b_map;   // X^T : dims (H*W, Cin, 3N or N),  box (64, BN, 1)
   int H, W, N;
-  int bw, bh;          // pixels per K chunk = bw * bh = 64
+  int chunks_img;      // 64-pixel K chunks per image = H * W / 64
   int taps;            // 9 or 1
   int cout, cin;
   int co_tiles, ci_tiles, ksplit;
@@ -53,12 +55,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   const int cit = item % p.ci_tiles; item /= p.ci_tiles;
   const int cot = item % p.co_tiles; item /= p.co_tiles;
   const int tap = item;
-  const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+  const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
+  const int dx = p.taps == 9 ? tap % 3 - 1 : -1;  // 1x1: a single unshifted copy (image index (dx + 1) * N + n = n)
   const int chunk0 = ks * p.chunks_per_split;
   int chunk1 = chunk0 + p.chunks_per_split;
   if (chunk1 > p.chunks_total) chunk1 = p.chunks_total;
   const int nchunks = chunk1 > chunk0 ? chunk1 - chunk0 : 0;
-  const int chunks_w = p.W / p.bw, chunks_h = p.H / p.bh;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.a_map);
@@ -85,13 +87,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       uint32_t phase = 0;
       for (int c = 0; c < nchunks; ++c) {
         const int chunk = chunk0 + c;
-        const int cx = chunk % chunks_w;
-        const int cy = (chunk / chunks_w) % chunks_h;
-        const int n = chunk / (chunks_w * chunks_h);
+        const int p0 = (chunk % p.chunks_img) * 64;
+        const int n = chunk / p.chunks_img;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-        tma_load_4d(&p.a_map, &full_bar[stage], smem + stage * STAGE, cx * p.bw, cy * p.bh, cot * 128, n);
-        tma_load_4d(&p.b_map, &full_bar[stage], smem + stage * STAGE + A_BYTES, cx * p.bw + dx, cy * p.bh + dy, cit * BN, n);
+        tma_load_3d(&p.a_map, &full_bar[stage], smem + stage * STAGE, p0, cot * 128, n);
+        tma_load_3d(&p.b_map, &full_bar[stage], smem + stage * STAGE + A_BYTES, p0 + dy * p.W, cit * BN, (dx + 1) * p.N + n);
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -174,17 +175,17 @@ EncodeFn encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap* m, int dtype, const void* base, int w, int h, int c, int n, int bw, int bh, int rows) {
+int make_map(CUtensorMap* m, int dtype, const void* base, long long pixels, int c, int n, int rows) {
   EncodeFn fn = encode_fn();
   EOVAE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[4] = {static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(n)};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(w) * 2, static_cast<cuuint64_t>(w) * h * 2, static_cast<cuuint64_t>(w) * h * c * 2};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(rows), 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, dtype == EOVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(pixels), static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(pixels) * 2, static_cast<cuuint64_t>(pixels) * c * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(rows), 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, dtype == EOVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                   const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  EOVAE_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled failed (%d) w %d h %d c %d n %d box %d %d %d", (int)r, w, h, c, n, bw, bh, rows);
+  EOVAE_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled failed (%d) pixels %lld c %d n %d rows %d", (int)r, pixels, c, n, rows);
   return 0;
 }
 
@@ -241,22 +242,19 @@ int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int n, int 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad: kernel size must be 3 or 1");
   EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "conv2d_wgrad: 16-bit operands only");
-  EOVAE_CHECK(w % 8 == 0 && cin % 16 == 0 && cin % 4 == 0, "conv2d_wgrad: W %% 8 and Cin %% 16 required (W %d, Cin %d)", w, cin);
-  const int bw = w >= 64 ? 64 : w;
-  EOVAE_CHECK(64 % bw == 0 && w % bw == 0, "conv2d_wgrad: W (%d) must be a power of two below 64 or a multiple of 64", w);
-  const int bh = 64 / bw;
-  EOVAE_CHECK(h % bh == 0, "conv2d_wgrad: H (%d) must be a multiple of %d", h, bh);
+  EOVAE_CHECK(w % 8 == 0 && cin % 16 == 0, "conv2d_wgrad: W %% 8 and Cin %% 16 required (W %d, Cin %d)", w, cin);
+  EOVAE_CHECK((static_cast<long long>(h) * w) % 64 == 0, "conv2d_wgrad: H * W (%d x %d) must be a multiple of 64", h, w);
   EOVAE_CHECK(workspace_bytes >= eovae_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, ksize), "conv2d_wgrad: workspace too small");
   WgradParams p;
   memset(&p, 0, sizeof(p));
   int bn;
   plan(n, h, w, cin, cout, ksize * ksize, &bn, &p.co_tiles, &p.ci_tiles, &p.ksplit, &p.chunks_per_split, &p.chunks_total);
-  p.H = h; p.W = w; p.N = n; p.bw = bw; p.bh = bh; p.taps = ksize * ksize; p.cout = cout; p.cin = cin;
+  p.H = h; p.W = w; p.N = n; p.chunks_img = h * w / 64; p.taps = ksize * ksize; p.cout = cout; p.cin = cin;
   p.partial = static_cast<float*>(workspace);
   const uint32_t fmt = dtype == EOVAE_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-  if (make_map(&p.a_map, dtype, dy_t, w, h, cout, n, bw, bh, 128)) return -3;
-  if (make_map(&p.b_map, dtype, x_t, w, h, cin, n, bw, bh, bn)) return -3;
+  if (make_map(&p.a_map, dtype, dy_t, static_cast<long long>(h) * w, cout, n, 128)) return -3;
+  if (make_map(&p.b_map, dtype, x_t, static_cast<long long>(h) * w, cin, ksize == 3 ? 3 * n : n, bn)) return -3;
   const int items = p.taps * p.co_tiles * p.ci_tiles * p.ksplit;
   int rc;
   switch (bn) {

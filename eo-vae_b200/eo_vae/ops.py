@@ -374,7 +374,12 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor
     _need_cuda(x, dy)
     n, cin, h, w = x.shape
     cout = dy.shape[1]
-    xt = transpose16(x.permute(0, 2, 3, 1).reshape(n, h * w, pix_stride(x))[:, :, :cin])    # [n, cin, h*w]
+    if ksize == 1:
+        xt = transpose16(x.permute(0, 2, 3, 1).reshape(n, h * w, pix_stride(x))[:, :, :cin])    # [n, cin, h*w]
+    else:
+        xt = torch.empty((3, n, cin, h * w), dtype=x.dtype, device=x.device)                     # x-shifted copies
+        _C.check(_C.lib().eovae_transpose16_xshift3(_ptr(x), pix_stride(x), _ptr(xt), n, h, w, cin, _stream()),
+                 "eovae_transpose16_xshift3")
     dyt = transpose16(dy.permute(0, 2, 3, 1).reshape(n, h * w, pix_stride(dy))[:, :, :cout])
     lib = _C.lib()
     ws_bytes = lib.eovae_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, ksize)

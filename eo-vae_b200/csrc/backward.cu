@@ -293,6 +293,59 @@ int block_threads(int c) {
   return t < vpp ? 0 : t;
 }
 
+struct Strides4 { long long n, c, y, x; };
+
+// ------------------------------------------------------------------------------------------------- attention / latent / loss
+// dS = scale * P o (dP - rowsum(dP o P)): one warp per row; P 16-bit, dP fp32, dS 16-bit with columns >= cols zeroed.
+template <typename T>
+__global__ void softmax_bwd_kernel(const T* __restrict__ p, long long p_ld, const float* __restrict__ dp, long long dp_ld,
+                                   T* __restrict__ ds, long long ds_ld, long long rows, int cols, int out_cols, float scale) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const T* pr = p + row * p_ld;
+  const float* dr = dp + row * dp_ld;
+  float dot = 0.f;
+  for (int j = lane; j < cols; j += 32) dot += T16<T>::to_f(pr[j]) * dr[j];
+  dot = warp_sum(dot);
+  T* o = ds + row * ds_ld;
+  for (int j = lane; j < out_cols; j += 32)
+    o[j] = j < cols ? T16<T>::from_f(scale * T16<T>::to_f(pr[j]) * (dr[j] - dot)) : T16<T>::from_f(0.f);
+}
+
+// z = mean + exp(0.5 * clamp(logvar)) * eps  ->  dmean = dz, dlogvar = dz * eps * 0.5 * std inside the clamp, else 0.
+// dmoments: dense NCHW fp32 [n][2zc][h][w].
+__global__ void reparam_bwd_kernel(const float* __restrict__ moments, Strides4 ms, const float* __restrict__ eps,
+                                   const float* __restrict__ dz, float* __restrict__ dmoments, int h, int w, int zc,
+                                   long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // over dz [n][zc][h][w]
+  if (i >= total) return;
+  const int x = static_cast<int>(i % w);
+  long long t = i / w;
+  const int y = static_cast<int>(t % h);
+  t /= h;
+  const int c = static_cast<int>(t % zc);
+  const long long n = t / zc;
+  const float lv = moments[n * ms.n + (zc + c) * ms.c + y * ms.y + x * ms.x];
+  const float g = dz[i];
+  const long long plane = static_cast<long long>(h) * w;
+  const long long o = (n * 2 * zc + c) * plane + static_cast<long long>(y) * w + x;
+  dmoments[o] = g;
+  const bool inside = lv >= -30.f && lv <= 20.f;
+  dmoments[o + zc * plane] = inside ? g * eps[i] * 0.5f * expf(0.5f * lv) : 0.f;
+}
+
+// d/da of mean|a-b| (kind 0) or mean sqrt((a-b)^2 + eps^2) (kind 1), times the upstream scalar *gscale.
+__global__ void pixel_loss_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long count, float eps2,
+                                      int kind, const float* __restrict__ gscale, float* __restrict__ ga) {
+  const float k = gscale[0] / static_cast<float>(count);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float d = a[i] - b[i];
+    ga[i] = k * (kind == 0 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : d * rsqrtf(d * d + eps2));
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -395,6 +448,46 @@ int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, fl
     colsum_partial_kernel<__half><<<blocks, threads, smem, stream>>>(static_cast<const __half*>(grad_out), pixels, c, partial, ppb);
   EOVAE_LAUNCH_CHECK();
   colsum_finalize_kernel<<<ceil_div(c, 128), 128, 0, stream>>>(partial, blocks, c, dbias, accumulate);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_softmax_backward(const void* p, long long p_ld, const float* dp, long long dp_ld, void* ds, long long ds_ld,
+                           int dtype, long long rows, int cols, int out_cols, float scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(p_ld >= cols && dp_ld >= cols && ds_ld >= out_cols && out_cols >= cols, "softmax_backward: bad pitches");
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (dtype == EOVAE_BF16)
+    softmax_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(p), p_ld, dp, dp_ld,
+                                                                static_cast<__nv_bfloat16*>(ds), ds_ld, rows, cols, out_cols, scale);
+  else if (dtype == EOVAE_F16)
+    softmax_bwd_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(p), p_ld, dp, dp_ld, static_cast<__half*>(ds),
+                                                         ds_ld, rows, cols, out_cols, scale);
+  else
+    EOVAE_CHECK(false, "softmax_backward: 16-bit probabilities only");
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_reparam_backward(const float* moments, const long long* mstrides, const float* eps, const float* dz, float* dmoments,
+                           int n, int h, int w, int zc, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const Strides4 ms{mstrides[0], mstrides[1], mstrides[2], mstrides[3]};
+  const long long total = static_cast<long long>(n) * zc * h * w;
+  reparam_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(moments, ms, eps, dz, dmoments, h, w, zc, total);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_pixel_loss_backward(const float* a, const float* b, long long count, float eps, int kind, const float* grad_scale,
+                              float* grad_a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(kind == 0 || kind == 1, "pixel_loss_backward: kind must be 0 (L1) or 1 (Charbonnier)");
+  long long blocks = (count + 1023) / 1024;
+  const long long cap = 8LL * eovae_num_sms();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  pixel_loss_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a, b, count, eps * eps, kind, grad_scale, grad_a);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

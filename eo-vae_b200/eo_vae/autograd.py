@@ -1,0 +1,325 @@
+"""Tape entries of the training path: ``torch.autograd.Function`` objects whose forward AND backward run libeovae_sm100
+kernels.  torch's autograd engine is only the tape (ordering, parameter ``.grad`` accumulation); no ATen compute kernel
+sits on the gradient path of the encoder / decoder bodies.
+
+One Function per reference module (layers.py: ResnetBlock :53-114, AttnBlock :117-142, Upsample :40-50; plain convs and
+GroupNorm+SiLU for the model edges) so that the gradient fan-in of every residual branch is fused into a kernel epilogue
+(``grad_add`` of the GroupNorm backward / the implicit-GEMM data gradient) instead of a separate elementwise add.
+
+Gradient kernels used:
+  data gradient     eovae_conv2d on eovae_pack_conv_weight_dgrad operands (flipped taps, swapped channels)
+  weight gradient   eovae_conv2d_wgrad (tcgen05, pixels contracted, deterministic split-K)
+  bias gradient     eovae_bias_grad
+  GroupNorm(+SiLU)  eovae_gn_backward
+  attention         eovae_gemm_tn_batched x4 + eovae_softmax_backward
+  stride-2 / x2     eovae_scatter_stride2 / eovae_pool2x2_sum
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+
+def grad_mode() -> bool:
+    """The modules take the tape-recording path whenever torch would record a graph."""
+    return torch.is_grad_enabled()
+
+
+def _grad_act(g: torch.Tensor, dtype) -> torch.Tensor:
+    """Incoming gradient -> 16-bit NHWC-stored tensor whose pixel pitch keeps TMA's 16-byte alignment."""
+    n, c, h, w = g.shape
+    if g.dtype == dtype:
+        try:
+            if ops.pix_stride(g) % 8 == 0:
+                return g
+        except RuntimeError:
+            pass
+    cp = (c + 15) // 16 * 16
+    if g.dtype == torch.float32 and g.is_contiguous():
+        return ops.nchw_to_act(g, cp, dtype)[:, :c]
+    out = ops.nhwc_empty(n, cp, h, w, dtype, g.device)[:, :c]
+    out.copy_(g)  # edge only (a gradient produced by torch glue on the latent)
+    return out
+
+
+def _dense(g: torch.Tensor) -> torch.Tensor:
+    if ops.pix_stride(g) == g.shape[1]:
+        return g
+    return g.contiguous(memory_format=torch.channels_last)
+
+
+def _wgrad(x: torch.Tensor, g: torch.Tensor, mode: int) -> torch.Tensor:
+    if mode == ops.CONV_3X3_S2:
+        return ops.conv2d_wgrad(x, ops.scatter_stride2(_dense(g), x.shape[2], x.shape[3]), 3)
+    return ops.conv2d_wgrad(x, g, 1 if mode == ops.CONV_1X1 else 3)
+
+
+def _bias(mod):
+    return None if mod.bias is None else mod.bias.detach()
+
+
+class ConvFn(Function):
+    """out = conv(x) + bias (+ residual) for the three built convolution modes."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, mod, out_dtype):
+        out = ops.conv2d(x, mod.packed_weight(x.dtype), _bias(mod), mod.out_channels, mod._mode, residual=residual,
+                         out_dtype=out_dtype)
+        ctx.save_for_backward(x, weight)
+        ctx.mode = mod._mode
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        g = _grad_act(dy, x.dtype)
+        need = ctx.needs_input_grad
+        dx = ops.conv2d_dgrad(_dense(g) if ctx.mode == ops.CONV_3X3_S2 else g, weight, ctx.mode, in_hw=x.shape[2:]) \
+            if need[0] else None
+        dw = _wgrad(x, g, ctx.mode) if need[1] else None
+        if dw is not None and dw.shape[1] != weight.shape[1]:  # input channels were zero-padded for the kernels
+            dw = dw[:, :weight.shape[1]].contiguous()
+        db = ops.bias_grad(g) if ctx.has_bias and need[2] else None
+        dres = g if need[3] else None
+        return dx, dw, db, dres, None, None
+
+
+class GroupNormFn(Function):
+    """y = [silu](GroupNorm(x)) (model edges: norm_out)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, silu, groups, eps):
+        stats = ops.gn_stats(x, groups, eps)
+        ctx.save_for_backward(x, stats, gamma, beta)
+        ctx.cfg = (silu, groups)
+        return ops.gn_apply(x, stats, gamma.detach(), beta.detach(), silu, groups)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, gamma, beta = ctx.saved_tensors
+        silu, groups = ctx.cfg
+        gx, dg, db = ops.gn_backward(x, _dense(_grad_act(dy, x.dtype)), stats, gamma, beta, silu, groups)
+        return gx, dg, db, None, None, None
+
+
+class ResnetBlockFn(Function):
+    """x -> conv2(silu(gn2(conv1(silu(gn1(x)))))) + shortcut(x)   (layers.py:96-114)."""
+
+    @staticmethod
+    def forward(ctx, x, g1, b1, w1, c1b, g2, b2, w2, c2b, wn, nb, mod):
+        dt = x.dtype
+        st1 = ops.gn_stats(x, 32, 1e-6)
+        a1 = ops.gn_apply(x, st1, g1.detach(), b1.detach(), True, 32)
+        h = ops.conv2d(a1, mod.conv1.packed_weight(dt), _bias(mod.conv1), mod.out_channels, ops.CONV_3X3, gn_groups=32)
+        fused = getattr(h, "_gn_stats", None)
+        st2 = fused[0] if fused is not None else ops.gn_stats(h, 32, 1e-6)
+        a2 = ops.gn_apply(h, st2, g2.detach(), b2.detach(), True, 32)
+        if wn is None:
+            out = ops.conv2d(a2, mod.conv2.packed_weight(dt), _bias(mod.conv2), mod.out_channels, ops.CONV_3X3, residual=x)
+        elif mod.in_channels % 64 == 0 and mod.out_channels % 64 == 0:
+            w, b = mod._conv2_with_shortcut(dt)
+            out = ops.conv2d(a2, w, b, mod.out_channels, ops.CONV_3X3, x2=x)
+        else:
+            sc = ops.conv2d(x, mod.nin_shortcut.packed_weight(dt), _bias(mod.nin_shortcut), mod.out_channels, ops.CONV_1X1)
+            out = ops.conv2d(a2, mod.conv2.packed_weight(dt), _bias(mod.conv2), mod.out_channels, ops.CONV_3X3, residual=sc)
+        ctx.save_for_backward(x, st1, a1, h, st2, a2, g1, b1, w1, g2, b2, w2, wn)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, st1, a1, h, st2, a2, g1, b1, w1, g2, b2, w2, wn = ctx.saved_tensors
+        g = _dense(_grad_act(dy, x.dtype))
+        # conv2 (+ shortcut)
+        da2 = ops.conv2d_dgrad(g, w2, ops.CONV_3X3)
+        dw2 = ops.conv2d_wgrad(a2, g, 3)
+        db2 = ops.bias_grad(g)
+        if wn is None:
+            gsc, dwn, dbn = g, None, None
+        else:
+            gsc = ops.conv2d_dgrad(g, wn, ops.CONV_1X1)
+            dwn = ops.conv2d_wgrad(x, g, 1)
+            dbn = db2
+        dh, dg2, dbe2 = ops.gn_backward(h, da2, st2, g2, b2, True, 32)
+        del da2
+        # conv1
+        da1 = ops.conv2d_dgrad(dh, w1, ops.CONV_3X3)
+        dw1 = ops.conv2d_wgrad(a1, dh, 3)
+        db1 = ops.bias_grad(dh)
+        # gn1, with the shortcut gradient added in the same pass
+        dx, dg1, dbe1 = ops.gn_backward(x, da1, st1, g1, b1, True, 32, grad_add=gsc)
+        return dx, dg1, dbe1, dw1, db1, dg2, dbe2, dw2, db2, dwn, dbn, None
+
+
+class AttnBlockFn(Function):
+    """x + proj(softmax(q k^T / sqrt(c)) v) with q, k, v = 1x1 convs of GroupNorm(x)   (layers.py:128-142)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, wq, bq, wk, bk, wv, bv, wp, bp, mod):
+        n, c, hh, ww = x.shape
+        L = hh * ww
+        lp = (L + 15) // 16 * 16
+        stn = ops.gn_stats(x, 32, 1e-6)
+        hn = ops.gn_apply(x, stn, gamma.detach(), beta.detach(), False, 32)
+        wqkv, bqkv = mod._qkv_operands(x.dtype)
+        qkv = ops.conv2d(hn, wqkv, bqkv, 3 * c, ops.CONV_1X1)
+        flat = qkv.permute(0, 2, 3, 1).reshape(n, L, 3 * c)
+        q, k, v = flat[:, :, :c], flat[:, :, c:2 * c], flat[:, :, 2 * c:]
+        scores = ops.gemm_tn_batched(q, k, torch.float32, scale=1.0 / math.sqrt(c))
+        probs = ops.softmax_rows(scores, x.dtype, cols=L, out_cols=lp)
+        del scores
+        o = ops.gemm_tn_batched(probs, ops.transpose16(v, out_rows=lp), x.dtype)
+        o = o.view(n, hh, ww, c).permute(0, 3, 1, 2)
+        out = ops.conv2d(o, mod.proj_out.packed_weight(x.dtype), _bias(mod.proj_out), c, ops.CONV_1X1, residual=x)
+        ctx.save_for_backward(x, stn, hn, qkv, probs, o, gamma, beta, wq, wk, wv, wp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stn, hn, qkv, probs, o, gamma, beta, wq, wk, wv, wp = ctx.saved_tensors
+        n, c, hh, ww = x.shape
+        L = hh * ww
+        lp = probs.shape[-1]
+        dt = x.dtype
+        scale = 1.0 / math.sqrt(c)
+        g = _dense(_grad_act(dy, dt))
+        # proj_out
+        do = ops.conv2d_dgrad(g, wp, ops.CONV_1X1)
+        dwp = ops.conv2d_wgrad(o, g, 1)
+        dbp = ops.bias_grad(g)
+        dof = do.permute(0, 2, 3, 1).reshape(n, L, c)
+        flat = qkv.permute(0, 2, 3, 1).reshape(n, L, 3 * c)
+        q, k, v = flat[:, :, :c], flat[:, :, c:2 * c], flat[:, :, 2 * c:]
+        dqkv = torch.empty((n, L, 3 * c), dtype=dt, device=x.device)
+        same = lp == L
+        # dV = P^T dO
+        pt = ops.transpose16(probs, out_rows=lp)          # [n, lp, lp]  (rows >= L of P^T are zero)
+        dot = ops.transpose16(dof, out_rows=lp)           # [n, c, lp]
+        if same:
+            ops.gemm_tn_batched(pt, dot, dt, out=dqkv[:, :, 2 * c:])
+        else:
+            dqkv[:, :, 2 * c:] = ops.gemm_tn_batched(pt, dot, dt)[:, :L]
+        del pt, dot
+        # dP = dO V^T ; dS = scale * P o (dP - rowsum(dP o P))
+        dp = ops.gemm_tn_batched(dof, v, torch.float32)   # [n, L, L]
+        ds = ops.softmax_backward(probs, dp, L, scale)    # [n, L, lp]
+        del dp
+        # dQ = dS K ; dK = dS^T Q
+        ops.gemm_tn_batched(ds, ops.transpose16(k, out_rows=lp), dt, out=dqkv[:, :, :c])
+        dst = ops.transpose16(ds, out_rows=lp)            # [n, lp, lp]
+        qt = ops.transpose16(q, out_rows=lp)              # [n, c, lp]
+        if same:
+            ops.gemm_tn_batched(dst, qt, dt, out=dqkv[:, :, c:2 * c])
+        else:
+            dqkv[:, :, c:2 * c] = ops.gemm_tn_batched(dst, qt, dt)[:, :L]
+        del ds, dst, qt
+        # fused q / k / v 1x1 convs
+        dqkv4 = dqkv.view(n, hh, ww, 3 * c).permute(0, 3, 1, 2)
+        wqkv = torch.cat([wq, wk, wv], dim=0)
+        dhn = ops.conv2d_dgrad(dqkv4, wqkv, ops.CONV_1X1)
+        dwqkv = ops.conv2d_wgrad(hn, dqkv4, 1)
+        dbqkv = ops.bias_grad(dqkv4)
+        dx, dgam, dbet = ops.gn_backward(x, dhn, stn, gamma, beta, False, 32, grad_add=g)
+        dwq, dwk, dwv = dwqkv[:c], dwqkv[c:2 * c], dwqkv[2 * c:]
+        dbq, dbk, dbv = dbqkv[:c], dbqkv[c:2 * c], dbqkv[2 * c:]
+        return dx, dgam, dbet, dwq, dbq, dwk, dbk, dwv, dbv, dwp, dbp, None
+
+
+class UpsampleFn(Function):
+    """conv3x3(nearest_x2(x))   (layers.py:47-50); the upsampled tensor is rebuilt in backward, not kept."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod):
+        ctx.save_for_backward(x, weight)
+        return ops.conv2d(ops.upsample2x(x), mod.conv.packed_weight(x.dtype), _bias(mod.conv), mod.conv.out_channels,
+                          ops.CONV_3X3)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        g = _grad_act(dy, x.dtype)
+        dx = ops.pool2x2_sum(ops.conv2d_dgrad(g, weight, ops.CONV_3X3))
+        dw = ops.conv2d_wgrad(ops.upsample2x(x), g, 3)
+        return dx, dw, ops.bias_grad(g), None
+
+
+class ActToNchwFn(Function):
+    """internal activation -> fp32 NCHW (model edge); the gradient comes back through eovae_nchw_to_nhwc16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.dt = x.dtype if x.dtype != torch.float32 else None
+        return ops.act_to_nchw_f32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .settings import compute_dtype
+        n, c, h, w = g.shape
+        return ops.nchw_to_act(g, (c + 15) // 16 * 16, ctx.dt or compute_dtype())[:, :c]
+
+
+def act_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+    if grad_mode() and x.requires_grad:
+        return ActToNchwFn.apply(x)
+    return ops.act_to_nchw_f32(x)
+
+
+class DynConvOutFn(Function):
+    """Decoder output layer (dynamic_conv.py:684-710): band kernels generated from the wavelengths, then a 3x3 conv.
+    Backward: data gradient through the generated kernel (the hypernetwork's own gradient is not built yet - its
+    parameters receive no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, mod, waves):
+        c = waves.size(0)
+        wk, b_raw = mod._generate(waves)
+        packed, bias, oihw = ops.pack_dyn_weight(wk, b_raw, c, mod.embed_dim, True, mod.scaler, mod.scaler * mod.scaler,
+                                                 x.dtype, True)
+        mod._last = (wk, b_raw, c)
+        ctx.save_for_backward(x, oihw)
+        return ops.conv2d(x, packed, bias, c, ops.CONV_3X3, out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, oihw = ctx.saved_tensors
+        g = _grad_act(dy, x.dtype)
+        return ops.conv2d_dgrad(g, oihw, ops.CONV_3X3), None, None
+
+
+class SampleFn(Function):
+    """z = mean + exp(0.5 * clamp(logvar, -30, 20)) * eps   (distributions.py:28-46) on the fused kernel."""
+
+    @staticmethod
+    def forward(ctx, moments, eps, zc):
+        eps = eps.to(device=moments.device, dtype=torch.float32).contiguous()
+        z, _ = ops.kl_reparam(moments, eps, zc, want_z=True)
+        ctx.save_for_backward(moments, eps)
+        ctx.zc = zc
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        moments, eps = ctx.saved_tensors
+        return ops.reparam_backward(moments, eps, dz, ctx.zc), None, None
+
+
+class PixelLossFn(Function):
+    """mean |a - b| (kind 0) or mean sqrt((a - b)^2 + eps^2) (kind 1)   (consistency_loss.py:12-21,418)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, eps, kind):
+        a = pred.to(torch.float32).contiguous()
+        b = target.to(torch.float32).contiguous()
+        ctx.save_for_backward(a, b)
+        ctx.cfg = (eps, kind)
+        return ops.l1_charbonnier(a, b, eps)[kind]
+
+    @staticmethod
+    def backward(ctx, gl):
+        a, b = ctx.saved_tensors
+        eps, kind = ctx.cfg
+        return ops.pixel_loss_backward(a, b, eps, kind, gl), None, None, None

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from .. import autograd as tape
 from .. import ops
 from ..settings import compute_dtype
 from .modules.dynamic_conv import DynamicConv, DynamicConv_decoder
@@ -91,7 +92,7 @@ class Encoder(nn.Module):
         return self.quant_conv(h, out_dtype=torch.float32)
 
     def forward(self, x: Tensor, wvs: Tensor = None) -> Tensor:
-        return ops.act_to_nchw_f32(self.moments_nhwc(x, wvs))
+        return tape.act_to_nchw_f32(self.moments_nhwc(x, wvs))
 
     def load_flux_weights(self, state_dict, strict=True):
         own = self.state_dict()
@@ -166,7 +167,7 @@ class Decoder(nn.Module):
         return self.conv_out(h, out_dtype=torch.float32)
 
     def forward(self, z: Tensor, wvs: Tensor = None) -> Tensor:
-        return ops.act_to_nchw_f32(self.forward_act(z, wvs))
+        return tape.act_to_nchw_f32(self.forward_act(z, wvs))
 
     def load_flux_weights(self, state_dict, strict=True):
         own = self.state_dict()

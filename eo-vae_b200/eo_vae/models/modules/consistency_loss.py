@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ... import autograd as tape
 from ... import ops
 
 
@@ -60,11 +61,17 @@ class EOConsistencyLoss(nn.Module):
         logs = {}
         total = torch.zeros((), device=inputs.device)
         if self.weights['pixel'] > 0:
-            both = ops.l1_charbonnier(reconstructions, inputs, self.char_loss.eps)
-            l_rec = both[0] if self.rec_loss_type == 'l1' else both[1]
+            kind = 0 if self.rec_loss_type == 'l1' else 1
+            if tape.grad_mode() and reconstructions.requires_grad:
+                l_rec = tape.PixelLossFn.apply(reconstructions, inputs, self.char_loss.eps, kind)
+            else:
+                l_rec = ops.l1_charbonnier(reconstructions, inputs, self.char_loss.eps)[kind]
             total = total + self.weights['pixel'] * l_rec
             logs[f'{split}/loss_rec'] = l_rec.detach()
         if self.weights['msssim'] > 0 and global_step >= self.starts['msssim']:
+            if tape.grad_mode() and reconstructions.requires_grad:
+                raise NotImplementedError('MS-SSIM has no backward kernel yet (DESIGN.md section 7): train with '
+                                          'global_step < msssim_start_step or msssim_weight = 0')
             l_msssim = self.msssim_loss(reconstructions, inputs)
             total = total + self.weights['msssim'] * l_msssim
             logs[f'{split}/loss_msssim'] = l_msssim.detach()

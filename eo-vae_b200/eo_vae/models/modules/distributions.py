@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import torch
 
+from ... import autograd as tape
 from ... import ops
 
 
@@ -42,6 +43,8 @@ class DiagonalGaussianDistribution:
             return self.mean.contiguous()
         if eps is None:
             eps = torch.randn(self.mean.shape).to(device=self.parameters.device)
+        if tape.grad_mode() and self.parameters.requires_grad:
+            return tape.SampleFn.apply(self.parameters, eps, self._zc)
         z, _ = ops.kl_reparam(self.parameters, eps, self._zc, want_z=True)
         return z
 

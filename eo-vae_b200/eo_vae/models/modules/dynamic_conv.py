@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from ... import autograd as tape
 from ... import ops
 from ...settings import compute_dtype
 
@@ -175,7 +176,8 @@ class DynamicConv(_DynamicBase):
         if img_feat.shape[1] != c:
             raise RuntimeError(f'DynamicConv: {img_feat.shape[1]} image bands but {c} wavelengths')
         dt = compute_dtype()
-        wk, b_raw = self._generate(wvs)
+        with torch.no_grad():  # TODO(training): hypernetwork gradient - generated kernel is a constant
+            wk, b_raw = self._generate(wvs)
         packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, self.embed_dim, False, self.scaler, self.scaler, dt, False)
         x = ops.nchw_to_act(img_feat, ops.dyn_cin_pad(c), dt)
         return ops.conv2d(x, packed, bias, self.embed_dim, ops.CONV_3X3, algo_cin=c, gn_groups=32, gn_eps=1e-6)
@@ -214,6 +216,8 @@ class DynamicConv_decoder(_DynamicBase):
         c = waves.size(0)
         self.scaler = 0.1
         x = ops.to_act(img_feat, compute_dtype())
+        if tape.grad_mode():
+            return tape.DynConvOutFn.apply(x, self, waves)
         wk, b_raw = self._generate(waves)
         packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, self.embed_dim, True, self.scaler,
                                               self.scaler * self.scaler, x.dtype, False)

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from ... import autograd as tape
 from ... import ops
 from ...settings import compute_dtype
 
@@ -32,6 +33,8 @@ class GroupNormSM100(nn.GroupNorm):
 
     def forward(self, x: Tensor, silu: bool = False) -> Tensor:  # noqa: D102
         x = ops.to_act(x, compute_dtype())
+        if tape.grad_mode():
+            return tape.GroupNormFn.apply(x, self.weight, self.bias, silu, self.num_groups, self.eps)
         return ops.group_norm(x, self.weight, self.bias, silu, self.num_groups, self.eps)
 
 
@@ -71,6 +74,10 @@ class Conv2dSM100(nn.Conv2d):
         pre_norm: compute conv(silu(pre_norm(x))); the normalisation runs inside the conv's mainloop when the shape
         allows it (no normalised tensor in HBM), otherwise as the separate GroupNorm-apply kernel."""
         x = ops.to_act(x, compute_dtype())
+        if tape.grad_mode():  # training path: tape entries with hand-written backward kernels (eo_vae/autograd.py)
+            if pre_norm is not None:
+                x = pre_norm(x, silu=True)
+            return tape.ConvFn.apply(x, self.weight, self.bias, residual, self, out_dtype)
         in_gn = None
         if pre_norm is not None:
             if ops.USE_GN_PROLOGUE and ops.gn_prologue_ok(x, self.out_channels, self._mode, pre_norm.num_groups):
@@ -108,6 +115,8 @@ class Upsample(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         x = ops.to_act(x, compute_dtype())
+        if tape.grad_mode():
+            return tape.UpsampleFn.apply(x, self.conv.weight, self.conv.bias, self)
         return self.conv(ops.upsample2x(x), gn_next=True)
 
 
@@ -150,6 +159,11 @@ class ResnetBlock(nn.Module):
         if self.cond_dim is not None and emb is not None:
             raise NotImplementedError("AdaIN-conditioned ResnetBlock (use_adain) is outside the built hot path")
         x = ops.to_act(x, compute_dtype())
+        if tape.grad_mode():
+            sc = getattr(self, 'nin_shortcut', None)
+            return tape.ResnetBlockFn.apply(x, self.norm1.weight, self.norm1.bias, self.conv1.weight, self.conv1.bias,
+                                            self.norm2.weight, self.norm2.bias, self.conv2.weight, self.conv2.bias,
+                                            None if sc is None else sc.weight, None if sc is None else sc.bias, self)
         h = self.conv1(x, gn_next=True, pre_norm=self.norm1)  # GN1 + SiLU inside the conv where the shape allows
         if self.in_channels == self.out_channels:
             # GN2 + SiLU in the prologue, residual add + next GN's statistics in the epilogue
@@ -193,6 +207,10 @@ class AttnBlock(nn.Module):
         if c % 16 != 0:
             raise RuntimeError("AttnBlock: channel count must be a multiple of 16 on the sm_100a path")
         L = hh * ww
+        if tape.grad_mode():
+            return tape.AttnBlockFn.apply(x, self.norm.weight, self.norm.bias, self.q.weight, self.q.bias, self.k.weight,
+                                          self.k.bias, self.v.weight, self.v.bias, self.proj_out.weight,
+                                          self.proj_out.bias, self)
         h = self.norm(x, silu=False)
         wqkv, bqkv = self._qkv_operands(x.dtype)
         qkv = ops.conv2d(h, wqkv, bqkv, 3 * c, ops.CONV_1X1)  # NHWC [n, L, 3c]

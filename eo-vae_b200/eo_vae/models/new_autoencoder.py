@@ -24,6 +24,7 @@ from torch import Tensor
 from torch.optim import Optimizer
 from torch.optim.lr_scheduler import LambdaLR
 
+from .. import autograd as tape
 from .. import ops
 from .._lightning import LightningModule
 from ..settings import compute_dtype
@@ -250,12 +251,16 @@ class EOFluxVAE(LightningModule):
 
     def _decoder_input(self, z_packed: Tensor) -> Tensor:
         """packed normalised latent [B, 4z, h, w] -> inverse BN (running stats, eps 1e-4) -> unshuffle -> NHWC act."""
+        if tape.grad_mode() and z_packed.requires_grad:
+            # training: per-channel affine + index permutation on the (tiny) latent stay torch tensor glue so the tape
+            # sees them; everything from post_quant_conv on is kernels again
+            return ops.to_act(_shuffle2(self._inv_normalize_latent(z_packed)), compute_dtype())
         z_spatial = _shuffle2(z_packed)  # index permutation; the affine is applied per (c, parity) in the kernel
         return ops.latent_denorm(z_spatial, self.bn.running_mean, self.bn.running_var, self.bn_eps, compute_dtype())
 
     def decode(self, z: Tensor, wvs: Tensor) -> Tensor:
         self.bn.eval()
-        return ops.act_to_nchw_f32(self.decoder.forward_act(self._decoder_input(z), wvs))
+        return tape.act_to_nchw_f32(self.decoder.forward_act(self._decoder_input(z), wvs))
 
     def decode_raw(self, z: Tensor, wvs: Tensor) -> Tensor:
         return self.decoder(z, wvs)
@@ -273,7 +278,7 @@ class EOFluxVAE(LightningModule):
             z_norm = ops.latent_norm(moments, self.bn.running_mean, self.bn.running_var, self.bn.eps,
                                      self.encoder.z_channels)
             h = ops.latent_denorm(z_norm, self.bn.running_mean, self.bn.running_var, self.bn_eps, compute_dtype())
-            return ops.act_to_nchw_f32(self.decoder.forward_act(h, wvs)), posterior
+            return tape.act_to_nchw_f32(self.decoder.forward_act(h, wvs)), posterior
         z = posterior.sample() if sample_posterior else posterior.mode()
         if scale is not None:
             z = self._apply_scale(z, scale)
@@ -295,7 +300,7 @@ class EOFluxVAE(LightningModule):
     def decode_spatial_normalized(self, z: Tensor, wvs: Tensor) -> Tensor:
         self.bn.eval()
         h = ops.latent_denorm(z, self.bn.running_mean, self.bn.running_var, self.bn_eps, compute_dtype())
-        return ops.act_to_nchw_f32(self.decoder.forward_act(h, wvs))
+        return tape.act_to_nchw_f32(self.decoder.forward_act(h, wvs))
 
     def _apply_scale(self, z: Tensor, scale) -> Tensor:
         h, w = z.shape[-2:]
@@ -343,11 +348,6 @@ class EOFluxVAE(LightningModule):
         Adam -> scheduler -> log.  The forward and loss kernels exist; the BACKWARD kernels (conv dgrad / wgrad,
         GroupNorm, attention, hypernetwork, MS-SSIM adjoints) are not built yet, and this path never falls back to
         torch autograd over library ops - so the step raises instead of silently training nothing."""
-        if not getattr(ops, "HAVE_BACKWARD", False):
-            raise NotImplementedError(
-                "EOFluxVAE.training_step: the sm_100a backward kernels are not part of this build (see DESIGN.md "
-                "section 7); inference paths (encode / decode / reconstruct / encode_spatial_normalized / "
-                "validation_step) are complete")
         opts = self.optimizers()
         opt_gen = opts[0] if isinstance(opts, list) else opts
         schs = self.lr_schedulers()

@@ -157,8 +157,9 @@ def gn_prologue_ok(x: torch.Tensor, cout: int, mode: int, groups: int = 32) -> b
     return pix_stride(x) == cin and bool(_C.lib().eovae_conv2d_gn_prologue_ok(n, h, w, cin, cout, mode, groups))
 
 
-def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 1.0) -> torch.Tensor:
-    """c[i] = scale * a[i] @ b[i].T ; a [B, M, K], b [B, N, K]; row pitches may exceed K (channel slices)."""
+def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """c[i] = scale * a[i] @ b[i].T ; a [B, M, K], b [B, N, K]; row pitches may exceed K (channel slices).  ``out``: an
+    existing [B, M, N] view (e.g. a channel slice of a wider buffer) whose batch stride equals M row pitches."""
     _need_cuda(a, b)
     bsz, m, k = a.shape
     n = b.shape[1]
@@ -166,9 +167,14 @@ def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 
         raise RuntimeError("eo_vae.gemm_tn_batched: bad operand layout")
     if a.stride(0) != m * a.stride(1):
         raise RuntimeError("eo_vae.gemm_tn_batched: A batches must be contiguous")
-    c = torch.empty((bsz, m, n), dtype=out_dtype, device=a.device)
+    if out is None:
+        c = torch.empty((bsz, m, n), dtype=out_dtype, device=a.device)
+    else:
+        c = out
+        if tuple(c.shape) != (bsz, m, n) or c.dtype != out_dtype or c.stride(2) != 1 or c.stride(0) != m * c.stride(1):
+            raise RuntimeError("eo_vae.gemm_tn_batched: bad output view")
     rc = _timed("attn_gemm", 2.0 * bsz * m * n * k, lambda: _C.lib().eovae_gemm_tn_batched(
-        _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1), b.stride(0), _ptr(c), DT[out_dtype], n, bsz, m, n, k,
+        _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1), b.stride(0), _ptr(c), DT[out_dtype], c.stride(1), bsz, m, n, k,
         DT[a.dtype], float(scale), _stream()))
     _C.check(rc, "eovae_gemm_tn_batched")
     return c
@@ -354,18 +360,24 @@ def pack_conv_weight_dgrad(w: torch.Tensor, dtype) -> torch.Tensor:
     return out
 
 
+def scatter_stride2(dy: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """dy [n, c, ho, wo] -> z [n, c, h, w], zero except z[2i+1][2j+1] = dy[i][j] (adjoint of the Downsample gather)."""
+    _need_cuda(dy)
+    n, c, ho, wo = dy.shape
+    if pix_stride(dy) != c:
+        raise RuntimeError("eo_vae.scatter_stride2: dense channels-last gradient required")
+    z = nhwc_empty(n, c, h, w, dy.dtype, dy.device)
+    _C.check(_C.lib().eovae_scatter_stride2(_ptr(dy), _ptr(z), n, ho, wo, h, w, c, _stream()), "eovae_scatter_stride2")
+    return z
+
+
 def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, mode: int, in_hw=None, grad_add=None) -> torch.Tensor:
     """Data gradient of eovae_conv2d (w: OIHW fp32 master weight) as another implicit GEMM; ``grad_add`` (same shape
     as the result) is accumulated in the epilogue (gradient fan-in of a residual branch)."""
     cout, cin = w.shape[0], w.shape[1]
     wp = pack_conv_weight_dgrad(w, dy.dtype)
     if mode == CONV_3X3_S2:
-        n, _, ho, wo = dy.shape
-        h, wd = in_hw
-        z = nhwc_empty(n, cout, h, wd, dy.dtype, dy.device)
-        _C.check(_C.lib().eovae_scatter_stride2(_ptr(dy), _ptr(z), n, ho, wo, h, wd, cout, _stream()),
-                 "eovae_scatter_stride2")
-        return conv2d(z, wp, None, cin, CONV_3X3, residual=grad_add)
+        return conv2d(scatter_stride2(dy, in_hw[0], in_hw[1]), wp, None, cin, CONV_3X3, residual=grad_add)
     return conv2d(dy, wp, None, cin, mode, residual=grad_add)
 
 
@@ -374,6 +386,12 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor
     _need_cuda(x, dy)
     n, cin, h, w = x.shape
     cout = dy.shape[1]
+    if cin % 16 != 0:  # narrow edge layers (e.g. an 8-channel latent): zero-pad the channels, slice the result
+        if dw is not None:
+            raise RuntimeError("eo_vae.conv2d_wgrad: accumulation needs Cin % 16 == 0")
+        xp = torch.zeros((n, h, w, (cin + 15) // 16 * 16), dtype=x.dtype, device=x.device).permute(0, 3, 1, 2)
+        xp[:, :cin].copy_(x)
+        return conv2d_wgrad(xp, dy, ksize)[:, :cin].contiguous()
     if ksize == 1:
         xt = transpose16(x.permute(0, 2, 3, 1).reshape(n, h * w, pix_stride(x))[:, :, :cin])    # [n, cin, h*w]
     else:
@@ -395,15 +413,14 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor
 def bias_grad(dy: torch.Tensor) -> torch.Tensor:
     _need_cuda(dy)
     n, c, h, w = dy.shape
-    if pix_stride(dy) != c:
-        raise RuntimeError("eo_vae.bias_grad: dense channels-last gradient required")
+    cp = pix_stride(dy)  # a padded pixel pitch is summed as extra columns and dropped
     lib = _C.lib()
-    ws_bytes = lib.eovae_bias_grad_workspace_bytes(n * h * w, c)
+    ws_bytes = lib.eovae_bias_grad_workspace_bytes(n * h * w, cp)
     ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=dy.device)
-    out = torch.empty((c,), dtype=torch.float32, device=dy.device)
-    _C.check(lib.eovae_bias_grad(_ptr(dy), DT[dy.dtype], n * h * w, c, _ptr(out), 0, _ptr(ws), ws_bytes, _stream()),
+    out = torch.empty((cp,), dtype=torch.float32, device=dy.device)
+    _C.check(lib.eovae_bias_grad(_ptr(dy), DT[dy.dtype], n * h * w, cp, _ptr(out), 0, _ptr(ws), ws_bytes, _stream()),
              "eovae_bias_grad")
-    return out
+    return out[:c]
 
 
 def gn_backward(x: torch.Tensor, grad_out: torch.Tensor, stats, gamma, beta, silu: bool, groups: int = 32,
@@ -423,6 +440,39 @@ def gn_backward(x: torch.Tensor, grad_out: torch.Tensor, stats, gamma, beta, sil
                                    groups, 1 if silu else 0, _ptr(grad_add), _ptr(gx), _ptr(dg), _ptr(db), 0, _ptr(ws),
                                    ws_bytes, _stream()), "eovae_gn_backward")
     return gx, dg, db
+
+
+def softmax_backward(p: torch.Tensor, dp: torch.Tensor, cols: int, scale: float) -> torch.Tensor:
+    """ds = scale * p o (dp - rowsum(dp o p)); p 16-bit [..., lp], dp fp32 [..., >= cols] -> ds 16-bit [..., lp]."""
+    _need_cuda(p, dp)
+    if not p.is_contiguous() or not dp.is_contiguous() or dp.dtype != torch.float32:
+        raise RuntimeError("eo_vae.softmax_backward: contiguous p (16-bit) and dp (fp32) required")
+    lp = p.shape[-1]
+    rows = p.numel() // lp
+    ds = torch.empty_like(p)
+    _C.check(_C.lib().eovae_softmax_backward(_ptr(p), lp, _ptr(dp), dp.shape[-1], _ptr(ds), lp, DT[p.dtype], rows, cols, lp,
+                                             float(scale), _stream()), "eovae_softmax_backward")
+    return ds
+
+
+def reparam_backward(moments: torch.Tensor, eps: torch.Tensor, dz: torch.Tensor, zc: int) -> torch.Tensor:
+    _need_cuda(moments, eps, dz)
+    n, c2, h, w = moments.shape
+    dz = dz.to(torch.float32).contiguous()
+    dm = torch.empty((n, c2, h, w), dtype=torch.float32, device=moments.device)
+    _C.check(_C.lib().eovae_reparam_backward(_ptr(moments), _strides4(moments), _ptr(eps), _ptr(dz), _ptr(dm), n, h, w, zc,
+                                             _stream()), "eovae_reparam_backward")
+    return dm
+
+
+def pixel_loss_backward(a: torch.Tensor, b: torch.Tensor, eps: float, kind: int, grad_scale: torch.Tensor) -> torch.Tensor:
+    """gradient wrt a (fp32, a's shape) of mean|a-b| (kind 0) / Charbonnier (kind 1) times the device scalar grad_scale."""
+    _need_cuda(a, b, grad_scale)
+    ga = torch.empty_like(a)
+    gs = grad_scale.to(torch.float32).reshape(1)
+    _C.check(_C.lib().eovae_pixel_loss_backward(_ptr(a), _ptr(b), a.numel(), float(eps), kind, _ptr(gs), _ptr(ga), _stream()),
+             "eovae_pixel_loss_backward")
+    return ga
 
 
 def pool2x2_sum(g: torch.Tensor) -> torch.Tensor:

@@ -183,6 +183,17 @@ int eovae_pool2x2_sum(const void* g, void* out, int dtype, int n, int h, int w, 
 size_t eovae_conv2d_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize);
 int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int n, int h, int w, int cin, int cout, int ksize,
                        float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* attention backward: ds = scale * p o (dp - rowsum(dp o p)); p 16-bit [rows][p_ld], dp fp32, ds 16-bit zero padded to
+ * out_cols (layers.py:134-141 adjoint) */
+int eovae_softmax_backward(const void* p, long long p_ld, const float* dp, long long dp_ld, void* ds, long long ds_ld,
+                           int dtype, long long rows, int cols, int out_cols, float scale, void* stream);
+/* adjoint of the reparameterisation in eovae_kl_reparam (distributions.py:44-46): dz NCHW fp32 [n][zc][h][w] ->
+ * dmoments dense NCHW fp32 [n][2zc][h][w] (mean half = dz, logvar half = dz*eps*std/2 inside the clamp) */
+int eovae_reparam_backward(const float* moments, const long long* mstrides, const float* eps, const float* dz, float* dmoments,
+                           int n, int h, int w, int zc, void* stream);
+/* gradient of eovae_l1_charbonnier wrt a: kind 0 = L1, 1 = Charbonnier; *grad_scale = upstream scalar (device) */
+int eovae_pixel_loss_backward(const float* a, const float* b, long long count, float eps, int kind, const float* grad_scale,
+                              float* grad_a, void* stream);
 /* dbias[c] (+)= sum over pixels of grad_out [pixels][c] (16-bit) */
 size_t eovae_bias_grad_workspace_bytes(long long pixels, int c);
 int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, float* dbias, int accumulate, void* workspace,

@@ -46,6 +46,24 @@ def _grad_act(g: torch.Tensor, dtype) -> torch.Tensor:
     return out
 
 
+def _grad_act_pad8(g: torch.Tensor, dtype) -> torch.Tensor:
+    """Like _grad_act, but the channel count itself is padded to a multiple of 8 with ZERO lanes (the data-gradient
+    GEMM contracts over them): used where the forward output had a ragged channel count (a 12-band reconstruction)."""
+    n, c, h, w = g.shape
+    if c % 8 == 0:
+        return _grad_act(g, dtype)
+    c8 = (c + 7) // 8 * 8
+    a = _grad_act(g, dtype)
+    ps = ops.pix_stride(a)
+    if ps >= c8:
+        wide = torch.as_strided(a, (n, c8, h, w), a.stride(), a.storage_offset())
+        wide[:, c:].zero_()
+        return wide
+    out = torch.zeros((n, h, w, (c + 15) // 16 * 16), dtype=dtype, device=g.device).permute(0, 3, 1, 2)
+    out[:, :c].copy_(a)
+    return out[:, :c8]
+
+
 def _dense(g: torch.Tensor) -> torch.Tensor:
     if ops.pix_stride(g) == g.shape[1]:
         return g
@@ -286,8 +304,7 @@ class DynConvOutFn(Function):
     @staticmethod
     def backward(ctx, dy):
         x, oihw = ctx.saved_tensors
-        g = _grad_act(dy, x.dtype)
-        return ops.conv2d_dgrad(g, oihw, ops.CONV_3X3), None, None
+        return ops.conv2d_dgrad(_grad_act_pad8(dy, x.dtype), oihw, ops.CONV_3X3), None, None
 
 
 class SampleFn(Function):

@@ -381,6 +381,13 @@ def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, mode: int, in_hw=None, grad_
     return conv2d(dy, wp, None, cin, mode, residual=grad_add)
 
 
+def _pixel_rows(t: torch.Tensor) -> torch.Tensor:
+    """[N, C, H, W] NHWC-stored (pixel pitch may exceed C) -> [N, H*W, C] view with the pitch as row stride."""
+    n, c, h, w = t.shape
+    ps = pix_stride(t)
+    return torch.as_strided(t, (n, h * w, c), (h * w * ps, ps, 1), t.storage_offset())
+
+
 def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor | None = None) -> torch.Tensor:
     """Weight gradient [cout, cin, k, k] fp32 of a stride-1 conv (x: its NHWC 16-bit input, dy: output gradient)."""
     _need_cuda(x, dy)
@@ -393,12 +400,12 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor
         xp[:, :cin].copy_(x)
         return conv2d_wgrad(xp, dy, ksize)[:, :cin].contiguous()
     if ksize == 1:
-        xt = transpose16(x.permute(0, 2, 3, 1).reshape(n, h * w, pix_stride(x))[:, :, :cin])    # [n, cin, h*w]
+        xt = transpose16(_pixel_rows(x))    # [n, cin, h*w]
     else:
         xt = torch.empty((3, n, cin, h * w), dtype=x.dtype, device=x.device)                     # x-shifted copies
         _C.check(_C.lib().eovae_transpose16_xshift3(_ptr(x), pix_stride(x), _ptr(xt), n, h, w, cin, _stream()),
                  "eovae_transpose16_xshift3")
-    dyt = transpose16(dy.permute(0, 2, 3, 1).reshape(n, h * w, pix_stride(dy))[:, :, :cout])
+    dyt = transpose16(_pixel_rows(dy))
     lib = _C.lib()
     ws_bytes = lib.eovae_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, ksize)
     ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=x.device)

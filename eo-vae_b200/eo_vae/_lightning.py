@@ -19,6 +19,13 @@ except Exception:  # noqa: BLE001
             self._optimizers = None
             self._schedulers = None
             self.logged: dict = {}
+            self._grad_sync = None
+
+        def enable_ddp(self, bucket_bytes: int = 64 << 20) -> None:
+            """Stand-in for Trainer(strategy='ddp'): average the gradients over the default process group inside
+            ``manual_backward`` (bucketed NCCL all-reduce overlapped with backward, eo_vae/ddp.py)."""
+            from .ddp import GradSync
+            self._grad_sync = GradSync(self.parameters(), bucket_bytes)
 
         def attach_optimizers(self) -> None:
             """Stand-in for Trainer wiring: calls ``configure_optimizers`` once and stores the result."""
@@ -44,6 +51,8 @@ except Exception:  # noqa: BLE001
 
         def manual_backward(self, loss: torch.Tensor) -> None:
             loss.backward()
+            if self._grad_sync is not None:
+                self._grad_sync.finish()
 
         def log_dict(self, d: dict, **_: object) -> None:
             self.logged.update({k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in d.items()})

@@ -59,3 +59,52 @@ def test_shard_indices_partition():
     for world in (1, 2, 4, 8):
         seen = sorted(i for r in range(world) for i in shard_indices(37, r, world))
         assert seen == list(range(37))
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    """Two replicas, different data: after GradSync the gradients equal the mean of the per-rank gradients, parameters
+    start from rank 0's values, and a parameter that gets no gradient (unused branch) does not stall the exchange."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "eo-vae_b200"))
+    from eo_vae.ddp import GradSync
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                      # replicas start DIFFERENT; the constructor broadcast fixes that
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4))
+    unused = torch.nn.Parameter(torch.ones(3))
+    sync = GradSync(list(net.parameters()) + [unused], bucket_bytes=256)   # several small buckets
+    x = torch.randn(5, 8, generator=torch.Generator().manual_seed(rank))
+    for _ in range(2):                                 # two steps: the bucket bookkeeping resets in finish()
+        for p in net.parameters():
+            p.grad = None
+        net(x).pow(2).sum().backward()
+        sync.finish()
+    torch.save({"grads": [p.grad.clone() for p in net.parameters()], "params": [p.detach().clone() for p in net.parameters()],
+                "x": x}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_sync(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(2))
+    for a, b in zip(r0["params"], r1["params"]):
+        assert torch.equal(a, b)                       # broadcast from rank 0
+    for a, b in zip(r0["grads"], r1["grads"]):
+        assert torch.equal(a, b)                       # both ranks hold the same averaged gradient
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4))
+    with torch.no_grad():
+        for p, v in zip(net.parameters(), r0["params"]):
+            p.copy_(v)
+    want = None
+    for r in (r0, r1):
+        for p in net.parameters():
+            p.grad = None
+        net(r["x"]).pow(2).sum().backward()
+        gs = [p.grad.clone() for p in net.parameters()]
+        want = gs if want is None else [w + g for w, g in zip(want, gs)]
+    for got, w in zip(r0["grads"], want):
+        assert torch.allclose(got, w / 2, atol=1e-6)

@@ -258,8 +258,7 @@ __global__ void __launch_bounds__(kThreads) colsum_partial_kernel(const T* __res
     const long long p0 = blockIdx.x * pix_per_block;
     long long p1 = p0 + pix_per_block;
     if (p1 > pixels) p1 = pixels;
-    for (long long p = p0 + r; p < p1; p += rows) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + p * c + v * 8));
+    auto add = [&](const uint4& u) {
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -267,7 +266,16 @@ __global__ void __launch_bounds__(kThreads) colsum_partial_kernel(const T* __res
         s[2 * j] += f.x;
         s[2 * j + 1] += f.y;
       }
+    };
+    long long p = p0 + r;
+    for (; p + 3LL * rows < p1; p += 4LL * rows) {  // four independent 16-byte loads in flight per thread
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(g + p * c + v * 8));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(g + (p + rows) * c + v * 8));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(g + (p + 2LL * rows) * c + v * 8));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(g + (p + 3LL * rows) * c + v * 8));
+      add(u0); add(u1); add(u2); add(u3);
     }
+    for (; p < p1; p += rows) add(__ldg(reinterpret_cast<const uint4*>(g + p * c + v * 8)));
 #pragma unroll
     for (int j = 0; j < 8; ++j) sm[r * c + v * 8 + j] = s[j];
   }
@@ -278,13 +286,22 @@ __global__ void __launch_bounds__(kThreads) colsum_partial_kernel(const T* __res
     partial[static_cast<long long>(blockIdx.x) * c + ch] = a;
   }
 }
+// block (32 channels, 8 slices): slice y sums the partial rows b = y, y + 8, ...; fixed-order combine (deterministic)
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ out,
                                        int accumulate) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+  __shared__ double red[8][32];
+  const int ch = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0;
-  for (int b = 0; b < blocks; ++b) a += partial[static_cast<long long>(b) * c + ch];
-  out[ch] = (accumulate ? out[ch] : 0.f) + static_cast<float>(a);
+  if (ch < c)
+    for (int b = threadIdx.y; b < blocks; b += 8) a += partial[static_cast<long long>(b) * c + ch];
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < c) {
+    double t = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    out[ch] = (accumulate ? out[ch] : 0.f) + static_cast<float>(t);
+  }
 }
 
 int block_threads(int c) {
@@ -427,7 +444,7 @@ int eovae_pool2x2_sum(const void* g, void* out, int dtype, int n, int h, int w, 
 }
 
 size_t eovae_bias_grad_workspace_bytes(long long pixels, int c) {
-  return sizeof(float) * static_cast<size_t>((pixels + 4095) / 4096 + 1) * c;
+  return sizeof(float) * static_cast<size_t>((pixels + 511) / 512 + 1) * c;
 }
 
 int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, float* dbias, int accumulate, void* workspace,
@@ -438,7 +455,7 @@ int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, fl
   const int threads = block_threads(c);
   EOVAE_CHECK(threads > 0, "bias_grad: C too large");
   const int rows = threads / (c / 8);
-  const long long ppb = 4096;
+  const long long ppb = 512;
   const int blocks = static_cast<int>((pixels + ppb - 1) / ppb);
   float* partial = static_cast<float*>(workspace);
   const size_t smem = sizeof(float) * rows * c;
@@ -447,7 +464,7 @@ int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, fl
   else
     colsum_partial_kernel<__half><<<blocks, threads, smem, stream>>>(static_cast<const __half*>(grad_out), pixels, c, partial, ppb);
   EOVAE_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<ceil_div(c, 128), 128, 0, stream>>>(partial, blocks, c, dbias, accumulate);
+  colsum_finalize_kernel<<<ceil_div(c, 32), dim3(32, 8), 0, stream>>>(partial, blocks, c, dbias, accumulate);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -175,6 +175,250 @@ int linear(const float* x, int ldx, const float* w, const float* b, const float*
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------- backward pieces
+// C[m][n] (+)= sum_k A[i*a_rs + k*a_cs] * B[k*b_rs + j*b_cs]: generic-stride fp32 GEMM for the (tiny, <= 142-row)
+// hypernetwork gradients; 64 x 64 tiles, 4 x 4 outputs per thread.
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ a, long long a_rs, long long a_cs,
+                                                            const float* __restrict__ b, long long b_rs, long long b_cs,
+                                                            float* __restrict__ c, long long ldc, int m, int n, int k,
+                                                            int accumulate) {
+  __shared__ float as[LBK][LBM + 4];
+  __shared__ float bs[LBK][LBN + 4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int row0 = blockIdx.y * LBM, col0 = blockIdx.x * LBN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < k; k0 += LBK) {
+    for (int e = threadIdx.x; e < LBM * LBK; e += 256) {
+      const int kk = e % LBK, rr = e / LBK;
+      as[kk][rr] = (row0 + rr < m && k0 + kk < k) ? a[(row0 + rr) * a_rs + (k0 + kk) * a_cs] : 0.f;
+      const int cc = e % LBN, k2 = e / LBN;
+      bs[k2][cc] = (col0 + cc < n && k0 + k2 < k) ? b[(k0 + k2) * b_rs + (col0 + cc) * b_cs] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < LBK; ++kk) {
+      const float4 av4 = *reinterpret_cast<const float4*>(&as[kk][ty * 4]);
+      const float4 bv4 = *reinterpret_cast<const float4*>(&bs[kk][tx * 4]);
+      const float av[4] = {av4.x, av4.y, av4.z, av4.w}, bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = row0 + ty * 4 + i;
+    if (rr >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = col0 + tx * 4 + j;
+      if (cc < n) {
+        float* o = c + rr * ldc + cc;
+        *o = (accumulate ? *o : 0.f) + acc[i][j];
+      }
+    }
+  }
+}
+
+int sgemm(const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c,
+          long long ldc, int m, int n, int k, int accumulate, cudaStream_t st) {
+  dim3 grid(ceil_div(n, LBN), ceil_div(m, LBM));
+  sgemm_strided_kernel<<<grid, 256, 0, st>>>(a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, m, n, k, accumulate);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[j] (+)= sum_r x[r][j]
+__global__ void colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out,
+                                  int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float a = 0.f;
+  for (int r = 0; r < rows; ++r) a += x[r * ld + j];
+  out[j] = (accumulate ? out[j] : 0.f) + a;
+}
+
+// y[i] = act(z[i]) (forward with a saved pre-activation) / dz[i] = dy[i] * act'(z[i])
+__global__ void gelu_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = 0.5f * z[i] * (1.f + erff(z[i] * 0.70710678118654752f));
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dy, float* __restrict__ dz, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = z[i];
+  const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * expf(-0.5f * v * v);
+  dz[i] = dy[i] * (cdf + v * pdf);
+}
+// dz = dy where pos > 0 (ReLU mask taken from the activation's OUTPUT, optionally output - base), else 0
+__global__ void relu_bwd_kernel(const float* __restrict__ out, const float* __restrict__ base, const float* __restrict__ dy,
+                                float* __restrict__ dz, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = out[i] - (base != nullptr ? base[i] : 0.f);
+  dz[i] = v > 0.f ? dy[i] : 0.f;
+}
+// y[i] (+)= alpha * x[i]
+__global__ void axpy_kernel(const float* __restrict__ x, float alpha, float* __restrict__ y, long long n, int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = (accumulate ? y[i] : 0.f) + alpha * x[i];
+}
+
+// LayerNorm backward, one warp per row: dx; row statistics go to rowstat[row] = (mean, rstd) for the parameter pass
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ dy,
+                                     float* __restrict__ dx, float* __restrict__ rowstat, int rows, int d, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + static_cast<long long>(row) * d;
+  const float* dr = dy + static_cast<long long>(row) * d;
+  float s = 0.f;
+  for (int i = lane; i < d; i += 32) s += xr[i];
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float t = xr[i] - mean;
+    q += t * t;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  float a = 0.f, b = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float dg = dr[i] * g[i];
+    a += dg;
+    b += dg * (xr[i] - mean) * rstd;
+  }
+  a = warp_sum(a) / d;
+  b = warp_sum(b) / d;
+  for (int i = lane; i < d; i += 32) {
+    const float xh = (xr[i] - mean) * rstd;
+    dx[static_cast<long long>(row) * d + i] = rstd * (dr[i] * g[i] - a - xh * b);
+  }
+  if (lane == 0) {
+    rowstat[2 * row] = mean;
+    rowstat[2 * row + 1] = rstd;
+  }
+}
+__global__ void layernorm_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                           const float* __restrict__ rowstat, float* __restrict__ dg, float* __restrict__ db,
+                                           int rows, int d) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  float a = 0.f, b = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float g = dy[static_cast<long long>(r) * d + j];
+    a += g * (x[static_cast<long long>(r) * d + j] - rowstat[2 * r]) * rowstat[2 * r + 1];
+    b += g;
+  }
+  dg[j] = a;
+  db[j] = b;
+}
+
+// attention backward, pass 1: one warp per (head, query): recompute the probability row, dP = dO V^T,
+// dS = P o (dP - sum(P o dP)) * scale; writes P and dS rows ([heads][s][s]) and dQ.
+__global__ void __launch_bounds__(128) mha_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
+                                                        float* __restrict__ pbuf, float* __restrict__ dsbuf,
+                                                        float* __restrict__ dqkv, int s, int d, int heads) {
+  __shared__ float probs[4][MHA_MAX_S];
+  __shared__ float dsr[4][MHA_MAX_S];
+  __shared__ float qs[4][128];
+  __shared__ float dos[4][128];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + wid;
+  const int hd = d / heads;
+  if (item >= s * heads) return;
+  const int h = item / s, qi = item % s;
+  const float scale = rsqrtf(static_cast<float>(hd));
+  const float* qp = qkv + static_cast<long long>(qi) * 3 * d + h * hd;
+  const float* dop = dout + static_cast<long long>(qi) * d + h * hd;
+  for (int i = lane; i < hd; i += 32) {
+    qs[wid][i] = qp[i] * scale;
+    dos[wid][i] = dop[i];
+  }
+  __syncwarp();
+  float m = -INFINITY;
+  for (int j = lane; j < s; j += 32) {
+    const float* kp = qkv + static_cast<long long>(j) * 3 * d + d + h * hd;
+    const float* vp = kp + d;
+    float acc = 0.f, dp = 0.f;
+    for (int i = 0; i < hd; ++i) {
+      acc = fmaf(qs[wid][i], kp[i], acc);
+      dp = fmaf(dos[wid][i], vp[i], dp);
+    }
+    probs[wid][j] = acc;
+    dsr[wid][j] = dp;
+    m = fmaxf(m, acc);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < s; j += 32) {
+    const float e = expf(probs[wid][j] - m);
+    probs[wid][j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  float dot = 0.f;
+  for (int j = lane; j < s; j += 32) {
+    const float p = probs[wid][j] * inv;
+    probs[wid][j] = p;
+    dot += p * dsr[wid][j];
+  }
+  dot = warp_sum(dot);
+  float* prow = pbuf + (static_cast<long long>(h) * s + qi) * s;
+  float* dsrow = dsbuf + (static_cast<long long>(h) * s + qi) * s;
+  for (int j = lane; j < s; j += 32) {
+    const float p = probs[wid][j];
+    const float ds = p * (dsr[wid][j] - dot) * scale;
+    dsr[wid][j] = ds;
+    prow[j] = p;
+    dsrow[j] = ds;
+  }
+  __syncwarp();
+  for (int i = lane; i < hd; i += 32) {  // dQ_i = sum_j dS_ij K_j
+    float acc = 0.f;
+    for (int j = 0; j < s; ++j) acc = fmaf(dsr[wid][j], qkv[static_cast<long long>(j) * 3 * d + d + h * hd + i], acc);
+    dqkv[static_cast<long long>(qi) * 3 * d + h * hd + i] = acc;
+  }
+}
+// pass 2: one warp per (head, key): dK_j = sum_i dS_ij Q_i, dV_j = sum_i P_ij dO_i
+__global__ void __launch_bounds__(128) mha_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
+                                                         const float* __restrict__ pbuf, const float* __restrict__ dsbuf,
+                                                         float* __restrict__ dqkv, int s, int d, int heads) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + wid;
+  const int hd = d / heads;
+  if (item >= s * heads) return;
+  const int h = item / s, kj = item % s;
+  for (int i = lane; i < hd; i += 32) {
+    float dk = 0.f, dv = 0.f;
+    for (int q = 0; q < s; ++q) {
+      const long long pi = (static_cast<long long>(h) * s + q) * s + kj;
+      dk = fmaf(dsbuf[pi], qkv[static_cast<long long>(q) * 3 * d + h * hd + i], dk);
+      dv = fmaf(pbuf[pi], dout[static_cast<long long>(q) * d + h * hd + i], dv);
+    }
+    dqkv[static_cast<long long>(kj) * 3 * d + d + h * hd + i] = dk;
+    dqkv[static_cast<long long>(kj) * 3 * d + 2 * d + h * hd + i] = dv;
+  }
+}
+
+// d_wk[band][tap*E + e] = scale * dW[o][ci][tap], (o, ci) = decoder ? (band, e) : (e, band); dW rows have cin_ld inputs
+__global__ void dyn_weight_grad_kernel(const float* __restrict__ dw, int cin_ld, int c, int embed, int decoder, float scale,
+                                       float* __restrict__ dwk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c * 9 * embed) return;
+  const int e = i % embed;
+  const int tap = (i / embed) % 9;
+  const int band = i / (9 * embed);
+  const int o = decoder ? band : e, ci = decoder ? e : band;
+  dwk[i] = scale * dw[(static_cast<long long>(o) * cin_ld + ci) * 9 + tap];
+}
+
+inline unsigned blocks_for(long long n) { return static_cast<unsigned>((n + 255) / 256); }
+
 }  // namespace
 
 extern "C" {
@@ -246,6 +490,190 @@ int eovae_hypernet_forward(const float* wvs_um, int c, const float* const* param
   } else {
     if (linear(x + (128 + c) * d, d, params[9], params[10], nullptr, 0, bias_out, embed, 1, embed, d, ACT_NONE, part, st)) return -1;
   }
+  return 0;
+}
+
+// ---- backward of eovae_hypernet_forward (+ eovae_pack_dyn_weight): the forward is re-run keeping every activation in
+// the workspace, then walked backwards.  grads[i] receives the gradient of params[i] (written, not accumulated; index 0,
+// the sincos table, is not a parameter and may be NULL).
+size_t eovae_hypernet_backward_workspace_bytes(int c, int d, int ff, int embed, int num_layers) {
+  const size_t s = 128 + c + 1;
+  const size_t per_layer = s * d * 5 + s * 3 * d + 2 * s * ff;
+  const size_t heads_max = 8;
+  const size_t floats = 5 * static_cast<size_t>(c) * d + s * d + num_layers * per_layer  // tape
+                        + 4 * s * d + s * 3 * d + 2 * s * ff                               // gradient scratch
+                        + 2 * heads_max * s * s + 2 * s + static_cast<size_t>(c) * 9 * embed + 64 + kLinearPartFloats;
+  return floats * sizeof(float);
+}
+
+int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads,
+                            int ff, int embed, int decoder, const float* dw_oihw, int dw_cin_ld, float w_scale,
+                            const float* dbias, float bias_scale, float* const* grads, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c >= 1 && c <= 62, "hypernet: band count %d out of range [1, 62]", c);
+  EOVAE_CHECK(d % heads == 0 && d / heads <= 128 && d % 2 == 0 && heads <= 8, "hypernet: bad d_model/heads (%d/%d)", d, heads);
+  EOVAE_CHECK(workspace_bytes >= eovae_hypernet_backward_workspace_bytes(c, d, ff, embed, num_layers),
+              "hypernet backward: workspace too small");
+  const int s = 128 + c + 1;
+  EOVAE_CHECK(s <= MHA_MAX_S, "hypernet: sequence too long");
+  const long long sd = static_cast<long long>(s) * d, sf = static_cast<long long>(s) * ff, cd = static_cast<long long>(c) * d;
+  float* ws = static_cast<float*>(workspace);
+  auto take = [&](long long n) { float* p = ws; ws += n; return p; };
+  float* emb = take(cd); float* t1 = take(cd); float* waves = take(cd); float* headin = take(cd); float* headin2 = take(cd);
+  float* x0 = take(sd);
+  struct Layer { float *qkv, *att, *tmp1, *x1, *z, *ffh, *tmp2, *xout; };
+  Layer L[16];
+  EOVAE_CHECK(num_layers <= 16, "hypernet backward: too many layers");
+  for (int l = 0; l < num_layers; ++l) {
+    L[l].qkv = take(3 * sd); L[l].att = take(sd); L[l].tmp1 = take(sd); L[l].x1 = take(sd); L[l].z = take(sf);
+    L[l].ffh = take(sf); L[l].tmp2 = take(sd); L[l].xout = take(sd);
+  }
+  float* dx = take(sd); float* da = take(sd); float* db_ = take(sd); float* dc = take(sd);
+  float* dqkv = take(3 * sd); float* dffh = take(sf); float* dz = take(sf);
+  float* pbuf = take(8LL * s * s); float* dsbuf = take(8LL * s * s);
+  float* rowstat = take(2 * s);
+  float* dwk = take(static_cast<long long>(c) * 9 * embed);
+  float* part = take(64);
+  part = ws;
+  const float* omega = params[0];
+  const float* wtok = params[1];
+  const float* btok = params[2];
+
+  // ---------------- forward with tape
+  sincos_kernel<<<ceil_div(c * d / 2, 128), 128, 0, st>>>(wvs_um, omega, emb, c, d);
+  EOVAE_LAUNCH_CHECK();
+  if (linear(emb, d, params[3], params[4], nullptr, 0, t1, d, c, d, d, ACT_RELU, part, st)) return -1;
+  if (linear(t1, d, params[5], params[6], emb, d, waves, d, c, d, d, ACT_RELU, part, st)) return -1;
+  EOVAE_CUDA(cudaMemcpyAsync(x0, wtok, sizeof(float) * 128 * d, cudaMemcpyDeviceToDevice, st));
+  EOVAE_CUDA(cudaMemcpyAsync(x0 + 128 * d, waves, sizeof(float) * cd, cudaMemcpyDeviceToDevice, st));
+  EOVAE_CUDA(cudaMemcpyAsync(x0 + (128 + c) * d, btok, sizeof(float) * d, cudaMemcpyDeviceToDevice, st));
+  const float* xin = x0;
+  for (int l = 0; l < num_layers; ++l) {
+    const float* const* lp = params + 11 + 12 * l;
+    if (linear(xin, d, lp[0], lp[1], nullptr, 0, L[l].qkv, 3 * d, s, 3 * d, d, ACT_NONE, part, st)) return -1;
+    mha_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(L[l].qkv, L[l].att, s, d, heads);
+    EOVAE_LAUNCH_CHECK();
+    if (linear(L[l].att, d, lp[2], lp[3], xin, d, L[l].tmp1, d, s, d, d, ACT_NONE, part, st)) return -1;
+    layernorm_kernel<<<ceil_div(s, 4), 128, 0, st>>>(L[l].tmp1, lp[8], lp[9], L[l].x1, s, d, 1e-5f);
+    EOVAE_LAUNCH_CHECK();
+    if (linear(L[l].x1, d, lp[4], lp[5], nullptr, 0, L[l].z, ff, s, ff, d, ACT_NONE, part, st)) return -1;
+    gelu_fwd_kernel<<<blocks_for(sf), 256, 0, st>>>(L[l].z, L[l].ffh, sf);
+    EOVAE_LAUNCH_CHECK();
+    if (linear(L[l].ffh, ff, lp[6], lp[7], L[l].x1, d, L[l].tmp2, d, s, d, ff, ACT_NONE, part, st)) return -1;
+    layernorm_kernel<<<ceil_div(s, 4), 128, 0, st>>>(L[l].tmp2, lp[10], lp[11], L[l].xout, s, d, 1e-5f);
+    EOVAE_LAUNCH_CHECK();
+    xin = L[l].xout;
+  }
+  const float* xl = xin;
+  add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(xl + 128 * d, waves, headin, c, d, 0);
+  EOVAE_LAUNCH_CHECK();
+  if (decoder) {
+    add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(xl + 128 * d, btok, headin2, c, d, 1);
+    EOVAE_LAUNCH_CHECK();
+  }
+
+  // ---------------- heads
+  const int ne = 9 * embed;
+  dyn_weight_grad_kernel<<<blocks_for(static_cast<long long>(c) * ne), 256, 0, st>>>(dw_oihw, dw_cin_ld, c, embed, decoder, w_scale, dwk);
+  EOVAE_LAUNCH_CHECK();
+  EOVAE_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * sd, st));
+  float* dwaves = da;  // [c][d]
+  // wk = headin Wfw^T + bfw
+  if (sgemm(dwk, 1, ne, headin, d, 1, grads[7], d, ne, d, c, 0, st)) return -1;            // dWfw [9E][d] = dwk^T headin
+  colsum_f32_kernel<<<ceil_div(ne, 128), 128, 0, st>>>(dwk, ne, c, ne, grads[8], 0);
+  EOVAE_LAUNCH_CHECK();
+  if (sgemm(dwk, ne, 1, params[7], d, 1, dwaves, d, c, d, ne, 0, st)) return -1;            // dheadin [c][d] = dwk Wfw
+  axpy_kernel<<<blocks_for(cd), 256, 0, st>>>(dwaves, 1.f, dx + 128 * d, cd, 1);
+  EOVAE_LAUNCH_CHECK();
+  EOVAE_CUDA(cudaMemsetAsync(grads[2], 0, sizeof(float) * d, st));
+  if (decoder) {
+    // bias[c] = bias_scale * (headin2 wfb^T + bfb), wfb [1][d]
+    axpy_kernel<<<blocks_for(c), 256, 0, st>>>(dbias, bias_scale, rowstat, c, 0);           // d(bias_raw) [c]
+    EOVAE_LAUNCH_CHECK();
+    if (sgemm(rowstat, 0, 1, headin2, d, 1, grads[9], d, 1, d, c, 0, st)) return -1;        // dwfb [1][d]
+    colsum_f32_kernel<<<1, 32, 0, st>>>(rowstat, 1, c, 1, grads[10], 0);
+    EOVAE_LAUNCH_CHECK();
+    if (sgemm(rowstat, 1, 0, params[9], 0, 1, db_, d, c, d, 1, 0, st)) return -1;           // dheadin2 [c][d] = db (x) wfb
+    axpy_kernel<<<blocks_for(cd), 256, 0, st>>>(db_, 1.f, dx + 128 * d, cd, 1);
+    EOVAE_LAUNCH_CHECK();
+    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(db_, d, c, d, grads[2], 1);         // bias_token (broadcast add)
+    EOVAE_LAUNCH_CHECK();
+  } else {
+    // bias[E] = bias_scale * (x_last Wfb^T + bfb), Wfb [E][d]
+    axpy_kernel<<<blocks_for(embed), 256, 0, st>>>(dbias, bias_scale, grads[10], embed, 0);
+    EOVAE_LAUNCH_CHECK();
+    if (sgemm(grads[10], 1, 0, xl + (128 + c) * d, 0, 1, grads[9], d, embed, d, 1, 0, st)) return -1;   // dWfb = db (x) x_last
+    if (sgemm(grads[10], 0, 1, params[9], d, 1, dx + (128 + c) * d, d, 1, d, embed, 1, st)) return -1;  // dx_last += db Wfb
+  }
+
+  // ---------------- transformer layers, last to first (dx = gradient of the layer output)
+  for (int l = num_layers - 1; l >= 0; --l) {
+    const float* const* lp = params + 11 + 12 * l;
+    float* const* lg = grads + 11 + 12 * l;
+    const float* lin = l == 0 ? x0 : L[l - 1].xout;
+    float* dtmp2 = db_;
+    layernorm_bwd_kernel<<<ceil_div(s, 4), 128, 0, st>>>(L[l].tmp2, lp[10], dx, dtmp2, rowstat, s, d, 1e-5f);
+    EOVAE_LAUNCH_CHECK();
+    layernorm_bwd_param_kernel<<<ceil_div(d, 128), 128, 0, st>>>(L[l].tmp2, dx, rowstat, lg[10], lg[11], s, d);
+    EOVAE_LAUNCH_CHECK();
+    // tmp2 = ffh W2^T + b2 + x1
+    if (sgemm(dtmp2, d, 1, lp[6], ff, 1, dffh, ff, s, ff, d, 0, st)) return -1;             // dffh = dtmp2 W2
+    if (sgemm(dtmp2, 1, d, L[l].ffh, ff, 1, lg[6], ff, d, ff, s, 0, st)) return -1;          // dW2 [d][ff]
+    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dtmp2, d, s, d, lg[7], 0);
+    EOVAE_LAUNCH_CHECK();
+    gelu_bwd_kernel<<<blocks_for(sf), 256, 0, st>>>(L[l].z, dffh, dz, sf);
+    EOVAE_LAUNCH_CHECK();
+    // z = x1 W1^T + b1 ; dx1 = dtmp2 + dz W1
+    float* dx1 = dc;
+    EOVAE_CUDA(cudaMemcpyAsync(dx1, dtmp2, sizeof(float) * sd, cudaMemcpyDeviceToDevice, st));
+    if (sgemm(dz, ff, 1, lp[4], d, 1, dx1, d, s, d, ff, 1, st)) return -1;
+    if (sgemm(dz, 1, ff, L[l].x1, d, 1, lg[4], d, ff, d, s, 0, st)) return -1;               // dW1 [ff][d]
+    colsum_f32_kernel<<<ceil_div(ff, 128), 128, 0, st>>>(dz, ff, s, ff, lg[5], 0);
+    EOVAE_LAUNCH_CHECK();
+    float* dtmp1 = db_;
+    layernorm_bwd_kernel<<<ceil_div(s, 4), 128, 0, st>>>(L[l].tmp1, lp[8], dx1, dtmp1, rowstat, s, d, 1e-5f);
+    EOVAE_LAUNCH_CHECK();
+    layernorm_bwd_param_kernel<<<ceil_div(d, 128), 128, 0, st>>>(L[l].tmp1, dx1, rowstat, lg[8], lg[9], s, d);
+    EOVAE_LAUNCH_CHECK();
+    // tmp1 = att Wo^T + bo + xin
+    float* datt = dc;
+    if (sgemm(dtmp1, d, 1, lp[2], d, 1, datt, d, s, d, d, 0, st)) return -1;
+    if (sgemm(dtmp1, 1, d, L[l].att, d, 1, lg[2], d, d, d, s, 0, st)) return -1;             // dWo [d][d]
+    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dtmp1, d, s, d, lg[3], 0);
+    EOVAE_LAUNCH_CHECK();
+    mha_bwd_q_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(L[l].qkv, datt, pbuf, dsbuf, dqkv, s, d, heads);
+    EOVAE_LAUNCH_CHECK();
+    mha_bwd_kv_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(L[l].qkv, datt, pbuf, dsbuf, dqkv, s, d, heads);
+    EOVAE_LAUNCH_CHECK();
+    // qkv = xin Win^T + bin ; dxin = dtmp1 + dqkv Win
+    EOVAE_CUDA(cudaMemcpyAsync(dx, dtmp1, sizeof(float) * sd, cudaMemcpyDeviceToDevice, st));
+    if (sgemm(dqkv, 3 * d, 1, lp[0], d, 1, dx, d, s, d, 3 * d, 1, st)) return -1;
+    if (sgemm(dqkv, 1, 3 * d, lin, d, 1, lg[0], d, 3 * d, d, s, 0, st)) return -1;           // dWin [3d][d]
+    colsum_f32_kernel<<<ceil_div(3 * d, 128), 128, 0, st>>>(dqkv, 3 * d, s, 3 * d, lg[1], 0);
+    EOVAE_LAUNCH_CHECK();
+  }
+
+  // ---------------- tokens and FCResLayer
+  EOVAE_CUDA(cudaMemcpyAsync(grads[1], dx, sizeof(float) * 128 * d, cudaMemcpyDeviceToDevice, st));
+  axpy_kernel<<<blocks_for(d), 256, 0, st>>>(dx + (128 + c) * d, 1.f, grads[2], d, 1);
+  EOVAE_LAUNCH_CHECK();
+  axpy_kernel<<<blocks_for(cd), 256, 0, st>>>(dx + 128 * d, 1.f, dwaves, cd, 1);
+  EOVAE_LAUNCH_CHECK();
+  // waves = emb + relu(u2), u2 = t1 W2^T + b2, t1 = relu(emb W1^T + b1)
+  float* du2 = db_;
+  relu_bwd_kernel<<<blocks_for(cd), 256, 0, st>>>(waves, emb, dwaves, du2, cd);
+  EOVAE_LAUNCH_CHECK();
+  if (sgemm(du2, 1, d, t1, d, 1, grads[5], d, d, d, c, 0, st)) return -1;
+  colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(du2, d, c, d, grads[6], 0);
+  EOVAE_LAUNCH_CHECK();
+  float* dt1 = dc;
+  if (sgemm(du2, d, 1, params[5], d, 1, dt1, d, c, d, d, 0, st)) return -1;
+  relu_bwd_kernel<<<blocks_for(cd), 256, 0, st>>>(t1, nullptr, dt1, dt1, cd);
+  EOVAE_LAUNCH_CHECK();
+  if (sgemm(dt1, 1, d, emb, d, 1, grads[3], d, d, d, c, 0, st)) return -1;
+  colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dt1, d, c, d, grads[4], 0);
+  EOVAE_LAUNCH_CHECK();
   return 0;
 }
 

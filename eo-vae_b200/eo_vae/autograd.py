@@ -286,25 +286,55 @@ def act_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     return ops.act_to_nchw_f32(x)
 
 
-class DynConvOutFn(Function):
-    """Decoder output layer (dynamic_conv.py:684-710): band kernels generated from the wavelengths, then a 3x3 conv.
-    Backward: data gradient through the generated kernel (the hypernetwork's own gradient is not built yet - its
-    parameters receive no gradient)."""
+class DynConvInFn(Function):
+    """Encoder input layer (dynamic_conv.py:511-527): kernel [E, C, 3, 3] and bias [E] generated from the wavelengths.
+    Backward: weight / bias gradient of the conv, then the hypernetwork's own backward (eovae_hypernet_backward)."""
 
     @staticmethod
-    def forward(ctx, x, mod, waves):
+    def forward(ctx, x, mod, wvs, *hparams):
+        c = wvs.size(0)
+        wk, b_raw = mod._generate(wvs)
+        packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, mod.embed_dim, False, mod.scaler, mod.scaler, x.dtype, False)
+        ctx.save_for_backward(x, wvs)
+        ctx.mod = mod
+        return ops.conv2d(x, packed, bias, mod.embed_dim, ops.CONV_3X3, algo_cin=c)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wvs = ctx.saved_tensors
+        mod = ctx.mod
+        g = _dense(_grad_act(dy, x.dtype))
+        dw = ops.conv2d_wgrad(x, g, 3)  # [E, C padded to 16, 3, 3]
+        grads = mod._hyper_backward(wvs, dw, ops.bias_grad(g), mod.scaler)
+        return (None, None, None) + tuple(grads)
+
+
+class DynConvOutFn(Function):
+    """Decoder output layer (dynamic_conv.py:684-710): band kernels [C, E, 3, 3] and per-band bias generated from the
+    wavelengths, then a 3x3 conv.  Backward: data gradient through the generated kernel, its weight / bias gradient,
+    and the hypernetwork's backward."""
+
+    @staticmethod
+    def forward(ctx, x, mod, waves, *hparams):
         c = waves.size(0)
         wk, b_raw = mod._generate(waves)
         packed, bias, oihw = ops.pack_dyn_weight(wk, b_raw, c, mod.embed_dim, True, mod.scaler, mod.scaler * mod.scaler,
                                                  x.dtype, True)
         mod._last = (wk, b_raw, c)
-        ctx.save_for_backward(x, oihw)
+        ctx.save_for_backward(x, oihw, waves)
+        ctx.mod = mod
         return ops.conv2d(x, packed, bias, c, ops.CONV_3X3, out_dtype=torch.float32)
 
     @staticmethod
     def backward(ctx, dy):
-        x, oihw = ctx.saved_tensors
-        return ops.conv2d_dgrad(_grad_act_pad8(dy, x.dtype), oihw, ops.CONV_3X3), None, None
+        x, oihw, waves = ctx.saved_tensors
+        mod = ctx.mod
+        c = waves.size(0)
+        g = _grad_act_pad8(dy, x.dtype)
+        dx = ops.conv2d_dgrad(g, oihw, ops.CONV_3X3) if ctx.needs_input_grad[0] else None
+        dw = ops.conv2d_wgrad(x, g[:, :c], 3)  # [C, E, 3, 3]
+        grads = mod._hyper_backward(waves, dw, ops.bias_grad(g[:, :c]), mod.scaler * mod.scaler)
+        return (dx, None, None) + tuple(grads)
 
 
 class SampleFn(Function):

@@ -70,14 +70,19 @@ class TransformerWeightGenerator(nn.Module):
         torch.nn.init.normal_(self.bias_token, std=0.02)
         self.input_dim, self.embed_dim, self.num_heads, self.num_layers = input_dim, embed_dim, num_heads, num_layers
 
-    def kernel_params(self, fclayer: FCResLayer, omega: Tensor) -> list:
-        """Device pointers in the order eovae_hypernet_forward expects (include/eovae.h)."""
-        ps = [omega, self.weight_tokens, self.bias_token, fclayer.w1.weight, fclayer.w1.bias, fclayer.w2.weight,
+    def parameter_list(self, fclayer: FCResLayer) -> list:
+        """The trainable tensors in kernel order (entry 0 of the kernel list, the sincos table, is not a parameter)."""
+        ps = [self.weight_tokens, self.bias_token, fclayer.w1.weight, fclayer.w1.bias, fclayer.w2.weight,
               fclayer.w2.bias, self.fc_weight.weight, self.fc_weight.bias, self.fc_bias.weight, self.fc_bias.bias]
         for l in self.transformer_encoder.layers:
             ps += [l.self_attn.in_proj_weight, l.self_attn.in_proj_bias, l.self_attn.out_proj.weight,
                    l.self_attn.out_proj.bias, l.linear1.weight, l.linear1.bias, l.linear2.weight, l.linear2.bias,
                    l.norm1.weight, l.norm1.bias, l.norm2.weight, l.norm2.bias]
+        return ps
+
+    def kernel_params(self, fclayer: FCResLayer, omega: Tensor) -> list:
+        """Device pointers in the order eovae_hypernet_forward expects (include/eovae.h)."""
+        ps = [omega] + self.parameter_list(fclayer)
         for p in ps:
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("hypernetwork parameters must be contiguous fp32 tensors")
@@ -156,6 +161,14 @@ class _DynamicBase(nn.Module):
         return ops.hypernet_forward(wvs, params, g.num_layers, g.input_dim, g.num_heads, g.ff_dim, self.embed_dim,
                                     self._decoder)
 
+    def _hyper_backward(self, wvs: Tensor, dw_oihw: Tensor, dbias: Tensor, bias_scale: float) -> list:
+        """Gradients of ``weight_generator.parameter_list(fclayer)`` given the generated kernel's / bias' gradient."""
+        g = self.weight_generator
+        dev = g.weight_tokens.device
+        params = g.kernel_params(self.fclayer, self._omega_dev(dev))
+        return ops.hypernet_backward(wvs.to(device=dev, dtype=torch.float32), params, g.num_layers, g.input_dim, g.num_heads,
+                                     g.ff_dim, self.embed_dim, self._decoder, dw_oihw, self.scaler, dbias, bias_scale)
+
     def _get_weights(self, waves: Tensor):
         raise NotImplementedError('the CUDA path generates weights from wavelengths directly; use _generate(wvs)')
 
@@ -176,8 +189,10 @@ class DynamicConv(_DynamicBase):
         if img_feat.shape[1] != c:
             raise RuntimeError(f'DynamicConv: {img_feat.shape[1]} image bands but {c} wavelengths')
         dt = compute_dtype()
-        with torch.no_grad():  # TODO(training): hypernetwork gradient - generated kernel is a constant
-            wk, b_raw = self._generate(wvs)
+        if tape.grad_mode():
+            x = ops.nchw_to_act(img_feat, ops.dyn_cin_pad(c), dt)
+            return tape.DynConvInFn.apply(x, self, wvs, *self.weight_generator.parameter_list(self.fclayer))
+        wk, b_raw = self._generate(wvs)
         packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, self.embed_dim, False, self.scaler, self.scaler, dt, False)
         x = ops.nchw_to_act(img_feat, ops.dyn_cin_pad(c), dt)
         return ops.conv2d(x, packed, bias, self.embed_dim, ops.CONV_3X3, algo_cin=c, gn_groups=32, gn_eps=1e-6)
@@ -217,7 +232,7 @@ class DynamicConv_decoder(_DynamicBase):
         self.scaler = 0.1
         x = ops.to_act(img_feat, compute_dtype())
         if tape.grad_mode():
-            return tape.DynConvOutFn.apply(x, self, waves)
+            return tape.DynConvOutFn.apply(x, self, waves, *self.weight_generator.parameter_list(self.fclayer))
         wk, b_raw = self._generate(waves)
         packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, self.embed_dim, True, self.scaler,
                                               self.scaler * self.scaler, x.dtype, False)

@@ -510,6 +510,27 @@ def hypernet_forward(wvs: torch.Tensor, params: list, num_layers: int, d: int, h
     return wk, bias
 
 
+def hypernet_backward(wvs: torch.Tensor, params: list, num_layers: int, d: int, heads: int, ff: int, embed: int, decoder: bool,
+                      dw_oihw: torch.Tensor, w_scale: float, dbias: torch.Tensor, bias_scale: float) -> list:
+    """Gradients of params[1:] (params[0] is the sincos table) given the gradient of the generated kernel / bias."""
+    _need_cuda(wvs, dw_oihw, dbias, *params)
+    wvs = wvs.to(torch.float32).contiguous()
+    c = wvs.numel()
+    dw_oihw = dw_oihw.to(torch.float32).contiguous()
+    dbias = dbias.to(torch.float32).contiguous()
+    lib = _C.lib()
+    ws_bytes = lib.eovae_hypernet_backward_workspace_bytes(c, d, ff, embed, num_layers)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=wvs.device)
+    grads = [None] + [torch.empty_like(p) for p in params[1:]]
+    parr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    garr = (ctypes.c_void_p * len(params))(*[None if g is None else g.data_ptr() for g in grads])
+    rc = lib.eovae_hypernet_backward(_ptr(wvs), c, parr, num_layers, d, heads, ff, embed, 1 if decoder else 0, _ptr(dw_oihw),
+                                     dw_oihw.shape[1], float(w_scale), _ptr(dbias), float(bias_scale), garr, _ptr(ws),
+                                     ws_bytes, _stream())
+    _C.check(rc, "eovae_hypernet_backward")
+    return grads[1:]
+
+
 def pack_dyn_weight(wk: torch.Tensor, bias_raw: torch.Tensor, c: int, embed: int, decoder: bool, scale: float,
                     bias_scale: float, dtype, want_oihw: bool):
     """generated kernel -> (igemm B operand, scaled bias, optional fp32 OIHW weight)."""

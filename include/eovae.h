@@ -194,6 +194,16 @@ int eovae_reparam_backward(const float* moments, const long long* mstrides, cons
 /* gradient of eovae_l1_charbonnier wrt a: kind 0 = L1, 1 = Charbonnier; *grad_scale = upstream scalar (device) */
 int eovae_pixel_loss_backward(const float* a, const float* b, long long count, float eps, int kind, const float* grad_scale,
                               float* grad_a, void* stream);
+/* backward of eovae_hypernet_forward + eovae_pack_dyn_weight: dw_oihw = gradient of the generated conv kernel
+ * ([embed][dw_cin_ld >= c][3][3] for the encoder layer, [c][dw_cin_ld >= embed][3][3] for the decoder layer), dbias the
+ * gradient of the scaled bias; w_scale / bias_scale the factors eovae_pack_dyn_weight applied.  grads[i] receives the
+ * gradient of params[i] (same order as the forward; written, not accumulated; grads[0] is ignored).  The forward is
+ * re-run inside (activations kept in the workspace).  dynamic_conv.py:110-130,162-183,352-366,511-525,684-697 adjoint. */
+size_t eovae_hypernet_backward_workspace_bytes(int c, int d, int ff, int embed, int num_layers);
+int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads,
+                            int ff, int embed, int decoder, const float* dw_oihw, int dw_cin_ld, float w_scale,
+                            const float* dbias, float bias_scale, float* const* grads, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* dbias[c] (+)= sum over pixels of grad_out [pixels][c] (16-bit) */
 size_t eovae_bias_grad_workspace_bytes(long long pixels, int c);
 int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, float* dbias, int accumulate, void* workspace,

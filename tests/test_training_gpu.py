@@ -94,6 +94,46 @@ def test_resample_gradients(cuda, kind):
     _check_module(mod, O.upsample if kind == "up" else O.downsample, _act(2, 64, 16, 16, cuda, 6), cuda)
 
 
+@pytest.mark.parametrize("decoder", [False, True])
+@pytest.mark.parametrize("modality", ["S2L2A", "S1RTC"])
+def test_hypernet_backward(cuda, decoder, modality):
+    """eovae_hypernet_backward (full-size generator: d 256, 4 layers, 4 heads, ff 2048) vs autograd over the oracle."""
+    from eo_vae.models.modules.dynamic_conv import DynamicConv, DynamicConv_decoder
+    from oracle import eovae_oracle as O
+    from oracle.weights import WAVELENGTHS
+    torch.manual_seed(7)
+    cls = DynamicConv_decoder if decoder else DynamicConv
+    mod = cls(wv_planes=256, inter_dim=128, kernel_size=3, stride=1, padding=1, embed_dim=128, num_layers=4, num_heads=4).to(cuda)
+    wvs = torch.tensor(WAVELENGTHS[modality], dtype=torch.float32, device=cuda)
+    c, e = wvs.numel(), 128
+    g = torch.Generator().manual_seed(3)
+    shape = (c, e, 3, 3) if decoder else (e, c, 3, 3)
+    dw = torch.randn(shape, generator=g).to(cuda)
+    db = torch.randn((c if decoder else e,), generator=g).to(cuda)
+    bias_scale = 0.01 if decoder else 0.1
+    if decoder:
+        dw_in = dw
+    else:  # the encoder layer's weight gradient comes with the band dimension padded to 16
+        dw_in = torch.zeros((e, 16, 3, 3), device=cuda)
+        dw_in[:, :c] = dw
+    grads = mod._hyper_backward(wvs, dw_in, db, bias_scale)
+    sd = {"m." + k: v.detach().cpu().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+    w_ref, b_ref = O.hypernet(sd, "m", wvs.cpu(), decoder, heads=4)
+    ((w_ref * dw.cpu()).sum() + (b_ref * db.cpu()).sum()).backward()
+    names = [n for n, _ in mod.named_parameters()]
+    by_ptr = {p.data_ptr(): n for n, p in mod.named_parameters()}
+    plist = mod.weight_generator.parameter_list(mod.fclayer)
+    assert len(plist) == len(names)
+    bad = {}
+    for p, got in zip(plist, grads):
+        name = by_ptr[p.data_ptr()]
+        want = sd["m." + name].grad
+        err = float((got.cpu() - want).norm())
+        if not err < 2e-3 * float(want.norm()) + 1e-6:
+            bad[name] = (err, float(want.norm()))
+    assert not bad, bad
+
+
 def _tiny(cuda, seed=3):
     import __graft_entry__ as ge
     from oracle.weights import TINY_CONFIG, make_state_dict
@@ -129,8 +169,6 @@ def test_tiny_model_gradients(cuda):
 
     got, want, worst = [], [], {}
     for name, p in model.named_parameters():
-        if "weight_generator" in name or "fclayer" in name:
-            continue  # hypernetwork gradient: not built yet
         assert p.grad is not None, name
         gr = ref_sd[name].grad
         got.append(p.grad.flatten().cpu())

@@ -169,6 +169,161 @@ size_t partial_floats(int b, int c, int h, int w) {
   return n;
 }
 
+
+// ------------------------------------------------------------------------------------------------- backward
+// d(mean MS-SSIM)/d(pred).  Per scale the map value at an output pixel is f(mu_p, mu_t, E_pp, E_tt, E_pt) with the five
+// Gaussian-filtered fields; only outputs inside the 5-pixel crop count, and those never touch the reflect padding, so
+// the adjoint of the filter is the same symmetric 11-tap correlation with zeros outside the crop:
+//   dp = G*A + 2 p (G*B) + t (G*C),  A = k df/dmu_p, B = k df/dE_pp, C = k df/dE_pt,  k = per-(sample, scale) scalar.
+// A block owns a 32x32 tile of dp: it stages the 52x52 haloed inputs, recomputes the filtered fields on the 42x42 outputs
+// that reach the tile, and runs the adjoint passes out of shared memory; the 2x2 average-pool adjoint of the next
+// (coarser) scale's gradient is added on the way out.  Scales run coarse -> fine.
+constexpr int OUTR = TS + 2 * HALO;   // 42: outputs that reach the tile
+constexpr int INR = TS + 4 * HALO;    // 52: inputs those outputs read
+constexpr size_t kBwdSmemFloats = 2 * INR * (INR + 1) + 5 * INR * (OUTR + 1) + 3 * OUTR * (OUTR + 1) + 3 * OUTR * (TS + 1);
+
+__global__ void __launch_bounds__(256) ssim_scale_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t, int h,
+                                                             int w, int c, Gauss g, float c1, float c2,
+                                                             const float* __restrict__ coef, int use_ssim,
+                                                             const float* __restrict__ dp_next, float* __restrict__ dp) {
+  extern __shared__ float smf[];
+  float (*sp)[INR + 1] = reinterpret_cast<float (*)[INR + 1]>(smf);
+  float (*st)[INR + 1] = reinterpret_cast<float (*)[INR + 1]>(smf + INR * (INR + 1));
+  float (*hz)[INR][OUTR + 1] = reinterpret_cast<float (*)[INR][OUTR + 1]>(smf + 2 * INR * (INR + 1));
+  float (*abc)[OUTR][OUTR + 1] = reinterpret_cast<float (*)[OUTR][OUTR + 1]>(smf + 2 * INR * (INR + 1) + 5 * INR * (OUTR + 1));
+  float (*h2)[OUTR][TS + 1] =
+      reinterpret_cast<float (*)[OUTR][TS + 1]>(smf + 2 * INR * (INR + 1) + 5 * INR * (OUTR + 1) + 3 * OUTR * (OUTR + 1));
+  const int plane = blockIdx.z;
+  const float k = coef[plane / c];
+  const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+  const float* pp = p + static_cast<long long>(plane) * h * w;
+  const float* tp = t + static_cast<long long>(plane) * h * w;
+  for (int i = threadIdx.x; i < INR * INR; i += 256) {
+    const int r = i / INR, cc = i % INR;
+    const int yc = min(max(y0 + r - 2 * HALO, 0), h - 1), xc = min(max(x0 + cc - 2 * HALO, 0), w - 1);
+    sp[r][cc] = __ldg(pp + static_cast<long long>(yc) * w + xc);
+    st[r][cc] = __ldg(tp + static_cast<long long>(yc) * w + xc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < INR * OUTR; i += 256) {
+    const int r = i / OUTR, cc = i % OUTR;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+      const float pv = sp[r][cc + j], tv = st[r][cc + j], wk = g.w[j];
+      a0 = fmaf(wk, pv, a0);
+      a1 = fmaf(wk, tv, a1);
+      a2 = fmaf(wk, pv * pv, a2);
+      a3 = fmaf(wk, tv * tv, a3);
+      a4 = fmaf(wk, pv * tv, a4);
+    }
+    hz[0][r][cc] = a0; hz[1][r][cc] = a1; hz[2][r][cc] = a2; hz[3][r][cc] = a3; hz[4][r][cc] = a4;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < OUTR * OUTR; i += 256) {
+    const int r = i / OUTR, cc = i % OUTR;
+    const int y = y0 + r - HALO, x = x0 + cc - HALO;
+    float va = 0.f, vb = 0.f, vc = 0.f;
+    if (k != 0.f && y >= HALO && y < h - HALO && x >= HALO && x < w - HALO) {
+      float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 11; ++j) {
+        const float wk = g.w[j];
+        m0 = fmaf(wk, hz[0][r + j][cc], m0);
+        m1 = fmaf(wk, hz[1][r + j][cc], m1);
+        m2 = fmaf(wk, hz[2][r + j][cc], m2);
+        m3 = fmaf(wk, hz[3][r + j][cc], m3);
+        m4 = fmaf(wk, hz[4][r + j][cc], m4);
+      }
+      const float mpp = m0 * m0, mtt = m1 * m1, mpt = m0 * m1;
+      const float vpp = m2 - mpp;
+      const float spp = fmaxf(vpp, 0.f), stt = fmaxf(m3 - mtt, 0.f), spt = m4 - mpt;
+      const float gate = vpp > 0.f ? 1.f : 0.f;
+      const float upper = 2.f * spt + c2, lower = spp + stt + c2;
+      const float inv_l = 1.f / lower;
+      const float cs = upper * inv_l;
+      const float dcs_dspt = 2.f * inv_l, dcs_dspp = -upper * inv_l * inv_l * gate;
+      // chain: spt = E_pt - mu_p mu_t ; spp = E_pp - mu_p^2
+      float d_ept = dcs_dspt, d_epp = dcs_dspp, d_mu = dcs_dspt * (-m1) + dcs_dspp * (-2.f * m0);
+      if (use_ssim) {
+        const float ln = 2.f * mpt + c1, ld = mpp + mtt + c1;
+        const float lum = ln / ld;
+        const float dlum = (2.f * m1 * ld - ln * 2.f * m0) / (ld * ld);
+        d_mu = lum * d_mu + cs * dlum;
+        d_ept *= lum;
+        d_epp *= lum;
+      }
+      va = k * d_mu;
+      vb = k * d_epp;
+      vc = k * d_ept;
+    }
+    abc[0][r][cc] = va; abc[1][r][cc] = vb; abc[2][r][cc] = vc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < OUTR * TS; i += 256) {
+    const int r = i / TS, cc = i % TS;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+      const float wk = g.w[j];
+      a0 = fmaf(wk, abc[0][r][cc + j], a0);
+      a1 = fmaf(wk, abc[1][r][cc + j], a1);
+      a2 = fmaf(wk, abc[2][r][cc + j], a2);
+    }
+    h2[0][r][cc] = a0; h2[1][r][cc] = a1; h2[2][r][cc] = a2;
+  }
+  __syncthreads();
+  const int hn = h / 2, wn = w / 2;
+  for (int i = threadIdx.x; i < TS * TS; i += 256) {
+    const int r = i / TS, cc = i % TS;
+    const int y = y0 + r, x = x0 + cc;
+    if (y >= h || x >= w) continue;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+      const float wk = g.w[j];
+      a0 = fmaf(wk, h2[0][r + j][cc], a0);
+      a1 = fmaf(wk, h2[1][r + j][cc], a1);
+      a2 = fmaf(wk, h2[2][r + j][cc], a2);
+    }
+    float v = a0 + 2.f * sp[r + 2 * HALO][cc + 2 * HALO] * a1 + st[r + 2 * HALO][cc + 2 * HALO] * a2;
+    if (dp_next != nullptr && (y >> 1) < hn && (x >> 1) < wn)
+      v += 0.25f * dp_next[(static_cast<long long>(plane) * hn + (y >> 1)) * wn + (x >> 1)];
+    dp[(static_cast<long long>(plane) * h + y) * w + x] = v;
+  }
+}
+
+// coef[s][n] = gscale / B * beta_s * prod_n / v_{n,s} / count_s   (0 where the relu clipped v)
+__global__ void msssim_coef_kernel(const float* __restrict__ partial, Scales sc, int b, const float* __restrict__ gscale,
+                                   float* __restrict__ coef) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= b) return;
+  double v[NSCALES], prod = 1.0;
+  for (int s = 0; s < NSCALES; ++s) {
+    const float* base = partial + sc.s[s].offset + static_cast<long long>(n) * sc.s[s].slots_per_sample * 2;
+    double a = 0.0, cc = 0.0;
+    for (int i = 0; i < sc.s[s].slots_per_sample; ++i) {
+      a += base[2 * i];
+      cc += base[2 * i + 1];
+    }
+    v[s] = (s == NSCALES - 1 ? a : cc) / sc.s[s].count;
+    if (v[s] < 0.0) v[s] = 0.0;
+    prod *= pow(v[s], static_cast<double>(sc.beta[s]));
+  }
+  for (int s = 0; s < NSCALES; ++s)
+    coef[s * b + n] = v[s] > 0.0 ? static_cast<float>(gscale[0] / b * sc.beta[s] * prod / v[s] / sc.s[s].count) : 0.f;
+}
+
+void make_gauss(Gauss* g) {
+  double sum = 0.0, tmp[11];
+  for (int i = 0; i < 11; ++i) {
+    const double d = (i - 5) / 1.5;
+    tmp[i] = exp(-d * d / 2.0);
+    sum += tmp[i];
+  }
+  for (int i = 0; i < 11; ++i) g->w[i] = static_cast<float>(tmp[i] / sum);
+}
+
 }  // namespace
 
 extern "C" {
@@ -230,6 +385,76 @@ int eovae_msssim(const float* pred, const float* target, int b, int c, int h, in
   }
   msssim_finalize_kernel<<<1, 256, 0, stream>>>(partial, sc, b, per_sample, out);
   EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w) {
+  // forward workspace (pyramid + partial sums) + gradient pyramid (pred half only) + coefficients
+  return eovae_msssim_workspace_bytes(b, c, h, w) + sizeof(float) * (pyramid_floats(b, c, h, w) / 2 + NSCALES * static_cast<size_t>(b) + 64);
+}
+
+/* grad_pred = *grad_scale * d(mean MS-SSIM)/d(pred); re-runs the forward pyramid inside. */
+int eovae_msssim_backward(const float* pred, const float* target, int b, int c, int h, int w, float data_range,
+                          const float* grad_scale, float* grad_pred, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(workspace_bytes >= eovae_msssim_backward_workspace_bytes(b, c, h, w), "msssim_backward: workspace too small");
+  float* ws = static_cast<float*>(workspace);
+  const size_t fwd_floats = eovae_msssim_workspace_bytes(b, c, h, w) / sizeof(float);
+  float* out_scratch = ws + fwd_floats - 32;  // inside the forward workspace's 64-float slack
+  if (int rc = eovae_msssim(pred, target, b, c, h, w, data_range, out_scratch, nullptr, workspace,
+                            eovae_msssim_workspace_bytes(b, c, h, w), stream_))
+    return rc;
+  float* pyr = ws;
+  float* partial = ws + pyramid_floats(b, c, h, w);
+  float* gpyr = ws + fwd_floats;
+  float* coef = gpyr + pyramid_floats(b, c, h, w) / 2;
+  Gauss g;
+  make_gauss(&g);
+  const float c1 = (0.01f * data_range) * (0.01f * data_range), c2 = (0.03f * data_range) * (0.03f * data_range);
+  const float betas[NSCALES] = {0.0448f, 0.2856f, 0.3001f, 0.2363f, 0.1333f};
+  Scales sc;
+  const float* ps[NSCALES];
+  const float* ts[NSCALES];
+  float* gs[NSCALES];
+  int hs[NSCALES], wsz[NSCALES];
+  {
+    long long poff = 0, pyoff = 0, goff = 0;
+    int hh = h, ww = w;
+    ps[0] = pred; ts[0] = target; gs[0] = grad_pred;
+    for (int s = 0; s < NSCALES; ++s) {
+      hs[s] = hh; wsz[s] = ww;
+      const int tx = ceil_div(ww, TS), ty = ceil_div(hh, TS);
+      sc.s[s].offset = poff;
+      sc.s[s].slots_per_sample = c * tx * ty;
+      sc.s[s].count = static_cast<double>(c) * (hh - 2 * HALO) * (ww - 2 * HALO);
+      sc.beta[s] = betas[s];
+      poff += 2LL * b * c * tx * ty;
+      if (s + 1 < NSCALES) {
+        const long long plane_next = static_cast<long long>(b) * c * (hh / 2) * (ww / 2);
+        ps[s + 1] = pyr + pyoff;
+        ts[s + 1] = pyr + pyoff + plane_next;
+        pyoff += 2 * plane_next;
+        gs[s + 1] = gpyr + goff;
+        goff += plane_next;
+      }
+      hh /= 2;
+      ww /= 2;
+    }
+  }
+  msssim_coef_kernel<<<ceil_div(b, 64), 64, 0, stream>>>(partial, sc, b, grad_scale, coef);
+  EOVAE_LAUNCH_CHECK();
+  static bool attr = false;
+  const size_t smem = kBwdSmemFloats * sizeof(float);
+  if (!attr) {
+    EOVAE_CUDA(cudaFuncSetAttribute(ssim_scale_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = true;
+  }
+  for (int s = NSCALES - 1; s >= 0; --s) {
+    dim3 grid(ceil_div(wsz[s], TS), ceil_div(hs[s], TS), b * c);
+    ssim_scale_bwd_kernel<<<grid, 256, smem, stream>>>(ps[s], ts[s], hs[s], wsz[s], c, g, c1, c2, coef + s * b,
+                                                        s == NSCALES - 1 ? 1 : 0, s + 1 < NSCALES ? gs[s + 1] : nullptr, gs[s]);
+    EOVAE_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -370,3 +370,20 @@ class PixelLossFn(Function):
         a, b = ctx.saved_tensors
         eps, kind = ctx.cfg
         return ops.pixel_loss_backward(a, b, eps, kind, gl), None, None, None
+
+
+class MsssimFn(Function):
+    """batch-mean MS-SSIM (consistency_loss.py:24-37); backward = eovae_msssim_backward."""
+
+    @staticmethod
+    def forward(ctx, pred, target, data_range):
+        a = pred.to(torch.float32).contiguous()
+        b = target.to(torch.float32).contiguous()
+        ctx.save_for_backward(a, b)
+        ctx.data_range = data_range
+        return ops.msssim(a, b, data_range)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return ops.msssim_backward(a, b, ctx.data_range, g), None, None

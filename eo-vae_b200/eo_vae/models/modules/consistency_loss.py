@@ -32,6 +32,8 @@ class SSIMLoss(nn.Module):
         self.data_range = 6.0
 
     def forward(self, pred, target):
+        if tape.grad_mode() and pred.requires_grad:
+            return 1.0 - tape.MsssimFn.apply(pred, target, self.data_range)[0]
         return 1.0 - ops.msssim(pred, target, self.data_range)[0][0]
 
 
@@ -69,9 +71,6 @@ class EOConsistencyLoss(nn.Module):
             total = total + self.weights['pixel'] * l_rec
             logs[f'{split}/loss_rec'] = l_rec.detach()
         if self.weights['msssim'] > 0 and global_step >= self.starts['msssim']:
-            if tape.grad_mode() and reconstructions.requires_grad:
-                raise NotImplementedError('MS-SSIM has no backward kernel yet (DESIGN.md section 7): train with '
-                                          'global_step < msssim_start_step or msssim_weight = 0')
             l_msssim = self.msssim_loss(reconstructions, inputs)
             total = total + self.weights['msssim'] * l_msssim
             logs[f'{split}/loss_msssim'] = l_msssim.detach()

@@ -348,6 +348,22 @@ def msssim(pred: torch.Tensor, target: torch.Tensor, data_range: float = 6.0):
     return out, per
 
 
+def msssim_backward(pred: torch.Tensor, target: torch.Tensor, data_range: float, grad_scale: torch.Tensor) -> torch.Tensor:
+    """grad_scale * d(mean MS-SSIM)/d(pred), fp32 NCHW."""
+    _need_cuda(pred, target, grad_scale)
+    pred = pred.to(torch.float32).contiguous()
+    target = target.to(torch.float32).contiguous()
+    b, c, h, w = pred.shape
+    lib = _C.lib()
+    ws_bytes = lib.eovae_msssim_backward_workspace_bytes(b, c, h, w)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=pred.device)
+    g = torch.empty_like(pred)
+    gs = grad_scale.to(torch.float32).reshape(1)
+    _C.check(lib.eovae_msssim_backward(_ptr(pred), _ptr(target), b, c, h, w, float(data_range), _ptr(gs), _ptr(g), _ptr(ws),
+                                       ws_bytes, _stream()), "eovae_msssim_backward")
+    return g
+
+
 # ------------------------------------------------------------------------------------------------ backward pieces
 def pack_conv_weight_dgrad(w: torch.Tensor, dtype) -> torch.Tensor:
     """OIHW fp32 -> operand of the data-gradient conv (flipped taps, in/out channels swapped)."""

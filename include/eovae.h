@@ -204,6 +204,11 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
                             int ff, int embed, int decoder, const float* dw_oihw, int dw_cin_ld, float w_scale,
                             const float* dbias, float bias_scale, float* const* grads, void* workspace,
                             size_t workspace_bytes, void* stream);
+/* gradient of eovae_msssim's batch-mean value wrt pred (fp32 NCHW), times the device scalar *grad_scale; the forward
+ * pyramid is rebuilt inside the workspace (consistency_loss.py:24-37 adjoint) */
+size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w);
+int eovae_msssim_backward(const float* pred, const float* target, int b, int c, int h, int w, float data_range,
+                          const float* grad_scale, float* grad_pred, void* workspace, size_t workspace_bytes, void* stream);
 /* dbias[c] (+)= sum over pixels of grad_out [pixels][c] (16-bit) */
 size_t eovae_bias_grad_workspace_bytes(long long pixels, int c);
 int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, float* dbias, int accumulate, void* workspace,

@@ -134,6 +134,27 @@ def test_hypernet_backward(cuda, decoder, modality):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 176, 192), (1, 12, 256, 256)])
+@pytest.mark.parametrize("rec", ["char", "l1"])
+def test_loss_gradients(cuda, shape, rec):
+    """EOConsistencyLoss (pixel + MS-SSIM, the shipped training configuration) value and d/d(reconstruction)."""
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from oracle import eovae_oracle as O
+    g = torch.Generator().manual_seed(21)
+    target = torch.randn(shape, generator=g).clamp_(-2, 6)
+    pred0 = (target + 0.3 * torch.randn(shape, generator=g))
+    loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type=rec, msssim_weight=1.0, msssim_start_step=0).to(cuda)
+    pred = pred0.to(cuda).requires_grad_(True)
+    loss, logs = loss_fn(inputs=target.to(cuda), wvs=None, reconstructions=pred, global_step=10)
+    loss.backward()
+    pr = pred0.clone().requires_grad_(True)
+    ref = O.consistency_loss(target, pr, rec_loss_type=rec, pixel_weight=1.0, msssim_weight=1.0)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-3 * abs(float(ref))
+    assert _rel(pred.grad.cpu(), pr.grad) < 1e-3
+
+
 def _tiny(cuda, seed=3):
     import __graft_entry__ as ge
     from oracle.weights import TINY_CONFIG, make_state_dict

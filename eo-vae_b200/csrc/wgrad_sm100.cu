@@ -146,6 +146,147 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   }
 }
 
+// ---- NHWC variant: both operands are read straight from the pixel-major activations / gradients as MN-MAJOR UMMA
+// operands (the contracted index - the pixel - is the slow one in memory, exactly what MN-major means), so no transposed
+// copies exist at all.  A K chunk = a (bw x bh) = 64-pixel box of 64 channels = one 4-D TMA box, 128-byte swizzled:
+// shared memory holds [64 pixels][128 bytes], the canonical MN-major SW128 atom stack (8 pixel rows = 1024 bytes per
+// K group -> stride byte offset 1024; the next 64 channels are the next box -> leading byte offset 8192).  The tap shift
+// is a shifted box in (x, y), zero-filled outside the image by the TMA unit like in the forward conv.
+struct WgradNhwcParams {
+  CUtensorMap a_map;   // dY: dims (Cout, W, H, N), box (64, bw, bh, 1)
+  CUtensorMap b_map;   // X : dims (Cin,  W, H, N), box (64, bw, bh, 1)
+  int H, W, N;
+  int bw, bh;
+  int taps;
+  int cout, cin;
+  int co_tiles, ci_tiles, ksplit;
+  int chunks_total, chunks_per_split;
+  float* partial;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn128(uint32_t smem_addr) {
+  uint64_t d = static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);   // start address
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;                       // leading byte offset: next 64-channel atom column
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                       // stride byte offset: next group of 8 pixels (K)
+  d |= static_cast<uint64_t>(1) << 46;                               // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                               // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_constant__ WgradNhwcParams p) {
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * STAGE);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WG_STAGES;
+  uint64_t* done_bar = bars + 2 * WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int item = blockIdx.x;
+  const int ks = item % p.ksplit; item /= p.ksplit;
+  const int cit = item % p.ci_tiles; item /= p.ci_tiles;
+  const int cot = item % p.co_tiles; item /= p.co_tiles;
+  const int tap = item;
+  const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+  const int chunk0 = ks * p.chunks_per_split;
+  int chunk1 = chunk0 + p.chunks_per_split;
+  if (chunk1 > p.chunks_total) chunk1 = p.chunks_total;
+  const int nchunks = chunk1 > chunk0 ? chunk1 - chunk0 : 0;
+  const int chunks_w = p.W / p.bw, chunks_h = p.H / p.bh;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.a_map);
+    prefetch_tmap(&p.b_map);
+    for (int i = 0; i < WG_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int chunk = chunk0 + c;
+        const int x0 = (chunk % chunks_w) * p.bw;
+        const int y0 = ((chunk / chunks_w) % chunks_h) * p.bh;
+        const int n = chunk / (chunks_w * chunks_h);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+        uint8_t* sa = smem + stage * STAGE;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) tma_load_4d(&p.a_map, &full_bar[stage], sa + a * 8192, cot * 128 + a * 64, x0, y0, n);
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          tma_load_4d(&p.b_map, &full_bar[stage], sa + A_BYTES + b * 8192, cit * BN + b * 64, x0 + dx, y0 + dy, n);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 16 pixels (two 8-pixel K groups = 2048 bytes) per MMA
+          tc_mma_f16(tmem_base, make_smem_desc_mn128(sa + k * 2048), make_smem_desc_mn128(sa + A_BYTES + k * 2048), p.idesc,
+                     (c | k) != 0 ? 1u : 0u);
+        tc_commit(&empty_bar[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(done_bar);
+    }
+  } else {
+    const int sub = warp & 3;
+    const int co = cot * 128 + sub * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* dst = p.partial + ((static_cast<long long>(ks) * p.taps + tap) * p.cout + co) * p.cin + cit * BN;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t raw[16];
+      tc_ld16(taddr + c, raw);
+      tc_wait_ld();
+      if (co >= p.cout) continue;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        if (cit * BN + c + j < p.cin)
+          *reinterpret_cast<float4*>(dst + c + j) =
+              nchunks > 0 ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]),
+                                        __uint_as_float(raw[j + 3]))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // dW[co][ci][tap] (OIHW, taps innermost) (+)= sum_ks partial[ks][tap][co][ci]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ksplit, int taps, int cout,
                                     int cin, int accumulate, long long total) {
@@ -227,9 +368,109 @@ int launch(const WgradParams& p, int items, cudaStream_t stream) {
   return 0;
 }
 
+
+int make_map_nhwc(CUtensorMap* m, int dtype, const void* base, int c, long long pitch, int w, int h, int n, int bw, int bh) {
+  EncodeFn fn = encode_fn();
+  EOVAE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch) * 2, static_cast<cuuint64_t>(pitch) * 2 * w,
+                           static_cast<cuuint64_t>(pitch) * 2 * w * h};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, dtype == EOVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                  const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EOVAE_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled (NHWC) failed (%d) c %d pitch %lld w %d h %d n %d box %d %d", (int)r,
+              c, pitch, w, h, n, bw, bh);
+  return 0;
+}
+
+int pick_bn_nhwc(int cin) { return cin > 128 ? 256 : (cin > 64 ? 128 : 64); }
+
+void plan_nhwc(int n, int h, int w, int cin, int cout, int taps, int* bn, int* co_tiles, int* ci_tiles, int* ksplit, int* cps,
+               int* chunks_total) {
+  *bn = pick_bn_nhwc(cin);
+  *co_tiles = ceil_div(cout, 128);
+  *ci_tiles = ceil_div(cin, *bn);
+  *chunks_total = static_cast<int>(static_cast<long long>(n) * h * w / 64);
+  const int base = taps * *co_tiles * *ci_tiles;
+  int ks = ceil_div(4 * eovae_num_sms(), base);
+  int max_ks = *chunks_total / 16;
+  if (max_ks < 1) max_ks = 1;
+  if (ks > max_ks) ks = max_ks;
+  if (ks < 1) ks = 1;
+  *cps = ceil_div(*chunks_total, ks);
+  *ksplit = ceil_div(*chunks_total, *cps);
+}
+
+template <int BN>
+int launch_nhwc(const WgradNhwcParams& p, int items, cudaStream_t stream) {
+  constexpr int SMEM = WG_STAGES * (128 * 128 + BN * 128) + 1024 + 256;
+  auto kern = wgrad_nhwc_kernel<BN>;
+  static bool set = false;
+  if (!set) {
+    EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    set = true;
+  }
+  kern<<<items, WG_THREADS, SMEM, stream>>>(p);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int eovae_conv2d_wgrad_nhwc_ok(int h, int w) {
+  const int bw = w >= 64 ? 64 : w;
+  if (bw <= 0 || 64 % bw != 0 || w % bw != 0) return 0;
+  return h % (64 / bw) == 0 ? 1 : 0;
+}
+
+size_t eovae_conv2d_wgrad_nhwc_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize) {
+  int bn, cot, cit, ks, cps, ct;
+  plan_nhwc(n, h, w, cin, cout, ksize * ksize, &bn, &cot, &cit, &ks, &cps, &ct);
+  return sizeof(float) * static_cast<size_t>(ks) * ksize * ksize * cout * cin;
+}
+
+int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int h,
+                            int w, int cin, int cout, int ksize, float* dw_oihw, int accumulate, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad_nhwc: kernel size must be 3 or 1");
+  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "conv2d_wgrad_nhwc: 16-bit operands only");
+  EOVAE_CHECK(eovae_conv2d_wgrad_nhwc_ok(h, w), "conv2d_wgrad_nhwc: %dx%d images do not tile into 64-pixel boxes", h, w);
+  EOVAE_CHECK(cin % 4 == 0 && x_pix_stride % 8 == 0 && dy_pix_stride % 8 == 0 && x_pix_stride >= cin && dy_pix_stride >= cout,
+              "conv2d_wgrad_nhwc: Cin %% 4 and 16-byte pixel pitches required (Cin %d, pitches %lld / %lld)", cin, x_pix_stride,
+              dy_pix_stride);
+  EOVAE_CHECK(workspace_bytes >= eovae_conv2d_wgrad_nhwc_workspace_bytes(n, h, w, cin, cout, ksize), "conv2d_wgrad_nhwc: workspace too small");
+  WgradNhwcParams p;
+  memset(&p, 0, sizeof(p));
+  int bn;
+  plan_nhwc(n, h, w, cin, cout, ksize * ksize, &bn, &p.co_tiles, &p.ci_tiles, &p.ksplit, &p.chunks_per_split, &p.chunks_total);
+  p.H = h; p.W = w; p.N = n; p.taps = ksize * ksize; p.cout = cout; p.cin = cin;
+  p.bw = w >= 64 ? 64 : w;
+  p.bh = 64 / p.bw;
+  p.partial = static_cast<float*>(workspace);
+  const uint32_t fmt = dtype == EOVAE_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(bn >> 3) << 17) |
+            (static_cast<uint32_t>(128 >> 4) << 24);  // bits 15 / 16: A and B are MN-major
+  if (make_map_nhwc(&p.a_map, dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+  if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+  const int items = p.taps * p.co_tiles * p.ci_tiles * p.ksplit;
+  int rc;
+  switch (bn) {
+    case 256: rc = launch_nhwc<256>(p, items, stream); break;
+    case 128: rc = launch_nhwc<128>(p, items, stream); break;
+    default: rc = launch_nhwc<64>(p, items, stream); break;
+  }
+  if (rc) return rc;
+  const long long total = static_cast<long long>(p.taps) * cout * cin;
+  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p.partial, dw_oihw, p.ksplit, p.taps, cout,
+                                                                                      cin, accumulate, total);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
 
 size_t eovae_conv2d_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize) {
   int bn, cot, cit, ks, cps, ct;

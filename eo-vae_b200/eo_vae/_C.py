@@ -43,6 +43,9 @@ SIGNATURES = {
     "eovae_hypernet_backward": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _f, _vp, _vp, _sz, _vp]),
     "eovae_msssim_backward_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "eovae_msssim_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "eovae_conv2d_wgrad_nhwc_ok": (_i, [_i, _i]),
+    "eovae_conv2d_wgrad_nhwc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "eovae_conv2d_wgrad_nhwc": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "eovae_softmax_backward": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _ll, _i, _i, _f, _vp]),
     "eovae_reparam_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "eovae_pixel_loss_backward": (_i, [_vp, _vp, _ll, _f, _i, _vp, _vp, _vp]),

@@ -29,6 +29,7 @@ class GradSync:
         self._pending = [len(b) for b in self.buckets]
         self._inflight: list = []
         self._launched = [False] * len(self.buckets)
+        self.overlap = True   # False: no hooks fire (graph replay) and finish() launches every bucket itself
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self.broadcast_parameters()
 
@@ -48,6 +49,8 @@ class GradSync:
         self._inflight.append((work, flat, ps))
 
     def _on_grad(self, p) -> None:
+        if not self.overlap:
+            return
         i = self._bucket_of[id(p)]
         self._pending[i] -= 1
         if self._pending[i] == 0:

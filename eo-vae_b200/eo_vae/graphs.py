@@ -39,3 +39,93 @@ class GraphedEncoder:
             self.x.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.z
+
+
+def _invalidate_operand_caches(model) -> None:
+    """The derived 16-bit weight operands are keyed on ``weight._version``, which a graph replay does not advance."""
+    for m in model.modules():
+        if hasattr(m, "_packed_key"):
+            m._packed_key = None
+        if hasattr(m, "_fused_key"):
+            m._fused_key = None
+        if hasattr(m, "_qkv_key"):
+            m._qkv_key = None
+
+
+class GraphedTrainStep:
+    """One EOFluxVAE optimisation step with forward + loss + backward replayed as ONE CUDA graph (~1.4k kernel launches
+    whose Python/ctypes issue cost otherwise leaves the GPU idle ~20 % of the step), followed by the eager gradient
+    exchange / clip / Adam / scheduler of ``training_step`` (new_autoencoder.py:587-690).
+
+    Fixed at capture: batch shape, wavelengths (band count), the python-side branches (``p_prior = p_prior_s = 0``,
+    MS-SSIM active or not).  The reparameterisation noise is drawn per step on the CPU generator like the reference
+    (distributions.py:44) and copied into the graph's static buffer."""
+
+    def __init__(self, model, batch: dict, warmup: int = 3):
+        if model.p_prior or model.p_prior_s or model.latent_noise_p:
+            raise RuntimeError("GraphedTrainStep: the EQ-VAE scale/rotation and latent-noise branches are python-side random "
+                               "choices and cannot be frozen into a graph")
+        self.model = model
+        dev = batch["wvs"].device
+        self.x = batch[model.image_key].detach().to(torch.float32).clone()
+        self.wvs = batch["wvs"].detach().clone()
+        b, _, h, w = self.x.shape
+        self.eps_shape = (b, model.encoder.z_channels, h // 8, w // 8)
+        self.eps = torch.zeros(self.eps_shape, dtype=torch.float32, device=dev)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        model._static_eps = self.eps
+        if getattr(model, "_grad_sync", None) is not None:
+            model._grad_sync.overlap = False  # autograd hooks do not run on replay: exchange after the graph instead
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._zero()
+                self.eps.copy_(torch.randn(self.eps_shape))
+                self._forward_backward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self._zero()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._forward_backward()
+        self.grads = [p.grad for p in self.params]
+        self.step_index = 0
+
+    def _zero(self) -> None:
+        for p in self.params:
+            p.grad = None
+
+    def _forward_backward(self) -> torch.Tensor:
+        m = self.model
+        recon, _ = m(self.x, self.wvs)
+        loss, self.logs = m.loss_fn(inputs=self.x, wvs=self.wvs, reconstructions=recon, optimizer_idx=0,
+                                    global_step=m.global_step, last_layer=None, split='train')
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, batch: dict) -> torch.Tensor:
+        m = self.model
+        x = batch[m.image_key]
+        if tuple(x.shape) != tuple(self.x.shape) or batch["wvs"].numel() != self.wvs.numel():
+            raise RuntimeError("GraphedTrainStep was captured for another batch shape / band count")
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x, non_blocking=True)
+        self.wvs.copy_(batch["wvs"], non_blocking=True)
+        self.eps.copy_(torch.randn(self.eps_shape), non_blocking=False)
+        self.graph.replay()
+        for p, g in zip(self.params, self.grads):
+            p.grad = g
+        if getattr(m, "_grad_sync", None) is not None:
+            m._grad_sync.finish()
+        opts = m.optimizers()
+        opt = opts[0] if isinstance(opts, list) else opts
+        if m.clip_grad:
+            torch.nn.utils.clip_grad_norm_(opt.param_groups[0]['params'], m.clip_grad)
+        opt.step()
+        schs = m.lr_schedulers()
+        sch = schs[0] if isinstance(schs, list) and schs else schs
+        if sch:
+            sch.step()
+        _invalidate_operand_caches(m)
+        self.step_index += 1
+        return self.loss

@@ -279,7 +279,8 @@ class EOFluxVAE(LightningModule):
                                      self.encoder.z_channels)
             h = ops.latent_denorm(z_norm, self.bn.running_mean, self.bn.running_var, self.bn_eps, compute_dtype())
             return tape.act_to_nchw_f32(self.decoder.forward_act(h, wvs)), posterior
-        z = posterior.sample() if sample_posterior else posterior.mode()
+        # _static_eps: a device buffer the caller refills every step (eo_vae.graphs.GraphedTrainStep); default = CPU draw
+        z = posterior.sample(getattr(self, '_static_eps', None)) if sample_posterior else posterior.mode()
         if scale is not None:
             z = self._apply_scale(z, scale)
         if angle is not None:

@@ -397,6 +397,9 @@ def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, mode: int, in_hw=None, grad_
     return conv2d(dy, wp, None, cin, mode, residual=grad_add)
 
 
+USE_WGRAD_NHWC = True  # False: always take the transposed-copy kernel (kept for image sizes that do not tile into 64-pixel boxes)
+
+
 def _pixel_rows(t: torch.Tensor) -> torch.Tensor:
     """[N, C, H, W] NHWC-stored (pixel pitch may exceed C) -> [N, H*W, C] view with the pitch as row stride."""
     n, c, h, w = t.shape
@@ -409,12 +412,26 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor
     _need_cuda(x, dy)
     n, cin, h, w = x.shape
     cout = dy.shape[1]
+    lib = _C.lib()
+    if (USE_WGRAD_NHWC and cin % 4 == 0 and pix_stride(x) % 8 == 0 and pix_stride(dy) % 8 == 0
+            and lib.eovae_conv2d_wgrad_nhwc_ok(h, w)):
+        # operands read in place (MN-major UMMA operands): no transposed copies
+        ws_bytes = lib.eovae_conv2d_wgrad_nhwc_workspace_bytes(n, h, w, cin, cout, ksize)
+        ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=x.device)
+        acc = dw is not None
+        if dw is None:
+            dw = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+        flops = 2.0 * n * h * w * cout * cin * ksize * ksize
+        rc = _timed("wgrad", flops, lambda: lib.eovae_conv2d_wgrad_nhwc(
+            _ptr(x), pix_stride(x), _ptr(dy), pix_stride(dy), DT[x.dtype], n, h, w, cin, cout, ksize, _ptr(dw), 1 if acc else 0,
+            _ptr(ws), ws_bytes, _stream()))
+        _C.check(rc, "eovae_conv2d_wgrad_nhwc")
+        return dw
     if cin % 16 != 0:  # narrow edge layers (e.g. an 8-channel latent): zero-pad the channels, slice the result
-        if dw is not None:
-            raise RuntimeError("eo_vae.conv2d_wgrad: accumulation needs Cin % 16 == 0")
         xp = torch.zeros((n, h, w, (cin + 15) // 16 * 16), dtype=x.dtype, device=x.device).permute(0, 3, 1, 2)
         xp[:, :cin].copy_(x)
-        return conv2d_wgrad(xp, dy, ksize)[:, :cin].contiguous()
+        fresh = conv2d_wgrad(xp, dy, ksize)[:, :cin].contiguous()
+        return fresh if dw is None else dw.add_(fresh)
     if ksize == 1:
         xt = transpose16(_pixel_rows(x))    # [n, cin, h*w]
     else:

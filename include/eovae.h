@@ -209,6 +209,14 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
 size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w);
 int eovae_msssim_backward(const float* pred, const float* target, int b, int c, int h, int w, float data_range,
                           const float* grad_scale, float* grad_pred, void* workspace, size_t workspace_bytes, void* stream);
+/* the same weight gradient read straight from the NHWC tensors (x: conv input, dy: output gradient, pixel pitches in
+ * elements) as MN-major tcgen05 operands - no transposed copies.  Usable when eovae_conv2d_wgrad_nhwc_ok(h, w) returns 1
+ * (W divides 64 or is a multiple of 64, H a multiple of 64 / min(W, 64)); otherwise use eovae_conv2d_wgrad. */
+int eovae_conv2d_wgrad_nhwc_ok(int h, int w);
+size_t eovae_conv2d_wgrad_nhwc_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize);
+int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int h,
+                            int w, int cin, int cout, int ksize, float* dw_oihw, int accumulate, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* dbias[c] (+)= sum over pixels of grad_out [pixels][c] (16-bit) */
 size_t eovae_bias_grad_workspace_bytes(long long pixels, int c);
 int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, float* dbias, int accumulate, void* workspace,

@@ -47,10 +47,13 @@ def test_conv_dgrad(cuda, n, h, w, cin, cout, mode):
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 64, 128), (1, 64, 64, 128, 128), (2, 16, 16, 256, 512),
                                             (4, 8, 128, 64, 256), (2, 16, 16, 32, 64), (3, 32, 32, 512, 64),
-                                            (2, 64, 64, 16, 128)])
+                                            (2, 64, 64, 16, 128), (1, 128, 128, 128, 24), (2, 8, 8, 8, 32)])
 @pytest.mark.parametrize("k", [3, 1])
-def test_conv_wgrad_and_bias_grad(cuda, n, h, w, cin, cout, k):
+@pytest.mark.parametrize("nhwc", [True, False])
+def test_conv_wgrad_and_bias_grad(cuda, monkeypatch, n, h, w, cin, cout, k, nhwc):
+    """nhwc=True: operands read in place as MN-major tcgen05 operands; False: the transposed-copy kernel."""
     from eo_vae import ops
+    monkeypatch.setattr(ops, "USE_WGRAD_NHWC", nhwc)
     x = _act(n, cin, h, w, cuda, seed=5)
     wgt = (torch.randn(cout, cin, k, k) / math.sqrt(cin * k * k)).to(cuda).requires_grad_(True)
     bias = torch.zeros(cout, device=cuda, requires_grad=True)

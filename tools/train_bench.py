@@ -2,7 +2,7 @@
 Adam).  Single process = 1 GPU; under torchrun every rank wraps the model in DistributedDataParallel (NCCL gradient
 all-reduce overlapped with backward) and rank 0 prints the whole-job number (max over ranks).
 
-usage: python tools/train_bench.py [batch] [steps] [msssim_start_step] [profile]
+usage: python tools/train_bench.py [batch] [steps] [msssim_start_step] [profile|graph]
 """
 import os
 import sys
@@ -21,6 +21,7 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 ms_start = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
 profile = len(sys.argv) > 4 and sys.argv[4] == "profile"
+use_graph = len(sys.argv) > 4 and sys.argv[4] == "graph"
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -45,8 +46,14 @@ x = torch.randn((batch, 12, 256, 256), device=dev, generator=gen).clamp_(-2, 6)
 batch_d = {model.image_key: x, "wvs": wvs}
 
 
+graphed = None
+if use_graph:
+    from eo_vae.graphs import GraphedTrainStep
+    graphed = GraphedTrainStep(model, batch_d)
+
+
 def step(i):
-    return model.training_step(batch_d, i)
+    return graphed(batch_d) if graphed is not None else model.training_step(batch_d, i)
 
 
 for i in range(3):
@@ -68,7 +75,7 @@ if world > 1:
 ms = float(ms)
 if rank == 0:
     pps = world * batch / ms * 1e3
-    print(f"train_step: {world} GPU x batch {batch}: {ms:.1f} ms/step, {pps:.1f} patches/s, {pps * 2.695:.0f} TFLOP/s algorithmic "
+    print(f"train_step{' (CUDA graph)' if use_graph else ''}: {world} GPU x batch {batch}: {ms:.1f} ms/step, {pps:.1f} patches/s, {pps * 2.695:.0f} TFLOP/s algorithmic "
           f"(2695 GF/patch), loss {float(loss):.4f}, {(ops.launch_count() - l0) // steps} kernel launches/step, peak mem "
           f"{torch.cuda.max_memory_allocated() / 2**30:.1f} GiB, wall {1e3 * (time.time() - t0) / steps:.1f} ms/step")
 if profile and rank == 0:

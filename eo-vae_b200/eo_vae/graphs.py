@@ -70,7 +70,8 @@ class GraphedTrainStep:
         self.x = batch[model.image_key].detach().to(torch.float32).clone()
         self.wvs = batch["wvs"].detach().clone()
         b, _, h, w = self.x.shape
-        self.eps_shape = (b, model.encoder.z_channels, h // 8, w // 8)
+        f = 2 ** (model.encoder.num_resolutions - 1)
+        self.eps_shape = (b, model.encoder.z_channels, h // f, w // f)
         self.eps = torch.zeros(self.eps_shape, dtype=torch.float32, device=dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
         model._static_eps = self.eps
@@ -85,6 +86,9 @@ class GraphedTrainStep:
                 self._forward_backward()
         torch.cuda.current_stream(dev).wait_stream(side)
         self._zero()
+        # the 16-bit weight operands must be REBUILT INSIDE the graph (the optimiser changes the master weights between
+        # replays): drop the caches so the pack kernels are captured and their outputs live in the graph's pool
+        _invalidate_operand_caches(model)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._forward_backward()
@@ -126,6 +130,5 @@ class GraphedTrainStep:
         sch = schs[0] if isinstance(schs, list) and schs else schs
         if sch:
             sch.step()
-        _invalidate_operand_caches(m)
         self.step_index += 1
         return self.loss

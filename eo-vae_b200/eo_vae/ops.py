@@ -315,6 +315,8 @@ def kl_reparam(moments: torch.Tensor, eps, zc: int, want_z: bool = True):
     kl = torch.empty((n,), dtype=torch.float32, device=moments.device)
     if eps is not None:
         eps = eps.to(device=moments.device, dtype=torch.float32).contiguous()
+        if eps.numel() != n * zc * h * w:
+            raise RuntimeError(f"eo_vae.kl_reparam: noise has {eps.numel()} elements, the latent {n * zc * h * w}")
     rc = _C.lib().eovae_kl_reparam(_ptr(moments), _strides4(moments), _ptr(eps), _ptr(z), _ptr(kl), n, h, w, zc, _stream())
     _C.check(rc, "eovae_kl_reparam")
     return z, kl

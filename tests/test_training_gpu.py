@@ -201,6 +201,54 @@ def test_tiny_model_gradients(cuda):
     assert total < 5e-2, (total, top)
 
 
+@pytest.mark.parametrize("modality", ["S1RTC", "S2RGB", "S2L1C"])
+def test_mixed_modality_training_steps(cuda, modality):
+    """BASELINE configs[3]: the band count changes from batch to batch (2 / 3 / 13 bands), the parameters do not; every
+    trainable tensor - the wavelength hypernetworks included - receives a finite gradient."""
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from oracle.weights import WAVELENGTHS, synthetic_patches
+    model, sd, cfg = _tiny(cuda)
+    model.train()
+    model.loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="l1").to(cuda)
+    model.clip_grad = 1.0
+    losses = []
+    for step, mod in enumerate(["S2L2A", modality, "S2L2A", modality]):
+        wvs = torch.tensor(WAVELENGTHS[mod], dtype=torch.float32).to(cuda)
+        x = synthetic_patches(2, wvs.numel(), cfg["resolution"], seed=30 + step).to(cuda)
+        losses.append(float(model.training_step({model.image_key: x, "wvs": wvs}, step)))
+    assert all(l == l and abs(l) < 1e6 for l in losses), losses
+    for name, p in model.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+
+
+def test_graphed_train_step_matches_eager(cuda):
+    """GraphedTrainStep (forward + loss + backward as one CUDA graph) produces the eager step's gradients."""
+    from eo_vae.graphs import GraphedTrainStep
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from oracle.weights import WAVELENGTHS, synthetic_patches
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"], dtype=torch.float32).to(cuda)
+    grads = []
+    for graphed in (False, True):
+        model, sd, cfg = _tiny(cuda)
+        model.train()
+        model.loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="char").to(cuda)
+        model.base_lr = 0.0   # keep the parameters fixed so both runs differentiate the same function
+        batch = {model.image_key: synthetic_patches(2, 12, cfg["resolution"], seed=5).to(cuda), "wvs": wvs}
+        torch.manual_seed(77)
+        if graphed:
+            step = GraphedTrainStep(model, batch, warmup=2)
+            with torch.no_grad():  # the warm-up / capture passes moved the BatchNorm running statistics: restore them
+                model.bn.running_mean.copy_(sd["bn.running_mean"])
+                model.bn.running_var.copy_(sd["bn.running_var"])
+            torch.manual_seed(77)
+            loss = step(batch)
+        else:
+            loss = model.training_step(batch, 0)
+        grads.append((float(loss), torch.cat([p.grad.flatten().float() for p in model.parameters()]).clone()))
+    assert abs(grads[0][0] - grads[1][0]) < 1e-6 * abs(grads[0][0]) + 1e-7
+    assert torch.equal(grads[0][1], grads[1][1])
+
+
 def test_training_step_reduces_loss(cuda):
     """A few manual-optimisation steps (Adam, clip 1.0) on one batch: finite, parameters move, loss goes down."""
     from eo_vae.models.modules.consistency_loss import EOConsistencyLoss

@@ -89,13 +89,27 @@ __global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, const 
                                        int c, int groups, float* __restrict__ gsum /*[n][groups][2]*/,
                                        float* __restrict__ chsum /*[n][c][2]*/) {
   const int n = blockIdx.x;
-  extern __shared__ float tot[];  // [c][2]
+  extern __shared__ float tot[];  // [c][2] totals, then [slices][c][2] slice sums
+  // the bpi partial rows of a channel are split over `slices` threads (fixed assignment), combined in slice order
+  const int slices = c <= static_cast<int>(blockDim.x) ? static_cast<int>(blockDim.x) / c : 1;
+  float* slice_sum = tot + 2 * c;
+  for (int t = threadIdx.x; t < c * slices; t += blockDim.x) {
+    const int ch = t % c, sl = t / c;
+    double a = 0.0, b = 0.0;
+    for (int k = sl; k < bpi; k += slices) {
+      const float2 o = *reinterpret_cast<const float2*>(partial + ((static_cast<long long>(n) * bpi + k) * c + ch) * 2);
+      a += o.x;
+      b += o.y;
+    }
+    slice_sum[(sl * c + ch) * 2] = static_cast<float>(a);
+    slice_sum[(sl * c + ch) * 2 + 1] = static_cast<float>(b);
+  }
+  __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < bpi; ++k) {
-      const float* o = partial + ((static_cast<long long>(n) * bpi + k) * c + ch) * 2;
-      a += o[0];
-      b += o[1];
+    for (int sl = 0; sl < slices; ++sl) {
+      a += slice_sum[(sl * c + ch) * 2];
+      b += slice_sum[(sl * c + ch) * 2 + 1];
     }
     tot[2 * ch] = static_cast<float>(a);
     tot[2 * ch + 1] = static_cast<float>(b);
@@ -404,7 +418,11 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const floa
   if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_R(__nv_bfloat16, true); else EOVAE_GNB_R(__nv_bfloat16, false); }
   else { if (with_silu) EOVAE_GNB_R(__half, true); else EOVAE_GNB_R(__half, false); }
   EOVAE_LAUNCH_CHECK();
-  gn_bwd_finalize_kernel<<<n, 256, sizeof(float) * 2 * c, stream>>>(partial, gamma, n, bpi, c, groups, gsum, chsum);
+  {
+    const int fthreads = 1024;
+    const int slices = c <= fthreads ? fthreads / c : 1;
+    gn_bwd_finalize_kernel<<<n, fthreads, sizeof(float) * 2 * c * (1 + slices), stream>>>(partial, gamma, n, bpi, c, groups, gsum, chsum);
+  }
   EOVAE_LAUNCH_CHECK();
   if (dgamma != nullptr && dbeta != nullptr) {
     gn_bwd_param_kernel<<<ceil_div(c, 128), 128, 0, stream>>>(chsum, n, c, dgamma, dbeta, accumulate_params);

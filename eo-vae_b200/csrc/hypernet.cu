@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
   float acc[4][4] = {};
   for (int k0 = 0; k0 < k; k0 += LBK) {
     for (int e = threadIdx.x; e < LBM * LBK; e += 256) {
-      const int kk = e % LBK, rr = e / LBK;
+      // consecutive threads walk the unit-stride direction of A (rows when A is read transposed, a_rs == 1)
+      const int kk = a_rs == 1 ? e / LBM : e % LBK, rr = a_rs == 1 ? e % LBM : e / LBK;
       as[kk][rr] = (row0 + rr < m && k0 + kk < k) ? a[(row0 + rr) * a_rs + (k0 + kk) * a_cs] : 0.f;
       const int cc = e % LBN, k2 = e / LBN;
       bs[k2][cc] = (col0 + cc < n && k0 + k2 < k) ? b[(k0 + k2) * b_rs + (col0 + cc) * b_cs] : 0.f;

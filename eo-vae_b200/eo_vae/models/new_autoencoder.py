@@ -346,9 +346,10 @@ class EOFluxVAE(LightningModule):
 
     def training_step(self, batch, batch_idx):
         """Mirror of the reference step (:587-690): forward (sampled posterior) -> loss -> manual backward -> clip ->
-        Adam -> scheduler -> log.  The forward and loss kernels exist; the BACKWARD kernels (conv dgrad / wgrad,
-        GroupNorm, attention, hypernetwork, MS-SSIM adjoints) are not built yet, and this path never falls back to
-        torch autograd over library ops - so the step raises instead of silently training nothing."""
+        Adam -> scheduler -> log.  With gradients enabled every module records one tape entry of eo_vae/autograd.py, so
+        ``manual_backward`` runs the hand-written backward kernels (conv dgrad / wgrad, GroupNorm, attention,
+        hypernetwork, reparameterisation, Charbonnier / L1 and MS-SSIM adjoints); under ``enable_ddp()`` the gradients
+        are averaged over the ranks while backward is still running (eo_vae/ddp.py)."""
         opts = self.optimizers()
         opt_gen = opts[0] if isinstance(opts, list) else opts
         schs = self.lr_schedulers()

@@ -285,29 +285,39 @@ __global__ void transpose16_kernel(const uint16_t* __restrict__ in, long long in
   }
 }
 
-// out[d][b][c][y*w + x] = in[b][y*w + x + d - 1][c] when 0 <= x + d - 1 < w, else 0 (d = 0, 1, 2): the three x-shifted
-// channel-major copies the weight-gradient GEMM reads (TMA cannot shift the innermost coordinate by one element).
-__global__ void transpose16_xshift3_kernel(const uint16_t* __restrict__ in, long long in_ld, uint16_t* __restrict__ out,
-                                           int rows, int w, int cols, long long copy_stride) {
+// Channel-major copies for the transposed-operand weight-gradient kernel, image rows padded to w_pad (a multiple of 8 so
+// that a vertical tap shift of +-w_pad pixels keeps the TMA box start 16-byte aligned):
+//   out[d][b][c][y*w_pad + xp] = in[b][y*w + xp + d - 1][c]  when xp < w and 0 <= xp + d - 1 < w, else 0,
+// for the copies d in [d0, d0 + ncopies) (d = 1 is the unshifted copy; TMA cannot shift the innermost coordinate by one
+// element, so the horizontal taps come as separate copies).
+__global__ void transpose16_xshift_kernel(const uint16_t* __restrict__ in, long long in_ld, uint16_t* __restrict__ out,
+                                          int h, int w, int w_pad, int cols, int d0, int ncopies, long long copy_stride) {
   __shared__ uint16_t tile[34][33];
   const long long b = blockIdx.z;
-  const uint16_t* ib = in + b * rows * in_ld;
-  uint16_t* ob = out + b * static_cast<long long>(cols) * rows;
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int rows_out = h * w_pad;
+  const uint16_t* ib = in + b * static_cast<long long>(h) * w * in_ld;
+  uint16_t* ob = out + b * static_cast<long long>(cols) * rows_out;
+  const int c0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 34; j += blockDim.y) {
-    const int r = r0 + j - 1, cc = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (r >= 0 && r < rows && cc < cols) ? ib[static_cast<long long>(r) * in_ld + cc] : uint16_t(0);
+    const int o = o0 + j - 1, cc = c0 + threadIdx.x;
+    uint16_t v = 0;
+    if (o >= 0 && o < rows_out && cc < cols) {
+      const int y = o / w_pad, xp = o % w_pad;
+      if (xp < w) v = ib[(static_cast<long long>(y) * w + xp) * in_ld + cc];
+    }
+    tile[j][threadIdx.x] = v;
   }
   __syncthreads();
-  const int r = r0 + threadIdx.x;
-  const int x = r % w;
+  const int o = o0 + threadIdx.x;
+  const int xp = o % w_pad;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int cc = c0 + j;
-    if (cc >= cols || r >= rows) continue;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const int xs = x + d - 1;
-      ob[d * copy_stride + static_cast<long long>(cc) * rows + r] = (xs >= 0 && xs < w) ? tile[threadIdx.x + d][j] : uint16_t(0);
+    if (cc >= cols || o >= rows_out) continue;
+    for (int i = 0; i < ncopies; ++i) {
+      const int d = d0 + i;
+      const int xs = xp + d - 1;
+      ob[i * copy_stride + static_cast<long long>(cc) * rows_out + o] =
+          (xp < w && xs >= 0 && xs < w) ? tile[threadIdx.x + d][j] : uint16_t(0);
     }
   }
 }
@@ -559,14 +569,17 @@ int eovae_transpose16(const void* in, long long in_ld, void* out, long long out_
   return 0;
 }
 
-int eovae_transpose16_xshift3(const void* in, long long in_ld, void* out, int batch, int h, int w, int cols, void* stream_) {
+int eovae_transpose16_xshift(const void* in, long long in_ld, void* out, int batch, int h, int w, int w_pad, int cols,
+                             int first_shift, int ncopies, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  EOVAE_CHECK(in_ld >= cols, "transpose16_xshift3: pitch smaller than extent");
-  const int rows = h * w;
+  EOVAE_CHECK(in_ld >= cols && w_pad >= w, "transpose16_xshift: pitch smaller than extent");
+  EOVAE_CHECK(first_shift >= -1 && ncopies >= 1 && first_shift + ncopies <= 2, "transpose16_xshift: shifts must lie in [-1, 1]");
+  const int rows = h * w_pad;
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), batch);
   dim3 block(32, 8);
-  transpose16_xshift3_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(in), in_ld, static_cast<uint16_t*>(out), rows, w,
-                                                         cols, static_cast<long long>(batch) * cols * rows);
+  transpose16_xshift_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(in), in_ld, static_cast<uint16_t*>(out), h, w,
+                                                        w_pad, cols, first_shift + 1, ncopies,
+                                                        static_cast<long long>(batch) * cols * rows);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

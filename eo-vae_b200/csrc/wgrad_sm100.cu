@@ -24,7 +24,7 @@ struct WgradParams {
   CUtensorMap a_map;   // dY^T: dims (H*W, Cout, N),       box (64, 128, 1)
   CUtensorMap b_map;   // X^T : dims (H*W, Cin, 3N or N),  box (64, BN, 1)
   int H, W, N;
-  int chunks_img;      // 64-pixel K chunks per image = H * W / 64
+  int chunks_img;      // 64-pixel K chunks per image = ceil(H * W / 64); the ragged tail is TMA zero fill
   int taps;            // 9 or 1
   int cout, cin;
   int co_tiles, ci_tiles, ksplit;
@@ -189,11 +189,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // item order: taps fastest, K split slowest - the CTAs resident at the same time read the SAME pixel range (all taps
+  // and channel tiles of it), so each operand byte comes from DRAM once and from L2 otherwise
   int item = blockIdx.x;
-  const int ks = item % p.ksplit; item /= p.ksplit;
+  const int tap = item % p.taps; item /= p.taps;
   const int cit = item % p.ci_tiles; item /= p.ci_tiles;
   const int cot = item % p.co_tiles; item /= p.co_tiles;
-  const int tap = item;
+  const int ks = item;
   const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
   const int chunk0 = ks * p.chunks_per_split;
   int chunk1 = chunk0 + p.chunks_per_split;
@@ -343,7 +345,7 @@ void plan(int n, int h, int w, int cin, int cout, int taps, int* bn, int* co_til
   *bn = pick_bn(cin);
   *co_tiles = ceil_div(cout, 128);
   *ci_tiles = ceil_div(cin, *bn);
-  *chunks_total = static_cast<int>(static_cast<long long>(n) * h * w / 64);
+  *chunks_total = n * ceil_div(h * w, 64);
   const int base = taps * *co_tiles * *ci_tiles;
   int ks = ceil_div(4 * eovae_num_sms(), base);
   int max_ks = *chunks_total / 16;  // at least 16 K chunks (1024 pixels) per item
@@ -483,14 +485,13 @@ int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int n, int 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad: kernel size must be 3 or 1");
   EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "conv2d_wgrad: 16-bit operands only");
-  EOVAE_CHECK(w % 8 == 0 && cin % 16 == 0, "conv2d_wgrad: W %% 8 and Cin %% 16 required (W %d, Cin %d)", w, cin);
-  EOVAE_CHECK((static_cast<long long>(h) * w) % 64 == 0, "conv2d_wgrad: H * W (%d x %d) must be a multiple of 64", h, w);
+  EOVAE_CHECK(w % 8 == 0 && cin % 16 == 0, "conv2d_wgrad: (padded) W %% 8 and Cin %% 16 required (W %d, Cin %d)", w, cin);
   EOVAE_CHECK(workspace_bytes >= eovae_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, ksize), "conv2d_wgrad: workspace too small");
   WgradParams p;
   memset(&p, 0, sizeof(p));
   int bn;
   plan(n, h, w, cin, cout, ksize * ksize, &bn, &p.co_tiles, &p.ci_tiles, &p.ksplit, &p.chunks_per_split, &p.chunks_total);
-  p.H = h; p.W = w; p.N = n; p.chunks_img = h * w / 64; p.taps = ksize * ksize; p.cout = cout; p.cin = cin;
+  p.H = h; p.W = w; p.N = n; p.chunks_img = ceil_div(h * w, 64); p.taps = ksize * ksize; p.cout = cout; p.cin = cin;
   p.partial = static_cast<float*>(workspace);
   const uint32_t fmt = dtype == EOVAE_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);

@@ -49,7 +49,7 @@ SIGNATURES = {
     "eovae_softmax_backward": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _ll, _i, _i, _f, _vp]),
     "eovae_reparam_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "eovae_pixel_loss_backward": (_i, [_vp, _vp, _ll, _f, _i, _vp, _vp, _vp]),
-    "eovae_transpose16_xshift3": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _vp]),
+    "eovae_transpose16_xshift": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "eovae_latent_norm": (_i, [_vp, C.POINTER(_ll), _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "eovae_latent_denorm": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp]),
     "eovae_kl_reparam": (_i, [_vp, C.POINTER(_ll), _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

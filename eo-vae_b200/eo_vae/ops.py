@@ -434,20 +434,20 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor
         xp[:, :cin].copy_(x)
         fresh = conv2d_wgrad(xp, dy, ksize)[:, :cin].contiguous()
         return fresh if dw is None else dw.add_(fresh)
-    if ksize == 1:
-        xt = transpose16(_pixel_rows(x))    # [n, cin, h*w]
-    else:
-        xt = torch.empty((3, n, cin, h * w), dtype=x.dtype, device=x.device)                     # x-shifted copies
-        _C.check(_C.lib().eovae_transpose16_xshift3(_ptr(x), pix_stride(x), _ptr(xt), n, h, w, cin, _stream()),
-                 "eovae_transpose16_xshift3")
-    dyt = transpose16(_pixel_rows(dy))
-    lib = _C.lib()
-    ws_bytes = lib.eovae_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, ksize)
+    # transposed-operand kernel: channel-major copies, image rows padded to a multiple of 8 pixels
+    wp = (w + 7) // 8 * 8
+    xt = torch.empty((3 if ksize == 3 else 1, n, cin, h * wp), dtype=x.dtype, device=x.device)
+    _C.check(lib.eovae_transpose16_xshift(_ptr(x), pix_stride(x), _ptr(xt), n, h, w, wp, cin, -1 if ksize == 3 else 0,
+                                          3 if ksize == 3 else 1, _stream()), "eovae_transpose16_xshift")
+    dyt = torch.empty((n, cout, h * wp), dtype=dy.dtype, device=dy.device)
+    _C.check(lib.eovae_transpose16_xshift(_ptr(dy), pix_stride(dy), _ptr(dyt), n, h, w, wp, cout, 0, 1, _stream()),
+             "eovae_transpose16_xshift")
+    ws_bytes = lib.eovae_conv2d_wgrad_workspace_bytes(n, h, wp, cin, cout, ksize)
     ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=x.device)
     acc = dw is not None
     if dw is None:
         dw = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
-    _C.check(lib.eovae_conv2d_wgrad(_ptr(xt), _ptr(dyt), DT[x.dtype], n, h, w, cin, cout, ksize, _ptr(dw), 1 if acc else 0,
+    _C.check(lib.eovae_conv2d_wgrad(_ptr(xt), _ptr(dyt), DT[x.dtype], n, h, wp, cin, cout, ksize, _ptr(dw), 1 if acc else 0,
                                     _ptr(ws), ws_bytes, _stream()), "eovae_conv2d_wgrad")
     return dw
 

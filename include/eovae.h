@@ -111,9 +111,11 @@ int eovae_softmax_rows(const void* s, int s_dtype, long long s_ld, void* p, int 
 /* batched transpose of 16-bit matrices: in [batch][rows][in_ld>=cols] -> out [batch][cols][out_ld>=rows], zero padded */
 int eovae_transpose16(const void* in, long long in_ld, void* out, long long out_ld, int batch, int rows, int cols,
                       void* stream);
-/* in [batch][h*w][in_ld>=cols] -> out [3][batch][cols][h*w]: copy d holds the pixels shifted by d-1 along x, zero where
- * x+d-1 leaves the row (the B operand of eovae_conv2d_wgrad for 3x3 kernels) */
-int eovae_transpose16_xshift3(const void* in, long long in_ld, void* out, int batch, int h, int w, int cols, void* stream);
+/* in [batch][h*w][in_ld>=cols] (NHWC rows) -> out [ncopies][batch][cols][h*w_pad]: channel-major copies with the image
+ * rows padded to w_pad; copy i holds the pixels shifted by first_shift + i along x (zero where the shift leaves the row and
+ * in the pad columns).  Operands of eovae_conv2d_wgrad: the gradient as one unshifted copy, the 3x3 input as shifts -1..1 */
+int eovae_transpose16_xshift(const void* in, long long in_ld, void* out, int batch, int h, int w, int w_pad, int cols,
+                             int first_shift, int ncopies, void* stream);
 
 /* ---- posterior + latent glue (distributions.py:20-67, new_autoencoder.py:466-469,533-543,730-738) ------------ */
 /* moments fp32, logical [n][2*zc][h][w] with HOST array mstrides[4] = element strides (n, c, y, x)
@@ -177,8 +179,8 @@ int eovae_scatter_stride2(const void* dy, void* z, int n, int ho, int wo, int h,
 /* out [n][h][w][c] = sum over the 2x2 blocks of g [n][2h][2w][c] (adjoint of nearest x2 upsampling) */
 int eovae_pool2x2_sum(const void* g, void* out, int dtype, int n, int h, int w, int c, void* stream);
 /* weight gradient of a 3x3 (stride 1, pad 1) or 1x1 convolution on tcgen05, contracted over the pixels:
- * dy_t: CHANNEL-MAJOR 16-bit copy [n][cout][h*w] (eovae_transpose16 of the NHWC gradient); x_t: [n][cin][h*w] for 1x1,
- * the three x-shifted copies [3][n][cin][h*w] of eovae_transpose16_xshift3 for 3x3; h*w must be a multiple of 64;
+ * dy_t: CHANNEL-MAJOR 16-bit copy [n][cout][h*w] (eovae_transpose16_xshift, one unshifted copy); x_t: [n][cin][h*w] for
+ * 1x1, the three x-shifted copies [3][n][cin][h*w] for 3x3; here `w` is the PADDED row length (a multiple of 8);
  * dw_oihw fp32 [cout][cin][k][k] (optionally accumulated).  Deterministic (fixed-order split-K reduction).          */
 size_t eovae_conv2d_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize);
 int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int n, int h, int w, int cin, int cout, int ksize,

@@ -47,7 +47,8 @@ def test_conv_dgrad(cuda, n, h, w, cin, cout, mode):
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 64, 128), (1, 64, 64, 128, 128), (2, 16, 16, 256, 512),
                                             (4, 8, 128, 64, 256), (2, 16, 16, 32, 64), (3, 32, 32, 512, 64),
-                                            (2, 64, 64, 16, 128), (1, 128, 128, 128, 24), (2, 8, 8, 8, 32)])
+                                            (2, 64, 64, 16, 128), (1, 128, 128, 128, 24), (2, 8, 8, 8, 32),
+                                            (2, 14, 14, 64, 128), (1, 28, 28, 128, 64), (2, 12, 20, 32, 64), (1, 7, 9, 16, 16)])
 @pytest.mark.parametrize("k", [3, 1])
 @pytest.mark.parametrize("nhwc", [True, False])
 def test_conv_wgrad_and_bias_grad(cuda, monkeypatch, n, h, w, cin, cout, k, nhwc):

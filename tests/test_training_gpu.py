@@ -221,6 +221,31 @@ def test_mixed_modality_training_steps(cuda, modality):
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
 
 
+def test_training_step_odd_image_size(cuda):
+    """56x56 patches (activations 56 / 28 / 14 pixels wide: none tiles into 64-pixel TMA boxes) - the weight gradients
+    take the row-padded transposed-operand kernel; gradients still match autograd over the oracle."""
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from oracle import eovae_oracle as O
+    from oracle.weights import WAVELENGTHS, synthetic_patches
+    model, sd, cfg = _tiny(cuda)
+    model.train()
+    wvs = torch.tensor(WAVELENGTHS["S2RGB"], dtype=torch.float32)
+    x = synthetic_patches(2, 3, 56, seed=13)
+    loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="l1").to(cuda)
+    torch.manual_seed(99)
+    recon, _ = model(x.to(cuda), wvs.to(cuda))
+    loss, _ = loss_fn(inputs=x.to(cuda), wvs=wvs.to(cuda), reconstructions=recon, global_step=0)
+    loss.backward()
+    ref_sd = {k: (v.clone().float().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    torch.manual_seed(99)
+    eps = torch.randn((2, cfg["z_channels"], 14, 14))
+    recon_ref, _ = O.forward(ref_sd, x, wvs, eps, train=True, heads=cfg["hyper_heads"])
+    O.l1_loss(recon_ref, x).backward()
+    got = torch.cat([p.grad.flatten().cpu() for n, p in model.named_parameters()])
+    want = torch.cat([ref_sd[n].grad.flatten() for n, p in model.named_parameters()])
+    assert _rel(got, want) < 6e-2, _rel(got, want)
+
+
 def test_graphed_train_step_matches_eager(cuda):
     """GraphedTrainStep (forward + loss + backward as one CUDA graph) produces the eager step's gradients."""
     from eo_vae.graphs import GraphedTrainStep

@@ -432,6 +432,68 @@ __global__ void l1_char_finalize_kernel(const double* ws, double count, float* o
   out[1] = static_cast<float>(ws[1] / count);
 }
 
+// ------------------------------------------------------------------------------------------------- latent statistics
+// encode_latents.py:36-109 (RunningStatsButFast): per-channel batch mean / unbiased variance / min / max of an NCHW fp32
+// latent batch in ONE pass (one block per channel, fp64 sums), then the parallel-variance merge into the running state
+// on the device - no host synchronisation per batch.
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, int n, int c, long long hw,
+                                                            float* __restrict__ tmp /*[c][4]*/) {
+  const int ch = blockIdx.x;
+  double s = 0.0, q = 0.0;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int img = 0; img < n; ++img) {
+    const float* p = x + (static_cast<long long>(img) * c + ch) * hw;
+    for (long long i = threadIdx.x; i < hw; i += blockDim.x) {
+      const float v = p[i];
+      s += v;
+      q += static_cast<double>(v) * v;
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+  }
+  __shared__ double ss[256], sq[256];
+  __shared__ float smn[256], smx[256];
+  ss[threadIdx.x] = s; sq[threadIdx.x] = q; smn[threadIdx.x] = mn; smx[threadIdx.x] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    float tn = INFINITY, tx = -INFINITY;
+    for (int i = 0; i < 256; ++i) {  // fixed order: deterministic
+      ts += ss[i]; tq += sq[i];
+      tn = fminf(tn, smn[i]); tx = fmaxf(tx, smx[i]);
+    }
+    const double cnt = static_cast<double>(n) * hw;
+    const double mean = ts / cnt;
+    const double var = cnt > 1.0 ? (tq - cnt * mean * mean) / (cnt - 1.0) : 0.0;  // torch.var default: unbiased
+    tmp[4 * ch] = static_cast<float>(mean);
+    tmp[4 * ch + 1] = static_cast<float>(var > 0.0 ? var : 0.0);
+    tmp[4 * ch + 2] = tn;
+    tmp[4 * ch + 3] = tx;
+  }
+}
+// the reference's merge, formula for formula (encode_latents.py:78-94), one thread per channel
+__global__ void running_stats_merge_kernel(const float* __restrict__ tmp, int c, float batch_count, float* __restrict__ mean,
+                                           float* __restrict__ var, float* __restrict__ std, float* __restrict__ count,
+                                           float* __restrict__ vmin, float* __restrict__ vmax) {
+  const int ch = threadIdx.x;
+  const float cnt = count[0];
+  if (ch < c) {
+    const float bm = tmp[4 * ch], bv = tmp[4 * ch + 1];
+    const float n_ab = cnt + batch_count;
+    const float m_a = mean[ch] * cnt, m_b = bm * batch_count;
+    const float M2_a = var[ch] * cnt, M2_b = bv * batch_count;
+    const float delta = bm - mean[ch];
+    mean[ch] = (m_a + m_b) / n_ab;
+    const float v = (M2_a + M2_b + delta * delta * cnt * batch_count / (n_ab + 1e-8f)) / n_ab;
+    var[ch] = v;
+    std[ch] = sqrtf(v + 1e-8f);
+    vmin[ch] = fminf(vmin[ch], tmp[4 * ch + 2]);
+    vmax[ch] = fmaxf(vmax[ch], tmp[4 * ch + 3]);
+  }
+  __syncthreads();
+  if (ch == 0) count[0] = cnt + batch_count;
+}
+
 }  // namespace
 
 extern "C" {
@@ -637,6 +699,18 @@ int eovae_l1_charbonnier(const float* a, const float* b, long long count, float 
       reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), n4, a + n4 * 4, b + n4 * 4, tail, eps * eps, ws);
   EOVAE_LAUNCH_CHECK();
   l1_char_finalize_kernel<<<1, 1, 0, stream>>>(ws, static_cast<double>(count), out);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_running_stats_update(const float* x, int n, int c, long long hw, float* mean, float* var, float* std, float* count,
+                               float* vmin, float* vmax, float* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c >= 1 && c <= 1024 && n >= 1 && hw >= 1, "running_stats_update: bad shape");
+  channel_stats_kernel<<<c, 256, 0, stream>>>(x, n, c, hw, workspace);
+  EOVAE_LAUNCH_CHECK();
+  running_stats_merge_kernel<<<1, round_up(c, 32), 0, stream>>>(workspace, c, static_cast<float>(static_cast<double>(n) * hw), mean, var,
+                                                              std, count, vmin, vmax);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -154,6 +154,12 @@ int eovae_pack_dyn_weight(const float* wk, int c, int embed, int decoder, float 
 int eovae_l1_charbonnier(const float* a, const float* b, long long count, float eps, float* out, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ----  latent statistics of the encode_latents pipeline (encode_latents.py:36-109, RunningStatsButFast):
+ * per-channel mean / unbiased variance / min / max of x [n][c][hw] fp32 merged into the running state (all device
+ * buffers: mean, var, std, vmin, vmax [c], count [1]; workspace 4*c floats) without a host round trip */
+int eovae_running_stats_update(const float* x, int n, int c, long long hw, float* mean, float* var, float* std, float* count,
+                               float* vmin, float* vmax, float* workspace, void* stream);
+
 /* mean multi-scale SSIM over the batch (out[0]) and per sample (per_sample[b], may be NULL); pred, target fp32 NCHW
  * [b][c][h][w], h and w multiples of 16 and >= 176; 5 scales, 11-tap sigma-1.5 Gaussian, reflect padding, relu
  * normalisation, betas (0.0448, 0.2856, 0.3001, 0.2363, 0.1333): torchmetrics' algorithm as called by the reference

@@ -108,3 +108,38 @@ def test_two_rank_gradient_sync(tmp_path):
         want = gs if want is None else [w + g for w, g in zip(want, gs)]
     for got, w in zip(r0["grads"], want):
         assert torch.allclose(got, w / 2, atol=1e-6)
+
+
+def _stats_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "eo-vae_b200"))
+    from eo_vae.encode_latents import RunningStatsButFast
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = torch.randn(6, 4, 8, 8, generator=torch.Generator().manual_seed(3)) * 2 + 1
+    st = O.running_stats_init(4)
+    for i in range(rank, 6, world):                    # this rank's shard, one item per update
+        st = O.running_stats_update(st, x[i:i + 1])
+    rs = RunningStatsButFast((4,), [0, 2, 3])
+    for k in ("mean", "var", "std", "count", "min", "max"):
+        getattr(rs, k).copy_(st[k])
+    rs.merge_ranks()
+    if rank == 0:
+        torch.save(rs.get_stats_dict(), os.path.join(out_dir, "stats.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_latent_statistics_merge(tmp_path):
+    """per-rank running statistics of a sharded encode merge to the single-process statistics."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_stats_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(os.path.join(tmp_path, "stats.pt"))
+    x = torch.randn(6, 4, 8, 8, generator=torch.Generator().manual_seed(3)) * 2 + 1
+    st = O.running_stats_init(4)
+    for i in range(6):
+        st = O.running_stats_update(st, x[i:i + 1])
+    for k in ("mean", "var", "std", "min", "max", "count"):
+        assert torch.allclose(got[k], st[k], rtol=1e-5, atol=1e-6), k

@@ -174,12 +174,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn128(uint32_t smem_addr) {
   return d;
 }
 
-template <int BN>
+// TPI = taps per work item: narrow-Cin layers put TPI taps side by side in the MMA's N dimension (N = TPI * BN <= 256), so
+// the dY tile is loaded once per TPI taps and every instruction runs at the N = 256 operand-traffic ratio.
+template <int BN, int TPI>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_constant__ WgradNhwcParams p) {
   constexpr int A_BYTES = 128 * 128;
-  constexpr int B_BYTES = BN * 128;
+  constexpr int NT = BN * TPI;
+  constexpr int B_BYTES = NT * 128;
   constexpr int STAGE = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  constexpr int TMEM_COLS = NT <= 64 ? 64 : (NT <= 128 ? 128 : 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * STAGE);
@@ -192,11 +195,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_
   // item order: taps fastest, K split slowest - the CTAs resident at the same time read the SAME pixel range (all taps
   // and channel tiles of it), so each operand byte comes from DRAM once and from L2 otherwise
   int item = blockIdx.x;
-  const int tap = item % p.taps; item /= p.taps;
+  const int groups = (p.taps + TPI - 1) / TPI;
+  const int tap0 = (item % groups) * TPI; item /= groups;
   const int cit = item % p.ci_tiles; item /= p.ci_tiles;
   const int cot = item % p.co_tiles; item /= p.co_tiles;
   const int ks = item;
-  const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+  const int ntaps = p.taps - tap0 < TPI ? p.taps - tap0 : TPI;
   const int chunk0 = ks * p.chunks_per_split;
   int chunk1 = chunk0 + p.chunks_per_split;
   if (chunk1 > p.chunks_total) chunk1 = p.chunks_total;
@@ -232,13 +236,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_
         const int y0 = ((chunk / chunks_w) % chunks_h) * p.bh;
         const int n = chunk / (chunks_w * chunks_h);
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+        mbar_expect_tx(&full_bar[stage], A_BYTES + ntaps * BN * 128);
         uint8_t* sa = smem + stage * STAGE;
 #pragma unroll
         for (int a = 0; a < 2; ++a) tma_load_4d(&p.a_map, &full_bar[stage], sa + a * 8192, cot * 128 + a * 64, x0, y0, n);
+        for (int j = 0; j < ntaps; ++j) {
+          const int tap = tap0 + j;
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
 #pragma unroll
-        for (int b = 0; b < BN / 64; ++b)
-          tma_load_4d(&p.b_map, &full_bar[stage], sa + A_BYTES + b * 8192, cit * BN + b * 64, x0 + dx, y0 + dy, n);
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_4d(&p.b_map, &full_bar[stage], sa + A_BYTES + (j * (BN / 64) + b) * 8192, cit * BN + b * 64, x0 + dx, y0 + dy, n);
+        }
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -264,14 +272,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_
     const int co = cot * 128 + sub * 32 + lane;
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    float* dst = p.partial + ((static_cast<long long>(ks) * p.taps + tap) * p.cout + co) * p.cin + cit * BN;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
+    for (int cc = 0; cc < NT; cc += 16) {
+      const int jt = cc / BN, c = cc % BN;  // tap slot, channel inside the Cin tile
+      if (jt >= ntaps) break;
       uint32_t raw[16];
-      tc_ld16(taddr + c, raw);
+      tc_ld16(taddr + cc, raw);
       tc_wait_ld();
       if (co >= p.cout) continue;
+      float* dst = p.partial + ((static_cast<long long>(ks) * p.taps + tap0 + jt) * p.cout + co) * p.cin + cit * BN;
 #pragma unroll
       for (int j = 0; j < 16; j += 4)
         if (cit * BN + c + j < p.cin)
@@ -389,13 +399,15 @@ int make_map_nhwc(CUtensorMap* m, int dtype, const void* base, int c, long long 
 
 int pick_bn_nhwc(int cin) { return cin > 128 ? 256 : (cin > 64 ? 128 : 64); }
 
+int pick_tpi(int bn, int taps) { return taps == 1 ? 1 : 256 / bn; }
+
 void plan_nhwc(int n, int h, int w, int cin, int cout, int taps, int* bn, int* co_tiles, int* ci_tiles, int* ksplit, int* cps,
                int* chunks_total) {
   *bn = pick_bn_nhwc(cin);
   *co_tiles = ceil_div(cout, 128);
   *ci_tiles = ceil_div(cin, *bn);
   *chunks_total = static_cast<int>(static_cast<long long>(n) * h * w / 64);
-  const int base = taps * *co_tiles * *ci_tiles;
+  const int base = ceil_div(taps, pick_tpi(*bn, taps)) * *co_tiles * *ci_tiles;
   int ks = ceil_div(4 * eovae_num_sms(), base);
   int max_ks = *chunks_total / 16;
   if (max_ks < 1) max_ks = 1;
@@ -405,10 +417,10 @@ void plan_nhwc(int n, int h, int w, int cin, int cout, int taps, int* bn, int* c
   *ksplit = ceil_div(*chunks_total, *cps);
 }
 
-template <int BN>
+template <int BN, int TPI>
 int launch_nhwc(const WgradNhwcParams& p, int items, cudaStream_t stream) {
-  constexpr int SMEM = WG_STAGES * (128 * 128 + BN * 128) + 1024 + 256;
-  auto kern = wgrad_nhwc_kernel<BN>;
+  constexpr int SMEM = WG_STAGES * (128 * 128 + BN * TPI * 128) + 1024 + 256;
+  auto kern = wgrad_nhwc_kernel<BN, TPI>;
   static bool set = false;
   if (!set) {
     EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -455,16 +467,19 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
   p.bh = 64 / p.bw;
   p.partial = static_cast<float*>(workspace);
   const uint32_t fmt = dtype == EOVAE_BF16 ? 1u : 0u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(bn >> 3) << 17) |
+  const int tpi = pick_tpi(bn, p.taps);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>((bn * tpi) >> 3) << 17) |
             (static_cast<uint32_t>(128 >> 4) << 24);  // bits 15 / 16: A and B are MN-major
   if (make_map_nhwc(&p.a_map, dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh)) return -3;
   if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh)) return -3;
-  const int items = p.taps * p.co_tiles * p.ci_tiles * p.ksplit;
+  const int items = ceil_div(p.taps, tpi) * p.co_tiles * p.ci_tiles * p.ksplit;
   int rc;
-  switch (bn) {
-    case 256: rc = launch_nhwc<256>(p, items, stream); break;
-    case 128: rc = launch_nhwc<128>(p, items, stream); break;
-    default: rc = launch_nhwc<64>(p, items, stream); break;
+  switch (bn * 8 + tpi) {
+    case 256 * 8 + 1: rc = launch_nhwc<256, 1>(p, items, stream); break;
+    case 128 * 8 + 2: rc = launch_nhwc<128, 2>(p, items, stream); break;
+    case 128 * 8 + 1: rc = launch_nhwc<128, 1>(p, items, stream); break;
+    case 64 * 8 + 4: rc = launch_nhwc<64, 4>(p, items, stream); break;
+    default: rc = launch_nhwc<64, 1>(p, items, stream); break;
   }
   if (rc) return rc;
   const long long total = static_cast<long long>(p.taps) * cout * cin;

@@ -11,6 +11,8 @@
 // Work item = (tap, 128-row Cout tile, Cin tile, K split); every CTA accumulates its pixel range in TMEM and writes one
 // fp32 partial tile, a second kernel reduces the K splits in fixed order (deterministic) into OIHW fp32.
 #include "../../include/eovae.h"
+#include <cstdlib>
+
 #include "igemm_sm100.cuh"
 
 namespace {
@@ -299,6 +301,137 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_
   }
 }
 
+// ---- CTA-pair variant for the wide layers (Cout % 256 == 0, Cin % 256 == 0): one tcgen05.mma.cta_group::2 instruction
+// covers 256 Cout rows x 256 Cin columns; CTA r of the pair stages ITS 128 dY channels and HALF of the X tile (128 of the
+// 256 Cin columns), so an instruction reads 8 KB of shared memory per CTA instead of 12 KB (the 1-CTA 128x256x16 MMA is
+// operand-bandwidth bound at ~187 cycles; the pair runs at the ~128-cycle tensor rate).  Barrier protocol = the forward
+// igemm's: all TMA bytes of both CTAs complete on the LEADER's full barrier, the leader issues the MMAs and multicasts
+// the commit to both CTAs' empty barriers.
+constexpr int WG2_STAGES = 3;
+constexpr int WG2_KC = 2;      // 64-pixel K chunks per pipeline stage (the single producer / issuer threads pay ~300 cycles per stage)
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc2_kernel(const __grid_constant__ WgradNhwcParams p) {
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int B_BYTES = 128 * 128;   // this CTA's half of the 256 Cin columns
+  constexpr int CHUNK = A_BYTES + B_BYTES;
+  constexpr int STAGE = WG2_KC * CHUNK;
+  constexpr int TMEM_COLS = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG2_STAGES * STAGE);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WG2_STAGES;
+  uint64_t* done_bar = bars + 2 * WG2_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG2_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  int item = blockIdx.x >> 1;
+  const int tap = item % p.taps; item /= p.taps;
+  const int cit = item % p.ci_tiles; item /= p.ci_tiles;
+  const int cot2 = item % p.co_tiles; item /= p.co_tiles;   // here co_tiles counts 256-row tiles
+  const int ks = item;
+  const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+  const int chunk0 = ks * p.chunks_per_split;
+  int chunk1 = chunk0 + p.chunks_per_split;
+  if (chunk1 > p.chunks_total) chunk1 = p.chunks_total;
+  const int nchunks = chunk1 > chunk0 ? chunk1 - chunk0 : 0;
+  const int chunks_w = p.W / p.bw, chunks_h = p.H / p.bh;
+  const int co_base = cot2 * 256 + static_cast<int>(rank) * 128;
+  const int ci_base = cit * 256 + static_cast<int>(rank) * 128;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.a_map);
+    prefetch_tmap(&p.b_map);
+    for (int i = 0; i < WG2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);    // one producer arrive per CTA of the pair (the leader's copy is the live one)
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nchunks; c += WG2_KC) {
+        const int nck = nchunks - c < WG2_KC ? nchunks - c : WG2_KC;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) mbar_expect_tx(&full_bar[stage], 2 * nck * CHUNK); else mbar_arrive_leader(&full_bar[stage]);
+        for (int q = 0; q < nck; ++q) {
+          const int chunk = chunk0 + c + q;
+          const int x0 = (chunk % chunks_w) * p.bw;
+          const int y0 = ((chunk / chunks_w) % chunks_h) * p.bh;
+          const int n = chunk / (chunks_w * chunks_h);
+          uint8_t* sa = smem + stage * STAGE + q * CHUNK;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) tma2_load_4d(&p.a_map, &full_bar[stage], sa + a * 8192, co_base + a * 64, x0, y0, n);
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            tma2_load_4d(&p.b_map, &full_bar[stage], sa + A_BYTES + b * 8192, ci_base + b * 64, x0 + dx, y0 + dy, n);
+        }
+        if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nchunks; c += WG2_KC) {
+        const int nck = nchunks - c < WG2_KC ? nchunks - c : WG2_KC;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        for (int q = 0; q < nck; ++q) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE + q * CHUNK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc2_mma_f16(tmem_base, make_smem_desc_mn128(sa + k * 2048), make_smem_desc_mn128(sa + A_BYTES + k * 2048), p.idesc,
+                        (c | q | k) != 0 ? 1u : 0u);
+        }
+        tc2_commit_mc(&empty_bar[stage]);
+        if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc2_commit_mc(done_bar);
+    }
+  } else {
+    const int sub = warp & 3;
+    const int co = co_base + sub * 32 + lane;
+    if (nchunks > 0) mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* dst = p.partial + ((static_cast<long long>(ks) * p.taps + tap) * p.cout + co) * p.cin + cit * 256;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 16) {
+      uint32_t raw[16];
+      if (nchunks > 0) {
+        tc_ld16(taddr + c, raw);
+        tc_wait_ld();
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(dst + c + j) =
+            nchunks > 0 ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]),
+                                      __uint_as_float(raw[j + 3]))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // dW[co][ci][tap] (OIHW, taps innermost) (+)= sum_ks partial[ks][tap][co][ci]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ksplit, int taps, int cout,
                                     int cin, int accumulate, long long total) {
@@ -397,6 +530,8 @@ int make_map_nhwc(CUtensorMap* m, int dtype, const void* base, int c, long long 
   return 0;
 }
 
+bool g_no_pair = false;  // EOVAE_WGRAD_NO_PAIR=1: keep the 1-CTA kernel (A/B measurements)
+
 int pick_bn_nhwc(int cin) { return cin > 128 ? 256 : (cin > 64 ? 128 : 64); }
 
 int pick_tpi(int bn, int taps) { return taps == 1 ? 1 : 256 / bn; }
@@ -444,6 +579,16 @@ int eovae_conv2d_wgrad_nhwc_ok(int h, int w) {
 size_t eovae_conv2d_wgrad_nhwc_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize) {
   int bn, cot, cit, ks, cps, ct;
   plan_nhwc(n, h, w, cin, cout, ksize * ksize, &bn, &cot, &cit, &ks, &cps, &ct);
+  if (cout % 256 == 0 && cin % 256 == 0) {  // CTA-pair plan (see eovae_conv2d_wgrad_nhwc)
+    const int base = ksize * ksize * (cout / 256) * (cin / 256);
+    int ks2 = ceil_div(2 * eovae_num_sms(), base);
+    int max_ks = ct / 16;
+    if (max_ks < 1) max_ks = 1;
+    if (ks2 > max_ks) ks2 = max_ks;
+    const int cps2 = ceil_div(ct, ks2);
+    ks2 = ceil_div(ct, cps2);
+    if (ks2 > ks) ks = ks2;
+  }
   return sizeof(float) * static_cast<size_t>(ks) * ksize * ksize * cout * cin;
 }
 
@@ -458,6 +603,12 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
               "conv2d_wgrad_nhwc: Cin %% 4 and 16-byte pixel pitches required (Cin %d, pitches %lld / %lld)", cin, x_pix_stride,
               dy_pix_stride);
   EOVAE_CHECK(workspace_bytes >= eovae_conv2d_wgrad_nhwc_workspace_bytes(n, h, w, cin, cout, ksize), "conv2d_wgrad_nhwc: workspace too small");
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("EOVAE_WGRAD_NO_PAIR");
+    g_no_pair = e != nullptr && e[0] == '1';
+    env_read = true;
+  }
   WgradNhwcParams p;
   memset(&p, 0, sizeof(p));
   int bn;
@@ -467,6 +618,49 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
   p.bh = 64 / p.bw;
   p.partial = static_cast<float*>(workspace);
   const uint32_t fmt = dtype == EOVAE_BF16 ? 1u : 0u;
+  if (cout % 256 == 0 && cin % 256 == 0 && !g_no_pair) {
+    // CTA-pair kernel: co_tiles counts 256-row tiles; same split-K plan (the partial layout does not depend on the tiling)
+    p.co_tiles = cout / 256;
+    p.ci_tiles = cin / 256;
+    const int base = p.taps * p.co_tiles * p.ci_tiles;
+    int ks = ceil_div(2 * eovae_num_sms(), base);      // 2 CTAs per item
+    int max_ks = p.chunks_total / 16;
+    if (max_ks < 1) max_ks = 1;
+    if (ks > max_ks) ks = max_ks;
+    p.chunks_per_split = ceil_div(p.chunks_total, ks);
+    p.ksplit = ceil_div(p.chunks_total, p.chunks_per_split);
+    EOVAE_CHECK(workspace_bytes >= sizeof(float) * static_cast<size_t>(p.ksplit) * p.taps * cout * cin, "conv2d_wgrad_nhwc: workspace too small");
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(256 >> 3) << 17) |
+              (static_cast<uint32_t>(256 >> 4) << 24);
+    if (make_map_nhwc(&p.a_map, dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+    if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+    constexpr int SMEM2 = WG2_STAGES * WG2_KC * (2 * 128 * 128) + 1024 + 256;
+    static bool set2 = false;
+    if (!set2) {
+      EOVAE_CUDA(cudaFuncSetAttribute(wgrad_nhwc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2));
+      set2 = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * base * p.ksplit));
+    cfg.blockDim = dim3(WG_THREADS);
+    cfg.dynamicSmemBytes = SMEM2;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EOVAE_CUDA(cudaLaunchKernelEx(&cfg, wgrad_nhwc2_kernel, p));
+    EOVAE_LAUNCH_CHECK();
+    const long long total2 = static_cast<long long>(p.taps) * cout * cin;
+    wgrad_reduce_kernel<<<static_cast<unsigned>((total2 + 255) / 256), 256, 0, stream>>>(p.partial, dw_oihw, p.ksplit, p.taps, cout,
+                                                                                        cin, accumulate, total2);
+    EOVAE_LAUNCH_CHECK();
+    return 0;
+  }
   const int tpi = pick_tpi(bn, p.taps);
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>((bn * tpi) >> 3) << 17) |
             (static_cast<uint32_t>(128 >> 4) << 24);  // bits 15 / 16: A and B are MN-major

@@ -475,6 +475,24 @@ int make_map(CUtensorMap* m, int dtype, const void* base, long long pixels, int 
   return 0;
 }
 
+// K split: `base` independent tiles, `chunks` 64-pixel K chunks each, `slots` CTAs (or CTA pairs) resident at once.
+// cost(ks) = waves(ks) x (chunks per item + fixed per-item cost): an item pays ~4 us of TMEM allocation, barrier setup,
+// pipeline fill and fp32 partial-tile write-out, about the MMA time of 16 chunks; whole waves only (1 CTA per SM).
+int pick_ksplit(int base, int chunks, int slots) {
+  int best = 1;
+  long long best_cost = -1;
+  const int max_ks = chunks / 8 > 1 ? chunks / 8 : 1;
+  for (int ks = 1; ks <= max_ks && ks <= 4096; ++ks) {
+    const long long waves = ceil_div(base * ks, slots);
+    const long long cost = waves * (ceil_div(chunks, ks) + 16);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = ks;
+    }
+  }
+  return best;
+}
+
 int pick_bn(int cin) {
   if (cin >= 256) return 256;
   if (cin >= 128) return 128;
@@ -490,11 +508,7 @@ void plan(int n, int h, int w, int cin, int cout, int taps, int* bn, int* co_til
   *ci_tiles = ceil_div(cin, *bn);
   *chunks_total = n * ceil_div(h * w, 64);
   const int base = taps * *co_tiles * *ci_tiles;
-  int ks = ceil_div(4 * eovae_num_sms(), base);
-  int max_ks = *chunks_total / 16;  // at least 16 K chunks (1024 pixels) per item
-  if (max_ks < 1) max_ks = 1;
-  if (ks > max_ks) ks = max_ks;
-  if (ks < 1) ks = 1;
+  const int ks = pick_ksplit(base, *chunks_total, eovae_num_sms());
   *cps = ceil_div(*chunks_total, ks);
   *ksplit = ceil_div(*chunks_total, *cps);
 }
@@ -543,11 +557,7 @@ void plan_nhwc(int n, int h, int w, int cin, int cout, int taps, int* bn, int* c
   *ci_tiles = ceil_div(cin, *bn);
   *chunks_total = static_cast<int>(static_cast<long long>(n) * h * w / 64);
   const int base = ceil_div(taps, pick_tpi(*bn, taps)) * *co_tiles * *ci_tiles;
-  int ks = ceil_div(4 * eovae_num_sms(), base);
-  int max_ks = *chunks_total / 16;
-  if (max_ks < 1) max_ks = 1;
-  if (ks > max_ks) ks = max_ks;
-  if (ks < 1) ks = 1;
+  const int ks = pick_ksplit(base, *chunks_total, eovae_num_sms());
   *cps = ceil_div(*chunks_total, ks);
   *ksplit = ceil_div(*chunks_total, *cps);
 }
@@ -581,10 +591,7 @@ size_t eovae_conv2d_wgrad_nhwc_workspace_bytes(int n, int h, int w, int cin, int
   plan_nhwc(n, h, w, cin, cout, ksize * ksize, &bn, &cot, &cit, &ks, &cps, &ct);
   if (cout % 256 == 0 && cin % 256 == 0) {  // CTA-pair plan (see eovae_conv2d_wgrad_nhwc)
     const int base = ksize * ksize * (cout / 256) * (cin / 256);
-    int ks2 = ceil_div(2 * eovae_num_sms(), base);
-    int max_ks = ct / 16;
-    if (max_ks < 1) max_ks = 1;
-    if (ks2 > max_ks) ks2 = max_ks;
+    int ks2 = pick_ksplit(base, ct, eovae_num_sms() / 2);
     const int cps2 = ceil_div(ct, ks2);
     ks2 = ceil_div(ct, cps2);
     if (ks2 > ks) ks = ks2;
@@ -623,10 +630,7 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
     p.co_tiles = cout / 256;
     p.ci_tiles = cin / 256;
     const int base = p.taps * p.co_tiles * p.ci_tiles;
-    int ks = ceil_div(2 * eovae_num_sms(), base);      // 2 CTAs per item
-    int max_ks = p.chunks_total / 16;
-    if (max_ks < 1) max_ks = 1;
-    if (ks > max_ks) ks = max_ks;
+    const int ks = pick_ksplit(base, p.chunks_total, eovae_num_sms() / 2);  // one CTA pair per two SMs
     p.chunks_per_split = ceil_div(p.chunks_total, ks);
     p.ksplit = ceil_div(p.chunks_total, p.chunks_per_split);
     EOVAE_CHECK(workspace_bytes >= sizeof(float) * static_cast<size_t>(p.ksplit) * p.taps * cout * cin, "conv2d_wgrad_nhwc: workspace too small");

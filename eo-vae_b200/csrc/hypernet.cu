@@ -178,23 +178,32 @@ int linear(const float* x, int ldx, const float* w, const float* b, const float*
 
 // ------------------------------------------------------------------------------------------------- backward pieces
 // C[m][n] (+)= sum_k A[i*a_rs + k*a_cs] * B[k*b_rs + j*b_cs]: generic-stride fp32 GEMM for the (tiny, <= 142-row)
-// hypernetwork gradients; 64 x 64 tiles, 4 x 4 outputs per thread.
+// hypernetwork gradients; 64 x 64 tiles, 4 x 4 outputs per thread.  blockIdx.z = batch index (per-head products, batch
+// strides a_bs / b_bs / c_bs) x K split: with `splits` > 1 every z-slice owns a K range and writes its tile to
+// part[split][batch][m][n]; sgemm_reduce_kernel sums the slices in fixed order (deterministic).
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ a, long long a_rs, long long a_cs,
-                                                            const float* __restrict__ b, long long b_rs, long long b_cs,
-                                                            float* __restrict__ c, long long ldc, int m, int n, int k,
-                                                            int accumulate) {
+                                                            long long a_bs, const float* __restrict__ b, long long b_rs,
+                                                            long long b_cs, long long b_bs, float* __restrict__ c,
+                                                            long long ldc, long long c_bs, int m, int n, int k,
+                                                            int accumulate, int splits, int k_per_split,
+                                                            float* __restrict__ part) {
   __shared__ float as[LBK][LBM + 4];
   __shared__ float bs[LBK][LBN + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int row0 = blockIdx.y * LBM, col0 = blockIdx.x * LBN;
+  const int batch = blockIdx.z / splits, split = blockIdx.z % splits;
+  a += batch * a_bs;
+  b += batch * b_bs;
+  const int kb = split * k_per_split;
+  const int ke = min(k, kb + k_per_split);
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < k; k0 += LBK) {
+  for (int k0 = kb; k0 < ke; k0 += LBK) {
     for (int e = threadIdx.x; e < LBM * LBK; e += 256) {
       // consecutive threads walk the unit-stride direction of A (rows when A is read transposed, a_rs == 1)
       const int kk = a_rs == 1 ? e / LBM : e % LBK, rr = a_rs == 1 ? e % LBM : e / LBK;
-      as[kk][rr] = (row0 + rr < m && k0 + kk < k) ? a[(row0 + rr) * a_rs + (k0 + kk) * a_cs] : 0.f;
+      as[kk][rr] = (row0 + rr < m && k0 + kk < ke) ? a[(row0 + rr) * a_rs + (k0 + kk) * a_cs] : 0.f;
       const int cc = e % LBN, k2 = e / LBN;
-      bs[k2][cc] = (col0 + cc < n && k0 + k2 < k) ? b[(k0 + k2) * b_rs + (col0 + cc) * b_cs] : 0.f;
+      bs[k2][cc] = (col0 + cc < n && k0 + k2 < ke) ? b[(k0 + k2) * b_rs + (col0 + cc) * b_cs] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -209,6 +218,8 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
     }
     __syncthreads();
   }
+  float* out = splits > 1 ? part + (static_cast<long long>(split) * gridDim.z / splits + batch) * m * n : c + batch * c_bs;
+  const long long ld = splits > 1 ? n : ldc;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rr = row0 + ty * 4 + i;
@@ -217,19 +228,55 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
     for (int j = 0; j < 4; ++j) {
       const int cc = col0 + tx * 4 + j;
       if (cc < n) {
-        float* o = c + rr * ldc + cc;
-        *o = (accumulate ? *o : 0.f) + acc[i][j];
+        float* o = out + rr * ld + cc;
+        *o = (splits == 1 && accumulate ? *o : 0.f) + acc[i][j];
       }
     }
   }
 }
+__global__ void sgemm_reduce_kernel(const float* __restrict__ part, int splits, int batches, float* __restrict__ c, long long ldc,
+                                    long long c_bs, int m, int n, int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // over (batch, m, n)
+  const long long per = static_cast<long long>(m) * n;
+  if (i >= per * batches) return;
+  const int batch = static_cast<int>(i / per);
+  const long long r = i % per;
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += part[(static_cast<long long>(z) * batches + batch) * per + r];
+  float* o = c + batch * c_bs + (r / n) * ldc + (r % n);
+  *o = (accumulate ? *o : 0.f) + v;
+}
 
+// `part`: split-K scratch (kLinearPartFloats floats) or nullptr to forbid splitting
+int sgemm_b(const float* a, long long a_rs, long long a_cs, long long a_bs, const float* b, long long b_rs, long long b_cs,
+            long long b_bs, float* c, long long ldc, long long c_bs, int batches, int m, int n, int k, int accumulate, float* part,
+            cudaStream_t st) {
+  const int tiles = ceil_div(n, LBN) * ceil_div(m, LBM) * batches;
+  int splits = 1;
+  if (part != nullptr && tiles < eovae_num_sms() && k >= 8 * LBK) {
+    splits = ceil_div(2 * eovae_num_sms(), tiles);
+    const int max_splits = k / (4 * LBK);  // at least 64 k per split
+    if (splits > max_splits) splits = max_splits;
+    while (splits > 1 && static_cast<size_t>(splits) * batches * m * n > static_cast<size_t>(32) * 192 * 2048) --splits;
+    if (splits < 1) splits = 1;
+  }
+  int kps = round_up(ceil_div(k, splits), LBK);
+  splits = ceil_div(k, kps);
+  dim3 grid(ceil_div(n, LBN), ceil_div(m, LBM), batches * splits);
+  sgemm_strided_kernel<<<grid, 256, 0, st>>>(a, a_rs, a_cs, a_bs, b, b_rs, b_cs, b_bs, c, ldc, c_bs, m, n, k, accumulate, splits, kps, part);
+  EOVAE_LAUNCH_CHECK();
+  if (splits > 1) {
+    const long long total = static_cast<long long>(batches) * m * n;
+    sgemm_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(part, splits, batches, c, ldc, c_bs, m, n, accumulate);
+    EOVAE_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+thread_local float* g_sgemm_part = nullptr;  // split-K scratch of the eovae_hypernet_backward call running on this host thread
 int sgemm(const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c,
           long long ldc, int m, int n, int k, int accumulate, cudaStream_t st) {
-  dim3 grid(ceil_div(n, LBN), ceil_div(m, LBM));
-  sgemm_strided_kernel<<<grid, 256, 0, st>>>(a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, m, n, k, accumulate);
-  EOVAE_LAUNCH_CHECK();
-  return 0;
+  return sgemm_b(a, a_rs, a_cs, 0, b, b_rs, b_cs, 0, c, ldc, 0, 1, m, n, k, accumulate, g_sgemm_part, st);
 }
 
 // out[j] (+)= sum_r x[r][j]
@@ -537,6 +584,7 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
   float* dwk = take(static_cast<long long>(c) * 9 * embed);
   float* part = take(64);
   part = ws;
+  g_sgemm_part = part;
   const float* omega = params[0];
   const float* wtok = params[1];
   const float* btok = params[2];
@@ -645,8 +693,11 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
     EOVAE_LAUNCH_CHECK();
     mha_bwd_q_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(L[l].qkv, datt, pbuf, dsbuf, dqkv, s, d, heads);
     EOVAE_LAUNCH_CHECK();
-    mha_bwd_kv_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(L[l].qkv, datt, pbuf, dsbuf, dqkv, s, d, heads);
-    EOVAE_LAUNCH_CHECK();
+    {  // dK_h = dS_h^T Q_h, dV_h = P_h^T dO_h: two head-batched GEMMs over the query index
+      const int hd = d / heads;
+      if (sgemm_b(dsbuf, 1, s, static_cast<long long>(s) * s, L[l].qkv, 3 * d, 1, hd, dqkv + d, 3 * d, hd, heads, s, hd, s, 0, nullptr, st)) return -1;
+      if (sgemm_b(pbuf, 1, s, static_cast<long long>(s) * s, datt, d, 1, hd, dqkv + 2 * d, 3 * d, hd, heads, s, hd, s, 0, nullptr, st)) return -1;
+    }
     // qkv = xin Win^T + bin ; dxin = dtmp1 + dqkv Win
     EOVAE_CUDA(cudaMemcpyAsync(dx, dtmp1, sizeof(float) * sd, cudaMemcpyDeviceToDevice, st));
     if (sgemm(dqkv, 3 * d, 1, lp[0], d, 1, dx, d, s, d, 3 * d, 1, st)) return -1;

@@ -10,7 +10,7 @@ namespace {
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ float silu_grad(float z) {  // d/dz [z * sigmoid(z)]
-  const float s = 1.0f / (1.0f + __expf(-z));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-z));
   return s * (1.0f + z * (1.0f - s));
 }
 
@@ -47,9 +47,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __rest
     if (p1 > hw) p1 = hw;
     const T* xb = x + (static_cast<long long>(n) * hw) * c + v * 8;
     const T* gb = g + (static_cast<long long>(n) * hw) * c + v * 8;
-    for (long long p = p0 + r; p < p1; p += rows) {
-      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(xb + p * c));
-      const uint4 ug = __ldg(reinterpret_cast<const uint4*>(gb + p * c));
+    auto accum = [&](const uint4& ux, const uint4& ug) {
       const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -63,7 +61,18 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __rest
         sa[2 * j] += d0; sb[2 * j] = fmaf(d0, xh0, sb[2 * j]);
         sa[2 * j + 1] += d1; sb[2 * j + 1] = fmaf(d1, xh1, sb[2 * j + 1]);
       }
+    };
+    long long p = p0 + r;
+    for (; p + rows < p1; p += 2LL * rows) {  // two pixels per iteration: four 16-byte loads in flight per thread
+      const uint4 ux0 = __ldg(reinterpret_cast<const uint4*>(xb + p * c));
+      const uint4 ug0 = __ldg(reinterpret_cast<const uint4*>(gb + p * c));
+      const uint4 ux1 = __ldg(reinterpret_cast<const uint4*>(xb + (p + rows) * c));
+      const uint4 ug1 = __ldg(reinterpret_cast<const uint4*>(gb + (p + rows) * c));
+      accum(ux0, ug0);
+      accum(ux1, ug1);
     }
+    for (; p < p1; p += rows)
+      accum(__ldg(reinterpret_cast<const uint4*>(xb + p * c)), __ldg(reinterpret_cast<const uint4*>(gb + p * c)));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sm[(r * 2) * c + v * 8 + j] = sa[j];
@@ -174,11 +183,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
   long long p1 = p0 + pix_per_block;
   if (p1 > hw) p1 = hw;
   const long long base = (static_cast<long long>(n) * hw) * c + v * 8;
-  for (long long p = p0 + r; p < p1; p += rows) {
-    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + base + p * c));
-    const uint4 ug = __ldg(reinterpret_cast<const uint4*>(g + base + p * c));
-    uint4 ua = make_uint4(0, 0, 0, 0);
-    if (add != nullptr) ua = __ldg(reinterpret_cast<const uint4*>(add + base + p * c));
+  auto compute = [&](const uint4& ux, const uint4& ug, const uint4& ua) {
     const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w}, wa[4] = {ua.x, ua.y, ua.z, ua.w};
     uint32_t o[4];
 #pragma unroll
@@ -196,12 +201,32 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
       const float r1 = rstd[2 * j + 1] * (d1 * ga[2 * j + 1] - k1[2 * j + 1] - xh1 * k2[2 * j + 1]) + fa.y;
       o[j] = T16<T>::from_f2(r0, r1);
     }
-    *reinterpret_cast<uint4*>(dx + base + p * c) = make_uint4(o[0], o[1], o[2], o[3]);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  long long p = p0 + r;
+  for (; p + rows < p1; p += 2LL * rows) {  // two pixels per iteration: up to six 16-byte loads in flight per thread
+    const long long o0 = base + p * c, o1 = base + (p + rows) * c;
+    const uint4 ux0 = __ldg(reinterpret_cast<const uint4*>(x + o0)), ug0 = __ldg(reinterpret_cast<const uint4*>(g + o0));
+    const uint4 ux1 = __ldg(reinterpret_cast<const uint4*>(x + o1)), ug1 = __ldg(reinterpret_cast<const uint4*>(g + o1));
+    uint4 ua0 = zero4, ua1 = zero4;
+    if (add != nullptr) {
+      ua0 = __ldg(reinterpret_cast<const uint4*>(add + o0));
+      ua1 = __ldg(reinterpret_cast<const uint4*>(add + o1));
+    }
+    *reinterpret_cast<uint4*>(dx + o0) = compute(ux0, ug0, ua0);
+    *reinterpret_cast<uint4*>(dx + o1) = compute(ux1, ug1, ua1);
+  }
+  for (; p < p1; p += rows) {
+    const long long o0 = base + p * c;
+    const uint4 ua0 = add != nullptr ? __ldg(reinterpret_cast<const uint4*>(add + o0)) : zero4;
+    *reinterpret_cast<uint4*>(dx + o0) =
+        compute(__ldg(reinterpret_cast<const uint4*>(x + o0)), __ldg(reinterpret_cast<const uint4*>(g + o0)), ua0);
   }
 }
 
 void bwd_grid(long long hw, int c, int rows, int* bpi, int* ppb) {
-  long long per = 16384 / c;
+  long long per = 32768 / c;  // pixels per block
   if (per < rows) per = rows;
   per = (per + rows - 1) / rows * rows;
   if (per > hw) per = (hw + rows - 1) / rows * rows;

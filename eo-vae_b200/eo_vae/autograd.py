@@ -76,6 +76,14 @@ def _wgrad(x: torch.Tensor, g: torch.Tensor, mode: int) -> torch.Tensor:
     return ops.conv2d_wgrad(x, g, 1 if mode == ops.CONV_1X1 else 3)
 
 
+def _stats_of(x: torch.Tensor, groups: int = 32, eps: float = 1e-6) -> torch.Tensor:
+    """GroupNorm statistics of x: the ones the producing conv's epilogue left on the tensor, else one stats pass."""
+    fused = getattr(x, "_gn_stats", None)
+    if fused is not None and fused[1] == groups and fused[2] == float(eps):
+        return fused[0]
+    return ops.gn_stats(x, groups, eps)
+
+
 def _bias(mod):
     return None if mod.bias is None else mod.bias.detach()
 
@@ -84,9 +92,9 @@ class ConvFn(Function):
     """out = conv(x) + bias (+ residual) for the three built convolution modes."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, mod, out_dtype):
+    def forward(ctx, x, weight, bias, residual, mod, out_dtype, gn_next=False):
         out = ops.conv2d(x, mod.packed_weight(x.dtype), _bias(mod), mod.out_channels, mod._mode, residual=residual,
-                         out_dtype=out_dtype)
+                         out_dtype=out_dtype, gn_groups=32 if gn_next else 0)
         ctx.save_for_backward(x, weight)
         ctx.mode = mod._mode
         ctx.has_bias = bias is not None
@@ -104,7 +112,7 @@ class ConvFn(Function):
             dw = dw[:, :weight.shape[1]].contiguous()
         db = ops.bias_grad(g) if ctx.has_bias and need[2] else None
         dres = g if need[3] else None
-        return dx, dw, db, dres, None, None
+        return dx, dw, db, dres, None, None, None
 
 
 class GroupNormFn(Function):
@@ -112,7 +120,7 @@ class GroupNormFn(Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, silu, groups, eps):
-        stats = ops.gn_stats(x, groups, eps)
+        stats = _stats_of(x, groups, eps)
         ctx.save_for_backward(x, stats, gamma, beta)
         ctx.cfg = (silu, groups)
         return ops.gn_apply(x, stats, gamma.detach(), beta.detach(), silu, groups)
@@ -131,20 +139,22 @@ class ResnetBlockFn(Function):
     @staticmethod
     def forward(ctx, x, g1, b1, w1, c1b, g2, b2, w2, c2b, wn, nb, mod):
         dt = x.dtype
-        st1 = ops.gn_stats(x, 32, 1e-6)
+        st1 = _stats_of(x)
         a1 = ops.gn_apply(x, st1, g1.detach(), b1.detach(), True, 32)
         h = ops.conv2d(a1, mod.conv1.packed_weight(dt), _bias(mod.conv1), mod.out_channels, ops.CONV_3X3, gn_groups=32)
         fused = getattr(h, "_gn_stats", None)
         st2 = fused[0] if fused is not None else ops.gn_stats(h, 32, 1e-6)
         a2 = ops.gn_apply(h, st2, g2.detach(), b2.detach(), True, 32)
         if wn is None:
-            out = ops.conv2d(a2, mod.conv2.packed_weight(dt), _bias(mod.conv2), mod.out_channels, ops.CONV_3X3, residual=x)
+            out = ops.conv2d(a2, mod.conv2.packed_weight(dt), _bias(mod.conv2), mod.out_channels, ops.CONV_3X3, residual=x,
+                             gn_groups=32)
         elif mod.in_channels % 64 == 0 and mod.out_channels % 64 == 0:
             w, b = mod._conv2_with_shortcut(dt)
-            out = ops.conv2d(a2, w, b, mod.out_channels, ops.CONV_3X3, x2=x)
+            out = ops.conv2d(a2, w, b, mod.out_channels, ops.CONV_3X3, x2=x, gn_groups=32)
         else:
             sc = ops.conv2d(x, mod.nin_shortcut.packed_weight(dt), _bias(mod.nin_shortcut), mod.out_channels, ops.CONV_1X1)
-            out = ops.conv2d(a2, mod.conv2.packed_weight(dt), _bias(mod.conv2), mod.out_channels, ops.CONV_3X3, residual=sc)
+            out = ops.conv2d(a2, mod.conv2.packed_weight(dt), _bias(mod.conv2), mod.out_channels, ops.CONV_3X3, residual=sc,
+                             gn_groups=32)
         ctx.save_for_backward(x, st1, a1, h, st2, a2, g1, b1, w1, g2, b2, w2, wn)
         return out
 
@@ -181,7 +191,7 @@ class AttnBlockFn(Function):
         n, c, hh, ww = x.shape
         L = hh * ww
         lp = (L + 15) // 16 * 16
-        stn = ops.gn_stats(x, 32, 1e-6)
+        stn = _stats_of(x)
         hn = ops.gn_apply(x, stn, gamma.detach(), beta.detach(), False, 32)
         wqkv, bqkv = mod._qkv_operands(x.dtype)
         qkv = ops.conv2d(hn, wqkv, bqkv, 3 * c, ops.CONV_1X1)
@@ -192,7 +202,7 @@ class AttnBlockFn(Function):
         del scores
         o = ops.gemm_tn_batched(probs, ops.transpose16(v, out_rows=lp), x.dtype)
         o = o.view(n, hh, ww, c).permute(0, 3, 1, 2)
-        out = ops.conv2d(o, mod.proj_out.packed_weight(x.dtype), _bias(mod.proj_out), c, ops.CONV_1X1, residual=x)
+        out = ops.conv2d(o, mod.proj_out.packed_weight(x.dtype), _bias(mod.proj_out), c, ops.CONV_1X1, residual=x, gn_groups=32)
         ctx.save_for_backward(x, stn, hn, qkv, probs, o, gamma, beta, wq, wk, wv, wp)
         return out
 
@@ -254,7 +264,7 @@ class UpsampleFn(Function):
     def forward(ctx, x, weight, bias, mod):
         ctx.save_for_backward(x, weight)
         return ops.conv2d(ops.upsample2x(x), mod.conv.packed_weight(x.dtype), _bias(mod.conv), mod.conv.out_channels,
-                          ops.CONV_3X3)
+                          ops.CONV_3X3, gn_groups=32)
 
     @staticmethod
     def backward(ctx, dy):
@@ -297,7 +307,7 @@ class DynConvInFn(Function):
         packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, mod.embed_dim, False, mod.scaler, mod.scaler, x.dtype, False)
         ctx.save_for_backward(x, wvs)
         ctx.mod = mod
-        return ops.conv2d(x, packed, bias, mod.embed_dim, ops.CONV_3X3, algo_cin=c)
+        return ops.conv2d(x, packed, bias, mod.embed_dim, ops.CONV_3X3, algo_cin=c, gn_groups=32)
 
     @staticmethod
     def backward(ctx, dy):

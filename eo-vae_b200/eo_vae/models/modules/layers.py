@@ -77,7 +77,7 @@ class Conv2dSM100(nn.Conv2d):
         if tape.grad_mode():  # training path: tape entries with hand-written backward kernels (eo_vae/autograd.py)
             if pre_norm is not None:
                 x = pre_norm(x, silu=True)
-            return tape.ConvFn.apply(x, self.weight, self.bias, residual, self, out_dtype)
+            return tape.ConvFn.apply(x, self.weight, self.bias, residual, self, out_dtype, gn_next)
         in_gn = None
         if pre_norm is not None:
             if ops.USE_GN_PROLOGUE and ops.gn_prologue_ok(x, self.out_channels, self._mode, pre_norm.num_groups):

@@ -160,12 +160,18 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
                                                                  const float* __restrict__ beta,
                                                                  const float* __restrict__ gsum, const T* __restrict__ add,
                                                                  T* __restrict__ dx, long long hw, int c, int groups,
-                                                                 int pix_per_block) {
+                                                                 int pix_per_block, float* __restrict__ colpart) {
+  // colpart != NULL: also emit this block's per-channel sums of dx (fixed slot [n][block][c]) - the bias gradient of the
+  // convolution that produced x's forward input, for free (no extra pass over dx)
+  extern __shared__ float sm_cs[];  // [rows][c], only with colpart
   const int vpp = c >> 3;
   const int rows = blockDim.x / vpp;
   const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
   const int n = blockIdx.y;
-  if (r >= rows) return;
+  float cs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+  if (r < rows) {
   const int cpg = c / groups;
   const float inv_m = 1.0f / (static_cast<float>(hw) * cpg);
   float mean[8], rstd[8], ga[8], be[8], k1[8], k2[8];
@@ -199,6 +205,8 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
       }
       const float r0 = rstd[2 * j] * (d0 * ga[2 * j] - k1[2 * j] - xh0 * k2[2 * j]) + fa.x;
       const float r1 = rstd[2 * j + 1] * (d1 * ga[2 * j + 1] - k1[2 * j + 1] - xh1 * k2[2 * j + 1]) + fa.y;
+      cs[2 * j] += r0;
+      cs[2 * j + 1] += r1;
       o[j] = T16<T>::from_f2(r0, r1);
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
@@ -222,6 +230,18 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
     const uint4 ua0 = add != nullptr ? __ldg(reinterpret_cast<const uint4*>(add + o0)) : zero4;
     *reinterpret_cast<uint4*>(dx + o0) =
         compute(__ldg(reinterpret_cast<const uint4*>(x + o0)), __ldg(reinterpret_cast<const uint4*>(g + o0)), ua0);
+  }
+  }  // r < rows
+  if (colpart == nullptr) return;
+  if (r < rows) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm_cs[r * c + v * 8 + j] = cs[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += sm_cs[rr * c + ch];
+    colpart[(static_cast<long long>(n) * gridDim.x + blockIdx.x) * c + ch] = a;
   }
 }
 
@@ -325,20 +345,20 @@ __global__ void __launch_bounds__(kThreads) colsum_partial_kernel(const T* __res
     partial[static_cast<long long>(blockIdx.x) * c + ch] = a;
   }
 }
-// block (32 channels, 8 slices): slice y sums the partial rows b = y, y + 8, ...; fixed-order combine (deterministic)
+// block (32 channels, 32 slices): slice y sums the partial rows b = y, y + 32, ...; fixed-order combine (deterministic)
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ out,
                                        int accumulate) {
-  __shared__ double red[8][32];
+  __shared__ double red[32][32];
   const int ch = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0;
   if (ch < c)
-    for (int b = threadIdx.y; b < blocks; b += 8) a += partial[static_cast<long long>(b) * c + ch];
+    for (int b = threadIdx.y; b < blocks; b += 32) a += partial[static_cast<long long>(b) * c + ch];
   red[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   if (threadIdx.y == 0 && ch < c) {
     double t = 0.0;
 #pragma unroll
-    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    for (int y = 0; y < 32; ++y) t += red[y][threadIdx.x];
     out[ch] = (accumulate ? out[ch] : 0.f) + static_cast<float>(t);
   }
 }
@@ -417,8 +437,8 @@ size_t eovae_gn_backward_workspace_bytes(int n, long long hw, int c, int groups)
 
 int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const float* stats, const float* gamma,
                       const float* beta, int n, long long hw, int c, int groups, int with_silu, const void* grad_add,
-                      void* grad_x, float* dgamma, float* dbeta, int accumulate_params, void* workspace,
-                      size_t workspace_bytes, void* stream_) {
+                      void* grad_x, float* dgamma, float* dbeta, int accumulate_params, float* grad_x_colsum,
+                      void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   EOVAE_CHECK(c % 8 == 0 && c % groups == 0, "gn_backward: C (%d) must be a multiple of 8 and of groups (%d)", c, groups);
   EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "gn_backward: 16-bit tensors only");
@@ -437,9 +457,9 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const floa
   gn_bwd_reduce_kernel<T, S><<<grid, threads, smem, stream>>>(static_cast<const T*>(x), static_cast<const T*>(grad_out), \
                                                              stats, gamma, beta, hw, c, groups, partial, ppb)
 #define EOVAE_GNB_A(T, S)                                                                                            \
-  gn_bwd_apply_kernel<T, S><<<grid, threads, 0, stream>>>(static_cast<const T*>(x), static_cast<const T*>(grad_out),  \
-                                                          stats, gamma, beta, gsum, static_cast<const T*>(grad_add),  \
-                                                          static_cast<T*>(grad_x), hw, c, groups, ppb)
+  gn_bwd_apply_kernel<T, S><<<grid, threads, grad_x_colsum ? sizeof(float) * c * rows : 0, stream>>>(                \
+      static_cast<const T*>(x), static_cast<const T*>(grad_out), stats, gamma, beta, gsum, static_cast<const T*>(grad_add), \
+      static_cast<T*>(grad_x), hw, c, groups, ppb, grad_x_colsum ? partial : nullptr)
   if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_R(__nv_bfloat16, true); else EOVAE_GNB_R(__nv_bfloat16, false); }
   else { if (with_silu) EOVAE_GNB_R(__half, true); else EOVAE_GNB_R(__half, false); }
   EOVAE_LAUNCH_CHECK();
@@ -457,6 +477,10 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const floa
     if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_A(__nv_bfloat16, true); else EOVAE_GNB_A(__nv_bfloat16, false); }
     else { if (with_silu) EOVAE_GNB_A(__half, true); else EOVAE_GNB_A(__half, false); }
     EOVAE_LAUNCH_CHECK();
+    if (grad_x_colsum != nullptr) {  // the reduce partials are dead by now: their buffer carried the column-sum slots
+      colsum_finalize_kernel<<<ceil_div(c, 32), dim3(32, 32), 0, stream>>>(partial, n * bpi, c, grad_x_colsum, 0);
+      EOVAE_LAUNCH_CHECK();
+    }
   }
 #undef EOVAE_GNB_R
 #undef EOVAE_GNB_A
@@ -507,7 +531,7 @@ int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, fl
   else
     colsum_partial_kernel<__half><<<blocks, threads, smem, stream>>>(static_cast<const __half*>(grad_out), pixels, c, partial, ppb);
   EOVAE_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<ceil_div(c, 32), dim3(32, 8), 0, stream>>>(partial, blocks, c, dbias, accumulate);
+  colsum_finalize_kernel<<<ceil_div(c, 32), dim3(32, 32), 0, stream>>>(partial, blocks, c, dbias, accumulate);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -60,7 +60,7 @@ SIGNATURES = {
     "eovae_l1_charbonnier": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _sz, _vp]),
     "eovae_pack_conv_weight_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "eovae_gn_backward_workspace_bytes": (_sz, [_i, _ll, _i, _i]),
-    "eovae_gn_backward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "eovae_gn_backward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "eovae_scatter_stride2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "eovae_pool2x2_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "eovae_conv2d_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),

@@ -455,6 +455,9 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor
 def bias_grad(dy: torch.Tensor) -> torch.Tensor:
     _need_cuda(dy)
     n, c, h, w = dy.shape
+    fused = getattr(dy, "_colsum", None)  # left by eovae_gn_backward when dy is its grad_x output
+    if fused is not None and fused.numel() == c:
+        return fused
     cp = pix_stride(dy)  # a padded pixel pitch is summed as extra columns and dropped
     lib = _C.lib()
     ws_bytes = lib.eovae_bias_grad_workspace_bytes(n * h * w, cp)
@@ -478,9 +481,11 @@ def gn_backward(x: torch.Tensor, grad_out: torch.Tensor, stats, gamma, beta, sil
     gx = nhwc_empty(n, c, h, w, x.dtype, x.device)
     dg = torch.empty((c,), dtype=torch.float32, device=x.device)
     db = torch.empty((c,), dtype=torch.float32, device=x.device)
+    cs = torch.empty((c,), dtype=torch.float32, device=x.device)
     _C.check(lib.eovae_gn_backward(_ptr(x), _ptr(grad_out), DT[x.dtype], _ptr(stats), _ptr(gamma), _ptr(beta), n, h * w, c,
-                                   groups, 1 if silu else 0, _ptr(grad_add), _ptr(gx), _ptr(dg), _ptr(db), 0, _ptr(ws),
+                                   groups, 1 if silu else 0, _ptr(grad_add), _ptr(gx), _ptr(dg), _ptr(db), 0, _ptr(cs), _ptr(ws),
                                    ws_bytes, _stream()), "eovae_gn_backward")
+    gx._colsum = cs  # per-channel sum of gx (bias gradient of the conv that produced x): rides along like _gn_stats
     return gx, dg, db
 
 

@@ -174,12 +174,13 @@ int eovae_msssim(const float* pred, const float* target, int b, int c, int h, in
 int eovae_pack_conv_weight_dgrad(const float* w_oihw, void* out, int cout, int cin, int kh, int kw, int dtype,
                                  void* stream);
 /* GroupNorm(+SiLU) backward (dense NHWC 16-bit x, grad_out): grad_x = dL/dx (+ grad_add if not NULL),
- * dgamma/dbeta fp32 [c] (optionally accumulated); grad_x or the parameter outputs may be NULL                      */
+ * dgamma/dbeta fp32 [c] (optionally accumulated); grad_x or the parameter outputs may be NULL; grad_x_colsum (fp32 [c],
+ * may be NULL) receives the per-channel sum of grad_x = the bias gradient of the conv that produced x, from the same pass */
 size_t eovae_gn_backward_workspace_bytes(int n, long long hw, int c, int groups);
 int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const float* stats, const float* gamma,
                       const float* beta, int n, long long hw, int c, int groups, int with_silu, const void* grad_add,
-                      void* grad_x, float* dgamma, float* dbeta, int accumulate_params, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      void* grad_x, float* dgamma, float* dbeta, int accumulate_params, float* grad_x_colsum,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* dy [n][ho][wo][c] -> z [n][h][w][c] = 0 except z[2i+1][2j+1] = dy[i][j] (adjoint of the Downsample stride-2 gather) */
 int eovae_scatter_stride2(const void* dy, void* z, int n, int ho, int wo, int h, int w, int c, void* stream);
 /* out [n][h][w][c] = sum over the 2x2 blocks of g [n][2h][2w][c] (adjoint of nearest x2 upsampling) */

@@ -94,6 +94,7 @@ class GraphedTrainStep:
             self.loss = self._forward_backward()
         self.grads = [p.grad for p in self.params]
         self.step_index = 0
+        model._static_eps = None  # only the capture reads it; eager steps draw their own noise again
 
     def _zero(self) -> None:
         for p in self.params:

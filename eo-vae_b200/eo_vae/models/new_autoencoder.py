@@ -350,6 +350,8 @@ class EOFluxVAE(LightningModule):
         ``manual_backward`` runs the hand-written backward kernels (conv dgrad / wgrad, GroupNorm, attention,
         hypernetwork, reparameterisation, Charbonnier / L1 and MS-SSIM adjoints); under ``enable_ddp()`` the gradients
         are averaged over the ranks while backward is still running (eo_vae/ddp.py)."""
+        if getattr(self, 'graph_training', False) and not (self.p_prior or self.p_prior_s or self.latent_noise_p):
+            return self._graphed_training_step(batch)
         opts = self.optimizers()
         opt_gen = opts[0] if isinstance(opts, list) else opts
         schs = self.lr_schedulers()
@@ -381,6 +383,27 @@ class EOFluxVAE(LightningModule):
         logs['train/lr'] = opt_gen.param_groups[0]['lr']
         self.log_dict(logs, prog_bar=True, logger=True, on_step=True, on_epoch=False)
         return gen_loss
+
+    def _graphed_training_step(self, batch):
+        """Opt-in (``model.graph_training = True``): the same step with forward + loss + backward replayed as one CUDA
+        graph per (batch shape, band count, active loss terms) signature - e.g. three graphs for a mixed S2L2A / S1RTC /
+        S2RGB collate.  Semantics of the eager step are kept (CPU-drawn posterior noise, clip, Adam, scheduler, logs)."""
+        from ..graphs import GraphedTrainStep
+        images, wvs = batch[self.image_key], batch['wvs']
+        starts = getattr(self.loss_fn, 'starts', {})
+        active = tuple(sorted(k for k, v in starts.items() if self.global_step >= v))
+        key = (tuple(images.shape), int(wvs.numel()), active)
+        cache = self.__dict__.setdefault('_train_graphs', {})
+        if key not in cache:
+            cache[key] = GraphedTrainStep(self, batch)
+        step = cache[key]
+        loss = step(batch)
+        logs = dict(step.logs)
+        opts = self.optimizers()
+        opt_gen = opts[0] if isinstance(opts, list) else opts
+        logs['train/lr'] = opt_gen.param_groups[0]['lr']
+        self.log_dict(logs, prog_bar=True, logger=True, on_step=True, on_epoch=False)
+        return loss
 
     def validation_step(self, batch, batch_idx):
         images, wvs = batch[self.image_key], batch['wvs']

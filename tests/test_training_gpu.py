@@ -274,6 +274,31 @@ def test_graphed_train_step_matches_eager(cuda):
     assert torch.equal(grads[0][1], grads[1][1])
 
 
+def test_graph_training_flag_mixed_modalities(cuda):
+    """model.graph_training = True: training_step keeps one CUDA graph per (shape, band count) signature; a mixed
+    S2L2A / S1RTC sequence reuses them and the loss on a fixed batch goes down."""
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from oracle.weights import WAVELENGTHS, synthetic_patches
+    model, sd, cfg = _tiny(cuda)
+    model.train()
+    model.loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="char").to(cuda)
+    model.base_lr = 2e-4
+    model.clip_grad = 1.0
+    model.graph_training = True
+    batches = {}
+    for mod in ("S2L2A", "S1RTC"):
+        wvs = torch.tensor(WAVELENGTHS[mod], dtype=torch.float32).to(cuda)
+        batches[mod] = {model.image_key: synthetic_patches(2, wvs.numel(), cfg["resolution"], seed=60).to(cuda), "wvs": wvs}
+    torch.manual_seed(0)
+    losses = {"S2L2A": [], "S1RTC": []}
+    for step in range(8):
+        mod = ("S2L2A", "S1RTC")[step % 2]
+        losses[mod].append(float(model.training_step(batches[mod], step)))
+    assert len(model._train_graphs) == 2
+    for mod, ls in losses.items():
+        assert all(l == l for l in ls) and ls[-1] < ls[0], (mod, ls)
+
+
 def test_training_step_reduces_loss(cuda):
     """A few manual-optimisation steps (Adam, clip 1.0) on one batch: finite, parameters move, loss goes down."""
     from eo_vae.models.modules.consistency_loss import EOConsistencyLoss

@@ -422,6 +422,109 @@ __global__ void pixel_loss_bwd_kernel(const float* __restrict__ a, const float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------- train-mode latent glue
+// new_autoencoder.py:466-469,533-543 in TRAIN mode, one block per packed channel k = (c, pi, pj) of the 2x2-unshuffled
+// latent: batch statistics (biased variance, eps_bn) -> running-statistics update (momentum, unbiased variance) ->
+// normalise -> inverse normalisation with the UPDATED running statistics (eps_inv) -> pixel shuffle -> NHWC 16-bit decoder
+// input.  Everything the reference does with ~8 tiny ATen kernels and three tensor round trips.
+template <typename T>
+__global__ void __launch_bounds__(256) latent_bn_train_fwd_kernel(const float* __restrict__ z, int n, int zc, int h, int w,
+                                                                  float* __restrict__ running_mean,
+                                                                  float* __restrict__ running_var, float momentum,
+                                                                  float eps_bn, float eps_inv, T* __restrict__ out,
+                                                                  long long out_pitch, float* __restrict__ save /*[4zc][3]*/) {
+  const int k = blockIdx.x, c = k >> 2, pi = (k >> 1) & 1, pj = k & 1;
+  const int h2 = h >> 1, w2 = w >> 1;
+  const long long per = static_cast<long long>(n) * h2 * w2;
+  __shared__ double red[2][256];
+  double s = 0.0, q = 0.0;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const int j2 = static_cast<int>(i % w2);
+    const int i2 = static_cast<int>((i / w2) % h2);
+    const long long img = i / (static_cast<long long>(w2) * h2);
+    const float v = z[((img * zc + c) * h + 2 * i2 + pi) * w + 2 * j2 + pj];
+    s += v;
+    q += static_cast<double>(v) * v;
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = q;
+  __syncthreads();
+  __shared__ float sh[4];
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int i = 0; i < 256; ++i) { ts += red[0][i]; tq += red[1][i]; }
+    const double mean = ts / per;
+    double var = tq / per - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double unbiased = per > 1 ? var * per / (per - 1) : var;
+    const float rm = (1.f - momentum) * running_mean[k] + momentum * static_cast<float>(mean);
+    const float rv = (1.f - momentum) * running_var[k] + momentum * static_cast<float>(unbiased);
+    running_mean[k] = rm;
+    running_var[k] = rv;
+    const float rstd = rsqrtf(static_cast<float>(var) + eps_bn);
+    const float scale = sqrtf(rv + eps_inv);
+    sh[0] = static_cast<float>(mean); sh[1] = rstd; sh[2] = scale; sh[3] = rm;
+    save[3 * k] = static_cast<float>(mean);
+    save[3 * k + 1] = rstd;
+    save[3 * k + 2] = scale;
+  }
+  __syncthreads();
+  const float mean = sh[0], rstd = sh[1], scale = sh[2], rm = sh[3];
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const int j2 = static_cast<int>(i % w2);
+    const int i2 = static_cast<int>((i / w2) % h2);
+    const long long img = i / (static_cast<long long>(w2) * h2);
+    const int y = 2 * i2 + pi, x = 2 * j2 + pj;
+    const float v = z[((img * zc + c) * h + y) * w + x];
+    out[((img * h + y) * w + x) * out_pitch + c] = T16<T>::from_f((v - mean) * rstd * scale + rm);
+  }
+}
+
+// adjoint: dzn = dout * scale, then the BatchNorm backward dz = rstd * (dzn - mean(dzn) - zn * mean(dzn * zn))
+template <typename T>
+__global__ void __launch_bounds__(256) latent_bn_train_bwd_kernel(const T* __restrict__ dout, long long dout_pitch,
+                                                                  const float* __restrict__ z, int n, int zc, int h, int w,
+                                                                  const float* __restrict__ save, float* __restrict__ dz) {
+  const int k = blockIdx.x, c = k >> 2, pi = (k >> 1) & 1, pj = k & 1;
+  const int h2 = h >> 1, w2 = w >> 1;
+  const long long per = static_cast<long long>(n) * h2 * w2;
+  const float mean = save[3 * k], rstd = save[3 * k + 1], scale = save[3 * k + 2];
+  __shared__ double red[2][256];
+  double a = 0.0, b = 0.0;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const int j2 = static_cast<int>(i % w2);
+    const int i2 = static_cast<int>((i / w2) % h2);
+    const long long img = i / (static_cast<long long>(w2) * h2);
+    const int y = 2 * i2 + pi, x = 2 * j2 + pj;
+    const float g = T16<T>::to_f(dout[((img * h + y) * w + x) * dout_pitch + c]) * scale;
+    const float zn = (z[((img * zc + c) * h + y) * w + x] - mean) * rstd;
+    a += g;
+    b += static_cast<double>(g) * zn;
+  }
+  red[0][threadIdx.x] = a;
+  red[1][threadIdx.x] = b;
+  __syncthreads();
+  __shared__ float sh[2];
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int i = 0; i < 256; ++i) { ta += red[0][i]; tb += red[1][i]; }
+    sh[0] = static_cast<float>(ta / per);
+    sh[1] = static_cast<float>(tb / per);
+  }
+  __syncthreads();
+  const float ma = sh[0], mb = sh[1];
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const int j2 = static_cast<int>(i % w2);
+    const int i2 = static_cast<int>((i / w2) % h2);
+    const long long img = i / (static_cast<long long>(w2) * h2);
+    const int y = 2 * i2 + pi, x = 2 * j2 + pj;
+    const long long zi = ((img * zc + c) * h + y) * w + x;
+    const float g = T16<T>::to_f(dout[((img * h + y) * w + x) * dout_pitch + c]) * scale;
+    const float zn = (z[zi] - mean) * rstd;
+    dz[zi] = rstd * (g - ma - zn * mb);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -572,6 +675,38 @@ int eovae_pixel_loss_backward(const float* a, const float* b, long long count, f
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   pixel_loss_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a, b, count, eps * eps, kind, grad_scale, grad_a);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_latent_bn_train_forward(const float* z, int n, int zc, int h, int w, float* running_mean, float* running_var,
+                                  float momentum, float eps_bn, float eps_inv, void* out, int out_dtype, long long out_pix_stride,
+                                  float* save, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(h % 2 == 0 && w % 2 == 0, "latent_bn_train: latent H, W must be even (2x2 packing)");
+  if (out_dtype == EOVAE_BF16)
+    latent_bn_train_fwd_kernel<__nv_bfloat16><<<4 * zc, 256, 0, stream>>>(z, n, zc, h, w, running_mean, running_var, momentum, eps_bn,
+                                                                          eps_inv, static_cast<__nv_bfloat16*>(out), out_pix_stride, save);
+  else if (out_dtype == EOVAE_F16)
+    latent_bn_train_fwd_kernel<__half><<<4 * zc, 256, 0, stream>>>(z, n, zc, h, w, running_mean, running_var, momentum, eps_bn, eps_inv,
+                                                                   static_cast<__half*>(out), out_pix_stride, save);
+  else
+    EOVAE_CHECK(false, "latent_bn_train: 16-bit output only");
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_latent_bn_train_backward(const void* dout, int dtype, long long dout_pix_stride, const float* z, int n, int zc, int h, int w,
+                                   const float* save, float* dz, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (dtype == EOVAE_BF16)
+    latent_bn_train_bwd_kernel<__nv_bfloat16><<<4 * zc, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dout), dout_pix_stride, z, n,
+                                                                          zc, h, w, save, dz);
+  else if (dtype == EOVAE_F16)
+    latent_bn_train_bwd_kernel<__half><<<4 * zc, 256, 0, stream>>>(static_cast<const __half*>(dout), dout_pix_stride, z, n, zc, h, w,
+                                                                   save, dz);
+  else
+    EOVAE_CHECK(false, "latent_bn_train_backward: 16-bit gradient only");
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -397,3 +397,37 @@ class MsssimFn(Function):
     def backward(ctx, g):
         a, b = ctx.saved_tensors
         return ops.msssim_backward(a, b, ctx.data_range, g), None, None
+
+
+class LatentTrainFn(Function):
+    """TRAIN-mode latent glue in one kernel each way: pixel-unshuffle -> BatchNorm2d (batch statistics, running buffers
+    updated in place) -> inverse normalisation with the updated buffers -> pixel-shuffle -> decoder input activation
+    (new_autoencoder.py:466-469,533-543)."""
+
+    @staticmethod
+    def forward(ctx, z, bn, eps_inv, dtype):
+        z = z.to(torch.float32).contiguous()
+        n, zc, h, w = z.shape
+        out = ops.nhwc_empty(n, zc, h, w, dtype, z.device)
+        save = torch.empty((4 * zc, 3), dtype=torch.float32, device=z.device)
+        momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+        _C = ops._C
+        _C.check(_C.lib().eovae_latent_bn_train_forward(z.data_ptr(), n, zc, h, w, bn.running_mean.data_ptr(),
+                                                        bn.running_var.data_ptr(), momentum, float(bn.eps), float(eps_inv),
+                                                        out.data_ptr(), ops.DT[dtype], ops.pix_stride(out), save.data_ptr(),
+                                                        ops._stream()), "eovae_latent_bn_train_forward")
+        bn.num_batches_tracked += 1
+        ctx.save_for_backward(z, save)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, save = ctx.saved_tensors
+        n, zc, h, w = z.shape
+        g = _grad_act(dout, dout.dtype if dout.dtype != torch.float32 else torch.bfloat16)
+        dz = torch.empty_like(z)
+        _C = ops._C
+        _C.check(_C.lib().eovae_latent_bn_train_backward(g.data_ptr(), ops.DT[g.dtype], ops.pix_stride(g), z.data_ptr(), n, zc, h, w,
+                                                         save.data_ptr(), dz.data_ptr(), ops._stream()),
+                 "eovae_latent_bn_train_backward")
+        return dz, None, None, None

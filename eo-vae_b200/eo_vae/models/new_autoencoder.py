@@ -281,6 +281,11 @@ class EOFluxVAE(LightningModule):
             return tape.act_to_nchw_f32(self.decoder.forward_act(h, wvs)), posterior
         # _static_eps: a device buffer the caller refills every step (eo_vae.graphs.GraphedTrainStep); default = CPU draw
         z = posterior.sample(getattr(self, '_static_eps', None)) if sample_posterior else posterior.mode()
+        if (self.training and scale is None and angle is None and self.latent_noise_p == 0 and self.bn.track_running_stats
+                and self.bn.momentum is not None and z.is_cuda):
+            # train-mode glue fused: unshuffle -> BN(batch stats, buffers updated) -> inverse BN -> shuffle -> activation
+            h = tape.LatentTrainFn.apply(z, self.bn, self.bn_eps, compute_dtype())
+            return tape.act_to_nchw_f32(self.decoder.forward_act(h, wvs)), posterior
         if scale is not None:
             z = self._apply_scale(z, scale)
         if angle is not None:

@@ -226,6 +226,15 @@ size_t eovae_conv2d_wgrad_nhwc_workspace_bytes(int n, int h, int w, int cin, int
 int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int h,
                             int w, int cin, int cout, int ksize, float* dw_oihw, int accumulate, void* workspace,
                             size_t workspace_bytes, void* stream);
+/* TRAIN-mode latent glue (new_autoencoder.py:466-469 with self.training, :533-543): z NCHW fp32 [n][zc][h][w] ->
+ * pixel-unshuffle(2) -> BatchNorm2d batch statistics (biased variance, eps_bn) with the running statistics [4*zc] updated
+ * in place (momentum, unbiased variance) -> inverse normalisation with the UPDATED running statistics (eps_inv) ->
+ * pixel-shuffle -> decoder input, NHWC 16-bit.  save [4*zc][3] = (batch mean, rstd, inverse scale) for the backward. */
+int eovae_latent_bn_train_forward(const float* z, int n, int zc, int h, int w, float* running_mean, float* running_var,
+                                  float momentum, float eps_bn, float eps_inv, void* out, int out_dtype, long long out_pix_stride,
+                                  float* save, void* stream);
+int eovae_latent_bn_train_backward(const void* dout, int dtype, long long dout_pix_stride, const float* z, int n, int zc, int h, int w,
+                                   const float* save, float* dz, void* stream);
 /* dbias[c] (+)= sum over pixels of grad_out [pixels][c] (16-bit) */
 size_t eovae_bias_grad_workspace_bytes(long long pixels, int c);
 int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, float* dbias, int accumulate, void* workspace,

@@ -183,10 +183,16 @@ def test_tiny_model_gradients(cuda):
     zc = cfg["z_channels"]
     hl = cfg["resolution"] // 2 ** (len(cfg["ch_mult"]) - 1)
     eps = torch.randn((2, zc, hl, hl))  # the draw DiagonalGaussianDistribution.sample makes on the CPU generator
-    recon_ref, _ = O.forward(ref_sd, x, wvs, eps, train=True, heads=cfg["hyper_heads"])
+    recon_ref, moments_ref = O.forward(ref_sd, x, wvs, eps, train=True, heads=cfg["hyper_heads"])
     loss_ref = O.charbonnier_loss(recon_ref, x)
     loss_ref.backward()
     assert abs(float(loss) - float(loss_ref)) < 1e-2 * abs(float(loss_ref)) + 1e-3
+    # the fused train-mode latent kernel also updated the BatchNorm running statistics like nn.BatchNorm2d does
+    with torch.no_grad():
+        _, new = O.bn_train(ref_sd, O.pixel_unshuffle2(O.posterior_sample(moments_ref, eps)))
+    assert torch.allclose(model.bn.running_mean.cpu(), new["bn.running_mean"], atol=2e-3)
+    assert torch.allclose(model.bn.running_var.cpu(), new["bn.running_var"], rtol=2e-2, atol=1e-3)
+    assert int(model.bn.num_batches_tracked) == int(sd["bn.num_batches_tracked"]) + 1
 
     got, want, worst = [], [], {}
     for name, p in model.named_parameters():

@@ -28,8 +28,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const T* __restr
   if (p1 > hw) p1 = hw;
   if (r < rows) {
     const T* base = x + (static_cast<long long>(n) * hw) * pix_stride + v * 8;
-    for (long long p = p0 + r; p < p1; p += rows) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * pix_stride));
+    auto add = [&](const uint4& u) {
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -39,7 +38,16 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const T* __restr
         s[2 * j + 1] += f.y;
         q[2 * j + 1] += f.y * f.y;
       }
+    };
+    long long p = p0 + r;
+    for (; p + 3LL * rows < p1; p += 4LL * rows) {  // four 16-byte loads in flight per thread
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + p * pix_stride));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (p + rows) * pix_stride));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (p + 2LL * rows) * pix_stride));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (p + 3LL * rows) * pix_stride));
+      add(u0); add(u1); add(u2); add(u3);
     }
+    for (; p < p1; p += rows) add(__ldg(reinterpret_cast<const uint4*>(base + p * pix_stride)));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s_part[(r * 2) * c + v * 8 + j] = s[j];

@@ -337,7 +337,10 @@ class EOFluxVAE(LightningModule):
     def configure_optimizers(self):
         params = [p for p in self.encoder.parameters() if p.requires_grad] + \
                  [p for p in self.decoder.parameters() if p.requires_grad]
-        optimizers = [torch.optim.Adam(params, lr=self.base_lr)]
+        # same optimiser as the reference (:556); torch's fused implementation (one multi-tensor kernel instead of ~10
+        # foreach passes over the 95.5 M parameters) when everything lives on the GPU
+        fused = bool(params) and all(p.is_cuda and p.dtype == torch.float32 for p in params)
+        optimizers = [torch.optim.Adam(params, lr=self.base_lr, fused=fused)]
         if hasattr(self.loss_fn, 'discriminator'):
             optimizers.append(torch.optim.Adam(self.loss_fn.discriminator.parameters(), lr=self.base_lr))
         schedulers = []

@@ -502,6 +502,54 @@ __global__ void running_stats_merge_kernel(const float* __restrict__ tmp, int c,
   if (ch == 0) count[0] = cnt + batch_count;
 }
 
+// ------------------------------------------------------------------------------------------------- data-side prologue
+// terramesh_datamodule.py:189-197 (clip + z-score), :476-479 (bilinear resize, align_corners = False), :347-369 (D4
+// augmentation: horizontal flip, vertical flip, k x rot90) in ONE gather pass: raw NCHW (fp32 or 16-bit integer DNs) ->
+// normalised, resized, augmented NCHW fp32.  The affine normalisation commutes with the (convex) bilinear weights, so the
+// clip is applied to the four taps and the z-score to the interpolated value.
+template <typename TIn>
+__global__ void preprocess_kernel(const TIn* __restrict__ in, int c, int hi, int wi, int hr, int wr, int ho, int wo,
+                                  const float* __restrict__ mean, const float* __restrict__ std, float std_eps, int do_clip,
+                                  float clip_lo, float clip_hi, int flip_h, int flip_v, int rot_k, float* __restrict__ out,
+                                  long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % wo);
+  long long t = i / wo;
+  const int y = static_cast<int>(t % ho);
+  t /= ho;
+  const int ch = static_cast<int>(t % c);
+  const long long b = t / c;
+  // undo rot90 (torch.rot90 over dims [-2, -1], counter-clockwise): output (y, x) -> position (ry, rx) of the h_r x w_r image
+  int ry, rx;
+  switch (rot_k & 3) {
+    case 1: ry = x; rx = wr - 1 - y; break;
+    case 2: ry = hr - 1 - y; rx = wr - 1 - x; break;
+    case 3: ry = hr - 1 - x; rx = y; break;
+    default: ry = y; rx = x; break;
+  }
+  if (flip_v) ry = hr - 1 - ry;
+  if (flip_h) rx = wr - 1 - rx;
+  const TIn* plane = in + (b * c + ch) * static_cast<long long>(hi) * wi;
+  auto tap = [&](int yy, int xx) {
+    float v = static_cast<float>(plane[static_cast<long long>(yy) * wi + xx]);
+    if (do_clip) v = fminf(fmaxf(v, clip_lo), clip_hi);
+    return v;
+  };
+  float v;
+  if (hr == hi && wr == wi) {
+    v = tap(ry, rx);
+  } else {  // F.interpolate(mode='bilinear', align_corners=False)
+    const float sy = fmaxf((ry + 0.5f) * (static_cast<float>(hi) / hr) - 0.5f, 0.f);
+    const float sx = fmaxf((rx + 0.5f) * (static_cast<float>(wi) / wr) - 0.5f, 0.f);
+    const int y0 = min(static_cast<int>(sy), hi - 1), x0 = min(static_cast<int>(sx), wi - 1);
+    const int y1 = min(y0 + 1, hi - 1), x1 = min(x0 + 1, wi - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    v = (1.f - ly) * ((1.f - lx) * tap(y0, x0) + lx * tap(y0, x1)) + ly * ((1.f - lx) * tap(y1, x0) + lx * tap(y1, x1));
+  }
+  out[i] = (v - mean[ch]) / (std[ch] + std_eps);
+}
+
 }  // namespace
 
 extern "C" {
@@ -719,6 +767,28 @@ int eovae_running_stats_update(const float* x, int n, int c, long long hw, float
   EOVAE_LAUNCH_CHECK();
   running_stats_merge_kernel<<<1, round_up(c, 32), 0, stream>>>(workspace, c, static_cast<float>(static_cast<double>(n) * hw), mean, var,
                                                               std, count, vmin, vmax);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_preprocess(const void* in, int in_dtype, int n, int c, int hi, int wi, int hr, int wr, const float* mean,
+                     const float* std, float std_eps, int do_clip, float clip_lo, float clip_hi, int flip_h, int flip_v, int rot_k,
+                     float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int odd = rot_k & 1;
+  const int ho = odd ? wr : hr, wo = odd ? hr : wr;
+  const long long total = static_cast<long long>(n) * c * ho * wo;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+#define EOVAE_PRE(T)                                                                                                   \
+  preprocess_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(in), c, hi, wi, hr, wr, ho, wo, mean, std, std_eps, \
+                                                 do_clip, clip_lo, clip_hi, flip_h, flip_v, rot_k, out, total)
+  switch (in_dtype) {
+    case 2: EOVAE_PRE(float); break;          /* EOVAE_DT_F32 */
+    case 3: EOVAE_PRE(int16_t); break;        /* EOVAE_DT_I16 */
+    case 4: EOVAE_PRE(uint16_t); break;       /* EOVAE_DT_U16 */
+    default: EOVAE_CHECK(false, "preprocess: input dtype must be fp32, int16 or uint16 (got %d)", in_dtype);
+  }
+#undef EOVAE_PRE
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -160,6 +160,14 @@ int eovae_l1_charbonnier(const float* a, const float* b, long long count, float 
 int eovae_running_stats_update(const float* x, int n, int c, long long hw, float* mean, float* var, float* std, float* count,
                                float* vmin, float* vmax, float* workspace, void* stream);
 
+/* ----  data-side prologue in one gather pass: raw batch [n][c][hi][wi] (EOVAE_DT_F32, or 16-bit integer
+ * digital numbers: 3 = int16, 4 = uint16) -> optional clip -> bilinear resize to hr x wr (align_corners = False) ->
+ * D4 augmentation (horizontal flip, vertical flip, rot_k x 90 degrees counter-clockwise) -> (v - mean[c]) / (std[c] + eps),
+ * NCHW fp32 [n][c][ho][wo] with (ho, wo) = (hr, wr) swapped for odd rot_k.  terramesh_datamodule.py:189-197,347-369,476-482 */
+int eovae_preprocess(const void* in, int in_dtype, int n, int c, int hi, int wi, int hr, int wr, const float* mean,
+                     const float* std, float std_eps, int do_clip, float clip_lo, float clip_hi, int flip_h, int flip_v, int rot_k,
+                     float* out, void* stream);
+
 /* mean multi-scale SSIM over the batch (out[0]) and per sample (per_sample[b], may be NULL); pred, target fp32 NCHW
  * [b][c][h][w], h and w multiples of 16 and >= 176; 5 scales, 11-tap sigma-1.5 Gaussian, reflect padding, relu
  * normalisation, betas (0.0448, 0.2856, 0.3001, 0.2363, 0.1333): torchmetrics' algorithm as called by the reference

@@ -1,0 +1,329 @@
+// Fused flash-style single-head attention for the mid block (layers.py:128-142: softmax(q k^T / sqrt(C)) v, one head,
+// d = C up to 512): scores and probabilities never touch HBM.
+//
+// One CTA = 128 queries of one image x one half of the head dimension (C > 256: two CTAs share a query tile, each owns
+// 256 output columns and recomputes the cheap-in-context score tile; attention is < 1 % of the encoder's FLOPs and this
+// keeps the fp32 O accumulator (128 x 256) + the S tile (128 x 64) inside the 512 TMEM columns).
+//
+//   phase A (statistics):  for every 64-key block  S = Q K^T (tcgen05, fp32 in TMEM) -> row max / row sum, online, in
+//                          registers of the 4 softmax warps (thread = query row);
+//   phase B (output):      S again -> P = exp((S - max) / sqrt(C)) / sum as bf16/fp16 into a 128-byte-swizzled K-major
+//                          shared-memory tile -> O += P V (V read in place from the NHWC qkv tensor as an MN-major operand).
+// Two passes instead of online rescaling: the accumulator never has to be read back and rescaled in TMEM; the price is a
+// second Q K^T (+50 % of this kernel's FLOPs), irrelevant at its share of the step.
+//
+// warp 0: TMA producer (Q once; K chunks through a 4-stage ring in both phases; V per key block in phase B)
+// warp 1: MMA issuer      warps 2-5: softmax / epilogue (TMEM lane quarter = warp & 3)
+#include "../../include/eovae.h"
+#include "igemm_sm100.cuh"
+
+namespace {
+
+using namespace igemm;
+
+constexpr int AT_THREADS = 192;
+constexpr int KSTAGES = 4;
+constexpr int QROWS = 128;  // queries per CTA
+constexpr int KB = 64;      // keys per block
+
+struct AttnParams {
+  CUtensorMap q_map;   // qkv as (3C, L, N), box (64, 128, 1)
+  CUtensorMap kv_map;  // same tensor, box (64, 64, 1)
+  int L, C, N;
+  int dsplit;          // 1 or 2 CTAs per query tile
+  int npv;             // output columns per CTA = C / dsplit (multiple of 64, <= 256)
+  void* out;           // [N][L][out_ld] 16-bit
+  long long out_ld;
+  float scale_log2e;   // log2(e) / sqrt(C)
+  uint32_t idesc_qk;   // M 128, N 64, both operands K-major
+  uint32_t idesc_pv;   // M 128, N npv, A K-major, B MN-major
+  int bf16;
+};
+
+__device__ __forceinline__ uint64_t desc_mn128(uint32_t smem_addr) {  // MN-major SW128: 64-key x 64-channel atoms
+  uint64_t d = static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;   // next 64 channels (N)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;   // next 8 keys (K)
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kchunks = p.C / 64;                       // 64-channel chunks of the head dimension
+  uint8_t* sq = smem;                                 // Q: kchunks x [128 rows x 128 B]
+  uint8_t* sk = sq + kchunks * 16384;                 // K ring: KSTAGES x [64 rows x 128 B]
+  uint8_t* sp = sk + KSTAGES * 8192;                  // P: [128 rows x 128 B]
+  uint8_t* sv = sp + 16384;                           // V: (npv / 64) x [64 keys x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sv + (p.npv / 64) * 8192);
+  uint64_t* k_full = bars;                            // [KSTAGES]
+  uint64_t* k_empty = bars + KSTAGES;                 // [KSTAGES]
+  uint64_t* q_full = bars + 2 * KSTAGES;
+  uint64_t* s_full = q_full + 1;
+  uint64_t* s_free = q_full + 2;
+  uint64_t* p_ready = q_full + 3;
+  uint64_t* pv_done = q_full + 4;
+  uint64_t* v_full = q_full + 5;
+  uint64_t* o_full = q_full + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 7);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dhalf = blockIdx.x % p.dsplit;
+  const int qt = blockIdx.x / p.dsplit;
+  const int img = blockIdx.y;
+  const int q0 = qt * QROWS;
+  const int nblocks = (p.L + KB - 1) / KB;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.q_map);
+    prefetch_tmap(&p.kv_map);
+    for (int i = 0; i < KSTAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);     // one arrive per softmax warp
+    mbar_init(p_ready, 4);
+    mbar_init(pv_done, 1);
+    mbar_init(v_full, 1);
+    mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;        // columns [0, 64)
+  const uint32_t tmem_o = tmem_base + 64;   // columns [64, 64 + npv)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kchunks * 16384);
+      for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(&p.q_map, q_full, sq + kc * 16384, kc * 64, q0, img);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ph = 0; ph < 2; ++ph) {
+        for (int j = 0; j < nblocks; ++j) {
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&k_empty[stage], phase ^ 1);
+            mbar_expect_tx(&k_full[stage], 8192);
+            tma_load_3d(&p.kv_map, &k_full[stage], sk + stage * 8192, p.C + kc * 64, j * KB, img);
+            if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
+          }
+          if (ph == 1) {
+            if (j > 0) mbar_wait(pv_done, (j - 1) & 1);   // the previous block's P V MMAs have consumed the V tile
+            mbar_expect_tx(v_full, (p.npv / 64) * 8192);
+            for (int b = 0; b < p.npv / 64; ++b)
+              tma_load_3d(&p.kv_map, v_full, sv + b * 8192, 2 * p.C + dhalf * p.npv + b * 64, j * KB, img);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(q_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;  // score tiles issued so far (both phases)
+      for (int ph = 0; ph < 2; ++ph) {
+        for (int j = 0; j < nblocks; ++j, ++it) {
+          if (it > 0) mbar_wait(s_free, (it - 1) & 1);     // softmax warps have drained the previous score tile
+          tc_fence_after();
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&k_full[stage], phase);
+            tc_fence_after();
+            const uint64_t da = make_smem_desc<128>(smem_u32(sq + kc * 16384));
+            const uint64_t db = make_smem_desc<128>(smem_u32(sk + stage * 8192));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16(tmem_s, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc_qk, (kc | k) != 0 ? 1u : 0u);
+            tc_commit(&k_empty[stage]);
+            if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(s_full);
+          if (ph == 1) {
+            mbar_wait(p_ready, j & 1);
+            mbar_wait(v_full, j & 1);
+            tc_fence_after();
+            const uint64_t dp = make_smem_desc<128>(smem_u32(sp));
+            const uint32_t svb = smem_u32(sv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // 16 keys per MMA: P advances 32 B inside its 128-B rows, V two 8-key groups
+              tc_mma_f16(tmem_o, dp + static_cast<uint64_t>(k * 2), desc_mn128(svb + k * 2048), p.idesc_pv, (j | k) != 0 ? 1u : 0u);
+            tc_commit(pv_done);
+          }
+        }
+      }
+      tc_commit(o_full);
+    }
+  } else {
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;            // query row inside the tile = TMEM lane
+    const int q = q0 + row;
+    const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    int it = 0;
+    // ---- phase A: row max and row sum of exp((s - max) * scale)
+    for (int j = 0; j < nblocks; ++j, ++it) {
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      float s[KB];
+#pragma unroll
+      for (int c = 0; c < KB; c += 16) tc_ld16(tmem_s + lane_addr + c, reinterpret_cast<uint32_t*>(s + c));
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      const int valid = p.L - j * KB;            // keys of this block inside the sequence
+      float bm = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        if (c >= valid) s[c] = -INFINITY;
+        bm = fmaxf(bm, s[c]);
+      }
+      const float mn = fmaxf(m, bm);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < KB; ++c) sum += ex2f((s[c] - mn) * p.scale_log2e);
+      l = l * ex2f((m - mn) * p.scale_log2e) + sum;
+      m = mn;
+    }
+    const float inv_l = 1.f / l;
+    // ---- phase B: normalised probabilities -> swizzled shared-memory tile (A operand of P V)
+    for (int j = 0; j < nblocks; ++j, ++it) {
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      float s[KB];
+#pragma unroll
+      for (int c = 0; c < KB; c += 16) tc_ld16(tmem_s + lane_addr + c, reinterpret_cast<uint32_t*>(s + c));
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      const int valid = p.L - j * KB;
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);   // the previous P tile has been consumed
+      uint8_t* prow = sp + row * 128;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {              // 8 keys = one 16-byte chunk; chunk index XOR (row & 7) = 128-B swizzle
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int c = c8 * 8 + 2 * h;
+          const float p0 = c < valid ? ex2f((s[c] - m) * p.scale_log2e) * inv_l : 0.f;
+          const float p1 = c + 1 < valid ? ex2f((s[c + 1] - m) * p.scale_log2e) * inv_l : 0.f;
+          w[h] = pack16(p0, p1, p.bf16 ? EOVAE_BF16 : EOVAE_F16);
+        }
+        *reinterpret_cast<uint4*>(prow + ((c8 ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    // ---- epilogue: O (already normalised) -> 16-bit rows of the output
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    uint16_t* orow = static_cast<uint16_t*>(p.out) + (static_cast<long long>(img) * p.L + q) * p.out_ld + dhalf * p.npv;
+#pragma unroll 1
+    for (int c = 0; c < p.npv; c += 16) {
+      uint32_t raw[16];
+      tc_ld16(tmem_o + lane_addr + c, raw);
+      tc_wait_ld();
+      if (q < p.L) {
+        uint32_t w[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h)
+          w[h] = pack16(__uint_as_float(raw[2 * h]), __uint_as_float(raw[2 * h + 1]), p.bf16 ? EOVAE_BF16 : EOVAE_F16);
+        *reinterpret_cast<uint4*>(orow + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn attn_encode_fn() {
+  static EncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  return fn;
+}
+
+int make_qkv_map(CUtensorMap* m, int dtype, const void* base, int channels, long long ld, int L, int n, int box_rows) {
+  EncodeFn fn = attn_encode_fn();
+  EOVAE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(channels), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * L};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, dtype == EOVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                  const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EOVAE_CHECK(r == CUDA_SUCCESS, "attention: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eovae_attention_fused_ok(int l, int c) { return (c % 64 == 0 && c >= 64 && c <= 512 && (c <= 256 || (c / 2) % 64 == 0) && l >= 1) ? 1 : 0; }
+
+int eovae_attention_fused(const void* qkv, long long qkv_ld, int n, int l, int c, void* out, long long out_ld, int dtype,
+                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "attention_fused: 16-bit tensors only");
+  EOVAE_CHECK(eovae_attention_fused_ok(l, c), "attention_fused: unsupported shape (L %d, C %d)", l, c);
+  EOVAE_CHECK(qkv_ld % 8 == 0 && qkv_ld >= 3 * c && out_ld % 8 == 0 && out_ld >= c, "attention_fused: bad pitches");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = l; p.C = c; p.N = n;
+  p.dsplit = c > 256 ? 2 : 1;
+  p.npv = c / p.dsplit;
+  p.out = out;
+  p.out_ld = out_ld;
+  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(c));
+  p.bf16 = dtype == EOVAE_BF16 ? 1 : 0;
+  const uint32_t fmt = dtype == EOVAE_BF16 ? 1u : 0u;
+  p.idesc_qk = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(KB >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  p.idesc_pv = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | (static_cast<uint32_t>(p.npv >> 3) << 17) |
+               (static_cast<uint32_t>(128 >> 4) << 24);
+  if (make_qkv_map(&p.q_map, dtype, qkv, 3 * c, qkv_ld, l, n, QROWS)) return -3;
+  if (make_qkv_map(&p.kv_map, dtype, qkv, 3 * c, qkv_ld, l, n, KB)) return -3;
+  const int smem = (c / 64) * 16384 + KSTAGES * 8192 + 16384 + (p.npv / 64) * 8192 + 256 + 1024;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    EOVAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  dim3 grid(ceil_div(l, QROWS) * p.dsplit, n);
+  attn_fwd_kernel<<<grid, AT_THREADS, smem, stream>>>(p);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

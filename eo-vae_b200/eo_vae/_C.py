@@ -50,6 +50,8 @@ SIGNATURES = {
     "eovae_latent_bn_train_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _f, _f, _vp, _i, _ll, _vp, _vp]),
     "eovae_latent_bn_train_backward": (_i, [_vp, _i, _ll, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eovae_preprocess": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _f, _f, _i, _i, _i, _vp, _vp]),
+    "eovae_attention_fused_ok": (_i, [_i, _i]),
+    "eovae_attention_fused": (_i, [_vp, _ll, _i, _i, _i, _vp, _ll, _i, _vp]),
     "eovae_softmax_backward": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _ll, _i, _i, _f, _vp]),
     "eovae_reparam_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "eovae_pixel_loss_backward": (_i, [_vp, _vp, _ll, _f, _i, _vp, _vp, _vp]),

@@ -215,6 +215,10 @@ class AttnBlock(nn.Module):
         wqkv, bqkv = self._qkv_operands(x.dtype)
         qkv = ops.conv2d(h, wqkv, bqkv, 3 * c, ops.CONV_1X1)  # NHWC [n, L, 3c]
         flat = qkv.permute(0, 2, 3, 1).reshape(n, L, 3 * c)     # view: pixel-major rows, pitch 3c
+        if ops.attention_fused_ok(L, c):
+            # flash-style: scores / probabilities live in TMEM and shared memory only
+            o = ops.attention_fused(flat, c).view(n, hh, ww, c).permute(0, 3, 1, 2)
+            return self.proj_out(o, residual=x, gn_next=True)
         q, k, v = flat[:, :, :c], flat[:, :, c:2 * c], flat[:, :, 2 * c:]
         lp = (L + 15) // 16 * 16  # key extent padded to the MMA K step (zero probabilities / zero values)
         scores = ops.gemm_tn_batched(q, k, torch.float32, scale=1.0 / math.sqrt(c))  # [n, L, L] fp32

@@ -180,6 +180,27 @@ def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 
     return c
 
 
+USE_FUSED_ATTENTION = True  # False: q k^T GEMM -> softmax kernel -> p v GEMM (scores materialised in HBM)
+
+
+def attention_fused_ok(l: int, c: int) -> bool:
+    return USE_FUSED_ATTENTION and bool(_C.lib().eovae_attention_fused_ok(l, c))
+
+
+def attention_fused(qkv: torch.Tensor, c: int) -> torch.Tensor:
+    """qkv: [N, L, 3c] 16-bit rows (pitch may exceed 3c) -> softmax(q k^T / sqrt(c)) v as [N, L, c]; one fused kernel."""
+    _need_cuda(qkv)
+    n, l, _ = qkv.shape
+    if qkv.stride(2) != 1 or qkv.stride(0) != l * qkv.stride(1):
+        raise RuntimeError("eo_vae.attention_fused: bad qkv layout")
+    out = torch.empty((n, l, c), dtype=qkv.dtype, device=qkv.device)
+    flops = 4.0 * n * l * l * c
+    rc = _timed("attn_fused", flops, lambda: _C.lib().eovae_attention_fused(_ptr(qkv), qkv.stride(1), n, l, c, _ptr(out), c,
+                                                                            DT[qkv.dtype], _stream()))
+    _C.check(rc, "eovae_attention_fused")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ group norm
 def gn_stats(x: torch.Tensor, groups: int = 32, eps: float = 1e-6) -> torch.Tensor:
     _need_cuda(x)

@@ -85,6 +85,13 @@ int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride
                           long long b_batch_stride, void* c, int c_dtype, long long ldc, int batch, int m, int n, int k,
                           int ab_dtype, float scale, void* stream);
 
+/* ---- fused flash-style attention of AttnBlock (layers.py:134-141): out[n][q][:] = softmax_k(q . k / sqrt(c)) v for
+ *      qkv [n][l][qkv_ld >= 3c] 16-bit (q | k | v channel slices of one tensor), out [n][l][out_ld >= c] 16-bit.  Scores
+ *      and probabilities stay in TMEM / shared memory.  eovae_attention_fused_ok(l, c): c % 64 == 0, c <= 512.        */
+int eovae_attention_fused_ok(int l, int c);
+int eovae_attention_fused(const void* qkv, long long qkv_ld, int n, int l, int c, void* out, long long out_ld, int dtype,
+                          void* stream);
+
 /* ---- GroupNorm(32, eps) statistics + normalise/affine(/SiLU): replaces ATen group_norm + x*sigmoid(x)
  *      (layers.py:61,78,120; layers.py:21-22; model.py:159,193-194,295,349-350)
  *      stats: float [n][groups][2] = (mean, rstd);  workspace: eovae_gn_stats_workspace_bytes(...) bytes.

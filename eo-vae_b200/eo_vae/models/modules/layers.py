@@ -215,7 +215,7 @@ class AttnBlock(nn.Module):
         wqkv, bqkv = self._qkv_operands(x.dtype)
         qkv = ops.conv2d(h, wqkv, bqkv, 3 * c, ops.CONV_1X1)  # NHWC [n, L, 3c]
         flat = qkv.permute(0, 2, 3, 1).reshape(n, L, 3 * c)     # view: pixel-major rows, pitch 3c
-        if ops.attention_fused_ok(L, c):
+        if ops.attention_fused_ok(L, c, n):
             # flash-style: scores / probabilities live in TMEM and shared memory only
             o = ops.attention_fused(flat, c).view(n, hh, ww, c).permute(0, 3, 1, 2)
             return self.proj_out(o, residual=x, gn_next=True)

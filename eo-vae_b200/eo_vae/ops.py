@@ -180,11 +180,18 @@ def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 
     return c
 
 
-USE_FUSED_ATTENTION = True  # False: q k^T GEMM -> softmax kernel -> p v GEMM (scores materialised in HBM)
+# Fused flash-style attention (eovae_attention_fused) is parity-green but, at the encoder's shapes, slower than the
+# q k^T GEMM -> softmax -> p v GEMM path on the tuned implicit-GEMM kernel (0.74 vs 0.44 ms at batch 64, L 1024, C 512:
+# serialised QK / softmax / PV, 64-key score tiles, statistics pass and head-dimension split recompute QK - see DESIGN.md
+# 3.4), so it is used when asked for (True) or when the score tensor would not be reasonable to materialise.
+USE_FUSED_ATTENTION = False
+FUSED_ATTENTION_SCORE_BYTES = 8 << 30   # auto-switch: N * L^2 * 6 bytes of scores + probabilities above this
 
 
-def attention_fused_ok(l: int, c: int) -> bool:
-    return USE_FUSED_ATTENTION and bool(_C.lib().eovae_attention_fused_ok(l, c))
+def attention_fused_ok(l: int, c: int, n: int = 1) -> bool:
+    if not _C.lib().eovae_attention_fused_ok(l, c):
+        return False
+    return USE_FUSED_ATTENTION or 6 * n * l * l > FUSED_ATTENTION_SCORE_BYTES
 
 
 def attention_fused(qkv: torch.Tensor, c: int) -> torch.Tensor:

@@ -16,7 +16,7 @@ def test_attention_fused_matches_reference(cuda, n, l, c, dtype):
     from eo_vae import ops
     g = torch.Generator().manual_seed(l + c)
     qkv = (torch.randn((n, l, 3 * c), generator=g) * 1.5).to(cuda).to(dtype)
-    assert ops.attention_fused_ok(l, c)
+    assert ops._C.lib().eovae_attention_fused_ok(l, c)
     out = ops.attention_fused(qkv, c)
     q, k, v = (t.float() for t in qkv.split(c, dim=2))
     ref = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(c), dim=-1) @ v
@@ -35,7 +35,12 @@ def test_attn_block_fused_equals_unfused(cuda, monkeypatch):
     blk = AttnBlock(128).to(cuda)
     x = torch.randn((2, 128, 16, 16), device=cuda).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
     with torch.no_grad():
+        monkeypatch.setattr(ops, "USE_FUSED_ATTENTION", True)
+        before = ops.launch_count()
         fused = blk(x)
+        fused_launches = ops.launch_count() - before
         monkeypatch.setattr(ops, "USE_FUSED_ATTENTION", False)
+        before = ops.launch_count()
         unfused = blk(x)
+        assert ops.launch_count() - before > fused_launches   # the fused path really replaced GEMM + softmax + GEMM
     assert float((fused.float() - unfused.float()).norm() / unfused.float().norm()) < 5e-3

@@ -5,14 +5,13 @@
 // 256 output columns and recomputes the cheap-in-context score tile; attention is < 1 % of the encoder's FLOPs and this
 // keeps the fp32 O accumulator (128 x 256) + the S tile (128 x 64) inside the 512 TMEM columns).
 //
-//   phase A (statistics):  for every 64-key block  S = Q K^T (tcgen05, fp32 in TMEM) -> row max / row sum, online, in
-//                          registers of the 4 softmax warps (thread = query row);
-//   phase B (output):      S again -> P = exp((S - max) / sqrt(C)) / sum as bf16/fp16 into a 128-byte-swizzled K-major
-//                          shared-memory tile -> O += P V (V read in place from the NHWC qkv tensor as an MN-major operand).
-// Two passes instead of online rescaling: the accumulator never has to be read back and rescaled in TMEM; the price is a
-// second Q K^T (+50 % of this kernel's FLOPs), irrelevant at its share of the step.
+//   for every 64-key block:  S = Q K^T (tcgen05, fp32 in TMEM, two S buffers so the next block's Q K^T runs under this
+//   block's softmax) -> online softmax by the 4 softmax warps (thread = query row): running max m and sum l in registers,
+//   P = exp((S - m) / sqrt(C)) as bf16/fp16 into a 128-byte-swizzled K-major shared-memory tile -> O += P V (V read in
+//   place from the NHWC qkv tensor as an MN-major operand).  When a row's maximum moves, its O row in TMEM is rescaled
+//   (tcgen05.ld -> multiply -> tcgen05.st; skipped warp-wide when no row of the warp changed).  O / l in the epilogue.
 //
-// warp 0: TMA producer (Q once; K chunks through a 4-stage ring in both phases; V per key block in phase B)
+// warp 0: TMA producer (Q once; K chunks through a 4-stage ring; V per key block)
 // warp 1: MMA issuer      warps 2-5: softmax / epilogue (TMEM lane quarter = warp & 3)
 #include "../../include/eovae.h"
 #include "igemm_sm100.cuh"
@@ -49,6 +48,15 @@ __device__ __forceinline__ uint64_t desc_mn128(uint32_t smem_addr) {  // MN-majo
   return d;
 }
 
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -67,13 +75,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
   uint64_t* k_full = bars;                            // [KSTAGES]
   uint64_t* k_empty = bars + KSTAGES;                 // [KSTAGES]
   uint64_t* q_full = bars + 2 * KSTAGES;
-  uint64_t* s_full = q_full + 1;
-  uint64_t* s_free = q_full + 2;
-  uint64_t* p_ready = q_full + 3;
-  uint64_t* pv_done = q_full + 4;
-  uint64_t* v_full = q_full + 5;
-  uint64_t* o_full = q_full + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 7);
+  uint64_t* s_full = q_full + 1;    // [2]
+  uint64_t* s_free = q_full + 3;    // [2]
+  uint64_t* p_ready = q_full + 5;
+  uint64_t* pv_done = q_full + 6;
+  uint64_t* v_full = q_full + 7;
+  uint64_t* o_full = q_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dhalf = blockIdx.x % p.dsplit;
@@ -90,8 +98,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
       mbar_init(&k_empty[i], 1);
     }
     mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 4);     // one arrive per softmax warp
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);   // one arrive per softmax warp
+    }
     mbar_init(p_ready, 4);
     mbar_init(pv_done, 1);
     mbar_init(v_full, 1);
@@ -106,8 +116,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;        // columns [0, 64)
-  const uint32_t tmem_o = tmem_base + 64;   // columns [64, 64 + npv)
+  const uint32_t tmem_s = tmem_base;        // two score tiles: columns [0, 64) and [64, 128)
+  const uint32_t tmem_o = tmem_base + 128;  // columns [128, 128 + npv)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -115,21 +125,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
       for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(&p.q_map, q_full, sq + kc * 16384, kc * 64, q0, img);
       int stage = 0;
       uint32_t phase = 0;
-      for (int ph = 0; ph < 2; ++ph) {
-        for (int j = 0; j < nblocks; ++j) {
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&k_empty[stage], phase ^ 1);
-            mbar_expect_tx(&k_full[stage], 8192);
-            tma_load_3d(&p.kv_map, &k_full[stage], sk + stage * 8192, p.C + kc * 64, j * KB, img);
-            if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
-          }
-          if (ph == 1) {
-            if (j > 0) mbar_wait(pv_done, (j - 1) & 1);   // the previous block's P V MMAs have consumed the V tile
-            mbar_expect_tx(v_full, (p.npv / 64) * 8192);
-            for (int b = 0; b < p.npv / 64; ++b)
-              tma_load_3d(&p.kv_map, v_full, sv + b * 8192, 2 * p.C + dhalf * p.npv + b * 64, j * KB, img);
-          }
+      for (int j = 0; j < nblocks; ++j) {
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&k_empty[stage], phase ^ 1);
+          mbar_expect_tx(&k_full[stage], 8192);
+          tma_load_3d(&p.kv_map, &k_full[stage], sk + stage * 8192, p.C + kc * 64, j * KB, img);
+          if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
         }
+        if (j > 0) mbar_wait(pv_done, (j - 1) & 1);   // the previous block's P V MMAs have consumed the V tile
+        mbar_expect_tx(v_full, (p.npv / 64) * 8192);
+        for (int b = 0; b < p.npv / 64; ++b)
+          tma_load_3d(&p.kv_map, v_full, sv + b * 8192, 2 * p.C + dhalf * p.npv + b * 64, j * KB, img);
       }
     }
   } else if (warp == 1) {
@@ -137,35 +143,36 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
       mbar_wait(q_full, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;  // score tiles issued so far (both phases)
-      for (int ph = 0; ph < 2; ++ph) {
-        for (int j = 0; j < nblocks; ++j, ++it) {
-          if (it > 0) mbar_wait(s_free, (it - 1) & 1);     // softmax warps have drained the previous score tile
+      auto issue_qk = [&](int t) {   // score tile t into S buffer t & 1
+        const int b = t & 1;
+        if (t >= 2) mbar_wait(&s_free[b], ((t >> 1) - 1) & 1);   // softmax warps have drained the buffer's previous tile
+        tc_fence_after();
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&k_full[stage], phase);
           tc_fence_after();
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&k_full[stage], phase);
-            tc_fence_after();
-            const uint64_t da = make_smem_desc<128>(smem_u32(sq + kc * 16384));
-            const uint64_t db = make_smem_desc<128>(smem_u32(sk + stage * 8192));
+          const uint64_t da = make_smem_desc<128>(smem_u32(sq + kc * 16384));
+          const uint64_t db = make_smem_desc<128>(smem_u32(sk + stage * 8192));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_f16(tmem_s, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc_qk, (kc | k) != 0 ? 1u : 0u);
-            tc_commit(&k_empty[stage]);
-            if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
-          }
-          tc_commit(s_full);
-          if (ph == 1) {
-            mbar_wait(p_ready, j & 1);
-            mbar_wait(v_full, j & 1);
-            tc_fence_after();
-            const uint64_t dp = make_smem_desc<128>(smem_u32(sp));
-            const uint32_t svb = smem_u32(sv);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)   // 16 keys per MMA: P advances 32 B inside its 128-B rows, V two 8-key groups
-              tc_mma_f16(tmem_o, dp + static_cast<uint64_t>(k * 2), desc_mn128(svb + k * 2048), p.idesc_pv, (j | k) != 0 ? 1u : 0u);
-            tc_commit(pv_done);
-          }
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(tmem_s + b * KB, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), p.idesc_qk,
+                       (kc | k) != 0 ? 1u : 0u);
+          tc_commit(&k_empty[stage]);
+          if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
         }
+        tc_commit(&s_full[b]);
+      };
+      issue_qk(0);
+      for (int j = 0; j < nblocks; ++j) {
+        if (j + 1 < nblocks) issue_qk(j + 1);          // runs on the tensor pipe while the softmax warps work on tile j
+        mbar_wait(p_ready, j & 1);
+        mbar_wait(v_full, j & 1);
+        tc_fence_after();
+        const uint64_t dp = make_smem_desc<128>(smem_u32(sp));
+        const uint32_t svb = smem_u32(sv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // 16 keys per MMA: P advances 32 B inside its 128-B rows, V two 8-key groups
+          tc_mma_f16(tmem_o, dp + static_cast<uint64_t>(k * 2), desc_mn128(svb + k * 2048), p.idesc_pv, (j | k) != 0 ? 1u : 0u);
+        tc_commit(pv_done);
       }
       tc_commit(o_full);
     }
@@ -175,19 +182,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     const int q = q0 + row;
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
     float m = -INFINITY, l = 0.f;
-    int it = 0;
-    // ---- phase A: row max and row sum of exp((s - max) * scale)
-    for (int j = 0; j < nblocks; ++j, ++it) {
-      mbar_wait(s_full, it & 1);
+    for (int j = 0; j < nblocks; ++j) {
+      const int b = j & 1;
+      mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
       float s[KB];
 #pragma unroll
-      for (int c = 0; c < KB; c += 16) tc_ld16(tmem_s + lane_addr + c, reinterpret_cast<uint32_t*>(s + c));
+      for (int c = 0; c < KB; c += 16) tc_ld16(tmem_s + b * KB + lane_addr + c, reinterpret_cast<uint32_t*>(s + c));
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);
-      const int valid = p.L - j * KB;            // keys of this block inside the sequence
+      if (lane == 0) mbar_arrive(&s_free[b]);
+      const int valid = p.L - j * KB;             // keys of this block inside the sequence
       float bm = -INFINITY;
 #pragma unroll
       for (int c = 0; c < KB; ++c) {
@@ -195,44 +201,46 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
         bm = fmaxf(bm, s[c]);
       }
       const float mn = fmaxf(m, bm);
+      const float alpha = ex2f((m - mn) * p.scale_log2e);   // 0 on the first block (m = -inf), 1 when the maximum stays
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < KB; ++c) sum += ex2f((s[c] - mn) * p.scale_log2e);
-      l = l * ex2f((m - mn) * p.scale_log2e) + sum;
+      for (int c = 0; c < KB; ++c) {
+        s[c] = ex2f((s[c] - mn) * p.scale_log2e);
+        sum += s[c];
+      }
+      l = l * alpha + sum;
       m = mn;
-    }
-    const float inv_l = 1.f / l;
-    // ---- phase B: normalised probabilities -> swizzled shared-memory tile (A operand of P V)
-    for (int j = 0; j < nblocks; ++j, ++it) {
-      mbar_wait(s_full, it & 1);
-      tc_fence_after();
-      float s[KB];
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);           // O holds blocks < j, the P tile and the V tile are free again
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {   // some row of this warp moved its maximum: rescale the warp's O rows
+#pragma unroll 1
+          for (int c = 0; c < p.npv; c += 16) {
+            uint32_t raw[16];
+            tc_ld16(tmem_o + lane_addr + c, raw);
+            tc_wait_ld();
 #pragma unroll
-      for (int c = 0; c < KB; c += 16) tc_ld16(tmem_s + lane_addr + c, reinterpret_cast<uint32_t*>(s + c));
-      tc_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);
-      const int valid = p.L - j * KB;
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);   // the previous P tile has been consumed
+            for (int h = 0; h < 16; ++h) raw[h] = __float_as_uint(__uint_as_float(raw[h]) * alpha);
+            tc_st16(tmem_o + lane_addr + c, raw);
+          }
+          tc_wait_st();
+        }
+      }
       uint8_t* prow = sp + row * 128;
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {              // 8 keys = one 16-byte chunk; chunk index XOR (row & 7) = 128-B swizzle
         uint32_t w[4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int c = c8 * 8 + 2 * h;
-          const float p0 = c < valid ? ex2f((s[c] - m) * p.scale_log2e) * inv_l : 0.f;
-          const float p1 = c + 1 < valid ? ex2f((s[c + 1] - m) * p.scale_log2e) * inv_l : 0.f;
-          w[h] = pack16(p0, p1, p.bf16 ? EOVAE_BF16 : EOVAE_F16);
-        }
+        for (int h = 0; h < 4; ++h) w[h] = pack16(s[c8 * 8 + 2 * h], s[c8 * 8 + 2 * h + 1], p.bf16 ? EOVAE_BF16 : EOVAE_F16);
         *reinterpret_cast<uint4*>(prow + ((c8 ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // ---- epilogue: O (already normalised) -> 16-bit rows of the output
+    const float inv_l = 1.f / l;
+    // ---- epilogue: O / l -> 16-bit rows of the output
     mbar_wait(o_full, 0);
     tc_fence_after();
     uint16_t* orow = static_cast<uint16_t*>(p.out) + (static_cast<long long>(img) * p.L + q) * p.out_ld + dhalf * p.npv;
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
         uint32_t w[8];
 #pragma unroll
         for (int h = 0; h < 8; ++h)
-          w[h] = pack16(__uint_as_float(raw[2 * h]), __uint_as_float(raw[2 * h + 1]), p.bf16 ? EOVAE_BF16 : EOVAE_F16);
+          w[h] = pack16(__uint_as_float(raw[2 * h]) * inv_l, __uint_as_float(raw[2 * h + 1]) * inv_l, p.bf16 ? EOVAE_BF16 : EOVAE_F16);
         *reinterpret_cast<uint4*>(orow + c) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
       }

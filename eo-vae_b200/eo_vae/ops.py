@@ -180,18 +180,19 @@ def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 
     return c
 
 
-# Fused flash-style attention (eovae_attention_fused) is parity-green but, at the encoder's shapes, slower than the
-# q k^T GEMM -> softmax -> p v GEMM path on the tuned implicit-GEMM kernel (0.74 vs 0.44 ms at batch 64, L 1024, C 512:
-# serialised QK / softmax / PV, 64-key score tiles, statistics pass and head-dimension split recompute QK - see DESIGN.md
-# 3.4), so it is used when asked for (True) or when the score tensor would not be reasonable to materialise.
-USE_FUSED_ATTENTION = False
-FUSED_ATTENTION_SCORE_BYTES = 8 << 30   # auto-switch: N * L^2 * 6 bytes of scores + probabilities above this
+# Fused flash-style attention (eovae_attention_fused).  Measured against the q k^T GEMM -> softmax -> p v
+# GEMM path (tools/attn_bench.py, C 512): 0.124 vs 0.132 ms at 16 x 1024, 0.466 vs 0.437 ms at 64 x 1024, 3.30 vs 1.92 ms at
+# 32 x 4096 - on par at the 256-pixel shapes (and 384 MiB of scores never written), slower for very long sequences, where it
+# is used only when the score tensor would be unreasonable to materialise.
+USE_FUSED_ATTENTION = True
+FUSED_ATTENTION_MAX_L = 2048            # above this the GEMM path is faster ...
+FUSED_ATTENTION_SCORE_BYTES = 8 << 30   # ... unless N * L^2 * 6 bytes of scores + probabilities exceed this
 
 
 def attention_fused_ok(l: int, c: int, n: int = 1) -> bool:
-    if not _C.lib().eovae_attention_fused_ok(l, c):
+    if not USE_FUSED_ATTENTION or not _C.lib().eovae_attention_fused_ok(l, c):
         return False
-    return USE_FUSED_ATTENTION or 6 * n * l * l > FUSED_ATTENTION_SCORE_BYTES
+    return l <= FUSED_ATTENTION_MAX_L or 6 * n * l * l > FUSED_ATTENTION_SCORE_BYTES
 
 
 def attention_fused(qkv: torch.Tensor, c: int) -> torch.Tensor:

@@ -35,6 +35,7 @@ def test_attn_block_fused_equals_unfused(cuda, monkeypatch):
     blk = AttnBlock(128).to(cuda)
     x = torch.randn((2, 128, 16, 16), device=cuda).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
     with torch.no_grad():
+        blk(x)  # builds the weight-operand caches
         monkeypatch.setattr(ops, "USE_FUSED_ATTENTION", True)
         before = ops.launch_count()
         fused = blk(x)

@@ -366,7 +366,8 @@ __global__ void layernorm_bwd_param_kernel(const float* __restrict__ x, const fl
 }
 
 // attention backward, pass 1: one warp per (head, query): recompute the probability row, dP = dO V^T,
-// dS = P o (dP - sum(P o dP)) * scale; writes P and dS rows ([heads][s][s]) and dQ.
+// dS = P o (dP - sum(P o dP)) * scale; writes P and dS rows ([heads][s][s]) and dQ.  (dK = dS^T Q and dV = P^T dO are two
+// head-batched GEMMs on these buffers.)
 __global__ void __launch_bounds__(128) mha_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
                                                         float* __restrict__ pbuf, float* __restrict__ dsbuf,
                                                         float* __restrict__ dqkv, int s, int d, int heads) {
@@ -432,27 +433,6 @@ __global__ void __launch_bounds__(128) mha_bwd_q_kernel(const float* __restrict_
     dqkv[static_cast<long long>(qi) * 3 * d + h * hd + i] = acc;
   }
 }
-// pass 2: one warp per (head, key): dK_j = sum_i dS_ij Q_i, dV_j = sum_i P_ij dO_i
-__global__ void __launch_bounds__(128) mha_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
-                                                         const float* __restrict__ pbuf, const float* __restrict__ dsbuf,
-                                                         float* __restrict__ dqkv, int s, int d, int heads) {
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * 4 + wid;
-  const int hd = d / heads;
-  if (item >= s * heads) return;
-  const int h = item / s, kj = item % s;
-  for (int i = lane; i < hd; i += 32) {
-    float dk = 0.f, dv = 0.f;
-    for (int q = 0; q < s; ++q) {
-      const long long pi = (static_cast<long long>(h) * s + q) * s + kj;
-      dk = fmaf(dsbuf[pi], qkv[static_cast<long long>(q) * 3 * d + h * hd + i], dk);
-      dv = fmaf(pbuf[pi], dout[static_cast<long long>(q) * d + h * hd + i], dv);
-    }
-    dqkv[static_cast<long long>(kj) * 3 * d + d + h * hd + i] = dk;
-    dqkv[static_cast<long long>(kj) * 3 * d + 2 * d + h * hd + i] = dv;
-  }
-}
-
 // d_wk[band][tap*E + e] = scale * dW[o][ci][tap], (o, ci) = decoder ? (band, e) : (e, band); dW rows have cin_ld inputs
 __global__ void dyn_weight_grad_kernel(const float* __restrict__ dw, int cin_ld, int c, int embed, int decoder, float scale,
                                        float* __restrict__ dwk) {

@@ -534,42 +534,48 @@ size_t eovae_hypernet_backward_workspace_bytes(int c, int d, int ff, int embed, 
   return floats * sizeof(float);
 }
 
-int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads,
-                            int ff, int embed, int decoder, const float* dw_oihw, int dw_cin_ld, float w_scale,
-                            const float* dbias, float bias_scale, float* const* grads, void* workspace,
-                            size_t workspace_bytes, void* stream_) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  EOVAE_CHECK(c >= 1 && c <= 62, "hypernet: band count %d out of range [1, 62]", c);
-  EOVAE_CHECK(d % heads == 0 && d / heads <= 128 && d % 2 == 0 && heads <= 8, "hypernet: bad d_model/heads (%d/%d)", d, heads);
-  EOVAE_CHECK(workspace_bytes >= eovae_hypernet_backward_workspace_bytes(c, d, ff, embed, num_layers),
-              "hypernet backward: workspace too small");
+}  // extern "C"
+
+namespace {
+
+struct TapeLayer { float *qkv, *att, *tmp1, *x1, *z, *ffh, *tmp2, *xout; };
+struct Tape {
+  float *emb, *t1, *waves, *headin, *headin2, *x0;
+  TapeLayer L[16];
+  float *dx, *da, *db_, *dc, *dqkv, *dffh, *dz, *pbuf, *dsbuf, *rowstat, *dwk, *part;
+};
+
+// one layout for the taped forward and the backward (eovae_hypernet_backward_workspace_bytes covers it)
+void carve_tape(Tape& t, void* workspace, int c, int d, int ff, int embed, int num_layers) {
   const int s = 128 + c + 1;
-  EOVAE_CHECK(s <= MHA_MAX_S, "hypernet: sequence too long");
   const long long sd = static_cast<long long>(s) * d, sf = static_cast<long long>(s) * ff, cd = static_cast<long long>(c) * d;
   float* ws = static_cast<float*>(workspace);
   auto take = [&](long long n) { float* p = ws; ws += n; return p; };
-  float* emb = take(cd); float* t1 = take(cd); float* waves = take(cd); float* headin = take(cd); float* headin2 = take(cd);
-  float* x0 = take(sd);
-  struct Layer { float *qkv, *att, *tmp1, *x1, *z, *ffh, *tmp2, *xout; };
-  Layer L[16];
-  EOVAE_CHECK(num_layers <= 16, "hypernet backward: too many layers");
+  t.emb = take(cd); t.t1 = take(cd); t.waves = take(cd); t.headin = take(cd); t.headin2 = take(cd);
+  t.x0 = take(sd);
   for (int l = 0; l < num_layers; ++l) {
-    L[l].qkv = take(3 * sd); L[l].att = take(sd); L[l].tmp1 = take(sd); L[l].x1 = take(sd); L[l].z = take(sf);
-    L[l].ffh = take(sf); L[l].tmp2 = take(sd); L[l].xout = take(sd);
+    t.L[l].qkv = take(3 * sd); t.L[l].att = take(sd); t.L[l].tmp1 = take(sd); t.L[l].x1 = take(sd); t.L[l].z = take(sf);
+    t.L[l].ffh = take(sf); t.L[l].tmp2 = take(sd); t.L[l].xout = take(sd);
   }
-  float* dx = take(sd); float* da = take(sd); float* db_ = take(sd); float* dc = take(sd);
-  float* dqkv = take(3 * sd); float* dffh = take(sf); float* dz = take(sf);
-  float* pbuf = take(8LL * s * s); float* dsbuf = take(8LL * s * s);
-  float* rowstat = take(2 * s);
-  float* dwk = take(static_cast<long long>(c) * 9 * embed);
-  float* part = take(64);
-  part = ws;
-  g_sgemm_part = part;
+  t.dx = take(sd); t.da = take(sd); t.db_ = take(sd); t.dc = take(sd);
+  t.dqkv = take(3 * sd); t.dffh = take(sf); t.dz = take(sf);
+  t.pbuf = take(8LL * s * s); t.dsbuf = take(8LL * s * s);
+  t.rowstat = take(2 * s);
+  t.dwk = take(static_cast<long long>(c) * 9 * embed);
+  take(64);
+  t.part = ws;
+}
+
+// forward keeping every activation (the backward's inputs) in the tape
+int tape_forward(Tape& t, const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads, int ff,
+                 int decoder, cudaStream_t st) {
+  const int s = 128 + c + 1;
+  const long long sf = static_cast<long long>(s) * ff, cd = static_cast<long long>(c) * d;
+  float *emb = t.emb, *t1 = t.t1, *waves = t.waves, *headin = t.headin, *headin2 = t.headin2, *x0 = t.x0, *part = t.part;
+  TapeLayer* L = t.L;
   const float* omega = params[0];
   const float* wtok = params[1];
   const float* btok = params[2];
-
-  // ---------------- forward with tape
   sincos_kernel<<<ceil_div(c * d / 2, 128), 128, 0, st>>>(wvs_um, omega, emb, c, d);
   EOVAE_LAUNCH_CHECK();
   if (linear(emb, d, params[3], params[4], nullptr, 0, t1, d, c, d, d, ACT_RELU, part, st)) return -1;
@@ -594,13 +600,65 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
     EOVAE_LAUNCH_CHECK();
     xin = L[l].xout;
   }
-  const float* xl = xin;
-  add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(xl + 128 * d, waves, headin, c, d, 0);
+  add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(xin + 128 * d, waves, headin, c, d, 0);
   EOVAE_LAUNCH_CHECK();
   if (decoder) {
-    add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(xl + 128 * d, btok, headin2, c, d, 1);
+    add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(xin + 128 * d, btok, headin2, c, d, 1);
     EOVAE_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+/* eovae_hypernet_forward that also leaves the tape of activations in `workspace` (layout and size of
+ * eovae_hypernet_backward_workspace_bytes) for a following eovae_hypernet_backward(..., tape_valid = 1) */
+int eovae_hypernet_forward_taped(const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads,
+                                 int ff, int embed, int decoder, float* wk_out, float* bias_out, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c >= 1 && c <= 62, "hypernet: band count %d out of range [1, 62]", c);
+  EOVAE_CHECK(d % heads == 0 && d / heads <= 128 && d % 2 == 0 && heads <= 8, "hypernet: bad d_model/heads (%d/%d)", d, heads);
+  EOVAE_CHECK(num_layers <= 16 && 128 + c + 1 <= MHA_MAX_S, "hypernet: too many layers / tokens");
+  EOVAE_CHECK(workspace_bytes >= eovae_hypernet_backward_workspace_bytes(c, d, ff, embed, num_layers), "hypernet taped forward: workspace too small");
+  Tape t;
+  carve_tape(t, workspace, c, d, ff, embed, num_layers);
+  if (tape_forward(t, wvs_um, c, params, num_layers, d, heads, ff, decoder, st)) return -1;
+  const float* xl = num_layers > 0 ? t.L[num_layers - 1].xout : t.x0;
+  if (linear(t.headin, d, params[7], params[8], nullptr, 0, wk_out, 9 * embed, c, 9 * embed, d, ACT_NONE, t.part, st)) return -1;
+  if (decoder) {
+    if (linear(t.headin2, d, params[9], params[10], nullptr, 0, bias_out, 1, c, 1, d, ACT_NONE, t.part, st)) return -1;
+  } else {
+    if (linear(xl + (128 + c) * d, d, params[9], params[10], nullptr, 0, bias_out, embed, 1, embed, d, ACT_NONE, t.part, st)) return -1;
+  }
+  return 0;
+}
+
+int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads,
+                            int ff, int embed, int decoder, const float* dw_oihw, int dw_cin_ld, float w_scale,
+                            const float* dbias, float bias_scale, float* const* grads, int tape_valid, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(c >= 1 && c <= 62, "hypernet: band count %d out of range [1, 62]", c);
+  EOVAE_CHECK(d % heads == 0 && d / heads <= 128 && d % 2 == 0 && heads <= 8, "hypernet: bad d_model/heads (%d/%d)", d, heads);
+  EOVAE_CHECK(workspace_bytes >= eovae_hypernet_backward_workspace_bytes(c, d, ff, embed, num_layers),
+              "hypernet backward: workspace too small");
+  const int s = 128 + c + 1;
+  EOVAE_CHECK(s <= MHA_MAX_S && num_layers <= 16, "hypernet: sequence too long / too many layers");
+  const long long sd = static_cast<long long>(s) * d, sf = static_cast<long long>(s) * ff, cd = static_cast<long long>(c) * d;
+  Tape t;
+  carve_tape(t, workspace, c, d, ff, embed, num_layers);
+  if (!tape_valid && tape_forward(t, wvs_um, c, params, num_layers, d, heads, ff, decoder, st)) return -1;
+  float *waves = t.waves, *emb = t.emb, *t1 = t.t1, *headin = t.headin, *headin2 = t.headin2, *x0 = t.x0;
+  float *dx = t.dx, *da = t.da, *db_ = t.db_, *dc = t.dc, *dqkv = t.dqkv, *dffh = t.dffh, *dz = t.dz, *pbuf = t.pbuf,
+        *dsbuf = t.dsbuf, *rowstat = t.rowstat, *dwk = t.dwk;
+  TapeLayer* L = t.L;
+  g_sgemm_part = t.part;
+  const float* btok = params[2];
+  (void)btok;
+  const float* xl = num_layers > 0 ? L[num_layers - 1].xout : x0;
 
   // ---------------- heads
   const int ne = 9 * embed;

@@ -303,19 +303,19 @@ class DynConvInFn(Function):
     @staticmethod
     def forward(ctx, x, mod, wvs, *hparams):
         c = wvs.size(0)
-        wk, b_raw = mod._generate(wvs)
+        wk, b_raw, tape = mod._generate_taped(wvs)
         packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, mod.embed_dim, False, mod.scaler, mod.scaler, x.dtype, False)
-        ctx.save_for_backward(x, wvs)
+        ctx.save_for_backward(x, wvs, tape)
         ctx.mod = mod
         return ops.conv2d(x, packed, bias, mod.embed_dim, ops.CONV_3X3, algo_cin=c, gn_groups=32)
 
     @staticmethod
     def backward(ctx, dy):
-        x, wvs = ctx.saved_tensors
+        x, wvs, tape = ctx.saved_tensors
         mod = ctx.mod
         g = _dense(_grad_act(dy, x.dtype))
         dw = ops.conv2d_wgrad(x, g, 3)  # [E, C padded to 16, 3, 3]
-        grads = mod._hyper_backward(wvs, dw, ops.bias_grad(g), mod.scaler)
+        grads = mod._hyper_backward(wvs, dw, ops.bias_grad(g), mod.scaler, tape)
         return (None, None, None) + tuple(grads)
 
 
@@ -327,23 +327,23 @@ class DynConvOutFn(Function):
     @staticmethod
     def forward(ctx, x, mod, waves, *hparams):
         c = waves.size(0)
-        wk, b_raw = mod._generate(waves)
+        wk, b_raw, tape = mod._generate_taped(waves)
         packed, bias, oihw = ops.pack_dyn_weight(wk, b_raw, c, mod.embed_dim, True, mod.scaler, mod.scaler * mod.scaler,
                                                  x.dtype, True)
         mod._last = (wk, b_raw, c)
-        ctx.save_for_backward(x, oihw, waves)
+        ctx.save_for_backward(x, oihw, waves, tape)
         ctx.mod = mod
         return ops.conv2d(x, packed, bias, c, ops.CONV_3X3, out_dtype=torch.float32)
 
     @staticmethod
     def backward(ctx, dy):
-        x, oihw, waves = ctx.saved_tensors
+        x, oihw, waves, tape = ctx.saved_tensors
         mod = ctx.mod
         c = waves.size(0)
         g = _grad_act_pad8(dy, x.dtype)
         dx = ops.conv2d_dgrad(g, oihw, ops.CONV_3X3) if ctx.needs_input_grad[0] else None
         dw = ops.conv2d_wgrad(x, g[:, :c], 3)  # [C, E, 3, 3]
-        grads = mod._hyper_backward(waves, dw, ops.bias_grad(g[:, :c]), mod.scaler * mod.scaler)
+        grads = mod._hyper_backward(waves, dw, ops.bias_grad(g[:, :c]), mod.scaler * mod.scaler, tape)
         return (dx, None, None) + tuple(grads)
 
 

@@ -161,13 +161,21 @@ class _DynamicBase(nn.Module):
         return ops.hypernet_forward(wvs, params, g.num_layers, g.input_dim, g.num_heads, g.ff_dim, self.embed_dim,
                                     self._decoder)
 
-    def _hyper_backward(self, wvs: Tensor, dw_oihw: Tensor, dbias: Tensor, bias_scale: float) -> list:
+    def _generate_taped(self, wvs: Tensor):
+        """_generate that also returns the activation tape for _hyper_backward (training forward)."""
+        g = self.weight_generator
+        dev = g.weight_tokens.device
+        params = g.kernel_params(self.fclayer, self._omega_dev(dev))
+        return ops.hypernet_forward_taped(wvs.to(device=dev, dtype=torch.float32), params, g.num_layers, g.input_dim,
+                                          g.num_heads, g.ff_dim, self.embed_dim, self._decoder)
+
+    def _hyper_backward(self, wvs: Tensor, dw_oihw: Tensor, dbias: Tensor, bias_scale: float, tape=None) -> list:
         """Gradients of ``weight_generator.parameter_list(fclayer)`` given the generated kernel's / bias' gradient."""
         g = self.weight_generator
         dev = g.weight_tokens.device
         params = g.kernel_params(self.fclayer, self._omega_dev(dev))
         return ops.hypernet_backward(wvs.to(device=dev, dtype=torch.float32), params, g.num_layers, g.input_dim, g.num_heads,
-                                     g.ff_dim, self.embed_dim, self._decoder, dw_oihw, self.scaler, dbias, bias_scale)
+                                     g.ff_dim, self.embed_dim, self._decoder, dw_oihw, self.scaler, dbias, bias_scale, tape)
 
     def _get_weights(self, waves: Tensor):
         raise NotImplementedError('the CUDA path generates weights from wavelengths directly; use _generate(wvs)')

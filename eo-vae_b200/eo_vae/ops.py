@@ -579,9 +579,28 @@ def hypernet_forward(wvs: torch.Tensor, params: list, num_layers: int, d: int, h
     return wk, bias
 
 
+def hypernet_forward_taped(wvs: torch.Tensor, params: list, num_layers: int, d: int, heads: int, ff: int, embed: int,
+                           decoder: bool):
+    """hypernet_forward that also returns the activation tape (a workspace tensor) for hypernet_backward(tape=...)."""
+    _need_cuda(wvs, *params)
+    wvs = wvs.to(torch.float32).contiguous()
+    c = wvs.numel()
+    lib = _C.lib()
+    ws_bytes = lib.eovae_hypernet_backward_workspace_bytes(c, d, ff, embed, num_layers)
+    tape = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=wvs.device)
+    wk = torch.empty((c, 9 * embed), dtype=torch.float32, device=wvs.device)
+    bias = torch.empty((c if decoder else embed,), dtype=torch.float32, device=wvs.device)
+    arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    rc = lib.eovae_hypernet_forward_taped(_ptr(wvs), c, arr, num_layers, d, heads, ff, embed, 1 if decoder else 0, _ptr(wk),
+                                          _ptr(bias), _ptr(tape), ws_bytes, _stream())
+    _C.check(rc, "eovae_hypernet_forward_taped")
+    return wk, bias, tape
+
+
 def hypernet_backward(wvs: torch.Tensor, params: list, num_layers: int, d: int, heads: int, ff: int, embed: int, decoder: bool,
-                      dw_oihw: torch.Tensor, w_scale: float, dbias: torch.Tensor, bias_scale: float) -> list:
-    """Gradients of params[1:] (params[0] is the sincos table) given the gradient of the generated kernel / bias."""
+                      dw_oihw: torch.Tensor, w_scale: float, dbias: torch.Tensor, bias_scale: float, tape=None) -> list:
+    """Gradients of params[1:] (params[0] is the sincos table) given the gradient of the generated kernel / bias.
+    ``tape``: the workspace hypernet_forward_taped returned for the same inputs (skips the forward re-run)."""
     _need_cuda(wvs, dw_oihw, dbias, *params)
     wvs = wvs.to(torch.float32).contiguous()
     c = wvs.numel()
@@ -589,13 +608,13 @@ def hypernet_backward(wvs: torch.Tensor, params: list, num_layers: int, d: int, 
     dbias = dbias.to(torch.float32).contiguous()
     lib = _C.lib()
     ws_bytes = lib.eovae_hypernet_backward_workspace_bytes(c, d, ff, embed, num_layers)
-    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=wvs.device)
+    ws = tape if tape is not None else torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=wvs.device)
     grads = [None] + [torch.empty_like(p) for p in params[1:]]
     parr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
     garr = (ctypes.c_void_p * len(params))(*[None if g is None else g.data_ptr() for g in grads])
     rc = lib.eovae_hypernet_backward(_ptr(wvs), c, parr, num_layers, d, heads, ff, embed, 1 if decoder else 0, _ptr(dw_oihw),
-                                     dw_oihw.shape[1], float(w_scale), _ptr(dbias), float(bias_scale), garr, _ptr(ws),
-                                     ws_bytes, _stream())
+                                     dw_oihw.shape[1], float(w_scale), _ptr(dbias), float(bias_scale), garr,
+                                     1 if tape is not None else 0, _ptr(ws), ws_bytes, _stream())
     _C.check(rc, "eovae_hypernet_backward")
     return grads[1:]
 

@@ -221,13 +221,18 @@ int eovae_pixel_loss_backward(const float* a, const float* b, long long count, f
 /* backward of eovae_hypernet_forward + eovae_pack_dyn_weight: dw_oihw = gradient of the generated conv kernel
  * ([embed][dw_cin_ld >= c][3][3] for the encoder layer, [c][dw_cin_ld >= embed][3][3] for the decoder layer), dbias the
  * gradient of the scaled bias; w_scale / bias_scale the factors eovae_pack_dyn_weight applied.  grads[i] receives the
- * gradient of params[i] (same order as the forward; written, not accumulated; grads[0] is ignored).  The forward is
- * re-run inside (activations kept in the workspace).  dynamic_conv.py:110-130,162-183,352-366,511-525,684-697 adjoint. */
+ * gradient of params[i] (same order as the forward; written, not accumulated; grads[0] is ignored).  tape_valid = 0: the
+ * forward is re-run inside (activations kept in the workspace); 1: the workspace still holds eovae_hypernet_forward_taped's.  dynamic_conv.py:110-130,162-183,352-366,511-525,684-697 adjoint. */
 size_t eovae_hypernet_backward_workspace_bytes(int c, int d, int ff, int embed, int num_layers);
 int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads,
                             int ff, int embed, int decoder, const float* dw_oihw, int dw_cin_ld, float w_scale,
-                            const float* dbias, float bias_scale, float* const* grads, void* workspace,
+                            const float* dbias, float bias_scale, float* const* grads, int tape_valid, void* workspace,
                             size_t workspace_bytes, void* stream);
+/* forward that ALSO leaves its activations in `workspace` (size eovae_hypernet_backward_workspace_bytes) so that a
+ * following eovae_hypernet_backward(..., tape_valid = 1, same workspace) does not re-run it */
+int eovae_hypernet_forward_taped(const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads,
+                                 int ff, int embed, int decoder, float* wk_out, float* bias_out, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 /* gradient of eovae_msssim's batch-mean value wrt pred (fp32 NCHW), times the device scalar *grad_scale; the forward
  * pyramid is rebuilt inside the workspace (consistency_loss.py:24-37 adjoint) */
 size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w);

@@ -55,6 +55,37 @@ def test_train_mode_forward_matches_reference():
     assert torch.allclose(recon, recon_ref, atol=1e-4)
 
 
+def test_train_mode_gradients_match_reference():
+    """Pins the oracle's GRADIENT semantics: train-mode forward + Charbonnier loss, every parameter gradient of the
+    unmodified reference (torch autograd) equals autograd over the oracle - in particular the BatchNorm running-statistics
+    update is outside the graph, although the inverse normalisation of the same forward reads the updated buffers."""
+    cfg = TINY_CONFIG
+    sd = make_state_dict(cfg, 6)
+    model = ref_shim.build_reference_model(cfg, sd, train=True)
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"])
+    x = synthetic_patches(2, 12, 32, seed=79)
+    torch.manual_seed(321)
+    recon_ref, post = model(x, wvs)
+    torch.sqrt((recon_ref - x) ** 2 + 1e-3 ** 2).mean().backward()        # CharbonnierLoss, consistency_loss.py:12-21
+    torch.manual_seed(321)
+    eps = torch.randn(post.mean.shape)
+    osd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    recon, _ = O.forward(osd, x, wvs, eps=eps, train=True, heads=cfg["hyper_heads"])
+    O.charbonnier_loss(recon, x).backward()
+    checked = 0
+    # conv biases in front of a GroupNorm with one channel per group have a mathematically zero gradient (rounding noise
+    # ~1e-9 on both sides), hence the absolute floor relative to the largest gradient of the model
+    floor = 1e-6 * max(float(p.grad.abs().max()) for p in model.parameters())
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        got = osd[name].grad
+        assert got is not None, name
+        scale = float(p.grad.abs().max())
+        assert float((got - p.grad).abs().max()) < 2e-4 * scale + floor, name
+        checked += 1
+    assert checked > 150
+
+
 def test_dropin_package_has_reference_checkpoint_layout():
     """eo_vae (this repo) registers exactly the reference's parameters/buffers: a reference checkpoint loads strictly."""
     import __graft_entry__ as g

@@ -202,6 +202,10 @@ def test_tiny_model_gradients(cuda):
         want.append(gr.flatten())
         worst[name] = _rel(p.grad.cpu(), gr)
     total = _rel(torch.cat(got), torch.cat(want))
+    wn = float(torch.cat(want).norm())
+    contrib = sorted(((round(float((p.grad.float().cpu() - ref_sd[n].grad).norm()) / wn, 5), round(worst[n], 4), n)
+                      for n, p in model.named_parameters()), reverse=True)[:5]
+    print("largest contributions (share of total error, own rel err, name):", contrib)
     top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
     print(f"tiny model gradient: total rel-L2 {total:.3e}; worst tensors {top}")
     assert total < 5e-2, (total, top)
@@ -303,6 +307,71 @@ def test_graph_training_flag_mixed_modalities(cuda):
     assert len(model._train_graphs) == 2
     for mod, ls in losses.items():
         assert all(l == l for l in ls) and ls[-1] < ls[0], (mod, ls)
+
+
+def test_freeze_body_trains_only_the_dynamic_layers(cuda):
+    """freeze_body=True (the reference default, new_autoencoder.py:284-293): only the wavelength hypernetworks receive
+    gradients / move; the frozen Flux body still back-propagates the data gradient to the dynamic input layer."""
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from oracle.weights import WAVELENGTHS, synthetic_patches
+    model, sd, cfg = _tiny(cuda)
+    model._freeze_body()
+    model.train()
+    model.loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="l1").to(cuda)
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"], dtype=torch.float32).to(cuda)
+    batch = {model.image_key: synthetic_patches(2, 12, cfg["resolution"], seed=5).to(cuda), "wvs": wvs}
+    before = {k: v.detach().clone() for k, v in model.named_parameters()}
+    loss = model.training_step(batch, 0)
+    assert float(loss) == float(loss)
+    for k, v in model.named_parameters():
+        dyn = "encoder.conv_in" in k or "decoder.conv_out" in k
+        assert v.requires_grad == dyn, k
+        if dyn:
+            assert v.grad is not None and bool(torch.isfinite(v.grad).all()), k
+        else:
+            assert torch.equal(v.detach(), before[k]), k
+    moved = [k for k, v in model.named_parameters() if v.requires_grad and not torch.equal(v.detach(), before[k])]
+    assert len(moved) > 10
+
+
+def test_training_step_fp16_operands(cuda):
+    """The training path with the reference trainer's operand type (precision 16-mixed -> fp16): gradients vs the oracle."""
+    import eo_vae
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from oracle import eovae_oracle as O
+    from oracle.weights import WAVELENGTHS, synthetic_patches
+    eo_vae.set_compute_dtype(torch.float16)
+    try:
+        model, sd, cfg = _tiny(cuda)
+        model.train()
+        wvs = torch.tensor(WAVELENGTHS["S2L2A"], dtype=torch.float32)
+        x = synthetic_patches(2, 12, cfg["resolution"], seed=11)
+        loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="char").to(cuda)
+        torch.manual_seed(1234)
+        recon, _ = model(x.to(cuda), wvs.to(cuda))
+        loss, _ = loss_fn(inputs=x.to(cuda), wvs=wvs.to(cuda), reconstructions=recon, global_step=0)
+        # fp16 gradients need the usual loss scaling (Lightning's 16-mixed plugin wraps manual_backward in a GradScaler):
+        # unscaled, the ~1e-6 inter-layer gradients fall into fp16's subnormal range (measured 1.2e-2 instead of 3e-3)
+        scale = 4096.0
+        (loss * scale).backward()
+        for p in model.parameters():
+            p.grad.div_(scale)
+    finally:
+        eo_vae.set_compute_dtype(torch.bfloat16)
+    ref_sd = {k: (v.clone().float().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    torch.manual_seed(1234)
+    hl = cfg["resolution"] // 2 ** (len(cfg["ch_mult"]) - 1)
+    eps = torch.randn((2, cfg["z_channels"], hl, hl))
+    recon_ref, _ = O.forward(ref_sd, x, wvs, eps, train=True, heads=cfg["hyper_heads"])
+    O.charbonnier_loss(recon_ref, x).backward()
+    got = torch.cat([p.grad.flatten().float().cpu() for _, p in model.named_parameters()])
+    want = torch.cat([ref_sd[n].grad.flatten() for n, _ in model.named_parameters()])
+    err = _rel(got, want)
+    contrib = sorted(((round(float((p.grad.float().cpu() - ref_sd[n].grad).norm()) / float(want.norm()), 5),
+                       round(_rel(p.grad.cpu(), ref_sd[n].grad), 4), round(float(ref_sd[n].grad.norm()) / float(want.norm()), 3), n)
+                      for n, p in model.named_parameters()), reverse=True)[:6]
+    print(f"fp16-operand training gradient rel-L2 {err:.3e}; largest contributions {contrib}")
+    assert err < 8e-3, err  # measured 5.6e-3
 
 
 def test_training_step_reduces_loss(cuda):

@@ -768,3 +768,257 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// FactorizedWeightGenerator(_decoder) (dynamic_conv.py:186-302): PRE-norm transformer layers (norm_first=True, ff = 4 d)
+// and a low-rank head Linear(d, rank) -> GELU -> Linear(rank, 9E).  Same building blocks as above; the forward always
+// keeps its activations (the tape is ~1 MB), so one entry point serves inference and training.  Dropout (p = 0.1 inside
+// the reference's train-mode transformer) is not applied: the generated kernel is deterministic in both modes.
+// params: 0 omega | 1 weight_tokens | 2 bias_token | 3,4 fclayer.w1 | 5,6 fclayer.w2 | 7,8 fc_weight.0 [rank][d] |
+//         9,10 fc_weight.2 [9E][rank] | 11,12 fc_bias | per layer (12): in_proj, out_proj, linear1, linear2, norm1, norm2
+namespace {
+
+struct FTapeLayer { float *ln1, *qkv, *att, *x1, *ln2, *z, *ffh, *xout; };
+struct FTape {
+  float *emb, *t1, *waves, *headin, *headin2, *hr, *hg, *x0;
+  FTapeLayer L[16];
+  float *dx, *da, *db_, *dc, *dqkv, *dffh, *dz, *pbuf, *dsbuf, *rowstat, *dwk, *dhg, *dhr, *part;
+};
+
+size_t carve_ftape(FTape* t, void* workspace, int c, int d, int ff, int embed, int rank, int num_layers) {
+  const int s = 128 + c + 1;
+  const long long sd = static_cast<long long>(s) * d, sf = static_cast<long long>(s) * ff, cd = static_cast<long long>(c) * d;
+  const long long cr = static_cast<long long>(c) * rank;
+  float* base = static_cast<float*>(workspace);
+  float* ws = base;
+  auto take = [&](long long n) { float* p = ws; ws += (n + 3) / 4 * 4; return p; };
+  FTape tmp;
+  FTape& T = t != nullptr ? *t : tmp;
+  T.emb = take(cd); T.t1 = take(cd); T.waves = take(cd); T.headin = take(cd); T.headin2 = take(cd);
+  T.hr = take(cr); T.hg = take(cr); T.x0 = take(sd);
+  for (int l = 0; l < num_layers; ++l) {
+    T.L[l].ln1 = take(sd); T.L[l].qkv = take(3 * sd); T.L[l].att = take(sd); T.L[l].x1 = take(sd); T.L[l].ln2 = take(sd);
+    T.L[l].z = take(sf); T.L[l].ffh = take(sf); T.L[l].xout = take(sd);
+  }
+  T.dx = take(sd); T.da = take(sd); T.db_ = take(sd); T.dc = take(sd);
+  T.dqkv = take(3 * sd); T.dffh = take(sf); T.dz = take(sf);
+  T.pbuf = take(8LL * s * s); T.dsbuf = take(8LL * s * s);
+  T.rowstat = take(2 * s);
+  T.dwk = take(static_cast<long long>(c) * 9 * embed);
+  T.dhg = take(cr); T.dhr = take(cr);
+  take(64);
+  T.part = ws;
+  return static_cast<size_t>(ws - base) + kLinearPartFloats;
+}
+
+int factorized_check(int c, int d, int heads, int ff, int embed, int rank, int num_layers) {
+  EOVAE_CHECK(c >= 1 && c <= 62, "hypernet: band count %d out of range [1, 62]", c);
+  EOVAE_CHECK(d % heads == 0 && d / heads <= 128 && d % 4 == 0 && heads <= 8, "hypernet: bad d_model/heads (%d/%d)", d, heads);
+  EOVAE_CHECK(num_layers >= 0 && num_layers <= 16 && 128 + c + 1 <= MHA_MAX_S, "hypernet: too many layers / tokens");
+  EOVAE_CHECK(rank >= 4 && rank % 4 == 0 && ff % 4 == 0 && embed >= 1, "factorized hypernet: rank (%d) and ff (%d) must be multiples of 4", rank, ff);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t eovae_hypernet_factorized_workspace_bytes(int c, int d, int ff, int embed, int rank, int num_layers) {
+  if (num_layers < 0 || num_layers > 16) return 0;
+  return carve_ftape(nullptr, nullptr, c, d, ff, embed, rank, num_layers) * sizeof(float);
+}
+
+int eovae_hypernet_factorized_forward(const float* wvs_um, int c, const float* const* params, int num_layers, int d,
+                                      int heads, int ff, int embed, int rank, int decoder, float* wk_out, float* bias_out,
+                                      void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (factorized_check(c, d, heads, ff, embed, rank, num_layers)) return -1;
+  EOVAE_CHECK(workspace_bytes >= eovae_hypernet_factorized_workspace_bytes(c, d, ff, embed, rank, num_layers),
+              "factorized hypernet: workspace too small");
+  FTape t;
+  carve_ftape(&t, workspace, c, d, ff, embed, rank, num_layers);
+  const int s = 128 + c + 1;
+  const long long sf = static_cast<long long>(s) * ff, cd = static_cast<long long>(c) * d, cr = static_cast<long long>(c) * rank;
+  float* part = t.part;
+  const float* wtok = params[1];
+  const float* btok = params[2];
+  sincos_kernel<<<ceil_div(c * d / 2, 128), 128, 0, st>>>(wvs_um, params[0], t.emb, c, d);
+  EOVAE_LAUNCH_CHECK();
+  if (linear(t.emb, d, params[3], params[4], nullptr, 0, t.t1, d, c, d, d, ACT_RELU, part, st)) return -1;
+  if (linear(t.t1, d, params[5], params[6], t.emb, d, t.waves, d, c, d, d, ACT_RELU, part, st)) return -1;
+  EOVAE_CUDA(cudaMemcpyAsync(t.x0, wtok, sizeof(float) * 128 * d, cudaMemcpyDeviceToDevice, st));
+  EOVAE_CUDA(cudaMemcpyAsync(t.x0 + 128 * d, t.waves, sizeof(float) * cd, cudaMemcpyDeviceToDevice, st));
+  EOVAE_CUDA(cudaMemcpyAsync(t.x0 + (128 + c) * d, btok, sizeof(float) * d, cudaMemcpyDeviceToDevice, st));
+  const float* xin = t.x0;
+  for (int l = 0; l < num_layers; ++l) {
+    const float* const* lp = params + 13 + 12 * l;
+    FTapeLayer& L = t.L[l];
+    // x1 = x + out_proj(MHA(LN1(x)))
+    layernorm_kernel<<<ceil_div(s, 4), 128, 0, st>>>(xin, lp[8], lp[9], L.ln1, s, d, 1e-5f);
+    EOVAE_LAUNCH_CHECK();
+    if (linear(L.ln1, d, lp[0], lp[1], nullptr, 0, L.qkv, 3 * d, s, 3 * d, d, ACT_NONE, part, st)) return -1;
+    mha_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(L.qkv, L.att, s, d, heads);
+    EOVAE_LAUNCH_CHECK();
+    if (linear(L.att, d, lp[2], lp[3], xin, d, L.x1, d, s, d, d, ACT_NONE, part, st)) return -1;
+    // xout = x1 + W2 gelu(W1 LN2(x1))
+    layernorm_kernel<<<ceil_div(s, 4), 128, 0, st>>>(L.x1, lp[10], lp[11], L.ln2, s, d, 1e-5f);
+    EOVAE_LAUNCH_CHECK();
+    if (linear(L.ln2, d, lp[4], lp[5], nullptr, 0, L.z, ff, s, ff, d, ACT_NONE, part, st)) return -1;
+    gelu_fwd_kernel<<<blocks_for(sf), 256, 0, st>>>(L.z, L.ffh, sf);
+    EOVAE_LAUNCH_CHECK();
+    if (linear(L.ffh, ff, lp[6], lp[7], L.x1, d, L.xout, d, s, d, ff, ACT_NONE, part, st)) return -1;
+    xin = L.xout;
+  }
+  // features = T[128:128+C] + waves ; wk = W2h gelu(W0 features + b0) + b2h
+  add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(xin + 128 * d, t.waves, t.headin, c, d, 0);
+  EOVAE_LAUNCH_CHECK();
+  if (linear(t.headin, d, params[7], params[8], nullptr, 0, t.hr, rank, c, rank, d, ACT_NONE, part, st)) return -1;
+  gelu_fwd_kernel<<<blocks_for(cr), 256, 0, st>>>(t.hr, t.hg, cr);
+  EOVAE_LAUNCH_CHECK();
+  if (linear(t.hg, rank, params[9], params[10], nullptr, 0, wk_out, 9 * embed, c, 9 * embed, rank, ACT_NONE, part, st)) return -1;
+  if (decoder) {  // bias[c] = fc_bias(features + bias_token)  (dynamic_conv.py:296-299)
+    add_rows_kernel<<<ceil_div(c * d, 256), 256, 0, st>>>(t.headin, btok, t.headin2, c, d, 1);
+    EOVAE_LAUNCH_CHECK();
+    if (linear(t.headin2, d, params[11], params[12], nullptr, 0, bias_out, 1, c, 1, d, ACT_NONE, part, st)) return -1;
+  } else {        // bias[E] = fc_bias(T[-1])
+    if (linear(xin + (128 + c) * d, d, params[11], params[12], nullptr, 0, bias_out, embed, 1, embed, d, ACT_NONE, part, st)) return -1;
+  }
+  return 0;
+}
+
+/* adjoint of eovae_hypernet_factorized_forward (+ eovae_pack_dyn_weight); `workspace` must still hold that forward's
+ * activations (same arguments).  grads[i] <- d/d params[i] (written; grads[0] unused). */
+int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* const* params, int num_layers, int d,
+                                       int heads, int ff, int embed, int rank, int decoder, const float* dw_oihw,
+                                       int dw_cin_ld, float w_scale, const float* dbias, float bias_scale,
+                                       float* const* grads, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  (void)wvs_um;
+  if (factorized_check(c, d, heads, ff, embed, rank, num_layers)) return -1;
+  EOVAE_CHECK(workspace_bytes >= eovae_hypernet_factorized_workspace_bytes(c, d, ff, embed, rank, num_layers),
+              "factorized hypernet backward: workspace too small");
+  FTape t;
+  carve_ftape(&t, workspace, c, d, ff, embed, rank, num_layers);
+  const int s = 128 + c + 1;
+  const long long sd = static_cast<long long>(s) * d, sf = static_cast<long long>(s) * ff, cd = static_cast<long long>(c) * d;
+  const long long cr = static_cast<long long>(c) * rank;
+  g_sgemm_part = t.part;
+  float *dx = t.dx, *da = t.da, *db_ = t.db_, *dc = t.dc, *dqkv = t.dqkv, *dffh = t.dffh, *dz = t.dz, *rowstat = t.rowstat;
+  const float* xl = num_layers > 0 ? t.L[num_layers - 1].xout : t.x0;
+  const int ne = 9 * embed;
+
+  // ---------------- heads
+  dyn_weight_grad_kernel<<<blocks_for(static_cast<long long>(c) * ne), 256, 0, st>>>(dw_oihw, dw_cin_ld, c, embed, decoder, w_scale, t.dwk);
+  EOVAE_LAUNCH_CHECK();
+  EOVAE_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * sd, st));
+  // wk = hg W2h^T + b2h
+  if (sgemm(t.dwk, 1, ne, t.hg, rank, 1, grads[9], rank, ne, rank, c, 0, st)) return -1;      // dW2h [9E][rank]
+  colsum_f32_kernel<<<ceil_div(ne, 128), 128, 0, st>>>(t.dwk, ne, c, ne, grads[10], 0);
+  EOVAE_LAUNCH_CHECK();
+  if (sgemm(t.dwk, ne, 1, params[9], rank, 1, t.dhg, rank, c, rank, ne, 0, st)) return -1;    // dhg [c][rank]
+  gelu_bwd_kernel<<<blocks_for(cr), 256, 0, st>>>(t.hr, t.dhg, t.dhr, cr);
+  EOVAE_LAUNCH_CHECK();
+  if (sgemm(t.dhr, 1, rank, t.headin, d, 1, grads[7], d, rank, d, c, 0, st)) return -1;       // dW0 [rank][d]
+  colsum_f32_kernel<<<ceil_div(rank, 128), 128, 0, st>>>(t.dhr, rank, c, rank, grads[8], 0);
+  EOVAE_LAUNCH_CHECK();
+  float* dfeat = da;  // [c][d] gradient of features = T[128:128+C] + waves
+  if (sgemm(t.dhr, rank, 1, params[7], d, 1, dfeat, d, c, d, rank, 0, st)) return -1;
+  EOVAE_CUDA(cudaMemsetAsync(grads[2], 0, sizeof(float) * d, st));
+  if (decoder) {
+    axpy_kernel<<<blocks_for(c), 256, 0, st>>>(dbias, bias_scale, rowstat, c, 0);             // d(bias_raw) [c]
+    EOVAE_LAUNCH_CHECK();
+    if (sgemm(rowstat, 0, 1, t.headin2, d, 1, grads[11], d, 1, d, c, 0, st)) return -1;       // dwfb [1][d]
+    colsum_f32_kernel<<<1, 32, 0, st>>>(rowstat, 1, c, 1, grads[12], 0);
+    EOVAE_LAUNCH_CHECK();
+    if (sgemm(rowstat, 1, 0, params[11], 0, 1, db_, d, c, d, 1, 0, st)) return -1;            // dheadin2 [c][d]
+    axpy_kernel<<<blocks_for(cd), 256, 0, st>>>(db_, 1.f, dfeat, cd, 1);                      // headin2 = features + btok
+    EOVAE_LAUNCH_CHECK();
+    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(db_, d, c, d, grads[2], 1);
+    EOVAE_LAUNCH_CHECK();
+  } else {
+    axpy_kernel<<<blocks_for(embed), 256, 0, st>>>(dbias, bias_scale, grads[12], embed, 0);
+    EOVAE_LAUNCH_CHECK();
+    if (sgemm(grads[12], 1, 0, xl + (128 + c) * d, 0, 1, grads[11], d, embed, d, 1, 0, st)) return -1;
+    if (sgemm(grads[12], 0, 1, params[11], d, 1, dx + (128 + c) * d, d, 1, d, embed, 1, st)) return -1;
+  }
+  axpy_kernel<<<blocks_for(cd), 256, 0, st>>>(dfeat, 1.f, dx + 128 * d, cd, 1);
+  EOVAE_LAUNCH_CHECK();
+  float* dwaves = da;  // the `waves` summand of features keeps dfeat until the token gradient is added below
+
+  // ---------------- pre-norm layers, last to first (dx = gradient of the layer output)
+  for (int l = num_layers - 1; l >= 0; --l) {
+    const float* const* lp = params + 13 + 12 * l;
+    float* const* lg = grads + 13 + 12 * l;
+    FTapeLayer& L = t.L[l];
+    const float* lin = l == 0 ? t.x0 : t.L[l - 1].xout;
+    // xout = x1 + ffh W2^T + b2
+    if (sgemm(dx, d, 1, lp[6], ff, 1, dffh, ff, s, ff, d, 0, st)) return -1;                  // dffh = dx W2
+    if (sgemm(dx, 1, d, L.ffh, ff, 1, lg[6], ff, d, ff, s, 0, st)) return -1;                 // dW2 [d][ff]
+    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dx, d, s, d, lg[7], 0);
+    EOVAE_LAUNCH_CHECK();
+    gelu_bwd_kernel<<<blocks_for(sf), 256, 0, st>>>(L.z, dffh, dz, sf);
+    EOVAE_LAUNCH_CHECK();
+    // z = ln2 W1^T + b1
+    float* dln2 = db_;
+    if (sgemm(dz, ff, 1, lp[4], d, 1, dln2, d, s, d, ff, 0, st)) return -1;
+    if (sgemm(dz, 1, ff, L.ln2, d, 1, lg[4], d, ff, d, s, 0, st)) return -1;                  // dW1 [ff][d]
+    colsum_f32_kernel<<<ceil_div(ff, 128), 128, 0, st>>>(dz, ff, s, ff, lg[5], 0);
+    EOVAE_LAUNCH_CHECK();
+    // ln2 = LN(x1; norm2): dx1 = dx + LN'(dln2)
+    float* dx1 = dc;
+    layernorm_bwd_kernel<<<ceil_div(s, 4), 128, 0, st>>>(L.x1, lp[10], dln2, dx1, rowstat, s, d, 1e-5f);
+    EOVAE_LAUNCH_CHECK();
+    layernorm_bwd_param_kernel<<<ceil_div(d, 128), 128, 0, st>>>(L.x1, dln2, rowstat, lg[10], lg[11], s, d);
+    EOVAE_LAUNCH_CHECK();
+    axpy_kernel<<<blocks_for(sd), 256, 0, st>>>(dx, 1.f, dx1, sd, 1);
+    EOVAE_LAUNCH_CHECK();
+    // x1 = xin + att Wo^T + bo
+    float* datt = db_;
+    if (sgemm(dx1, d, 1, lp[2], d, 1, datt, d, s, d, d, 0, st)) return -1;
+    if (sgemm(dx1, 1, d, L.att, d, 1, lg[2], d, d, d, s, 0, st)) return -1;                   // dWo [d][d]
+    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dx1, d, s, d, lg[3], 0);
+    EOVAE_LAUNCH_CHECK();
+    mha_bwd_q_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(L.qkv, datt, t.pbuf, t.dsbuf, dqkv, s, d, heads);
+    EOVAE_LAUNCH_CHECK();
+    {
+      const int hd = d / heads;
+      if (sgemm_b(t.dsbuf, 1, s, static_cast<long long>(s) * s, L.qkv, 3 * d, 1, hd, dqkv + d, 3 * d, hd, heads, s, hd, s, 0, nullptr, st)) return -1;
+      if (sgemm_b(t.pbuf, 1, s, static_cast<long long>(s) * s, datt, d, 1, hd, dqkv + 2 * d, 3 * d, hd, heads, s, hd, s, 0, nullptr, st)) return -1;
+    }
+    // qkv = ln1 Win^T + bin ; ln1 = LN(xin; norm1): dxin = dx1 + LN'(dqkv Win)
+    float* dln1 = db_;
+    if (sgemm(dqkv, 3 * d, 1, lp[0], d, 1, dln1, d, s, d, 3 * d, 0, st)) return -1;
+    if (sgemm(dqkv, 1, 3 * d, L.ln1, d, 1, lg[0], d, 3 * d, d, s, 0, st)) return -1;           // dWin [3d][d]
+    colsum_f32_kernel<<<ceil_div(3 * d, 128), 128, 0, st>>>(dqkv, 3 * d, s, 3 * d, lg[1], 0);
+    EOVAE_LAUNCH_CHECK();
+    layernorm_bwd_kernel<<<ceil_div(s, 4), 128, 0, st>>>(lin, lp[8], dln1, dx, rowstat, s, d, 1e-5f);
+    EOVAE_LAUNCH_CHECK();
+    layernorm_bwd_param_kernel<<<ceil_div(d, 128), 128, 0, st>>>(lin, dln1, rowstat, lg[8], lg[9], s, d);
+    EOVAE_LAUNCH_CHECK();
+    axpy_kernel<<<blocks_for(sd), 256, 0, st>>>(dx1, 1.f, dx, sd, 1);
+    EOVAE_LAUNCH_CHECK();
+  }
+
+  // ---------------- tokens and FCResLayer
+  EOVAE_CUDA(cudaMemcpyAsync(grads[1], dx, sizeof(float) * 128 * d, cudaMemcpyDeviceToDevice, st));
+  axpy_kernel<<<blocks_for(d), 256, 0, st>>>(dx + (128 + c) * d, 1.f, grads[2], d, 1);
+  EOVAE_LAUNCH_CHECK();
+  axpy_kernel<<<blocks_for(cd), 256, 0, st>>>(dx + 128 * d, 1.f, dwaves, cd, 1);
+  EOVAE_LAUNCH_CHECK();
+  float* du2 = db_;
+  relu_bwd_kernel<<<blocks_for(cd), 256, 0, st>>>(t.waves, t.emb, dwaves, du2, cd);
+  EOVAE_LAUNCH_CHECK();
+  if (sgemm(du2, 1, d, t.t1, d, 1, grads[5], d, d, d, c, 0, st)) return -1;
+  colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(du2, d, c, d, grads[6], 0);
+  EOVAE_LAUNCH_CHECK();
+  float* dt1 = dc;
+  if (sgemm(du2, d, 1, params[5], d, 1, dt1, d, c, d, d, 0, st)) return -1;
+  relu_bwd_kernel<<<blocks_for(cd), 256, 0, st>>>(t.t1, nullptr, dt1, dt1, cd);
+  EOVAE_LAUNCH_CHECK();
+  if (sgemm(dt1, 1, d, t.emb, d, 1, grads[3], d, d, d, c, 0, st)) return -1;
+  colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dt1, d, c, d, grads[4], 0);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,8 +1,8 @@
 """Wavelength-conditioned dynamic input / output convolutions on the sm_100a kernels.
 
 Interface mirror of the reference ``eo_vae/models/modules/dynamic_conv.py`` (TransformerWeightGenerator :62,
-TransformerWeightGenerator_decoder :133, FCResLayer :336, DynamicConv :369, DynamicConv_decoder :538): identical
-constructor arguments, parameter names / shapes / initialisation, ``forward`` and ``get_distillation_weight``.
+TransformerWeightGenerator_decoder :133, FactorizedWeightGenerator :186, FactorizedWeightGenerator_decoder :267,
+FCResLayer :336, DynamicConv :369, DynamicConv_decoder :538): identical constructor arguments, parameter names / shapes / initialisation, ``forward`` and ``get_distillation_weight``.
 The hypernetwork (sincos -> FCRes -> post-norm transformer over 128 + C + 1 tokens -> linear heads) runs as fp32
 CUDA kernels (``eovae_hypernet_forward``) and its output is packed straight into the K-major tensor-core operand
 of the band-mixing 3x3 implicit GEMM (``eovae_pack_dyn_weight`` -> ``eovae_conv2d``); no OIHW weight tensor is
@@ -103,6 +103,64 @@ class TransformerWeightGenerator_decoder(TransformerWeightGenerator):
         self.fc_bias = nn.Linear(input_dim, 1)
 
 
+class FactorizedWeightGenerator(nn.Module):
+    """Low-rank head + pre-norm transformer (dynamic_conv.py:186-264): parameter container with the reference's
+    registration order (transformer_encoder, fc_weight.{0,2}, fc_bias, weight_tokens, bias_token) and init.
+    Runs on eovae_hypernet_factorized_forward/backward.  The reference's train-mode dropout (p = 0.1 inside the
+    transformer layers) is NOT applied by the kernels: the generated kernel is deterministic in both modes."""
+
+    _decoder_head = False
+    factorized = True
+
+    def __init__(self, input_dim: int, output_dim: int, embed_dim: int, num_heads: int = 4, num_layers: int = 2,
+                 rank_ratio: int = 4) -> None:
+        super().__init__()
+        layer = nn.TransformerEncoderLayer(d_model=input_dim, nhead=num_heads, dim_feedforward=input_dim * 4,
+                                           activation='gelu', norm_first=True, batch_first=False, dropout=0.1)
+        self.transformer_encoder = nn.TransformerEncoder(layer, num_layers=num_layers, enable_nested_tensor=False)
+        rank = max(32, output_dim // rank_ratio)
+        self.fc_weight = nn.Sequential(nn.Linear(input_dim, rank), nn.GELU(), nn.Linear(rank, output_dim))
+        self.fc_bias = nn.Linear(input_dim, embed_dim)
+        self.wt_num = 128
+        self.weight_tokens = nn.Parameter(torch.empty([self.wt_num, input_dim]))
+        self.bias_token = nn.Parameter(torch.empty([1, input_dim]))
+        torch.nn.init.normal_(self.weight_tokens, std=0.02)
+        torch.nn.init.normal_(self.bias_token, std=0.02)
+        self._init_head()
+        self.input_dim, self.embed_dim, self.num_heads, self.num_layers = input_dim, embed_dim, num_heads, num_layers
+        self.rank = rank
+
+    def _init_head(self) -> None:
+        nn.init.xavier_uniform_(self.fc_weight[0].weight)
+        nn.init.zeros_(self.fc_weight[-1].weight)
+        nn.init.zeros_(self.fc_weight[-1].bias)
+
+    def parameter_list(self, fclayer: FCResLayer) -> list:
+        """Trainable tensors in the order of eovae_hypernet_factorized_forward (entry 0, the sincos table, excluded)."""
+        ps = [self.weight_tokens, self.bias_token, fclayer.w1.weight, fclayer.w1.bias, fclayer.w2.weight,
+              fclayer.w2.bias, self.fc_weight[0].weight, self.fc_weight[0].bias, self.fc_weight[2].weight,
+              self.fc_weight[2].bias, self.fc_bias.weight, self.fc_bias.bias]
+        for l in self.transformer_encoder.layers:
+            ps += [l.self_attn.in_proj_weight, l.self_attn.in_proj_bias, l.self_attn.out_proj.weight,
+                   l.self_attn.out_proj.bias, l.linear1.weight, l.linear1.bias, l.linear2.weight, l.linear2.bias,
+                   l.norm1.weight, l.norm1.bias, l.norm2.weight, l.norm2.bias]
+        return ps
+
+    kernel_params = TransformerWeightGenerator.kernel_params
+    ff_dim = TransformerWeightGenerator.ff_dim
+
+
+class FactorizedWeightGenerator_decoder(FactorizedWeightGenerator):
+    """Per-band scalar bias head on (features + bias_token) (dynamic_conv.py:267-302)."""
+
+    _decoder_head = True
+
+    def __init__(self, input_dim: int, output_dim: int, embed_dim: int, num_heads: int = 4, num_layers: int = 2,
+                 rank_ratio: int = 4) -> None:
+        super().__init__(input_dim, output_dim, embed_dim, num_heads, num_layers, rank_ratio)
+        self.fc_bias = nn.Linear(input_dim, 1)
+
+
 def _xavier_linear(m: nn.Module) -> None:
     if isinstance(m, nn.Linear):
         nn.init.xavier_uniform_(m.weight)
@@ -117,8 +175,6 @@ class _DynamicBase(nn.Module):
                  embed_dim: int = 128, num_layers: int = 1, num_heads: int = 4, generator_type: str = 'transformer',
                  rank_ratio: int = 4) -> None:
         super().__init__()
-        if generator_type != 'transformer':
-            raise NotImplementedError("generator_type='factorized' is outside the built hot path (SURVEY.md 8f-3)")
         if (kernel_size, stride, padding) != (3, 1, 1):
             raise NotImplementedError('dynamic conv kernels are built for kernel 3, stride 1, padding 1')
         self.kernel_size = kernel_size
@@ -131,8 +187,14 @@ class _DynamicBase(nn.Module):
         self.stride = stride
         self.padding = padding
         self.generator_type = generator_type
-        gen = TransformerWeightGenerator_decoder if self._decoder else TransformerWeightGenerator
-        self.weight_generator = gen(wv_planes, self._num_kernel, embed_dim, num_heads=num_heads, num_layers=num_layers)
+        if generator_type == 'factorized':  # dynamic_conv.py:412-421, 581-590
+            gen = FactorizedWeightGenerator_decoder if self._decoder else FactorizedWeightGenerator
+            self.weight_generator = gen(wv_planes, self._num_kernel, embed_dim, num_heads=num_heads,
+                                        num_layers=num_layers, rank_ratio=rank_ratio)
+        else:
+            gen = TransformerWeightGenerator_decoder if self._decoder else TransformerWeightGenerator
+            self.weight_generator = gen(wv_planes, self._num_kernel, embed_dim, num_heads=num_heads,
+                                        num_layers=num_layers)
         self.use_weight_standardization = False
         self.scaler = 0.1
         self.fclayer = FCResLayer(wv_planes)
@@ -158,6 +220,9 @@ class _DynamicBase(nn.Module):
         dev = g.weight_tokens.device
         wvs = wvs.to(device=dev, dtype=torch.float32)
         params = g.kernel_params(self.fclayer, self._omega_dev(dev))
+        if getattr(g, 'factorized', False):
+            return ops.hypernet_factorized_forward(wvs, params, g.num_layers, g.input_dim, g.num_heads, g.ff_dim,
+                                                   self.embed_dim, g.rank, self._decoder)[:2]
         return ops.hypernet_forward(wvs, params, g.num_layers, g.input_dim, g.num_heads, g.ff_dim, self.embed_dim,
                                     self._decoder)
 
@@ -166,6 +231,10 @@ class _DynamicBase(nn.Module):
         g = self.weight_generator
         dev = g.weight_tokens.device
         params = g.kernel_params(self.fclayer, self._omega_dev(dev))
+        if getattr(g, 'factorized', False):
+            return ops.hypernet_factorized_forward(wvs.to(device=dev, dtype=torch.float32), params, g.num_layers,
+                                                   g.input_dim, g.num_heads, g.ff_dim, self.embed_dim, g.rank,
+                                                   self._decoder)
         return ops.hypernet_forward_taped(wvs.to(device=dev, dtype=torch.float32), params, g.num_layers, g.input_dim,
                                           g.num_heads, g.ff_dim, self.embed_dim, self._decoder)
 
@@ -174,6 +243,12 @@ class _DynamicBase(nn.Module):
         g = self.weight_generator
         dev = g.weight_tokens.device
         params = g.kernel_params(self.fclayer, self._omega_dev(dev))
+        if getattr(g, 'factorized', False):
+            if tape is None:
+                tape = self._generate_taped(wvs)[2]
+            return ops.hypernet_factorized_backward(wvs.to(device=dev, dtype=torch.float32), params, g.num_layers,
+                                                    g.input_dim, g.num_heads, g.ff_dim, self.embed_dim, g.rank,
+                                                    self._decoder, dw_oihw, self.scaler, dbias, bias_scale, tape)
         return ops.hypernet_backward(wvs.to(device=dev, dtype=torch.float32), params, g.num_layers, g.input_dim, g.num_heads,
                                      g.ff_dim, self.embed_dim, self._decoder, dw_oihw, self.scaler, dbias, bias_scale, tape)
 

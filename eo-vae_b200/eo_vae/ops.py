@@ -619,6 +619,48 @@ def hypernet_backward(wvs: torch.Tensor, params: list, num_layers: int, d: int, 
     return grads[1:]
 
 
+def hypernet_factorized_forward(wvs: torch.Tensor, params: list, num_layers: int, d: int, heads: int, ff: int, embed: int,
+                                rank: int, decoder: bool):
+    """FactorizedWeightGenerator(_decoder): -> (wk [C, 9*embed], bias_raw, tape); the tape (activations) feeds
+    hypernet_factorized_backward.  Parameter order: see eovae_hypernet_factorized_forward (include/eovae.h)."""
+    _need_cuda(wvs, *params)
+    wvs = wvs.to(torch.float32).contiguous()
+    c = wvs.numel()
+    lib = _C.lib()
+    ws_bytes = lib.eovae_hypernet_factorized_workspace_bytes(c, d, ff, embed, rank, num_layers)
+    tape = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=wvs.device)
+    wk = torch.empty((c, 9 * embed), dtype=torch.float32, device=wvs.device)
+    bias = torch.empty((c if decoder else embed,), dtype=torch.float32, device=wvs.device)
+    arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    rc = lib.eovae_hypernet_factorized_forward(_ptr(wvs), c, arr, num_layers, d, heads, ff, embed, rank, 1 if decoder else 0,
+                                               _ptr(wk), _ptr(bias), _ptr(tape), ws_bytes, _stream())
+    _C.check(rc, "eovae_hypernet_factorized_forward")
+    return wk, bias, tape
+
+
+def hypernet_factorized_backward(wvs: torch.Tensor, params: list, num_layers: int, d: int, heads: int, ff: int, embed: int,
+                                 rank: int, decoder: bool, dw_oihw: torch.Tensor, w_scale: float, dbias: torch.Tensor,
+                                 bias_scale: float, tape: torch.Tensor) -> list:
+    """Gradients of params[1:] given the gradient of the generated kernel / bias; ``tape`` from the forward."""
+    _need_cuda(wvs, dw_oihw, dbias, tape, *params)
+    wvs = wvs.to(torch.float32).contiguous()
+    c = wvs.numel()
+    dw_oihw = dw_oihw.to(torch.float32).contiguous()
+    dbias = dbias.to(torch.float32).contiguous()
+    lib = _C.lib()
+    ws_bytes = lib.eovae_hypernet_factorized_workspace_bytes(c, d, ff, embed, rank, num_layers)
+    if tape.numel() * 4 < ws_bytes:
+        raise RuntimeError("hypernet_factorized_backward: tape does not belong to this configuration")
+    grads = [None] + [torch.empty_like(p) for p in params[1:]]
+    parr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    garr = (ctypes.c_void_p * len(params))(*[None if g is None else g.data_ptr() for g in grads])
+    rc = lib.eovae_hypernet_factorized_backward(_ptr(wvs), c, parr, num_layers, d, heads, ff, embed, rank,
+                                                1 if decoder else 0, _ptr(dw_oihw), dw_oihw.shape[1], float(w_scale),
+                                                _ptr(dbias), float(bias_scale), garr, _ptr(tape), ws_bytes, _stream())
+    _C.check(rc, "eovae_hypernet_factorized_backward")
+    return grads[1:]
+
+
 def pack_dyn_weight(wk: torch.Tensor, bias_raw: torch.Tensor, c: int, embed: int, decoder: bool, scale: float,
                     bias_scale: float, dtype, want_oihw: bool):
     """generated kernel -> (igemm B operand, scaled bias, optional fp32 OIHW weight)."""

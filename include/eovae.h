@@ -233,6 +233,24 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
 int eovae_hypernet_forward_taped(const float* wvs_um, int c, const float* const* params, int num_layers, int d, int heads,
                                  int ff, int embed, int decoder, float* wk_out, float* bias_out, void* workspace,
                                  size_t workspace_bytes, void* stream);
+/* ---- FactorizedWeightGenerator(_decoder) variant of the wavelength hypernetwork (dynamic_conv.py:186-302; selected by
+ * generator_type='factorized', configs/finetune_consistency_factor.yaml:55-73): pre-norm transformer layers
+ * (norm_first=True, ff = 4 d) and a low-rank head Linear(d, rank) -> GELU -> Linear(rank, 9 embed).  Outputs as
+ * eovae_hypernet_forward.  The forward always leaves its activations in `workspace`
+ * (eovae_hypernet_factorized_workspace_bytes) for eovae_hypernet_factorized_backward.  Dropout is not applied.
+ * params: 0 omega[d/2] | 1 weight_tokens | 2 bias_token | 3,4 fclayer.w1 (w,b) | 5,6 fclayer.w2 | 7,8 fc_weight.0
+ * [rank][d] | 9,10 fc_weight.2 [9 embed][rank] | 11,12 fc_bias | per layer (12): in_proj, out_proj, linear1, linear2,
+ * norm1, norm2 (w,b each) */
+size_t eovae_hypernet_factorized_workspace_bytes(int c, int d, int ff, int embed, int rank, int num_layers);
+int eovae_hypernet_factorized_forward(const float* wvs_um, int c, const float* const* params, int num_layers, int d,
+                                      int heads, int ff, int embed, int rank, int decoder, float* wk_out, float* bias_out,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+/* adjoint of the above + eovae_pack_dyn_weight (arguments as eovae_hypernet_backward); `workspace` must still hold the
+ * activations of eovae_hypernet_factorized_forward for the same inputs */
+int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* const* params, int num_layers, int d,
+                                       int heads, int ff, int embed, int rank, int decoder, const float* dw_oihw,
+                                       int dw_cin_ld, float w_scale, const float* dbias, float bias_scale,
+                                       float* const* grads, void* workspace, size_t workspace_bytes, void* stream);
 /* gradient of eovae_msssim's batch-mean value wrt pred (fp32 NCHW), times the device scalar *grad_scale; the forward
  * pyramid is rebuilt inside the workspace (consistency_loss.py:24-37 adjoint) */
 size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w);

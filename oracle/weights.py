@@ -23,6 +23,9 @@ FULL_CONFIG = dict(resolution=256, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=
 TINY_CONFIG = dict(resolution=64, ch=32, ch_mult=(1, 2, 2), num_res_blocks=1, z_channels=8,
                    hyper_layers=1, wv_planes=64, hyper_heads=4)
 
+# generator_type='factorized' (configs/finetune_consistency_factor.yaml:50-73: num_layers 4, rank_ratio 2) at toy width
+TINY_FACTORIZED_CONFIG = dict(TINY_CONFIG, hyper_layers=2, generator_type="factorized", rank_ratio=2)
+
 # eo_vae/datasets/terramesh_datamodule.py:18-50 (micrometres)
 WAVELENGTHS = {
     "S2RGB": [0.665, 0.56, 0.49],
@@ -54,7 +57,41 @@ def _attn(spec, p, c):
         spec[f"{p}.{n}.bias"] = (c,)
 
 
-def _hypernet(spec, p, d, embed, layers, decoder):
+def _hypernet_factorized(spec, p, d, embed, layers, decoder, rank_ratio):
+    """FactorizedWeightGenerator(_decoder) registration order (dynamic_conv.py:186-236, 267-285): transformer layers
+    (ff = 4 d), fc_weight.{0,2}, fc_bias; then fclayer."""
+    g = p + ".weight_generator"
+    rank = max(32, 9 * embed // rank_ratio)
+    spec[g + ".weight_tokens"] = (128, d)   # direct parameters precede submodules in a state_dict
+    spec[g + ".bias_token"] = (1, d)
+    for i in range(layers):
+        l = f"{g}.transformer_encoder.layers.{i}"
+        spec[l + ".self_attn.in_proj_weight"] = (3 * d, d)
+        spec[l + ".self_attn.in_proj_bias"] = (3 * d,)
+        spec[l + ".self_attn.out_proj.weight"] = (d, d)
+        spec[l + ".self_attn.out_proj.bias"] = (d,)
+        spec[l + ".linear1.weight"] = (4 * d, d)
+        spec[l + ".linear1.bias"] = (4 * d,)
+        spec[l + ".linear2.weight"] = (d, 4 * d)
+        spec[l + ".linear2.bias"] = (d,)
+        spec[l + ".norm1.weight"] = (d,)
+        spec[l + ".norm1.bias"] = (d,)
+        spec[l + ".norm2.weight"] = (d,)
+        spec[l + ".norm2.bias"] = (d,)
+    spec[g + ".fc_weight.0.weight"] = (rank, d)
+    spec[g + ".fc_weight.0.bias"] = (rank,)
+    spec[g + ".fc_weight.2.weight"] = (9 * embed, rank)
+    spec[g + ".fc_weight.2.bias"] = (9 * embed,)
+    spec[g + ".fc_bias.weight"] = (1 if decoder else embed, d)
+    spec[g + ".fc_bias.bias"] = (1 if decoder else embed,)
+    for w in ("w1", "w2"):
+        spec[f"{p}.fclayer.{w}.weight"] = (d, d)
+        spec[f"{p}.fclayer.{w}.bias"] = (d,)
+
+
+def _hypernet(spec, p, d, embed, layers, decoder, cfg=None):
+    if cfg is not None and cfg.get("generator_type", "transformer") == "factorized":
+        return _hypernet_factorized(spec, p, d, embed, layers, decoder, cfg.get("rank_ratio", 4))
     g = p + ".weight_generator"
     spec[g + ".weight_tokens"] = (128, d)
     spec[g + ".bias_token"] = (1, d)
@@ -88,7 +125,7 @@ def state_dict_spec(cfg: dict) -> "OrderedDict[str, tuple]":
     nres = len(mult)
     spec: OrderedDict[str, tuple] = OrderedDict()
     # ---- encoder (model.py:67-165)
-    _hypernet(spec, "encoder.conv_in", d, ch, hl, decoder=False)
+    _hypernet(spec, "encoder.conv_in", d, ch, hl, decoder=False, cfg=cfg)
     in_mult = (1,) + mult
     block_in = ch
     for lvl in range(nres):
@@ -133,7 +170,7 @@ def state_dict_spec(cfg: dict) -> "OrderedDict[str, tuple]":
         spec.update(up_specs[lvl])
     spec["decoder.norm_out.weight"] = (block_in,)
     spec["decoder.norm_out.bias"] = (block_in,)
-    _hypernet(spec, "decoder.conv_out", d, block_in, hl, decoder=True)
+    _hypernet(spec, "decoder.conv_out", d, block_in, hl, decoder=True, cfg=cfg)
     # ---- latent BatchNorm (new_autoencoder.py:125)
     spec["bn.running_mean"] = (4 * zc,)
     spec["bn.running_var"] = (4 * zc,)

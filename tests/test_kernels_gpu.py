@@ -320,3 +320,65 @@ def test_hypernet(cuda, modality, cfg_name):
     w, b = model.decoder.conv_out.get_distillation_weight(wvs.to(cuda))
     assert _rel(w.cpu(), w_ref) < 2e-4
     assert _rel(b.cpu(), b_ref * 10.0) < 2e-4  # get_distillation_weight scales the bias once (x0.1), forward twice
+
+
+@pytest.mark.parametrize("modality", ["S2RGB", "S1RTC", "S2L2A", "S2L1C"])
+@pytest.mark.parametrize("cfg_name", ["tiny", "full"])
+def test_hypernet_factorized(cuda, modality, cfg_name):
+    """generator_type='factorized' (FactorizedWeightGenerator(_decoder), dynamic_conv.py:186-302: pre-norm layers,
+    low-rank head): generated kernels / biases vs the CPU oracle (fp32 both sides; oracle pinned against the reference
+    in tests/test_oracle_vs_reference.py)."""
+    import __graft_entry__ as g
+    from oracle import eovae_oracle as O
+    from oracle.weights import FULL_CONFIG, TINY_FACTORIZED_CONFIG, WAVELENGTHS, make_state_dict
+    cfg = TINY_FACTORIZED_CONFIG if cfg_name == "tiny" else dict(FULL_CONFIG, generator_type="factorized", rank_ratio=2)
+    sd = make_state_dict(cfg, 1)
+    model = g._model(cfg, sd, cuda)
+    assert type(model.encoder.conv_in.weight_generator).__name__ == "FactorizedWeightGenerator"
+    wvs = torch.tensor(WAVELENGTHS[modality])
+    w_ref, b_ref = O.hypernet(sd, "encoder.conv_in", wvs, False, cfg["hyper_heads"])
+    w, b = model.encoder.conv_in.get_distillation_weight(wvs.to(cuda))
+    assert _rel(w.cpu(), w_ref) < 2e-4 and _rel(b.cpu(), b_ref) < 2e-4
+    w_ref, b_ref = O.hypernet(sd, "decoder.conv_out", wvs, True, cfg["hyper_heads"])
+    w, b = model.decoder.conv_out.get_distillation_weight(wvs.to(cuda))
+    assert _rel(w.cpu(), w_ref) < 2e-4
+    assert _rel(b.cpu(), b_ref * 10.0) < 2e-4
+
+
+def test_factorized_model_forward_and_gradients(cuda):
+    """Whole tiny model with factorized generators: latents / reconstruction (bf16 path) and, in train mode, every
+    hypernetwork parameter gradient (fp32 kernels end to end) vs autograd over the oracle."""
+    import __graft_entry__ as g
+    from oracle import eovae_oracle as O
+    from oracle.weights import TINY_FACTORIZED_CONFIG, WAVELENGTHS, make_state_dict, synthetic_patches
+    cfg = TINY_FACTORIZED_CONFIG
+    sd = make_state_dict(cfg, 4)
+    model = g._model(cfg, sd, cuda)
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"])
+    x = synthetic_patches(2, 12, cfg["resolution"], seed=21)
+    with torch.no_grad():
+        z = model.encode_spatial_normalized(x.to(cuda), wvs.to(cuda))
+        r = model.reconstruct(x.to(cuda), wvs.to(cuda))
+    z_ref = O.encode_spatial_normalized(sd, x, wvs, cfg["hyper_heads"])
+    r_ref = O.reconstruct(sd, x, wvs, cfg["hyper_heads"])
+    print(f"factorized tiny: latent {_rel(z.cpu(), z_ref):.3e} recon {_rel(r.cpu(), r_ref):.3e}")
+    assert _rel(z.cpu(), z_ref) < 1.5e-2 and _rel(r.cpu(), r_ref) < 4e-2
+    # gradients: deterministic forward (mode of the posterior), Charbonnier loss
+    model.train()
+    recon, _ = model(x.to(cuda), wvs.to(cuda), sample_posterior=False)
+    torch.sqrt((recon - x.to(cuda)) ** 2 + 1e-6).mean().backward()
+    osd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    rr, _ = O.forward(osd, x, wvs, None, True, cfg["hyper_heads"])
+    O.charbonnier_loss(rr, x).backward()
+    got, want = [], []
+    for name, p in model.named_parameters():
+        if "weight_generator" in name or "fclayer" in name:
+            assert p.grad is not None, name
+            got.append(p.grad.flatten().float().cpu())
+            want.append(osd[name].grad.flatten())
+    assert len(got) > 60
+    for side in ("encoder.conv_in", "decoder.conv_out"):
+        a = torch.cat([p.grad.flatten().float().cpu() for n, p in model.named_parameters() if n.startswith(side)])
+        b = torch.cat([osd[n].grad.flatten() for n, p in model.named_parameters() if n.startswith(side)])
+        print(f"factorized hypernet gradients {side}: rel-L2 {_rel(a, b):.3e}")
+        assert _rel(a, b) < 6e-2, (side, _rel(a, b))

@@ -5,12 +5,16 @@ import torch
 
 from oracle import eovae_oracle as O
 from oracle import ref_shim
-from oracle.weights import FULL_CONFIG, TINY_CONFIG, WAVELENGTHS, make_state_dict, state_dict_spec, synthetic_patches
+from oracle.weights import FULL_CONFIG, TINY_CONFIG, TINY_FACTORIZED_CONFIG, WAVELENGTHS, make_state_dict, state_dict_spec, synthetic_patches
 
 pytestmark = pytest.mark.skipif(ref_shim.reference_root() is None, reason="reference tree not available")
 
 
-@pytest.mark.parametrize("cfg", [TINY_CONFIG, FULL_CONFIG], ids=["tiny", "full"])
+FULL_FACTORIZED_CONFIG = dict(FULL_CONFIG, generator_type="factorized", rank_ratio=2)  # finetune_consistency_factor.yaml
+
+
+@pytest.mark.parametrize("cfg", [TINY_CONFIG, FULL_CONFIG, TINY_FACTORIZED_CONFIG, FULL_FACTORIZED_CONFIG],
+                         ids=["tiny", "full", "tiny-factorized", "full-factorized"])
 def test_state_dict_layout(cfg):
     model = ref_shim.build_reference_model(cfg)
     ref_sd = model.state_dict()
@@ -37,6 +41,45 @@ def test_oracle_equals_reference_live(modality):
     assert torch.allclose(z, z_ref, atol=2e-5) and torch.allclose(r, r_ref, atol=5e-5)
     assert torch.allclose(O.posterior_kl(m), post.kl(), rtol=1e-5)
     assert torch.allclose(O.posterior(m)[1], post.logvar, atol=2e-5)
+
+
+@pytest.mark.parametrize("modality", ["S2RGB", "S1RTC", "S2L2A"])
+def test_factorized_generator_oracle_equals_reference(modality):
+    """generator_type='factorized' (dynamic_conv.py:186-302): generated kernels / biases of both dynamic layers, latents
+    and reconstructions, and (eval mode, dropout off) every hypernetwork parameter gradient vs reference autograd."""
+    cfg = TINY_FACTORIZED_CONFIG
+    sd = make_state_dict(cfg, 8)
+    model = ref_shim.build_reference_model(cfg, sd, train=False)
+    wvs = torch.tensor(WAVELENGTHS[modality])
+    x = synthetic_patches(2, len(wvs), 32, seed=80)
+    with torch.no_grad():
+        w_ref, b_ref = model.encoder.conv_in.get_distillation_weight(wvs)
+        w, b = O.hypernet(sd, "encoder.conv_in", wvs, decoder=False, heads=cfg["hyper_heads"])
+        assert torch.allclose(w, w_ref, atol=1e-5) and torch.allclose(b, b_ref, atol=1e-5)
+        w_ref, b_ref = model.decoder.conv_out.get_distillation_weight(wvs)
+        w, b = O.hypernet(sd, "decoder.conv_out", wvs, decoder=True, heads=cfg["hyper_heads"])
+        # get_distillation_weight scales the decoder bias once (:660), the forward twice (:692-697)
+        assert torch.allclose(w, w_ref, atol=1e-5) and torch.allclose(b * 10.0, b_ref.reshape(-1), atol=1e-5)
+        z_ref = model.encode_spatial_normalized(x, wvs)
+        r_ref = model.reconstruct(x, wvs)
+        z = O.encode_spatial_normalized(sd, x, wvs, cfg["hyper_heads"])
+        r = O.reconstruct(sd, x, wvs, cfg["hyper_heads"])
+    assert torch.allclose(z, z_ref, atol=2e-5) and torch.allclose(r, r_ref, atol=5e-5)
+    # gradients (eval mode: deterministic)
+    r_ref = model(x, wvs, sample_posterior=False)[0]       # reconstruct() itself runs under no_grad
+    torch.sqrt((r_ref - x) ** 2 + 1e-6).mean().backward()
+    osd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    O.charbonnier_loss(O.forward(osd, x, wvs, None, False, cfg["hyper_heads"])[0], x).backward()
+    floor = 1e-6 * max(float(p.grad.abs().max()) for p in model.parameters() if p.grad is not None)
+    checked = 0
+    for name, p in model.named_parameters():
+        if "weight_generator" not in name and "fclayer" not in name:
+            continue
+        got = osd[name].grad
+        assert got is not None and p.grad is not None, name
+        assert float((got - p.grad).abs().max()) < 2e-4 * float(p.grad.abs().max()) + floor, name
+        checked += 1
+    assert checked > 60
 
 
 def test_train_mode_forward_matches_reference():

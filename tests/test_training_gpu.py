@@ -94,16 +94,19 @@ def test_resample_gradients(cuda, kind):
     _check_module(mod, O.upsample if kind == "up" else O.downsample, _act(2, 64, 16, 16, cuda, 6), cuda)
 
 
+@pytest.mark.parametrize("generator", ["transformer", "factorized"])
 @pytest.mark.parametrize("decoder", [False, True])
 @pytest.mark.parametrize("modality", ["S2L2A", "S1RTC"])
-def test_hypernet_backward(cuda, decoder, modality):
-    """eovae_hypernet_backward (full-size generator: d 256, 4 layers, 4 heads, ff 2048) vs autograd over the oracle."""
+def test_hypernet_backward(cuda, decoder, modality, generator):
+    """eovae_hypernet_backward / eovae_hypernet_factorized_backward (full-size generator: d 256, 4 layers, 4 heads, ff 2048
+    / 1024 + rank-576 head) vs autograd over the oracle, fp32 on both sides."""
     from eo_vae.models.modules.dynamic_conv import DynamicConv, DynamicConv_decoder
     from oracle import eovae_oracle as O
     from oracle.weights import WAVELENGTHS
     torch.manual_seed(7)
     cls = DynamicConv_decoder if decoder else DynamicConv
-    mod = cls(wv_planes=256, inter_dim=128, kernel_size=3, stride=1, padding=1, embed_dim=128, num_layers=4, num_heads=4).to(cuda)
+    mod = cls(wv_planes=256, inter_dim=128, kernel_size=3, stride=1, padding=1, embed_dim=128, num_layers=4, num_heads=4,
+              generator_type=generator, rank_ratio=2).to(cuda).eval()
     wvs = torch.tensor(WAVELENGTHS[modality], dtype=torch.float32, device=cuda)
     c, e = wvs.numel(), 128
     g = torch.Generator().manual_seed(3)

@@ -46,6 +46,11 @@ SIGNATURES = {
     "eovae_hypernet_factorized_forward": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "eovae_hypernet_factorized_backward": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _f, _vp, _vp,
                                                 _sz, _vp]),
+    "eovae_wavelength_style_workspace_bytes": (_sz, [_i]),
+    "eovae_wavelength_style_forward": (_i, [_vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "eovae_wavelength_style_backward": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "eovae_adain_affine_forward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "eovae_adain_affine_backward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "eovae_msssim_backward_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "eovae_msssim_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "eovae_conv2d_wgrad_nhwc_ok": (_i, [_i, _i]),

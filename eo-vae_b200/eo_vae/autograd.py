@@ -431,3 +431,38 @@ class LatentTrainFn(Function):
                                                          save.data_ptr(), dz.data_ptr(), ops._stream()),
                  "eovae_latent_bn_train_backward")
         return dz, None, None, None
+
+
+class WavelengthStyleFn(Function):
+    """WavelengthConditioner (model.py:35-64): wavelengths -> style row [1, d] on eovae_wavelength_style_forward/backward."""
+
+    @staticmethod
+    def forward(ctx, wvs, omega, *mlp):
+        params = [omega] + [p.detach() for p in mlp]
+        style, tape_ws = ops.wavelength_style_forward(wvs, params, omega.numel() * 2)
+        ctx.save_for_backward(tape_ws, omega, *mlp)
+        return style
+
+    @staticmethod
+    def backward(ctx, dstyle):
+        tape_ws, omega, *mlp = ctx.saved_tensors
+        grads = ops.wavelength_style_backward([omega] + [p.detach() for p in mlp], omega.numel() * 2, dstyle, tape_ws)
+        return (None, None) + tuple(grads)
+
+
+class AdaINAffineFn(Function):
+    """(style, emb_proj, norm2 affine) -> modulated GroupNorm affine gamma*scale, beta*scale + shift (layers.py:96-104)."""
+
+    @staticmethod
+    def forward(ctx, style, wproj, bproj, gamma, beta):
+        g_out, b_out, style2 = ops.adain_affine_forward(style.detach().contiguous(), wproj.detach(), bproj.detach(),
+                                                        gamma.detach(), beta.detach())
+        ctx.save_for_backward(style, wproj, gamma, beta, style2)
+        return g_out, b_out
+
+    @staticmethod
+    def backward(ctx, dg_out, db_out):
+        style, wproj, gamma, beta, style2 = ctx.saved_tensors
+        dgamma, dbeta, dw, dbp, dstyle = ops.adain_affine_backward(style.detach().contiguous(), wproj.detach(), gamma.detach(),
+                                                                   beta.detach(), style2, dg_out, db_out)
+        return dstyle.view_as(style), dw, dbp, dgamma, dbeta

@@ -14,7 +14,7 @@ from torch import Tensor
 from .. import autograd as tape
 from .. import ops
 from ..settings import compute_dtype
-from .modules.dynamic_conv import DynamicConv, DynamicConv_decoder
+from .modules.dynamic_conv import DynamicConv, DynamicConv_decoder, _omega_table
 from .modules.layers import AttnBlock, Conv2dSM100, Downsample, GroupNormSM100, ResnetBlock, Upsample
 
 
@@ -22,12 +22,50 @@ def swish(x: Tensor) -> Tensor:
     return x * torch.sigmoid(x)
 
 
+def get_1d_sincos_pos_embed(embed_dim: int, pos: Tensor) -> Tensor:
+    """[N] or [B, N] positions -> [B, N, D] (sin | cos) embedding (model.py:17-32).  Host/torch utility kept for API
+    parity; the CUDA path evaluates the same formula inside eovae_wavelength_style_forward."""
+    if pos.dim() == 1:
+        pos = pos.unsqueeze(0)
+    out = torch.einsum('bn,d->bnd', pos.float(), _omega_table(embed_dim).to(pos.device))
+    return torch.cat([torch.sin(out), torch.cos(out)], dim=2)
+
+
+class WavelengthConditioner(nn.Module):
+    """Wavelength set -> global AdaIN style vector (model.py:35-64): mean over bands of the sincos embedding (wavelengths
+    in micrometres, unscaled), then Linear(d, 2d) -> SiLU -> Linear(2d, d) -> SiLU -> Linear(d, d), computed by
+    eovae_wavelength_style_forward/backward.  The style is a function of the wavelength vector only, so one row is
+    computed and returned as an expanded [batch_size, d] view (the reference materialises the repeat)."""
+
+    def __init__(self, embed_dim: int = 512):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.mlp = nn.Sequential(nn.Linear(embed_dim, embed_dim * 2), nn.SiLU(), nn.Linear(embed_dim * 2, embed_dim),
+                                 nn.SiLU(), nn.Linear(embed_dim, embed_dim))
+        self._omega = None
+
+    def forward(self, wvs: Tensor, batch_size: int) -> Tensor:
+        if wvs.dim() != 1:
+            raise RuntimeError('WavelengthConditioner: one wavelength vector per batch ([N]) on the sm_100a path')
+        dev = self.mlp[0].weight.device
+        if self._omega is None or self._omega.device != dev:
+            self._omega = _omega_table(self.embed_dim).to(dev)
+        ps = [self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight, self.mlp[2].bias, self.mlp[4].weight,
+              self.mlp[4].bias]
+        wvs = wvs.to(device=dev, dtype=torch.float32)
+        if tape.grad_mode():
+            style = tape.WavelengthStyleFn.apply(wvs, self._omega, *ps)
+        else:
+            style = ops.wavelength_style_forward(wvs, [self._omega] + [p.detach() for p in ps], self.embed_dim)[0]
+        return style.expand(batch_size, -1)
+
+
 def _split_dynamic_kwargs(dynamic_conv_kwargs):
+    """-> (use_adain, wv_planes, inter_dim, kwargs passed on to the dynamic layer)   (model.py:94-104, 248-251, 299-308)"""
     kw = dict(dynamic_conv_kwargs) if dynamic_conv_kwargs else {}
-    if kw.pop('use_adain', False):
-        raise NotImplementedError('use_adain (WavelengthConditioner) is outside the built hot path (SURVEY.md 8f-3)')
+    use_adain = bool(kw.pop('use_adain', False))
     kw.pop('mode', 'conv')
-    return kw.pop('wv_planes', 128), kw.pop('inter_dim', 128), kw
+    return use_adain, kw.pop('wv_planes', 128), kw.pop('inter_dim', 128), kw
 
 
 class Encoder(nn.Module):
@@ -44,7 +82,10 @@ class Encoder(nn.Module):
         self.use_adain = False
         self.cond_dim = None
         if use_dynamic_ops:
-            wv_planes, inter_dim, rest = _split_dynamic_kwargs(dynamic_conv_kwargs)
+            self.use_adain, wv_planes, inter_dim, rest = _split_dynamic_kwargs(dynamic_conv_kwargs)
+            if self.use_adain:
+                self.cond_dim = 512
+                self.conditioner = WavelengthConditioner(embed_dim=self.cond_dim)
             self.conv_in = DynamicConv(wv_planes=wv_planes, inter_dim=inter_dim, kernel_size=3, stride=1, padding=1,
                                        embed_dim=ch, **rest)
         else:
@@ -60,34 +101,37 @@ class Encoder(nn.Module):
             block_in = ch * in_ch_mult[lvl]
             block_out = ch * ch_mult[lvl]
             for _ in range(num_res_blocks):
-                stage.block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, cond_dim=None))
+                stage.block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, cond_dim=self.cond_dim))
                 block_in = block_out
             if lvl != self.num_resolutions - 1:
                 stage.downsample = Downsample(block_in)
             self.down.append(stage)
         self.mid = nn.Module()
-        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, cond_dim=None)
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, cond_dim=self.cond_dim)
         self.mid.attn_1 = AttnBlock(block_in)
-        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, cond_dim=None)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, cond_dim=self.cond_dim)
         self.norm_out = GroupNormSM100(num_groups=32, num_channels=block_in, eps=1e-6, affine=True)
         self.conv_out = Conv2dSM100(block_in, 2 * z_channels, kernel_size=3, stride=1, padding=1)
         self.quant_conv = Conv2dSM100(2 * z_channels, 2 * z_channels, 1)
 
     def moments_nhwc(self, x: Tensor, wvs: Tensor = None) -> Tensor:
         """fp32 moments, logical [B, 2z, H/8, W/8] with NHWC storage (what the fused latent kernels consume)."""
+        emb = None
         if self.use_dynamic_ops:
             assert wvs is not None, 'wvs must be provided for Dynamic Encoder'
+            if self.use_adain:
+                emb = self.conditioner(wvs, x.shape[0])
             h = self.conv_in(x, wvs)
         else:
             h = self.conv_in(ops.nchw_to_act(x, (x.shape[1] + 15) // 16 * 16, compute_dtype()))
         for lvl, stage in enumerate(self.down):
             for block in stage.block:
-                h = block(h)
+                h = block(h, emb)
             if lvl != self.num_resolutions - 1:
                 h = stage.downsample(h)
-        h = self.mid.block_1(h)
+        h = self.mid.block_1(h, emb)
         h = self.mid.attn_1(h)
-        h = self.mid.block_2(h)
+        h = self.mid.block_2(h, emb)
         h = self.conv_out(self.norm_out(h, silu=True))
         return self.quant_conv(h, out_dtype=torch.float32)
 
@@ -96,7 +140,7 @@ class Encoder(nn.Module):
 
     def load_flux_weights(self, state_dict, strict=True):
         own = self.state_dict()
-        skip = ['conv_in'] if self.use_dynamic_ops else []
+        skip = (['conv_in'] if self.use_dynamic_ops else []) + (['conditioner', 'emb_proj'] if self.use_adain else [])
         for name, param in state_dict.items():
             if any(s in name for s in skip):
                 continue
@@ -121,15 +165,18 @@ class Decoder(nn.Module):
         self.use_adain = False
         self.cond_dim = None
         if use_dynamic_ops:
-            wv_planes, inter_dim, rest = _split_dynamic_kwargs(dynamic_conv_kwargs)
+            self.use_adain, wv_planes, inter_dim, rest = _split_dynamic_kwargs(dynamic_conv_kwargs)
+            if self.use_adain:
+                self.cond_dim = 512
+                self.conditioner = WavelengthConditioner(embed_dim=self.cond_dim)
         block_in = ch * ch_mult[self.num_resolutions - 1]
         curr_res = resolution // 2 ** (self.num_resolutions - 1)
         self.z_shape = (1, z_channels, curr_res, curr_res)
         self.conv_in = Conv2dSM100(z_channels, block_in, kernel_size=3, stride=1, padding=1)
         self.mid = nn.Module()
-        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, cond_dim=None)
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, cond_dim=self.cond_dim)
         self.mid.attn_1 = AttnBlock(block_in)
-        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, cond_dim=None)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, cond_dim=self.cond_dim)
         self.up = nn.ModuleList()
         for lvl in reversed(range(self.num_resolutions)):
             stage = nn.Module()
@@ -137,7 +184,7 @@ class Decoder(nn.Module):
             stage.attn = nn.ModuleList()
             block_out = ch * ch_mult[lvl]
             for _ in range(num_res_blocks + 1):
-                stage.block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, cond_dim=None))
+                stage.block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, cond_dim=self.cond_dim))
                 block_in = block_out
             if lvl != 0:
                 stage.upsample = Upsample(block_in)
@@ -152,12 +199,16 @@ class Decoder(nn.Module):
     def forward_act(self, z: Tensor, wvs: Tensor = None) -> Tensor:
         """z: activation (NHWC 16-bit) or any [B, z, h, w] tensor -> fp32 NHWC-stored reconstruction."""
         h = self.conv_in(self.post_quant_conv(z), gn_next=True)
-        h = self.mid.block_1(h)
+        emb = None
+        if self.use_dynamic_ops and self.use_adain:
+            assert wvs is not None
+            emb = self.conditioner(wvs, z.shape[0])
+        h = self.mid.block_1(h, emb)
         h = self.mid.attn_1(h)
-        h = self.mid.block_2(h)
+        h = self.mid.block_2(h, emb)
         for lvl in reversed(range(self.num_resolutions)):
             for block in self.up[lvl].block:
-                h = block(h)
+                h = block(h, emb)
             if lvl != 0:
                 h = self.up[lvl].upsample(h)
         h = self.norm_out(h, silu=True)
@@ -171,7 +222,7 @@ class Decoder(nn.Module):
 
     def load_flux_weights(self, state_dict, strict=True):
         own = self.state_dict()
-        skip = ['conv_out'] if self.use_dynamic_ops else []
+        skip = (['conv_out'] if self.use_dynamic_ops else []) + (['conditioner', 'emb_proj'] if self.use_adain else [])
         for name, param in state_dict.items():
             if any(s in name for s in skip) or name not in own:
                 continue

@@ -38,6 +38,16 @@ class GroupNormSM100(nn.GroupNorm):
         return ops.group_norm(x, self.weight, self.bias, silu, self.num_groups, self.eps)
 
 
+class _ModulatedNorm:
+    """GroupNormSM100 stand-in whose affine is the AdaIN-modulated (gamma', beta') of one forward call."""
+
+    def __init__(self, norm: GroupNormSM100, weight: Tensor, bias: Tensor):
+        self.weight, self.bias, self.num_groups, self.eps = weight, bias, norm.num_groups, norm.eps
+
+    def __call__(self, x: Tensor, silu: bool = False) -> Tensor:
+        return ops.group_norm(ops.to_act(x, compute_dtype()), self.weight, self.bias, silu, self.num_groups, self.eps)
+
+
 class Conv2dSM100(nn.Conv2d):
     """nn.Conv2d parameter container (same init, same state_dict keys) executed by eovae_conv2d.
 
@@ -131,7 +141,7 @@ class ResnetBlock(nn.Module):
         self.cond_dim = cond_dim
         self.norm1 = GroupNormSM100(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
         self.conv1 = Conv2dSM100(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
-        if self.cond_dim is not None:  # AdaIN projection: parameters kept for checkpoint parity
+        if self.cond_dim is not None:  # AdaIN projection, initialised to identity (layers.py:68-76)
             self.emb_proj = nn.Linear(cond_dim, out_channels * 2)
             nn.init.zeros_(self.emb_proj.bias)
             self.emb_proj.weight.data.zero_()
@@ -155,20 +165,35 @@ class ResnetBlock(nn.Module):
             self._fused, self._fused_key = (w, b), key
         return self._fused
 
+    def _norm2_affine(self, emb: Tensor | None):
+        """norm2's affine, modulated by the AdaIN style when given (layers.py:96-107).  ``emb`` is the conditioner's
+        [B, cond_dim] output; its rows are identical (the style is a function of the wavelength vector), row 0 is used."""
+        if self.cond_dim is None or emb is None:
+            return self.norm2.weight, self.norm2.bias
+        if emb.dim() != 2 or emb.shape[1] != self.cond_dim:
+            raise RuntimeError(f"ResnetBlock: emb must be [B, {self.cond_dim}], got {tuple(emb.shape)}")
+        style = emb[:1]
+        if tape.grad_mode():
+            return tape.AdaINAffineFn.apply(style, self.emb_proj.weight, self.emb_proj.bias, self.norm2.weight,
+                                            self.norm2.bias)
+        return ops.adain_affine_forward(style.detach().contiguous(), self.emb_proj.weight.detach(),
+                                        self.emb_proj.bias.detach(), self.norm2.weight.detach(),
+                                        self.norm2.bias.detach())[:2]
+
     def forward(self, x: Tensor, emb: Tensor | None = None) -> Tensor:
-        if self.cond_dim is not None and emb is not None:
-            raise NotImplementedError("AdaIN-conditioned ResnetBlock (use_adain) is outside the built hot path")
         x = ops.to_act(x, compute_dtype())
+        g2, b2 = self._norm2_affine(emb)
         if tape.grad_mode():
             sc = getattr(self, 'nin_shortcut', None)
             return tape.ResnetBlockFn.apply(x, self.norm1.weight, self.norm1.bias, self.conv1.weight, self.conv1.bias,
-                                            self.norm2.weight, self.norm2.bias, self.conv2.weight, self.conv2.bias,
+                                            g2, b2, self.conv2.weight, self.conv2.bias,
                                             None if sc is None else sc.weight, None if sc is None else sc.bias, self)
         h = self.conv1(x, gn_next=True, pre_norm=self.norm1)  # GN1 + SiLU inside the conv where the shape allows
+        norm2 = self.norm2 if g2 is self.norm2.weight else _ModulatedNorm(self.norm2, g2, b2)
         if self.in_channels == self.out_channels:
             # GN2 + SiLU in the prologue, residual add + next GN's statistics in the epilogue
-            return self.conv2(h, residual=x, gn_next=True, pre_norm=self.norm2)
-        h = self.norm2(h, silu=True)
+            return self.conv2(h, residual=x, gn_next=True, pre_norm=norm2)
+        h = norm2(h, silu=True)
         if self.in_channels % 64 == 0 and self.out_channels % 64 == 0:
             # 1x1 shortcut folded into conv2's K loop: no shortcut tensor is written or re-read
             w, b = self._conv2_with_shortcut(x.dtype)

@@ -661,6 +661,66 @@ def hypernet_factorized_backward(wvs: torch.Tensor, params: list, num_layers: in
     return grads[1:]
 
 
+def wavelength_style_forward(wvs: torch.Tensor, params: list, d: int):
+    """WavelengthConditioner (model.py:35-64): -> (style [1, d] fp32, tape).  params: omega, mlp.0/2/4 (w, b)."""
+    _need_cuda(wvs, *params)
+    wvs = wvs.to(torch.float32).contiguous()
+    lib = _C.lib()
+    ws_bytes = lib.eovae_wavelength_style_workspace_bytes(d)
+    tape = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=wvs.device)
+    style = torch.empty((1, d), dtype=torch.float32, device=wvs.device)
+    arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    _C.check(lib.eovae_wavelength_style_forward(_ptr(wvs), wvs.numel(), arr, d, _ptr(style), _ptr(tape), ws_bytes, _stream()),
+             "eovae_wavelength_style_forward")
+    return style, tape
+
+
+def wavelength_style_backward(params: list, d: int, dstyle: torch.Tensor, tape: torch.Tensor) -> list:
+    """-> gradients of params[1:] (mlp.0/2/4 weights and biases)."""
+    _need_cuda(dstyle, tape, *params)
+    dstyle = dstyle.to(torch.float32).contiguous()
+    lib = _C.lib()
+    grads = [None] + [torch.empty_like(p) for p in params[1:]]
+    parr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    garr = (ctypes.c_void_p * len(params))(*[None if g is None else g.data_ptr() for g in grads])
+    _C.check(lib.eovae_wavelength_style_backward(parr, d, _ptr(dstyle), garr, _ptr(tape), tape.numel() * 4, _stream()),
+             "eovae_wavelength_style_backward")
+    return grads[1:]
+
+
+def adain_affine_forward(style: torch.Tensor, wproj: torch.Tensor, bproj: torch.Tensor, gamma: torch.Tensor,
+                         beta: torch.Tensor):
+    """[scale | shift] = emb_proj(style); -> (gamma * scale, beta * scale + shift, style2) (layers.py:96-104 folded)."""
+    _need_cuda(style, wproj, bproj, gamma, beta)
+    cout, d = gamma.numel(), style.numel()
+    if tuple(wproj.shape) != (2 * cout, d):
+        raise RuntimeError(f"adain_affine: emb_proj weight {tuple(wproj.shape)} does not match ({2 * cout}, {d})")
+    g_out, b_out = torch.empty_like(gamma), torch.empty_like(beta)
+    style2 = torch.empty((2 * cout,), dtype=torch.float32, device=style.device)
+    _C.check(_C.lib().eovae_adain_affine_forward(_ptr(style), d, _ptr(wproj), _ptr(bproj), _ptr(gamma), _ptr(beta), cout,
+                                                 _ptr(g_out), _ptr(b_out), _ptr(style2), _stream()),
+             "eovae_adain_affine_forward")
+    return g_out, b_out, style2
+
+
+def adain_affine_backward(style, wproj, gamma, beta, style2, dg_out, db_out):
+    """-> (dgamma, dbeta, dwproj, dbproj, dstyle [1, d])."""
+    _need_cuda(style, wproj, gamma, beta, style2, dg_out, db_out)
+    cout, d = gamma.numel(), style.numel()
+    dg_out = dg_out.to(torch.float32).contiguous()
+    db_out = db_out.to(torch.float32).contiguous()
+    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+    dw = torch.empty_like(wproj)
+    dbp = torch.empty((2 * cout,), dtype=torch.float32, device=style.device)
+    dstyle = torch.empty((1, d), dtype=torch.float32, device=style.device)
+    dstyle2 = torch.empty((2 * cout,), dtype=torch.float32, device=style.device)
+    _C.check(_C.lib().eovae_adain_affine_backward(_ptr(style), d, _ptr(wproj), _ptr(gamma), _ptr(beta), _ptr(style2), cout,
+                                                  _ptr(dg_out), _ptr(db_out), _ptr(dgamma), _ptr(dbeta), _ptr(dw), _ptr(dbp),
+                                                  _ptr(dstyle), _ptr(dstyle2), _stream()),
+             "eovae_adain_affine_backward")
+    return dgamma, dbeta, dw, dbp, dstyle
+
+
 def pack_dyn_weight(wk: torch.Tensor, bias_raw: torch.Tensor, c: int, embed: int, decoder: bool, scale: float,
                     bias_scale: float, dtype, want_oihw: bool):
     """generated kernel -> (igemm B operand, scaled bias, optional fp32 OIHW weight)."""

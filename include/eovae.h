@@ -251,6 +251,27 @@ int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* 
                                        int heads, int ff, int embed, int rank, int decoder, const float* dw_oihw,
                                        int dw_cin_ld, float w_scale, const float* dbias, float bias_scale,
                                        float* const* grads, void* workspace, size_t workspace_bytes, void* stream);
+/* ---- AdaIN conditioning of the ResnetBlocks (use_adain=True in dynamic_conv_kwargs; model.py:96-100, 173-191, 331-343) --
+ * WavelengthConditioner.forward (model.py:35-64): style[d] = mlp(mean over bands of sincos(wvs)), mlp = Linear(d, 2d) ->
+ * SiLU -> Linear(2d, d) -> SiLU -> Linear(d, d); wvs in micrometres (no x1000 here).  The style depends on the wavelength
+ * vector only, so one row is computed (the reference repeats it over the batch).
+ * params: 0 omega[d/2] | 1,2 mlp.0 (w,b) | 3,4 mlp.2 | 5,6 mlp.4.  The forward leaves its activations in `workspace`
+ * (eovae_wavelength_style_workspace_bytes) for the backward; grads[i] <- d/d params[i] (written; grads[0] unused). */
+size_t eovae_wavelength_style_workspace_bytes(int d);
+int eovae_wavelength_style_forward(const float* wvs_um, int c, const float* const* params, int d, float* style,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+int eovae_wavelength_style_backward(const float* const* params, int d, const float* dstyle, float* const* grads,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+/* ResnetBlock AdaIN (layers.py:68-76, 96-104): [scale | shift] = emb_proj(style); GroupNorm(h)*gamma+beta followed by
+ * *scale + shift is the same GroupNorm with gamma' = gamma*scale, beta' = beta*scale + shift, which is what the
+ * GroupNorm-apply / conv-prologue kernels then consume.  style2 [2 cout] keeps emb_proj's output for the backward.
+ * Backward: dgamma_out / dbeta_out are the (batch-summed) affine gradients of the GroupNorm backward kernel. */
+int eovae_adain_affine_forward(const float* style, int d, const float* wproj, const float* bproj, const float* gamma,
+                               const float* beta, int cout, float* gamma_out, float* beta_out, float* style2, void* stream);
+int eovae_adain_affine_backward(const float* style, int d, const float* wproj, const float* gamma, const float* beta,
+                                const float* style2, int cout, const float* dgamma_out, const float* dbeta_out,
+                                float* dgamma, float* dbeta, float* dwproj, float* dbproj, float* dstyle, float* dstyle2,
+                                void* stream);
 /* gradient of eovae_msssim's batch-mean value wrt pred (fp32 NCHW), times the device scalar *grad_scale; the forward
  * pyramid is rebuilt inside the workspace (consistency_loss.py:24-37 adjoint) */
 size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w);

@@ -109,6 +109,8 @@ def build_reference_model(cfg: dict, state_dict=None, train: bool = False):
     dyn = dict(num_layers=cfg["hyper_layers"], wv_planes=cfg["wv_planes"], num_heads=cfg["hyper_heads"])
     if cfg.get("generator_type", "transformer") != "transformer":
         dyn.update(generator_type=cfg["generator_type"], rank_ratio=cfg.get("rank_ratio", 4))
+    if cfg.get("use_adain", False):
+        dyn.update(use_adain=True)
     enc = ns.model.Encoder(resolution=cfg["resolution"], in_channels=3, ch=cfg["ch"], ch_mult=list(cfg["ch_mult"]),
                            num_res_blocks=cfg["num_res_blocks"], z_channels=cfg["z_channels"],
                            use_dynamic_ops=True, dynamic_conv_kwargs=dict(dyn))

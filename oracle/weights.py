@@ -26,6 +26,9 @@ TINY_CONFIG = dict(resolution=64, ch=32, ch_mult=(1, 2, 2), num_res_blocks=1, z_
 # generator_type='factorized' (configs/finetune_consistency_factor.yaml:50-73: num_layers 4, rank_ratio 2) at toy width
 TINY_FACTORIZED_CONFIG = dict(TINY_CONFIG, hyper_layers=2, generator_type="factorized", rank_ratio=2)
 
+# use_adain=True in dynamic_conv_kwargs (model.py:96-100): WavelengthConditioner + emb_proj in every ResnetBlock
+TINY_ADAIN_CONFIG = dict(TINY_CONFIG, use_adain=True)
+
 # eo_vae/datasets/terramesh_datamodule.py:18-50 (micrometres)
 WAVELENGTHS = {
     "S2RGB": [0.665, 0.56, 0.49],
@@ -35,11 +38,24 @@ WAVELENGTHS = {
 }
 
 
+_ADAIN = [False]  # set by state_dict_spec while it walks a use_adain config (layers.py:68-76: emb_proj after conv1)
+
+
+def _conditioner(spec, p, d=512):
+    """WavelengthConditioner.mlp (model.py:42-48)."""
+    for i, (o, k) in ((0, (2 * d, d)), (2, (d, 2 * d)), (4, (d, d))):
+        spec[f"{p}.mlp.{i}.weight"] = (o, k)
+        spec[f"{p}.mlp.{i}.bias"] = (o,)
+
+
 def _resblock(spec, p, cin, cout):
     spec[p + ".norm1.weight"] = (cin,)
     spec[p + ".norm1.bias"] = (cin,)
     spec[p + ".conv1.weight"] = (cout, cin, 3, 3)
     spec[p + ".conv1.bias"] = (cout,)
+    if _ADAIN[0]:
+        spec[p + ".emb_proj.weight"] = (2 * cout, 512)
+        spec[p + ".emb_proj.bias"] = (2 * cout,)
     spec[p + ".norm2.weight"] = (cout,)
     spec[p + ".norm2.bias"] = (cout,)
     spec[p + ".conv2.weight"] = (cout, cout, 3, 3)
@@ -124,7 +140,10 @@ def state_dict_spec(cfg: dict) -> "OrderedDict[str, tuple]":
     d, hl = cfg["wv_planes"], cfg["hyper_layers"]
     nres = len(mult)
     spec: OrderedDict[str, tuple] = OrderedDict()
+    _ADAIN[0] = bool(cfg.get("use_adain", False))
     # ---- encoder (model.py:67-165)
+    if _ADAIN[0]:
+        _conditioner(spec, "encoder.conditioner")
     _hypernet(spec, "encoder.conv_in", d, ch, hl, decoder=False, cfg=cfg)
     in_mult = (1,) + mult
     block_in = ch
@@ -149,6 +168,8 @@ def state_dict_spec(cfg: dict) -> "OrderedDict[str, tuple]":
     # ---- decoder (model.py:223-322)
     spec["decoder.post_quant_conv.weight"] = (zc, zc, 1, 1)
     spec["decoder.post_quant_conv.bias"] = (zc,)
+    if _ADAIN[0]:
+        _conditioner(spec, "decoder.conditioner")
     block_in = ch * mult[-1]
     spec["decoder.conv_in.weight"] = (block_in, zc, 3, 3)
     spec["decoder.conv_in.bias"] = (block_in,)
@@ -199,6 +220,9 @@ def make_state_dict(cfg: dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]
             a = 0.02 * g.standard_normal(shape)
         elif ".norm" in key and key.endswith(".weight") and len(shape) == 1:
             a = 1.0 + 0.1 * g.standard_normal(shape)
+        elif key.endswith("emb_proj.bias"):          # [scale | shift]: scale around the identity init of layers.py:72-76
+            a = 0.05 * g.standard_normal(shape)
+            a[: shape[0] // 2] += 1.0
         elif key.endswith((".bias", "in_proj_bias")):
             a = 0.05 * g.standard_normal(shape)
         else:

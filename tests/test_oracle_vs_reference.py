@@ -5,7 +5,7 @@ import torch
 
 from oracle import eovae_oracle as O
 from oracle import ref_shim
-from oracle.weights import FULL_CONFIG, TINY_CONFIG, TINY_FACTORIZED_CONFIG, WAVELENGTHS, make_state_dict, state_dict_spec, synthetic_patches
+from oracle.weights import FULL_CONFIG, TINY_ADAIN_CONFIG, TINY_CONFIG, TINY_FACTORIZED_CONFIG, WAVELENGTHS, make_state_dict, state_dict_spec, synthetic_patches
 
 pytestmark = pytest.mark.skipif(ref_shim.reference_root() is None, reason="reference tree not available")
 
@@ -13,8 +13,9 @@ pytestmark = pytest.mark.skipif(ref_shim.reference_root() is None, reason="refer
 FULL_FACTORIZED_CONFIG = dict(FULL_CONFIG, generator_type="factorized", rank_ratio=2)  # finetune_consistency_factor.yaml
 
 
-@pytest.mark.parametrize("cfg", [TINY_CONFIG, FULL_CONFIG, TINY_FACTORIZED_CONFIG, FULL_FACTORIZED_CONFIG],
-                         ids=["tiny", "full", "tiny-factorized", "full-factorized"])
+@pytest.mark.parametrize("cfg", [TINY_CONFIG, FULL_CONFIG, TINY_FACTORIZED_CONFIG, FULL_FACTORIZED_CONFIG,
+                                 TINY_ADAIN_CONFIG, dict(FULL_CONFIG, use_adain=True)],
+                         ids=["tiny", "full", "tiny-factorized", "full-factorized", "tiny-adain", "full-adain"])
 def test_state_dict_layout(cfg):
     model = ref_shim.build_reference_model(cfg)
     ref_sd = model.state_dict()
@@ -80,6 +81,35 @@ def test_factorized_generator_oracle_equals_reference(modality):
         assert float((got - p.grad).abs().max()) < 2e-4 * float(p.grad.abs().max()) + floor, name
         checked += 1
     assert checked > 60
+
+
+@pytest.mark.parametrize("modality", ["S2RGB", "S2L2A"])
+def test_adain_oracle_equals_reference(modality):
+    """use_adain=True (model.py:35-64, 96-100, 173-191, 331-343; layers.py:68-76, 96-104): latents, reconstruction and
+    every parameter gradient (conditioner MLPs and emb_proj included) vs the unmodified reference."""
+    cfg = TINY_ADAIN_CONFIG
+    sd = make_state_dict(cfg, 9)
+    model = ref_shim.build_reference_model(cfg, sd, train=False)
+    wvs = torch.tensor(WAVELENGTHS[modality])
+    x = synthetic_patches(2, len(wvs), 32, seed=81)
+    with torch.no_grad():
+        z_ref = model.encode_spatial_normalized(x, wvs)
+        r_ref = model.reconstruct(x, wvs)
+        z = O.encode_spatial_normalized(sd, x, wvs, cfg["hyper_heads"])
+        r = O.reconstruct(sd, x, wvs, cfg["hyper_heads"])
+    assert torch.allclose(z, z_ref, atol=2e-5) and torch.allclose(r, r_ref, atol=5e-5)
+    r_ref = model(x, wvs, sample_posterior=False)[0]
+    torch.sqrt((r_ref - x) ** 2 + 1e-6).mean().backward()
+    osd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    O.charbonnier_loss(O.forward(osd, x, wvs, None, False, cfg["hyper_heads"])[0], x).backward()
+    floor = 1e-6 * max(float(p.grad.abs().max()) for p in model.parameters() if p.grad is not None)
+    checked = 0
+    for name, p in model.named_parameters():
+        got = osd[name].grad
+        assert got is not None and p.grad is not None, name
+        assert float((got - p.grad).abs().max()) < 2e-4 * float(p.grad.abs().max()) + floor, name
+        checked += "conditioner" in name or "emb_proj" in name
+    assert checked >= 12 + 2 * 13  # two conditioners (6 tensors each) + emb_proj (w, b) of 13 ResnetBlocks
 
 
 def test_train_mode_forward_matches_reference():

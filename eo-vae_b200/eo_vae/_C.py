@@ -51,6 +51,10 @@ SIGNATURES = {
     "eovae_wavelength_style_backward": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "eovae_adain_affine_forward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "eovae_adain_affine_backward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "eovae_sam_loss": (_i, [_vp, _vp, _i, _i, _ll, _f, _vp, _vp, _sz, _vp]),
+    "eovae_sam_loss_backward": (_i, [_vp, _vp, _i, _i, _ll, _f, _vp, _vp, _vp]),
+    "eovae_grad_diff_loss": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp, _sz, _vp]),
+    "eovae_grad_diff_loss_backward": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp, _vp]),
     "eovae_msssim_backward_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "eovae_msssim_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "eovae_conv2d_wgrad_nhwc_ok": (_i, [_i, _i]),

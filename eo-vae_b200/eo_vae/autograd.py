@@ -466,3 +466,36 @@ class AdaINAffineFn(Function):
         dgamma, dbeta, dw, dbp, dstyle = ops.adain_affine_backward(style.detach().contiguous(), wproj.detach(), gamma.detach(),
                                                                    beta.detach(), style2, dg_out, db_out)
         return dstyle.view_as(style), dw, dbp, dgamma, dbeta
+
+
+class SamLossFn(Function):
+    """mean(1 - cos(pred, target)) along the band axis (SAMLoss, consistency_loss.py:186-210)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, eps):
+        a = pred.to(torch.float32).contiguous()
+        b = target.to(torch.float32).contiguous()
+        ctx.save_for_backward(a, b)
+        ctx.eps = eps
+        return ops.sam_loss(a, b, eps)
+
+    @staticmethod
+    def backward(ctx, gl):
+        a, b = ctx.saved_tensors
+        return ops.sam_loss_backward(a, b, ctx.eps, gl), None, None
+
+
+class GradDiffLossFn(Function):
+    """GradientDifferenceLoss with alpha = 1 (consistency_loss.py:241-269)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        a = pred.to(torch.float32).contiguous()
+        b = target.to(torch.float32).contiguous()
+        ctx.save_for_backward(a, b)
+        return ops.grad_diff_loss(a, b)
+
+    @staticmethod
+    def backward(ctx, gl):
+        a, b = ctx.saved_tensors
+        return ops.grad_diff_loss_backward(a, b, gl), None

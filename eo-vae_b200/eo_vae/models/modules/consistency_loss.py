@@ -37,6 +37,35 @@ class SSIMLoss(nn.Module):
         return 1.0 - ops.msssim(pred, target, self.data_range)[0][0]
 
 
+class SAMLoss(nn.Module):
+    """1 - cosine similarity along the band axis, averaged (consistency_loss.py:186-210) on eovae_sam_loss."""
+
+    def __init__(self, eps=1e-8):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, x_rec, x_true):
+        if tape.grad_mode() and x_rec.requires_grad:
+            return tape.SamLossFn.apply(x_rec, x_true, self.eps)
+        return ops.sam_loss(x_rec, x_true, self.eps)
+
+
+class GradientDifferenceLoss(nn.Module):
+    """| |dx pred| - |dx target| | + the same along y, averaged (consistency_loss.py:241-269) on eovae_grad_diff_loss.
+    The kernels implement alpha = 1, the value EOConsistencyLoss constructs it with (:386)."""
+
+    def __init__(self, alpha=1.0):
+        super().__init__()
+        if float(alpha) != 1.0:
+            raise NotImplementedError('GradientDifferenceLoss: only alpha = 1 is built (EOConsistencyLoss default)')
+        self.alpha = alpha
+
+    def forward(self, pred, target):
+        if tape.grad_mode() and pred.requires_grad:
+            return tape.GradDiffLossFn.apply(pred, target)
+        return ops.grad_diff_loss(pred, target)
+
+
 class EOConsistencyLoss(nn.Module):
     def __init__(self, pixel_weight: float = 1.0, rec_loss_type: str = 'l1', spectral_weight: float = 0.0,
                  spatial_weight: float = 0.0, freq_weight: float = 0.0, feature_weight: float = 0.0,
@@ -44,9 +73,8 @@ class EOConsistencyLoss(nn.Module):
                  freq_start_step: int = 0, feature_start_step: int = 0, msssim_start_step: int = 0,
                  patch_factor: int = 2, ffl_alpha: float = 1.0, dofa_net: nn.Module = None):
         super().__init__()
-        for name, wgt in (('spectral', spectral_weight), ('spatial', spatial_weight), ('freq', freq_weight),
-                          ('feature', feature_weight)):
-            if wgt > 0:
+        for name, wgt in (('freq', freq_weight), ('feature', feature_weight)):
+            if wgt > 0:  # focal-frequency (FFT) and DOFA-feature branches: not built (SURVEY.md 8f-4 / out of scope)
                 raise NotImplementedError(f'{name}_weight > 0: branch outside the built hot path (SURVEY.md 8f-4)')
         if rec_loss_type not in ('l1', 'char'):
             raise ValueError("rec_loss_type must be 'l1' or 'char'")
@@ -55,6 +83,8 @@ class EOConsistencyLoss(nn.Module):
                        'feature': feature_start_step, 'msssim': msssim_start_step}
         self.weights = {'pixel': pixel_weight, 'spectral': spectral_weight, 'spatial': spatial_weight,
                         'freq': freq_weight, 'feature': feature_weight, 'msssim': msssim_weight}
+        self.sam_loss = SAMLoss()
+        self.grad_loss = GradientDifferenceLoss()
         self.char_loss = CharbonnierLoss()
         self.msssim_loss = SSIMLoss()
 
@@ -70,6 +100,14 @@ class EOConsistencyLoss(nn.Module):
                 l_rec = ops.l1_charbonnier(reconstructions, inputs, self.char_loss.eps)[kind]
             total = total + self.weights['pixel'] * l_rec
             logs[f'{split}/loss_rec'] = l_rec.detach()
+        if self.weights['spectral'] > 0 and global_step >= self.starts['spectral']:
+            l_sam = self.sam_loss(reconstructions, inputs)
+            total = total + self.weights['spectral'] * l_sam
+            logs[f'{split}/loss_spectral'] = l_sam.detach()
+        if self.weights['spatial'] > 0 and global_step >= self.starts['spatial']:
+            l_spat = self.grad_loss(reconstructions, inputs)
+            total = total + self.weights['spatial'] * l_spat
+            logs[f'{split}/loss_spatial'] = l_spat.detach()
         if self.weights['msssim'] > 0 and global_step >= self.starts['msssim']:
             l_msssim = self.msssim_loss(reconstructions, inputs)
             total = total + self.weights['msssim'] * l_msssim

@@ -363,6 +363,53 @@ def l1_charbonnier(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-3):
     return out
 
 
+def _nchw_f32_pair(pred: torch.Tensor, target: torch.Tensor):
+    _need_cuda(pred, target)
+    if pred.dim() != 4 or pred.shape != target.shape:
+        raise RuntimeError(f"loss inputs must be two [B, C, H, W] tensors of one shape, got {tuple(pred.shape)} / {tuple(target.shape)}")
+    return pred.to(torch.float32).contiguous(), target.to(torch.float32).contiguous()
+
+
+def sam_loss(pred: torch.Tensor, target: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """SAMLoss (consistency_loss.py:186-210) -> fp32 scalar tensor."""
+    a, b = _nchw_f32_pair(pred, target)
+    n, c, h, w = a.shape
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    ws = torch.empty((2,), dtype=torch.float64, device=a.device)
+    _C.check(_C.lib().eovae_sam_loss(_ptr(a), _ptr(b), n, c, h * w, float(eps), _ptr(out), _ptr(ws), 16, _stream()), "eovae_sam_loss")
+    return out[0]
+
+
+def sam_loss_backward(a: torch.Tensor, b: torch.Tensor, eps: float, grad_scale: torch.Tensor) -> torch.Tensor:
+    _need_cuda(a, b, grad_scale)
+    n, c, h, w = a.shape
+    ga = torch.empty_like(a)
+    gs = grad_scale.to(torch.float32).reshape(1)
+    _C.check(_C.lib().eovae_sam_loss_backward(_ptr(a), _ptr(b), n, c, h * w, float(eps), _ptr(gs), _ptr(ga), _stream()),
+             "eovae_sam_loss_backward")
+    return ga
+
+
+def grad_diff_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """GradientDifferenceLoss, alpha = 1 (consistency_loss.py:241-269) -> fp32 scalar tensor."""
+    a, b = _nchw_f32_pair(pred, target)
+    n, c, h, w = a.shape
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    ws = torch.empty((2,), dtype=torch.float64, device=a.device)
+    _C.check(_C.lib().eovae_grad_diff_loss(_ptr(a), _ptr(b), n * c, h, w, _ptr(out), _ptr(ws), 16, _stream()), "eovae_grad_diff_loss")
+    return out[0]
+
+
+def grad_diff_loss_backward(a: torch.Tensor, b: torch.Tensor, grad_scale: torch.Tensor) -> torch.Tensor:
+    _need_cuda(a, b, grad_scale)
+    n, c, h, w = a.shape
+    ga = torch.empty_like(a)
+    gs = grad_scale.to(torch.float32).reshape(1)
+    _C.check(_C.lib().eovae_grad_diff_loss_backward(_ptr(a), _ptr(b), n * c, h, w, _ptr(gs), _ptr(ga), _stream()),
+             "eovae_grad_diff_loss_backward")
+    return ga
+
+
 def msssim(pred: torch.Tensor, target: torch.Tensor, data_range: float = 6.0):
     """-> (mean MS-SSIM over the batch [1], per-sample MS-SSIM [B]); fp32 NCHW inputs."""
     _need_cuda(pred, target)

@@ -272,6 +272,19 @@ int eovae_adain_affine_backward(const float* style, int d, const float* wproj, c
                                 const float* style2, int cout, const float* dgamma_out, const float* dbeta_out,
                                 float* dgamma, float* dbeta, float* dwproj, float* dbproj, float* dstyle, float* dstyle2,
                                 void* stream);
+/* ---- optional EOConsistencyLoss branches, fp32 NCHW contiguous, out = one device scalar ------------------
+ * SAMLoss.forward (consistency_loss.py:186-210): mean over (b, pixel) of 1 - <p, t> / (|p| |t| + eps), channel axis = 1.
+ * workspace: 16 bytes.  Backward: gradient wrt pred times the device scalar *grad_scale. */
+int eovae_sam_loss(const float* pred, const float* target, int b, int c, long long hw, float eps, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int eovae_sam_loss_backward(const float* pred, const float* target, int b, int c, long long hw, float eps,
+                            const float* grad_scale, float* grad_pred, void* stream);
+/* GradientDifferenceLoss.forward with alpha = 1 (consistency_loss.py:241-269): mean | |dx p| - |dx t| | + mean | |dy p| - |dy t| |
+ * over `planes` = B*C images of h x w (forward differences).  workspace: 16 bytes. */
+int eovae_grad_diff_loss(const float* pred, const float* target, long long planes, int h, int w, float* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int eovae_grad_diff_loss_backward(const float* pred, const float* target, long long planes, int h, int w,
+                                  const float* grad_scale, float* grad_pred, void* stream);
 /* gradient of eovae_msssim's batch-mean value wrt pred (fp32 NCHW), times the device scalar *grad_scale; the forward
  * pyramid is rebuilt inside the workspace (consistency_loss.py:24-37 adjoint) */
 size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w);

@@ -89,6 +89,36 @@ def load_reference():
     return _namespace()
 
 
+def load_reference_losses():
+    """The reference's ``consistency_loss`` module (SAMLoss, GradientDifferenceLoss, CharbonnierLoss, EOConsistencyLoss with
+    msssim_weight = 0), executed from /root/reference.  ``torchmetrics`` is absent here: its one imported name is stubbed
+    with a class that raises when used, so everything except the MS-SSIM branch is the unmodified reference."""
+    if load_reference() is None:
+        return None
+    name = ALIAS + ".models.modules.consistency_loss"
+    if name in sys.modules:
+        return sys.modules[name]
+    if "torchmetrics" not in sys.modules:
+        try:
+            import torchmetrics  # noqa: F401
+        except Exception:
+            import torch
+
+            tm, tmi = types.ModuleType("torchmetrics"), types.ModuleType("torchmetrics.image")
+
+            class MultiScaleStructuralSimilarityIndexMeasure(torch.nn.Module):
+                def __init__(self, *a, **k):
+                    super().__init__()
+
+                def forward(self, *a, **k):
+                    raise RuntimeError("torchmetrics is not available in this container (MS-SSIM parity is unpinned)")
+
+            tmi.MultiScaleStructuralSimilarityIndexMeasure = MultiScaleStructuralSimilarityIndexMeasure
+            tm.image = tmi
+            sys.modules["torchmetrics"], sys.modules["torchmetrics.image"] = tm, tmi
+    return importlib.import_module(name)
+
+
 def _namespace():
     ns = types.SimpleNamespace()
     ns.layers = sys.modules[ALIAS + ".models.modules.layers"]

@@ -457,3 +457,38 @@ def test_adain_model_forward_and_gradients(cuda):
         b = torch.cat([osd[n].grad.flatten() for n, p in model.named_parameters() if sel in n])
         print(f"adain gradients [{sel or 'all'}]: rel-L2 {_rel(a, b):.3e}")
         assert _rel(a, b) < 6e-2, (sel, _rel(a, b))
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 64, 64), (3, 2, 37, 51), (16, 12, 256, 256), (1, 13, 16, 16)])
+def test_spectral_and_spatial_losses(cuda, shape):
+    """eovae_sam_loss / eovae_grad_diff_loss forward + backward and the EOConsistencyLoss branches that use them
+    (consistency_loss.py:186-210, 241-269, 426-440) vs the oracle (pinned against the reference classes on CPU)."""
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss, GradientDifferenceLoss, SAMLoss
+    from oracle import eovae_oracle as O
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(shape, generator=g)
+    r0 = x + 0.3 * torch.randn(shape, generator=g)
+    r0[0, :, 0, 0] = 0.0
+    r0[0, 0, 1, 1:4] = x[0, 0, 1, 1:4]        # exact ties: sign(0) = 0 in the gradient-difference adjoint
+    for mod, fn in ((SAMLoss(), O.sam_loss), (GradientDifferenceLoss(), O.grad_diff_loss)):
+        a = r0.clone().to(cuda).requires_grad_(True)
+        b = r0.clone().requires_grad_(True)
+        la = mod(a, x.to(cuda))
+        lb = fn(b, x)
+        (3.0 * la).backward(); (3.0 * lb).backward()
+        assert abs(float(la) - float(lb)) < 1e-5 * abs(float(lb)) + 1e-7, (type(mod).__name__, float(la), float(lb))
+        assert _rel(a.grad.cpu(), b.grad) < 1e-4, (type(mod).__name__, _rel(a.grad.cpu(), b.grad))
+        with torch.no_grad():
+            assert abs(float(mod(r0.to(cuda), x.to(cuda))) - float(lb)) < 1e-5 * abs(float(lb)) + 1e-7
+    loss = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="char", spectral_weight=0.5, spatial_weight=2.0,
+                             spatial_start_step=10).to(cuda)
+    for step in (0, 10):
+        a = r0.clone().to(cuda).requires_grad_(True)
+        b = r0.clone().requires_grad_(True)
+        total, logs = loss(inputs=x.to(cuda), wvs=None, reconstructions=a, global_step=step)
+        want, _, _ = O.consistency_loss(x, b, "char", 1.0, 0.0, step, 0, spectral_weight=0.5, spatial_weight=2.0,
+                                        spatial_start_step=10)
+        total.backward(); want.backward()
+        assert abs(float(total) - float(want)) < 1e-5 * abs(float(want))
+        assert _rel(a.grad.cpu(), b.grad) < 1e-4
+        assert ("train/loss_spatial" in logs) == (step >= 10) and "train/loss_spectral" in logs

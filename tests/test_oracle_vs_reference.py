@@ -180,3 +180,28 @@ def test_dropin_package_has_reference_checkpoint_layout():
     frozen = EOFluxVAE(enc, dec, torch.nn.Identity(), freeze_body=True)
     names = {n for n, p in frozen.named_parameters() if p.requires_grad}
     assert names and all(n.startswith(("encoder.conv_in.", "decoder.conv_out.")) for n in names)
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 24, 20), (3, 2, 17, 33)])
+def test_spectral_and_spatial_losses_match_reference(shape):
+    """SAMLoss / GradientDifferenceLoss / EOConsistencyLoss with spectral + spatial branches (consistency_loss.py:186-210,
+    241-269, 426-440): oracle restatement vs the unmodified reference classes - values and d/d(reconstruction)."""
+    ref = ref_shim.load_reference_losses()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(shape, generator=g)
+    r0 = x + 0.3 * torch.randn(shape, generator=g)
+    r0[0, :, 0, 0] = 0.0                      # a zero spectrum: norm subgradient 0, eps keeps the quotient finite
+    for fn_ref, fn in ((ref.SAMLoss(), O.sam_loss), (ref.GradientDifferenceLoss(), O.grad_diff_loss)):
+        a, b = r0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+        la, lb = fn_ref(a, x), fn(b, x)
+        la.backward(); lb.backward()
+        assert torch.allclose(la, lb, rtol=1e-6, atol=1e-7)
+        assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-9)
+    loss = ref.EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="char", spectral_weight=0.5, spatial_weight=2.0,
+                                 spatial_start_step=10)
+    for step in (0, 10):
+        total, logs = loss(inputs=x, wvs=None, reconstructions=r0, global_step=step)
+        want, _, _ = O.consistency_loss(x, r0, "char", 1.0, 0.0, step, 0, spectral_weight=0.5, spatial_weight=2.0,
+                                        spatial_start_step=10)
+        assert torch.allclose(total, want, rtol=1e-6)
+        assert ("train/loss_spatial" in logs) == (step >= 10) and "train/loss_spectral" in logs

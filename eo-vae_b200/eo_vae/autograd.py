@@ -499,3 +499,31 @@ class GradDiffLossFn(Function):
     def backward(ctx, gl):
         a, b = ctx.saved_tensors
         return ops.grad_diff_loss_backward(a, b, gl), None
+
+
+class DistillWeightFn(Function):
+    """Differentiable ``get_distillation_weight`` (dynamic_conv.py:471-497, 638-664): wavelengths -> generated OIHW kernel
+    and bias, both scaled by 0.1, for the stage-1 weight distillation loop (weight_distill_train.py:190-264: MSE against
+    the Flux conv_in / conv_out weights).  Backward = the hypernetwork's backward kernels on (dW, dbias)."""
+
+    @staticmethod
+    def forward(ctx, mod, wvs, *hparams):
+        c = wvs.numel()
+        wk, b_raw, tape_ws = mod._generate_taped(wvs)
+        _, bias, oihw = ops.pack_dyn_weight(wk, b_raw, c, mod.embed_dim, mod._decoder, mod.scaler, mod.scaler,
+                                            torch.bfloat16, True)
+        ctx.save_for_backward(wvs, tape_ws)
+        ctx.mod = mod
+        return oihw, bias
+
+    @staticmethod
+    def backward(ctx, dw, db):
+        wvs, tape_ws = ctx.saved_tensors
+        mod = ctx.mod
+        if dw is None:
+            dw = torch.zeros((wvs.numel(), mod.embed_dim, 3, 3) if mod._decoder else (mod.embed_dim, wvs.numel(), 3, 3),
+                             dtype=torch.float32, device=wvs.device)
+        if db is None:
+            db = torch.zeros((wvs.numel() if mod._decoder else mod.embed_dim,), dtype=torch.float32, device=wvs.device)
+        grads = mod._hyper_backward(wvs, dw.contiguous(), db.contiguous(), mod.scaler, tape_ws)
+        return (None, None) + tuple(grads)

@@ -262,6 +262,10 @@ class DynamicConv(_DynamicBase):
     _decoder = False
 
     def get_distillation_weight(self, wvs_microns: Tensor):
+        if tape.grad_mode():  # stage-1 weight distillation (weight_distill_train.py:190-264) trains the hypernetwork
+            dev = self.weight_generator.weight_tokens.device
+            return tape.DistillWeightFn.apply(self, wvs_microns.to(device=dev, dtype=torch.float32),
+                                              *self.weight_generator.parameter_list(self.fclayer))
         wk, b_raw = self._generate(wvs_microns)
         _, bias, oihw = ops.pack_dyn_weight(wk, b_raw, wvs_microns.numel(), self.embed_dim, False, self.scaler,
                                             self.scaler, compute_dtype(), want_oihw=True)
@@ -296,6 +300,10 @@ class DynamicConv_decoder(_DynamicBase):
         self._last = None
 
     def get_distillation_weight(self, wvs_microns: Tensor):
+        if tape.grad_mode():
+            dev = self.weight_generator.weight_tokens.device
+            return tape.DistillWeightFn.apply(self, wvs_microns.to(device=dev, dtype=torch.float32),
+                                              *self.weight_generator.parameter_list(self.fclayer))
         wk, b_raw = self._generate(wvs_microns)
         _, bias, oihw = ops.pack_dyn_weight(wk, b_raw, wvs_microns.numel(), self.embed_dim, True, self.scaler,
                                             self.scaler, compute_dtype(), want_oihw=True)

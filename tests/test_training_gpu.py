@@ -398,3 +398,48 @@ def test_training_step_reduces_loss(cuda):
     for k, v in model.named_parameters():
         if k in before:
             assert not torch.equal(v.detach(), before[k])
+
+
+@pytest.mark.parametrize("generator", ["transformer", "factorized"])
+def test_weight_distillation_loop(cuda, generator):
+    """Stage-1 weight distillation (weight_distill_train.py:190-264): MSE between ``get_distillation_weight(rgb_wvs)`` of
+    both dynamic layers and fixed teacher conv weights, Adam on the hypernetworks only.  First-step gradients vs autograd
+    over the oracle, then the loss must fall."""
+    import torch.nn.functional as F
+    from eo_vae.models.modules.dynamic_conv import DynamicConv, DynamicConv_decoder
+    from oracle import eovae_oracle as O
+    torch.manual_seed(3)
+    kw = dict(wv_planes=128, inter_dim=128, kernel_size=3, stride=1, padding=1, embed_dim=128, num_layers=2, num_heads=4,
+              generator_type=generator, rank_ratio=4)
+    enc, dec = DynamicConv(**kw).to(cuda).eval(), DynamicConv_decoder(**kw).to(cuda).eval()
+    wvs = torch.tensor([0.665, 0.56, 0.49], device=cuda)
+    g = torch.Generator().manual_seed(1)
+    t_enc_w, t_enc_b = 0.1 * torch.randn((128, 3, 3, 3), generator=g), 0.1 * torch.randn((128,), generator=g)
+    t_dec_w, t_dec_b = 0.1 * torch.randn((3, 128, 3, 3), generator=g), 0.1 * torch.randn((3,), generator=g)
+
+    def loss_of(ew, eb, dw, db, dev):
+        return (F.mse_loss(ew, t_enc_w.to(dev)) + F.mse_loss(eb, t_enc_b.to(dev)) + F.mse_loss(dw, t_dec_w.to(dev))
+                + F.mse_loss(db.reshape(-1), t_dec_b.to(dev)))
+
+    params = list(enc.parameters()) + list(dec.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3)
+    losses = []
+    for step in range(12):
+        opt.zero_grad(set_to_none=True)
+        loss = loss_of(*enc.get_distillation_weight(wvs), *dec.get_distillation_weight(wvs), cuda)
+        loss.backward()
+        if step == 0:
+            sd = {"e." + k: v.detach().cpu().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
+            sd.update({"d." + k: v.detach().cpu().clone().requires_grad_(True) for k, v in dec.state_dict().items()})
+            ew, eb = O.hypernet(sd, "e", wvs.cpu(), False, heads=4)
+            dw, db = O.hypernet(sd, "d", wvs.cpu(), True, heads=4)
+            want = loss_of(ew, eb, dw, db * 10.0, "cpu")   # distillation bias: scaled once (dynamic_conv.py:660)
+            want.backward()
+            assert abs(float(loss) - float(want)) < 1e-4 * abs(float(want))
+            for pre, mod in (("e.", enc), ("d.", dec)):
+                a = torch.cat([p.grad.flatten().cpu() for _, p in mod.named_parameters()])
+                b = torch.cat([sd[pre + n].grad.flatten() for n, _ in mod.named_parameters()])
+                assert _rel(a, b) < 2e-3, (pre, _rel(a, b))
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < 0.7 * losses[0], losses

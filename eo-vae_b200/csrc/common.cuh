@@ -14,6 +14,10 @@ namespace eovae {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 extern unsigned long long g_launches;
+// C[batch][i][j] (+)= sum_k A[batch*a_bs + i*a_rs + k*a_cs] * B[batch*b_bs + k*b_rs + j*b_cs]   (fp32 SIMT, hypernet.cu)
+int sgemm_batched(const float* a, long long a_rs, long long a_cs, long long a_bs, const float* b, long long b_rs, long long b_cs,
+                  long long b_bs, float* c, long long ldc, long long c_bs, int batches, int m, int n, int k, int accumulate,
+                  cudaStream_t st);
 }  // namespace eovae
 
 #define EOVAE_CHECK(cond, ...)            \

@@ -769,6 +769,21 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
 
 }  // extern "C"
 
+// batched strided fp32 GEMM for the other translation units (focal-frequency loss DFTs), no split-K
+namespace eovae {
+int sgemm_batched(const float* a, long long a_rs, long long a_cs, long long a_bs, const float* b, long long b_rs, long long b_cs,
+                  long long b_bs, float* c, long long ldc, long long c_bs, int batches, int m, int n, int k, int accumulate,
+                  cudaStream_t st) {
+  for (int b0 = 0; b0 < batches; b0 += 32768) {  // gridDim.z limit
+    const int nb = batches - b0 < 32768 ? batches - b0 : 32768;
+    if (sgemm_b(a + b0 * a_bs, a_rs, a_cs, a_bs, b + b0 * b_bs, b_rs, b_cs, b_bs, c + b0 * c_bs, ldc, c_bs, nb, m, n, k, accumulate,
+                nullptr, st))
+      return -1;
+  }
+  return 0;
+}
+}  // namespace eovae
+
 // =====================================================================================================================
 // FactorizedWeightGenerator(_decoder) (dynamic_conv.py:186-302): PRE-norm transformer layers (norm_first=True, ff = 4 d)
 // and a low-rank head Linear(d, rank) -> GELU -> Linear(rank, 9E).  Same building blocks as above; the forward always

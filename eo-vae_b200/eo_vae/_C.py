@@ -55,6 +55,9 @@ SIGNATURES = {
     "eovae_sam_loss_backward": (_i, [_vp, _vp, _i, _i, _ll, _f, _vp, _vp, _vp]),
     "eovae_grad_diff_loss": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp, _sz, _vp]),
     "eovae_grad_diff_loss_backward": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp, _vp]),
+    "eovae_focal_freq_loss_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "eovae_focal_freq_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _sz, _vp]),
+    "eovae_focal_freq_loss_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "eovae_msssim_backward_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "eovae_msssim_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "eovae_conv2d_wgrad_nhwc_ok": (_i, [_i, _i]),

@@ -527,3 +527,20 @@ class DistillWeightFn(Function):
             db = torch.zeros((wvs.numel() if mod._decoder else mod.embed_dim,), dtype=torch.float32, device=wvs.device)
         grads = mod._hyper_backward(wvs, dw.contiguous(), db.contiguous(), mod.scaler, tape_ws)
         return (None, None) + tuple(grads)
+
+
+class FocalFreqLossFn(Function):
+    """FocalFrequencyLoss (ffl.py:17-104) with the detached batch-normalised log weight matrix."""
+
+    @staticmethod
+    def forward(ctx, pred, target, patch_factor, alpha):
+        out, ws = ops.focal_freq_loss(pred, target, patch_factor, alpha, keep=True)
+        ctx.save_for_backward(ws)
+        ctx.cfg = (tuple(pred.shape), patch_factor)
+        return out
+
+    @staticmethod
+    def backward(ctx, gl):
+        (ws,) = ctx.saved_tensors
+        shape, pf = ctx.cfg
+        return ops.focal_freq_loss_backward(shape, pf, gl, ws), None, None, None

@@ -66,6 +66,25 @@ class GradientDifferenceLoss(nn.Module):
         return ops.grad_diff_loss(pred, target)
 
 
+class FocalFrequencyLoss(nn.Module):
+    """ffl.py:17-104 on eovae_focal_freq_loss: the configuration EOConsistencyLoss uses (ave_spectrum False, batch_matrix
+    and log_matrix True, no external weight matrix); other option combinations raise."""
+
+    def __init__(self, loss_weight=1.0, alpha=1.0, patch_factor=1, ave_spectrum=False, log_matrix=False, batch_matrix=False):
+        super().__init__()
+        if ave_spectrum or not (log_matrix and batch_matrix):
+            raise NotImplementedError('FocalFrequencyLoss: built for ave_spectrum=False, log_matrix=True, batch_matrix=True')
+        self.loss_weight, self.alpha, self.patch_factor = loss_weight, alpha, patch_factor
+        self.ave_spectrum, self.log_matrix, self.batch_matrix = ave_spectrum, log_matrix, batch_matrix
+
+    def forward(self, pred, target, matrix=None, **kwargs):
+        if matrix is not None:
+            raise NotImplementedError('FocalFrequencyLoss: external weight matrix is not supported')
+        if tape.grad_mode() and pred.requires_grad:
+            return tape.FocalFreqLossFn.apply(pred, target, self.patch_factor, self.alpha) * self.loss_weight
+        return ops.focal_freq_loss(pred, target, self.patch_factor, self.alpha)[0] * self.loss_weight
+
+
 class EOConsistencyLoss(nn.Module):
     def __init__(self, pixel_weight: float = 1.0, rec_loss_type: str = 'l1', spectral_weight: float = 0.0,
                  spatial_weight: float = 0.0, freq_weight: float = 0.0, feature_weight: float = 0.0,
@@ -73,9 +92,8 @@ class EOConsistencyLoss(nn.Module):
                  freq_start_step: int = 0, feature_start_step: int = 0, msssim_start_step: int = 0,
                  patch_factor: int = 2, ffl_alpha: float = 1.0, dofa_net: nn.Module = None):
         super().__init__()
-        for name, wgt in (('freq', freq_weight), ('feature', feature_weight)):
-            if wgt > 0:  # focal-frequency (FFT) and DOFA-feature branches: not built (SURVEY.md 8f-4 / out of scope)
-                raise NotImplementedError(f'{name}_weight > 0: branch outside the built hot path (SURVEY.md 8f-4)')
+        if feature_weight > 0 or dofa_net is not None:  # DOFA feature branch: needs an external pretrained network
+            raise NotImplementedError('feature_weight > 0: the DOFA semantic-feature branch is outside the built hot path')
         if rec_loss_type not in ('l1', 'char'):
             raise ValueError("rec_loss_type must be 'l1' or 'char'")
         self.rec_loss_type = rec_loss_type
@@ -85,6 +103,8 @@ class EOConsistencyLoss(nn.Module):
                         'freq': freq_weight, 'feature': feature_weight, 'msssim': msssim_weight}
         self.sam_loss = SAMLoss()
         self.grad_loss = GradientDifferenceLoss()
+        self.fft_loss = FocalFrequencyLoss(loss_weight=1.0, alpha=ffl_alpha, patch_factor=patch_factor, ave_spectrum=False,
+                                           batch_matrix=True, log_matrix=True)
         self.char_loss = CharbonnierLoss()
         self.msssim_loss = SSIMLoss()
 
@@ -108,6 +128,13 @@ class EOConsistencyLoss(nn.Module):
             l_spat = self.grad_loss(reconstructions, inputs)
             total = total + self.weights['spatial'] * l_spat
             logs[f'{split}/loss_spatial'] = l_spat.detach()
+        if self.weights['freq'] > 0 and global_step >= self.starts['freq']:
+            raw = self.fft_loss(reconstructions, inputs)
+            warmup = min(1.0, max(0.0, (global_step - self.starts['freq']) / 1000))   # consistency_loss.py:443-452
+            current = self.weights['freq'] * warmup
+            total = total + raw * current
+            logs[f'{split}/loss_freq_raw'] = raw.detach()
+            logs[f'{split}/ffl_weight'] = torch.tensor(current)
         if self.weights['msssim'] > 0 and global_step >= self.starts['msssim']:
             l_msssim = self.msssim_loss(reconstructions, inputs)
             total = total + self.weights['msssim'] * l_msssim

@@ -410,6 +410,30 @@ def grad_diff_loss_backward(a: torch.Tensor, b: torch.Tensor, grad_scale: torch.
     return ga
 
 
+def focal_freq_loss(pred: torch.Tensor, target: torch.Tensor, patch_factor: int = 1, alpha: float = 1.0, keep: bool = False):
+    """FocalFrequencyLoss (ffl.py:17-104; batch_matrix, log_matrix) -> (fp32 scalar tensor, workspace | None).  ``keep``:
+    return the workspace (weight * spectrum) for focal_freq_loss_backward."""
+    a, b = _nchw_f32_pair(pred, target)
+    n, c, h, w = a.shape
+    lib = _C.lib()
+    ws_bytes = lib.eovae_focal_freq_loss_workspace_bytes(n, c, h, w, patch_factor)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=a.device)
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    _C.check(lib.eovae_focal_freq_loss(_ptr(a), _ptr(b), n, c, h, w, int(patch_factor), float(alpha), 1 if keep else 0, _ptr(out),
+                                       _ptr(ws), ws_bytes, _stream()), "eovae_focal_freq_loss")
+    return out[0], (ws if keep else None)
+
+
+def focal_freq_loss_backward(shape, patch_factor: int, grad_scale: torch.Tensor, ws: torch.Tensor) -> torch.Tensor:
+    _need_cuda(grad_scale, ws)
+    n, c, h, w = shape
+    ga = torch.empty(shape, dtype=torch.float32, device=ws.device)
+    gs = grad_scale.to(torch.float32).reshape(1)
+    _C.check(_C.lib().eovae_focal_freq_loss_backward(n, c, h, w, int(patch_factor), _ptr(gs), _ptr(ga), _ptr(ws),
+                                                     (ws.numel() - 1) * 4, _stream()), "eovae_focal_freq_loss_backward")
+    return ga
+
+
 def msssim(pred: torch.Tensor, target: torch.Tensor, data_range: float = 6.0):
     """-> (mean MS-SSIM over the batch [1], per-sample MS-SSIM [B]); fp32 NCHW inputs."""
     _need_cuda(pred, target)

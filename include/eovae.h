@@ -285,6 +285,16 @@ int eovae_grad_diff_loss(const float* pred, const float* target, long long plane
                          size_t workspace_bytes, void* stream);
 int eovae_grad_diff_loss_backward(const float* pred, const float* target, long long planes, int h, int w,
                                   const float* grad_scale, float* grad_pred, void* stream);
+/* FocalFrequencyLoss.forward (ffl.py:17-104) as EOConsistencyLoss builds it (consistency_loss.py:388-395: patch_factor,
+ * alpha, ave_spectrum = False, batch_matrix = True, log_matrix = True): orthonormal 2-D DFT of (pred - target) per
+ * H/pf x W/pf patch (dense fp32 DFT-matrix products, any patch size), weight = clamp(log1p(|Z|^alpha) / batch max, 0, 1)
+ * (detached), out = mean(weight |Z|^2).  keep_for_backward = 1 leaves weight * Z in `workspace` for the backward, which
+ * returns d out / d pred times the device scalar *grad_scale. */
+size_t eovae_focal_freq_loss_workspace_bytes(int b, int c, int h, int w, int patch_factor);
+int eovae_focal_freq_loss(const float* pred, const float* target, int b, int c, int h, int w, int patch_factor, float alpha,
+                          int keep_for_backward, float* out, void* workspace, size_t workspace_bytes, void* stream);
+int eovae_focal_freq_loss_backward(int b, int c, int h, int w, int patch_factor, const float* grad_scale, float* grad_pred,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 /* gradient of eovae_msssim's batch-mean value wrt pred (fp32 NCHW), times the device scalar *grad_scale; the forward
  * pyramid is rebuilt inside the workspace (consistency_loss.py:24-37 adjoint) */
 size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w);

@@ -492,3 +492,32 @@ def test_spectral_and_spatial_losses(cuda, shape):
         assert abs(float(total) - float(want)) < 1e-5 * abs(float(want))
         assert _rel(a.grad.cpu(), b.grad) < 1e-4
         assert ("train/loss_spatial" in logs) == (step >= 10) and "train/loss_spectral" in logs
+
+
+@pytest.mark.parametrize("shape,pf,alpha", [((2, 3, 64, 64), 2, 1.0), ((1, 12, 24, 36), 1, 1.0), ((2, 2, 28, 44), 2, 0.5),
+                                            ((4, 12, 256, 256), 2, 1.0)])
+def test_focal_frequency_loss(cuda, shape, pf, alpha):
+    """eovae_focal_freq_loss forward + backward (DFT-matrix products, power-of-two and other patch sizes) and the freq
+    branch of EOConsistencyLoss with its warm-up vs the oracle (pinned against the reference's ffl.py on CPU)."""
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss, FocalFrequencyLoss
+    from oracle import eovae_oracle as O
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(shape, generator=g)
+    r0 = x + 0.3 * torch.randn(shape, generator=g)
+    mod = FocalFrequencyLoss(alpha=alpha, patch_factor=pf, batch_matrix=True, log_matrix=True)
+    a = r0.clone().to(cuda).requires_grad_(True)
+    b = r0.clone().requires_grad_(True)
+    la, lb = mod(a, x.to(cuda)), O.focal_freq_loss(b, x, pf, alpha)
+    (2.0 * la).backward(); (2.0 * lb).backward()
+    print(f"ffl {shape} pf {pf}: value {float(la.detach()):.6e} vs {float(lb.detach()):.6e}, grad rel {_rel(a.grad.cpu(), b.grad):.2e}")
+    assert abs(float(la.detach()) - float(lb.detach())) < 2e-4 * abs(float(lb.detach()))
+    assert _rel(a.grad.cpu(), b.grad) < 1e-3
+    loss = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="l1", freq_weight=3.0, freq_start_step=100, patch_factor=pf,
+                             ffl_alpha=alpha).to(cuda)
+    for step in (0, 600):
+        with torch.no_grad():
+            total, logs = loss(inputs=x.to(cuda), wvs=None, reconstructions=r0.to(cuda), global_step=step)
+        want, _, _ = O.consistency_loss(x, r0, "l1", 1.0, 0.0, step, 0, freq_weight=3.0, freq_start_step=100, patch_factor=pf,
+                                        ffl_alpha=alpha)
+        assert abs(float(total) - float(want)) < 2e-4 * abs(float(want))
+        assert ("train/loss_freq_raw" in logs) == (step >= 100)

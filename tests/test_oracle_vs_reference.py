@@ -205,3 +205,26 @@ def test_spectral_and_spatial_losses_match_reference(shape):
                                         spatial_start_step=10)
         assert torch.allclose(total, want, rtol=1e-6)
         assert ("train/loss_spatial" in logs) == (step >= 10) and "train/loss_spectral" in logs
+
+
+@pytest.mark.parametrize("shape,pf,alpha", [((2, 3, 32, 32), 2, 1.0), ((1, 12, 24, 36), 1, 1.0), ((2, 2, 28, 28), 2, 0.5)])
+def test_focal_frequency_loss_matches_reference(shape, pf, alpha):
+    """FocalFrequencyLoss (ffl.py:17-104) in EOConsistencyLoss's configuration, and the freq branch with its weight warm-up
+    (consistency_loss.py:442-463): oracle vs the unmodified reference, value and d/d(reconstruction)."""
+    ref = ref_shim.load_reference_losses()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(shape, generator=g)
+    r0 = x + 0.3 * torch.randn(shape, generator=g)
+    fn_ref = ref.FFL(loss_weight=1.0, alpha=alpha, patch_factor=pf, ave_spectrum=False, batch_matrix=True, log_matrix=True)
+    a, b = r0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+    la, lb = fn_ref(a, x), O.focal_freq_loss(b, x, pf, alpha)
+    la.backward(); lb.backward()
+    assert torch.allclose(la, lb, rtol=1e-5) and torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-8)
+    loss = ref.EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="l1", freq_weight=3.0, freq_start_step=100, patch_factor=pf,
+                                 ffl_alpha=alpha)
+    for step in (0, 100, 600, 5000):
+        total, logs = loss(inputs=x, wvs=None, reconstructions=r0, global_step=step)
+        want, _, _ = O.consistency_loss(x, r0, "l1", 1.0, 0.0, step, 0, freq_weight=3.0, freq_start_step=100, patch_factor=pf,
+                                        ffl_alpha=alpha)
+        assert torch.allclose(total, want, rtol=1e-5), step
+        assert ("train/loss_freq_raw" in logs) == (step >= 100)

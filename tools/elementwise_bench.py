@@ -77,6 +77,21 @@ ms = timeit(lambda: ops.msssim(a, b, 6.0))
 rows.append(("ms-ssim forward 16x12x256x256 (10/3 N s)", a.numel() * 4 * 10 / 3, ms))
 ms = timeit(lambda: ops.msssim_backward(a, b, 6.0, one))
 rows.append(("ms-ssim backward (fwd + adjoint, 6 N s)", a.numel() * 4 * 6, ms))
+# optional EOConsistencyLoss branches: forward = read both tensors, backward = read both + write the gradient
+ms = timeit(lambda: ops.sam_loss(a, b))
+rows.append(("sam forward 16x12x256x256", a.numel() * 8, ms))
+ms = timeit(lambda: ops.sam_loss_backward(a, b, 1e-8, one))
+rows.append(("sam backward", a.numel() * 12, ms))
+ms = timeit(lambda: ops.grad_diff_loss(a, b))
+rows.append(("gradient-difference forward", a.numel() * 8, ms))
+ms = timeit(lambda: ops.grad_diff_loss_backward(a, b, one))
+rows.append(("gradient-difference backward", a.numel() * 12, ms))
+ms = timeit(lambda: ops.focal_freq_loss(a, b, 2, 1.0))
+ffl_flop = 6 * 2 * 128 * a.numel()  # six real 128-wide DFT-matrix products over every element
+print(f"focal-frequency forward 16x12x256x256 (pf 2): {ms:.3f} ms = {ffl_flop / ms / 1e9:.1f} TFLOP/s fp32 SIMT (compute bound, not in the GB/s table)")
+_, ffl_ws = ops.focal_freq_loss(a, b, 2, 1.0, keep=True)
+ms = timeit(lambda: ops.focal_freq_loss_backward(tuple(a.shape), 2, one, ffl_ws))
+print(f"focal-frequency backward: {ms:.3f} ms = {ffl_flop / ms / 1e9:.1f} TFLOP/s fp32 SIMT")
 p = torch.softmax(torch.randn((16, 1024, 1024), device=dev), -1).bfloat16()
 dp = torch.randn((16, 1024, 1024), device=dev)
 ms = timeit(lambda: ops.softmax_backward(p, dp, 1024, 0.044))

@@ -58,6 +58,9 @@ SIGNATURES = {
     "eovae_focal_freq_loss_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "eovae_focal_freq_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _sz, _vp]),
     "eovae_focal_freq_loss_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "eovae_latent_resize_rot": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp]),
+    "eovae_latent_resize_rot_backward": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp]),
+    "eovae_area_resize_rot": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp]),
     "eovae_msssim_backward_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "eovae_msssim_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "eovae_conv2d_wgrad_nhwc_ok": (_i, [_i, _i]),

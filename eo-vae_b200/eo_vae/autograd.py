@@ -544,3 +544,18 @@ class FocalFreqLossFn(Function):
         (ws,) = ctx.saved_tensors
         shape, pf = ctx.cfg
         return ops.focal_freq_loss_backward(shape, pf, gl, ws), None, None, None
+
+
+class LatentResizeRotFn(Function):
+    """EQ-VAE latent transform: bilinear rescale then rot90 (new_autoencoder.py:460-464, 519-531) on one gather kernel;
+    backward = its adjoint (scatter of the four taps)."""
+
+    @staticmethod
+    def forward(ctx, z, size, rot_k):
+        ctx.cfg = (tuple(z.shape), size, rot_k)
+        return ops.latent_resize_rot(z, size, rot_k)
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, size, rot_k = ctx.cfg
+        return ops.latent_resize_rot_backward(g, shape, size, rot_k), None, None

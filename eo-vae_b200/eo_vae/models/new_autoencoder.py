@@ -281,15 +281,17 @@ class EOFluxVAE(LightningModule):
             return tape.act_to_nchw_f32(self.decoder.forward_act(h, wvs)), posterior
         # _static_eps: a device buffer the caller refills every step (eo_vae.graphs.GraphedTrainStep); default = CPU draw
         z = posterior.sample(getattr(self, '_static_eps', None)) if sample_posterior else posterior.mode()
-        if (self.training and scale is None and angle is None and self.latent_noise_p == 0 and self.bn.track_running_stats
+        if scale is not None or angle is not None:
+            # EQ-VAE transforms (:460-464): bilinear rescale + rot90 as one gather kernel (adjoint scatter in backward)
+            size = self._scaled_size(z.shape[-2:], scale) if scale is not None else None
+            k = 0 if angle is None else int(angle) % 4
+            z = tape.LatentResizeRotFn.apply(z, size, k) if tape.grad_mode() and z.requires_grad else \
+                ops.latent_resize_rot(z, size, k)
+        if (self.training and self.latent_noise_p == 0 and self.bn.track_running_stats
                 and self.bn.momentum is not None and z.is_cuda):
             # train-mode glue fused: unshuffle -> BN(batch stats, buffers updated) -> inverse BN -> shuffle -> activation
             h = tape.LatentTrainFn.apply(z, self.bn, self.bn_eps, compute_dtype())
             return tape.act_to_nchw_f32(self.decoder.forward_act(h, wvs)), posterior
-        if scale is not None:
-            z = self._apply_scale(z, scale)
-        if angle is not None:
-            z = torch.rot90(z, k=angle, dims=[-1, -2])
         z_normalized = self._normalize_latent(_unshuffle2(z))
         if self.training and random.random() < self.latent_noise_p:
             z_normalized = self.noising(z_normalized)
@@ -308,12 +310,17 @@ class EOFluxVAE(LightningModule):
         h = ops.latent_denorm(z, self.bn.running_mean, self.bn.running_var, self.bn_eps, compute_dtype())
         return tape.act_to_nchw_f32(self.decoder.forward_act(h, wvs))
 
-    def _apply_scale(self, z: Tensor, scale) -> Tensor:
-        h, w = z.shape[-2:]
+    def _scaled_size(self, hw, scale):
+        """(new_h, new_w) of the rescaled latent, multiples of the 2 x 2 packing (:519-527)."""
+        h, w = hw
         sh, sw = scale if isinstance(scale, (tuple, list)) else (scale, scale)
-        new_h = round(h * sh / self.ps[0]) * self.ps[0]
-        new_w = round(w * sw / self.ps[1]) * self.ps[1]
-        return F.interpolate(z, size=(new_h, new_w), mode='bilinear', align_corners=False)
+        return round(h * sh / self.ps[0]) * self.ps[0], round(w * sw / self.ps[1]) * self.ps[1]
+
+    def _apply_scale(self, z: Tensor, scale) -> Tensor:
+        size = self._scaled_size(z.shape[-2:], scale)
+        if tape.grad_mode() and z.requires_grad:
+            return tape.LatentResizeRotFn.apply(z, size, 0)
+        return ops.latent_resize_rot(z, size, 0)
 
     def _normalize_latent(self, z: Tensor) -> Tensor:
         self.bn.train() if self.training else self.bn.eval()
@@ -371,12 +378,12 @@ class EOFluxVAE(LightningModule):
             angle = random.choice([1, 2, 3])
             scale = (random.choice(bins), random.choice(bins)) if self.anisotropic else random.choice(bins)
             recon, _ = self.forward(images, wvs, scale=scale, angle=angle)
-            with torch.no_grad():
-                target = torch.rot90(F.interpolate(images, size=recon.shape[-2:], mode='area'), k=angle, dims=[-1, -2])
+            with torch.no_grad():  # area-average to the reconstruction size, then the same rotation (:618-624)
+                target = ops.area_resize_rot(images, tuple(recon.shape[-2:]), angle)
         elif random.random() < self.p_prior_s:
             recon, _ = self.forward(images, wvs, scale=random.choice(bins))
             with torch.no_grad():
-                target = F.interpolate(images, size=recon.shape[-2:], mode='area')
+                target = ops.area_resize_rot(images, tuple(recon.shape[-2:]), 0)
         else:
             recon, _ = self.forward(images, wvs)
         opt_gen.zero_grad()

@@ -434,6 +434,47 @@ def focal_freq_loss_backward(shape, patch_factor: int, grad_scale: torch.Tensor,
     return ga
 
 
+def _rot_shape(nh: int, nw: int, k: int):
+    return (nw, nh) if k & 1 else (nh, nw)
+
+
+def latent_resize_rot(z: torch.Tensor, size, rot_k: int) -> torch.Tensor:
+    """rot90(bilinear resize(z, size), k, dims=[-1, -2]) (new_autoencoder.py:460-464, 519-531); size None = rotation only."""
+    _need_cuda(z)
+    z = z.to(torch.float32).contiguous()
+    n, c, h, w = z.shape
+    nh, nw = (h, w) if size is None else size
+    oh, ow = _rot_shape(nh, nw, rot_k)
+    out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=z.device)
+    _C.check(_C.lib().eovae_latent_resize_rot(_ptr(z), n * c, h, w, nh, nw, int(rot_k) & 3, _ptr(out), _stream()),
+             "eovae_latent_resize_rot")
+    return out
+
+
+def latent_resize_rot_backward(grad_out: torch.Tensor, in_shape, size, rot_k: int) -> torch.Tensor:
+    _need_cuda(grad_out)
+    g = grad_out.to(torch.float32).contiguous()
+    n, c, h, w = in_shape
+    nh, nw = (h, w) if size is None else size
+    gz = torch.empty(in_shape, dtype=torch.float32, device=g.device)
+    _C.check(_C.lib().eovae_latent_resize_rot_backward(_ptr(g), n * c, h, w, nh, nw, int(rot_k) & 3, _ptr(gz), _stream()),
+             "eovae_latent_resize_rot_backward")
+    return gz
+
+
+def area_resize_rot(x: torch.Tensor, size, rot_k: int) -> torch.Tensor:
+    """rot90(F.interpolate(x, size, mode='area'), k, dims=[-1, -2]): the EQ-VAE reconstruction target (:611-636)."""
+    _need_cuda(x)
+    x = x.to(torch.float32).contiguous()
+    n, c, h, w = x.shape
+    nh, nw = size
+    oh, ow = _rot_shape(nh, nw, rot_k)
+    out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+    _C.check(_C.lib().eovae_area_resize_rot(_ptr(x), n * c, h, w, nh, nw, int(rot_k) & 3, _ptr(out), _stream()),
+             "eovae_area_resize_rot")
+    return out
+
+
 def msssim(pred: torch.Tensor, target: torch.Tensor, data_range: float = 6.0):
     """-> (mean MS-SSIM over the batch [1], per-sample MS-SSIM [B]); fp32 NCHW inputs."""
     _need_cuda(pred, target)

@@ -295,6 +295,14 @@ int eovae_focal_freq_loss(const float* pred, const float* target, int b, int c, 
                           int keep_for_backward, float* out, void* workspace, size_t workspace_bytes, void* stream);
 int eovae_focal_freq_loss_backward(int b, int c, int h, int w, int patch_factor, const float* grad_scale, float* grad_pred,
                                    void* workspace, size_t workspace_bytes, void* stream);
+/* ---- EQ-VAE transforms of the training step (new_autoencoder.py:460-464, 519-531, 611-636), fp32 NCHW contiguous ------
+ * out = torch.rot90(F.interpolate(z, size=(nh, nw), mode='bilinear', align_corners=False), k=rot_k, dims=[-1, -2]);
+ * out is [planes][nw][nh] when rot_k is odd, else [planes][nh][nw].  nh = h, nw = w: rotation only. */
+int eovae_latent_resize_rot(const float* z, long long planes, int h, int w, int nh, int nw, int rot_k, float* out, void* stream);
+int eovae_latent_resize_rot_backward(const float* grad_out, long long planes, int h, int w, int nh, int nw, int rot_k,
+                                     float* grad_z, void* stream);
+/* reconstruction target: torch.rot90(F.interpolate(x, size=(nh, nw), mode='area'), k=rot_k, dims=[-1, -2]) (no gradient) */
+int eovae_area_resize_rot(const float* x, long long planes, int h, int w, int nh, int nw, int rot_k, float* out, void* stream);
 /* gradient of eovae_msssim's batch-mean value wrt pred (fp32 NCHW), times the device scalar *grad_scale; the forward
  * pyramid is rebuilt inside the workspace (consistency_loss.py:24-37 adjoint) */
 size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w);

@@ -521,3 +521,71 @@ def test_focal_frequency_loss(cuda, shape, pf, alpha):
                                         ffl_alpha=alpha)
         assert abs(float(total) - float(want)) < 2e-4 * abs(float(want))
         assert ("train/loss_freq_raw" in logs) == (step >= 100)
+
+
+@pytest.mark.parametrize("shape,size,k", [((2, 8, 16, 16), (8, 8), 1), ((2, 8, 16, 16), (12, 12), 3), ((3, 4, 16, 24), (6, 18), 2),
+                                          ((1, 32, 32, 32), (16, 24), 1), ((2, 8, 16, 16), None, 1), ((2, 8, 16, 16), (6, 6), 0)])
+def test_latent_resize_rot_and_area_target(cuda, shape, size, k):
+    """eovae_latent_resize_rot (+ backward) and eovae_area_resize_rot vs the torch fp32 ops the reference calls
+    (F.interpolate bilinear / area, torch.rot90 with dims=[-1, -2]; new_autoencoder.py:460-464, 519-531, 614-624)."""
+    import torch.nn.functional as F
+    from eo_vae import autograd as tape
+    from eo_vae import ops
+    g = torch.Generator().manual_seed(4)
+    z = torch.randn(shape, generator=g)
+    a = z.clone().to(cuda).requires_grad_(True)
+    b = z.clone().requires_grad_(True)
+    out = tape.LatentResizeRotFn.apply(a, size, k)
+    ref = b if size is None else F.interpolate(b, size=size, mode="bilinear", align_corners=False)
+    ref = torch.rot90(ref, k=k, dims=[-1, -2])
+    assert out.shape == ref.shape
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) < 1e-5
+    sel = torch.randn(ref.shape, generator=g)
+    (out * sel.to(cuda)).sum().backward(); (ref * sel).sum().backward()
+    assert float((a.grad.cpu() - b.grad).abs().max()) < 1e-4
+    if size is not None:
+        x = torch.randn((shape[0], 3, shape[2] * 8, shape[3] * 8), generator=g)
+        big = (size[0] * 8, size[1] * 8)
+        t = ops.area_resize_rot(x.to(cuda), big, k)
+        t_ref = torch.rot90(F.interpolate(x, size=big, mode="area"), k=k, dims=[-1, -2])
+        assert t.shape == t_ref.shape and float((t.cpu() - t_ref).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("scale,angle", [(0.5, 1), (0.75, 3), (0.5, None)])
+def test_eq_vae_forward_and_training_step(cuda, scale, angle):
+    """EQ-VAE modes end to end on the tiny model: train-mode forward with scale / angle vs the oracle (same noise), and a
+    training_step with p_prior = 1 (latent equivariance mode) runs on the kernels and moves the parameters."""
+    import __graft_entry__ as g
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from oracle import eovae_oracle as O
+    from oracle.weights import TINY_CONFIG, WAVELENGTHS, make_state_dict, synthetic_patches
+    cfg = TINY_CONFIG
+    sd = make_state_dict(cfg, 6)
+    model = g._model(cfg, sd, cuda)
+    model.train()
+    wvs = torch.tensor(WAVELENGTHS["S2RGB"])
+    x = synthetic_patches(2, 3, cfg["resolution"], seed=83)
+    hl = cfg["resolution"] // 2 ** (len(cfg["ch_mult"]) - 1)
+    torch.manual_seed(7)
+    eps = torch.randn((2, cfg["z_channels"], hl, hl))
+    torch.manual_seed(7)
+    with torch.no_grad():
+        recon, _ = model(x.to(cuda), wvs.to(cuda), scale=scale, angle=angle)
+    recon_ref, _ = O.forward(sd, x, wvs, eps=eps, train=True, heads=cfg["hyper_heads"], scale=scale, angle=angle)
+    assert recon.shape == recon_ref.shape
+    err = _rel(recon.cpu(), recon_ref)
+    print(f"eq-vae forward scale {scale} angle {angle}: recon rel-L2 {err:.3e}")
+    assert err < 4e-2
+    if angle is not None:
+        import random
+        from eo_vae import _lightning  # noqa: F401
+        model2 = g._model(cfg, make_state_dict(cfg, 6), cuda)
+        model2.train()
+        model2.p_prior = 1.0
+        model2.loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="char").to(cuda)
+        before = {k: v.detach().clone() for k, v in model2.named_parameters()}
+        random.seed(3)
+        loss = model2.training_step({model2.image_key: x.to(cuda), "wvs": wvs.to(cuda)}, 0)
+        assert float(loss) == float(loss)
+        moved = sum(not torch.equal(v.detach(), before[k]) for k, v in model2.named_parameters())
+        assert moved > 100

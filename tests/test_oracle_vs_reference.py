@@ -228,3 +228,26 @@ def test_focal_frequency_loss_matches_reference(shape, pf, alpha):
                                         ffl_alpha=alpha)
         assert torch.allclose(total, want, rtol=1e-5), step
         assert ("train/loss_freq_raw" in logs) == (step >= 100)
+
+
+@pytest.mark.parametrize("scale,angle", [(0.5, 1), (0.75, 3), ((0.375, 0.75), 2), (0.5, None), (None, 1)])
+def test_eq_vae_transforms_match_reference(scale, angle):
+    """EQ-VAE modes (new_autoencoder.py:460-464, 519-531, 605-627): train-mode forward with a rescaled / rotated latent and
+    the area-averaged, rotated target - oracle vs the unmodified reference (same posterior noise)."""
+    cfg = TINY_CONFIG
+    sd = make_state_dict(cfg, 6)
+    model = ref_shim.build_reference_model(cfg, sd, train=True)
+    wvs = torch.tensor(WAVELENGTHS["S2RGB"])
+    x = synthetic_patches(2, 3, 64, seed=83)
+    torch.manual_seed(7)
+    with torch.no_grad():
+        recon_ref, post = model(x, wvs, scale=scale, angle=angle)
+        torch.manual_seed(7)
+        eps = torch.randn(post.mean.shape)
+        recon, _ = O.forward(sd, x, wvs, eps=eps, train=True, heads=cfg["hyper_heads"], scale=scale, angle=angle)
+    assert recon.shape == recon_ref.shape and torch.allclose(recon, recon_ref, atol=1e-4)
+    import torch.nn.functional as F
+    t_ref = F.interpolate(x, size=recon_ref.shape[-2:], mode="area")
+    if angle is not None:
+        t_ref = torch.rot90(t_ref, k=angle, dims=[-1, -2])
+    assert torch.equal(O.eq_target(x, recon_ref.shape[-2:], angle), t_ref)

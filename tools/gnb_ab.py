@@ -1,4 +1,6 @@
-"""A/B of the fused GroupNorm-backward reduce (ops.USE_FUSED_GN_BWD_REDUCE) on the training step + an encode step timing."""
+"""A/B of the fused GroupNorm-backward reduce (ops.USE_FUSED_GN_BWD_REDUCE) on the training step + an encode step timing.
+The flag only exists with profiles/r1_gn_bwd_epilogue_experiment.patch applied (experiment measured, not adopted); without
+it both arms time the same two-pass path."""
 import os
 import sys
 

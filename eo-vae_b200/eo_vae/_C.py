@@ -61,6 +61,8 @@ SIGNATURES = {
     "eovae_latent_resize_rot": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp]),
     "eovae_latent_resize_rot_backward": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp]),
     "eovae_area_resize_rot": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp]),
+    "eovae_grad_norm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "eovae_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _i, _vp, _f, _vp]),
     "eovae_msssim_backward_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "eovae_msssim_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "eovae_conv2d_wgrad_nhwc_ok": (_i, [_i, _i]),

@@ -124,9 +124,8 @@ class GraphedTrainStep:
             m._grad_sync.finish()
         opts = m.optimizers()
         opt = opts[0] if isinstance(opts, list) else opts
-        if m.clip_grad:
-            torch.nn.utils.clip_grad_norm_(opt.param_groups[0]['params'], m.clip_grad)
-        opt.step()
+        from .models.new_autoencoder import _clip_and_step
+        _clip_and_step(opt, m.clip_grad)
         schs = m.lr_schedulers()
         sch = schs[0] if isinstance(schs, list) and schs else schs
         if sch:

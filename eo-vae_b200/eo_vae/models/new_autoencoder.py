@@ -46,6 +46,18 @@ def get_cosine_schedule_with_warmup(optimizer: Optimizer, num_warmup_steps: int,
     return LambdaLR(optimizer, scale)
 
 
+def _clip_and_step(opt, clip_grad) -> None:
+    """clip_grad_norm_(params, clip_grad) + opt.step() (:650-657); one fused pass when the optimiser supports it
+    (eo_vae.optim.FusedClipAdam, possibly behind a LightningOptimizer wrapper)."""
+    core = getattr(opt, 'optimizer', opt)
+    if getattr(core, 'fused_clip', False):
+        opt.step(clip_norm=clip_grad or None)
+        return
+    if clip_grad:
+        torch.nn.utils.clip_grad_norm_(opt.param_groups[0]['params'], clip_grad)
+    opt.step()
+
+
 def _unshuffle2(z: Tensor) -> Tensor:
     """'c (i pi) (j pj) -> (c pi pj) i j', pi = pj = 2 (index permutation only)."""
     *lead, c, h, w = z.shape
@@ -344,10 +356,14 @@ class EOFluxVAE(LightningModule):
     def configure_optimizers(self):
         params = [p for p in self.encoder.parameters() if p.requires_grad] + \
                  [p for p in self.decoder.parameters() if p.requires_grad]
-        # same optimiser as the reference (:556); torch's fused implementation (one multi-tensor kernel instead of ~10
-        # foreach passes over the 95.5 M parameters) when everything lives on the GPU
-        fused = bool(params) and all(p.is_cuda and p.dtype == torch.float32 for p in params)
-        optimizers = [torch.optim.Adam(params, lr=self.base_lr, fused=fused)]
+        # same optimiser as the reference (:556).  With everything on the GPU: the multi-tensor Adam of csrc/optimizer.cu,
+        # a torch.optim.Adam subclass (same state_dict) whose step(clip_norm=...) folds clip_grad_norm_ into the update
+        on_gpu = bool(params) and all(p.is_cuda and p.dtype == torch.float32 for p in params)
+        if on_gpu:
+            from ..optim import FusedClipAdam
+            optimizers = [FusedClipAdam(params, lr=self.base_lr)]
+        else:
+            optimizers = [torch.optim.Adam(params, lr=self.base_lr)]
         if hasattr(self.loss_fn, 'discriminator'):
             optimizers.append(torch.optim.Adam(self.loss_fn.discriminator.parameters(), lr=self.base_lr))
         schedulers = []
@@ -390,9 +406,7 @@ class EOFluxVAE(LightningModule):
         gen_loss, logs = self.loss_fn(inputs=target, wvs=wvs, reconstructions=recon, optimizer_idx=0,
                                       global_step=self.global_step, last_layer=None, split='train')
         self.manual_backward(gen_loss)
-        if self.clip_grad:
-            torch.nn.utils.clip_grad_norm_(opt_gen.param_groups[0]['params'], self.clip_grad)
-        opt_gen.step()
+        _clip_and_step(opt_gen, self.clip_grad)
         if sch_gen:
             sch_gen.step()
         logs['train/lr'] = opt_gen.param_groups[0]['lr']

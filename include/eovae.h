@@ -303,6 +303,18 @@ int eovae_latent_resize_rot_backward(const float* grad_out, long long planes, in
                                      float* grad_z, void* stream);
 /* reconstruction target: torch.rot90(F.interpolate(x, size=(nh, nw), mode='area'), k=rot_k, dims=[-1, -2]) (no gradient) */
 int eovae_area_resize_rot(const float* x, long long planes, int h, int w, int nh, int nw, int rot_k, float* out, void* stream);
+/* ---- optimiser half of the training step (new_autoencoder.py:549-557 torch.optim.Adam(lr); :650-657 clip_grad_norm_ +
+ * step), multi-tensor, fp32.  The tensors are described by DEVICE tables the caller builds: pointer arrays [T], sizes [T]
+ * (elements) and a chunk table (chunk i covers elements [chunk_offset[i], + chunk_elems) of tensor chunk_tensor[i]).
+ * eovae_grad_norm: *out_norm = sqrt(sum over all tensors of g^2) (fixed-slot partials [num_chunks], deterministic).
+ * eovae_adam_step: torch.optim.Adam's update (no weight decay / amsgrad / maximize) at step number `step` (1-based) with
+ * g scaled by min(max_norm / (*grad_norm + 1e-6), 1) when grad_norm != NULL and max_norm > 0 (clip_grad_norm_ folded in). */
+int eovae_grad_norm(const float* const* grads, const long long* sizes, const int* chunk_tensor, const long long* chunk_offset,
+                    int num_chunks, int chunk_elems, float* partial, float* out_norm, void* stream);
+int eovae_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                    const long long* sizes, const int* chunk_tensor, const long long* chunk_offset, int num_chunks,
+                    int chunk_elems, float lr, float beta1, float beta2, float eps, int step, const float* grad_norm,
+                    float max_norm, void* stream);
 /* gradient of eovae_msssim's batch-mean value wrt pred (fp32 NCHW), times the device scalar *grad_scale; the forward
  * pyramid is rebuilt inside the workspace (consistency_loss.py:24-37 adjoint) */
 size_t eovae_msssim_backward_workspace_bytes(int b, int c, int h, int w);

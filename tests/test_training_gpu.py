@@ -443,3 +443,36 @@ def test_weight_distillation_loop(cuda, generator):
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+@pytest.mark.parametrize("clip", [None, 1.0, 1e-3])
+def test_fused_clip_adam_matches_torch(cuda, clip):
+    """eovae_grad_norm + eovae_adam_step (FusedClipAdam) vs clip_grad_norm_ + torch.optim.Adam over several steps on tensors
+    of awkward sizes (odd lengths, a scalar, > one chunk), including the state_dict layout."""
+    from eo_vae.optim import FusedClipAdam
+    g = torch.Generator().manual_seed(2)
+    shapes = [(3,), (), (257, 129), (70001,), (64, 3, 3, 3), (5, 7)]
+    pa = [torch.randn(s, generator=g).to(cuda).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa, ob = FusedClipAdam(pa, lr=3e-3), torch.optim.Adam(pb, lr=3e-3)
+    for it in range(5):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).to(cuda) * (10.0 if it % 2 else 0.1)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        if clip:
+            want_norm = torch.nn.utils.clip_grad_norm_(pb, clip)
+        oa.step(clip_norm=clip)
+        ob.step()
+        if clip:
+            assert abs(float(oa.last_grad_norm) - float(want_norm)) < 1e-5 * float(want_norm)
+        for a, b in zip(pa, pb):
+            assert float((a - b).abs().max()) < 2e-6 + 1e-5 * float(b.abs().max()), (it, tuple(a.shape))
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["param_groups"][0]["lr"] == sb["param_groups"][0]["lr"] and set(sa["state"].keys()) == set(sb["state"].keys())
+    for k in sa["state"]:
+        assert set(sa["state"][k].keys()) == set(sb["state"][k].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 5.0
+        for key in ("exp_avg", "exp_avg_sq"):   # fma vs mul + addcmul rounding: a few ulp
+            assert float((sa["state"][k][key] - sb["state"][k][key]).abs().max()) < 1e-6 + 1e-4 * float(sb["state"][k][key].abs().max())
+    ob.load_state_dict(sa)      # interchangeable checkpoints
+    oa.load_state_dict(sb)

@@ -1,7 +1,7 @@
 """Data-parallel gradient exchange for the training step: replicated parameters, one all-reduce
 (sum, then / world) of the gradients per step, bucketed in reverse registration order (~ the order backward produces
 them) and launched asynchronously from post-accumulate hooks so NCCL traffic over NVLink overlaps the remaining
-backward kernels.  ``finish()`` (called by ``manual_backward``) waits, averages and scatters the buckets back.
+backward kernels.  ``finish()`` (called by ``manual_backward``) waits and hands the averaged buckets back as gradient views (no copy).
 
 Plumbing only: ``torch.distributed`` does the transport (NCCL on GPUs; gloo in the CPU tests)."""
 from __future__ import annotations
@@ -44,9 +44,23 @@ class GradSync:
         self._launched[i] = True
         if not ps:
             return
-        flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in ps])
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._inflight.append((work, flat, ps))
+        # one flat fp32 buffer per bucket; every gradient starts on a 16-byte boundary (zero pads in between) so the views
+        # handed back in finish() keep the vectorised path of the optimiser kernels
+        pieces, offs, off = [], [], 0
+        for p in ps:
+            n = p.numel()
+            pieces.append(p.grad.reshape(-1).to(torch.float32))
+            offs.append(off)
+            off += n
+            pad = (-n) % 4
+            if pad:
+                pieces.append(torch.zeros((pad,), dtype=torch.float32, device=p.grad.device))
+                off += pad
+        flat = torch.cat(pieces)
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then divide in finish()
+        avg = dist.get_backend(self.group) == "nccl"
+        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._inflight.append((work, flat, ps, offs, avg))
 
     def _on_grad(self, p) -> None:
         if not self.overlap:
@@ -61,14 +75,12 @@ class GradSync:
         for i in range(len(self.buckets)):
             if not self._launched[i]:
                 self._launch(i)
-        for work, flat, ps in self._inflight:
+        for work, flat, ps, offs, avg in self._inflight:
             work.wait()
-            flat.div_(self.world)
-            off = 0
-            for p in ps:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+            if not avg:
+                flat.div_(self.world)
+            for p, off in zip(ps, offs):   # the averaged gradients are VIEWS of the bucket: no copy back
+                p.grad = flat[off:off + p.numel()].view_as(p)
         self._inflight.clear()
         self._pending = [len(b) for b in self.buckets]
         self._launched = [False] * len(self.buckets)

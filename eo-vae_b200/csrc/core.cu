@@ -63,6 +63,55 @@ __global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, T* __
   out[i] = T16<T>::from_f(v);
 }
 
+// Coalesced versions of the two packs (every conv weight is re-packed twice per training step: forward operand and data-
+// gradient operand).  Forward: one block per output channel stages w[o] ([cin][taps] fp32, contiguous) in shared memory and
+// writes out[o][tap][0..kpt) as 32-bit pairs.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_conv_weight_tiled_kernel(const float* __restrict__ w, T* __restrict__ out, int cout,
+                                                                     int cin, int taps, int kpt) {
+  extern __shared__ float sm[];
+  const int o = blockIdx.x;
+  const int n = cin * taps;
+  if (o < cout)
+    for (int i = threadIdx.x; i < n; i += 256) sm[i] = w[static_cast<long long>(o) * n + i];
+  __syncthreads();
+  const int half = kpt >> 1;
+  uint32_t* orow = reinterpret_cast<uint32_t*>(out + static_cast<long long>(o) * taps * kpt);
+  for (int i = threadIdx.x; i < taps * half; i += 256) {
+    const int tap = i / half, c = 2 * (i % half);
+    const float v0 = (o < cout && c < cin) ? sm[c * taps + tap] : 0.f;
+    const float v1 = (o < cout && c + 1 < cin) ? sm[(c + 1) * taps + tap] : 0.f;
+    orow[i] = T16<T>::from_f2(v0, v1);
+  }
+}
+
+// Data-gradient operand out[ci][tap][co] = w[co][ci][taps-1-tap]: a (64 co) x (16 ci) tile goes through shared memory so that
+// both the fp32 reads (16 * taps contiguous floats per co) and the 16-bit writes (64 contiguous co per (ci, tap)) coalesce.
+constexpr int PD_CO = 64, PD_CI = 16;
+template <typename T>
+__global__ void __launch_bounds__(256) pack_conv_weight_dgrad_tiled_kernel(const float* __restrict__ w, T* __restrict__ out,
+                                                                           int cout, int cin, int cin_pad, int taps, int kpt) {
+  __shared__ float sm[PD_CO][PD_CI * 9 + 1];
+  const int ci0 = blockIdx.x * PD_CI, co0 = blockIdx.y * PD_CO;
+  const int seg = PD_CI * taps;
+  for (int i = threadIdx.x; i < PD_CO * seg; i += 256) {
+    const int r = i / seg, j = i % seg;
+    const int co = co0 + r, ci = ci0 + j / taps;
+    sm[r][j] = (co < cout && ci < cin) ? w[(static_cast<long long>(co) * cin + ci0) * taps + j] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < seg * (PD_CO / 2); i += 256) {
+    const int pair = i % (PD_CO / 2), t = i / (PD_CO / 2);
+    const int tap = t % taps, cil = t / taps;
+    const int ci = ci0 + cil, co = co0 + 2 * pair;
+    if (ci < cin_pad && co < kpt) {
+      const int src = cil * taps + (taps - 1 - tap);
+      *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(ci) * taps + tap) * kpt + co) =
+          T16<T>::from_f2(sm[2 * pair][src], sm[2 * pair + 1][src]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void pack_dyn_weight_kernel(const float* __restrict__ wk, int c, int embed, int decoder, float scale,
                                        T* __restrict__ packed, int kpt, int rows_pad, float* __restrict__ oihw,
@@ -106,6 +155,16 @@ int eovae_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, in
   const int kpt = eovae_conv_k_per_tap(cin);
   const long long total = static_cast<long long>(round_up(cout, 16)) * taps * kpt;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  const size_t stage = sizeof(float) * static_cast<size_t>(cin) * taps;
+  if (stage <= 40 * 1024 && (dtype == EOVAE_BF16 || dtype == EOVAE_F16)) {  // coalesced path: one block per output channel
+    const int rows = round_up(cout, 16);
+    if (dtype == EOVAE_BF16)
+      pack_conv_weight_tiled_kernel<__nv_bfloat16><<<rows, 256, stage, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, taps, kpt);
+    else
+      pack_conv_weight_tiled_kernel<__half><<<rows, 256, stage, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, taps, kpt);
+    EOVAE_LAUNCH_CHECK();
+    return 0;
+  }
   if (dtype == EOVAE_BF16)
     pack_conv_weight_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, taps, kpt, total);
   else if (dtype == EOVAE_F16)
@@ -124,6 +183,16 @@ int eovae_pack_conv_weight_dgrad(const float* w_oihw, void* out, int cout, int c
   const int kpt = eovae_conv_k_per_tap(round_up(cout, 8));
   const long long total = static_cast<long long>(round_up(cin, 16)) * taps * kpt;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == EOVAE_BF16 || dtype == EOVAE_F16) {  // coalesced path: (64 co) x (16 ci) tiles through shared memory
+    const int cin_pad = round_up(cin, 16);
+    dim3 tg(cin_pad / PD_CI, ceil_div(kpt, PD_CO));
+    if (dtype == EOVAE_BF16)
+      pack_conv_weight_dgrad_tiled_kernel<__nv_bfloat16><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, cin_pad, taps, kpt);
+    else
+      pack_conv_weight_dgrad_tiled_kernel<__half><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, cin_pad, taps, kpt);
+    EOVAE_LAUNCH_CHECK();
+    return 0;
+  }
   if (dtype == EOVAE_BF16)
     pack_conv_weight_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, taps, kpt, total);
   else if (dtype == EOVAE_F16)

@@ -589,3 +589,26 @@ def test_eq_vae_forward_and_training_step(cuda, scale, angle):
         assert float(loss) == float(loss)
         moved = sum(not torch.equal(v.detach(), before[k]) for k, v in model2.named_parameters())
         assert moved > 100
+
+
+@pytest.mark.parametrize("cout,cin,k", [(128, 128, 3), (512, 256, 3), (64, 512, 3), (12, 128, 3), (128, 12, 3), (24, 40, 3),
+                                        (512, 512, 1), (64, 64, 1), (32, 8, 1), (256, 1024, 3)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_weight_pack_layouts(cuda, cout, cin, k, dtype):
+    """eovae_pack_conv_weight / eovae_pack_conv_weight_dgrad (coalesced shared-memory kernels): exact bits of the K-major
+    forward operand [round_up(cout,16)][taps][k_per_tap] and of the data-gradient operand (taps flipped, channels swapped),
+    zero padding included."""
+    from eo_vae import ops
+    g = torch.Generator().manual_seed(cout * 131 + cin)
+    w = torch.randn((cout, cin, k, k), generator=g)
+    taps = k * k
+    fwd = ops.pack_conv_weight(w.to(cuda), dtype).cpu()
+    rows, kpt = fwd.shape[0], fwd.shape[2]
+    want = torch.zeros((rows, taps, kpt), dtype=dtype)
+    want[:cout, :, :cin] = w.reshape(cout, cin, taps).permute(0, 2, 1).to(dtype)
+    assert fwd.shape == want.shape and torch.equal(fwd, want)
+    dg = ops.pack_conv_weight_dgrad(w.to(cuda), dtype).cpu()
+    rows, kpt = dg.shape[0], dg.shape[2]
+    want = torch.zeros((rows, taps, kpt), dtype=dtype)
+    want[:cin, :, :cout] = w.reshape(cout, cin, taps).flip(2).permute(1, 2, 0).to(dtype)
+    assert dg.shape == want.shape and torch.equal(dg, want)

@@ -162,7 +162,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("EOVAE_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # keep stdout to the ONE JSON line: NCCL writes its banner ("NCCL version ...") and warnings to its debug file,
+        # which defaults to stdout - send it to a per-process file instead
+        os.environ["NCCL_DEBUG"] = os.environ.get("EOVAE_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/eovae_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     if not os.path.exists(g.LIB):
         raise RuntimeError("libeovae_sm100.so missing - run __graft_entry__.build() first")

@@ -36,7 +36,14 @@ def launch_count() -> int:
     return int(_C.lib().eovae_launch_count())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (raw handle: ~10x cheaper than building a
+    torch.cuda.Stream object for each of the ~550 launches of a training step)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -39,7 +39,7 @@ model.train()
 model.loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="char", msssim_weight=1.0, msssim_start_step=ms_start).to(dev)
 model.clip_grad = 1.0
 if world > 1:
-    model.enable_ddp()
+    model.enable_ddp(int(os.environ.get("EOVAE_DDP_BUCKET_MB", "64")) << 20)
 wvs = torch.tensor(WAVELENGTHS["S2L2A"], device=dev)
 gen = torch.Generator(device=dev).manual_seed(1234 + rank)
 x = torch.randn((batch, 12, 256, 256), device=dev, generator=gen).clamp_(-2, 6)

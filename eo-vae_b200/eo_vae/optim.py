@@ -50,7 +50,7 @@ class FusedClipAdam(torch.optim.Adam):
             with torch.enable_grad():
                 loss = closure()
         lib = _C.lib()
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = None
         for gi, group in enumerate(self.param_groups):
             ps = [p for p in group['params'] if p.grad is not None]
             if not ps:
@@ -79,6 +79,8 @@ class FusedClipAdam(torch.optim.Adam):
             if len(steps) != 1:
                 raise RuntimeError('FusedClipAdam: parameters of one group must share the step count')
             dev = ps[0].device
+            if stream is None:
+                stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             ct, co, sizes, nchunks = self._chunk_table([p.numel() for p in ps], dev)
             ptrs = torch.tensor([[t.data_ptr() for t in lst] for lst in (ps, gs, ms, vs)], dtype=torch.int64).to(dev, non_blocking=True)
             norm = None

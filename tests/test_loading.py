@@ -162,3 +162,22 @@ def test_from_pretrained_uses_hub_files(tmp_path, monkeypatch):
     assert calls == [("nilsleh/eo-vae", "model_config.yaml", "main", True), ("nilsleh/eo-vae", "eo-vae.ckpt", "main", True)]
     _same(model.state_dict(), sd)
     assert not model.training
+
+
+def test_optimizer_selection_and_no_cpu_path():
+    """configure_optimizers (new_autoencoder.py:549-585): plain torch Adam while the model lives on the CPU (construction /
+    checkpoint handling only); the kernel-backed FusedClipAdam refuses CPU tensors instead of falling back."""
+    from eo_vae.models.new_autoencoder import EOFluxVAE  # noqa: F401
+    from eo_vae.optim import FusedClipAdam
+    import __graft_entry__ as g
+    cfg = TINY_CONFIG
+    model = g._model(cfg, make_state_dict(cfg, 16), torch.device("cpu"))
+    opt = model.configure_optimizers()
+    opt = opt[0] if isinstance(opt, (list, tuple)) else opt
+    assert type(opt) is torch.optim.Adam and opt.param_groups[0]["lr"] == model.base_lr
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FusedClipAdam([p], lr=1e-3).step(clip_norm=1.0)
+    with pytest.raises(NotImplementedError):
+        FusedClipAdam([p], lr=1e-3, weight_decay=0.1)

@@ -11,6 +11,26 @@ try:  # pragma: no cover - depends on the environment
 except Exception:  # noqa: BLE001
     HAVE_LIGHTNING = False
 
+    class _CountingOptimizer:
+        """What ``LightningOptimizer`` does for manual optimisation: forwards to the wrapped optimiser (``.optimizer``)
+        and advances the module's ``global_step`` once per ``step()`` call, so ``*_start_step`` loss schedules and
+        warm-ups move under a plain loop exactly as they do under ``Trainer.fit``."""
+
+        def __init__(self, optimizer, module) -> None:
+            self.__dict__['optimizer'] = optimizer
+            self.__dict__['_module'] = module
+
+        def step(self, *args, **kwargs):
+            out = self.optimizer.step(*args, **kwargs)
+            self._module.global_step += 1
+            return out
+
+        def __getattr__(self, name):
+            return getattr(self.__dict__['optimizer'], name)
+
+        def __setattr__(self, name, value):
+            setattr(self.__dict__['optimizer'], name, value)
+
     class LightningModule(torch.nn.Module):  # type: ignore[no-redef]
         def __init__(self) -> None:
             super().__init__()
@@ -35,7 +55,8 @@ except Exception:  # noqa: BLE001
                 self._schedulers = [s['scheduler'] if isinstance(s, dict) else s for s in schs]
             else:
                 opts, self._schedulers = cfg, []
-            self._optimizers = list(opts) if isinstance(opts, (list, tuple)) else [opts]
+            opts = list(opts) if isinstance(opts, (list, tuple)) else [opts]
+            self._optimizers = [_CountingOptimizer(o, self) for o in opts]
 
         def optimizers(self):
             if self._optimizers is None:

@@ -77,6 +77,9 @@ class GraphedTrainStep:
         model._static_eps = self.eps
         if getattr(model, "_grad_sync", None) is not None:
             model._grad_sync.overlap = False  # autograd hooks do not run on replay: exchange after the graph instead
+        self._refresh = getattr(model.loss_fn, 'refresh_graph_scalars', None)
+        if self._refresh is not None:
+            self._refresh(model.global_step, dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -104,7 +107,7 @@ class GraphedTrainStep:
         m = self.model
         recon, _ = m(self.x, self.wvs)
         loss, self.logs = m.loss_fn(inputs=self.x, wvs=self.wvs, reconstructions=recon, optimizer_idx=0,
-                                    global_step=m.global_step, last_layer=None, split='train')
+                                    global_step=m.global_step, last_layer=m.get_last_layer(), split='train')
         loss.backward()
         return loss.detach()
 
@@ -117,6 +120,8 @@ class GraphedTrainStep:
             self.x.copy_(x, non_blocking=True)
         self.wvs.copy_(batch["wvs"], non_blocking=True)
         self.eps.copy_(torch.randn(self.eps_shape), non_blocking=False)
+        if self._refresh is not None:   # global_step-dependent loss scalars live in device memory the graph reads
+            self._refresh(m.global_step, self.eps.device)
         self.graph.replay()
         for p, g in zip(self.params, self.grads):
             p.grad = g

@@ -2,9 +2,9 @@
 
 Interface mirror of the reference ``eo_vae/models/modules/consistency_loss.py`` (CharbonnierLoss :12-21, SSIMLoss
 :24-37, EOConsistencyLoss :329-483): same constructor arguments, ``forward(inputs, wvs, reconstructions,
-global_step, split, **kwargs) -> (total, logs)`` and log keys.  The spectral / gradient / FFL / DOFA-feature
-branches have weight 0 in the shipped config (configs/eo-vae.yaml:26-31) and are outside the built hot path: asking
-for them raises instead of silently computing something else.
+global_step, split, **kwargs) -> (total, logs)`` and log keys.  Pixel (L1 / Charbonnier), MS-SSIM, spectral-angle,
+gradient-difference and focal-frequency branches all run on the reduction kernels (values and gradients); only the
+DOFA semantic-feature branch (``feature_weight > 0``: needs an external pretrained network) raises.
 """
 from __future__ import annotations
 
@@ -107,6 +107,20 @@ class EOConsistencyLoss(nn.Module):
                                            batch_matrix=True, log_matrix=True)
         self.char_loss = CharbonnierLoss()
         self.msssim_loss = SSIMLoss()
+        self._graph_ffl = None   # device scalar read by a CAPTURED step (see refresh_graph_scalars)
+
+    def ffl_weight_at(self, global_step: int) -> float:
+        """freq_weight x linear warm-up over 1000 steps after freq_start_step (consistency_loss.py:443-452)."""
+        warmup = min(1.0, max(0.0, (global_step - self.starts['freq']) / 1000))
+        return self.weights['freq'] * warmup
+
+    def refresh_graph_scalars(self, global_step: int, device) -> None:
+        """Every ``global_step``-dependent scalar of the loss, as device memory a CUDA graph reads at replay time.  A
+        Python float would be frozen into the captured kernels (the warm-up would stay at its capture-time value
+        forever); ``eo_vae.graphs.GraphedTrainStep`` calls this before the capture and before every replay."""
+        if self._graph_ffl is None or self._graph_ffl.device != torch.device(device):
+            self._graph_ffl = torch.zeros((), dtype=torch.float32, device=device)
+        self._graph_ffl.fill_(self.ffl_weight_at(global_step))
 
     def forward(self, inputs: torch.Tensor, wvs: torch.Tensor, reconstructions: torch.Tensor, global_step: int = 0,
                 split: str = 'train', **kwargs):
@@ -130,11 +144,17 @@ class EOConsistencyLoss(nn.Module):
             logs[f'{split}/loss_spatial'] = l_spat.detach()
         if self.weights['freq'] > 0 and global_step >= self.starts['freq']:
             raw = self.fft_loss(reconstructions, inputs)
-            warmup = min(1.0, max(0.0, (global_step - self.starts['freq']) / 1000))   # consistency_loss.py:443-452
-            current = self.weights['freq'] * warmup
+            if inputs.is_cuda and torch.cuda.is_current_stream_capturing():
+                if self._graph_ffl is None:
+                    raise RuntimeError('EOConsistencyLoss: call refresh_graph_scalars(global_step, device) before capturing '
+                                       'a step with freq_weight > 0 (the warm-up must not be baked into the graph)')
+                current = self._graph_ffl          # device scalar, refilled by the caller before each replay
+                logs[f'{split}/ffl_weight'] = current
+            else:
+                current = self.ffl_weight_at(global_step)
+                logs[f'{split}/ffl_weight'] = torch.tensor(current)
             total = total + raw * current
             logs[f'{split}/loss_freq_raw'] = raw.detach()
-            logs[f'{split}/ffl_weight'] = torch.tensor(current)
         if self.weights['msssim'] > 0 and global_step >= self.starts['msssim']:
             l_msssim = self.msssim_loss(reconstructions, inputs)
             total = total + self.weights['msssim'] * l_msssim

@@ -381,12 +381,15 @@ class EOFluxVAE(LightningModule):
         ``manual_backward`` runs the hand-written backward kernels (conv dgrad / wgrad, GroupNorm, attention,
         hypernetwork, reparameterisation, Charbonnier / L1 and MS-SSIM adjoints); under ``enable_ddp()`` the gradients
         are averaged over the ranks while backward is still running (eo_vae/ddp.py)."""
-        if getattr(self, 'graph_training', False) and not (self.p_prior or self.p_prior_s or self.latent_noise_p):
+        has_disc = hasattr(self.loss_fn, 'discriminator')
+        if (getattr(self, 'graph_training', False) and not has_disc
+                and not (self.p_prior or self.p_prior_s or self.latent_noise_p)):
             return self._graphed_training_step(batch)
-        opts = self.optimizers()
-        opt_gen = opts[0] if isinstance(opts, list) else opts
-        schs = self.lr_schedulers()
-        sch_gen = schs[0] if isinstance(schs, list) and schs else schs
+        opts, schs = self.optimizers(), self.lr_schedulers()
+        opts = opts if isinstance(opts, list) else [opts]
+        schs = schs if isinstance(schs, list) else ([schs] if schs else [])
+        opt_gen, opt_disc = opts[0], (opts[1] if len(opts) > 1 else None)
+        sch_gen, sch_disc = (schs[0] if schs else None), (schs[1] if len(schs) > 1 else None)
         images, wvs = batch[self.image_key], batch['wvs']
         bins = [0.375, 0.5, 0.75]
         target = images
@@ -402,13 +405,29 @@ class EOFluxVAE(LightningModule):
                 target = ops.area_resize_rot(images, tuple(recon.shape[-2:]), 0)
         else:
             recon, _ = self.forward(images, wvs)
+        # generator half (:638-657)
         opt_gen.zero_grad()
+        if opt_disc is not None and has_disc:
+            self.loss_fn.discriminator.eval()
         gen_loss, logs = self.loss_fn(inputs=target, wvs=wvs, reconstructions=recon, optimizer_idx=0,
-                                      global_step=self.global_step, last_layer=None, split='train')
+                                      global_step=self.global_step, last_layer=self.get_last_layer(), split='train')
         self.manual_backward(gen_loss)
         _clip_and_step(opt_gen, self.clip_grad)
         if sch_gen:
             sch_gen.step()
+        # discriminator half (:659-684): only for a user-supplied GAN loss exposing discriminator / disc_start / disc_weight
+        # (such losses are torch modules outside the built path; the control flow around them is the reference's)
+        if (opt_disc is not None and self.global_step >= self.loss_fn.disc_start and self.loss_fn.disc_weight > 0.0):
+            if has_disc:
+                self.loss_fn.discriminator.train()
+            opt_disc.zero_grad()
+            disc_loss, disc_logs = self.loss_fn(inputs=target, wvs=wvs, reconstructions=recon.detach(), optimizer_idx=1,
+                                                global_step=self.global_step, last_layer=None, split='train')
+            self.manual_backward(disc_loss)
+            opt_disc.step()
+            if sch_disc:
+                sch_disc.step()
+            logs.update(disc_logs)
         logs['train/lr'] = opt_gen.param_groups[0]['lr']
         self.log_dict(logs, prog_bar=True, logger=True, on_step=True, on_epoch=False)
         return gen_loss

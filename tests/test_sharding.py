@@ -71,14 +71,22 @@ def _ddp_worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(100 + rank)                      # replicas start DIFFERENT; the constructor broadcast fixes that
     net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4))
-    unused = torch.nn.Parameter(torch.ones(3))
-    sync = GradSync(list(net.parameters()) + [unused], bucket_bytes=256)   # several small buckets
+    unused = torch.nn.Parameter(torch.ones(3))         # no gradient on any rank
+    partial = torch.nn.Parameter(torch.ones(5))        # gradient on rank 1 only (a branch only that rank took)
+    sync = GradSync(list(net.parameters()) + [unused, partial], bucket_bytes=256, tail_bytes=300)   # several small buckets
+    assert len(sync.buckets) >= 3
     x = torch.randn(5, 8, generator=torch.Generator().manual_seed(rank))
     for _ in range(2):                                 # two steps: the bucket bookkeeping resets in finish()
-        for p in net.parameters():
+        for p in list(net.parameters()) + [unused, partial]:
             p.grad = None
-        net(x).pow(2).sum().backward()
+        loss = net(x).pow(2).sum()
+        if rank == 1:
+            loss = loss + (partial * 2.0).sum()
+        loss.backward()
         sync.finish()
+    assert unused.grad is None                         # unused everywhere: stays None, like DDP
+    assert torch.allclose(partial.grad, torch.full((5,), 1.0))   # (0 + 2) / 2 on BOTH ranks: replicas step identically
+    assert sync.launches == 2 * len(sync.buckets)
     torch.save({"grads": [p.grad.clone() for p in net.parameters()], "params": [p.detach().clone() for p in net.parameters()],
                 "x": x}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()

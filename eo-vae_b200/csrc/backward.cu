@@ -28,8 +28,9 @@ __device__ __forceinline__ float silu_grad2(float z, float neg_z_log2e) {
 
 // Pass 1: per (image, channel) sums  A = sum dz,  B = sum dz * xhat   with dz = g * silu'(z) (or g when !SILU),
 // z = xhat * gamma + beta, xhat = (x - mean) * rstd.  grid (blocks_per_image, n); fixed-slot partials (deterministic).
-template <typename T, bool SILU>
-__global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ g,
+// T = storage type of the forward activation x, TG = storage type of the gradients (g in, dx out, optional add)
+template <typename T, typename TG, bool SILU>
+__global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __restrict__ x, const TG* __restrict__ g,
                                                                   const float* __restrict__ stats,
                                                                   const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, long long hw, int c,
@@ -62,12 +63,12 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __rest
     long long p1 = p0 + pix_per_block;
     if (p1 > hw) p1 = hw;
     const T* xb = x + (static_cast<long long>(n) * hw) * c + v * 8;
-    const T* gb = g + (static_cast<long long>(n) * hw) * c + v * 8;
+    const TG* gb = g + (static_cast<long long>(n) * hw) * c + v * 8;
     auto accum = [&](const uint4& ux, const uint4& ug) {
       const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 fx = T16<T>::to_f2(wx[j]), fg = T16<T>::to_f2(wg[j]);
+        const float2 fx = T16<T>::to_f2(wx[j]), fg = T16<TG>::to_f2(wg[j]);
         const float xh0 = fmaf(fx.x, rs[2 * j], nm[2 * j]), xh1 = fmaf(fx.y, rs[2 * j + 1], nm[2 * j + 1]);
         float d0 = fg.x, d1 = fg.y;
         if (SILU) {
@@ -183,13 +184,13 @@ __global__ void gn_bwd_param_kernel(const float* __restrict__ chsum, int n_img, 
 }
 
 // Pass 3: dx = rstd * (dz*gamma - (s1 + xhat*s2) / M) (+ optional accumulation into an existing gradient)
-template <typename T, bool SILU>
-__global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ g,
+template <typename T, typename TG, bool SILU>
+__global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restrict__ x, const TG* __restrict__ g,
                                                                  const float* __restrict__ stats,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta,
-                                                                 const float* __restrict__ gsum, const T* __restrict__ add,
-                                                                 T* __restrict__ dx, long long hw, int c, int groups,
+                                                                 const float* __restrict__ gsum, const TG* __restrict__ add,
+                                                                 TG* __restrict__ dx, long long hw, int c, int groups,
                                                                  int pix_per_block, float* __restrict__ colpart) {
   // colpart != NULL: also emit this block's per-channel sums of dx (fixed slot [n][block][c]) - the bias gradient of the
   // convolution that produced x's forward input, for free (no extra pass over dx)
@@ -229,9 +230,9 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 fx = T16<T>::to_f2(wx[j]), fg = T16<T>::to_f2(wg[j]);
+      const float2 fx = T16<T>::to_f2(wx[j]), fg = T16<TG>::to_f2(wg[j]);
       float2 fa = make_float2(0.f, 0.f);
-      if (add != nullptr) fa = T16<T>::to_f2(wa[j]);
+      if (add != nullptr) fa = T16<TG>::to_f2(wa[j]);
       const float xh0 = fmaf(fx.x, rs[2 * j], nm[2 * j]), xh1 = fmaf(fx.y, rs[2 * j + 1], nm[2 * j + 1]);
       float d0 = fg.x, d1 = fg.y;
       if (SILU) {
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
       const float r1 = fmaf(-xh1, c2[2 * j + 1], fmaf(d1, za[2 * j + 1], fa.y - c1[2 * j + 1]));
       cs[2 * j] += r0;
       cs[2 * j + 1] += r1;
-      o[j] = T16<T>::from_f2(r0, r1);
+      o[j] = T16<TG>::from_f2(r0, r1);
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
   };
@@ -408,9 +409,9 @@ struct Strides4 { long long n, c, y, x; };
 
 // ------------------------------------------------------------------------------------------------- attention / latent / loss
 // dS = scale * P o (dP - rowsum(dP o P)): one warp per row; P 16-bit, dP fp32, dS 16-bit with columns >= cols zeroed.
-template <typename T>
+template <typename T, typename TG>
 __global__ void softmax_bwd_kernel(const T* __restrict__ p, long long p_ld, const float* __restrict__ dp, long long dp_ld,
-                                   T* __restrict__ ds, long long ds_ld, long long rows, int cols, int out_cols, float scale) {
+                                   TG* __restrict__ ds, long long ds_ld, long long rows, int cols, int out_cols, float scale) {
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -419,9 +420,9 @@ __global__ void softmax_bwd_kernel(const T* __restrict__ p, long long p_ld, cons
   float dot = 0.f;
   for (int j = lane; j < cols; j += 32) dot += T16<T>::to_f(pr[j]) * dr[j];
   dot = warp_sum(dot);
-  T* o = ds + row * ds_ld;
+  TG* o = ds + row * ds_ld;
   for (int j = lane; j < out_cols; j += 32)
-    o[j] = j < cols ? T16<T>::from_f(scale * T16<T>::to_f(pr[j]) * (dr[j] - dot)) : T16<T>::from_f(0.f);
+    o[j] = j < cols ? T16<TG>::from_f(scale * T16<T>::to_f(pr[j]) * (dr[j] - dot)) : T16<TG>::from_f(0.f);
 }
 
 // z = mean + exp(0.5 * clamp(logvar)) * eps  ->  dmean = dz, dlogvar = dz * eps * 0.5 * std inside the clamp, else 0.
@@ -573,13 +574,14 @@ size_t eovae_gn_backward_workspace_bytes(int n, long long hw, int c, int groups)
                           2 * static_cast<size_t>(n) * c + 64);
 }
 
-int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const float* stats, const float* gamma,
+int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_dtype, const float* stats, const float* gamma,
                       const float* beta, int n, long long hw, int c, int groups, int with_silu, const void* grad_add,
                       void* grad_x, float* dgamma, float* dbeta, int accumulate_params, float* grad_x_colsum,
                       void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   EOVAE_CHECK(c % 8 == 0 && c % groups == 0, "gn_backward: C (%d) must be a multiple of 8 and of groups (%d)", c, groups);
-  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "gn_backward: 16-bit tensors only");
+  EOVAE_CHECK((dtype == EOVAE_BF16 || dtype == EOVAE_F16) && (grad_dtype == EOVAE_BF16 || grad_dtype == EOVAE_F16),
+              "gn_backward: 16-bit tensors only");
   const int threads = block_threads(c);
   EOVAE_CHECK(threads > 0, "gn_backward: C too large (%d)", c);
   EOVAE_CHECK(workspace_bytes >= eovae_gn_backward_workspace_bytes(n, hw, c, groups), "gn_backward: workspace too small");
@@ -591,15 +593,27 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const floa
   float* chsum = gsum + 2 * static_cast<size_t>(n) * groups;
   dim3 grid(bpi, n);
   const size_t smem = sizeof(float) * 2 * c * rows;
-#define EOVAE_GNB_R(T, S)                                                                                             \
-  gn_bwd_reduce_kernel<T, S><<<grid, threads, smem, stream>>>(static_cast<const T*>(x), static_cast<const T*>(grad_out), \
-                                                             stats, gamma, beta, hw, c, groups, partial, ppb)
-#define EOVAE_GNB_A(T, S)                                                                                            \
-  gn_bwd_apply_kernel<T, S><<<grid, threads, grad_x_colsum ? sizeof(float) * c * rows : 0, stream>>>(                \
-      static_cast<const T*>(x), static_cast<const T*>(grad_out), stats, gamma, beta, gsum, static_cast<const T*>(grad_add), \
-      static_cast<T*>(grad_x), hw, c, groups, ppb, grad_x_colsum ? partial : nullptr)
-  if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_R(__nv_bfloat16, true); else EOVAE_GNB_R(__nv_bfloat16, false); }
-  else { if (with_silu) EOVAE_GNB_R(__half, true); else EOVAE_GNB_R(__half, false); }
+#define EOVAE_GNB_R(T, TG, S)                                                                                             \
+  gn_bwd_reduce_kernel<T, TG, S><<<grid, threads, smem, stream>>>(static_cast<const T*>(x), static_cast<const TG*>(grad_out), \
+                                                                 stats, gamma, beta, hw, c, groups, partial, ppb)
+#define EOVAE_GNB_A(T, TG, S)                                                                                            \
+  gn_bwd_apply_kernel<T, TG, S><<<grid, threads, grad_x_colsum ? sizeof(float) * c * rows : 0, stream>>>(                \
+      static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, gsum, static_cast<const TG*>(grad_add), \
+      static_cast<TG*>(grad_x), hw, c, groups, ppb, grad_x_colsum ? partial : nullptr)
+  // (activation type, gradient type): bf16/bf16, f16/f16 and the default training mix f16 activations / bf16 gradients
+#define EOVAE_GNB_DISPATCH(M)                                                                                  \
+  do {                                                                                                         \
+    if (dtype == EOVAE_BF16 && grad_dtype == EOVAE_BF16) {                                                     \
+      if (with_silu) M(__nv_bfloat16, __nv_bfloat16, true); else M(__nv_bfloat16, __nv_bfloat16, false);       \
+    } else if (dtype == EOVAE_F16 && grad_dtype == EOVAE_F16) {                                                \
+      if (with_silu) M(__half, __half, true); else M(__half, __half, false);                                   \
+    } else if (dtype == EOVAE_F16 && grad_dtype == EOVAE_BF16) {                                               \
+      if (with_silu) M(__half, __nv_bfloat16, true); else M(__half, __nv_bfloat16, false);                     \
+    } else {                                                                                                   \
+      EOVAE_CHECK(false, "gn_backward: unsupported (activation, gradient) dtype pair (%d, %d)", dtype, grad_dtype); \
+    }                                                                                                          \
+  } while (0)
+  EOVAE_GNB_DISPATCH(EOVAE_GNB_R);
   EOVAE_LAUNCH_CHECK();
   {
     const int fthreads = 1024;
@@ -612,8 +626,7 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const floa
     EOVAE_LAUNCH_CHECK();
   }
   if (grad_x != nullptr) {
-    if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_A(__nv_bfloat16, true); else EOVAE_GNB_A(__nv_bfloat16, false); }
-    else { if (with_silu) EOVAE_GNB_A(__half, true); else EOVAE_GNB_A(__half, false); }
+    EOVAE_GNB_DISPATCH(EOVAE_GNB_A);
     EOVAE_LAUNCH_CHECK();
     if (grad_x_colsum != nullptr) {  // the reduce partials are dead by now: their buffer carried the column-sum slots
       colsum_finalize_kernel<<<ceil_div(c, 32), dim3(32, 32), 0, stream>>>(partial, n * bpi, c, grad_x_colsum, 0);
@@ -622,6 +635,7 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const floa
   }
 #undef EOVAE_GNB_R
 #undef EOVAE_GNB_A
+#undef EOVAE_GNB_DISPATCH
   return 0;
 }
 
@@ -675,18 +689,18 @@ int eovae_bias_grad(const void* grad_out, int dtype, long long pixels, int c, fl
 }
 
 int eovae_softmax_backward(const void* p, long long p_ld, const float* dp, long long dp_ld, void* ds, long long ds_ld,
-                           int dtype, long long rows, int cols, int out_cols, float scale, void* stream_) {
+                           int dtype, int ds_dtype, long long rows, int cols, int out_cols, float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   EOVAE_CHECK(p_ld >= cols && dp_ld >= cols && ds_ld >= out_cols && out_cols >= cols, "softmax_backward: bad pitches");
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  if (dtype == EOVAE_BF16)
-    softmax_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(p), p_ld, dp, dp_ld,
-                                                                static_cast<__nv_bfloat16*>(ds), ds_ld, rows, cols, out_cols, scale);
-  else if (dtype == EOVAE_F16)
-    softmax_bwd_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(p), p_ld, dp, dp_ld, static_cast<__half*>(ds),
-                                                         ds_ld, rows, cols, out_cols, scale);
-  else
-    EOVAE_CHECK(false, "softmax_backward: 16-bit probabilities only");
+#define EOVAE_SMB(T, TG)                                                                                             \
+  softmax_bwd_kernel<T, TG><<<grid, 256, 0, stream>>>(static_cast<const T*>(p), p_ld, dp, dp_ld, static_cast<TG*>(ds), ds_ld, \
+                                                      rows, cols, out_cols, scale)
+  if (dtype == EOVAE_BF16 && ds_dtype == EOVAE_BF16) EOVAE_SMB(__nv_bfloat16, __nv_bfloat16);
+  else if (dtype == EOVAE_F16 && ds_dtype == EOVAE_F16) EOVAE_SMB(__half, __half);
+  else if (dtype == EOVAE_F16 && ds_dtype == EOVAE_BF16) EOVAE_SMB(__half, __nv_bfloat16);
+  else EOVAE_CHECK(false, "softmax_backward: unsupported (probability, gradient) dtype pair (%d, %d)", dtype, ds_dtype);
+#undef EOVAE_SMB
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

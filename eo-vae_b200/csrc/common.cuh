@@ -73,6 +73,12 @@ struct T16<__half> {
   static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
 };
 
+template <>
+struct T16<float> {  // scalar identity: lets the element-wise templates serve the fp32 validation path
+  static __device__ __forceinline__ float to_f(float v) { return v; }
+  static __device__ __forceinline__ float from_f(float v) { return v; }
+};
+
 __device__ __forceinline__ float2 unpack16(uint32_t u, int dtype) {
   return dtype == EOVAE_BF16 ? T16<__nv_bfloat16>::to_f2(u) : T16<__half>::to_f2(u);
 }

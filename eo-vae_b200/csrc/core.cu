@@ -169,6 +169,8 @@ int eovae_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, in
     pack_conv_weight_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, taps, kpt, total);
   else if (dtype == EOVAE_F16)
     pack_conv_weight_kernel<__half><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, taps, kpt, total);
+  else if (dtype == EOVAE_F32)  // fp32 validation path: same [cout][tap][k_per_tap] layout, unrounded
+    pack_conv_weight_kernel<float><<<grid, 256, 0, stream>>>(w_oihw, static_cast<float*>(out), cout, cin, taps, kpt, total);
   else
     EOVAE_CHECK(false, "pack_conv_weight: bad dtype %d", dtype);
   EOVAE_LAUNCH_CHECK();
@@ -217,6 +219,8 @@ int eovae_pack_dyn_weight(const float* wk, int c, int embed, int decoder, float 
     pack_dyn_weight_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(wk, c, embed, decoder, scale, static_cast<__nv_bfloat16*>(packed), k_per_tap, rows_pad, oihw_out, bias_raw, bias_scale, bias_out, nbias);
   else if (dtype == EOVAE_F16)
     pack_dyn_weight_kernel<__half><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(wk, c, embed, decoder, scale, static_cast<__half*>(packed), k_per_tap, rows_pad, oihw_out, bias_raw, bias_scale, bias_out, nbias);
+  else if (dtype == EOVAE_F32)
+    pack_dyn_weight_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(wk, c, embed, decoder, scale, static_cast<float*>(packed), k_per_tap, rows_pad, oihw_out, bias_raw, bias_scale, bias_out, nbias);
   else
     EOVAE_CHECK(false, "pack_dyn_weight: bad dtype %d", dtype);
   EOVAE_LAUNCH_CHECK();

@@ -3,6 +3,9 @@
 // NHWC channel axis; reductions use warp shuffles + a few fp64 atomics per block.
 #include "../../include/eovae.h"
 #include "common.cuh"
+#include "fp32_path.cuh"
+
+#include <type_traits>
 
 namespace {
 
@@ -226,6 +229,8 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(128) softmax_rows_kernel(const TI* __restrict__ s, TO* __restrict__ p, int cols,
                                                            long long s_ld, long long p_ld) {
   constexpr int MAXV = 32;  // cached values per thread (cols <= 4096)
+  // fp32 probabilities = the fp32 validation path: exact expf there, the fast ex2-based __expf for 16-bit outputs
+  auto ex = [](float v) { return std::is_same<TO, float>::value ? expf(v) : __expf(v); };
   const long long row = blockIdx.x;
   const TI* sr = s + row * s_ld;
   TO* pr = p + row * p_ld;
@@ -253,11 +258,11 @@ __global__ void __launch_bounds__(128) softmax_rows_kernel(const TI* __restrict_
   if (cached) {
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
-      v[j] = __expf(v[j] - m);  // exp(-inf) = 0 for the padding lanes
+      v[j] = ex(v[j] - m);  // exp(-inf) = 0 for the padding lanes
       sum += v[j];
     }
   } else {
-    for (int cidx = threadIdx.x; cidx < cols; cidx += 128) sum += __expf(load_as_float<TI>(sr + cidx) - m);
+    for (int cidx = threadIdx.x; cidx < cols; cidx += 128) sum += ex(load_as_float<TI>(sr + cidx) - m);
   }
   sum = warp_sum(sum);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(128) softmax_rows_kernel(const TI* __restrict_
     }
   } else {
     for (int cidx = threadIdx.x; cidx < cols; cidx += 128)
-      pr[cidx] = T16<TO>::from_f(__expf(load_as_float<TI>(sr + cidx) - m) * inv);
+      pr[cidx] = T16<TO>::from_f(ex(load_as_float<TI>(sr + cidx) - m) * inv);
   }
 }
 
@@ -565,6 +570,10 @@ size_t eovae_gn_stats_workspace_bytes(int n, long long hw, int c, int groups) {
 int eovae_gn_stats(const void* x, int x_dtype, int n, long long hw, int c, long long pix_stride, int groups, float eps,
                    float* stats, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (x_dtype == EOVAE_F32) {  // fp32 validation path (fp32_path.cu); needs no workspace
+    EOVAE_CHECK(groups > 0 && c % groups == 0, "gn_stats: C (%d) must be a multiple of groups (%d)", c, groups);
+    return eovae::f32::gn_stats(static_cast<const float*>(x), n, hw, c, pix_stride, groups, eps, stats, stream);
+  }
   EOVAE_CHECK(c % 8 == 0 && c % groups == 0, "gn_stats: C (%d) must be a multiple of 8 and of groups (%d)", c, groups);
   EOVAE_CHECK(pix_stride % 8 == 0, "gn_stats: pixel stride must be a multiple of 8");
   EOVAE_CHECK(x_dtype == EOVAE_BF16 || x_dtype == EOVAE_F16, "gn_stats: x must be 16-bit");
@@ -592,6 +601,12 @@ int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const flo
                    const float* beta, void* y, int y_dtype, long long y_pix_stride, int n, long long hw, int c, int groups,
                    int apply_silu, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (x_dtype == EOVAE_F32 || y_dtype == EOVAE_F32) {  // fp32 validation path
+    EOVAE_CHECK(x_dtype == EOVAE_F32 && y_dtype == EOVAE_F32 && groups > 0 && c % groups == 0,
+                "gn_apply: the fp32 path needs fp32 input and output and C a multiple of groups");
+    return eovae::f32::gn_apply(static_cast<const float*>(x), x_pix_stride, stats, gamma, beta, static_cast<float*>(y),
+                                y_pix_stride, n, hw, c, groups, apply_silu, stream);
+  }
   EOVAE_CHECK(c % 8 == 0 && c % groups == 0, "gn_apply: C (%d) must be a multiple of 8 and of groups (%d)", c, groups);
   EOVAE_CHECK(x_pix_stride % 8 == 0 && y_pix_stride % 8 == 0, "gn_apply: pixel strides must be multiples of 8");
   EOVAE_CHECK((x_dtype == EOVAE_BF16 || x_dtype == EOVAE_F16) && (y_dtype == EOVAE_BF16 || y_dtype == EOVAE_F16),
@@ -622,6 +637,10 @@ int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const flo
 
 int eovae_nchw_to_nhwc16(const float* x, void* out, int n, int c, int h, int w, int c_pad, int out_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (out_dtype == EOVAE_F32) {  // fp32 validation path
+    EOVAE_CHECK(c_pad % 4 == 0 && c_pad >= c, "nchw_to_nhwc16: c_pad (%d) must be a multiple of 4 and >= C (%d)", c_pad, c);
+    return eovae::f32::nchw_to_nhwc(x, static_cast<float*>(out), n, c, h, w, c_pad, stream);
+  }
   EOVAE_CHECK(c_pad % 8 == 0 && c_pad >= c, "nchw_to_nhwc16: c_pad (%d) must be a multiple of 8 and >= C (%d)", c_pad, c);
   const long long hw = static_cast<long long>(h) * w;
   dim3 grid(static_cast<unsigned>((hw + 255) / 256), n);
@@ -670,6 +689,7 @@ int eovae_softmax_rows(const void* s, int s_dtype, long long s_ld, void* p, int 
   else if (s_dtype == EOVAE_F32 && p_dtype == EOVAE_F16) EOVAE_SM(float, __half);
   else if (s_dtype == EOVAE_BF16 && p_dtype == EOVAE_BF16) EOVAE_SM(__nv_bfloat16, __nv_bfloat16);
   else if (s_dtype == EOVAE_F16 && p_dtype == EOVAE_F16) EOVAE_SM(__half, __half);
+  else if (s_dtype == EOVAE_F32 && p_dtype == EOVAE_F32) EOVAE_SM(float, float);  // fp32 validation path
   else EOVAE_CHECK(false, "softmax_rows: unsupported dtype pair %d -> %d", s_dtype, p_dtype);
 #undef EOVAE_SM
   EOVAE_LAUNCH_CHECK();
@@ -723,6 +743,8 @@ int eovae_latent_denorm(const float* z, const float* running_mean, const float* 
     latent_denorm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(z, running_mean, running_var, eps, static_cast<__nv_bfloat16*>(out), h, w, zc, total);
   else if (out_dtype == EOVAE_F16)
     latent_denorm_kernel<__half><<<grid, 256, 0, stream>>>(z, running_mean, running_var, eps, static_cast<__half*>(out), h, w, zc, total);
+  else if (out_dtype == EOVAE_F32)  // fp32 validation path
+    latent_denorm_kernel<float><<<grid, 256, 0, stream>>>(z, running_mean, running_var, eps, static_cast<float*>(out), h, w, zc, total);
   else
     EOVAE_CHECK(false, "latent_denorm: bad dtype");
   EOVAE_LAUNCH_CHECK();

@@ -4,6 +4,7 @@
 #include <unordered_map>
 
 #include "../../include/eovae.h"
+#include "fp32_path.cuh"
 #include "igemm_sm100.cuh"
 
 namespace {
@@ -179,8 +180,10 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
                  long long res_pix_stride, void* out, int out_dtype, long long out_pix_stride, int act_dtype,
                  float scale, cudaStream_t stream, float* gn_stats = nullptr, int gn_groups = 0, float gn_eps = 0.f,
                  void* gn_ws = nullptr, size_t gn_ws_bytes = 0, const ASpec* extra = nullptr,
-                 const GnPrologue* gnp = nullptr) {
-  EOVAE_CHECK(act_dtype == EOVAE_BF16 || act_dtype == EOVAE_F16, "igemm: operand dtype must be bf16/f16");
+                 const GnPrologue* gnp = nullptr, int w_dtype = -1) {
+  if (w_dtype < 0) w_dtype = act_dtype;  // B operand format; kind::f16 takes the A / B formats independently
+  EOVAE_CHECK((act_dtype == EOVAE_BF16 || act_dtype == EOVAE_F16) && (w_dtype == EOVAE_BF16 || w_dtype == EOVAE_F16),
+              "igemm: operand dtypes must be bf16/f16");
   EOVAE_CHECK(chunk_bytes == 32 || chunk_bytes == 64 || chunk_bytes == 128, "igemm: bad chunk bytes %d", chunk_bytes);
   EOVAE_CHECK(a.pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ptr) % 16) == 0,
               "igemm: activation pixel stride (%lld) must be a multiple of 8 elements and base 16B aligned", a.pix_stride);
@@ -240,8 +243,8 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   if (g_force_ctas == 1) ctas = 1;
   if (g_force_ctas == 2 && !(w_batches > 1 && (p.tiles_w * p.tiles_h) % 2 != 0)) ctas = 2;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B = bf16|f16, K-major both, N>>3, M>>4
-  const uint32_t fmt = act_dtype == EOVAE_BF16 ? 1u : 0u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) |
+  const uint32_t fmt = act_dtype == EOVAE_BF16 ? 1u : 0u, fmt_b = w_dtype == EOVAE_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt_b << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) |
             (static_cast<uint32_t>((igemm::BLOCK_M * ctas) >> 4) << 24);
 
   // --- A maps
@@ -297,7 +300,7 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     uint64_t strides[2] = {static_cast<uint64_t>(w_row_stride) * es, static_cast<uint64_t>(w_batch_stride) * es};
     if (w_batches <= 1) strides[1] = static_cast<uint64_t>(w_row_stride) * static_cast<uint64_t>(w_rows) * es;
     const uint32_t bbox[3] = {static_cast<uint32_t>(ch), static_cast<uint32_t>(block_n / ctas), 1};
-    int rc = encode_map(&p.b_map, act_dtype, 3, w, dims, strides, bbox, chunk_bytes);
+    int rc = encode_map(&p.b_map, w_dtype, 3, w, dims, strides, bbox, chunk_bytes);
     if (rc) return rc;
   }
   // --- output map for the TMA-store epilogue: each epilogue warp owns 32 consecutive tile rows; they must form a
@@ -466,6 +469,19 @@ int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_st
                  int in_gn_groups, void* in_gn_workspace, size_t in_gn_workspace_bytes, void* stream) {
   EOVAE_CHECK(mode == EOVAE_CONV_3X3 || mode == EOVAE_CONV_1X1 || mode == EOVAE_CONV_3X3_S2, "conv2d: bad mode %d", mode);
   EOVAE_CHECK(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "conv2d: empty shape");
+  if (act_dtype == EOVAE_F32) {
+    // fp32 validation path (fp32_path.cu): fp32 NHWC activations, fp32 [cout][tap][k_per_tap] weights, SIMT FMAs
+    EOVAE_CHECK(out_dtype == EOVAE_F32 && (residual == nullptr || res_dtype == EOVAE_F32),
+                "conv2d: the fp32 path needs fp32 output and residual");
+    EOVAE_CHECK(x2 == nullptr && in_gn_stats == nullptr && gn_stats == nullptr,
+                "conv2d: fused shortcut / GroupNorm prologue / statistics epilogue are tensor-core-path features");
+    EOVAE_CHECK(cin % 4 == 0, "conv2d: Cin (%d) must be a multiple of 4 on the fp32 path", cin);
+    const int kpt32 = eovae_conv_k_per_tap(cin);
+    const int taps32 = mode == EOVAE_CONV_1X1 ? 1 : 9;
+    return eovae::f32::conv2d(static_cast<const float*>(x), n, h, w, cin, x_pix_stride, mode, static_cast<const float*>(w_packed),
+                              static_cast<long long>(taps32) * kpt32, 1, 0, kpt32, cout, bias, static_cast<const float*>(residual),
+                              res_pix_stride, static_cast<float*>(out), out_pix_stride, scale, static_cast<cudaStream_t>(stream));
+  }
   EOVAE_CHECK(cin % 8 == 0, "conv2d: Cin (%d) must be a multiple of 8", cin);
   ASpec a{x, n, h, w, cin, x_pix_stride};
   ASpec e{x2, n, h, w, cin2, x2_pix_stride};
@@ -492,8 +508,16 @@ int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_st
 
 int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride, const void* b, long long ldb,
                           long long b_batch_stride, void* c, int c_dtype, long long ldc, int batch, int m, int n, int k,
-                          int ab_dtype, float scale, void* stream) {
+                          int a_dtype, int b_dtype, float scale, void* stream) {
   EOVAE_CHECK(batch > 0 && m > 0 && n > 0 && k > 0, "gemm_tn_batched: empty shape");
+  if (a_dtype == EOVAE_F32) {  // fp32 validation path: a 1x1 "conv" over [batch][1][m] pixels with a per-batch B operand
+    EOVAE_CHECK(b_dtype == EOVAE_F32 && c_dtype == EOVAE_F32 && k % 16 == 0 && lda % 4 == 0,
+                "gemm_tn_batched: the fp32 path needs fp32 A, B, C, K a multiple of 16 and lda a multiple of 4");
+    EOVAE_CHECK(a_batch_stride == static_cast<long long>(m) * lda, "gemm_tn_batched: A batches must be contiguous");
+    return eovae::f32::conv2d(static_cast<const float*>(a), batch, 1, m, k, lda, EOVAE_CONV_1X1, static_cast<const float*>(b), ldb, 1,
+                              batch == 1 ? 0 : b_batch_stride, k, n, nullptr, nullptr, 0, static_cast<float*>(c), ldc, scale,
+                              static_cast<cudaStream_t>(stream));
+  }
   EOVAE_CHECK(k % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm_tn_batched: K, lda, ldb must be multiples of 8");
   EOVAE_CHECK(a_batch_stride == static_cast<long long>(m) * lda, "gemm_tn_batched: A batches must be contiguous");
   EOVAE_CHECK(ldb >= k, "gemm_tn_batched: ldb < K");
@@ -502,7 +526,19 @@ int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride
   const int kpt = eovae_conv_k_per_tap(k);
   EOVAE_CHECK(kpt == k, "gemm_tn_batched: K (%d) must be a multiple of 16", k);
   return launch_igemm(as, EOVAE_CONV_1X1, b, kpt, cb, n, n, ldb, b_batch_stride, batch == 1 ? 1 : batch, nullptr, nullptr, 0, 0, c,
-                      c_dtype, ldc, ab_dtype, scale, static_cast<cudaStream_t>(stream));
+                      c_dtype, ldc, a_dtype, scale, static_cast<cudaStream_t>(stream), nullptr, 0, 0.f, nullptr, 0, nullptr, nullptr,
+                      b_dtype);
+}
+
+int eovae_gemm_strided_f32(const float* a, long long lda, long long a_batch_stride, const float* b, long long b_n_stride,
+                           long long b_k_stride, long long b_batch_stride, float* c, long long ldc, int batch, int m, int n, int k,
+                           float scale, void* stream) {
+  // fp32 validation path: c[i][r][j] = scale * sum_k a[i][r][k] * B_i(j, k), B_i(j, k) = b[i * b_batch_stride + j * b_n_stride +
+  // k * b_k_stride] (any operand orientation: P V of the attention reads V in place, keys along b_k_stride)
+  EOVAE_CHECK(batch > 0 && m > 0 && n > 0 && k > 0 && k % 16 == 0 && lda % 4 == 0, "gemm_strided_f32: bad shape (K %% 16, lda %% 4)");
+  EOVAE_CHECK(a_batch_stride == static_cast<long long>(m) * lda, "gemm_strided_f32: A batches must be contiguous");
+  return eovae::f32::conv2d(a, batch, 1, m, k, lda, EOVAE_CONV_1X1, b, b_n_stride, b_k_stride, batch == 1 ? 0 : b_batch_stride, k, n,
+                            nullptr, nullptr, 0, c, ldc, scale, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

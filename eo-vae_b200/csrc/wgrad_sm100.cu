@@ -599,12 +599,13 @@ size_t eovae_conv2d_wgrad_nhwc_workspace_bytes(int n, int h, int w, int cin, int
   return sizeof(float) * static_cast<size_t>(ks) * ksize * ksize * cout * cin;
 }
 
-int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int h,
+int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int dy_dtype, int n, int h,
                             int w, int cin, int cout, int ksize, float* dw_oihw, int accumulate, void* workspace,
                             size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad_nhwc: kernel size must be 3 or 1");
-  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "conv2d_wgrad_nhwc: 16-bit operands only");
+  EOVAE_CHECK((dtype == EOVAE_BF16 || dtype == EOVAE_F16) && (dy_dtype == EOVAE_BF16 || dy_dtype == EOVAE_F16),
+              "conv2d_wgrad_nhwc: 16-bit operands only");
   EOVAE_CHECK(eovae_conv2d_wgrad_nhwc_ok(h, w), "conv2d_wgrad_nhwc: %dx%d images do not tile into 64-pixel boxes", h, w);
   EOVAE_CHECK(cin % 4 == 0 && x_pix_stride % 8 == 0 && dy_pix_stride % 8 == 0 && x_pix_stride >= cin && dy_pix_stride >= cout,
               "conv2d_wgrad_nhwc: Cin %% 4 and 16-byte pixel pitches required (Cin %d, pitches %lld / %lld)", cin, x_pix_stride,
@@ -624,7 +625,8 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
   p.bw = w >= 64 ? 64 : w;
   p.bh = 64 / p.bw;
   p.partial = static_cast<float*>(workspace);
-  const uint32_t fmt = dtype == EOVAE_BF16 ? 1u : 0u;
+  const uint32_t fmt_a = dy_dtype == EOVAE_BF16 ? 1u : 0u;  // A operand = dY, B operand = X: kind::f16 takes the two
+  const uint32_t fmt_b = dtype == EOVAE_BF16 ? 1u : 0u;     // operand formats independently (f16 x bf16 allowed)
   if (cout % 256 == 0 && cin % 256 == 0 && !g_no_pair) {
     // CTA-pair kernel: co_tiles counts 256-row tiles; same split-K plan (the partial layout does not depend on the tiling)
     p.co_tiles = cout / 256;
@@ -634,9 +636,9 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
     p.chunks_per_split = ceil_div(p.chunks_total, ks);
     p.ksplit = ceil_div(p.chunks_total, p.chunks_per_split);
     EOVAE_CHECK(workspace_bytes >= sizeof(float) * static_cast<size_t>(p.ksplit) * p.taps * cout * cin, "conv2d_wgrad_nhwc: workspace too small");
-    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(256 >> 3) << 17) |
+    p.idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(256 >> 3) << 17) |
               (static_cast<uint32_t>(256 >> 4) << 24);
-    if (make_map_nhwc(&p.a_map, dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+    if (make_map_nhwc(&p.a_map, dy_dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh)) return -3;
     if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh)) return -3;
     constexpr int SMEM2 = WG2_STAGES * WG2_KC * (2 * 128 * 128) + 1024 + 256;
     static bool set2 = false;
@@ -666,9 +668,9 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
     return 0;
   }
   const int tpi = pick_tpi(bn, p.taps);
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>((bn * tpi) >> 3) << 17) |
+  p.idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>((bn * tpi) >> 3) << 17) |
             (static_cast<uint32_t>(128 >> 4) << 24);  // bits 15 / 16: A and B are MN-major
-  if (make_map_nhwc(&p.a_map, dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+  if (make_map_nhwc(&p.a_map, dy_dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh)) return -3;
   if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh)) return -3;
   const int items = ceil_div(p.taps, tpi) * p.co_tiles * p.ci_tiles * p.ksplit;
   int rc;
@@ -693,11 +695,12 @@ size_t eovae_conv2d_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout
   return sizeof(float) * static_cast<size_t>(ks) * ksize * ksize * cout * cin;
 }
 
-int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int n, int h, int w, int cin, int cout, int ksize,
+int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int dy_dtype, int n, int h, int w, int cin, int cout, int ksize,
                        float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad: kernel size must be 3 or 1");
-  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "conv2d_wgrad: 16-bit operands only");
+  EOVAE_CHECK((dtype == EOVAE_BF16 || dtype == EOVAE_F16) && (dy_dtype == EOVAE_BF16 || dy_dtype == EOVAE_F16),
+              "conv2d_wgrad: 16-bit operands only");
   EOVAE_CHECK(w % 8 == 0 && cin % 16 == 0, "conv2d_wgrad: (padded) W %% 8 and Cin %% 16 required (W %d, Cin %d)", w, cin);
   EOVAE_CHECK(workspace_bytes >= eovae_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, ksize), "conv2d_wgrad: workspace too small");
   WgradParams p;
@@ -706,9 +709,10 @@ int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int n, int 
   plan(n, h, w, cin, cout, ksize * ksize, &bn, &p.co_tiles, &p.ci_tiles, &p.ksplit, &p.chunks_per_split, &p.chunks_total);
   p.H = h; p.W = w; p.N = n; p.chunks_img = ceil_div(h * w, 64); p.taps = ksize * ksize; p.cout = cout; p.cin = cin;
   p.partial = static_cast<float*>(workspace);
-  const uint32_t fmt = dtype == EOVAE_BF16 ? 1u : 0u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-  if (make_map(&p.a_map, dtype, dy_t, static_cast<long long>(h) * w, cout, n, 128)) return -3;
+  const uint32_t fmt_a = dy_dtype == EOVAE_BF16 ? 1u : 0u;  // A operand = dY, B operand = X: kind::f16 takes the two
+  const uint32_t fmt_b = dtype == EOVAE_BF16 ? 1u : 0u;     // operand formats independently (f16 x bf16 allowed)
+  p.idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  if (make_map(&p.a_map, dy_dtype, dy_t, static_cast<long long>(h) * w, cout, n, 128)) return -3;
   if (make_map(&p.b_map, dtype, x_t, static_cast<long long>(h) * w, cin, ksize == 3 ? 3 * n : n, bn)) return -3;
   const int items = p.taps * p.co_tiles * p.ci_tiles * p.ksplit;
   int rc;

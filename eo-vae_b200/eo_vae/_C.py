@@ -30,7 +30,8 @@ SIGNATURES = {
     "eovae_conv2d_gn_prologue_ok": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "eovae_conv2d": (_i, [_vp, _i, _i, _i, _i, _ll, _i, _vp, _i, _vp, _vp, _i, _ll, _vp, _i, _ll, _i, _f, _vp, _i, _f, _vp,
                           _sz, _vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
-    "eovae_gemm_tn_batched": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _i, _ll, _i, _i, _i, _i, _i, _f, _vp]),
+    "eovae_gemm_tn_batched": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _i, _ll, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "eovae_gemm_strided_f32": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "eovae_gn_stats_workspace_bytes": (_sz, [_i, _ll, _i, _i]),
     "eovae_gn_stats": (_i, [_vp, _i, _i, _ll, _i, _ll, _i, _f, _vp, _vp, _sz, _vp]),
     "eovae_gn_apply": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _vp, _i, _ll, _i, _ll, _i, _i, _i, _vp]),
@@ -67,14 +68,14 @@ SIGNATURES = {
     "eovae_msssim_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "eovae_conv2d_wgrad_nhwc_ok": (_i, [_i, _i]),
     "eovae_conv2d_wgrad_nhwc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "eovae_conv2d_wgrad_nhwc": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "eovae_conv2d_wgrad_nhwc": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "eovae_running_stats_update": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "eovae_latent_bn_train_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _f, _f, _vp, _i, _ll, _vp, _vp]),
     "eovae_latent_bn_train_backward": (_i, [_vp, _i, _ll, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eovae_preprocess": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _f, _f, _i, _i, _i, _vp, _vp]),
     "eovae_attention_fused_ok": (_i, [_i, _i]),
     "eovae_attention_fused": (_i, [_vp, _ll, _i, _i, _i, _vp, _ll, _i, _vp]),
-    "eovae_softmax_backward": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _ll, _i, _i, _f, _vp]),
+    "eovae_softmax_backward": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _ll, _i, _i, _f, _vp]),
     "eovae_reparam_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "eovae_pixel_loss_backward": (_i, [_vp, _vp, _ll, _f, _i, _vp, _vp, _vp]),
     "eovae_transpose16_xshift": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -87,11 +88,11 @@ SIGNATURES = {
     "eovae_l1_charbonnier": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _sz, _vp]),
     "eovae_pack_conv_weight_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "eovae_gn_backward_workspace_bytes": (_sz, [_i, _ll, _i, _i]),
-    "eovae_gn_backward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "eovae_gn_backward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "eovae_scatter_stride2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "eovae_pool2x2_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "eovae_conv2d_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "eovae_conv2d_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "eovae_conv2d_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "eovae_bias_grad_workspace_bytes": (_sz, [_ll, _i]),
     "eovae_bias_grad": (_i, [_vp, _i, _ll, _i, _vp, _i, _vp, _sz, _vp]),
     "eovae_msssim_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -114,7 +115,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError => ABI mismatch, fail loudly
             fn.restype = res
             fn.argtypes = args
-        if handle.eovae_version() != 1:
+        if handle.eovae_version() != 2:
             raise RuntimeError("eo_vae: libeovae_sm100.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -22,11 +22,21 @@ import torch
 from torch.autograd import Function
 
 from . import ops
+from .settings import compute_dtype, grad_dtype
+
+
+def _gd(x: torch.Tensor):
+    """Storage type of the gradients between layers: bf16 beside 16-bit activations (settings.grad_dtype)."""
+    if x.dtype == torch.float32:
+        raise RuntimeError("eo_vae: the fp32 validation path is forward-only (set_compute_dtype(torch.float16 | torch.bfloat16) "
+                           "for training)")
+    return grad_dtype()
 
 
 def grad_mode() -> bool:
-    """The modules take the tape-recording path whenever torch would record a graph."""
-    return torch.is_grad_enabled()
+    """The modules take the tape-recording path whenever torch would record a graph (the fp32 validation path is
+    forward-only: it never records)."""
+    return torch.is_grad_enabled() and compute_dtype() != torch.float32
 
 
 def _grad_act(g: torch.Tensor, dtype) -> torch.Tensor:
@@ -103,7 +113,7 @@ class ConvFn(Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        g = _grad_act(dy, x.dtype)
+        g = _grad_act(dy, _gd(x))
         need = ctx.needs_input_grad
         dx = ops.conv2d_dgrad(_dense(g) if ctx.mode == ops.CONV_3X3_S2 else g, weight, ctx.mode, in_hw=x.shape[2:]) \
             if need[0] else None
@@ -129,7 +139,7 @@ class GroupNormFn(Function):
     def backward(ctx, dy):
         x, stats, gamma, beta = ctx.saved_tensors
         silu, groups = ctx.cfg
-        gx, dg, db = ops.gn_backward(x, _dense(_grad_act(dy, x.dtype)), stats, gamma, beta, silu, groups)
+        gx, dg, db = ops.gn_backward(x, _dense(_grad_act(dy, _gd(x))), stats, gamma, beta, silu, groups)
         return gx, dg, db, None, None, None
 
 
@@ -161,7 +171,7 @@ class ResnetBlockFn(Function):
     @staticmethod
     def backward(ctx, dy):
         x, st1, a1, h, st2, a2, g1, b1, w1, g2, b2, w2, wn = ctx.saved_tensors
-        g = _dense(_grad_act(dy, x.dtype))
+        g = _dense(_grad_act(dy, _gd(x)))
         # conv2 (+ shortcut)
         da2 = ops.conv2d_dgrad(g, w2, ops.CONV_3X3)
         dw2 = ops.conv2d_wgrad(a2, g, 3)
@@ -212,7 +222,7 @@ class AttnBlockFn(Function):
         n, c, hh, ww = x.shape
         L = hh * ww
         lp = probs.shape[-1]
-        dt = x.dtype
+        dt = _gd(x)   # gradients (bf16) meet forward activations (x.dtype) in mixed-format tcgen05 GEMMs below
         scale = 1.0 / math.sqrt(c)
         g = _dense(_grad_act(dy, dt))
         # proj_out
@@ -234,7 +244,7 @@ class AttnBlockFn(Function):
         del pt, dot
         # dP = dO V^T ; dS = scale * P o (dP - rowsum(dP o P))
         dp = ops.gemm_tn_batched(dof, v, torch.float32)   # [n, L, L]
-        ds = ops.softmax_backward(probs, dp, L, scale)    # [n, L, lp]
+        ds = ops.softmax_backward(probs, dp, L, scale, out_dtype=dt)    # [n, L, lp]
         del dp
         # dQ = dS K ; dK = dS^T Q
         ops.gemm_tn_batched(ds, ops.transpose16(k, out_rows=lp), dt, out=dqkv[:, :, :c])
@@ -269,7 +279,7 @@ class UpsampleFn(Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        g = _grad_act(dy, x.dtype)
+        g = _grad_act(dy, _gd(x))
         dx = ops.pool2x2_sum(ops.conv2d_dgrad(g, weight, ops.CONV_3X3))
         dw = ops.conv2d_wgrad(ops.upsample2x(x), g, 3)
         return dx, dw, ops.bias_grad(g), None
@@ -280,14 +290,12 @@ class ActToNchwFn(Function):
 
     @staticmethod
     def forward(ctx, x):
-        ctx.dt = x.dtype if x.dtype != torch.float32 else None
         return ops.act_to_nchw_f32(x)
 
     @staticmethod
     def backward(ctx, g):
-        from .settings import compute_dtype
         n, c, h, w = g.shape
-        return ops.nchw_to_act(g, (c + 15) // 16 * 16, ctx.dt or compute_dtype())[:, :c]
+        return ops.nchw_to_act(g, (c + 15) // 16 * 16, grad_dtype())[:, :c]
 
 
 def act_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
@@ -313,7 +321,7 @@ class DynConvInFn(Function):
     def backward(ctx, dy):
         x, wvs, tape = ctx.saved_tensors
         mod = ctx.mod
-        g = _dense(_grad_act(dy, x.dtype))
+        g = _dense(_grad_act(dy, _gd(x)))
         dw = ops.conv2d_wgrad(x, g, 3)  # [E, C padded to 16, 3, 3]
         grads = mod._hyper_backward(wvs, dw, ops.bias_grad(g), mod.scaler, tape)
         return (None, None, None) + tuple(grads)
@@ -340,7 +348,7 @@ class DynConvOutFn(Function):
         x, oihw, waves, tape = ctx.saved_tensors
         mod = ctx.mod
         c = waves.size(0)
-        g = _grad_act_pad8(dy, x.dtype)
+        g = _grad_act_pad8(dy, _gd(x))
         dx = ops.conv2d_dgrad(g, oihw, ops.CONV_3X3) if ctx.needs_input_grad[0] else None
         dw = ops.conv2d_wgrad(x, g[:, :c], 3)  # [C, E, 3, 3]
         grads = mod._hyper_backward(waves, dw, ops.bias_grad(g[:, :c]), mod.scaler * mod.scaler, tape)

@@ -194,7 +194,7 @@ class ResnetBlock(nn.Module):
             # GN2 + SiLU in the prologue, residual add + next GN's statistics in the epilogue
             return self.conv2(h, residual=x, gn_next=True, pre_norm=norm2)
         h = norm2(h, silu=True)
-        if self.in_channels % 64 == 0 and self.out_channels % 64 == 0:
+        if self.in_channels % 64 == 0 and self.out_channels % 64 == 0 and x.dtype != torch.float32:
             # 1x1 shortcut folded into conv2's K loop: no shortcut tensor is written or re-read
             w, b = self._conv2_with_shortcut(x.dtype)
             return ops.conv2d(h, w, b, self.out_channels, ops.CONV_3X3, gn_groups=32, gn_eps=1e-6, x2=x)
@@ -240,6 +240,14 @@ class AttnBlock(nn.Module):
         wqkv, bqkv = self._qkv_operands(x.dtype)
         qkv = ops.conv2d(h, wqkv, bqkv, 3 * c, ops.CONV_1X1)  # NHWC [n, L, 3c]
         flat = qkv.permute(0, 2, 3, 1).reshape(n, L, 3 * c)     # view: pixel-major rows, pitch 3c
+        if x.dtype == torch.float32:
+            # fp32 validation path: fp32 scores, exact-exp softmax, P V with V read in place (SIMT fp32 GEMMs)
+            if L % 16 != 0:
+                raise RuntimeError("AttnBlock (fp32 validation path): H*W must be a multiple of 16")
+            q, k, v = flat[:, :, :c], flat[:, :, c:2 * c], flat[:, :, 2 * c:]
+            scores = ops.gemm_tn_batched(q, k, torch.float32, scale=1.0 / math.sqrt(c))
+            o = ops.gemm_pv_f32(ops.softmax_rows(scores, torch.float32), v).view(n, hh, ww, c).permute(0, 3, 1, 2)
+            return self.proj_out(o, residual=x)
         if ops.attention_fused_ok(L, c, n):
             # flash-style: scores / probabilities live in TMEM and shared memory only
             o = ops.attention_fused(flat, c).view(n, hh, ww, c).permute(0, 3, 1, 2)

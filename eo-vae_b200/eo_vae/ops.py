@@ -124,7 +124,7 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, 
         raise RuntimeError("eo_vae.conv2d: bias must be fp32 [cout]")
     stats = ws = None
     ws_bytes = 0
-    if gn_groups > 0:
+    if gn_groups > 0 and x.dtype != torch.float32:   # (fp32 validation path: statistics come from eovae_gn_stats)
         ws_bytes = _C.lib().eovae_conv2d_gn_workspace_bytes(n, h, w, mode, cout, gn_groups)
         if ws_bytes > 0:
             stats = torch.empty((n, gn_groups, 2), dtype=torch.float32, device=x.device)
@@ -170,7 +170,8 @@ def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 
     _need_cuda(a, b)
     bsz, m, k = a.shape
     n = b.shape[1]
-    if b.shape[0] != bsz or b.shape[2] != k or a.stride(2) != 1 or b.stride(2) != 1 or a.dtype != b.dtype:
+    # a / b may mix f16 and bf16 (kind::f16 takes the two operand formats independently); fp32 = the validation path
+    if (b.shape[0] != bsz or b.shape[2] != k or a.stride(2) != 1 or b.stride(2) != 1 or a.element_size() != b.element_size()):
         raise RuntimeError("eo_vae.gemm_tn_batched: bad operand layout")
     if a.stride(0) != m * a.stride(1):
         raise RuntimeError("eo_vae.gemm_tn_batched: A batches must be contiguous")
@@ -182,7 +183,7 @@ def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 
             raise RuntimeError("eo_vae.gemm_tn_batched: bad output view")
     rc = _timed("attn_gemm", 2.0 * bsz * m * n * k, lambda: _C.lib().eovae_gemm_tn_batched(
         _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1), b.stride(0), _ptr(c), DT[out_dtype], c.stride(1), bsz, m, n, k,
-        DT[a.dtype], float(scale), _stream()))
+        DT[a.dtype], DT[b.dtype], float(scale), _stream()))
     _C.check(rc, "eovae_gemm_tn_batched")
     return c
 
@@ -194,6 +195,21 @@ def gemm_tn_batched(a: torch.Tensor, b: torch.Tensor, out_dtype, scale: float = 
 USE_FUSED_ATTENTION = True
 FUSED_ATTENTION_MAX_L = 2048            # above this the GEMM path is faster ...
 FUSED_ATTENTION_SCORE_BYTES = 8 << 30   # ... unless N * L^2 * 6 bytes of scores + probabilities exceed this
+
+
+def gemm_pv_f32(p: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """fp32 validation path: o[i] = p[i] @ v[i] with p [B, L, Lk] dense and v [B, Lk, C] read IN PLACE (a channel slice of the
+    qkv tensor: keys along the row pitch), Lk a multiple of 16."""
+    _need_cuda(p, v)
+    bsz, l, lk = p.shape
+    c = v.shape[2]
+    if p.dtype != torch.float32 or v.dtype != torch.float32 or not p.is_contiguous() or v.stride(2) != 1 or v.shape[1] != lk:
+        raise RuntimeError("eo_vae.gemm_pv_f32: bad operand layout")
+    out = torch.empty((bsz, l, c), dtype=torch.float32, device=p.device)
+    rc = _C.lib().eovae_gemm_strided_f32(_ptr(p), lk, l * lk, _ptr(v), 1, v.stride(1), v.stride(0), _ptr(out), c, bsz, l, c, lk,
+                                        1.0, _stream())
+    _C.check(rc, "eovae_gemm_strided_f32")
+    return out
 
 
 def attention_fused_ok(l: int, c: int, n: int = 1) -> bool:
@@ -278,7 +294,8 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     if pix_stride(x) != c:
         raise RuntimeError("eo_vae.upsample2x: dense channels-last input required")
     out = nhwc_empty(n, c, 2 * h, 2 * w, x.dtype, x.device)
-    _C.check(_C.lib().eovae_upsample2x(_ptr(x), _ptr(out), n, h, w, c, _stream()), "eovae_upsample2x")
+    # the kernel copies 16-byte vectors of 2-byte lanes: an fp32 pixel is twice as many lanes
+    _C.check(_C.lib().eovae_upsample2x(_ptr(x), _ptr(out), n, h, w, c * x.element_size() // 2, _stream()), "eovae_upsample2x")
     return out
 
 
@@ -573,7 +590,7 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor
             dw = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
         flops = 2.0 * n * h * w * cout * cin * ksize * ksize
         rc = _timed("wgrad", flops, lambda: lib.eovae_conv2d_wgrad_nhwc(
-            _ptr(x), pix_stride(x), _ptr(dy), pix_stride(dy), DT[x.dtype], n, h, w, cin, cout, ksize, _ptr(dw), 1 if acc else 0,
+            _ptr(x), pix_stride(x), _ptr(dy), pix_stride(dy), DT[x.dtype], DT[dy.dtype], n, h, w, cin, cout, ksize, _ptr(dw), 1 if acc else 0,
             _ptr(ws), ws_bytes, _stream()))
         _C.check(rc, "eovae_conv2d_wgrad_nhwc")
         return dw
@@ -595,7 +612,7 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: torch.Tensor
     acc = dw is not None
     if dw is None:
         dw = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
-    _C.check(lib.eovae_conv2d_wgrad(_ptr(xt), _ptr(dyt), DT[x.dtype], n, h, wp, cin, cout, ksize, _ptr(dw), 1 if acc else 0,
+    _C.check(lib.eovae_conv2d_wgrad(_ptr(xt), _ptr(dyt), DT[x.dtype], DT[dy.dtype], n, h, wp, cin, cout, ksize, _ptr(dw), 1 if acc else 0,
                                     _ptr(ws), ws_bytes, _stream()), "eovae_conv2d_wgrad")
     return dw
 
@@ -618,34 +635,37 @@ def bias_grad(dy: torch.Tensor) -> torch.Tensor:
 
 def gn_backward(x: torch.Tensor, grad_out: torch.Tensor, stats, gamma, beta, silu: bool, groups: int = 32,
                 grad_add=None):
-    """-> (grad_x, dgamma, dbeta) of y = [silu](GroupNorm(x))."""
+    """-> (grad_x, dgamma, dbeta) of y = [silu](GroupNorm(x)).  x is the forward activation (its dtype), grad_out / grad_add
+    / grad_x share the gradient dtype (the training default mixes f16 activations with bf16 gradients)."""
     _need_cuda(x, grad_out, stats, gamma, beta, grad_add)
     n, c, h, w = x.shape
     if pix_stride(x) != c or pix_stride(grad_out) != c or (grad_add is not None and pix_stride(grad_add) != c):
         raise RuntimeError("eo_vae.gn_backward: dense channels-last tensors required")
+    if grad_add is not None and grad_add.dtype != grad_out.dtype:
+        raise RuntimeError("eo_vae.gn_backward: grad_add must have the gradient dtype")
     lib = _C.lib()
     ws_bytes = lib.eovae_gn_backward_workspace_bytes(n, h * w, c, groups)
     ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=x.device)
-    gx = nhwc_empty(n, c, h, w, x.dtype, x.device)
+    gx = nhwc_empty(n, c, h, w, grad_out.dtype, x.device)
     dg = torch.empty((c,), dtype=torch.float32, device=x.device)
     db = torch.empty((c,), dtype=torch.float32, device=x.device)
     cs = torch.empty((c,), dtype=torch.float32, device=x.device)
-    _C.check(lib.eovae_gn_backward(_ptr(x), _ptr(grad_out), DT[x.dtype], _ptr(stats), _ptr(gamma), _ptr(beta), n, h * w, c,
+    _C.check(lib.eovae_gn_backward(_ptr(x), _ptr(grad_out), DT[x.dtype], DT[grad_out.dtype], _ptr(stats), _ptr(gamma), _ptr(beta), n, h * w, c,
                                    groups, 1 if silu else 0, _ptr(grad_add), _ptr(gx), _ptr(dg), _ptr(db), 0, _ptr(cs), _ptr(ws),
                                    ws_bytes, _stream()), "eovae_gn_backward")
     gx._colsum = cs  # per-channel sum of gx (bias gradient of the conv that produced x): rides along like _gn_stats
     return gx, dg, db
 
 
-def softmax_backward(p: torch.Tensor, dp: torch.Tensor, cols: int, scale: float) -> torch.Tensor:
-    """ds = scale * p o (dp - rowsum(dp o p)); p 16-bit [..., lp], dp fp32 [..., >= cols] -> ds 16-bit [..., lp]."""
+def softmax_backward(p: torch.Tensor, dp: torch.Tensor, cols: int, scale: float, out_dtype=None) -> torch.Tensor:
+    """ds = scale * p o (dp - rowsum(dp o p)); p 16-bit [..., lp], dp fp32 [..., >= cols] -> ds 16-bit [..., lp] (out_dtype)."""
     _need_cuda(p, dp)
     if not p.is_contiguous() or not dp.is_contiguous() or dp.dtype != torch.float32:
         raise RuntimeError("eo_vae.softmax_backward: contiguous p (16-bit) and dp (fp32) required")
     lp = p.shape[-1]
     rows = p.numel() // lp
-    ds = torch.empty_like(p)
-    _C.check(_C.lib().eovae_softmax_backward(_ptr(p), lp, _ptr(dp), dp.shape[-1], _ptr(ds), lp, DT[p.dtype], rows, cols, lp,
+    ds = torch.empty_like(p, dtype=out_dtype or p.dtype)
+    _C.check(_C.lib().eovae_softmax_backward(_ptr(p), lp, _ptr(dp), dp.shape[-1], _ptr(ds), lp, DT[p.dtype], DT[ds.dtype], rows, cols, lp,
                                              float(scale), _stream()), "eovae_softmax_backward")
     return ds
 

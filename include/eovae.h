@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EOVAE_ABI_VERSION 1
+#define EOVAE_ABI_VERSION 2
 
 /* dtype codes */
 #define EOVAE_DT_BF16 0
@@ -83,7 +83,15 @@ int eovae_conv2d(const void* x, int n, int h, int w, int cin, long long x_pix_st
  *      (F.scaled_dot_product_attention, layers.py:134-141)                                                      */
 int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride, const void* b, long long ldb,
                           long long b_batch_stride, void* c, int c_dtype, long long ldc, int batch, int m, int n, int k,
-                          int ab_dtype, float scale, void* stream);
+                          int a_dtype, int b_dtype, float scale, void* stream);
+
+/* fp32 validation path (north_star: 1e-4 against the fp32 reference; selected by dtype code EOVAE_DT_F32 in eovae_conv2d,
+ * eovae_gemm_tn_batched, eovae_gn_stats, eovae_gn_apply, eovae_nchw_to_nhwc16, eovae_softmax_rows, eovae_latent_denorm,
+ * eovae_pack_conv_weight, eovae_pack_dyn_weight): SIMT fp32 FMAs, no tensor cores.  This entry is its general batched GEMM
+ * c[i][r][j] = scale * sum_k a[i][r][k] * b[i*b_batch_stride + j*b_n_stride + k*b_k_stride]  (K a multiple of 16).       */
+int eovae_gemm_strided_f32(const float* a, long long lda, long long a_batch_stride, const float* b, long long b_n_stride,
+                           long long b_k_stride, long long b_batch_stride, float* c, long long ldc, int batch, int m, int n, int k,
+                           float scale, void* stream);
 
 /* ---- fused flash-style attention of AttnBlock (layers.py:134-141): out[n][q][:] = softmax_k(q . k / sqrt(c)) v for
  *      qkv [n][l][qkv_ld >= 3c] 16-bit (q | k | v channel slices of one tensor), out [n][l][out_ld >= c] 16-bit.  Scores
@@ -192,7 +200,9 @@ int eovae_pack_conv_weight_dgrad(const float* w_oihw, void* out, int cout, int c
  * dgamma/dbeta fp32 [c] (optionally accumulated); grad_x or the parameter outputs may be NULL; grad_x_colsum (fp32 [c],
  * may be NULL) receives the per-channel sum of grad_x = the bias gradient of the conv that produced x, from the same pass */
 size_t eovae_gn_backward_workspace_bytes(int n, long long hw, int c, int groups);
-int eovae_gn_backward(const void* x, const void* grad_out, int dtype, const float* stats, const float* gamma,
+/* dtype = storage type of the forward activation x; grad_dtype = storage type of grad_out / grad_add / grad_x (the
+ * training default mixes f16 activations with bf16 gradients) */
+int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_dtype, const float* stats, const float* gamma,
                       const float* beta, int n, long long hw, int c, int groups, int with_silu, const void* grad_add,
                       void* grad_x, float* dgamma, float* dbeta, int accumulate_params, float* grad_x_colsum,
                       void* workspace, size_t workspace_bytes, void* stream);
@@ -205,12 +215,12 @@ int eovae_pool2x2_sum(const void* g, void* out, int dtype, int n, int h, int w, 
  * 1x1, the three x-shifted copies [3][n][cin][h*w] for 3x3; here `w` is the PADDED row length (a multiple of 8);
  * dw_oihw fp32 [cout][cin][k][k] (optionally accumulated).  Deterministic (fixed-order split-K reduction).          */
 size_t eovae_conv2d_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize);
-int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int n, int h, int w, int cin, int cout, int ksize,
+int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int dy_dtype, int n, int h, int w, int cin, int cout, int ksize,
                        float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 /* attention backward: ds = scale * p o (dp - rowsum(dp o p)); p 16-bit [rows][p_ld], dp fp32, ds 16-bit zero padded to
  * out_cols (layers.py:134-141 adjoint) */
 int eovae_softmax_backward(const void* p, long long p_ld, const float* dp, long long dp_ld, void* ds, long long ds_ld,
-                           int dtype, long long rows, int cols, int out_cols, float scale, void* stream);
+                           int dtype, int ds_dtype, long long rows, int cols, int out_cols, float scale, void* stream);
 /* adjoint of the reparameterisation in eovae_kl_reparam (distributions.py:44-46): dz NCHW fp32 [n][zc][h][w] ->
  * dmoments dense NCHW fp32 [n][2zc][h][w] (mean half = dz, logvar half = dz*eps*std/2 inside the clamp) */
 int eovae_reparam_backward(const float* moments, const long long* mstrides, const float* eps, const float* dz, float* dmoments,
@@ -325,7 +335,7 @@ int eovae_msssim_backward(const float* pred, const float* target, int b, int c, 
  * (W divides 64 or is a multiple of 64, H a multiple of 64 / min(W, 64)); otherwise use eovae_conv2d_wgrad. */
 int eovae_conv2d_wgrad_nhwc_ok(int h, int w);
 size_t eovae_conv2d_wgrad_nhwc_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize);
-int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int h,
+int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int dy_dtype, int n, int h,
                             int w, int cin, int cout, int ksize, float* dw_oihw, int accumulate, void* workspace,
                             size_t workspace_bytes, void* stream);
 /* TRAIN-mode latent glue (new_autoencoder.py:466-469 with self.training, :533-543): z NCHW fp32 [n][zc][h][w] ->

@@ -3,10 +3,12 @@
 The reference package cannot be imported normally here (`import eo_vae.models` pulls `lightning`,
 `omegaconf`, `torchmetrics`, `focal_frequency_loss`).  This shim registers
 alias packages whose ``__path__`` points into the reference tree, stubs the two orchestration-only
-dependencies, and imports the hot-path modules by path.  Nothing is copied: the reference sources are
-executed from where they lie.  The reference only exists in the build container, never on the GPU box,
-so everything here is used only by ``tests/golden/make_golden.py`` and by ``-m "not gpu"`` tests
-that skip when the tree is absent.
+dependencies, and imports the hot-path modules by path.  The reference sources are executed from where they lie
+(``/root/reference`` in the build container).  On the GPU box that tree does not exist; the git-ignored copy
+``baseline/_ref/`` that ``__graft_entry__.build()`` makes of the reference's ``eo_vae/models`` package (the install step of
+the bench contract's reference arm: unmodified files, never part of the repository history) travels there with the
+snapshot and is used by ``bench.py`` alone (``--impl reference``, ``gpu_eager``).  Tests use only ``/root/reference`` and
+skip when it is absent.
 """
 from __future__ import annotations
 
@@ -18,8 +20,15 @@ import types
 ALIAS = "eovae_reference"
 
 
-def reference_root() -> str | None:
-    for cand in (os.environ.get("EOVAE_REFERENCE_ROOT"), "/root/reference"):
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INSTALLED_COPY = os.path.join(_REPO, "baseline", "_ref")
+
+
+def reference_root(allow_installed_copy: bool = True) -> str | None:
+    cands = [os.environ.get("EOVAE_REFERENCE_ROOT"), "/root/reference"]
+    if allow_installed_copy:
+        cands.append(INSTALLED_COPY)
+    for cand in cands:
         if cand and os.path.isdir(os.path.join(cand, "eo_vae", "models")):
             return cand
     return None

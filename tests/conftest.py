@@ -29,3 +29,12 @@ def cuda(built_lib):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _default_numerics():
+    """Every test starts from (and leaves behind) the package's default numeric mode."""
+    yield
+    import eo_vae
+    from eo_vae.settings import default_compute_dtype
+    eo_vae.set_compute_dtype(default_compute_dtype())

@@ -19,7 +19,9 @@ from oracle.weights import FULL_CONFIG, TINY_CONFIG, WAVELENGTHS, make_state_dic
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-def run(tag, cfg, modality, size, batch, seed):
+def run(tag, cfg, modality, size, batch, seed, recon_stride=1):
+    """recon_stride > 1: the reconstruction is stored on the pixel sub-lattice [::s, ::s] (a 12 x 256 x 256 fp32 batch
+    does not compress; the sub-lattice keeps the fixture small and the rel-L2 statistic unbiased)."""
     torch.manual_seed(0)
     sd = make_state_dict(cfg, seed)
     model = ref_shim.build_reference_model(cfg, sd, train=False)
@@ -42,7 +44,8 @@ def run(tag, cfg, modality, size, batch, seed):
         os.path.join(OUT, f"{tag}.npz"),
         modality=modality, size=size, batch=batch, seed=seed,
         moments=moments.numpy().astype(np.float32), kl=kl.numpy(), z_norm=z_norm.numpy(),
-        recon=recon.numpy(), w_in=w_in.numpy(), b_in=b_in.numpy(), w_out=w_out.numpy(), b_out=b_out.numpy(),
+        recon=recon[..., ::recon_stride, ::recon_stride].contiguous().numpy(), recon_stride=recon_stride,
+        recon_sum=recon.double().sum().numpy(), recon_sumsq=(recon.double() ** 2).sum().numpy(), w_in=w_in.numpy(), b_in=b_in.numpy(), w_out=w_out.numpy(), b_out=b_out.numpy(),
         z_sample=z_s.numpy(), l1=l1.numpy(), char=char.numpy())
     print(tag, "moments", tuple(moments.shape), "recon", tuple(recon.shape), "kl", kl.tolist(), "l1", float(l1))
 
@@ -53,3 +56,4 @@ if __name__ == "__main__":
     run("tiny_s2l1c", TINY_CONFIG, "S2L1C", 48, 1, 2)
     run("full_s2rgb", FULL_CONFIG, "S2RGB", 256, 1, 0)     # BASELINE.json configs[0]
     run("full_s2l2a_64", FULL_CONFIG, "S2L2A", 64, 2, 3)
+    run("full_s2l2a_256", FULL_CONFIG, "S2L2A", 256, 2, 5, recon_stride=4)   # BASELINE.json configs[1] patch shape

@@ -28,7 +28,7 @@ def test_binding_table_matches_header(built_lib):
     from eo_vae import _C
     assert sorted(_C.SIGNATURES) == _declared_symbols()
     handle = _C.lib()
-    assert handle.eovae_version() == 1
+    assert handle.eovae_version() == 2
     assert handle.eovae_conv_chunk_bytes(128) == 128 and handle.eovae_conv_chunk_bytes(32) == 64
     assert handle.eovae_conv_k_per_tap(12) == 16 and handle.eovae_conv_k_per_tap(512) == 512
 

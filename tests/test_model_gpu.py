@@ -31,43 +31,46 @@ def _setup(tag, cuda):
     return gold, model, x.to(cuda), wvs.to(cuda)
 
 
-# rel-L2 bounds (latent, reconstruction) per tensor-core operand type.  BASELINE.json asks for 1e-2 on both and 1e-3 on
-# the losses.  fp16 operands (the reference trainer's own `precision: 16-mixed`) meet all of it with a 3-8x margin.
-# bf16 operands sit AT that bar for latents (measured 0.8-1.07e-2) and above it for reconstructions (2.0-2.9e-2): this is
-# the bf16 noise floor of the network, not a kernel property - tools/precision_study.py shows an ideal implementation
-# that rounds nothing but the MMA operands to bf16 (fp32 storage, fp32 GN) at 0.73e-2 / 1.6e-2, our bf16-storage scheme
-# at 0.96e-2 / 2.1e-2, and SURVEY.md section 7 measured the reference itself under bf16 autocast at 1.7e-2 / 5.4e-2.
-BOUNDS = {torch.bfloat16: (1.5e-2, 3.5e-2), torch.float16: (3e-3, 6e-3)}
+# rel-L2 bounds (latent, reconstruction, KL, L1) per numeric mode, against the fp32 reference's golden vectors.
+#  * torch.float16 = the package DEFAULT and the dtype of every bench line: the north-star values, unwidened (latents and
+#    reconstructions within 1e-2, losses within 1e-3; measured 1.0-1.4e-3 / 2.4-3.3e-3).
+#  * torch.float32 = the fp32 validation path: 1e-4.
+#  * torch.bfloat16 = the opt-in wide-range mode.  Its 8-bit significand puts an IDEAL bf16 implementation of this network
+#    (only MMA operands rounded) at 0.7e-2 / 1.6e-2 (tools/precision_roles.py), so it is held to documented looser bounds
+#    and is not what the package ships as default.
+BOUNDS = {torch.float16: (1e-2, 1e-2, 1e-3, 1e-3), torch.float32: (1e-4, 1e-4, 1e-4, 1e-4),
+          torch.bfloat16: (1.5e-2, 3.5e-2, 1e-3, 2e-3)}
+DEFAULT = torch.float16
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("tag", ["tiny_s2l2a", "tiny_s1rtc", "tiny_s2l1c", "full_s2l2a_64", "full_s2rgb"])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("tag", ["tiny_s2l2a", "tiny_s1rtc", "tiny_s2l1c", "full_s2l2a_64", "full_s2rgb", "full_s2l2a_256"])
 def test_against_reference_golden(cuda, tag, dtype):
     import eo_vae
     gold, model, x, wvs = _setup(tag, cuda)
+    assert eo_vae.compute_dtype() == DEFAULT          # the default mode is the one held to the north-star bounds
     eo_vae.set_compute_dtype(dtype)
-    try:
-        with torch.no_grad():
-            moments = model.encoder(x, wvs)
-            z = model.encode_spatial_normalized(x, wvs)
-            recon = model.reconstruct(x, wvs)
-            post = model.encode(x, wvs)
-            kl = post.kl()
-    finally:
-        eo_vae.set_compute_dtype(torch.bfloat16)
+    with torch.no_grad():
+        moments = model.encoder(x, wvs)
+        z = model.encode_spatial_normalized(x, wvs)
+        recon = model.reconstruct(x, wvs)
+        post = model.encode(x, wvs)
+        kl = post.kl()
+    st = int(gold["recon_stride"]) if "recon_stride" in gold.files else 1   # large fixtures keep a pixel sub-lattice
     assert moments.shape == gold["moments"].shape and moments.is_contiguous()
-    assert z.shape == gold["z_norm"].shape and recon.shape == gold["recon"].shape
-    e_m, e_z, e_r = _rel(moments.cpu(), gold["moments"]), _rel(z.cpu(), gold["z_norm"]), _rel(recon.cpu(), gold["recon"])
+    assert z.shape == gold["z_norm"].shape and recon.shape == x.shape
+    e_m, e_z = _rel(moments.cpu(), gold["moments"]), _rel(z.cpu(), gold["z_norm"])
+    e_r = _rel(recon[..., ::st, ::st].cpu(), gold["recon"])
     e_kl = _rel(kl.cpu(), gold["kl"])
     l1 = float((recon.cpu() - x.cpu()).abs().mean())
     e_l1 = abs(l1 - float(gold["l1"])) / float(gold["l1"])
     print(f"PARITY {tag} {str(dtype).split('.')[-1]}: moments {e_m:.3e} latent {e_z:.3e} recon {e_r:.3e} "
           f"kl {e_kl:.3e} l1 {e_l1:.3e}")
-    bz, br = BOUNDS[dtype]
+    bz, br, bkl, bl1 = BOUNDS[dtype]
     assert e_z < bz, f"latent rel-L2 {e_z}"
     assert e_r < br, f"reconstruction rel-L2 {e_r}"
-    assert e_kl < 1e-3
-    assert e_l1 < (1e-3 if dtype == torch.float16 else 2e-3)
+    assert e_kl < bkl, f"KL {e_kl}"
+    assert e_l1 < bl1, f"L1 {e_l1}"
 
 
 def test_sample_and_decode_api(cuda):
@@ -80,7 +83,7 @@ def test_sample_and_decode_api(cuda):
         eps = torch.from_numpy(np.random.Generator(np.random.Philox(key=[int(gold["seed"]), 99])).standard_normal(
             tuple(post.mean.shape), dtype=np.float32))
         zs = post.sample(eps.to(cuda))
-        assert _rel(zs.cpu(), gold["z_sample"]) < BOUNDS[torch.bfloat16][0]
+        assert _rel(zs.cpu(), gold["z_sample"]) < BOUNDS[DEFAULT][0]
         # decode_spatial_normalized(encode_spatial_normalized(x)) == reconstruct(x)
         z = model.encode_spatial_normalized(x, wvs)
         r1 = model.decode_spatial_normalized(z, wvs)
@@ -92,7 +95,7 @@ def test_sample_and_decode_api(cuda):
         r3 = model.decode(zp, wvs)
         assert _rel(r3, r2) < 2e-3
         ref = O.decode(sd, zp.cpu(), wvs.cpu(), TINY_CONFIG["hyper_heads"])
-        assert _rel(r3.cpu(), ref) < BOUNDS[torch.bfloat16][1]
+        assert _rel(r3.cpu(), ref) < BOUNDS[DEFAULT][1]
 
 
 def test_full_size_properties(cuda):
@@ -129,8 +132,8 @@ def test_config5_512px_13band(cuda):
         z_ref = O.encode_spatial_normalized(sd, x[:1], wvs, FULL_CONFIG["hyper_heads"])
     assert z.shape == (2, 32, 64, 64)
     e = _rel(z[:1].cpu(), z_ref)
-    print(f"PARITY config5 512px bf16: latent {e:.3e}")
-    assert e < BOUNDS[torch.bfloat16][0]
+    print(f"PARITY config5 512px default numerics: latent {e:.3e}")
+    assert e < BOUNDS[DEFAULT][0]
 
 
 def test_cuda_graph_replay_is_bit_identical(cuda):
@@ -168,5 +171,5 @@ def test_forward_like_reference_test(cuda, modality, size, batch):
         torch.set_num_threads(max(1, os.cpu_count() or 1))
         ref = O.reconstruct(sd, x, wvs, FULL_CONFIG["hyper_heads"])
     e = _rel(recon.cpu(), ref)
-    print(f"PARITY forward {modality} {size}px bf16: recon {e:.3e}")
-    assert e < BOUNDS[torch.bfloat16][1]
+    print(f"PARITY forward {modality} {size}px default numerics: recon {e:.3e}")
+    assert e < BOUNDS[DEFAULT][1]

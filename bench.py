@@ -552,7 +552,8 @@ def run_ours(args, cfg):
         line = {
             "metric": cfg["metric"], "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": dtype_name(eo_vae.compute_dtype()), "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype_name(eo_vae.grad_dtype() if train else eo_vae.inference_dtype()),
+            "data": "synthetic",
             "config": {"workload": cfg["workload"], "batch_per_gpu": batch,
                        "parallelism": f"dp{world} (patches sharded by rank, " + ("one gradient all-reduce per step)" if train else "no collective)"),
                        "numerics": eo_vae.numerics_description(),

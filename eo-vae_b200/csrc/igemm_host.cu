@@ -1,5 +1,6 @@
 // Host side of the tcgen05 implicit-GEMM: TMA descriptor construction, tile-shape selection and launch.
 // Public C-ABI entry points are declared in include/eovae.h.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -181,9 +182,13 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
                  float scale, cudaStream_t stream, float* gn_stats = nullptr, int gn_groups = 0, float gn_eps = 0.f,
                  void* gn_ws = nullptr, size_t gn_ws_bytes = 0, const ASpec* extra = nullptr,
                  const GnPrologue* gnp = nullptr, int w_dtype = -1) {
-  if (w_dtype < 0) w_dtype = act_dtype;  // B operand format; kind::f16 takes the A / B formats independently
+  if (w_dtype < 0) w_dtype = act_dtype;
   EOVAE_CHECK((act_dtype == EOVAE_BF16 || act_dtype == EOVAE_F16) && (w_dtype == EOVAE_BF16 || w_dtype == EOVAE_F16),
               "igemm: operand dtypes must be bf16/f16");
+  // the instruction descriptor has separate A / B format fields, but sm_100a traps (illegal instruction, measured) on
+  // kind::f16 with f16 x bf16 operands: refuse instead of faulting.  EOVAE_ALLOW_MIXED_MMA=1 lifts the check (probe only).
+  EOVAE_CHECK(act_dtype == w_dtype || getenv("EOVAE_ALLOW_MIXED_MMA") != nullptr,
+              "igemm: A (%d) and B (%d) operand formats must be equal (tcgen05 kind::f16 rejects mixed f16/bf16)", act_dtype, w_dtype);
   EOVAE_CHECK(chunk_bytes == 32 || chunk_bytes == 64 || chunk_bytes == 128, "igemm: bad chunk bytes %d", chunk_bytes);
   EOVAE_CHECK(a.pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ptr) % 16) == 0,
               "igemm: activation pixel stride (%lld) must be a multiple of 8 elements and base 16B aligned", a.pix_stride);

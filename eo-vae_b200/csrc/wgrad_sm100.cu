@@ -606,6 +606,8 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
   EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad_nhwc: kernel size must be 3 or 1");
   EOVAE_CHECK((dtype == EOVAE_BF16 || dtype == EOVAE_F16) && (dy_dtype == EOVAE_BF16 || dy_dtype == EOVAE_F16),
               "conv2d_wgrad_nhwc: 16-bit operands only");
+  EOVAE_CHECK(dtype == dy_dtype || getenv("EOVAE_ALLOW_MIXED_MMA") != nullptr,
+              "conv2d_wgrad_nhwc: x (%d) and dy (%d) formats must be equal (tcgen05 kind::f16 rejects mixed f16/bf16)", dtype, dy_dtype);
   EOVAE_CHECK(eovae_conv2d_wgrad_nhwc_ok(h, w), "conv2d_wgrad_nhwc: %dx%d images do not tile into 64-pixel boxes", h, w);
   EOVAE_CHECK(cin % 4 == 0 && x_pix_stride % 8 == 0 && dy_pix_stride % 8 == 0 && x_pix_stride >= cin && dy_pix_stride >= cout,
               "conv2d_wgrad_nhwc: Cin %% 4 and 16-byte pixel pitches required (Cin %d, pitches %lld / %lld)", cin, x_pix_stride,
@@ -701,6 +703,8 @@ int eovae_conv2d_wgrad(const void* x_t, const void* dy_t, int dtype, int dy_dtyp
   EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad: kernel size must be 3 or 1");
   EOVAE_CHECK((dtype == EOVAE_BF16 || dtype == EOVAE_F16) && (dy_dtype == EOVAE_BF16 || dy_dtype == EOVAE_F16),
               "conv2d_wgrad: 16-bit operands only");
+  EOVAE_CHECK(dtype == dy_dtype || getenv("EOVAE_ALLOW_MIXED_MMA") != nullptr,
+              "conv2d_wgrad: x (%d) and dy (%d) formats must be equal (tcgen05 kind::f16 rejects mixed f16/bf16)", dtype, dy_dtype);
   EOVAE_CHECK(w % 8 == 0 && cin % 16 == 0, "conv2d_wgrad: (padded) W %% 8 and Cin %% 16 required (W %d, Cin %d)", w, cin);
   EOVAE_CHECK(workspace_bytes >= eovae_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, ksize), "conv2d_wgrad: workspace too small");
   WgradParams p;

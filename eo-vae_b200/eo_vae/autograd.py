@@ -26,11 +26,12 @@ from .settings import compute_dtype, grad_dtype
 
 
 def _gd(x: torch.Tensor):
-    """Storage type of the gradients between layers: bf16 beside 16-bit activations (settings.grad_dtype)."""
+    """Storage type of the gradients between layers = the type of the saved forward activation they meet in the
+    weight-gradient GEMMs (tcgen05 kind::f16 needs equal A / B formats): settings.train_dtype on every taped call."""
     if x.dtype == torch.float32:
         raise RuntimeError("eo_vae: the fp32 validation path is forward-only (set_compute_dtype(torch.float16 | torch.bfloat16) "
                            "for training)")
-    return grad_dtype()
+    return x.dtype
 
 
 def grad_mode() -> bool:

@@ -10,8 +10,12 @@ Three modes, selected with ``set_compute_dtype``:
   measured 1.0-1.4e-3 / 2.4-3.3e-3 against 0.8-1.1e-2 / 1.9-2.8e-2 for bf16, whose 8-bit significand puts the *ideal*
   bf16 implementation of this network at 0.7e-2 / 1.6e-2 (``tools/precision_roles.py``: bf16 storage of the residual
   stream alone costs 0.7e-2 / 1.4e-2, bf16 rounding of the un-normalised conv operands another 0.6e-2 / 1.2e-2).
-  Gradients flowing between layers in the training step are bf16 (``grad_dtype``): their dynamic range is what needs the
-  wide exponent (1 / (B*C*H*W) ~ 8e-8 at the shipped batch), exactly why the reference pairs fp16 with a GradScaler.
+  The TRAINING step (any call made with autograd enabled) runs in ``train_dtype`` instead, bf16 by default: the gradients
+  flowing between layers need the wide exponent (1 / (B*C*H*W) ~ 8e-8 at the shipped batch - why the reference pairs fp16
+  with a GradScaler), and tcgen05 ``kind::f16`` rejects mixed f16 x bf16 operands (illegal instruction on sm_100a, measured),
+  so the activations that meet those gradients in the weight-gradient GEMMs must be bf16 as well.  The losses of a bf16
+  forward stay within the stated 1e-3.  ``set_train_dtype(torch.float16)`` trains in half precision throughout for callers
+  that bring their own loss scaling (Lightning ``precision: 16-mixed``).
 * ``torch.bfloat16``: everything 16-bit in bf16 (fp16's range is 65504; a checkpoint whose residual stream exceeds it
   needs this mode and accepts the ~1e-2 / 2e-2 deviation).
 * ``torch.float32``: the validation path - fp32 activations and fp32 SIMT kernels end to end (``csrc/fp32_path.cu``), eval
@@ -20,17 +24,24 @@ Three modes, selected with ``set_compute_dtype``:
 import torch
 
 _COMPUTE_DTYPE = torch.float16
-_GRAD_DTYPE = torch.bfloat16
+_TRAIN_DTYPE = torch.bfloat16
 
 
 def compute_dtype() -> torch.dtype:
-    """Storage / operand type of the activations."""
+    """Storage / operand type of the activations of the call being made: the inference mode, or ``train_dtype`` when the
+    call records an autograd tape."""
+    if _COMPUTE_DTYPE != torch.float32 and torch.is_grad_enabled():
+        return _TRAIN_DTYPE
+    return _COMPUTE_DTYPE
+
+
+def inference_dtype() -> torch.dtype:
     return _COMPUTE_DTYPE
 
 
 def grad_dtype() -> torch.dtype:
-    """Storage type of the gradients that flow between layers in the training step (parameter gradients are fp32)."""
-    return _GRAD_DTYPE if _COMPUTE_DTYPE != torch.float32 else torch.float32
+    """Storage type of the activations AND inter-layer gradients of the training step (parameter gradients are fp32)."""
+    return _TRAIN_DTYPE
 
 
 def set_compute_dtype(dtype: torch.dtype) -> None:
@@ -40,8 +51,19 @@ def set_compute_dtype(dtype: torch.dtype) -> None:
     _COMPUTE_DTYPE = dtype
 
 
+def set_train_dtype(dtype: torch.dtype) -> None:
+    global _TRAIN_DTYPE
+    if dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("train dtype must be torch.bfloat16 (default) or torch.float16 (caller provides loss scaling)")
+    _TRAIN_DTYPE = dtype
+
+
 def default_compute_dtype() -> torch.dtype:
     return torch.float16
+
+
+def default_train_dtype() -> torch.dtype:
+    return torch.bfloat16
 
 
 def numerics_description() -> str:
@@ -49,5 +71,7 @@ def numerics_description() -> str:
     if _COMPUTE_DTYPE == torch.float32:
         return "fp32 validation path: fp32 activations, fp32 SIMT kernels (no tensor cores)"
     name = "fp16" if _COMPUTE_DTYPE == torch.float16 else "bf16"
-    return (f"{name} activations and tcgen05 operands (kind::f16), fp32 accumulate; fp32 GroupNorm statistics, softmax, "
-            f"hypernetwork and reductions; bf16 inter-layer gradients in training")
+    tname = "fp16" if _TRAIN_DTYPE == torch.float16 else "bf16"
+    return (f"inference: {name} activations and tcgen05 operands (kind::f16), fp32 accumulate; training step: {tname} "
+            f"activations, operands and inter-layer gradients, fp32 parameter gradients; fp32 GroupNorm statistics, softmax, "
+            f"hypernetwork and reductions in both")

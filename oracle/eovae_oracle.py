@@ -5,12 +5,16 @@ and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  
 one reference function as a pure function of a ``state_dict`` (no nn.Module, no autocast, no GPU) and
 cites the reference lines it follows (paths relative to /root/reference).
 
-Pinning: network + posterior + latent-normalisation functions are pinned against the unmodified
-reference modules executed in the build container (``tests/test_oracle_vs_reference.py``, live, and
-``tests/golden/*.npz`` generated by ``tests/golden/make_golden.py``).  **MS-SSIM: parity unpinned** - the
-reference delegates it to ``torchmetrics`` (un-vendored, unpinned, absent from this image and from
-/root/reference), so ``ms_ssim`` restates torchmetrics' published algorithm anchored on the reference's call
-site (``consistency_loss.py:24-37``: data_range=6.0, kernel_size=5, 5 betas, defaults otherwise).
+Pinning: network + posterior + latent-normalisation functions, the SAM / gradient-difference / focal-frequency losses,
+the running statistics (``encode_latents.py:36-109``) and the collate-side preprocessing
+(``terramesh_datamodule.py:130-369, 418-503``) are pinned against the unmodified reference code executed in the build
+container (``tests/test_oracle_vs_reference.py``, live - the last two bit for bit - and ``tests/golden/*.npz`` generated
+by ``tests/golden/make_golden.py``).  **MS-SSIM has no reference-held pin**: the reference delegates it to
+``torchmetrics`` (un-vendored, unpinned, absent from this image and from /root/reference), so ``ms_ssim`` restates
+torchmetrics' published algorithm anchored on the reference's call site (``consistency_loss.py:24-37``: data_range=6.0,
+kernel_size=5, 5 betas, defaults otherwise) and is cross-checked (value to 1e-10 in fp64, gradient by finite differences)
+against ``tests/msssim_independent.py``, an fp64 numpy / scipy implementation written separately from Wang et al.
+2003 / 2004 and the same documented conventions (``tests/test_oracle.py``).
 """
 from __future__ import annotations
 
@@ -378,8 +382,8 @@ def charbonnier_loss(pred, target, eps: float = 1e-3):
     return torch.sqrt(d * d + eps * eps).mean()
 
 
-def _gauss1d(size: int, sigma: float, dtype):
-    dist = torch.arange((1 - size) / 2, (1 + size) / 2, 1, dtype=dtype)
+def _gauss1d(size: int, sigma: float, dtype, device=None):
+    dist = torch.arange((1 - size) / 2, (1 + size) / 2, 1, dtype=dtype, device=device)
     g = torch.exp(-((dist / sigma) ** 2) / 2)
     return g / g.sum()
 
@@ -391,7 +395,7 @@ def ssim_and_cs(pred, target, data_range=6.0, sigma=1.5, k1=0.01, k2=0.03):
     ks = int(3.5 * sigma + 0.5) * 2 + 1
     pad = (ks - 1) // 2
     ch = pred.shape[1]
-    g = _gauss1d(ks, sigma, pred.dtype)
+    g = _gauss1d(ks, sigma, pred.dtype, pred.device)
     kern = (g[:, None] * g[None, :]).expand(ch, 1, ks, ks).contiguous()
     p = F.pad(pred, (pad, pad, pad, pad), mode="reflect")
     t = F.pad(target, (pad, pad, pad, pad), mode="reflect")
@@ -424,7 +428,7 @@ def ms_ssim(pred, target, data_range=6.0, betas=MS_BETAS):
         pred = F.avg_pool2d(pred, 2)
         target = F.avg_pool2d(target, 2)
     stack = torch.stack(vals)
-    b = torch.tensor(betas, dtype=stack.dtype).view(-1, 1)
+    b = torch.tensor(betas, dtype=stack.dtype, device=stack.device).view(-1, 1)
     return torch.prod(stack**b, dim=0).mean()
 
 

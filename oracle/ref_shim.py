@@ -128,6 +128,39 @@ def load_reference_losses():
     return importlib.import_module(name)
 
 
+def load_reference_definitions(rel_path: str, drop_imports=(), drop_defs=()):
+    """Execute a reference source file that cannot be imported whole (top-level imports of packages that are absent
+    here), UNMODIFIED except for the statements dropped by name: the file is parsed, ``import`` statements whose module
+    starts with one of ``drop_imports`` and top-level classes / functions listed in ``drop_defs`` (those that need the
+    dropped imports) are removed, and the remaining syntax tree is compiled and executed in a fresh module namespace.
+    Used to pin the oracle's running-statistics and collate restatements (``encode_latents.py:36-109``,
+    ``eo_vae/datasets/terramesh_datamodule.py:130-369, 418-503``).  Only /root/reference is read (never the installed
+    copy: it holds ``eo_vae/models`` alone)."""
+    import ast
+    root = reference_root(allow_installed_copy=False)
+    if root is None:
+        return None
+    path = os.path.join(root, rel_path)
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    kept = []
+    for node in tree.body:
+        if isinstance(node, ast.Import) and any(a.name.split(".")[0] in drop_imports for a in node.names):
+            continue
+        if isinstance(node, ast.ImportFrom) and ((node.module or "").split(".")[0] in drop_imports or node.level > 0):
+            continue
+        if isinstance(node, (ast.ClassDef, ast.FunctionDef)) and node.name in drop_defs:
+            continue
+        if isinstance(node, ast.If) and isinstance(node.test, ast.Compare) and "__main__" in ast.dump(node.test):
+            continue
+        kept.append(node)
+    tree.body = kept
+    mod = types.ModuleType(ALIAS + "_extract_" + os.path.basename(rel_path).replace(".", "_"))
+    mod.__file__ = path
+    exec(compile(tree, path, "exec"), mod.__dict__)
+    return mod
+
+
 def _namespace():
     ns = types.SimpleNamespace()
     ns.layers = sys.modules[ALIAS + ".models.modules.layers"]

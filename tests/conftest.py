@@ -36,5 +36,6 @@ def _default_numerics():
     """Every test starts from (and leaves behind) the package's default numeric mode."""
     yield
     import eo_vae
-    from eo_vae.settings import default_compute_dtype
+    from eo_vae.settings import default_compute_dtype, default_train_dtype
     eo_vae.set_compute_dtype(default_compute_dtype())
+    eo_vae.set_train_dtype(default_train_dtype())

@@ -251,3 +251,76 @@ def test_eq_vae_transforms_match_reference(scale, angle):
     if angle is not None:
         t_ref = torch.rot90(t_ref, k=angle, dims=[-1, -2])
     assert torch.equal(O.eq_target(x, recon_ref.shape[-2:], angle), t_ref)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Pins of the "next" rows' oracles: the reference files cannot be imported whole (hydra, lightning,
+# matplotlib ... at module level), so their definitions are executed from the parsed, otherwise unmodified source
+# (ref_shim.load_reference_definitions).
+
+def _ref_encode_latents():
+    return ref_shim.load_reference_definitions(
+        "encode_latents.py", drop_imports=("lightning", "omegaconf", "hydra", "matplotlib", "eo_vae", "tqdm", "einops"))
+
+
+def _ref_datamodule():
+    return ref_shim.load_reference_definitions("eo_vae/datasets/terramesh_datamodule.py",
+                                               drop_imports=("lightning", "omegaconf"), drop_defs=("TerraMeshDataModule",))
+
+
+@pytest.mark.parametrize("shape", [(3, 4, 8, 8), (1, 32, 16, 16), (5, 2, 7, 9)])
+def test_running_stats_oracle_equals_reference(shape):
+    """O.running_stats_update vs RunningStatsButFast.update (encode_latents.py:36-109): every buffer after every update of
+    a stream of batches with drifting mean / scale (the parallel-variance merge is order dependent), bit for bit."""
+    ref = _ref_encode_latents().RunningStatsButFast((shape[1],), [0, 2, 3])
+    st = O.running_stats_init(shape[1])
+    g = torch.Generator().manual_seed(17)
+    for i in range(6):
+        x = torch.randn(shape, generator=g) * (1.0 + 0.5 * i) + 0.3 * i
+        ref(x)
+        st = O.running_stats_update(st, x)
+        for k in ("mean", "var", "std", "count", "min", "max"):
+            assert torch.equal(getattr(ref, k), st[k]), (i, k)
+    # the module in the datamodule file is the same class body: pin that copy too
+    ref2 = _ref_datamodule().RunningStatsButFast((shape[1],), [0, 2, 3])
+    ref2(x)
+    assert torch.equal(ref2.mean, O.running_stats_update(O.running_stats_init(shape[1]), x)["mean"])
+
+
+@pytest.mark.parametrize("modality,scheme", [("S2L2A", "custom"), ("S2L1C", "custom"), ("S2L2A", "legacy"),
+                                             ("S1RTC", "legacy"), ("S2RGB", "legacy")])
+@pytest.mark.parametrize("target", [None, (24, 24), (40, 56)])
+def test_preprocess_oracle_equals_reference_collate(modality, scheme, target):
+    """O.preprocess vs the reference's own collate closure (terramesh_datamodule.py:418-503: normaliser -> bilinear resize
+    -> apply_batch_augmentations), train mode, for eight seeds (all three D4 draws vary).  The oracle receives the flags the
+    reference drew - Python's ``random`` replayed with the same seed, in the reference's draw order."""
+    import random
+    dm = _ref_datamodule()
+    bands = len(dm.WAVELENGTHS[modality])
+    collate = dm.single_modality_collate_fn([modality], normalize=True, norm_scheme=scheme, target_size=target, mode="train")
+    norm = dm.NormalizerFactory.create(modality, scheme)
+    custom = not isinstance(norm, dm.LegacyZScoreNorm)
+    mean, std = norm.mean.reshape(-1).float(), norm.std.reshape(-1).float()
+    g = torch.Generator().manual_seed(5)
+    # raw digital numbers incl. values outside the clip range of the custom scheme
+    x = torch.rand((2, bands, 32, 48), generator=g) * 14000.0 - 2000.0
+    for seed in range(8):
+        random.seed(seed)
+        got = collate({"image": x.clone()})
+        random.seed(seed)
+        fh, fv, k = random.random() > 0.5, random.random() > 0.5, random.randint(0, 3)
+        want = O.preprocess(x, mean, std, custom, target, fh, fv, k)
+        assert got["image"].shape == want.shape, (seed, got["image"].shape, want.shape)
+        assert torch.equal(got["image"], want), (seed, float((got["image"] - want).abs().max()))
+        assert torch.equal(got["wvs"], torch.tensor(WAVELENGTHS[modality])) and got["modality"] == modality
+    # eval mode: no augmentation
+    ev = dm.single_modality_collate_fn([modality], normalize=True, norm_scheme=scheme, target_size=target, mode="eval")
+    assert torch.equal(ev({"image": x.clone()})["image"], O.preprocess(x, mean, std, custom, target))
+
+
+def test_product_preprocess_constants_equal_reference():
+    """The statistics baked into eo_vae.preprocess are the reference's (terramesh_datamodule.py:141-182)."""
+    from eo_vae import preprocess as P
+    n = _ref_datamodule().Sentinel2L2ANorm()
+    assert torch.equal(n.mean.reshape(-1), torch.tensor(P.S2L2A_CUSTOM_MEAN))
+    assert torch.equal(n.std.reshape(-1), torch.tensor(P.S2L2A_CUSTOM_STD))

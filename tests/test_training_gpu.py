@@ -343,7 +343,7 @@ def test_training_step_fp16_operands(cuda):
     from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
     from oracle import eovae_oracle as O
     from oracle.weights import WAVELENGTHS, synthetic_patches
-    eo_vae.set_compute_dtype(torch.float16)
+    eo_vae.set_train_dtype(torch.float16)
     try:
         model, sd, cfg = _tiny(cuda)
         model.train()
@@ -360,7 +360,7 @@ def test_training_step_fp16_operands(cuda):
         for p in model.parameters():
             p.grad.div_(scale)
     finally:
-        eo_vae.set_compute_dtype(torch.bfloat16)
+        eo_vae.set_train_dtype(torch.bfloat16)
     ref_sd = {k: (v.clone().float().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
     torch.manual_seed(1234)
     hl = cfg["resolution"] // 2 ** (len(cfg["ch_mult"]) - 1)

@@ -10,8 +10,10 @@
   4  the same step with the modality drawn per step and per rank from {S2L2A, S1RTC, S2RGB}
   5  encode_spatial_normalized, S2L1C 13x512x512, batch 32 per GPU
 
-One "step" = one pass of the path over one batch (hypernetworks included; train configs: forward, loss, backward, gradient
-exchange, clip, Adam).
+One "step" = one pass of the path over one batch (train configs: forward incl. both hypernetworks, loss, backward, gradient
+exchange, clip, Adam; inference configs: the hypernetwork output depends on the wavelength vector and the parameters only,
+so after the first call it is served from the module's operand cache - EOVAE_BENCH_NO_OPERAND_CACHE=1 regenerates it
+every step, +~0.5 ms).
 * value        : device-resident inputs, CUDA events on the launching stream, max over ranks
 * e2e          : the same call fed from pinned HOST memory, result read back to the host, copies inside the timed region
 * roofline     : the tcgen05 implicit-GEMM family (every convolution / attention GEMM launch of a step), algorithmic
@@ -373,6 +375,8 @@ def run_ours(args, cfg):
     gf = statistics.mean(gf_per_patch(kind, len(WAVELENGTHS[m]), size) for m in mods)
 
     model = g._model(FULL_CONFIG, make_state_dict(FULL_CONFIG, 0), dev)
+    if os.environ.get("EOVAE_BENCH_NO_OPERAND_CACHE"):
+        model.encoder.conv_in.CACHE_EVAL_OPERANDS = model.decoder.conv_out.CACHE_EVAL_OPERANDS = False
     sync_state = {}
     if train:
         from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
@@ -527,14 +531,21 @@ def run_ours(args, cfg):
                 "share_of_step": (t_ms / nprof) / (ms_total / args.steps),
                 "other_tensor_kernels": other}
 
-    extra_train = None
+    # secondary figures of the default line: the other BASELINE configs at this N (their own lines: --config 3 / 4 / 5)
+    extra_train = extra_mixed = extra_512 = None
     if kind == "encode" and args.config == 2 and not os.environ.get("EOVAE_BENCH_NO_TRAIN"):
         data.clear()
+        if not train:
+            del x_dev
         torch.cuda.empty_cache()
-        try:
-            extra_train = measure_train_step(g, dev, world, rank)
-        except Exception as exc:  # noqa: BLE001 - the secondary figure must never take the headline line down
-            extra_train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        def guarded(fn, *a, **k):
+            try:
+                return fn(*a, **k)
+            except Exception as exc:  # noqa: BLE001 - a secondary figure must never take the headline line down
+                return {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        extra_512 = guarded(measure_encode, model, CONFIGS[5], dev, world, rank)
+        extra_train = guarded(measure_train_step, g, dev, world, rank)
+        extra_mixed = guarded(measure_train_step, g, dev, world, rank, mods=MIXED, graphed=False)
 
     eager = None
     if rank == 0 and world == 1 and not os.environ.get("EOVAE_BENCH_NO_EAGER"):
@@ -568,6 +579,10 @@ def run_ours(args, cfg):
             line["gradient_exchange"] = comm
         if extra_train is not None:
             line["train_step"] = extra_train
+        if extra_mixed is not None:
+            line["train_step_mixed_modality"] = extra_mixed
+        if extra_512 is not None:
+            line["encode_512px_13band"] = extra_512
         if eager is not None:
             line["gpu_eager"] = eager
         if world == 1 and not os.environ.get("EOVAE_BENCH_NO_CPU"):
@@ -583,10 +598,40 @@ def run_ours(args, cfg):
 TRAIN_BATCH = 16
 
 
-def measure_train_step(g, dev, world, rank, steps: int = 5):
-    """Secondary figure of the default line (BASELINE configs[2]): EOFluxVAE.training_step, S2L2A batch 16 per GPU, Charbonnier
-    + MS-SSIM loss, clip 1.0, Adam; gradients averaged over the ranks.  ``--config 3`` measures the same step as a line of
-    its own."""
+def measure_encode(model, cfg, dev, world, rank, steps: int = 5):
+    """Secondary figure of the default line: another encode configuration (BASELINE configs[4]: S2L1C 13x512x512, batch 32 per
+    GPU) with the model of the headline run; ``--config 5`` measures it as a line of its own."""
+    import torch
+    import torch.distributed as dist
+    from oracle.weights import WAVELENGTHS
+    wvs = torch.tensor(WAVELENGTHS[cfg["modality"]], dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(777 + rank)
+    x = torch.randn((cfg["batch"], wvs.numel(), cfg["size"], cfg["size"]), generator=gen, device=dev).clamp_(-2.0, 6.0)
+    with torch.no_grad():
+        for _ in range(3):
+            model.encode_spatial_normalized(x, wvs)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            model.encode_spatial_normalized(x, wvs)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    pps = world * cfg["batch"] / ms * 1e3
+    return {"workload": cfg["workload"], "patches_per_s": pps, "ms_per_step": ms,
+            "tensor_tflops": pps * gf_per_patch("encode", wvs.numel(), cfg["size"]) / 1000.0, "steps": steps}
+
+
+def measure_train_step(g, dev, world, rank, steps: int = 5, mods=("S2L2A",), graphed: bool = True):
+    """Secondary figure of the default line (BASELINE configs[2], or configs[3] with ``mods`` = the three modalities drawn per
+    step and per rank): EOFluxVAE.training_step, batch 16 per GPU, Charbonnier + MS-SSIM loss, clip 1.0, Adam; gradients
+    averaged over the ranks.  ``--config 3`` / ``--config 4`` measure the same steps as lines of their own."""
     import torch
     import torch.distributed as dist
     from eo_vae.graphs import GraphedTrainStep
@@ -602,12 +647,15 @@ def measure_train_step(g, dev, world, rank, steps: int = 5):
             m.enable_ddp()
         return m
 
-    wvs = torch.tensor(WAVELENGTHS["S2L2A"], dtype=torch.float32, device=dev)
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
-    batch = {"image": torch.randn((TRAIN_BATCH, 12, 256, 256), generator=gen, device=dev).clamp_(-2.0, 6.0), "wvs": wvs}
+    batches = {m: {"image": torch.randn((TRAIN_BATCH, len(WAVELENGTHS[m]), 256, 256), generator=gen, device=dev).clamp_(-2.0, 6.0),
+                   "wvs": torch.tensor(WAVELENGTHS[m], dtype=torch.float32, device=dev)} for m in mods}
+    rng = random.Random(1234 + rank)
+    seq = [rng.choice(list(mods)) for _ in range(64)]
+    batch = batches[mods[0]]
 
     def timed(fn):
-        for i in range(3):
+        for i in range(max(3, len(mods))):
             fn(i)
         torch.cuda.synchronize()
         if world > 1:
@@ -632,30 +680,40 @@ def measure_train_step(g, dev, world, rank, steps: int = 5):
         dist.all_gather(allc, chk)
         return bool(all(torch.equal(allc[0], c) for c in allc))
 
+    def eager(model):
+        # warm-up iterations 0..len(mods)-1 visit every modality once (weight-operand caches, allocator)
+        return lambda i: model.training_step(batches[mods[i] if i < len(mods) else seq[i % len(seq)]], i)
+
     model = build()
-    ms_eager, loss = timed(lambda i: model.training_step(batch, i))
+    ms_eager, loss = timed(eager(model))
     sync_eager = checksum(model)
     ms_local = None
     if world > 1:   # exposed cost of the exchange: the same step with the collective switched off
         gs = model._grad_sync
         model._grad_sync = None
         gs.remove()
-        ms_local, _ = timed(lambda i: model.training_step(batch, i))
+        ms_local, _ = timed(eager(model))
     del model
-    model = build()
-    graphed = GraphedTrainStep(model, batch)
-    ms_graph, _ = timed(lambda i: graphed(batch))
-    sync_graph = checksum(model)
     pps = lambda ms: world * TRAIN_BATCH / ms * 1e3  # noqa: E731
-    gf = gf_per_patch("train", 12, 256)
-    out = {"workload": CONFIGS[3]["workload"],
+    gf = statistics.mean(gf_per_patch("train", len(WAVELENGTHS[m]), 256) for m in mods)
+    out = {"workload": CONFIGS[3 if len(mods) == 1 else 4]["workload"],
            "patches_per_s": pps(ms_eager), "ms_per_step": ms_eager, "tensor_tflops": pps(ms_eager) * gf / 1000.0,
-           "graphed_patches_per_s": pps(ms_graph), "graphed_ms_per_step": ms_graph,
-           "graphed_tensor_tflops": pps(ms_graph) * gf / 1000.0, "loss_after_8_steps": loss, "steps": steps}
+           "loss_after_8_steps": loss, "steps": steps}
+    sync_graph = True
+    if graphed:
+        model = build()
+        graph_step = GraphedTrainStep(model, batch)
+        ms_graph, _ = timed(lambda i: graph_step(batch))
+        sync_graph = checksum(model)
+        out.update({"graphed_patches_per_s": pps(ms_graph), "graphed_ms_per_step": ms_graph,
+                    "graphed_tensor_tflops": pps(ms_graph) * gf / 1000.0})
+        del model, graph_step
     if world > 1:
         out.update({"ms_per_step_without_exchange": ms_local, "exposed_exchange_ms": ms_eager - ms_local,
-                    "scaling_eff": ms_local / ms_eager, "graphed_scaling_eff": ms_local / ms_graph if ms_graph > ms_local else 1.0,
-                    "replicas_in_sync": bool(sync_eager and sync_graph)})
+                    "scaling_eff": min(1.0, ms_local / ms_eager), "replicas_in_sync": bool(sync_eager and sync_graph)})
+        if graphed:
+            out["graphed_scaling_eff"] = min(1.0, ms_local / ms_graph)
+    torch.cuda.empty_cache()
     return out
 
 

@@ -252,6 +252,39 @@ class _DynamicBase(nn.Module):
         return ops.hypernet_backward(wvs.to(device=dev, dtype=torch.float32), params, g.num_layers, g.input_dim, g.num_heads,
                                      g.ff_dim, self.embed_dim, self._decoder, dw_oihw, self.scaler, dbias, bias_scale, tape)
 
+    # -- eval-mode operand cache ---------------------------------------------------------------------------------
+    # The generated kernel is a function of (wavelengths, hypernetwork parameters) only - not of the batch (SURVEY App. B
+    # item 8) - so outside training the packed conv operand is kept per wavelength vector and rebuilt when any parameter
+    # of the hypernetwork changes (autograd version counters; optimiser steps and load_state_dict advance them).
+    CACHE_EVAL_OPERANDS = True
+
+    def _wvs_key(self, wvs: Tensor):
+        if wvs.is_cuda:   # no device read: identity of the tensor (pointer + version + length)
+            return ('cuda', wvs.data_ptr(), wvs._version, wvs.numel(), str(wvs.dtype))
+        return ('cpu',) + tuple(float(v) for v in wvs.reshape(-1).tolist())
+
+    def _eval_operands(self, wvs: Tensor, dtype, bias_scale: float):
+        """-> (packed igemm B operand, scaled bias, (wk, bias_raw)) for the non-taped forward."""
+        c = wvs.numel()
+        if not self.CACHE_EVAL_OPERANDS:
+            wk, b_raw = self._generate(wvs)
+            packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, self.embed_dim, self._decoder, self.scaler, bias_scale, dtype, False)
+            return packed, bias, (wk, b_raw)
+        params = list(self.weight_generator.parameters()) + list(self.fclayer.parameters())
+        key = (self._wvs_key(wvs), dtype, float(bias_scale), float(self.scaler),
+               tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        cache = self.__dict__.setdefault('_operand_cache', {})
+        hit = cache.get(key[0])
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        wk, b_raw = self._generate(wvs)
+        packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, self.embed_dim, self._decoder, self.scaler, bias_scale, dtype, False)
+        if len(cache) >= 16:
+            cache.clear()
+        # a CUDA wavelength tensor is identified by pointer: keep it alive so the address cannot be recycled
+        cache[key[0]] = (key, (packed, bias, (wk, b_raw)), wvs)
+        return packed, bias, (wk, b_raw)
+
     def _get_weights(self, waves: Tensor):
         raise NotImplementedError('the CUDA path generates weights from wavelengths directly; use _generate(wvs)')
 
@@ -279,8 +312,7 @@ class DynamicConv(_DynamicBase):
         if tape.grad_mode():
             x = ops.nchw_to_act(img_feat, ops.dyn_cin_pad(c), dt)
             return tape.DynConvInFn.apply(x, self, wvs, *self.weight_generator.parameter_list(self.fclayer))
-        wk, b_raw = self._generate(wvs)
-        packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, self.embed_dim, False, self.scaler, self.scaler, dt, False)
+        packed, bias, _ = self._eval_operands(wvs, dt, self.scaler)
         x = ops.nchw_to_act(img_feat, ops.dyn_cin_pad(c), dt)
         return ops.conv2d(x, packed, bias, self.embed_dim, ops.CONV_3X3, algo_cin=c, gn_groups=32, gn_eps=1e-6)
 
@@ -324,8 +356,6 @@ class DynamicConv_decoder(_DynamicBase):
         x = ops.to_act(img_feat, compute_dtype())
         if tape.grad_mode():
             return tape.DynConvOutFn.apply(x, self, waves, *self.weight_generator.parameter_list(self.fclayer))
-        wk, b_raw = self._generate(waves)
-        packed, bias, _ = ops.pack_dyn_weight(wk, b_raw, c, self.embed_dim, True, self.scaler,
-                                              self.scaler * self.scaler, x.dtype, False)
+        packed, bias, (wk, b_raw) = self._eval_operands(waves, x.dtype, self.scaler * self.scaler)
         self._last = (wk, b_raw, c)
         return ops.conv2d(x, packed, bias, c, ops.CONV_3X3, out_dtype=torch.float32)

@@ -173,3 +173,32 @@ def test_forward_like_reference_test(cuda, modality, size, batch):
     e = _rel(recon.cpu(), ref)
     print(f"PARITY forward {modality} {size}px default numerics: recon {e:.3e}")
     assert e < BOUNDS[DEFAULT][1]
+
+
+def test_eval_operand_cache_follows_parameters_and_wavelengths(cuda):
+    """The generated dynamic-conv operands are cached per wavelength vector in eval (they do not depend on the batch); the
+    cache must follow in-place parameter updates (optimiser steps), new wavelength vectors and the numeric mode."""
+    import eo_vae
+    gold, model, x, wvs = _setup("tiny_s2l2a", cuda)
+    with torch.no_grad():
+        z0 = model.encode_spatial_normalized(x, wvs).clone()
+        assert torch.equal(model.encode_spatial_normalized(x, wvs), z0)            # served from the cache: identical bits
+        cache = model.encoder.conv_in._operand_cache
+        assert len(cache) == 1
+        p = model.encoder.conv_in.weight_generator.fc_weight.weight
+        p.mul_(1.5)                                                                 # what an optimiser step does: in place
+        z1 = model.encode_spatial_normalized(x, wvs).clone()
+        assert not torch.equal(z1, z0)
+        model.encoder.conv_in.CACHE_EVAL_OPERANDS = False
+        assert torch.equal(model.encode_spatial_normalized(x, wvs), z1)            # == a fresh generation
+        model.encoder.conv_in.CACHE_EVAL_OPERANDS = True
+        wvs2 = (wvs * 1.01).clone()                                                 # another wavelength vector
+        z2 = model.encode_spatial_normalized(x, wvs2)
+        assert not torch.equal(z2, z1) and len(cache) == 2
+        wvs2.copy_(wvs)                                                             # same tensor, new contents
+        assert torch.equal(model.encode_spatial_normalized(x, wvs2), z1)
+        r_cpu_wvs = model.reconstruct(x, wvs.cpu().to(cuda))                        # a fresh tensor with equal values
+        assert torch.equal(r_cpu_wvs, model.reconstruct(x, wvs))
+        eo_vae.set_compute_dtype(torch.bfloat16)
+        zb = model.encode_spatial_normalized(x, wvs)
+        assert not torch.equal(zb, z1)

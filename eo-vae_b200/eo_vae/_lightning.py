@@ -41,11 +41,11 @@ except Exception:  # noqa: BLE001
             self.logged: dict = {}
             self._grad_sync = None
 
-        def enable_ddp(self, bucket_bytes: int = 64 << 20) -> None:
+        def enable_ddp(self, bucket_bytes: int = 64 << 20, tail_bytes: int = 24 << 20) -> None:
             """Stand-in for Trainer(strategy='ddp'): average the gradients over the default process group inside
             ``manual_backward`` (bucketed NCCL all-reduce overlapped with backward, eo_vae/ddp.py)."""
             from .ddp import GradSync
-            self._grad_sync = GradSync(self.parameters(), bucket_bytes)
+            self._grad_sync = GradSync(self.parameters(), bucket_bytes, tail_bytes=tail_bytes)
 
         def attach_optimizers(self) -> None:
             """Stand-in for Trainer wiring: calls ``configure_optimizers`` once and stores the result."""

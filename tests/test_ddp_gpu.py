@@ -57,7 +57,7 @@ def _worker(rank, world, port, out_dir):
         want = gs if want is None else [a + b for a, b in zip(want, gs)]
     want = [w / world for w in want]
     model.bn.load_state_dict(bn0)
-    model.enable_ddp(bucket_bytes=1 << 16)     # several buckets on the tiny model
+    model.enable_ddp(bucket_bytes=1 << 16, tail_bytes=1 << 14)     # several buckets on the tiny model
     got = _grads(model, shards[rank], wvs, 1000 + rank)
     num = torch.sqrt(sum(((a - b) ** 2).sum() for a, b in zip(got, want)))
     den = torch.sqrt(sum((b ** 2).sum() for b in want))

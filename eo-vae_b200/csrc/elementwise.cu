@@ -91,13 +91,15 @@ __global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------- GN apply
-template <typename TI, typename TO, bool SILU>
-__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const TI* __restrict__ x, long long x_pix_stride,
-                                                              const float* __restrict__ stats,
-                                                              const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, TO* __restrict__ y,
-                                                              long long y_pix_stride, long long hw, int c, int groups,
-                                                              int pix_per_block) {
+// UNROLL = independent 16-byte loads in flight per thread.  Two launch shapes: 256 threads x 4 loads when the kernel has the
+// SMs to itself, and the "co-resident" shape 128 threads x 8 loads at <= 80 registers (10 K registers per CTA) that fits
+// beside a resident 320-thread x 168-register implicit-GEMM CTA, so that this HBM-bound pass of one half of a batch can run
+// UNDER the tensor-bound convolution of the other half (dual-stream encode, eo_vae/models/new_autoencoder.py).
+template <typename TI, typename TO, bool SILU, int UNROLL>
+__device__ __forceinline__ void gn_apply_body(const TI* __restrict__ x, long long x_pix_stride,
+                                              const float* __restrict__ stats, const float* __restrict__ gamma,
+                                              const float* __restrict__ beta, TO* __restrict__ y, long long y_pix_stride,
+                                              long long hw, int c, int groups, int pix_per_block) {
   const int vpp = c >> 3;
   const int rows = blockDim.x / vpp;
   const int v = threadIdx.x % vpp;
@@ -120,8 +122,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const TI* __restri
   if (p1 > hw) p1 = hw;
   const TI* xb = x + (static_cast<long long>(n) * hw) * x_pix_stride + v * 8;
   TO* yb = y + (static_cast<long long>(n) * hw) * y_pix_stride + v * 8;
-  // four independent 16-byte loads in flight per thread (the kernel is pure HBM streaming: 1 read + 1 write)
-  constexpr int UNROLL = 4;
+  // UNROLL independent 16-byte loads in flight per thread (the kernel is pure HBM streaming: 1 read + 1 write)
   for (long long p = p0 + r; p < p1; p += static_cast<long long>(rows) * UNROLL) {
     uint4 u[UNROLL];
 #pragma unroll
@@ -150,6 +151,30 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const TI* __restri
     }
   }
 }
+
+template <typename TI, typename TO, bool SILU>
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const TI* __restrict__ x, long long x_pix_stride,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, TO* __restrict__ y,
+                                                              long long y_pix_stride, long long hw, int c, int groups,
+                                                              int pix_per_block) {
+  gn_apply_body<TI, TO, SILU, 4>(x, x_pix_stride, stats, gamma, beta, y, y_pix_stride, hw, c, groups, pix_per_block);
+}
+
+// co-resident launch shape: the same body at 128 threads x 8 loads, registers capped so that one CTA fits in the ~11.7 K
+// registers a resident implicit-GEMM CTA leaves free on the SM
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(128, 6) gn_apply_co_kernel(const T* __restrict__ x, long long x_pix_stride,
+                                                                           const float* __restrict__ stats,
+                                                                           const float* __restrict__ gamma,
+                                                                           const float* __restrict__ beta, T* __restrict__ y,
+                                                                           long long y_pix_stride, long long hw, int c,
+                                                                           int groups, int pix_per_block) {
+  gn_apply_body<T, T, SILU, 8>(x, x_pix_stride, stats, gamma, beta, y, y_pix_stride, hw, c, groups, pix_per_block);
+}
+
+int g_gn_apply_coresident = 0;  // eovae_set_tuning(EOVAE_TUNE_GN_APPLY_CORESIDENT, 1)
 
 int gn_block_threads(int c) {
   const int vpp = c / 8;
@@ -597,6 +622,10 @@ int eovae_gn_stats(const void* x, int x_dtype, int n, long long hw, int c, long 
   return 0;
 }
 
+void eovae_set_tuning(int key, int value) {
+  if (key == EOVAE_TUNE_GN_APPLY_CORESIDENT) g_gn_apply_coresident = value;
+}
+
 int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const float* stats, const float* gamma,
                    const float* beta, void* y, int y_dtype, long long y_pix_stride, int n, long long hw, int c, int groups,
                    int apply_silu, void* stream_) {
@@ -616,6 +645,34 @@ int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const flo
   int bpi, ppb;
   gn_grid(n, hw, c, threads / (c / 8), &bpi, &ppb);
   dim3 grid(bpi, n);
+  if (g_gn_apply_coresident && x_dtype == y_dtype && c <= 1024) {
+    // co-resident launch shape (see the kernel comment): 128 threads, 8 loads in flight, capped registers
+    const int vpp = c / 8;
+    const int thr = (128 / vpp) * vpp;
+    if (thr >= vpp && thr > 0) {
+      gn_grid(n, hw, c, thr / vpp, &bpi, &ppb);
+      dim3 g2(bpi, n);
+      // An SM runs CTAs of two kernels side by side only under ONE L1 / shared-memory split.  The implicit GEMM needs the
+      // maximum shared-memory carve-out, so this kernel asks for the same split (it uses no shared memory and streams
+      // through L2; the smaller L1 costs it nothing) - with the default preference the SM would have to drain first.
+#define EOVAE_GN_APPLY_CO(T, S)                                                                                     \
+  do {                                                                                                              \
+    static bool carve_set = false;                                                                                  \
+    if (!carve_set) {                                                                                               \
+      EOVAE_CUDA(cudaFuncSetAttribute(gn_apply_co_kernel<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout,     \
+                                      cudaSharedmemCarveoutMaxShared));                                             \
+      carve_set = true;                                                                                             \
+    }                                                                                                               \
+    gn_apply_co_kernel<T, S><<<g2, thr, 0, stream>>>(static_cast<const T*>(x), x_pix_stride, stats, gamma, beta,    \
+                                                     static_cast<T*>(y), y_pix_stride, hw, c, groups, ppb);         \
+  } while (0)
+      if (x_dtype == EOVAE_BF16) { if (apply_silu) EOVAE_GN_APPLY_CO(__nv_bfloat16, true); else EOVAE_GN_APPLY_CO(__nv_bfloat16, false); }
+      else { if (apply_silu) EOVAE_GN_APPLY_CO(__half, true); else EOVAE_GN_APPLY_CO(__half, false); }
+#undef EOVAE_GN_APPLY_CO
+      EOVAE_LAUNCH_CHECK();
+      return 0;
+    }
+  }
 #define EOVAE_GN_APPLY(TI, TO, S)                                                                                        \
   gn_apply_kernel<TI, TO, S><<<grid, threads, 0, stream>>>(static_cast<const TI*>(x), x_pix_stride, stats, gamma, beta, \
                                                            static_cast<TO*>(y), y_pix_stride, hw, c, groups, ppb)

@@ -23,6 +23,7 @@ SIGNATURES = {
     "eovae_num_sms": (_i, []),
     "eovae_launch_count": (C.c_ulonglong, []),
     "eovae_set_debug_mode": (None, [_i]),
+    "eovae_set_tuning": (None, [_i, _i]),
     "eovae_conv_chunk_bytes": (_i, [_i]),
     "eovae_conv_k_per_tap": (_i, [_i]),
     "eovae_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

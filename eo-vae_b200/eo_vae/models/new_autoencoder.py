@@ -309,12 +309,47 @@ class EOFluxVAE(LightningModule):
             z_normalized = self.noising(z_normalized)
         return self.decode(z_normalized, wvs), posterior
 
+    # Dual-stream encode (OPT-IN, off by default): patches are independent (GroupNorm, attention and the eval-mode latent
+    # BatchNorm are per sample), so a batch can be encoded as two halves on two CUDA streams, the idea being that the
+    # HBM-bound passes of one half (GroupNorm apply) run UNDER the tensor-bound implicit GEMMs of the other half.  Built,
+    # bit-identical, and measured to gain nothing on B200 (3033 vs 3059 patches/s): a GroupNorm-apply CTA does co-reside
+    # with a resident implicit-GEMM CTA (128 threads x 80 registers, max-shared carve-out), but the pair takes exactly the
+    # SUM of the two kernels' times - the N = 128 convolutions already move ~7 TB/s from L2 into shared memory, and the
+    # streaming pass competes for that same fabric (tools/overlap_probe.py, profiles/r2_dual_stream_experiment.md).
+    DUAL_STREAM_MIN_BATCH = int(os.environ.get('EOVAE_DUAL_STREAM_MIN_BATCH', '0'))   # 0 = off; e.g. 8 to enable
+
+    def _side_stream(self, dev) -> 'torch.cuda.Stream':
+        streams = self.__dict__.setdefault('_side_streams', {})
+        if dev not in streams:
+            streams[dev] = torch.cuda.Stream(dev)
+        return streams[dev]
+
     @torch.no_grad()
     def encode_spatial_normalized(self, x: Tensor, wvs: Tensor) -> Tensor:
         """[B, C, H, W] -> spatial normalised latent [B, z, H/8, W/8] (reference :480-502) in one fused tail."""
         self.bn.eval()
-        return ops.latent_norm(self._moments(x, wvs), self.bn.running_mean, self.bn.running_var, self.bn.eps,
-                               self.encoder.z_channels)
+        b = x.shape[0]
+        if (not x.is_cuda or b < self.DUAL_STREAM_MIN_BATCH or not self.DUAL_STREAM_MIN_BATCH
+                or torch.cuda.is_current_stream_capturing()):
+            return ops.latent_norm(self._moments(x, wvs), self.bn.running_mean, self.bn.running_var, self.bn.eps,
+                                   self.encoder.z_channels)
+        dev = x.device
+        f = 2 ** (self.encoder.num_resolutions - 1)
+        z = torch.empty((b, self.encoder.z_channels, x.shape[2] // f, x.shape[3] // f), dtype=torch.float32, device=dev)
+        half = b // 2
+        main, side = torch.cuda.current_stream(dev), self._side_stream(dev)
+        ops.set_tuning(ops.TUNE_GN_APPLY_CORESIDENT, 1)
+        try:
+            side.wait_stream(main)                      # x, wvs, the parameters and z's allocation are ready
+            with torch.cuda.stream(side):
+                ops.latent_norm(self._moments(x[half:], wvs), self.bn.running_mean, self.bn.running_var, self.bn.eps,
+                                self.encoder.z_channels, out=z[half:])
+            ops.latent_norm(self._moments(x[:half], wvs), self.bn.running_mean, self.bn.running_var, self.bn.eps,
+                            self.encoder.z_channels, out=z[:half])
+            main.wait_stream(side)
+        finally:
+            ops.set_tuning(ops.TUNE_GN_APPLY_CORESIDENT, 0)
+        return z
 
     @torch.no_grad()
     def decode_spatial_normalized(self, z: Tensor, wvs: Tensor) -> Tensor:

@@ -31,6 +31,14 @@ def _timed(family: str, flops: float, call):
     return rc
 
 
+def set_tuning(key: int, value: int) -> None:
+    """Launch-shape knobs of the library (include/eovae.h EOVAE_TUNE_*); results never depend on them."""
+    _C.lib().eovae_set_tuning(int(key), int(value))
+
+
+TUNE_GN_APPLY_CORESIDENT = 1
+
+
 def launch_count() -> int:
     """Kernels launched so far by libeovae_sm100.so in this process."""
     return int(_C.lib().eovae_launch_count())
@@ -333,13 +341,16 @@ def _strides4(t: torch.Tensor):
     return (ctypes.c_longlong * 4)(*t.stride())
 
 
-def latent_norm(moments: torch.Tensor, running_mean, running_var, eps: float, zc: int) -> torch.Tensor:
-    """moments: fp32 logical [N, 2zc, H, W] (any strides) -> normalised spatial latent NCHW fp32 [N, zc, H, W]."""
+def latent_norm(moments: torch.Tensor, running_mean, running_var, eps: float, zc: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """moments: fp32 logical [N, 2zc, H, W] (any strides) -> normalised spatial latent NCHW fp32 [N, zc, H, W] (``out``: a
+    contiguous destination, e.g. a batch slice of a larger latent tensor)."""
     _need_cuda(moments, running_mean, running_var)
     n, c2, h, w = moments.shape
     if moments.dtype != torch.float32 or c2 != 2 * zc:
         raise RuntimeError("eo_vae.latent_norm: bad moments tensor")
-    z = torch.empty((n, zc, h, w), dtype=torch.float32, device=moments.device)
+    z = out if out is not None else torch.empty((n, zc, h, w), dtype=torch.float32, device=moments.device)
+    if tuple(z.shape) != (n, zc, h, w) or z.dtype != torch.float32 or not z.is_contiguous():
+        raise RuntimeError("eo_vae.latent_norm: bad output tensor")
     rc = _C.lib().eovae_latent_norm(_ptr(moments), _strides4(moments), _ptr(running_mean), _ptr(running_var), float(eps),
                                    _ptr(z), n, h, w, zc, _stream())
     _C.check(rc, "eovae_latent_norm")

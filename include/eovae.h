@@ -47,6 +47,11 @@ unsigned long long eovae_launch_count(void);
  * (cta_group::2) implicit GEMM; bit 10: force one K-chunk per stage; bit 11: per-thread stores instead of the TMA-store epilogue (tests run all).
  * The product path never sets it.                         */
 void eovae_set_debug_mode(int mode);
+/* launch-shape knobs (process-wide; results never depend on them).  EOVAE_TUNE_GN_APPLY_CORESIDENT = 1: eovae_gn_apply
+ * launches 128-thread CTAs with 8 loads in flight and <= 80 registers, a shape that fits on an SM beside a resident
+ * implicit-GEMM CTA, so that the pass overlaps a convolution running on another stream (the dual-stream encode). */
+#define EOVAE_TUNE_GN_APPLY_CORESIDENT 1
+void eovae_set_tuning(int key, int value);
 
 /* ---- weight packing (derived, non-persistent caches of the OIHW fp32 master parameters) -------------------- */
 /* channels per K-chunk (in bytes: 32/64/128) and padded channels per tap chosen for a given Cin */

@@ -202,3 +202,19 @@ def test_eval_operand_cache_follows_parameters_and_wavelengths(cuda):
         eo_vae.set_compute_dtype(torch.bfloat16)
         zb = model.encode_spatial_normalized(x, wvs)
         assert not torch.equal(zb, z1)
+
+
+def test_dual_stream_encode_is_bit_identical(cuda):
+    """Opt-in dual-stream encode (two halves of the batch on two streams): the latents must not depend on it."""
+    import __graft_entry__ as g
+    from oracle.weights import FULL_CONFIG, WAVELENGTHS, make_state_dict, synthetic_patches
+    model = g._model(FULL_CONFIG, make_state_dict(FULL_CONFIG, 0), cuda)
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"]).to(cuda)
+    x = synthetic_patches(9, 12, 128, seed=17).to(cuda)      # odd batch: halves of 4 and 5
+    with torch.no_grad():
+        model.DUAL_STREAM_MIN_BATCH = 8
+        z2 = model.encode_spatial_normalized(x, wvs)
+        z2b = model.encode_spatial_normalized(x, wvs)
+        model.DUAL_STREAM_MIN_BATCH = 0
+        z1 = model.encode_spatial_normalized(x, wvs)
+    assert torch.equal(z2, z1) and torch.equal(z2b, z1)

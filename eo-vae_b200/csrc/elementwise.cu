@@ -645,7 +645,10 @@ int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const flo
   int bpi, ppb;
   gn_grid(n, hw, c, threads / (c / 8), &bpi, &ppb);
   dim3 grid(bpi, n);
-  if (g_gn_apply_coresident && x_dtype == y_dtype && c <= 1024) {
+  // 128 threads x 8 loads in flight measures 5.66 vs 5.28 TB/s on the large tensors (tools/gn_apply_shapes.py) and loses on
+  // the small ones: taken from 32 M elements up, or always when the co-resident shape is requested
+  const bool big = static_cast<long long>(n) * hw * c >= (32LL << 20);
+  if ((g_gn_apply_coresident || big) && x_dtype == y_dtype && c <= 1024) {
     // co-resident launch shape (see the kernel comment): 128 threads, 8 loads in flight, capped registers
     const int vpp = c / 8;
     const int thr = (128 / vpp) * vpp;
@@ -657,11 +660,12 @@ int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const flo
       // through L2; the smaller L1 costs it nothing) - with the default preference the SM would have to drain first.
 #define EOVAE_GN_APPLY_CO(T, S)                                                                                     \
   do {                                                                                                              \
-    static bool carve_set = false;                                                                                  \
-    if (!carve_set) {                                                                                               \
-      EOVAE_CUDA(cudaFuncSetAttribute(gn_apply_co_kernel<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout,     \
-                                      cudaSharedmemCarveoutMaxShared));                                             \
-      carve_set = true;                                                                                             \
+    static int carve_set = -2;                                                                                      \
+    const int carve = g_gn_apply_coresident == 1 ? static_cast<int>(cudaSharedmemCarveoutMaxShared)                 \
+                                                 : static_cast<int>(cudaSharedmemCarveoutDefault);                  \
+    if (carve_set != carve) {                                                                                       \
+      EOVAE_CUDA(cudaFuncSetAttribute(gn_apply_co_kernel<T, S>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)); \
+      carve_set = carve;                                                                                            \
     }                                                                                                               \
     gn_apply_co_kernel<T, S><<<g2, thr, 0, stream>>>(static_cast<const T*>(x), x_pix_stride, stats, gamma, beta,    \
                                                      static_cast<T*>(y), y_pix_stride, hw, c, groups, ppb);         \

@@ -122,17 +122,19 @@ int pick_block_n(int cout_pad) {
 // stats[n][g] = (mean, rstd) from the per-tile partial sums written by the igemm epilogue; one warp per (n, g),
 // fixed summation order (deterministic).
 __global__ void gn_tiles_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int pairs, int groups,
-                                         int slots_per_img, double count, float eps) {
+                                         int slots_per_img, double count, float eps, int regions, long long region_stride) {
   const int pair = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pair >= pairs) return;
   const int n = pair / groups, g = pair % groups;
-  const float* base = partial + (static_cast<long long>(n) * slots_per_img * groups + g) * 2;
   double s = 0.0, q = 0.0;
-  for (int t = lane; t < slots_per_img; t += 32) {
-    const float2 v = *reinterpret_cast<const float2*>(base + static_cast<long long>(t) * groups * 2);
-    s += v.x;
-    q += v.y;
+  for (int r = 0; r < regions; ++r) {  // one region per sub-pixel phase (1 for an ordinary convolution)
+    const float* base = partial + r * region_stride + (static_cast<long long>(n) * slots_per_img * groups + g) * 2;
+    for (int t = lane; t < slots_per_img; t += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(base + static_cast<long long>(t) * groups * 2);
+      s += v.x;
+      q += v.y;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -170,6 +172,21 @@ struct GnPrologue {  // GroupNorm(+SiLU) of the conv INPUT, applied inside the m
   void* workspace;  // >= N * Cin * 8 bytes
 };
 
+// Custom tap geometry (mode = EOVAE_CONV_CUSTOM): the two sub-pixel forms of the nearest-x2 upsample convolution.
+//  * phases = 4, parity_in = false: FORWARD.  Four 2x2 convolutions on the low-resolution input; phase q = (py, px) writes
+//    out[:, py::2, px::2, :] of the high-resolution output (out_h2 x out_w2) and uses weight rows [q * rows_pad, ...).
+//  * phases = 1, parity_in = true : DATA GRADIENT.  16 taps, tap t reads the parity sub-lattice tap_map[t] of the
+//    high-resolution gradient (the tensor given as the A operand, extent 2H x 2W) at offset (tap_dx, tap_dy); output low-res.
+struct TapSpec {
+  int num_taps;
+  int tap_map[igemm::MAX_TAPS], tap_dx[igemm::MAX_TAPS], tap_dy[igemm::MAX_TAPS];
+  bool parity_in;
+  int phases;
+  int phase_dx[4], phase_dy[4];
+  int b_phase_rows;
+};
+constexpr int EOVAE_CONV_CUSTOM = 99;
+
 struct ASpec {       // activation-side operand: NHWC tensor view
   const void* ptr;
   int N, H, W, C;    // logical extent (C = channels visible to the contraction)
@@ -181,7 +198,7 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
                  long long res_pix_stride, void* out, int out_dtype, long long out_pix_stride, int act_dtype,
                  float scale, cudaStream_t stream, float* gn_stats = nullptr, int gn_groups = 0, float gn_eps = 0.f,
                  void* gn_ws = nullptr, size_t gn_ws_bytes = 0, const ASpec* extra = nullptr,
-                 const GnPrologue* gnp = nullptr, int w_dtype = -1) {
+                 const GnPrologue* gnp = nullptr, int w_dtype = -1, const TapSpec* taps = nullptr) {
   if (w_dtype < 0) w_dtype = act_dtype;
   EOVAE_CHECK((act_dtype == EOVAE_BF16 || act_dtype == EOVAE_F16) && (w_dtype == EOVAE_BF16 || w_dtype == EOVAE_F16),
               "igemm: operand dtypes must be bf16/f16");
@@ -200,12 +217,29 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
               "igemm: residual pixel stride (%lld) / base not 16-byte aligned", res_pix_stride);
   igemm::Params p;
   memset(&p, 0, sizeof(p));
+  p.phases = 1;
   const int ch = chunk_bytes / 2;
   int Ho = a.H, Wo = a.W;
   p.num_taps = (mode == EOVAE_CONV_1X1) ? 1 : 9;
   if (mode == EOVAE_CONV_3X3_S2) {
     Ho = (a.H - 2) / 2 + 1;  // pad (0,1,0,1) then 3x3 stride 2, pad 0
     Wo = (a.W - 2) / 2 + 1;
+  }
+  if (mode == EOVAE_CONV_CUSTOM) {
+    EOVAE_CHECK(taps != nullptr && taps->num_taps >= 1 && taps->num_taps <= igemm::MAX_TAPS && extra == nullptr && gnp == nullptr,
+                "igemm: bad custom tap geometry");
+    p.num_taps = taps->num_taps;
+    if (taps->parity_in) {   // A = high-resolution tensor read through its four parity sub-lattices; output = low resolution
+      EOVAE_CHECK(a.H % 2 == 0 && a.W % 2 == 0, "igemm: parity sub-lattices need even extents");
+      Ho = a.H / 2;
+      Wo = a.W / 2;
+    }
+    p.phases = taps->phases;
+    p.b_phase_rows = taps->b_phase_rows;
+    for (int q = 0; q < taps->phases; ++q) {
+      p.phase_dx[q] = taps->phase_dx[q];
+      p.phase_dy[q] = taps->phase_dy[q];
+    }
   }
   // --- M tile = one TMA box of pixels
   m_tiling(a.N, Ho, Wo, w_batches > 1, &p.box_w, &p.box_h, &p.box_n);
@@ -256,7 +290,7 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   const uint32_t box[4] = {static_cast<uint32_t>(ch), static_cast<uint32_t>(p.box_w), static_cast<uint32_t>(p.box_h),
                            static_cast<uint32_t>(p.box_n)};
   const uint64_t es = 2;
-  if (mode == EOVAE_CONV_3X3_S2) {
+  if (mode == EOVAE_CONV_3X3_S2 || (mode == EOVAE_CONV_CUSTOM && taps->parity_in)) {
     // four parity sub-lattices x[:, ph::2, pw::2, :]; tap (kh,kw) -> lattice (kh&1, kw&1), offset (kh>>1, kw>>1)
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) {
@@ -269,12 +303,20 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
         int rc = encode_map(&p.a_map[ph * 2 + pw], act_dtype, 4, base, dims, strides, box, chunk_bytes);
         if (rc) return rc;
       }
-    for (int kh = 0; kh < 3; ++kh)
-      for (int kw = 0; kw < 3; ++kw) {
-        p.tap_map[kh * 3 + kw] = (kh & 1) * 2 + (kw & 1);
-        p.tap_dy[kh * 3 + kw] = kh >> 1;
-        p.tap_dx[kh * 3 + kw] = kw >> 1;
+    if (mode == EOVAE_CONV_CUSTOM) {
+      for (int t = 0; t < p.num_taps; ++t) {
+        p.tap_map[t] = taps->tap_map[t];
+        p.tap_dy[t] = taps->tap_dy[t];
+        p.tap_dx[t] = taps->tap_dx[t];
       }
+    } else {
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          p.tap_map[kh * 3 + kw] = (kh & 1) * 2 + (kw & 1);
+          p.tap_dy[kh * 3 + kw] = kh >> 1;
+          p.tap_dx[kh * 3 + kw] = kw >> 1;
+        }
+    }
   } else {
     uint64_t dims[4] = {static_cast<uint64_t>(a.C), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
                         static_cast<uint64_t>(a.N)};
@@ -294,8 +336,13 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     }
     for (int t = 0; t < p.num_taps; ++t) {
       p.tap_map[t] = 0;
-      p.tap_dy[t] = (mode == EOVAE_CONV_1X1) ? 0 : t / 3 - 1;
-      p.tap_dx[t] = (mode == EOVAE_CONV_1X1) ? 0 : t % 3 - 1;
+      if (mode == EOVAE_CONV_CUSTOM) {
+        p.tap_dy[t] = taps->tap_dy[t];
+        p.tap_dx[t] = taps->tap_dx[t];
+      } else {
+        p.tap_dy[t] = (mode == EOVAE_CONV_1X1) ? 0 : t / 3 - 1;
+        p.tap_dx[t] = (mode == EOVAE_CONV_1X1) ? 0 : t % 3 - 1;
+      }
     }
   }
   // --- B map: [batch][rows][K] K-major
@@ -326,23 +373,39 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     if (sw > 0) {
       uint64_t odims[4] = {static_cast<uint64_t>(cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
                            static_cast<uint64_t>(a.N)};
-      uint64_t ostr[3] = {static_cast<uint64_t>(out_pix_stride) * es, static_cast<uint64_t>(Wo) * out_pix_stride * es,
-                          static_cast<uint64_t>(Ho) * Wo * out_pix_stride * es};
       const uint32_t obox[4] = {32u, static_cast<uint32_t>(sw), static_cast<uint32_t>(sh), static_cast<uint32_t>(sn)};
-      int rc0 = encode_map(&p.out_map, out_dtype, 4, out, odims, ostr, obox, 64, false);
-      if (rc0) return rc0;
+      if (p.phases == 1) {
+        uint64_t ostr[3] = {static_cast<uint64_t>(out_pix_stride) * es, static_cast<uint64_t>(Wo) * out_pix_stride * es,
+                            static_cast<uint64_t>(Ho) * Wo * out_pix_stride * es};
+        int rc0 = encode_map(&p.out_map, out_dtype, 4, out, odims, ostr, obox, 64, false);
+        if (rc0) return rc0;
+      } else {
+        // phase (py, px) stores the parity sub-lattice out[:, py::2, px::2, :] of the (2 Ho) x (2 Wo) output
+        const uint64_t W2 = 2ull * Wo, H2 = 2ull * Ho;
+        uint64_t ostr[3] = {2ull * out_pix_stride * es, 2ull * W2 * out_pix_stride * es, H2 * W2 * out_pix_stride * es};
+        for (int q = 0; q < 4; ++q) {
+          uint8_t* base = reinterpret_cast<uint8_t*>(out) + (static_cast<uint64_t>(q >> 1) * W2 + (q & 1)) * out_pix_stride * es;
+          int rc0 = encode_map(q == 0 ? &p.out_map : &p.out_map_ph[q - 1], out_dtype, 4, base, odims, ostr, obox, 64, false);
+          if (rc0) return rc0;
+        }
+      }
       p.out_tma = 1;
     }
   }
-  const int total_tiles = ceil_div(m_tiles_total, ctas) * p.n_tiles;  // work items
+  EOVAE_CHECK(p.phases == 1 || (p.out_tma == 1 && res == nullptr && p.box_n == 1),
+              "igemm: the sub-pixel upsample convolution needs the TMA-store epilogue (16-bit output, Cout >= 32, whole warps "
+              "inside the pixel box), one image per tile and no residual");
+  const int total_tiles = ceil_div(m_tiles_total, ctas) * p.n_tiles * p.phases;  // work items
   if (total_tiles == 0) return 0;
   if (gn_stats != nullptr) {
     EOVAE_CHECK(p.box_n == 1 && cout % 32 == 0 && gn_groups > 0 && cout % gn_groups == 0 && 32 % (cout / gn_groups) == 0 &&
                     block_n >= 32,
                 "igemm: fused GroupNorm statistics unsupported for this shape (query eovae_conv2d_gn_workspace_bytes)");
-    const size_t need = sizeof(float) * 2 * 4 * static_cast<size_t>(p.tiles_w) * p.tiles_h * p.tiles_n * gn_groups;
+    const size_t region = 2 * 4 * static_cast<size_t>(p.tiles_w) * p.tiles_h * p.tiles_n * gn_groups;
+    const size_t need = sizeof(float) * region * p.phases;
     EOVAE_CHECK(gn_ws != nullptr && gn_ws_bytes >= need, "igemm: GroupNorm workspace too small");
     p.gn_partial = static_cast<float*>(gn_ws);
+    p.gn_phase_stride = static_cast<long long>(region);
     p.gn_groups = gn_groups;
     p.gn_cpg = cout / gn_groups;
   }
@@ -405,7 +468,8 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   const int pairs = p.Nimg * gn_groups;
   gn_tiles_finalize_kernel<<<ceil_div(pairs, 4), 128, 0, stream>>>(p.gn_partial, gn_stats, pairs, gn_groups,
                                                                    p.tiles_w * p.tiles_h * 4,
-                                                                   static_cast<double>(Ho) * Wo * p.gn_cpg, gn_eps);
+                                                                   static_cast<double>(Ho) * Wo * p.gn_cpg * p.phases, gn_eps,
+                                                                   p.phases, p.gn_phase_stride);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -533,6 +597,148 @@ int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride
   return launch_igemm(as, EOVAE_CONV_1X1, b, kpt, cb, n, n, ldb, b_batch_stride, batch == 1 ? 1 : batch, nullptr, nullptr, 0, 0, c,
                       c_dtype, ldc, a_dtype, scale, static_cast<cudaStream_t>(stream), nullptr, 0, 0.f, nullptr, 0, nullptr, nullptr,
                       b_dtype);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Upsample (layers.py:40-50: nearest x2, then 3x3 conv) in sub-pixel form.  Output pixel (2i + py, 2j + px) only sees the
+// low-resolution pixels (i + a - 1 + py, j + b - 1 + px), a, b in {0, 1}, through the SUMS of the 3x3 taps that fall on the
+// same source pixel:  rows  py = 0: a = 0 <- kh 0, a = 1 <- kh 1 + 2;   py = 1: a = 0 <- kh 0 + 1, a = 1 <- kh 2  (columns alike).
+// Four 2x2 convolutions on the low-resolution tensor replace one 3x3 convolution on the 4x larger one: 16 instead of 36
+// MACs per output pixel pair, and the upsampled tensor is never materialised.
+}  // extern "C"
+
+namespace {
+
+__device__ __forceinline__ bool up2x_in_set(int parity, int a, int k) {  // does 3x3 index k fold onto 2x2 index a?
+  return parity == 0 ? (a == 0 ? k == 0 : k >= 1) : (a == 0 ? k <= 1 : k == 2);
+}
+
+// forward operand: out[q][o][t][c] (q = py*2+px, t = a*2+b; rows padded to rows_pad, channels to kpt), fp32 sums rounded once
+template <typename T>
+__global__ void pack_up2x_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int rows_pad, int kpt,
+                                 long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % kpt);
+  long long r = i / kpt;
+  const int t = static_cast<int>(r % 4); r /= 4;
+  const int o = static_cast<int>(r % rows_pad);
+  const int q = static_cast<int>(r / rows_pad);
+  float v = 0.f;
+  if (o < cout && c < cin) {
+    const float* wp = w + (static_cast<long long>(o) * cin + c) * 9;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        if (up2x_in_set(q >> 1, t >> 1, kh) && up2x_in_set(q & 1, t & 1, kw)) v += wp[kh * 3 + kw];
+  }
+  out[i] = T16<T>::from_f(v);
+}
+
+// data-gradient operand: out[ci][q*4 + t][co] = W'_q[t][co][ci] (rows padded to round_up(cin, 16), co to kpt)
+template <typename T>
+__global__ void pack_up2x_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int kpt,
+                                       long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % kpt);
+  long long r = i / kpt;
+  const int tap = static_cast<int>(r % 16);
+  const int ci = static_cast<int>(r / 16);
+  const int q = tap >> 2, t = tap & 3;
+  float v = 0.f;
+  if (co < cout && ci < cin) {
+    const float* wp = w + (static_cast<long long>(co) * cin + ci) * 9;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        if (up2x_in_set(q >> 1, t >> 1, kh) && up2x_in_set(q & 1, t & 1, kw)) v += wp[kh * 3 + kw];
+  }
+  out[i] = T16<T>::from_f(v);
+}
+
+}  // namespace
+
+extern "C" {
+
+int eovae_conv2d_up2x_ok(int n, int h, int w, int cin, int cout) {
+  // what the phase epilogue needs (see launch_igemm): 128-byte K chunks, whole 32-pixel warps inside one image's tile
+  if (cin % 64 != 0 || cout % 32 != 0 || n < 1) return 0;
+  int bw, bh, bn;
+  m_tiling(n, h, w, false, &bw, &bh, &bn);
+  if (bn != 1 || (bw * bh) % 32 != 0) return 0;
+  if (bw >= 32) return bw % 32 == 0 ? 1 : 0;
+  return (32 % bw == 0 && bh % (32 / bw) == 0) ? 1 : 0;
+}
+
+size_t eovae_conv2d_up2x_gn_workspace_bytes(int n, int h, int w, int cout, int groups) {
+  return 4 * eovae_conv2d_gn_workspace_bytes(n, h, w, EOVAE_CONV_1X1, cout, groups);
+}
+
+int eovae_pack_conv_weight_up2x(const float* w_oihw, void* out, int cout, int cin, int dtype, int dgrad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "pack_conv_weight_up2x: 16-bit operands only");
+  if (!dgrad) {
+    const int kpt = eovae_conv_k_per_tap(cin), rows_pad = round_up(cout, 16);
+    const long long total = 4LL * rows_pad * 4 * kpt;
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+    if (dtype == EOVAE_BF16) pack_up2x_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, rows_pad, kpt, total);
+    else pack_up2x_kernel<__half><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, rows_pad, kpt, total);
+  } else {
+    const int kpt = eovae_conv_k_per_tap(round_up(cout, 8));
+    const long long total = static_cast<long long>(round_up(cin, 16)) * 16 * kpt;
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+    if (dtype == EOVAE_BF16) pack_up2x_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, kpt, total);
+    else pack_up2x_dgrad_kernel<__half><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, kpt, total);
+  }
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int eovae_conv2d_up2x(const void* x, int n, int h, int w, int cin, long long x_pix_stride, const void* w_packed, int cout,
+                      const float* bias, void* out, int out_dtype, long long out_pix_stride, int act_dtype, float* gn_stats,
+                      int gn_groups, float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, void* stream) {
+  EOVAE_CHECK(eovae_conv2d_up2x_ok(n, h, w, cin, cout), "conv2d_up2x: unsupported shape (query eovae_conv2d_up2x_ok)");
+  EOVAE_CHECK(out_dtype == EOVAE_BF16 || out_dtype == EOVAE_F16, "conv2d_up2x: 16-bit output only");
+  TapSpec ts;
+  memset(&ts, 0, sizeof(ts));
+  ts.num_taps = 4;
+  for (int t = 0; t < 4; ++t) {
+    ts.tap_dy[t] = (t >> 1) - 1;
+    ts.tap_dx[t] = (t & 1) - 1;
+  }
+  ts.parity_in = false;
+  ts.phases = 4;
+  for (int q = 0; q < 4; ++q) {
+    ts.phase_dy[q] = q >> 1;
+    ts.phase_dx[q] = q & 1;
+  }
+  ts.b_phase_rows = round_up(cout, 16);
+  ASpec a{x, n, h, w, cin, x_pix_stride};
+  const int kpt = eovae_conv_k_per_tap(cin);
+  return launch_igemm(a, EOVAE_CONV_CUSTOM, w_packed, kpt, eovae_conv_chunk_bytes(cin), cout, 4LL * round_up(cout, 16), 4LL * kpt, 0, 1,
+                      bias, nullptr, 0, 0, out, out_dtype, out_pix_stride, act_dtype, 1.0f, static_cast<cudaStream_t>(stream), gn_stats,
+                      gn_groups, gn_eps, gn_workspace, gn_workspace_bytes, nullptr, nullptr, -1, &ts);
+}
+
+int eovae_conv2d_up2x_dgrad(const void* dy, int n, int h2, int w2, int cout, long long dy_pix_stride, const void* w_packed, int cin,
+                            void* dx, int dx_dtype, long long dx_pix_stride, int act_dtype, void* stream) {
+  // dx [n][h2/2][w2/2][cin] = sum over the 4 parity sub-lattices of dy and their 2x2 taps (adjoint of eovae_conv2d_up2x)
+  EOVAE_CHECK(h2 % 2 == 0 && w2 % 2 == 0 && cout % 8 == 0, "conv2d_up2x_dgrad: even extents and Cout %% 8 required");
+  TapSpec ts;
+  memset(&ts, 0, sizeof(ts));
+  ts.num_taps = 16;
+  for (int q = 0; q < 4; ++q)
+    for (int t = 0; t < 4; ++t) {
+      ts.tap_map[q * 4 + t] = q;
+      ts.tap_dy[q * 4 + t] = -((t >> 1) - 1 + (q >> 1));
+      ts.tap_dx[q * 4 + t] = -((t & 1) - 1 + (q & 1));
+    }
+  ts.parity_in = true;
+  ts.phases = 1;
+  ASpec a{dy, n, h2, w2, cout, dy_pix_stride};
+  const int kpt = eovae_conv_k_per_tap(round_up(cout, 8));
+  return launch_igemm(a, EOVAE_CONV_CUSTOM, w_packed, kpt, eovae_conv_chunk_bytes(cout), cin, round_up(cin, 16), 16LL * kpt, 0, 1, nullptr,
+                      nullptr, 0, 0, dx, dx_dtype, dx_pix_stride, act_dtype, 1.0f, static_cast<cudaStream_t>(stream), nullptr, 0, 0.f,
+                      nullptr, 0, nullptr, nullptr, -1, &ts);
 }
 
 int eovae_gemm_strided_f32(const float* a, long long lda, long long a_batch_stride, const float* b, long long b_n_stride,

@@ -31,7 +31,7 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 // GroupNorm-prologue variant: 5 warpgroups = {TMA, MMA, 2 idle} | 4 + 4 epilogue warps | 4 + 4 transform warps
 constexpr int NUM_XF_WARPS = 8;
 constexpr int NUM_THREADS_GNP = 128 + 32 * NUM_EPI_WARPS + 32 * NUM_XF_WARPS;
-constexpr int MAX_TAPS = 9;
+constexpr int MAX_TAPS = 16;  // 9 for a 3x3 kernel; 16 = 4 sub-pixel phases x 2x2 taps (data gradient of the upsample conv)
 
 struct Params {
   CUtensorMap a_map[4];
@@ -69,6 +69,15 @@ struct Params {
   int gnp_bf16;                   // activation element type of the A operand
   CUtensorMap out_map;            // 16-bit output, box = (32 channels, the 32 pixels of one epilogue warp), 64 B swizzle
   int out_tma;                    // 1: epilogue stores through out_map (shared-memory staging + bulk tensor store)
+  // Sub-pixel phases (nearest-x2 upsample + 3x3 conv as four 2x2 convs on the LOW-resolution input, layers.py:47-50): the
+  // work item gains a phase index; phase q reads the taps shifted by (phase_dx, phase_dy)[q], uses the weight rows
+  // [q * b_phase_rows, ...) of the packed matrix, stores through the q-th output map (the parity sub-lattice
+  // out[:, py::2, px::2, :] of the high-resolution tensor) and writes its GroupNorm partials into the q-th region.
+  int phases;                     // 1 (ordinary convolution) or 4
+  int phase_dx[4], phase_dy[4];
+  int b_phase_rows;
+  long long gn_phase_stride;      // floats between the phases' regions of gn_partial
+  CUtensorMap out_map_ph[3];      // output maps of phases 1..3 (phase 0 = out_map)
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -328,7 +337,8 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_work = ((m_tiles + CTAS - 1) / CTAS) * p.n_tiles;  // work item = CTAS adjacent m-tiles x one n-tile
+  // work item = CTAS adjacent m-tiles x one n-tile (x one sub-pixel phase, fastest: the phases of a tile share its A rows in L2)
+  const int total_work = ((m_tiles + CTAS - 1) / CTAS) * p.n_tiles * p.phases;
   const int main_items = p.num_taps * p.chunks_per_tap;
   // pipeline stages per tile; HALO: one stage per (kernel row, channel chunk), else KCH K-items per stage
   const int num_kb = HALO ? 3 * p.chunks_per_tap : (main_items + p.extra_chunks) / KCH;  // host guarantees divisibility
@@ -337,6 +347,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
     for (int i = 0; i < 4; ++i) prefetch_tmap(&p.a_map[i]);
     prefetch_tmap(&p.b_map);
     if (p.out_tma) prefetch_tmap(&p.out_map);
+    for (int i = 1; i < p.phases; ++i) prefetch_tmap(&p.out_map_ph[i - 1]);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], CTAS);   // one producer arrive per CTA of the group (the leader's copy is the live one)
       mbar_init(&empty_bar[i], 1);
@@ -386,14 +397,16 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
       int stage = 0;
       uint32_t phase = 0;
       for (int work = group_id; work < total_work; work += num_groups) {
-        const int nt = work % p.n_tiles;
-        const int mt = (work / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
+        const int ph = work % p.phases;
+        const int wk = work / p.phases;
+        const int nt = wk % p.n_tiles;
+        const int mt = (wk / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);  // == tiles_n for the padding tile of an odd tail: fully OOB -> zeros
-        const int x0 = tw * p.box_w, y0 = th * p.box_h, img0 = tn * p.box_n;
+        const int x0 = tw * p.box_w + p.phase_dx[ph], y0 = th * p.box_h + p.phase_dy[ph], img0 = tn * p.box_n;
         const int bb = p.b_batched ? img0 : 0;
-        const int b_row0 = nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS;
+        const int b_row0 = nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS + ph * p.b_phase_rows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p.debug_mode & 4) {
@@ -611,11 +624,14 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
     for (int work = group_id; work < total_work; work += num_groups, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = work % p.n_tiles;
-      const int mt = (work / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
+      const int ph = work % p.phases;
+      const int wk = work / p.phases;
+      const int nt = wk % p.n_tiles;
+      const int mt = (wk / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tn = mt / (p.tiles_w * p.tiles_h);
+      const CUtensorMap* omap = ph == 0 ? &p.out_map : &p.out_map_ph[ph - 1];
       const int ox = tw * p.box_w + wi, oy = th * p.box_h + hi, on = tn * p.box_n + ni;
       const bool valid = mt < m_tiles && row < box_pix && ox < p.Wo && oy < p.Ho && on < p.Nimg;
       const long long pix = (static_cast<long long>(on) * p.Ho + oy) * p.Wo + ox;
@@ -739,7 +755,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
                   if (lane == 0 && mt < m_tiles && sub * 32 < box_pix) {  // warps past the box hold no pixels
                     asm volatile(
                         "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                            reinterpret_cast<uint64_t>(&p.out_map)),
+                            reinterpret_cast<uint64_t>(omap)),
                         "r"(smem_u32(buf)), "r"(n0), "r"(tw * p.box_w + w_wi), "r"(th * p.box_h + w_hi),
                         "r"(tn * p.box_n + w_ni)
                         : "memory");
@@ -774,7 +790,8 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
               }
-              float* dst = p.gn_partial + ((static_cast<long long>(mt) * 4 + sub) * p.gn_groups + n0 / p.gn_cpg) * 2;
+              float* dst = p.gn_partial + ph * p.gn_phase_stride +
+                           ((static_cast<long long>(mt) * 4 + sub) * p.gn_groups + n0 / p.gn_cpg) * 2;
               switch (p.gn_cpg) {
                 case 1: gn_chunk<1>(v, lane, dst); break;
                 case 2: gn_chunk<2>(v, lane, dst); break;

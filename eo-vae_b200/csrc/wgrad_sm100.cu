@@ -165,6 +165,7 @@ struct WgradNhwcParams {
   int chunks_total, chunks_per_split;
   float* partial;
   uint32_t idesc;
+  signed char tap_dx[16], tap_dy[16];   // pixel shift of X for every tap (3x3: -1..1; 1x1: 0; sub-pixel upsample: see host)
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn128(uint32_t smem_addr) {
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_
         for (int a = 0; a < 2; ++a) tma_load_4d(&p.a_map, &full_bar[stage], sa + a * 8192, cot * 128 + a * 64, x0, y0, n);
         for (int j = 0; j < ntaps; ++j) {
           const int tap = tap0 + j;
-          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
 #pragma unroll
           for (int b = 0; b < BN / 64; ++b)
             tma_load_4d(&p.b_map, &full_bar[stage], sa + A_BYTES + (j * (BN / 64) + b) * 8192, cit * BN + b * 64, x0 + dx, y0 + dy, n);
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc2_kernel(const __grid
   const int cit = item % p.ci_tiles; item /= p.ci_tiles;
   const int cot2 = item % p.co_tiles; item /= p.co_tiles;   // here co_tiles counts 256-row tiles
   const int ks = item;
-  const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+  const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
   const int chunk0 = ks * p.chunks_per_split;
   int chunk1 = chunk0 + p.chunks_per_split;
   if (chunk1 > p.chunks_total) chunk1 = p.chunks_total;
@@ -528,12 +529,15 @@ int launch(const WgradParams& p, int items, cudaStream_t stream) {
 }
 
 
-int make_map_nhwc(CUtensorMap* m, int dtype, const void* base, int c, long long pitch, int w, int h, int n, int bw, int bh) {
+// lattice > 1: the map covers the sub-lattice base[:, ::lattice, ::lattice, :] of an image of (lattice*h) x (lattice*w) pixels
+int make_map_nhwc(CUtensorMap* m, int dtype, const void* base, int c, long long pitch, int w, int h, int n, int bw, int bh,
+                  int lattice = 1) {
   EncodeFn fn = encode_fn();
   EOVAE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t L = static_cast<cuuint64_t>(lattice);
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch) * 2, static_cast<cuuint64_t>(pitch) * 2 * w,
-                           static_cast<cuuint64_t>(pitch) * 2 * w * h};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch) * 2 * L, static_cast<cuuint64_t>(pitch) * 2 * (L * w) * L,
+                           static_cast<cuuint64_t>(pitch) * 2 * (L * w) * (L * h)};
   cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = fn(m, dtype == EOVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
@@ -599,20 +603,17 @@ size_t eovae_conv2d_wgrad_nhwc_workspace_bytes(int n, int h, int w, int cin, int
   return sizeof(float) * static_cast<size_t>(ks) * ksize * ksize * cout * cin;
 }
 
-int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int dy_dtype, int n, int h,
-                            int w, int cin, int cout, int ksize, float* dw_oihw, int accumulate, void* workspace,
-                            size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad_nhwc: kernel size must be 3 or 1");
-  EOVAE_CHECK((dtype == EOVAE_BF16 || dtype == EOVAE_F16) && (dy_dtype == EOVAE_BF16 || dy_dtype == EOVAE_F16),
-              "conv2d_wgrad_nhwc: 16-bit operands only");
-  EOVAE_CHECK(dtype == dy_dtype || getenv("EOVAE_ALLOW_MIXED_MMA") != nullptr,
-              "conv2d_wgrad_nhwc: x (%d) and dy (%d) formats must be equal (tcgen05 kind::f16 rejects mixed f16/bf16)", dtype, dy_dtype);
-  EOVAE_CHECK(eovae_conv2d_wgrad_nhwc_ok(h, w), "conv2d_wgrad_nhwc: %dx%d images do not tile into 64-pixel boxes", h, w);
-  EOVAE_CHECK(cin % 4 == 0 && x_pix_stride % 8 == 0 && dy_pix_stride % 8 == 0 && x_pix_stride >= cin && dy_pix_stride >= cout,
-              "conv2d_wgrad_nhwc: Cin %% 4 and 16-byte pixel pitches required (Cin %d, pitches %lld / %lld)", cin, x_pix_stride,
-              dy_pix_stride);
-  EOVAE_CHECK(workspace_bytes >= eovae_conv2d_wgrad_nhwc_workspace_bytes(n, h, w, cin, cout, ksize), "conv2d_wgrad_nhwc: workspace too small");
+}  // extern "C"
+
+namespace {
+
+// One weight-gradient launch: partial[ks][tap][cout][cin] then the fixed-order split-K reduction into dw_out laid out
+// [cout][cin][taps] (taps innermost = OIHW for a k x k kernel).  ``taps`` / offsets are free (3x3, 1x1, or the 2x2 taps of one
+// sub-pixel phase of the upsample conv); ``dy_lattice`` = 2 reads dY on the parity sub-lattice starting at ``dy``.
+int wgrad_nhwc_launch(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dy_lattice, int dtype,
+                      int dy_dtype, int n, int h, int w, int cin, int cout, int taps, const signed char* tap_dx,
+                      const signed char* tap_dy, float* dw_out, int accumulate, void* workspace, size_t workspace_bytes,
+                      cudaStream_t stream) {
   static bool env_read = false;
   if (!env_read) {
     const char* e = getenv("EOVAE_WGRAD_NO_PAIR");
@@ -622,13 +623,17 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
   WgradNhwcParams p;
   memset(&p, 0, sizeof(p));
   int bn;
-  plan_nhwc(n, h, w, cin, cout, ksize * ksize, &bn, &p.co_tiles, &p.ci_tiles, &p.ksplit, &p.chunks_per_split, &p.chunks_total);
-  p.H = h; p.W = w; p.N = n; p.taps = ksize * ksize; p.cout = cout; p.cin = cin;
+  plan_nhwc(n, h, w, cin, cout, taps, &bn, &p.co_tiles, &p.ci_tiles, &p.ksplit, &p.chunks_per_split, &p.chunks_total);
+  p.H = h; p.W = w; p.N = n; p.taps = taps; p.cout = cout; p.cin = cin;
+  for (int t = 0; t < taps; ++t) {
+    p.tap_dx[t] = tap_dx[t];
+    p.tap_dy[t] = tap_dy[t];
+  }
   p.bw = w >= 64 ? 64 : w;
   p.bh = 64 / p.bw;
   p.partial = static_cast<float*>(workspace);
-  const uint32_t fmt_a = dy_dtype == EOVAE_BF16 ? 1u : 0u;  // A operand = dY, B operand = X: kind::f16 takes the two
-  const uint32_t fmt_b = dtype == EOVAE_BF16 ? 1u : 0u;     // operand formats independently (f16 x bf16 allowed)
+  const uint32_t fmt_a = dy_dtype == EOVAE_BF16 ? 1u : 0u;  // A operand = dY, B operand = X
+  const uint32_t fmt_b = dtype == EOVAE_BF16 ? 1u : 0u;
   if (cout % 256 == 0 && cin % 256 == 0 && !g_no_pair) {
     // CTA-pair kernel: co_tiles counts 256-row tiles; same split-K plan (the partial layout does not depend on the tiling)
     p.co_tiles = cout / 256;
@@ -640,7 +645,7 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
     EOVAE_CHECK(workspace_bytes >= sizeof(float) * static_cast<size_t>(p.ksplit) * p.taps * cout * cin, "conv2d_wgrad_nhwc: workspace too small");
     p.idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(256 >> 3) << 17) |
               (static_cast<uint32_t>(256 >> 4) << 24);
-    if (make_map_nhwc(&p.a_map, dy_dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+    if (make_map_nhwc(&p.a_map, dy_dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh, dy_lattice)) return -3;
     if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh)) return -3;
     constexpr int SMEM2 = WG2_STAGES * WG2_KC * (2 * 128 * 128) + 1024 + 256;
     static bool set2 = false;
@@ -664,7 +669,7 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
     EOVAE_CUDA(cudaLaunchKernelEx(&cfg, wgrad_nhwc2_kernel, p));
     EOVAE_LAUNCH_CHECK();
     const long long total2 = static_cast<long long>(p.taps) * cout * cin;
-    wgrad_reduce_kernel<<<static_cast<unsigned>((total2 + 255) / 256), 256, 0, stream>>>(p.partial, dw_oihw, p.ksplit, p.taps, cout,
+    wgrad_reduce_kernel<<<static_cast<unsigned>((total2 + 255) / 256), 256, 0, stream>>>(p.partial, dw_out, p.ksplit, p.taps, cout,
                                                                                         cin, accumulate, total2);
     EOVAE_LAUNCH_CHECK();
     return 0;
@@ -672,7 +677,7 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
   const int tpi = pick_tpi(bn, p.taps);
   p.idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>((bn * tpi) >> 3) << 17) |
             (static_cast<uint32_t>(128 >> 4) << 24);  // bits 15 / 16: A and B are MN-major
-  if (make_map_nhwc(&p.a_map, dy_dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+  if (make_map_nhwc(&p.a_map, dy_dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh, dy_lattice)) return -3;
   if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh)) return -3;
   const int items = ceil_div(p.taps, tpi) * p.co_tiles * p.ci_tiles * p.ksplit;
   int rc;
@@ -685,8 +690,108 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
   }
   if (rc) return rc;
   const long long total = static_cast<long long>(p.taps) * cout * cin;
-  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p.partial, dw_oihw, p.ksplit, p.taps, cout,
+  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p.partial, dw_out, p.ksplit, p.taps, cout,
                                                                                       cin, accumulate, total);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// dW (3x3, OIHW) (+)= adjoint of the sub-pixel weight folding: dW[kh][kw] = sum over the phases (py, px) of
+// dW'[py,px][a(py,kh)][b(px,kw)], with a(0, kh) = (kh >= 1), a(1, kh) = (kh == 2) (the inverse of up2x_in_set in igemm_host.cu)
+__global__ void up2x_unfold_wgrad_kernel(const float* __restrict__ dwp /*[4][cout][cin][4]*/, float* __restrict__ dw, long long pairs,
+                                         int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (co, ci)
+  if (i >= pairs) return;
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(dwp + (q * pairs + i) * 4);
+    const float t[4] = {v.x, v.y, v.z, v.w};
+    const int py = q >> 1, px = q & 1;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int a = py == 0 ? (kh >= 1) : (kh == 2), b = px == 0 ? (kw >= 1) : (kw == 2);
+        acc[kh * 3 + kw] += t[a * 2 + b];
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) dw[i * 9 + k] = (accumulate ? dw[i * 9 + k] : 0.f) + acc[k];
+}
+
+}  // namespace
+
+extern "C" {
+
+int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int dy_dtype, int n, int h,
+                            int w, int cin, int cout, int ksize, float* dw_oihw, int accumulate, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(ksize == 3 || ksize == 1, "conv2d_wgrad_nhwc: kernel size must be 3 or 1");
+  EOVAE_CHECK((dtype == EOVAE_BF16 || dtype == EOVAE_F16) && (dy_dtype == EOVAE_BF16 || dy_dtype == EOVAE_F16),
+              "conv2d_wgrad_nhwc: 16-bit operands only");
+  EOVAE_CHECK(dtype == dy_dtype || getenv("EOVAE_ALLOW_MIXED_MMA") != nullptr,
+              "conv2d_wgrad_nhwc: x (%d) and dy (%d) formats must be equal (tcgen05 kind::f16 rejects mixed f16/bf16)", dtype, dy_dtype);
+  EOVAE_CHECK(eovae_conv2d_wgrad_nhwc_ok(h, w), "conv2d_wgrad_nhwc: %dx%d images do not tile into 64-pixel boxes", h, w);
+  EOVAE_CHECK(cin % 4 == 0 && x_pix_stride % 8 == 0 && dy_pix_stride % 8 == 0 && x_pix_stride >= cin && dy_pix_stride >= cout,
+              "conv2d_wgrad_nhwc: Cin %% 4 and 16-byte pixel pitches required (Cin %d, pitches %lld / %lld)", cin, x_pix_stride,
+              dy_pix_stride);
+  EOVAE_CHECK(workspace_bytes >= eovae_conv2d_wgrad_nhwc_workspace_bytes(n, h, w, cin, cout, ksize), "conv2d_wgrad_nhwc: workspace too small");
+  signed char dx[16], dyv[16];
+  for (int t = 0; t < ksize * ksize; ++t) {
+    dx[t] = ksize == 3 ? static_cast<signed char>(t % 3 - 1) : 0;
+    dyv[t] = ksize == 3 ? static_cast<signed char>(t / 3 - 1) : 0;
+  }
+  return wgrad_nhwc_launch(x, x_pix_stride, dy, dy_pix_stride, 1, dtype, dy_dtype, n, h, w, cin, cout, ksize * ksize, dx, dyv, dw_oihw,
+                           accumulate, workspace, workspace_bytes, stream);
+}
+
+// Weight gradient of the sub-pixel upsample convolution (eovae_conv2d_up2x): x = its LOW-resolution input [n][h][w][cin], dy =
+// the gradient of its high-resolution output [n][2h][2w][cout].  Four launches (one per phase, 2x2 taps, dY read on the
+// phase's parity sub-lattice) = 16 instead of 36 MAC units, then the 3x3 gradient is unfolded from the four 2x2 ones.
+// workspace: 4 * cout * cin * 4 floats (phase gradients) + the split-K partials of one launch.
+size_t eovae_conv2d_up2x_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout) {
+  int bn, cot, cit, ks, cps, ct;
+  plan_nhwc(n, h, w, cin, cout, 4, &bn, &cot, &cit, &ks, &cps, &ct);
+  if (cout % 256 == 0 && cin % 256 == 0) {
+    const int base = 4 * (cout / 256) * (cin / 256);
+    int ks2 = pick_ksplit(base, ct, eovae_num_sms() / 2);
+    const int cps2 = ceil_div(ct, ks2);
+    ks2 = ceil_div(ct, cps2);
+    if (ks2 > ks) ks = ks2;
+  }
+  return sizeof(float) * (static_cast<size_t>(ks) * 4 * cout * cin + 16 * static_cast<size_t>(cout) * cin);
+}
+
+int eovae_conv2d_up2x_wgrad(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int h,
+                            int w, int cin, int cout, float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+                            void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "conv2d_up2x_wgrad: 16-bit operands only");
+  EOVAE_CHECK(eovae_conv2d_wgrad_nhwc_ok(h, w), "conv2d_up2x_wgrad: %dx%d images do not tile into 64-pixel boxes", h, w);
+  EOVAE_CHECK(cin % 4 == 0 && x_pix_stride % 8 == 0 && dy_pix_stride % 8 == 0, "conv2d_up2x_wgrad: Cin %% 4 and 16-byte pixel pitches required");
+  EOVAE_CHECK(workspace_bytes >= eovae_conv2d_up2x_wgrad_workspace_bytes(n, h, w, cin, cout), "conv2d_up2x_wgrad: workspace too small");
+  float* phase_dw = static_cast<float*>(workspace);                       // [4][cout][cin][4]
+  const size_t phase_elems = 4 * static_cast<size_t>(cout) * cin;
+  float* partial = phase_dw + 4 * phase_elems;
+  const size_t partial_bytes = workspace_bytes - sizeof(float) * 4 * phase_elems;
+  for (int q = 0; q < 4; ++q) {
+    const int py = q >> 1, px = q & 1;
+    signed char dx[16], dyv[16];
+    for (int t = 0; t < 4; ++t) {
+      dyv[t] = static_cast<signed char>((t >> 1) - 1 + py);
+      dx[t] = static_cast<signed char>((t & 1) - 1 + px);
+    }
+    const uint8_t* dyq = static_cast<const uint8_t*>(dy) + (static_cast<size_t>(py) * (2 * w) + px) * dy_pix_stride * 2;
+    int rc = wgrad_nhwc_launch(x, x_pix_stride, dyq, dy_pix_stride, 2, dtype, dtype, n, h, w, cin, cout, 4, dx, dyv,
+                               phase_dw + q * phase_elems, 0, partial, partial_bytes, stream);
+    if (rc) return rc;
+  }
+  const long long pairs = static_cast<long long>(cout) * cin;
+  up2x_unfold_wgrad_kernel<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, stream>>>(phase_dw, dw_oihw, pairs, accumulate);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

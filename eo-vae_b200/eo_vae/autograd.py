@@ -274,6 +274,9 @@ class UpsampleFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, mod):
         ctx.save_for_backward(x, weight)
+        ctx.up2x = ops.up2x_ok(x, mod.conv.out_channels)
+        if ctx.up2x:   # sub-pixel form: four 2x2 convs on the low-resolution input
+            return ops.conv2d_up2x(x, mod.packed_weight_up2x(x.dtype), _bias(mod.conv), mod.conv.out_channels, gn_groups=32)
         return ops.conv2d(ops.upsample2x(x), mod.conv.packed_weight(x.dtype), _bias(mod.conv), mod.conv.out_channels,
                           ops.CONV_3X3, gn_groups=32)
 
@@ -281,8 +284,14 @@ class UpsampleFn(Function):
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
         g = _grad_act(dy, _gd(x))
-        dx = ops.pool2x2_sum(ops.conv2d_dgrad(g, weight, ops.CONV_3X3))
-        dw = ops.conv2d_wgrad(ops.upsample2x(x), g, 3)
+        if ctx.up2x and ops.pix_stride(g) % 8 == 0:
+            dx = ops.conv2d_up2x_dgrad(g, weight)           # one 16-tap launch over the parity sub-lattices of g
+        else:
+            dx = ops.pool2x2_sum(ops.conv2d_dgrad(g, weight, ops.CONV_3X3))
+        if ctx.up2x and ops.up2x_wgrad_ok(x, g):
+            dw = ops.conv2d_up2x_wgrad(x, g)                # four 2x2-tap launches, unfolded to the 3x3 gradient
+        else:
+            dw = ops.conv2d_wgrad(ops.upsample2x(x), g, 3)
         return dx, dw, ops.bias_grad(g), None
 
 

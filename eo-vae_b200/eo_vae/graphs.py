@@ -50,6 +50,8 @@ def _invalidate_operand_caches(model) -> None:
             m._fused_key = None
         if hasattr(m, "_qkv_key"):
             m._qkv_key = None
+        if hasattr(m, "_up_key"):
+            m._up_key = None
 
 
 class GraphedTrainStep:

@@ -162,6 +162,93 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, mode: int, 
     return out
 
 
+# ------------------------------------------------------------------------------------------------ sub-pixel upsample conv
+# Upsample (layers.py:40-50) = nearest x2 + conv3x3.  USE_UP2X: run it as four 2x2 convolutions on the low-resolution input
+# (16 instead of 36 MAC units, no materialised 4x tensor) in forward, data gradient and weight gradient.
+USE_UP2X = True
+
+
+def up2x_ok(x: torch.Tensor, cout: int) -> bool:
+    n, cin, h, w = x.shape
+    return (USE_UP2X and x.dtype != torch.float32 and pix_stride(x) % 8 == 0
+            and bool(_C.lib().eovae_conv2d_up2x_ok(n, h, w, cin, cout)))
+
+
+def pack_conv_weight_up2x(w: torch.Tensor, dtype, dgrad: bool = False) -> torch.Tensor:
+    """OIHW fp32 3x3 -> folded 2x2 operands: forward [4 phases][rows][4 taps][k] or data-gradient [cin rows][16][k]."""
+    _need_cuda(w)
+    cout, cin, kh, kw = w.shape
+    if (kh, kw) != (3, 3):
+        raise RuntimeError("eo_vae.pack_conv_weight_up2x: 3x3 kernels only")
+    wf = w.detach().to(torch.float32).contiguous()
+    if dgrad:
+        out = torch.empty(((cin + 15) // 16 * 16, 16, conv_k_per_tap((cout + 7) // 8 * 8)), dtype=dtype, device=w.device)
+    else:
+        out = torch.empty((4, (cout + 15) // 16 * 16, 4, conv_k_per_tap(cin)), dtype=dtype, device=w.device)
+    _C.check(_C.lib().eovae_pack_conv_weight_up2x(_ptr(wf), _ptr(out), cout, cin, DT[dtype], 1 if dgrad else 0, _stream()),
+             "eovae_pack_conv_weight_up2x")
+    return out
+
+
+def conv2d_up2x(x: torch.Tensor, w_packed: torch.Tensor, bias, cout: int, gn_groups: int = 0, gn_eps: float = 1e-6) -> torch.Tensor:
+    """conv3x3(nearest_x2(x)) + bias from the LOW-resolution x; optional GroupNorm statistics of the output."""
+    _need_cuda(x, w_packed, bias)
+    n, cin, h, w = x.shape
+    out = nhwc_empty(n, cout, 2 * h, 2 * w, x.dtype, x.device)
+    stats = ws = None
+    ws_bytes = 0
+    lib = _C.lib()
+    if gn_groups > 0:
+        ws_bytes = lib.eovae_conv2d_up2x_gn_workspace_bytes(n, h, w, cout, gn_groups)
+        if ws_bytes > 0:
+            stats = torch.empty((n, gn_groups, 2), dtype=torch.float32, device=x.device)
+            ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=x.device)
+    flops = 2.0 * n * (2 * h) * (2 * w) * cout * cin * 4   # MACs actually executed: 4 taps per output pixel
+    rc = _timed("conv", flops, lambda: lib.eovae_conv2d_up2x(
+        _ptr(x), n, h, w, cin, pix_stride(x), _ptr(w_packed), cout, _ptr(bias), _ptr(out), DT[out.dtype], pix_stride(out),
+        DT[x.dtype], _ptr(stats), gn_groups if stats is not None else 0, float(gn_eps), _ptr(ws), ws_bytes, _stream()))
+    _C.check(rc, "eovae_conv2d_up2x")
+    if stats is not None:
+        out._gn_stats = (stats, gn_groups, float(gn_eps))
+    return out
+
+
+def conv2d_up2x_dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Data gradient of conv2d_up2x wrt its low-resolution input (w: OIHW fp32 master weight): one 16-tap launch."""
+    _need_cuda(dy, w)
+    n, cout, h2, w2 = dy.shape
+    cin = w.shape[1]
+    wp = pack_conv_weight_up2x(w, dy.dtype, dgrad=True)
+    dx = nhwc_empty(n, cin, h2 // 2, w2 // 2, dy.dtype, dy.device)
+    flops = 2.0 * n * (h2 // 2) * (w2 // 2) * cin * cout * 16
+    rc = _timed("conv", flops, lambda: _C.lib().eovae_conv2d_up2x_dgrad(
+        _ptr(dy), n, h2, w2, cout, pix_stride(dy), _ptr(wp), cin, _ptr(dx), DT[dx.dtype], pix_stride(dx), DT[dy.dtype], _stream()))
+    _C.check(rc, "eovae_conv2d_up2x_dgrad")
+    return dx
+
+
+def conv2d_up2x_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """Weight gradient [cout, cin, 3, 3] fp32 of conv2d_up2x (x: low-resolution input, dy: high-resolution output gradient)."""
+    _need_cuda(x, dy)
+    n, cin, h, w = x.shape
+    cout = dy.shape[1]
+    lib = _C.lib()
+    ws_bytes = lib.eovae_conv2d_up2x_wgrad_workspace_bytes(n, h, w, cin, cout)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=x.device)
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
+    flops = 2.0 * n * h * w * cout * cin * 16
+    rc = _timed("wgrad", flops, lambda: lib.eovae_conv2d_up2x_wgrad(
+        _ptr(x), pix_stride(x), _ptr(dy), pix_stride(dy), DT[x.dtype], n, h, w, cin, cout, _ptr(dw), 0, _ptr(ws), ws_bytes, _stream()))
+    _C.check(rc, "eovae_conv2d_up2x_wgrad")
+    return dw
+
+
+def up2x_wgrad_ok(x: torch.Tensor, dy: torch.Tensor) -> bool:
+    n, cin, h, w = x.shape
+    return (USE_UP2X and x.dtype == dy.dtype and cin % 4 == 0 and pix_stride(x) % 8 == 0 and pix_stride(dy) % 8 == 0
+            and bool(_C.lib().eovae_conv2d_wgrad_nhwc_ok(h, w)))
+
+
 # The in-mainloop GroupNorm prologue is correct but slower than gn_apply + conv on B200 (see igemm_sm100.cuh): opt-in.
 USE_GN_PROLOGUE = False
 

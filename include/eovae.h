@@ -90,6 +90,27 @@ int eovae_gemm_tn_batched(const void* a, long long lda, long long a_batch_stride
                           long long b_batch_stride, void* c, int c_dtype, long long ldc, int batch, int m, int n, int k,
                           int a_dtype, int b_dtype, float scale, void* stream);
 
+/* ---- Upsample (layers.py:40-50: nearest x2 then conv3x3) in sub-pixel form: four 2x2 convolutions on the LOW-resolution
+ *      input, one per output parity (py, px), with the 3x3 taps that fall on the same source pixel summed (16 instead of 36
+ *      MACs per output pixel pair; the upsampled tensor is never materialised).  x [n][h][w][cin] -> out [n][2h][2w][cout].
+ *      eovae_pack_conv_weight_up2x: OIHW fp32 -> dgrad = 0: [4 phases][round_up(cout,16)][4 taps][k_per_tap(cin)]
+ *                                                 dgrad = 1: [round_up(cin,16)][16 = phase*4+tap][k_per_tap(round_up(cout,8))]
+ *      eovae_conv2d_up2x(_ok): forward (+ bias, + GroupNorm statistics of the output like eovae_conv2d);
+ *      eovae_conv2d_up2x_dgrad: dy [n][h2][w2][cout] -> dx [n][h2/2][w2/2][cin], ONE launch reading the four parity
+ *      sub-lattices of dy; eovae_conv2d_up2x_wgrad: dW (3x3 OIHW fp32) from the low-resolution input and dy.               */
+int eovae_conv2d_up2x_ok(int n, int h, int w, int cin, int cout);
+size_t eovae_conv2d_up2x_gn_workspace_bytes(int n, int h, int w, int cout, int groups);
+int eovae_pack_conv_weight_up2x(const float* w_oihw, void* out, int cout, int cin, int dtype, int dgrad, void* stream);
+int eovae_conv2d_up2x(const void* x, int n, int h, int w, int cin, long long x_pix_stride, const void* w_packed, int cout,
+                      const float* bias, void* out, int out_dtype, long long out_pix_stride, int act_dtype, float* gn_stats,
+                      int gn_groups, float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, void* stream);
+int eovae_conv2d_up2x_dgrad(const void* dy, int n, int h2, int w2, int cout, long long dy_pix_stride, const void* w_packed, int cin,
+                            void* dx, int dx_dtype, long long dx_pix_stride, int act_dtype, void* stream);
+size_t eovae_conv2d_up2x_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout);
+int eovae_conv2d_up2x_wgrad(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int h,
+                            int w, int cin, int cout, float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* fp32 validation path (north_star: 1e-4 against the fp32 reference; selected by dtype code EOVAE_DT_F32 in eovae_conv2d,
  * eovae_gemm_tn_batched, eovae_gn_stats, eovae_gn_apply, eovae_nchw_to_nhwc16, eovae_softmax_rows, eovae_latent_denorm,
  * eovae_pack_conv_weight, eovae_pack_dyn_weight): SIMT fp32 FMAs, no tensor cores.  This entry is its general batched GEMM

@@ -612,3 +612,67 @@ def test_weight_pack_layouts(cuda, cout, cin, k, dtype):
     want = torch.zeros((rows, taps, kpt), dtype=dtype)
     want[:cin, :, :cout] = w.reshape(cout, cin, taps).flip(2).permute(1, 2, 0).to(dtype)
     assert dg.shape == want.shape and torch.equal(dg, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Upsample in sub-pixel form (layers.py:40-50): forward, data gradient and weight gradient against torch on the SAME rounded
+# operands (nearest x2 + 3x3 conv, fp32), plus GroupNorm statistics of the output from the phase epilogue.
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n,c,cout,h,w", [(2, 64, 64, 32, 32), (1, 128, 64, 64, 64), (2, 256, 256, 16, 32), (3, 64, 96, 8, 16)])
+def test_upsample_subpixel_forward_and_gradients(cuda, dtype, n, c, cout, h, w):
+    from eo_vae import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(n * 1000 + c + h)
+    x = torch.randn((n, h, w, c), generator=g).to(cuda).to(dtype).permute(0, 3, 1, 2)
+    wgt = (torch.randn((cout, c, 3, 3), generator=g) * 0.05).to(cuda)
+    bias = torch.randn((cout,), generator=g).to(cuda)
+    assert ops.up2x_ok(x, cout)
+    out = ops.conv2d_up2x(x, ops.pack_conv_weight_up2x(wgt, dtype), bias, cout, gn_groups=32)
+    assert out.shape == (n, cout, 2 * h, 2 * w)
+    xr = x.float().detach().requires_grad_(True)
+    wr = wgt.clone().requires_grad_(True)
+    ref = F.conv2d(F.interpolate(xr, scale_factor=2.0, mode="nearest"), wr, bias, padding=1)
+    # the kernel rounds the FOLDED taps (sums of up to four fp32 weights) once; the reference rounds nothing: fp16/bf16 operand error
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2
+    assert _rel(out.float(), ref) < tol, _rel(out.float(), ref)
+    st = out._gn_stats[0]
+    grp = out.float().reshape(n, 32, -1)
+    assert torch.allclose(st[..., 0], grp.mean(-1), atol=2e-3)
+    assert torch.allclose(st[..., 1], 1.0 / torch.sqrt(grp.var(-1, unbiased=False) + 1e-6), rtol=2e-3)
+    dy = torch.randn((n, 2 * h, 2 * w, cout), generator=g).to(cuda).to(dtype).permute(0, 3, 1, 2)
+    ref.backward(dy.float())
+    dx = ops.conv2d_up2x_dgrad(dy, wgt)
+    assert dx.shape == x.shape and _rel(dx.float(), xr.grad) < tol * 1.5, _rel(dx.float(), xr.grad)
+    assert ops.up2x_wgrad_ok(x, dy)
+    dw = ops.conv2d_up2x_wgrad(x, dy)
+    assert _rel(dw, wr.grad) < 2e-3, _rel(dw, wr.grad)       # fp32 accumulate over exactly representable operands
+
+
+def test_upsample_module_subpixel_equals_materialised(cuda):
+    """The Upsample module through both paths (sub-pixel vs nearest-upsample + 3x3) and its taped gradients."""
+    from eo_vae import ops
+    from eo_vae.models.modules.layers import Upsample
+    torch.manual_seed(5)
+    up = Upsample(64).to(cuda)
+    x = torch.randn((2, 32, 32, 64), device=cuda).permute(0, 3, 1, 2)
+    with torch.no_grad():
+        a = up(x).float()
+        ops.USE_UP2X = False
+        try:
+            b = up(x).float()
+        finally:
+            ops.USE_UP2X = True
+    assert _rel(a, b) < 2e-3
+    grads = []
+    for flag in (True, False):
+        ops.USE_UP2X = flag
+        try:
+            xr = x.clone().requires_grad_(True)
+            up.zero_grad()
+            y = up(xr)
+            y.float().square().mean().backward()
+            grads.append((xr.grad.float().clone(), up.conv.weight.grad.clone(), up.conv.bias.grad.clone()))
+        finally:
+            ops.USE_UP2X = True
+    for u, v in zip(*grads):
+        assert _rel(u, v) < 1.5e-2, _rel(u, v)       # bf16 training operands: folded vs unfolded rounding

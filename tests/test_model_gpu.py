@@ -48,7 +48,7 @@ DEFAULT = torch.float16
 def test_against_reference_golden(cuda, tag, dtype):
     import eo_vae
     gold, model, x, wvs = _setup(tag, cuda)
-    assert eo_vae.compute_dtype() == DEFAULT          # the default mode is the one held to the north-star bounds
+    assert eo_vae.inference_dtype() == DEFAULT        # the default mode is the one held to the north-star bounds
     eo_vae.set_compute_dtype(dtype)
     with torch.no_grad():
         moments = model.encoder(x, wvs)

@@ -19,10 +19,17 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// d/dz [z * sigmoid(z)] = s + z s (1 - s); `neg_z_log2e` = -z * log2(e) comes from one FMA on the raw input (the per-channel
-// GroupNorm affine is folded into its coefficients), so the whole derivative is 2 MUFU + 5 FP32 instructions
-__device__ __forceinline__ float silu_grad2(float z, float neg_z_log2e) {
-  const float s = rcp_approx(1.0f + ex2_approx(neg_z_log2e));
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// d/dz [z * sigmoid(z)] = s + z s (1 - s) with s = sigmoid(z) = 0.5 + 0.5 tanh(z / 2); `half_z` = z / 2 comes from one FMA on
+// the raw input (the per-channel GroupNorm affine is folded into its coefficients).  ONE MUFU op (tanh.approx.f32, relative
+// error 2^-11 - below the bf16 / fp16 rounding of the gradient it multiplies) + 4 FP32 instructions: the ex2 + rcp form
+// (2 MUFU + 5 FP32) kept both backward kernels instruction-issue bound at 0.3-0.5 of the HBM rate.
+__device__ __forceinline__ float silu_grad2(float z, float half_z) {
+  const float s = fmaf(0.5f, tanh_approx(half_z), 0.5f);
   return fmaf(z * (1.0f - s), s, s);
 }
 
@@ -46,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __rest
 #pragma unroll
   for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
   if (r < rows) {
-    // per-channel constants: xhat = x * rs + nm, z = x * za + zb, -z log2(e) = x * ea + eb
+    // per-channel constants: xhat = x * rs + nm, z = x * za + zb, z / 2 = x * ea + eb
     float rs[8], nm[8], za[8], zb[8], ea[8], eb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -56,8 +63,8 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __rest
       nm[j] = -mean * rstd;
       za[j] = rstd * gamma[ch];
       zb[j] = fmaf(-mean, za[j], beta[ch]);
-      ea[j] = -1.4426950408889634f * za[j];
-      eb[j] = -1.4426950408889634f * zb[j];
+      ea[j] = 0.5f * za[j];
+      eb[j] = 0.5f * zb[j];
     }
     const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
     long long p1 = p0 + pix_per_block;
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
   if (r < rows) {
   const int cpg = c / groups;
   const float inv_m = 1.0f / (static_cast<float>(hw) * cpg);
-  // per-channel constants: xhat = x * rs + nm, z = x * za + zb, -z log2(e) = x * ea + eb,
+  // per-channel constants: xhat = x * rs + nm, z = x * za + zb, z / 2 = x * ea + eb,
   // dx = dz * za - c1 - xhat * c2   with c1 = rstd * s1 / M, c2 = rstd * s2 / M
   float rs[8], nm[8], za[8], zb[8], ea[8], eb[8], c1[8], c2[8];
 #pragma unroll
@@ -216,8 +223,8 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
     nm[j] = -mean * rstd;
     za[j] = rstd * gamma[ch];
     zb[j] = fmaf(-mean, za[j], beta[ch]);
-    ea[j] = -1.4426950408889634f * za[j];
-    eb[j] = -1.4426950408889634f * zb[j];
+    ea[j] = 0.5f * za[j];
+    eb[j] = 0.5f * zb[j];
     c1[j] = rstd * gsum[(n * groups + gi) * 2] * inv_m;
     c2[j] = rstd * gsum[(n * groups + gi) * 2 + 1] * inv_m;
   }

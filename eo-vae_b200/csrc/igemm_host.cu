@@ -655,6 +655,26 @@ __global__ void pack_up2x_dgrad_kernel(const float* __restrict__ w, T* __restric
   out[i] = T16<T>::from_f(v);
 }
 
+// data-gradient operand of the Downsample conv (pad (0,1,0,1) + 3x3 stride 2, layers.py:33-37) in sub-pixel form: input pixel
+// (2i + pu, 2j + pv) receives dy[i - a, j - b] through W[kh, kw]^T with kh = 2a for pu = 0 (a in {0, 1}) and kh = 1 (a = 0 only)
+// for pu = 1; columns alike.  out[q = pu*2+pv][ci][t = a*2+b][co], zero where the phase has no such tap.
+template <typename T>
+__global__ void pack_s2_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int rows_pad, int kpt,
+                                     long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % kpt);
+  long long r = i / kpt;
+  const int t = static_cast<int>(r % 4); r /= 4;
+  const int ci = static_cast<int>(r % rows_pad);
+  const int q = static_cast<int>(r / rows_pad);
+  const int pu = q >> 1, pv = q & 1, a = t >> 1, b = t & 1;
+  const int kh = pu == 0 ? 2 * a : (a == 0 ? 1 : -1), kw = pv == 0 ? 2 * b : (b == 0 ? 1 : -1);
+  float v = 0.f;
+  if (ci < cin && co < cout && kh >= 0 && kw >= 0) v = w[(static_cast<long long>(co) * cin + ci) * 9 + kh * 3 + kw];
+  out[i] = T16<T>::from_f(v);
+}
+
 }  // namespace
 
 extern "C" {
@@ -676,6 +696,15 @@ size_t eovae_conv2d_up2x_gn_workspace_bytes(int n, int h, int w, int cout, int g
 int eovae_pack_conv_weight_up2x(const float* w_oihw, void* out, int cout, int cin, int dtype, int dgrad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "pack_conv_weight_up2x: 16-bit operands only");
+  if (dgrad == 2) {  // data-gradient operand of the STRIDE-2 conv: [4 phases][round_up(cin,16)][4 taps][k_per_tap(cout)]
+    const int kpt = eovae_conv_k_per_tap(round_up(cout, 8)), rows_pad = round_up(cin, 16);
+    const long long total = 4LL * rows_pad * 4 * kpt;
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+    if (dtype == EOVAE_BF16) pack_s2_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, rows_pad, kpt, total);
+    else pack_s2_dgrad_kernel<__half><<<grid, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, rows_pad, kpt, total);
+    EOVAE_LAUNCH_CHECK();
+    return 0;
+  }
   if (!dgrad) {
     const int kpt = eovae_conv_k_per_tap(cin), rows_pad = round_up(cout, 16);
     const long long total = 4LL * rows_pad * 4 * kpt;
@@ -717,6 +746,29 @@ int eovae_conv2d_up2x(const void* x, int n, int h, int w, int cin, long long x_p
   return launch_igemm(a, EOVAE_CONV_CUSTOM, w_packed, kpt, eovae_conv_chunk_bytes(cin), cout, 4LL * round_up(cout, 16), 4LL * kpt, 0, 1,
                       bias, nullptr, 0, 0, out, out_dtype, out_pix_stride, act_dtype, 1.0f, static_cast<cudaStream_t>(stream), gn_stats,
                       gn_groups, gn_eps, gn_workspace, gn_workspace_bytes, nullptr, nullptr, -1, &ts);
+}
+
+int eovae_conv2d_s2_dgrad(const void* dy, int n, int ho, int wo, int cout, long long dy_pix_stride, const void* w_packed, int cin,
+                          void* dx, int dx_dtype, long long dx_pix_stride, int act_dtype, void* stream) {
+  // dx [n][2 ho][2 wo][cin]: the four input parities are four 2x2 (zero-padded) convolutions over dy, each stored on its
+  // parity sub-lattice - 16 tap units per dy pixel instead of the 36 of "scatter dy into a zero-interleaved image + full 3x3"
+  EOVAE_CHECK(eovae_conv2d_up2x_ok(n, ho, wo, round_up(cout, 64), cin), "conv2d_s2_dgrad: unsupported shape");
+  EOVAE_CHECK(dx_dtype == EOVAE_BF16 || dx_dtype == EOVAE_F16, "conv2d_s2_dgrad: 16-bit output only");
+  TapSpec ts;
+  memset(&ts, 0, sizeof(ts));
+  ts.num_taps = 4;
+  for (int t = 0; t < 4; ++t) {
+    ts.tap_dy[t] = -(t >> 1);
+    ts.tap_dx[t] = -(t & 1);
+  }
+  ts.parity_in = false;
+  ts.phases = 4;
+  ts.b_phase_rows = round_up(cin, 16);
+  ASpec a{dy, n, ho, wo, cout, dy_pix_stride};
+  const int kpt = eovae_conv_k_per_tap(round_up(cout, 8));
+  return launch_igemm(a, EOVAE_CONV_CUSTOM, w_packed, kpt, eovae_conv_chunk_bytes(cout), cin, 4LL * round_up(cin, 16), 4LL * kpt, 0, 1,
+                      nullptr, nullptr, 0, 0, dx, dx_dtype, dx_pix_stride, act_dtype, 1.0f, static_cast<cudaStream_t>(stream), nullptr, 0,
+                      0.f, nullptr, 0, nullptr, nullptr, -1, &ts);
 }
 
 int eovae_conv2d_up2x_dgrad(const void* dy, int n, int h2, int w2, int cout, long long dy_pix_stride, const void* w_packed, int cin,

@@ -610,8 +610,8 @@ namespace {
 // One weight-gradient launch: partial[ks][tap][cout][cin] then the fixed-order split-K reduction into dw_out laid out
 // [cout][cin][taps] (taps innermost = OIHW for a k x k kernel).  ``taps`` / offsets are free (3x3, 1x1, or the 2x2 taps of one
 // sub-pixel phase of the upsample conv); ``dy_lattice`` = 2 reads dY on the parity sub-lattice starting at ``dy``.
-int wgrad_nhwc_launch(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dy_lattice, int dtype,
-                      int dy_dtype, int n, int h, int w, int cin, int cout, int taps, const signed char* tap_dx,
+int wgrad_nhwc_launch(const void* x, long long x_pix_stride, int x_lattice, const void* dy, long long dy_pix_stride, int dy_lattice,
+                      int dtype, int dy_dtype, int n, int h, int w, int cin, int cout, int taps, const signed char* tap_dx,
                       const signed char* tap_dy, float* dw_out, int accumulate, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream) {
   static bool env_read = false;
@@ -646,7 +646,7 @@ int wgrad_nhwc_launch(const void* x, long long x_pix_stride, const void* dy, lon
     p.idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(256 >> 3) << 17) |
               (static_cast<uint32_t>(256 >> 4) << 24);
     if (make_map_nhwc(&p.a_map, dy_dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh, dy_lattice)) return -3;
-    if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+    if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh, x_lattice)) return -3;
     constexpr int SMEM2 = WG2_STAGES * WG2_KC * (2 * 128 * 128) + 1024 + 256;
     static bool set2 = false;
     if (!set2) {
@@ -678,7 +678,7 @@ int wgrad_nhwc_launch(const void* x, long long x_pix_stride, const void* dy, lon
   p.idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>((bn * tpi) >> 3) << 17) |
             (static_cast<uint32_t>(128 >> 4) << 24);  // bits 15 / 16: A and B are MN-major
   if (make_map_nhwc(&p.a_map, dy_dtype, dy, cout, dy_pix_stride, w, h, n, p.bw, p.bh, dy_lattice)) return -3;
-  if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh)) return -3;
+  if (make_map_nhwc(&p.b_map, dtype, x, cin, x_pix_stride, w, h, n, p.bw, p.bh, x_lattice)) return -3;
   const int items = ceil_div(p.taps, tpi) * p.co_tiles * p.ci_tiles * p.ksplit;
   int rc;
   switch (bn * 8 + tpi) {
@@ -722,9 +722,85 @@ __global__ void up2x_unfold_wgrad_kernel(const float* __restrict__ dwp /*[4][cou
   for (int k = 0; k < 9; ++k) dw[i * 9 + k] = (accumulate ? dw[i * 9 + k] : 0.f) + acc[k];
 }
 
+// dW[co][ci][kh][kw] (+)= the per-parity-class gradients of the stride-2 conv: class q = (kh & 1) * 2 + (kw & 1) holds its taps
+// in the order (kh >> 1) * (number of kw of the class) + (kw >> 1); classes start at offsets 0, 4, 6, 8 (x cout*cin) of dwp
+__global__ void s2_gather_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, long long pairs, int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (co, ci)
+  if (i >= pairs) return;
+  const int class_off[4] = {0, 4, 6, 8}, class_taps[4] = {4, 2, 2, 1}, class_kw[4] = {2, 1, 2, 1};
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int q = (kh & 1) * 2 + (kw & 1);
+      const int t = (kh >> 1) * class_kw[q] + (kw >> 1);
+      const float v = dwp[class_off[q] * pairs + i * class_taps[q] + t];
+      float* o = dw + i * 9 + kh * 3 + kw;
+      *o = (accumulate ? *o : 0.f) + v;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+// Weight gradient of the Downsample conv (pad (0,1,0,1) + 3x3 stride 2): dW[kh][kw] = sum dy[i][j] x[2i + kh][2j + kw].  x is read
+// on its four parity sub-lattices (one launch per class of taps with equal parity; the pad row / column is TMA zero fill),
+// dy as it is: 9 tap units over the (h/2 x w/2) output pixels instead of 9 over the zero-interleaved (h x w) image.
+size_t eovae_conv2d_s2_wgrad_workspace_bytes(int n, int ho, int wo, int cin, int cout) {
+  int bn, cot, cit, ks, cps, ct;
+  plan_nhwc(n, ho, wo, cin, cout, 4, &bn, &cot, &cit, &ks, &cps, &ct);
+  if (cout % 256 == 0 && cin % 256 == 0) {
+    for (int taps = 1; taps <= 4; ++taps) {
+      const int base = taps * (cout / 256) * (cin / 256);
+      int ks2 = pick_ksplit(base, ct, eovae_num_sms() / 2);
+      const int cps2 = ceil_div(ct, ks2);
+      ks2 = ceil_div(ct, cps2);
+      if (ks2 > ks) ks = ks2;
+    }
+  }
+  for (int taps = 1; taps <= 2; ++taps) {
+    int ks1;
+    plan_nhwc(n, ho, wo, cin, cout, taps, &bn, &cot, &cit, &ks1, &cps, &ct);
+    if (ks1 > ks) ks = ks1;
+  }
+  return sizeof(float) * (static_cast<size_t>(ks) * 4 * cout * cin + 9 * static_cast<size_t>(cout) * cin);
+}
+
+int eovae_conv2d_s2_wgrad(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int ho,
+                          int wo, int cin, int cout, float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EOVAE_CHECK(dtype == EOVAE_BF16 || dtype == EOVAE_F16, "conv2d_s2_wgrad: 16-bit operands only");
+  EOVAE_CHECK(eovae_conv2d_wgrad_nhwc_ok(ho, wo), "conv2d_s2_wgrad: %dx%d outputs do not tile into 64-pixel boxes", ho, wo);
+  EOVAE_CHECK(cin % 4 == 0 && x_pix_stride % 8 == 0 && dy_pix_stride % 8 == 0, "conv2d_s2_wgrad: Cin %% 4 and 16-byte pixel pitches required");
+  EOVAE_CHECK(workspace_bytes >= eovae_conv2d_s2_wgrad_workspace_bytes(n, ho, wo, cin, cout), "conv2d_s2_wgrad: workspace too small");
+  float* class_dw = static_cast<float*>(workspace);                      // 9 * cout * cin floats: classes of 4, 2, 2, 1 taps
+  const size_t pairs = static_cast<size_t>(cout) * cin;
+  float* partial = class_dw + 9 * pairs;
+  const size_t partial_bytes = workspace_bytes - sizeof(float) * 9 * pairs;
+  const int class_off[4] = {0, 4, 6, 8};
+  for (int q = 0; q < 4; ++q) {
+    const int ph = q >> 1, pw = q & 1;
+    const int nkh = ph == 0 ? 2 : 1, nkw = pw == 0 ? 2 : 1;
+    signed char dx[16], dyv[16];
+    for (int a = 0; a < nkh; ++a)
+      for (int b = 0; b < nkw; ++b) {
+        dyv[a * nkw + b] = static_cast<signed char>(a);   // x offset inside the lattice: kh >> 1
+        dx[a * nkw + b] = static_cast<signed char>(b);
+      }
+    // lattice (ph, pw) of x (extent 2 ho x 2 wo): rows ph, ph + 2, ...; the map covers ho x wo lattice points, offset + 1 at the
+    // last index is out of bounds = the zero pad of F.pad(0, 1, 0, 1)
+    const uint8_t* xq = static_cast<const uint8_t*>(x) + (static_cast<size_t>(ph) * (2 * wo) + pw) * x_pix_stride * 2;
+    int rc = wgrad_nhwc_launch(xq, x_pix_stride, 2, dy, dy_pix_stride, 1, dtype, dtype, n, ho, wo, cin, cout, nkh * nkw, dx, dyv,
+                               class_dw + class_off[q] * pairs, 0, partial, partial_bytes, stream);
+    if (rc) return rc;
+  }
+  s2_gather_wgrad_kernel<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, stream>>>(class_dw, dw_oihw, static_cast<long long>(pairs),
+                                                                                        accumulate);
+  EOVAE_LAUNCH_CHECK();
+  return 0;
+}
 
 int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int dy_dtype, int n, int h,
                             int w, int cin, int cout, int ksize, float* dw_oihw, int accumulate, void* workspace,
@@ -745,7 +821,7 @@ int eovae_conv2d_wgrad_nhwc(const void* x, long long x_pix_stride, const void* d
     dx[t] = ksize == 3 ? static_cast<signed char>(t % 3 - 1) : 0;
     dyv[t] = ksize == 3 ? static_cast<signed char>(t / 3 - 1) : 0;
   }
-  return wgrad_nhwc_launch(x, x_pix_stride, dy, dy_pix_stride, 1, dtype, dy_dtype, n, h, w, cin, cout, ksize * ksize, dx, dyv, dw_oihw,
+  return wgrad_nhwc_launch(x, x_pix_stride, 1, dy, dy_pix_stride, 1, dtype, dy_dtype, n, h, w, cin, cout, ksize * ksize, dx, dyv, dw_oihw,
                            accumulate, workspace, workspace_bytes, stream);
 }
 
@@ -786,7 +862,7 @@ int eovae_conv2d_up2x_wgrad(const void* x, long long x_pix_stride, const void* d
       dx[t] = static_cast<signed char>((t & 1) - 1 + px);
     }
     const uint8_t* dyq = static_cast<const uint8_t*>(dy) + (static_cast<size_t>(py) * (2 * w) + px) * dy_pix_stride * 2;
-    int rc = wgrad_nhwc_launch(x, x_pix_stride, dyq, dy_pix_stride, 2, dtype, dtype, n, h, w, cin, cout, 4, dx, dyv,
+    int rc = wgrad_nhwc_launch(x, x_pix_stride, 1, dyq, dy_pix_stride, 2, dtype, dtype, n, h, w, cin, cout, 4, dx, dyv,
                                phase_dw + q * phase_elems, 0, partial, partial_bytes, stream);
     if (rc) return rc;
   }

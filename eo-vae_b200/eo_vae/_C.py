@@ -37,6 +37,9 @@ SIGNATURES = {
     "eovae_pack_conv_weight_up2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "eovae_conv2d_up2x": (_i, [_vp, _i, _i, _i, _i, _ll, _vp, _i, _vp, _vp, _i, _ll, _i, _vp, _i, _f, _vp, _sz, _vp]),
     "eovae_conv2d_up2x_dgrad": (_i, [_vp, _i, _i, _i, _i, _ll, _vp, _i, _vp, _i, _ll, _i, _vp]),
+    "eovae_conv2d_s2_dgrad": (_i, [_vp, _i, _i, _i, _i, _ll, _vp, _i, _vp, _i, _ll, _i, _vp]),
+    "eovae_conv2d_s2_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "eovae_conv2d_s2_wgrad": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "eovae_conv2d_up2x_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "eovae_conv2d_up2x_wgrad": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "eovae_gemm_strided_f32": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp]),

@@ -83,6 +83,8 @@ def _dense(g: torch.Tensor) -> torch.Tensor:
 
 def _wgrad(x: torch.Tensor, g: torch.Tensor, mode: int) -> torch.Tensor:
     if mode == ops.CONV_3X3_S2:
+        if ops.s2_wgrad_ok(x, g):
+            return ops.conv2d_s2_wgrad(x, g)   # x on its parity sub-lattices: 9 tap units over the OUTPUT pixels
         return ops.conv2d_wgrad(x, ops.scatter_stride2(_dense(g), x.shape[2], x.shape[3]), 3)
     return ops.conv2d_wgrad(x, g, 1 if mode == ops.CONV_1X1 else 3)
 

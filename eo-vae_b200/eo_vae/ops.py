@@ -243,6 +243,30 @@ def conv2d_up2x_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
     return dw
 
 
+def conv2d_s2_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """Weight gradient [cout, cin, 3, 3] fp32 of the Downsample conv: x [n, cin, 2ho, 2wo] (read on its parity sub-lattices),
+    dy [n, cout, ho, wo] - no zero-interleaved gradient image."""
+    _need_cuda(x, dy)
+    n, cin, h, w = x.shape
+    cout, ho, wo = dy.shape[1], dy.shape[2], dy.shape[3]
+    lib = _C.lib()
+    ws_bytes = lib.eovae_conv2d_s2_wgrad_workspace_bytes(n, ho, wo, cin, cout)
+    ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=x.device)
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
+    flops = 2.0 * n * ho * wo * cout * cin * 9
+    rc = _timed("wgrad", flops, lambda: lib.eovae_conv2d_s2_wgrad(
+        _ptr(x), pix_stride(x), _ptr(dy), pix_stride(dy), DT[x.dtype], n, ho, wo, cin, cout, _ptr(dw), 0, _ptr(ws), ws_bytes, _stream()))
+    _C.check(rc, "eovae_conv2d_s2_wgrad")
+    return dw
+
+
+def s2_wgrad_ok(x: torch.Tensor, dy: torch.Tensor) -> bool:
+    n, cin, h, w = x.shape
+    ho, wo = dy.shape[2], dy.shape[3]
+    return (USE_UP2X and x.dtype == dy.dtype and (h, w) == (2 * ho, 2 * wo) and cin % 4 == 0 and pix_stride(x) % 8 == 0
+            and pix_stride(dy) % 8 == 0 and bool(_C.lib().eovae_conv2d_wgrad_nhwc_ok(ho, wo)))
+
+
 def up2x_wgrad_ok(x: torch.Tensor, dy: torch.Tensor) -> bool:
     n, cin, h, w = x.shape
     return (USE_UP2X and x.dtype == dy.dtype and cin % 4 == 0 and pix_stride(x) % 8 == 0 and pix_stride(dy) % 8 == 0
@@ -652,10 +676,36 @@ def scatter_stride2(dy: torch.Tensor, h: int, w: int) -> torch.Tensor:
     return z
 
 
+def conv2d_s2_dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Data gradient of the Downsample conv in sub-pixel form: four 2x2 convolutions over dy, one per input parity, each
+    stored on its parity sub-lattice of dx [n, cin, 2 ho, 2 wo] - no zero-interleaved gradient image, 16 / 36 of the MACs."""
+    _need_cuda(dy, w)
+    n, cout, ho, wo = dy.shape
+    cin = w.shape[1]
+    wf = w.detach().to(torch.float32).contiguous()
+    wp = torch.empty((4, (cin + 15) // 16 * 16, 4, conv_k_per_tap((cout + 7) // 8 * 8)), dtype=dy.dtype, device=dy.device)
+    _C.check(_C.lib().eovae_pack_conv_weight_up2x(_ptr(wf), _ptr(wp), cout, cin, DT[dy.dtype], 2, _stream()),
+             "eovae_pack_conv_weight_up2x")
+    dx = nhwc_empty(n, cin, 2 * ho, 2 * wo, dy.dtype, dy.device)
+    flops = 2.0 * n * ho * wo * cin * cout * 16
+    rc = _timed("conv", flops, lambda: _C.lib().eovae_conv2d_s2_dgrad(
+        _ptr(dy), n, ho, wo, cout, pix_stride(dy), _ptr(wp), cin, _ptr(dx), DT[dx.dtype], pix_stride(dx), DT[dy.dtype], _stream()))
+    _C.check(rc, "eovae_conv2d_s2_dgrad")
+    return dx
+
+
+def s2_dgrad_ok(dy: torch.Tensor, cin: int, in_hw) -> bool:
+    n, cout, ho, wo = dy.shape
+    return (USE_UP2X and in_hw is not None and tuple(in_hw) == (2 * ho, 2 * wo) and cout % 64 == 0 and pix_stride(dy) % 8 == 0
+            and bool(_C.lib().eovae_conv2d_up2x_ok(n, ho, wo, cout, cin)))
+
+
 def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, mode: int, in_hw=None, grad_add=None) -> torch.Tensor:
     """Data gradient of eovae_conv2d (w: OIHW fp32 master weight) as another implicit GEMM; ``grad_add`` (same shape
     as the result) is accumulated in the epilogue (gradient fan-in of a residual branch)."""
     cout, cin = w.shape[0], w.shape[1]
+    if mode == CONV_3X3_S2 and grad_add is None and s2_dgrad_ok(dy, cin, in_hw):
+        return conv2d_s2_dgrad(dy, w)
     wp = pack_conv_weight_dgrad(w, dy.dtype)
     if mode == CONV_3X3_S2:
         return conv2d(scatter_stride2(dy, in_hw[0], in_hw[1]), wp, None, cin, CONV_3X3, residual=grad_add)

@@ -106,6 +106,15 @@ int eovae_conv2d_up2x(const void* x, int n, int h, int w, int cin, long long x_p
                       int gn_groups, float gn_eps, void* gn_workspace, size_t gn_workspace_bytes, void* stream);
 int eovae_conv2d_up2x_dgrad(const void* dy, int n, int h2, int w2, int cout, long long dy_pix_stride, const void* w_packed, int cin,
                             void* dx, int dx_dtype, long long dx_pix_stride, int act_dtype, void* stream);
+/* data gradient of the Downsample conv (EOVAE_CONV_3X3_S2) in the same sub-pixel form: dy [n][ho][wo][cout] ->
+ * dx [n][2ho][2wo][cin]; operand = eovae_pack_conv_weight_up2x(..., dgrad = 2): [4][round_up(cin,16)][4][k_per_tap(cout)] */
+int eovae_conv2d_s2_dgrad(const void* dy, int n, int ho, int wo, int cout, long long dy_pix_stride, const void* w_packed, int cin,
+                          void* dx, int dx_dtype, long long dx_pix_stride, int act_dtype, void* stream);
+/* weight gradient of the Downsample conv: x [n][2ho][2wo][cin] read on its four parity sub-lattices, dy [n][ho][wo][cout] */
+size_t eovae_conv2d_s2_wgrad_workspace_bytes(int n, int ho, int wo, int cin, int cout);
+int eovae_conv2d_s2_wgrad(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int ho,
+                          int wo, int cin, int cout, float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+                          void* stream);
 size_t eovae_conv2d_up2x_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout);
 int eovae_conv2d_up2x_wgrad(const void* x, long long x_pix_stride, const void* dy, long long dy_pix_stride, int dtype, int n, int h,
                             int w, int cin, int cout, float* dw_oihw, int accumulate, void* workspace, size_t workspace_bytes,

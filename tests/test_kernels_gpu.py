@@ -679,3 +679,36 @@ def test_upsample_module_subpixel_equals_materialised(cuda):
             ops.USE_UP2X = True
     for u, v in zip(*grads):
         assert _rel(u, v) < 1.5e-2, _rel(u, v)       # bf16 training operands: folded vs unfolded rounding
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n,c,cout,h,w", [(2, 64, 64, 64, 64), (1, 128, 128, 32, 64), (2, 64, 128, 16, 32)])
+def test_downsample_subpixel_data_gradient(cuda, dtype, n, c, cout, h, w):
+    """Data gradient of the Downsample conv (pad (0,1,0,1) + 3x3 stride 2) as four 2x2 phase convolutions vs torch autograd."""
+    from eo_vae import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(n * 100 + c + h)
+    wgt = (torch.randn((cout, c, 3, 3), generator=g) * 0.05).to(cuda)
+    xr = torch.randn((n, c, h, w), generator=g).to(cuda).requires_grad_(True)
+    y = F.conv2d(F.pad(xr, (0, 1, 0, 1)), wgt, None, stride=2)
+    dy = torch.randn((n, h // 2, w // 2, cout), generator=g).to(cuda).to(dtype).permute(0, 3, 1, 2)
+    y.backward(dy.float())
+    assert ops.s2_dgrad_ok(dy, c, (h, w))
+    dx = ops.conv2d_dgrad(dy, wgt, ops.CONV_3X3_S2, in_hw=(h, w))
+    assert dx.shape == (n, c, h, w)
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2
+    assert _rel(dx.float(), xr.grad) < tol, _rel(dx.float(), xr.grad)
+    ops.USE_UP2X = False
+    try:
+        dx_old = ops.conv2d_dgrad(dy, wgt, ops.CONV_3X3_S2, in_hw=(h, w))
+    finally:
+        ops.USE_UP2X = True
+    assert _rel(dx.float(), dx_old.float()) < (2e-2 if dtype == torch.bfloat16 else 3e-3)
+    # weight gradient: x read on its parity sub-lattices
+    x16 = xr.detach().to(dtype).contiguous(memory_format=torch.channels_last)
+    xr2 = x16.float().requires_grad_(True)
+    wr = wgt.clone().requires_grad_(True)
+    F.conv2d(F.pad(xr2, (0, 1, 0, 1)), wr, None, stride=2).backward(dy.float())
+    assert ops.s2_wgrad_ok(x16, dy)
+    dw = ops.conv2d_s2_wgrad(x16, dy)
+    assert _rel(dw, wr.grad) < 2e-3, _rel(dw, wr.grad)

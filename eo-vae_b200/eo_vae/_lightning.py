@@ -71,7 +71,9 @@ except Exception:  # noqa: BLE001
             return self._schedulers if len(self._schedulers) > 1 else self._schedulers[0]
 
         def manual_backward(self, loss: torch.Tensor) -> None:
-            loss.backward()
+            from .autograd import async_hypernet
+            with async_hypernet():   # hypernetwork backward on the side stream, joined on exit
+                loss.backward()
             if self._grad_sync is not None:
                 self._grad_sync.finish()
 

@@ -71,9 +71,7 @@ except Exception:  # noqa: BLE001
             return self._schedulers if len(self._schedulers) > 1 else self._schedulers[0]
 
         def manual_backward(self, loss: torch.Tensor) -> None:
-            from .autograd import async_hypernet
-            with async_hypernet():   # hypernetwork backward on the side stream, joined on exit
-                loss.backward()
+            loss.backward()
             if self._grad_sync is not None:
                 self._grad_sync.finish()
 

@@ -34,65 +34,6 @@ def _gd(x: torch.Tensor):
     return x.dtype
 
 
-# ---------------------------------------------------------------------------------------------- hypernetwork side stream
-# The decoder's output hypernetwork is ~90 tiny latency-bound kernels each way (0.5 ms forward, 1.5 ms backward) that depend
-# on nothing but the wavelengths, the parameters and - backward - the generated kernel's gradient.  They run on a side stream:
-# the forward is PREFETCHED at the start of the step (under the encoder body), the backward runs beside the decoder body's
-# data-gradient chain.  The forward is joined where its result is consumed; the backward only under ``async_hypernet()``,
-# whose exit (and every GradSync bucket pack) joins the side stream again - callers that run ``loss.backward()`` on their own
-# (real Lightning, plain torch) keep the fully synchronous order.
-_SIDE: dict = {}
-_PENDING: list = []
-_ASYNC_BACKWARD = [False]
-
-
-def side_stream(dev) -> "torch.cuda.Stream":
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(torch.device("cuda", key))
-    return _SIDE[key]
-
-
-def join_side() -> None:
-    """Make the current stream wait for every side-stream job issued so far (no-op when none is pending)."""
-    while _PENDING:
-        torch.cuda.current_stream().wait_event(_PENDING.pop())
-
-
-class async_hypernet:
-    """``with async_hypernet(): loss.backward()`` - hypernetwork backward passes may run on the side stream inside the block;
-    leaving it joins them (before anything reads the parameter gradients)."""
-
-    def __enter__(self):
-        self.prev = _ASYNC_BACKWARD[0]
-        _ASYNC_BACKWARD[0] = True
-        return self
-
-    def __exit__(self, *exc):
-        _ASYNC_BACKWARD[0] = self.prev
-        join_side()
-        return False
-
-
-def _on_side(fn, *read_on_side):
-    """Run fn() on the side stream after everything issued so far on the current stream; returns (result, event).
-    ``read_on_side``: main-stream tensors fn reads (the allocator must not recycle them before the side stream is done)."""
-    main = torch.cuda.current_stream()
-    side = side_stream(main.device)
-    side.wait_stream(main)
-    for t in read_on_side:
-        if isinstance(t, torch.Tensor) and t.is_cuda:
-            t.record_stream(side)
-    with torch.cuda.stream(side):
-        out = fn()
-        ev = torch.cuda.Event()
-        ev.record(side)
-    for t in (out if isinstance(out, (tuple, list)) else (out,)):
-        if isinstance(t, torch.Tensor):
-            t.record_stream(main)     # allocated on the side stream, consumed on the main one
-    return out, ev
-
-
 def grad_mode() -> bool:
     """The modules take the tape-recording path whenever torch would record a graph (the fp32 validation path is
     forward-only: it never records)."""
@@ -406,12 +347,7 @@ class DynConvOutFn(Function):
     @staticmethod
     def forward(ctx, x, mod, waves, *hparams):
         c = waves.size(0)
-        pre = mod.__dict__.pop('_prefetched', None)
-        if pre is not None and pre[0] is waves:
-            (wk, b_raw, tape), ev = pre[1], pre[2]
-            torch.cuda.current_stream().wait_event(ev)     # generated on the side stream at the start of the step
-        else:
-            wk, b_raw, tape = mod._generate_taped(waves)
+        wk, b_raw, tape = mod._generate_taped(waves)
         packed, bias, oihw = ops.pack_dyn_weight(wk, b_raw, c, mod.embed_dim, True, mod.scaler, mod.scaler * mod.scaler,
                                                  x.dtype, True)
         mod._last = (wk, b_raw, c)
@@ -427,13 +363,7 @@ class DynConvOutFn(Function):
         g = _grad_act_pad8(dy, _gd(x))
         dx = ops.conv2d_dgrad(g, oihw, ops.CONV_3X3) if ctx.needs_input_grad[0] else None
         dw = ops.conv2d_wgrad(x, g[:, :c], 3)  # [C, E, 3, 3]
-        db = ops.bias_grad(g[:, :c])
-        if _ASYNC_BACKWARD[0]:
-            # beside the decoder body's data-gradient chain; joined by async_hypernet.__exit__ / GradSync._pack
-            grads, ev = _on_side(lambda: mod._hyper_backward(waves, dw, db, mod.scaler * mod.scaler, tape), dw, db, tape, waves)
-            _PENDING.append(ev)
-        else:
-            grads = mod._hyper_backward(waves, dw, db, mod.scaler * mod.scaler, tape)
+        grads = mod._hyper_backward(waves, dw, ops.bias_grad(g[:, :c]), mod.scaler * mod.scaler, tape)
         return (dx, None, None) + tuple(grads)
 
 

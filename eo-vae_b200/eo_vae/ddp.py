@@ -84,9 +84,6 @@ class GradSync:
     # ------------------------------------------------------------------------------------------------------------
     def _pack(self, b: _Bucket) -> None:
         """Gradients -> their fixed slots (one multi-tensor copy); slots of parameters without a gradient are zeroed."""
-        if torch.cuda.is_available() and b.flat.is_cuda:
-            from .autograd import join_side
-            join_side()   # gradients produced on the hypernetwork side stream must be complete before they are copied
         have = [(v, p.grad) for v, p in zip(b.views, b.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
         with torch.no_grad():
             if have:

@@ -110,9 +110,7 @@ class GraphedTrainStep:
         recon, _ = m(self.x, self.wvs)
         loss, self.logs = m.loss_fn(inputs=self.x, wvs=self.wvs, reconstructions=recon, optimizer_idx=0,
                                     global_step=m.global_step, last_layer=m.get_last_layer(), split='train')
-        from .autograd import async_hypernet
-        with async_hypernet():   # captured as a forked branch of the graph, joined on exit
-            loss.backward()
+        loss.backward()
         return loss.detach()
 
     def __call__(self, batch: dict) -> torch.Tensor:

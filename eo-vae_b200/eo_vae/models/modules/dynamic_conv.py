@@ -238,14 +238,6 @@ class _DynamicBase(nn.Module):
         return ops.hypernet_forward_taped(wvs.to(device=dev, dtype=torch.float32), params, g.num_layers, g.input_dim,
                                           g.num_heads, g.ff_dim, self.embed_dim, self._decoder)
 
-    def prefetch_taped(self, wvs: Tensor) -> None:
-        """Training forward: start the (taped) generation now, on the side stream; the tape entry of this layer picks the
-        result up when it runs (eo_vae.autograd.DynConvOutFn) - the ~0.5 ms of tiny kernels hide under the encoder body."""
-        if not wvs.is_cuda:
-            return
-        res, ev = tape._on_side(lambda: self._generate_taped(wvs), wvs)
-        self.__dict__['_prefetched'] = (wvs, res, ev)
-
     def _hyper_backward(self, wvs: Tensor, dw_oihw: Tensor, dbias: Tensor, bias_scale: float, tape=None) -> list:
         """Gradients of ``weight_generator.parameter_list(fclayer)`` given the generated kernel's / bias' gradient."""
         g = self.weight_generator

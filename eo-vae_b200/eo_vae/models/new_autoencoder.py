@@ -282,8 +282,6 @@ class EOFluxVAE(LightningModule):
         return x + sigma * torch.randn_like(x)
 
     def forward(self, x: Tensor, wvs: Tensor, sample_posterior: bool = True, scale=None, angle: int | None = None):
-        if tape.grad_mode() and self.decoder.use_dynamic_ops and hasattr(self.decoder.conv_out, 'prefetch_taped'):
-            self.decoder.conv_out.prefetch_taped(wvs)   # decoder hypernetwork forward: side stream, under the encoder body
         moments = self._moments(x, wvs)
         posterior = DiagonalGaussianDistribution(moments)
         plain = scale is None and angle is None and not self.training

@@ -37,6 +37,7 @@ def set_tuning(key: int, value: int) -> None:
 
 
 TUNE_GN_APPLY_CORESIDENT = 1
+TUNE_GN_BWD_FUSED = 2
 
 
 def launch_count() -> int:

@@ -3,8 +3,6 @@
 // Data gradients of the convolutions reuse the implicit-GEMM kernel with transposed / flipped weight operands
 // (eovae_pack_conv_weight_dgrad); weight gradients are in wgrad_sm100.cu.
 #include "../../include/eovae.h"
-#include <cstdlib>
-
 #include "common.cuh"
 
 int g_gn_bwd_fused_knob = 1;  // eovae_set_tuning(EOVAE_TUNE_GN_BWD_FUSED, 0) restores the two-pass kernels (A/B measurements)
@@ -909,9 +907,6 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
     EOVAE_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&gn_bwd_fused_kernel<T, TG, S>), dim3(fgrid),  \
                                            dim3(threads), args, fsmem, stream));                                       \
   } while (0)
-    if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_F(__nv_bfloat16, __nv_bfloat16, true); else EOVAE_GNB_F(__nv_bfloat16, __nv_bfloat16, false); }
-    else if (grad_dtype == EOVAE_F16) { if (with_silu) EOVAE_GNB_F(__half, __half, true); else EOVAE_GNB_F(__half, __half, false); }
-    else { if (with_silu) EOVAE_GNB_F(__half, __nv_bfloat16, true); else EOVAE_GNB_F(__half, __nv_bfloat16, false); }
 #undef EOVAE_GNB_F
     EOVAE_LAUNCH_CHECK();
     if (dgamma != nullptr && dbeta != nullptr) {

@@ -292,12 +292,13 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
 
 // ---------------------------------------------------------------------------------------------------------------------
 // FUSED GroupNorm(+SiLU) backward: the two passes above read x and g TWICE from HBM (5 tensor passes for 3 algorithmic ones;
-// measured 4.2 TB/s of actual traffic = 0.33-0.5 of the algorithmic rate).  Here one persistent, fully resident grid walks
-// the batch in ROUNDS of `ipr` images (bpi blocks per image, grid = ipr * bpi): pass A (per-block sums, x and g from HBM)
-// of round R + 1 is issued BEFORE the blocks meet for round R, so nobody waits at the rendezvous, and pass B of round R
-// then re-reads x and g while they are still in L2 (two rounds = ~64 MB in flight; bpi / ipr are sized for that) - HBM sees
-// x and g once and dx once.  Deterministic: fixed-slot partials and fixed summation orders (every block of an image
-// recomputes the 32 group sums from the per-block group partials, 64 floats per block).
+// measured 4.2 TB/s of actual traffic = 0.33-0.5 of the algorithmic rate).  Here one persistent grid walks the images in
+// order; the `bpi` blocks that share an image reduce their pixel ranges (pass A, x and g from HBM), meet at a per-image
+// counter, and then apply (pass B) over the SAME ranges while the image's x and g are still in L2: the grid keeps only
+// ~64 MB of tensor data in flight (bpi is sized for that), so pass B reads hit L2 and HBM sees x, g once and dx once.
+// Deterministic: fixed-slot partials, fixed summation order; every block of an image recomputes the 32 group sums from
+// the per-block group partials (64 floats per block).  Deadlock-free: the grid is sized to be fully resident and every
+// block takes its items in increasing order, so all blocks of the oldest unfinished image are always running.
 template <typename T, typename TG, bool SILU>
 __global__ void __launch_bounds__(kThreads, 2) gn_bwd_fused_kernel(
     const T* __restrict__ x, const TG* __restrict__ g, const float* __restrict__ stats, const float* __restrict__ gamma,
@@ -310,37 +311,34 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_fused_kernel(
   const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
   const int cpg = c / groups;
   float* sm_gs = sm + 2 * rows * c;  // [groups][2]
-  const int ipr = gridDim.x / bpi;                       // images per round
-  const int img_in_round = blockIdx.x / bpi, j = blockIdx.x % bpi;
-  const int rounds = (n_img + ipr - 1) / ipr;
-  const long long p0 = static_cast<long long>(j) * pix_per_block;
-  long long p1 = p0 + pix_per_block;
-  if (p1 > hw) p1 = hw;
-  float rs[8], nm[8], za[8], zb[8], ea[8], eb[8];
-  auto load_consts = [&](int n) {  // xhat = x * rs + nm, z = x * za + zb, z / 2 = x * ea + eb
+  const long long total_items = static_cast<long long>(n_img) * bpi;
+  for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int n = static_cast<int>(item / bpi), j = static_cast<int>(item % bpi);
+    const long long p0 = static_cast<long long>(j) * pix_per_block;
+    long long p1 = p0 + pix_per_block;
+    if (p1 > hw) p1 = hw;
+    // per-channel constants: xhat = x * rs + nm, z = x * za + zb, z / 2 = x * ea + eb
+    float rs[8], nm[8], za[8], zb[8], ea[8], eb[8];
+    if (r < rows) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int ch = v * 8 + q, gi = ch / cpg;
-      const float mean = stats[(n * groups + gi) * 2], rstd = stats[(n * groups + gi) * 2 + 1];
-      rs[q] = rstd;
-      nm[q] = -mean * rstd;
-      za[q] = rstd * gamma[ch];
-      zb[q] = fmaf(-mean, za[q], beta[ch]);
-      ea[q] = 0.5f * za[q];
-      eb[q] = 0.5f * zb[q];
+      for (int q = 0; q < 8; ++q) {
+        const int ch = v * 8 + q, gi = ch / cpg;
+        const float mean = stats[(n * groups + gi) * 2], rstd = stats[(n * groups + gi) * 2 + 1];
+        rs[q] = rstd;
+        nm[q] = -mean * rstd;
+        za[q] = rstd * gamma[ch];
+        zb[q] = fmaf(-mean, za[q], beta[ch]);
+        ea[q] = 0.5f * za[q];
+        eb[q] = 0.5f * zb[q];
+      }
     }
-  };
-  for (int R = 0; R <= rounds; ++R) {
-    // ---------------- pass A of round R: per-channel sums A = sum dz, B = sum dz * xhat over this block's pixels
-    const int nA = R * ipr + img_in_round;
-    if (R < rounds && nA < n_img) {
-      const long long item = static_cast<long long>(nA) * bpi + j;
-      const long long base = (static_cast<long long>(nA) * hw) * c + v * 8;
+    const long long base = (static_cast<long long>(n) * hw) * c + v * 8;
+    // ---------------- pass A: per-channel sums A = sum dz, B = sum dz * xhat over this block's pixels
+    {
       float sa[8], sb[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) sa[q] = sb[q] = 0.f;
       if (r < rows) {
-        load_consts(nA);
         auto accum = [&](const uint4& ux, const uint4& ug) {
           const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
 #pragma unroll
@@ -378,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_fused_kernel(
       }
       __syncthreads();
       // block totals per channel -> chpart (for dgamma / dbeta), and gamma-weighted per group -> gpart
-      float* cp = chpart + (item * c) * 2;
+      float* cp = chpart + (static_cast<long long>(item) * c) * 2;
       for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
         float a = 0.f, b = 0.f;
         for (int rr = 0; rr < rows; ++rr) {
@@ -387,11 +385,11 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_fused_kernel(
         }
         cp[2 * ch] = a;
         cp[2 * ch + 1] = b;
-        sm[ch] = a * gamma[ch];          // row 0 of the scratch is free again (each ch slot is written by its only reader)
+        sm[ch] = a * gamma[ch];          // row 0 of the scratch is free again (each ch slot written by its own reader)
         sm[c + ch] = b * gamma[ch];
       }
       __syncthreads();
-      float* gp = gpart + item * groups * 2;
+      float* gp = gpart + static_cast<long long>(item) * groups * 2;
       for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
         float s1 = 0.f, s2 = 0.f;
         for (int q = 0; q < cpg; ++q) {
@@ -403,14 +401,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_fused_kernel(
       }
       __threadfence();
       __syncthreads();
-      if (threadIdx.x == 0) atomicAdd(&counters[nA], 1u);   // this block's share of image nA is published
-    }
-    // ---------------- pass B of round R - 1: meet the other blocks of the image (they finished pass A a full round ago)
-    const int n = (R - 1) * ipr + img_in_round;
-    if (R >= 1 && n < n_img) {
-      const long long item = static_cast<long long>(n) * bpi + j;
-      const long long base = (static_cast<long long>(n) * hw) * c + v * 8;
       if (threadIdx.x == 0) {
+        atomicAdd(&counters[n], 1u);
+        // ---------------- meet the other blocks of this image
         unsigned int seen = 0, spins = 0;
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counters + n) : "memory");
@@ -421,101 +414,99 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_fused_kernel(
         } while (seen < static_cast<unsigned int>(bpi));
       }
       __syncthreads();
-      // group sums of the whole image: fixed order over the bpi blocks (every block computes the same bits)
-      {
-        const float* gp = gpart + static_cast<long long>(n) * bpi * groups * 2;
-        const int slots = groups * 2;                       // 64 values
-        const int parts = blockDim.x / slots;               // k-ranges summed in parallel, combined in order below
-        const int per = (bpi + parts - 1) / parts;
-        if (static_cast<int>(threadIdx.x) < slots * parts) {
-          const int slot = threadIdx.x % slots, part = threadIdx.x / slots;
-          const int k0 = part * per;
-          int k1 = k0 + per;
-          if (k1 > bpi) k1 = bpi;
-          float acc = 0.f;
-          for (int k = k0; k < k1; ++k) acc += __ldcg(gp + static_cast<long long>(k) * slots + slot);
-          sm[part * slots + slot] = acc;
-        }
-        __syncthreads();
-        if (static_cast<int>(threadIdx.x) < slots) {
-          float acc = 0.f;
-          for (int part = 0; part < parts; ++part) acc += sm[part * slots + threadIdx.x];
-          sm_gs[threadIdx.x] = acc;
-        }
-        __syncthreads();
+    }
+    // ---------------- group sums of the whole image: fixed order over the bpi blocks (every block computes the same bits)
+    {
+      const float* gp = gpart + static_cast<long long>(n) * bpi * groups * 2;
+      const int slots = groups * 2;                       // 64 values
+      const int parts = blockDim.x / slots;               // k-ranges summed in parallel, combined in order below
+      if (static_cast<int>(threadIdx.x) < slots * parts) {
+        const int slot = threadIdx.x % slots, part = threadIdx.x / slots;
+        const int k0 = part * ((bpi + parts - 1) / parts);
+        int k1 = k0 + (bpi + parts - 1) / parts;
+        if (k1 > bpi) k1 = bpi;
+        float acc = 0.f;
+        for (int k = k0; k < k1; ++k) acc += __ldcg(gp + static_cast<long long>(k) * slots + slot);
+        sm[part * slots + slot] = acc;
       }
-      // dx = dz * za - c1 - xhat * c2 (+ add), x and g out of L2
-      float cs[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) cs[q] = 0.f;
-      if (r < rows) {
-        load_consts(n);
-        const float inv_m = 1.0f / (static_cast<float>(hw) * cpg);
-        float c1[8], c2[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int gi = (v * 8 + q) / cpg;
-          c1[q] = rs[q] * sm_gs[2 * gi] * inv_m;
-          c2[q] = rs[q] * sm_gs[2 * gi + 1] * inv_m;
-        }
-        auto compute = [&](const uint4& ux, const uint4& ug, const uint4& ua) {
-          const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w}, wa[4] = {ua.x, ua.y, ua.z, ua.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 fx = T16<T>::to_f2(wx[q]), fg = T16<TG>::to_f2(wg[q]);
-            float2 fa = make_float2(0.f, 0.f);
-            if (add != nullptr) fa = T16<TG>::to_f2(wa[q]);
-            const float xh0 = fmaf(fx.x, rs[2 * q], nm[2 * q]), xh1 = fmaf(fx.y, rs[2 * q + 1], nm[2 * q + 1]);
-            float d0 = fg.x, d1 = fg.y;
-            if (SILU) {
-              d0 *= silu_grad2(fmaf(fx.x, za[2 * q], zb[2 * q]), fmaf(fx.x, ea[2 * q], eb[2 * q]));
-              d1 *= silu_grad2(fmaf(fx.y, za[2 * q + 1], zb[2 * q + 1]), fmaf(fx.y, ea[2 * q + 1], eb[2 * q + 1]));
-            }
-            const float r0 = fmaf(-xh0, c2[2 * q], fmaf(d0, za[2 * q], fa.x - c1[2 * q]));
-            const float r1 = fmaf(-xh1, c2[2 * q + 1], fmaf(d1, za[2 * q + 1], fa.y - c1[2 * q + 1]));
-            cs[2 * q] += r0;
-            cs[2 * q + 1] += r1;
-            o[q] = T16<TG>::from_f2(r0, r1);
-          }
-          return make_uint4(o[0], o[1], o[2], o[3]);
-        };
-        const uint4 zero4 = make_uint4(0, 0, 0, 0);
-        long long p = p0 + r;
-        for (; p + rows < p1; p += 2LL * rows) {
-          const long long o0 = base + p * c, o1 = base + (p + rows) * c;
-          const uint4 ux0 = __ldcg(reinterpret_cast<const uint4*>(x + o0)), ug0 = __ldcg(reinterpret_cast<const uint4*>(g + o0));
-          const uint4 ux1 = __ldcg(reinterpret_cast<const uint4*>(x + o1)), ug1 = __ldcg(reinterpret_cast<const uint4*>(g + o1));
-          uint4 ua0 = zero4, ua1 = zero4;
-          if (add != nullptr) {
-            ua0 = __ldcs(reinterpret_cast<const uint4*>(add + o0));
-            ua1 = __ldcs(reinterpret_cast<const uint4*>(add + o1));
-          }
-          __stcs(reinterpret_cast<uint4*>(dx + o0), compute(ux0, ug0, ua0));
-          __stcs(reinterpret_cast<uint4*>(dx + o1), compute(ux1, ug1, ua1));
-        }
-        for (; p < p1; p += rows) {
-          const long long o0 = base + p * c;
-          const uint4 ua0 = add != nullptr ? __ldcs(reinterpret_cast<const uint4*>(add + o0)) : zero4;
-          __stcs(reinterpret_cast<uint4*>(dx + o0),
-                 compute(__ldcg(reinterpret_cast<const uint4*>(x + o0)), __ldcg(reinterpret_cast<const uint4*>(g + o0)), ua0));
-        }
+      __syncthreads();
+      if (static_cast<int>(threadIdx.x) < slots) {
+        float acc = 0.f;
+        for (int part = 0; part < parts; ++part) acc += sm[part * slots + threadIdx.x];
+        sm_gs[threadIdx.x] = acc;
       }
-      if (colpart != nullptr) {
-        __syncthreads();  // sm_gs reads are done for every thread before the scratch is reused
-        if (r < rows) {
+      __syncthreads();
+    }
+    // ---------------- pass B: dx = dz * za - c1 - xhat * c2 (+ add), x and g from L2
+    float cs[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) sm[r * c + v * 8 + q] = cs[q];
+    for (int q = 0; q < 8; ++q) cs[q] = 0.f;
+    if (r < rows) {
+      const float inv_m = 1.0f / (static_cast<float>(hw) * cpg);
+      float c1[8], c2[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int gi = (v * 8 + q) / cpg;
+        c1[q] = rs[q] * sm_gs[2 * gi] * inv_m;
+        c2[q] = rs[q] * sm_gs[2 * gi + 1] * inv_m;
+      }
+      auto compute = [&](const uint4& ux, const uint4& ug, const uint4& ua) {
+        const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w}, wa[4] = {ua.x, ua.y, ua.z, ua.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fx = T16<T>::to_f2(wx[q]), fg = T16<TG>::to_f2(wg[q]);
+          float2 fa = make_float2(0.f, 0.f);
+          if (add != nullptr) fa = T16<TG>::to_f2(wa[q]);
+          const float xh0 = fmaf(fx.x, rs[2 * q], nm[2 * q]), xh1 = fmaf(fx.y, rs[2 * q + 1], nm[2 * q + 1]);
+          float d0 = fg.x, d1 = fg.y;
+          if (SILU) {
+            d0 *= silu_grad2(fmaf(fx.x, za[2 * q], zb[2 * q]), fmaf(fx.x, ea[2 * q], eb[2 * q]));
+            d1 *= silu_grad2(fmaf(fx.y, za[2 * q + 1], zb[2 * q + 1]), fmaf(fx.y, ea[2 * q + 1], eb[2 * q + 1]));
+          }
+          const float r0 = fmaf(-xh0, c2[2 * q], fmaf(d0, za[2 * q], fa.x - c1[2 * q]));
+          const float r1 = fmaf(-xh1, c2[2 * q + 1], fmaf(d1, za[2 * q + 1], fa.y - c1[2 * q + 1]));
+          cs[2 * q] += r0;
+          cs[2 * q + 1] += r1;
+          o[q] = T16<TG>::from_f2(r0, r1);
         }
-        __syncthreads();
-        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-          float a = 0.f;
-          for (int rr = 0; rr < rows; ++rr) a += sm[rr * c + ch];
-          colpart[item * c + ch] = a;
+        return make_uint4(o[0], o[1], o[2], o[3]);
+      };
+      const uint4 zero4 = make_uint4(0, 0, 0, 0);
+      long long p = p0 + r;
+      for (; p + rows < p1; p += 2LL * rows) {
+        const long long o0 = base + p * c, o1 = base + (p + rows) * c;
+        const uint4 ux0 = __ldcg(reinterpret_cast<const uint4*>(x + o0)), ug0 = __ldcg(reinterpret_cast<const uint4*>(g + o0));
+        const uint4 ux1 = __ldcg(reinterpret_cast<const uint4*>(x + o1)), ug1 = __ldcg(reinterpret_cast<const uint4*>(g + o1));
+        uint4 ua0 = zero4, ua1 = zero4;
+        if (add != nullptr) {
+          ua0 = __ldcs(reinterpret_cast<const uint4*>(add + o0));
+          ua1 = __ldcs(reinterpret_cast<const uint4*>(add + o1));
         }
+        __stcs(reinterpret_cast<uint4*>(dx + o0), compute(ux0, ug0, ua0));
+        __stcs(reinterpret_cast<uint4*>(dx + o1), compute(ux1, ug1, ua1));
+      }
+      for (; p < p1; p += rows) {
+        const long long o0 = base + p * c;
+        const uint4 ua0 = add != nullptr ? __ldcs(reinterpret_cast<const uint4*>(add + o0)) : zero4;
+        __stcs(reinterpret_cast<uint4*>(dx + o0),
+               compute(__ldcg(reinterpret_cast<const uint4*>(x + o0)), __ldcg(reinterpret_cast<const uint4*>(g + o0)), ua0));
       }
     }
-    __syncthreads();  // the scratch is reused by the next round
+    if (colpart != nullptr) {
+      __syncthreads();  // sm_gs reads are done for every thread before the scratch is reused
+      if (r < rows) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sm[r * c + v * 8 + q] = cs[q];
+      }
+      __syncthreads();
+      for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float a = 0.f;
+        for (int rr = 0; rr < rows; ++rr) a += sm[rr * c + ch];
+        colpart[static_cast<long long>(item) * c + ch] = a;
+      }
+    }
+    __syncthreads();  // the scratch is reused by the next item
   }
 }
 
@@ -546,25 +537,21 @@ __global__ void gn_bwd_param_fused_kernel(const float* __restrict__ chpart, long
 }
 
 
-// fused kernel plan: `ipr` images per round x `bpi` blocks per image = the grid (<= 2 blocks / SM, fully resident); two rounds
-// (the one in pass A and the one waiting for pass B) keep ~64 MB of (x, g) in flight
+// blocks per image of the fused kernel: the resident grid (2 blocks / SM) keeps ~64 MB of (x, g) in flight
 void fused_plan(int n, long long hw, int c, int rows, int* grid, int* bpi, int* ppb) {
   const int G = 2 * eovae_num_sms();
   const double img_bytes = 2.0 * static_cast<double>(hw) * c * 2.0;
-  int ipr = static_cast<int>(32.0 * 1048576.0 / img_bytes);
-  if (ipr < 1) ipr = 1;
-  if (ipr > n) ipr = n;
-  long long b = G / ipr;
-  const long long max_b = (hw + rows - 1) / rows;   // at least `rows` pixels per block
-  if (b > max_b) b = max_b;
+  long long b = static_cast<long long>(G * img_bytes / (64.0 * 1048576.0) + 0.999);
   if (b < 1) b = 1;
+  if (b > G) b = G;
   long long per = (hw + b - 1) / b;
   per = (per + rows - 1) / rows * rows;
+  if (per < rows) per = rows;
   b = (hw + per - 1) / per;
   *bpi = static_cast<int>(b);
   *ppb = static_cast<int>(per);
-  if (static_cast<long long>(ipr) * b > G) ipr = static_cast<int>(G / b);
-  *grid = static_cast<int>(ipr * b);
+  const long long items = static_cast<long long>(n) * b;
+  *grid = static_cast<int>(items < G ? items : G);
 }
 
 void bwd_grid(long long hw, int c, int rows, int* bpi, int* ppb) {
@@ -879,7 +866,7 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
   const bool pair_ok = (dtype == EOVAE_BF16 && grad_dtype == EOVAE_BF16) || (dtype == EOVAE_F16 && grad_dtype == EOVAE_F16) ||
                        (dtype == EOVAE_F16 && grad_dtype == EOVAE_BF16);
   if (g_gn_bwd_fused_knob && grad_x != nullptr && pair_ok && static_cast<long long>(n) * hw * c >= (1LL << 21) && threads >= 2 * groups &&
-      sizeof(float) * (2 * static_cast<size_t>(c) * rows + 2 * groups) <= 100 * 1024) {
+      sizeof(float) * (2 * static_cast<size_t>(c) * rows + 2 * groups) <= 200 * 1024) {
     // fused single-kernel path (see gn_bwd_fused_kernel): x and g from HBM once
     int fgrid;
     fused_plan(n, hw, c, rows, &fgrid, &bpi, &ppb);
@@ -890,23 +877,21 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
     unsigned int* counters = reinterpret_cast<unsigned int*>(colpart + items * c);
     EOVAE_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * n, stream));
     const size_t fsmem = sizeof(float) * (2 * static_cast<size_t>(c) * rows + 2 * groups);
-    // cooperative launch: the runtime starts the grid only when ALL of its blocks can be resident at once, which is what the
-    // per-image rendezvous needs (an ordinary launch next to a long-running kernel of another stream could leave waiting
-    // blocks holding every free slot)
-    const void* xp = x; const void* gp_ = grad_out; const void* addp = grad_add; void* dxp = grad_x;
-    float* colp = grad_x_colsum ? colpart : nullptr;
-    void* args[] = {&xp, &gp_, &stats, &gamma, &beta, &addp, &dxp, &n, &hw, &c, &groups, &bpi, &ppb, &chpart, &gpart, &colp, &counters};
 #define EOVAE_GNB_F(T, TG, S)                                                                                          \
   do {                                                                                                                 \
     static bool attr = false;                                                                                          \
     if (!attr) {                                                                                                       \
       EOVAE_CUDA(cudaFuncSetAttribute(gn_bwd_fused_kernel<T, TG, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                      100 * 1024));                                                                    \
+                                      200 * 1024));                                                                    \
       attr = true;                                                                                                     \
     }                                                                                                                  \
-    EOVAE_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&gn_bwd_fused_kernel<T, TG, S>), dim3(fgrid),  \
-                                           dim3(threads), args, fsmem, stream));                                       \
+    gn_bwd_fused_kernel<T, TG, S><<<fgrid, threads, fsmem, stream>>>(                                                  \
+        static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, static_cast<const TG*>(grad_add), \
+        static_cast<TG*>(grad_x), n, hw, c, groups, bpi, ppb, chpart, gpart, grad_x_colsum ? colpart : nullptr, counters); \
   } while (0)
+    if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_F(__nv_bfloat16, __nv_bfloat16, true); else EOVAE_GNB_F(__nv_bfloat16, __nv_bfloat16, false); }
+    else if (grad_dtype == EOVAE_F16) { if (with_silu) EOVAE_GNB_F(__half, __half, true); else EOVAE_GNB_F(__half, __half, false); }
+    else { if (with_silu) EOVAE_GNB_F(__half, __nv_bfloat16, true); else EOVAE_GNB_F(__half, __nv_bfloat16, false); }
 #undef EOVAE_GNB_F
     EOVAE_LAUNCH_CHECK();
     if (dgamma != nullptr && dbeta != nullptr) {

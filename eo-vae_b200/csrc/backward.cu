@@ -5,8 +5,6 @@
 #include "../../include/eovae.h"
 #include "common.cuh"
 
-int g_gn_bwd_fused_knob = 1;  // eovae_set_tuning(EOVAE_TUNE_GN_BWD_FUSED, 0) restores the two-pass kernels (A/B measurements)
-
 namespace {
 
 constexpr int kThreads = 256;
@@ -288,270 +286,6 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
     for (int rr = 0; rr < rows; ++rr) a += sm_cs[rr * c + ch];
     colpart[(static_cast<long long>(n) * gridDim.x + blockIdx.x) * c + ch] = a;
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// FUSED GroupNorm(+SiLU) backward: the two passes above read x and g TWICE from HBM (5 tensor passes for 3 algorithmic ones;
-// measured 4.2 TB/s of actual traffic = 0.33-0.5 of the algorithmic rate).  Here one persistent grid walks the images in
-// order; the `bpi` blocks that share an image reduce their pixel ranges (pass A, x and g from HBM), meet at a per-image
-// counter, and then apply (pass B) over the SAME ranges while the image's x and g are still in L2: the grid keeps only
-// ~64 MB of tensor data in flight (bpi is sized for that), so pass B reads hit L2 and HBM sees x, g once and dx once.
-// Deterministic: fixed-slot partials, fixed summation order; every block of an image recomputes the 32 group sums from
-// the per-block group partials (64 floats per block).  Deadlock-free: the grid is sized to be fully resident and every
-// block takes its items in increasing order, so all blocks of the oldest unfinished image are always running.
-template <typename T, typename TG, bool SILU>
-__global__ void __launch_bounds__(kThreads, 2) gn_bwd_fused_kernel(
-    const T* __restrict__ x, const TG* __restrict__ g, const float* __restrict__ stats, const float* __restrict__ gamma,
-    const float* __restrict__ beta, const TG* __restrict__ add, TG* __restrict__ dx, int n_img, long long hw, int c, int groups,
-    int bpi, int pix_per_block, float* __restrict__ chpart /*[n][bpi][c][2]*/, float* __restrict__ gpart /*[n][bpi][groups][2]*/,
-    float* __restrict__ colpart /*[n][bpi][c] or null*/, unsigned int* __restrict__ counters /*[n], zeroed*/) {
-  extern __shared__ float sm[];  // [rows][2][c] block reduction scratch, then [groups][2] group sums at sm_gs
-  const int vpp = c >> 3;
-  const int rows = blockDim.x / vpp;
-  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
-  const int cpg = c / groups;
-  float* sm_gs = sm + 2 * rows * c;  // [groups][2]
-  const long long total_items = static_cast<long long>(n_img) * bpi;
-  for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-    const int n = static_cast<int>(item / bpi), j = static_cast<int>(item % bpi);
-    const long long p0 = static_cast<long long>(j) * pix_per_block;
-    long long p1 = p0 + pix_per_block;
-    if (p1 > hw) p1 = hw;
-    // per-channel constants: xhat = x * rs + nm, z = x * za + zb, z / 2 = x * ea + eb
-    float rs[8], nm[8], za[8], zb[8], ea[8], eb[8];
-    if (r < rows) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int ch = v * 8 + q, gi = ch / cpg;
-        const float mean = stats[(n * groups + gi) * 2], rstd = stats[(n * groups + gi) * 2 + 1];
-        rs[q] = rstd;
-        nm[q] = -mean * rstd;
-        za[q] = rstd * gamma[ch];
-        zb[q] = fmaf(-mean, za[q], beta[ch]);
-        ea[q] = 0.5f * za[q];
-        eb[q] = 0.5f * zb[q];
-      }
-    }
-    const long long base = (static_cast<long long>(n) * hw) * c + v * 8;
-    // ---------------- pass A: per-channel sums A = sum dz, B = sum dz * xhat over this block's pixels
-    {
-      float sa[8], sb[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) sa[q] = sb[q] = 0.f;
-      if (r < rows) {
-        auto accum = [&](const uint4& ux, const uint4& ug) {
-          const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 fx = T16<T>::to_f2(wx[q]), fg = T16<TG>::to_f2(wg[q]);
-            const float xh0 = fmaf(fx.x, rs[2 * q], nm[2 * q]), xh1 = fmaf(fx.y, rs[2 * q + 1], nm[2 * q + 1]);
-            float d0 = fg.x, d1 = fg.y;
-            if (SILU) {
-              d0 *= silu_grad2(fmaf(fx.x, za[2 * q], zb[2 * q]), fmaf(fx.x, ea[2 * q], eb[2 * q]));
-              d1 *= silu_grad2(fmaf(fx.y, za[2 * q + 1], zb[2 * q + 1]), fmaf(fx.y, ea[2 * q + 1], eb[2 * q + 1]));
-            }
-            sa[2 * q] += d0; sb[2 * q] = fmaf(d0, xh0, sb[2 * q]);
-            sa[2 * q + 1] += d1; sb[2 * q + 1] = fmaf(d1, xh1, sb[2 * q + 1]);
-          }
-        };
-        long long p = p0 + r;
-        for (; p + 3LL * rows < p1; p += 4LL * rows) {
-          const uint4 ux0 = __ldg(reinterpret_cast<const uint4*>(x + base + p * c));
-          const uint4 ug0 = __ldg(reinterpret_cast<const uint4*>(g + base + p * c));
-          const uint4 ux1 = __ldg(reinterpret_cast<const uint4*>(x + base + (p + rows) * c));
-          const uint4 ug1 = __ldg(reinterpret_cast<const uint4*>(g + base + (p + rows) * c));
-          const uint4 ux2 = __ldg(reinterpret_cast<const uint4*>(x + base + (p + 2LL * rows) * c));
-          const uint4 ug2 = __ldg(reinterpret_cast<const uint4*>(g + base + (p + 2LL * rows) * c));
-          const uint4 ux3 = __ldg(reinterpret_cast<const uint4*>(x + base + (p + 3LL * rows) * c));
-          const uint4 ug3 = __ldg(reinterpret_cast<const uint4*>(g + base + (p + 3LL * rows) * c));
-          accum(ux0, ug0); accum(ux1, ug1); accum(ux2, ug2); accum(ux3, ug3);
-        }
-        for (; p < p1; p += rows)
-          accum(__ldg(reinterpret_cast<const uint4*>(x + base + p * c)), __ldg(reinterpret_cast<const uint4*>(g + base + p * c)));
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          sm[(r * 2) * c + v * 8 + q] = sa[q];
-          sm[(r * 2 + 1) * c + v * 8 + q] = sb[q];
-        }
-      }
-      __syncthreads();
-      // block totals per channel -> chpart (for dgamma / dbeta), and gamma-weighted per group -> gpart
-      float* cp = chpart + (static_cast<long long>(item) * c) * 2;
-      for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-        float a = 0.f, b = 0.f;
-        for (int rr = 0; rr < rows; ++rr) {
-          a += sm[(rr * 2) * c + ch];
-          b += sm[(rr * 2 + 1) * c + ch];
-        }
-        cp[2 * ch] = a;
-        cp[2 * ch + 1] = b;
-        sm[ch] = a * gamma[ch];          // row 0 of the scratch is free again (each ch slot written by its own reader)
-        sm[c + ch] = b * gamma[ch];
-      }
-      __syncthreads();
-      float* gp = gpart + static_cast<long long>(item) * groups * 2;
-      for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int q = 0; q < cpg; ++q) {
-          s1 += sm[gi * cpg + q];
-          s2 += sm[c + gi * cpg + q];
-        }
-        gp[2 * gi] = s1;
-        gp[2 * gi + 1] = s2;
-      }
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        atomicAdd(&counters[n], 1u);
-        // ---------------- meet the other blocks of this image
-        unsigned int seen = 0, spins = 0;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counters + n) : "memory");
-          if (seen < static_cast<unsigned int>(bpi)) {
-            __nanosleep(64);
-            if (++spins > (1u << 24)) __trap();  // a scheduling assumption broke: fail loudly instead of hanging the GPU
-          }
-        } while (seen < static_cast<unsigned int>(bpi));
-      }
-      __syncthreads();
-    }
-    // ---------------- group sums of the whole image: fixed order over the bpi blocks (every block computes the same bits)
-    {
-      const float* gp = gpart + static_cast<long long>(n) * bpi * groups * 2;
-      const int slots = groups * 2;                       // 64 values
-      const int parts = blockDim.x / slots;               // k-ranges summed in parallel, combined in order below
-      if (static_cast<int>(threadIdx.x) < slots * parts) {
-        const int slot = threadIdx.x % slots, part = threadIdx.x / slots;
-        const int k0 = part * ((bpi + parts - 1) / parts);
-        int k1 = k0 + (bpi + parts - 1) / parts;
-        if (k1 > bpi) k1 = bpi;
-        float acc = 0.f;
-        for (int k = k0; k < k1; ++k) acc += __ldcg(gp + static_cast<long long>(k) * slots + slot);
-        sm[part * slots + slot] = acc;
-      }
-      __syncthreads();
-      if (static_cast<int>(threadIdx.x) < slots) {
-        float acc = 0.f;
-        for (int part = 0; part < parts; ++part) acc += sm[part * slots + threadIdx.x];
-        sm_gs[threadIdx.x] = acc;
-      }
-      __syncthreads();
-    }
-    // ---------------- pass B: dx = dz * za - c1 - xhat * c2 (+ add), x and g from L2
-    float cs[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) cs[q] = 0.f;
-    if (r < rows) {
-      const float inv_m = 1.0f / (static_cast<float>(hw) * cpg);
-      float c1[8], c2[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int gi = (v * 8 + q) / cpg;
-        c1[q] = rs[q] * sm_gs[2 * gi] * inv_m;
-        c2[q] = rs[q] * sm_gs[2 * gi + 1] * inv_m;
-      }
-      auto compute = [&](const uint4& ux, const uint4& ug, const uint4& ua) {
-        const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w}, wa[4] = {ua.x, ua.y, ua.z, ua.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 fx = T16<T>::to_f2(wx[q]), fg = T16<TG>::to_f2(wg[q]);
-          float2 fa = make_float2(0.f, 0.f);
-          if (add != nullptr) fa = T16<TG>::to_f2(wa[q]);
-          const float xh0 = fmaf(fx.x, rs[2 * q], nm[2 * q]), xh1 = fmaf(fx.y, rs[2 * q + 1], nm[2 * q + 1]);
-          float d0 = fg.x, d1 = fg.y;
-          if (SILU) {
-            d0 *= silu_grad2(fmaf(fx.x, za[2 * q], zb[2 * q]), fmaf(fx.x, ea[2 * q], eb[2 * q]));
-            d1 *= silu_grad2(fmaf(fx.y, za[2 * q + 1], zb[2 * q + 1]), fmaf(fx.y, ea[2 * q + 1], eb[2 * q + 1]));
-          }
-          const float r0 = fmaf(-xh0, c2[2 * q], fmaf(d0, za[2 * q], fa.x - c1[2 * q]));
-          const float r1 = fmaf(-xh1, c2[2 * q + 1], fmaf(d1, za[2 * q + 1], fa.y - c1[2 * q + 1]));
-          cs[2 * q] += r0;
-          cs[2 * q + 1] += r1;
-          o[q] = T16<TG>::from_f2(r0, r1);
-        }
-        return make_uint4(o[0], o[1], o[2], o[3]);
-      };
-      const uint4 zero4 = make_uint4(0, 0, 0, 0);
-      long long p = p0 + r;
-      for (; p + rows < p1; p += 2LL * rows) {
-        const long long o0 = base + p * c, o1 = base + (p + rows) * c;
-        const uint4 ux0 = __ldcg(reinterpret_cast<const uint4*>(x + o0)), ug0 = __ldcg(reinterpret_cast<const uint4*>(g + o0));
-        const uint4 ux1 = __ldcg(reinterpret_cast<const uint4*>(x + o1)), ug1 = __ldcg(reinterpret_cast<const uint4*>(g + o1));
-        uint4 ua0 = zero4, ua1 = zero4;
-        if (add != nullptr) {
-          ua0 = __ldcs(reinterpret_cast<const uint4*>(add + o0));
-          ua1 = __ldcs(reinterpret_cast<const uint4*>(add + o1));
-        }
-        __stcs(reinterpret_cast<uint4*>(dx + o0), compute(ux0, ug0, ua0));
-        __stcs(reinterpret_cast<uint4*>(dx + o1), compute(ux1, ug1, ua1));
-      }
-      for (; p < p1; p += rows) {
-        const long long o0 = base + p * c;
-        const uint4 ua0 = add != nullptr ? __ldcs(reinterpret_cast<const uint4*>(add + o0)) : zero4;
-        __stcs(reinterpret_cast<uint4*>(dx + o0),
-               compute(__ldcg(reinterpret_cast<const uint4*>(x + o0)), __ldcg(reinterpret_cast<const uint4*>(g + o0)), ua0));
-      }
-    }
-    if (colpart != nullptr) {
-      __syncthreads();  // sm_gs reads are done for every thread before the scratch is reused
-      if (r < rows) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) sm[r * c + v * 8 + q] = cs[q];
-      }
-      __syncthreads();
-      for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-        float a = 0.f;
-        for (int rr = 0; rr < rows; ++rr) a += sm[rr * c + ch];
-        colpart[static_cast<long long>(item) * c + ch] = a;
-      }
-    }
-    __syncthreads();  // the scratch is reused by the next item
-  }
-}
-
-// dgamma[c] (+)= sum over (image, block) of B, dbeta[c] (+)= sum of A, from the fused kernel's per-block channel partials
-__global__ void gn_bwd_param_fused_kernel(const float* __restrict__ chpart, long long items, int c, float* __restrict__ dgamma,
-                                          float* __restrict__ dbeta, int accumulate) {
-  __shared__ double ra[8][32], rb[8][32];
-  const int ch = blockIdx.x * 32 + threadIdx.x;
-  double a = 0.0, b = 0.0;
-  if (ch < c)
-    for (long long i = threadIdx.y; i < items; i += 8) {
-      a += chpart[(i * c + ch) * 2];
-      b += chpart[(i * c + ch) * 2 + 1];
-    }
-  ra[threadIdx.y][threadIdx.x] = a;
-  rb[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.y == 0 && ch < c) {
-    double ta = 0.0, tb = 0.0;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) {
-      ta += ra[y][threadIdx.x];
-      tb += rb[y][threadIdx.x];
-    }
-    dbeta[ch] = (accumulate ? dbeta[ch] : 0.f) + static_cast<float>(ta);
-    dgamma[ch] = (accumulate ? dgamma[ch] : 0.f) + static_cast<float>(tb);
-  }
-}
-
-
-// blocks per image of the fused kernel: the resident grid (2 blocks / SM) keeps ~64 MB of (x, g) in flight
-void fused_plan(int n, long long hw, int c, int rows, int* grid, int* bpi, int* ppb) {
-  const int G = 2 * eovae_num_sms();
-  const double img_bytes = 2.0 * static_cast<double>(hw) * c * 2.0;
-  long long b = static_cast<long long>(G * img_bytes / (64.0 * 1048576.0) + 0.999);
-  if (b < 1) b = 1;
-  if (b > G) b = G;
-  long long per = (hw + b - 1) / b;
-  per = (per + rows - 1) / rows * rows;
-  if (per < rows) per = rows;
-  b = (hw + per - 1) / per;
-  *bpi = static_cast<int>(b);
-  *ppb = static_cast<int>(per);
-  const long long items = static_cast<long long>(n) * b;
-  *grid = static_cast<int>(items < G ? items : G);
 }
 
 void bwd_grid(long long hw, int c, int rows, int* bpi, int* ppb) {
@@ -843,11 +577,8 @@ size_t eovae_gn_backward_workspace_bytes(int n, long long hw, int c, int groups)
   if (threads <= 0) return 0;
   int bpi, ppb;
   bwd_grid(hw, c, threads / (c / 8), &bpi, &ppb);
-  const size_t two_pass = 2 * static_cast<size_t>(n) * bpi * c + 2 * static_cast<size_t>(n) * groups + 2 * static_cast<size_t>(n) * c + 64;
-  int fg, fb, fp;
-  fused_plan(n, hw, c, threads / (c / 8), &fg, &fb, &fp);
-  const size_t fused = static_cast<size_t>(n) * fb * (3 * static_cast<size_t>(c) + 2 * groups) + static_cast<size_t>(n) + 64;
-  return sizeof(float) * (two_pass > fused ? two_pass : fused);
+  return sizeof(float) * (2 * static_cast<size_t>(n) * bpi * c + 2 * static_cast<size_t>(n) * groups +
+                          2 * static_cast<size_t>(n) * c + 64);
 }
 
 int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_dtype, const float* stats, const float* gamma,
@@ -863,48 +594,6 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
   EOVAE_CHECK(workspace_bytes >= eovae_gn_backward_workspace_bytes(n, hw, c, groups), "gn_backward: workspace too small");
   const int rows = threads / (c / 8);
   int bpi, ppb;
-  const bool pair_ok = (dtype == EOVAE_BF16 && grad_dtype == EOVAE_BF16) || (dtype == EOVAE_F16 && grad_dtype == EOVAE_F16) ||
-                       (dtype == EOVAE_F16 && grad_dtype == EOVAE_BF16);
-  if (g_gn_bwd_fused_knob && grad_x != nullptr && pair_ok && static_cast<long long>(n) * hw * c >= (1LL << 21) && threads >= 2 * groups &&
-      sizeof(float) * (2 * static_cast<size_t>(c) * rows + 2 * groups) <= 200 * 1024) {
-    // fused single-kernel path (see gn_bwd_fused_kernel): x and g from HBM once
-    int fgrid;
-    fused_plan(n, hw, c, rows, &fgrid, &bpi, &ppb);
-    const size_t items = static_cast<size_t>(n) * bpi;
-    float* chpart = static_cast<float*>(workspace);
-    float* gpart = chpart + items * c * 2;
-    float* colpart = gpart + items * groups * 2;
-    unsigned int* counters = reinterpret_cast<unsigned int*>(colpart + items * c);
-    EOVAE_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * n, stream));
-    const size_t fsmem = sizeof(float) * (2 * static_cast<size_t>(c) * rows + 2 * groups);
-#define EOVAE_GNB_F(T, TG, S)                                                                                          \
-  do {                                                                                                                 \
-    static bool attr = false;                                                                                          \
-    if (!attr) {                                                                                                       \
-      EOVAE_CUDA(cudaFuncSetAttribute(gn_bwd_fused_kernel<T, TG, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                      200 * 1024));                                                                    \
-      attr = true;                                                                                                     \
-    }                                                                                                                  \
-    gn_bwd_fused_kernel<T, TG, S><<<fgrid, threads, fsmem, stream>>>(                                                  \
-        static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, static_cast<const TG*>(grad_add), \
-        static_cast<TG*>(grad_x), n, hw, c, groups, bpi, ppb, chpart, gpart, grad_x_colsum ? colpart : nullptr, counters); \
-  } while (0)
-    if (dtype == EOVAE_BF16) { if (with_silu) EOVAE_GNB_F(__nv_bfloat16, __nv_bfloat16, true); else EOVAE_GNB_F(__nv_bfloat16, __nv_bfloat16, false); }
-    else if (grad_dtype == EOVAE_F16) { if (with_silu) EOVAE_GNB_F(__half, __half, true); else EOVAE_GNB_F(__half, __half, false); }
-    else { if (with_silu) EOVAE_GNB_F(__half, __nv_bfloat16, true); else EOVAE_GNB_F(__half, __nv_bfloat16, false); }
-#undef EOVAE_GNB_F
-    EOVAE_LAUNCH_CHECK();
-    if (dgamma != nullptr && dbeta != nullptr) {
-      gn_bwd_param_fused_kernel<<<ceil_div(c, 32), dim3(32, 8), 0, stream>>>(chpart, static_cast<long long>(items), c, dgamma, dbeta,
-                                                                             accumulate_params);
-      EOVAE_LAUNCH_CHECK();
-    }
-    if (grad_x_colsum != nullptr) {
-      colsum_finalize_kernel<<<ceil_div(c, 32), dim3(32, 32), 0, stream>>>(colpart, static_cast<int>(items), c, grad_x_colsum, 0);
-      EOVAE_LAUNCH_CHECK();
-    }
-    return 0;
-  }
   bwd_grid(hw, c, rows, &bpi, &ppb);
   float* partial = static_cast<float*>(workspace);
   float* gsum = partial + 2 * static_cast<size_t>(n) * bpi * c;

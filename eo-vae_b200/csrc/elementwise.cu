@@ -622,10 +622,8 @@ int eovae_gn_stats(const void* x, int x_dtype, int n, long long hw, int c, long 
   return 0;
 }
 
-extern int g_gn_bwd_fused_knob;
 void eovae_set_tuning(int key, int value) {
   if (key == EOVAE_TUNE_GN_APPLY_CORESIDENT) g_gn_apply_coresident = value;
-  if (key == EOVAE_TUNE_GN_BWD_FUSED) g_gn_bwd_fused_knob = value;
 }
 
 int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const float* stats, const float* gamma,

@@ -37,7 +37,6 @@ def set_tuning(key: int, value: int) -> None:
 
 
 TUNE_GN_APPLY_CORESIDENT = 1
-TUNE_GN_BWD_FUSED = 2
 
 
 def launch_count() -> int:

@@ -51,8 +51,6 @@ void eovae_set_debug_mode(int mode);
  * launches 128-thread CTAs with 8 loads in flight and <= 80 registers, a shape that fits on an SM beside a resident
  * implicit-GEMM CTA, so that the pass overlaps a convolution running on another stream (the dual-stream encode). */
 #define EOVAE_TUNE_GN_APPLY_CORESIDENT 1
-/* EOVAE_TUNE_GN_BWD_FUSED = 0: eovae_gn_backward takes the two-pass kernels instead of the fused single-kernel path. */
-#define EOVAE_TUNE_GN_BWD_FUSED 2
 void eovae_set_tuning(int key, int value);
 
 /* ---- weight packing (derived, non-persistent caches of the OIHW fp32 master parameters) -------------------- */

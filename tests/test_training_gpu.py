@@ -476,3 +476,92 @@ def test_fused_clip_adam_matches_torch(cuda, clip):
             assert float((sa["state"][k][key] - sb["state"][k][key]).abs().max()) < 1e-6 + 1e-4 * float(sb["state"][k][key].abs().max())
     ob.load_state_dict(sa)      # interchangeable checkpoints
     oa.load_state_dict(sb)
+
+
+def test_eager_training_forward_uses_the_updated_weights(cuda):
+    """Round-1 advisor finding: FusedClipAdam writes parameters through raw pointers, and the derived 16-bit weight operands
+    (Conv2dSM100.packed_weight, the fused conv2 + shortcut operand, the q/k/v operand, the folded Upsample taps) are keyed on
+    the parameters' autograd versions.  After eager steps with freeze_body=False, a forward of the trained model must equal
+    a forward of a FRESH model loaded from its state_dict (whose operands are packed from scratch), in eval and in train mode."""
+    import __graft_entry__ as g
+    from eo_vae.models.modules.consistency_loss import EOConsistencyLoss
+    from eo_vae.optim import FusedClipAdam
+    from oracle.weights import TINY_CONFIG, WAVELENGTHS, synthetic_patches
+    model, sd, cfg = _tiny(cuda)
+    model.train()
+    model.loss_fn = EOConsistencyLoss(pixel_weight=1.0, rec_loss_type="char").to(cuda)
+    model.clip_grad = 1.0
+    model.base_lr = 1e-3
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"], dtype=torch.float32).to(cuda)
+    x = synthetic_patches(2, 12, cfg["resolution"], seed=5).to(cuda)
+    batch = {model.image_key: x, "wvs": wvs}
+    with torch.no_grad():
+        before = model.reconstruct(x, wvs).clone()      # packs every operand cache in the inference dtype
+    torch.manual_seed(0)
+    for step in range(3):
+        model.training_step(batch, step)
+    opt = model.optimizers()
+    assert isinstance(getattr(opt, "optimizer", opt), FusedClipAdam)
+    assert model.global_step == 3                        # the stand-in advances global_step like Lightning does
+    fresh = g._model(TINY_CONFIG, {k: v.detach().clone() for k, v in model.state_dict().items()}, cuda)
+    model.eval()
+    with torch.no_grad():
+        after = model.reconstruct(x, wvs)
+        want = fresh.reconstruct(x, wvs)
+    assert not torch.equal(after, before), "parameters did not move"
+    assert torch.equal(after, want), f"stale weight operands in eval forward: rel {_rel(after, want):.3e}"
+    # and a taped (train-dtype) forward on both: same posterior noise, same bits
+    model.train()
+    fresh.train()
+    torch.manual_seed(7)
+    r1, _ = model(x, wvs)
+    torch.manual_seed(7)
+    r2, _ = fresh(x, wvs)
+    assert torch.equal(r1.detach(), r2.detach()), f"stale weight operands in train forward: rel {_rel(r1, r2):.3e}"
+
+
+def test_training_step_runs_the_discriminator_half(cuda):
+    """The generator / discriminator control flow of the reference step (new_autoencoder.py:638-684) with a user-supplied GAN
+    loss module: the generator half receives get_last_layer(), the discriminator half starts at disc_start, trains only the
+    discriminator, and its logs are merged."""
+    from oracle.weights import WAVELENGTHS, synthetic_patches
+
+    class ToyGanLoss(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.discriminator = torch.nn.Sequential(torch.nn.Conv2d(12, 4, 3, padding=1), torch.nn.LeakyReLU(0.2),
+                                                     torch.nn.Conv2d(4, 1, 3, padding=1))
+            self.disc_start, self.disc_weight = 2, 0.5
+            self.seen = []
+
+        def forward(self, inputs, wvs, reconstructions, optimizer_idx, global_step, last_layer=None, split="train"):
+            self.seen.append((optimizer_idx, global_step, None if last_layer is None else tuple(last_layer.shape),
+                              self.discriminator.training))
+            if optimizer_idx == 0:
+                rec = (reconstructions - inputs).abs().mean()
+                gen = -self.discriminator(reconstructions).mean() if global_step >= self.disc_start else rec * 0.0
+                return rec + self.disc_weight * gen, {f"{split}/rec": rec.detach()}
+            d = torch.relu(1.0 - self.discriminator(inputs)).mean() + torch.relu(1.0 + self.discriminator(reconstructions)).mean()
+            return d, {f"{split}/disc": d.detach()}
+
+    model, sd, cfg = _tiny(cuda)
+    model.train()
+    model.loss_fn = ToyGanLoss().to(cuda)
+    wvs = torch.tensor(WAVELENGTHS["S2L2A"], dtype=torch.float32).to(cuda)
+    batch = {model.image_key: synthetic_patches(2, 12, cfg["resolution"], seed=9).to(cuda), "wvs": wvs}
+    d0 = [p.detach().clone() for p in model.loss_fn.discriminator.parameters()]
+    e0 = model.encoder.down[0].block[0].conv1.weight.detach().clone()
+    torch.manual_seed(0)
+    for step in range(3):
+        model.training_step(batch, step)
+    seen = model.loss_fn.seen
+    # two optimisers step per iteration once the discriminator trains: global_step counts optimiser steps (Lightning semantics)
+    gen_calls = [s for s in seen if s[0] == 0]
+    disc_calls = [s for s in seen if s[0] == 1]
+    assert len(gen_calls) == 3 and len(disc_calls) >= 1
+    assert all(s[2] == (12, cfg["ch"], 3, 3) for s in gen_calls)         # last_layer = generated decoder kernel [C, E, 3, 3]
+    assert all(s[3] is False for s in gen_calls) and all(s[3] is True for s in disc_calls)   # eval() / train() toggling
+    assert all(s[1] >= 2 for s in disc_calls)
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(d0, model.loss_fn.discriminator.parameters()))
+    assert not torch.equal(e0, model.encoder.down[0].block[0].conv1.weight.detach())
+    assert "train/disc" in model.logged and "train/rec" in model.logged

@@ -151,15 +151,24 @@ __global__ void gn_tiles_finalize_kernel(const float* __restrict__ partial, floa
 }
 
 // per-(image, channel) affine of GroupNorm for the fused prologue: z = x * a + b
+// packed16 (fp16 operands): .x = bits of half2(m16, a / 2) with m16 = the fp16 value nearest the mean, .y = bh =
+// (beta + (m16 - mean) a) / 2 in fp32 - the coefficients of h = z / 2 = (x - m16) (a / 2) + bh used by the half2 transform
 __global__ void gn_ab_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
-                             const float* __restrict__ beta, float2* __restrict__ ab, int c, int groups, int total) {
+                             const float* __restrict__ beta, float2* __restrict__ ab, int c, int groups, int total, int packed16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int n = i / c, ch = i % c;
   const int g = ch / (c / groups);
   const float mean = stats[(n * groups + g) * 2], rstd = stats[(n * groups + g) * 2 + 1];
   const float a = gamma[ch] * rstd;
-  ab[i] = make_float2(a, beta[ch] - mean * a);
+  if (!packed16) {
+    ab[i] = make_float2(a, beta[ch] - mean * a);
+    return;
+  }
+  const __half m16 = __float2half_rn(mean);
+  const __half ah = __float2half_rn(0.5f * a);
+  const uint32_t bits = static_cast<uint32_t>(__half_as_ushort(m16)) | (static_cast<uint32_t>(__half_as_ushort(ah)) << 16);
+  ab[i] = make_float2(__uint_as_float(bits), 0.5f * (beta[ch] + (__half2float(m16) - mean) * a));
 }
 
 void m_tiling(int n, int ho, int wo, bool batched, int* bw, int* bh, int* bn);
@@ -424,7 +433,8 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   if (gnp != nullptr) {
     const int total = a.N * a.C;
     gn_ab_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(gnp->stats, gnp->gamma, gnp->beta,
-                                                           static_cast<float2*>(gnp->workspace), a.C, gnp->groups, total);
+                                                           static_cast<float2*>(gnp->workspace), a.C, gnp->groups, total,
+                                                           act_dtype == EOVAE_F16 ? 1 : 0);
     EOVAE_LAUNCH_CHECK();
     p.gnp_ab = static_cast<const float2*>(gnp->workspace);
     p.gnp_cin = a.C;

@@ -557,13 +557,59 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
           mbar_wait(&a_full[stage], phase);
           if (mt < m_tiles && y >= 0 && y < p.gnp_h && !(p.debug_mode & 16)) {
             const float4* abp = reinterpret_cast<const float4*>(p.gnp_ab + static_cast<long long>(tn) * p.gnp_cin + c0);
+            const uint32_t tile = smem_u32(smem_a + stage * Cfg::A_BYTES);
+            if (!p.gnp_bf16) {
+              // fp16 operands: PACKED half2 math, 4 instructions per channel pair (sub, fma, tanh.approx.f16x2, fma) instead of
+              // ~11 fp32 ones per element - the fp32 form kept these 8 warps at ~3400 cycles per stage against ~1150 of MMA.
+              // silu(z) = h + h tanh(h), h = z / 2 = (x - m16) * (a / 2) + bh: the mean is subtracted FIRST (m16 = the fp16
+              // value nearest the mean, so x - m16 is exact or one rounding of a small number) and the coefficient rounding
+              // then acts on the centred value only; bh carries the fp32 remainder (beta + (m16 - mean) a) / 2.
+              uint32_t m2[4], a2[4], b2[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 f = __ldg(abp + q);   // two channels: (bits of half2(m16, a/2), bh) each
+                const uint32_t e0 = __float_as_uint(f.x), e1 = __float_as_uint(f.z);
+                m2[q] = (e0 & 0xFFFFu) | (e1 << 16);
+                a2[q] = (e0 >> 16) | (e1 & 0xFFFF0000u);
+                b2[q] = T16<__half>::from_f2(f.y, f.w);
+              }
+              auto xf = [&](uint32_t x, int q) {
+                uint32_t d, h, t, o;
+                asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(m2[q]));
+                asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(d), "r"(a2[q]), "r"(b2[q]));
+                asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+                asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
+                return o;
+              };
+              // four rows per trip: their loads are issued together (ILP for the 48-register transform warps)
+              for (int r0 = rg; r0 < HALO_ROWS; r0 += 4 * 4 * NUM_XF_WARPS) {
+                uint32_t v[4][4];
+                uint32_t addr[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int r = r0 + u * 4 * NUM_XF_WARPS;
+                  const int x = x0 - 1 + r;
+                  ok[u] = r < HALO_ROWS && x >= 0 && x < p.gnp_w;
+                  addr[u] = tile + r * 128 + ((j ^ (r & 7)) << 4);
+                  if (ok[u])
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "r"(addr[u]));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (!ok[u]) continue;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) v[u][q] = xf(v[u][q], q);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(v[u][0]), "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3]) : "memory");
+                }
+              }
+            } else {
             float ca[8], cb[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 f = __ldg(abp + q);
               ca[2 * q] = f.x; cb[2 * q] = f.y; ca[2 * q + 1] = f.z; cb[2 * q + 1] = f.w;
             }
-            const uint32_t tile = smem_u32(smem_a + stage * Cfg::A_BYTES);
 #pragma unroll 2
             for (int r = rg; r < HALO_ROWS; r += 4 * NUM_XF_WARPS) {
               const int x = x0 - 1 + r;
@@ -573,17 +619,17 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float2 f = p.gnp_bf16 ? T16<__nv_bfloat16>::to_f2(v[q]) : T16<__half>::to_f2(v[q]);
-                // silu(z) = z * sigmoid(z) = h + h * tanh(h) with h = z / 2: one MUFU op per element (an
-                // ex2.f16x2 + 2 x rcp formulation measured 1.4x slower here)
+                const float2 f = T16<__nv_bfloat16>::to_f2(v[q]);
+                // silu(z) = z * sigmoid(z) = h + h * tanh(h) with h = z / 2: one MUFU op per element
                 const float h0 = 0.5f * fmaf(f.x, ca[2 * q], cb[2 * q]), h1 = 0.5f * fmaf(f.y, ca[2 * q + 1], cb[2 * q + 1]);
                 float t0, t1;
                 asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
                 asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
                 const float o0 = fmaf(h0, t0, h0), o1 = fmaf(h1, t1, h1);
-                v[q] = p.gnp_bf16 ? T16<__nv_bfloat16>::from_f2(o0, o1) : T16<__half>::from_f2(o0, o1);
+                v[q] = T16<__nv_bfloat16>::from_f2(o0, o1);
               }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+            }
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA

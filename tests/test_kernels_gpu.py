@@ -154,7 +154,8 @@ def test_conv2d_gn_prologue(cuda, n, h, w, cin, cout, dtype):
     ref = F.conv2d(y, wgt.to(dtype).float(), bias, padding=1) + res.float()
     unfused = ops.conv2d(ops.gn_apply(x, stats, gamma, beta, True), wp, bias, cout, ops.CONV_3X3, residual=res,
                          out_dtype=torch.float32)
-    tol = 3e-3 if dtype == torch.bfloat16 else 6e-4   # rounding of the normalised operand may differ by one ulp
+    # bf16: fp32 transform, operand may differ by one ulp; fp16: packed half2 transform (3 fp16 roundings + tanh.approx.f16x2)
+    tol = 3e-3 if dtype == torch.bfloat16 else 2e-3
     assert _rel(fused, ref) < tol, _rel(fused, ref)
     assert _rel(fused, unfused) < tol
     rf = ref.reshape(n, 32, -1)

@@ -74,7 +74,7 @@ int launch_t(const igemm::Params& p, int total_work, cudaStream_t stream) {
   auto kern = igemm::igemm_kernel<BLOCK_N, CHUNK_BYTES, CTAS, KCH, HALO, GNP>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
-    EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    EOVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES + (GNP ? igemm::GNP_COEF_BYTES : 0)));
     attr_set = true;
   }
   const int max_groups = eovae_num_sms() / CTAS;  // one CTA (pair) per SM (pair), persistent over the work items
@@ -82,7 +82,7 @@ int launch_t(const igemm::Params& p, int total_work, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * CTAS);
   cfg.blockDim = dim3(GNP ? igemm::NUM_THREADS_GNP : igemm::NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES + (GNP ? igemm::GNP_COEF_BYTES : 0);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -428,7 +428,7 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   // halo reuse of the A tile across the three horizontal taps: m-tile = 128 consecutive pixels of one image row
   const bool halo = mode == EOVAE_CONV_3X3 && chunk_bytes == 128 && ctas == 2 && p.extra_chunks == 0 && p.box_w == 128 &&
                     p.box_h == 1 && p.box_n == 1 && (block_n == 16 || block_n == 128 || block_n == 256) && !g_no_halo;
-  EOVAE_CHECK(gnp == nullptr || (halo && block_n != 16 && a.C % 64 == 0 && a.C % gnp->groups == 0),
+  EOVAE_CHECK(gnp == nullptr || (halo && block_n != 16 && a.C % 64 == 0 && a.C % gnp->groups == 0 && a.C * 8 <= igemm::GNP_COEF_BYTES),
               "igemm: fused GroupNorm prologue unsupported for this shape (query eovae_conv2d_gn_prologue_ok)");
   if (gnp != nullptr) {
     const int total = a.N * a.C;

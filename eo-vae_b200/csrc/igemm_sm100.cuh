@@ -31,6 +31,7 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 // GroupNorm-prologue variant: 5 warpgroups = {TMA, MMA, 2 idle} | 4 + 4 epilogue warps | 4 + 4 transform warps
 constexpr int NUM_XF_WARPS = 8;
 constexpr int NUM_THREADS_GNP = 128 + 32 * NUM_EPI_WARPS + 32 * NUM_XF_WARPS;
+constexpr int GNP_COEF_BYTES = 4096;  // GroupNorm-prologue kernels: per-image coefficient table [Cin <= 512][8 bytes] in shared memory
 constexpr int MAX_TAPS = 16;  // 9 for a 3x3 kernel; 16 = 4 sub-pixel phases x 2x2 taps (data gradient of the upsample conv)
 
 struct Params {
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
   uint64_t* ready_bar = bars + 3 * STAGES + 6;    // GNP: A tiles of the whole group are transformed (leader's copy)
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 1024;  // TMA-store staging: 8 warps x 2 x 2 KB, 1 KB aligned
   constexpr int EPI_BUF_BYTES = 32 * 64;
+  uint8_t* coef_smem = epi_smem + Cfg::EPI_BYTES;  // GNP only (the launch adds GNP_COEF_BYTES)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -544,19 +546,30 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
       const int j = tl & 7, rg = tl >> 3;
       int stage = 0;
       uint32_t phase = 0;
+      int coef_img = -1;  // image whose coefficients sit in coef_smem
       for (int work = group_id; work < total_work; work += num_groups) {
         const int mt = (work / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
         const int x0 = tw * p.box_w, y0 = th * p.box_h;
+        if (tn != coef_img && mt < m_tiles) {
+          // The per-(image, channel) coefficients come from global memory once per IMAGE, not once per stage: a stage gives a
+          // thread four 16-byte vectors of work, so a dependent global load in front of them (measured: the transform alone
+          // took 3000 cycles per stage, whatever its arithmetic) was the whole cost of the fused prologue.
+          asm volatile("bar.sync 1, %0;" ::"n"(NUM_XF_WARPS * 32) : "memory");  // nobody still reads the old table
+          const float2* src = p.gnp_ab + static_cast<long long>(tn) * p.gnp_cin;
+          for (int i = tl; i < p.gnp_cin; i += NUM_XF_WARPS * 32) reinterpret_cast<float2*>(coef_smem)[i] = __ldg(src + i);
+          asm volatile("bar.sync 1, %0;" ::"n"(NUM_XF_WARPS * 32) : "memory");
+          coef_img = tn;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           const int kh = kb / p.chunks_per_tap;
           const int c0 = (kb - kh * p.chunks_per_tap) * CH_ELEMS + j * 8;
           const int y = y0 + kh - 1;
           mbar_wait(&a_full[stage], phase);
           if (mt < m_tiles && y >= 0 && y < p.gnp_h && !(p.debug_mode & 16)) {
-            const float4* abp = reinterpret_cast<const float4*>(p.gnp_ab + static_cast<long long>(tn) * p.gnp_cin + c0);
+            const float4* abp = reinterpret_cast<const float4*>(coef_smem) + (c0 >> 1);   // two channels per float4
             const uint32_t tile = smem_u32(smem_a + stage * Cfg::A_BYTES);
             if (!p.gnp_bf16) {
               // fp16 operands: PACKED half2 math, 4 instructions per channel pair (sub, fma, tanh.approx.f16x2, fma) instead of
@@ -567,7 +580,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
               uint32_t m2[4], a2[4], b2[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float4 f = __ldg(abp + q);   // two channels: (bits of half2(m16, a/2), bh) each
+                const float4 f = abp[q];   // two channels: (bits of half2(m16, a/2), bh) each
                 const uint32_t e0 = __float_as_uint(f.x), e1 = __float_as_uint(f.z);
                 m2[q] = (e0 & 0xFFFFu) | (e1 << 16);
                 a2[q] = (e0 >> 16) | (e1 & 0xFFFF0000u);
@@ -607,7 +620,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
             float ca[8], cb[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 f = __ldg(abp + q);
+              const float4 f = abp[q];
               ca[2 * q] = f.x; cb[2 * q] = f.y; ca[2 * q + 1] = f.z; cb[2 * q + 1] = f.w;
             }
 #pragma unroll 2

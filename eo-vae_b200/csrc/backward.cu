@@ -5,6 +5,9 @@
 #include "../../include/eovae.h"
 #include "common.cuh"
 
+int g_gn_bwd_bulk = 1;                // eovae_set_tuning(EOVAE_TUNE_GN_BWD_BULK, 0/1): cp.async.bulk staged kernels
+long long g_bwd_block_elems = 0;      // eovae_set_tuning(EOVAE_TUNE_GN_BWD_BLOCK_ELEMS, n): pixels x channels per block, 0 = auto
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -24,12 +27,12 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// d/dz [z * sigmoid(z)] = s + z s (1 - s) with s = sigmoid(z) = 0.5 + 0.5 tanh(z / 2); `half_z` = z / 2 comes from one FMA on
-// the raw input (the per-channel GroupNorm affine is folded into its coefficients).  ONE MUFU op (tanh.approx.f32, relative
-// error 2^-11 - below the bf16 / fp16 rounding of the gradient it multiplies) + 4 FP32 instructions: the ex2 + rcp form
+// d/dz [z * sigmoid(z)] = s + z s (1 - s) with s = sigmoid(z) = 0.5 + 0.5 tanh(z / 2); z comes from one FMA on the raw
+// input (the per-channel GroupNorm affine is folded into its coefficients).  ONE MUFU op (tanh.approx.f32, relative
+// error 2^-11 - below the bf16 / fp16 rounding of the gradient it multiplies) + 5 FP32 instructions: the ex2 + rcp form
 // (2 MUFU + 5 FP32) kept both backward kernels instruction-issue bound at 0.3-0.5 of the HBM rate.
-__device__ __forceinline__ float silu_grad2(float z, float half_z) {
-  const float s = fmaf(0.5f, tanh_approx(half_z), 0.5f);
+__device__ __forceinline__ float silu_grad2(float z) {
+  const float s = fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
   return fmaf(z * (1.0f - s), s, s);
 }
 
@@ -37,7 +40,7 @@ __device__ __forceinline__ float silu_grad2(float z, float half_z) {
 // z = xhat * gamma + beta, xhat = (x - mean) * rstd.  grid (blocks_per_image, n); fixed-slot partials (deterministic).
 // T = storage type of the forward activation x, TG = storage type of the gradients (g in, dx out, optional add)
 template <typename T, typename TG, bool SILU>
-__global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __restrict__ x, const TG* __restrict__ g,
+__global__ void __launch_bounds__(kThreads, 3) gn_bwd_reduce_kernel(const T* __restrict__ x, const TG* __restrict__ g,
                                                                   const float* __restrict__ stats,
                                                                   const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, long long hw, int c,
@@ -53,8 +56,8 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __rest
 #pragma unroll
   for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
   if (r < rows) {
-    // per-channel constants: xhat = x * rs + nm, z = x * za + zb, z / 2 = x * ea + eb
-    float rs[8], nm[8], za[8], zb[8], ea[8], eb[8];
+    // per-channel constants: xhat = x * rs + nm, z = x * za + zb
+    float rs[8], nm[8], za[8], zb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ch = v * 8 + j, gi = ch / cpg;
@@ -63,8 +66,6 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __rest
       nm[j] = -mean * rstd;
       za[j] = rstd * gamma[ch];
       zb[j] = fmaf(-mean, za[j], beta[ch]);
-      ea[j] = 0.5f * za[j];
-      eb[j] = 0.5f * zb[j];
     }
     const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
     long long p1 = p0 + pix_per_block;
@@ -79,8 +80,8 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const T* __rest
         const float xh0 = fmaf(fx.x, rs[2 * j], nm[2 * j]), xh1 = fmaf(fx.y, rs[2 * j + 1], nm[2 * j + 1]);
         float d0 = fg.x, d1 = fg.y;
         if (SILU) {
-          d0 *= silu_grad2(fmaf(fx.x, za[2 * j], zb[2 * j]), fmaf(fx.x, ea[2 * j], eb[2 * j]));
-          d1 *= silu_grad2(fmaf(fx.y, za[2 * j + 1], zb[2 * j + 1]), fmaf(fx.y, ea[2 * j + 1], eb[2 * j + 1]));
+          d0 *= silu_grad2(fmaf(fx.x, za[2 * j], zb[2 * j]));
+          d1 *= silu_grad2(fmaf(fx.y, za[2 * j + 1], zb[2 * j + 1]));
         }
         sa[2 * j] += d0; sb[2 * j] = fmaf(d0, xh0, sb[2 * j]);
         sa[2 * j + 1] += d1; sb[2 * j + 1] = fmaf(d1, xh1, sb[2 * j + 1]);
@@ -143,7 +144,8 @@ __global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, const 
   for (int t = threadIdx.x; t < c * slices; t += blockDim.x) {
     const int ch = t % c, sl = t / c;
     double a = 0.0, b = 0.0;
-    for (int k = sl; k < bpi; k += slices) {
+#pragma unroll 8
+    for (int k = sl; k < bpi; k += slices) {  // unrolled: the loads of a batch of rows are issued together
       const float2 o = *reinterpret_cast<const float2*>(partial + ((static_cast<long long>(n) * bpi + k) * c + ch) * 2);
       a += o.x;
       b += o.y;
@@ -192,7 +194,7 @@ __global__ void gn_bwd_param_kernel(const float* __restrict__ chsum, int n_img, 
 
 // Pass 3: dx = rstd * (dz*gamma - (s1 + xhat*s2) / M) (+ optional accumulation into an existing gradient)
 template <typename T, typename TG, bool SILU>
-__global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restrict__ x, const TG* __restrict__ g,
+__global__ void __launch_bounds__(kThreads, 3) gn_bwd_apply_kernel(const T* __restrict__ x, const TG* __restrict__ g,
                                                                  const float* __restrict__ stats,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta,
@@ -212,21 +214,19 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
   if (r < rows) {
   const int cpg = c / groups;
   const float inv_m = 1.0f / (static_cast<float>(hw) * cpg);
-  // per-channel constants: xhat = x * rs + nm, z = x * za + zb, z / 2 = x * ea + eb,
-  // dx = dz * za - c1 - xhat * c2   with c1 = rstd * s1 / M, c2 = rstd * s2 / M
-  float rs[8], nm[8], za[8], zb[8], ea[8], eb[8], c1[8], c2[8];
+  // per-channel constants: z = x * za + zb and, with xhat = (x - mean) * rstd, c1 = rstd * s1 / M, c2 = rstd * s2 / M,
+  // dx = dz * za - c1 - xhat * c2 = dz * za + x * xa + xb   (xa = -rstd * c2, xb = mean * rstd * c2 - c1)
+  float za[8], zb[8], xa[8], xb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = v * 8 + j, gi = ch / cpg;
     const float mean = stats[(n * groups + gi) * 2], rstd = stats[(n * groups + gi) * 2 + 1];
-    rs[j] = rstd;
-    nm[j] = -mean * rstd;
     za[j] = rstd * gamma[ch];
     zb[j] = fmaf(-mean, za[j], beta[ch]);
-    ea[j] = 0.5f * za[j];
-    eb[j] = 0.5f * zb[j];
-    c1[j] = rstd * gsum[(n * groups + gi) * 2] * inv_m;
-    c2[j] = rstd * gsum[(n * groups + gi) * 2 + 1] * inv_m;
+    const float c1 = rstd * gsum[(n * groups + gi) * 2] * inv_m;
+    const float c2 = rstd * gsum[(n * groups + gi) * 2 + 1] * inv_m;
+    xa[j] = -rstd * c2;
+    xb[j] = fmaf(mean * rstd, c2, -c1);
   }
   const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
   long long p1 = p0 + pix_per_block;
@@ -240,14 +240,13 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
       const float2 fx = T16<T>::to_f2(wx[j]), fg = T16<TG>::to_f2(wg[j]);
       float2 fa = make_float2(0.f, 0.f);
       if (add != nullptr) fa = T16<TG>::to_f2(wa[j]);
-      const float xh0 = fmaf(fx.x, rs[2 * j], nm[2 * j]), xh1 = fmaf(fx.y, rs[2 * j + 1], nm[2 * j + 1]);
       float d0 = fg.x, d1 = fg.y;
       if (SILU) {
-        d0 *= silu_grad2(fmaf(fx.x, za[2 * j], zb[2 * j]), fmaf(fx.x, ea[2 * j], eb[2 * j]));
-        d1 *= silu_grad2(fmaf(fx.y, za[2 * j + 1], zb[2 * j + 1]), fmaf(fx.y, ea[2 * j + 1], eb[2 * j + 1]));
+        d0 *= silu_grad2(fmaf(fx.x, za[2 * j], zb[2 * j]));
+        d1 *= silu_grad2(fmaf(fx.y, za[2 * j + 1], zb[2 * j + 1]));
       }
-      const float r0 = fmaf(-xh0, c2[2 * j], fmaf(d0, za[2 * j], fa.x - c1[2 * j]));
-      const float r1 = fmaf(-xh1, c2[2 * j + 1], fmaf(d1, za[2 * j + 1], fa.y - c1[2 * j + 1]));
+      const float r0 = fmaf(fx.x, xa[2 * j], fmaf(d0, za[2 * j], fa.x + xb[2 * j]));
+      const float r1 = fmaf(fx.y, xa[2 * j + 1], fmaf(d1, za[2 * j + 1], fa.y + xb[2 * j + 1]));
       cs[2 * j] += r0;
       cs[2 * j + 1] += r1;
       o[j] = T16<TG>::from_f2(r0, r1);
@@ -288,8 +287,17 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const T* __restr
   }
 }
 
-void bwd_grid(long long hw, int c, int rows, int* bpi, int* ppb) {
-  long long per = 131072 / c;  // pixels per block: enough work per thread to amortise the per-block parameter loads and the shared-memory reduction
+void bwd_grid(int n, long long hw, int c, int rows, int* bpi, int* ppb) {
+  // elements (pixels x channels) per block: enough work to amortise the per-block parameter loads, the pipeline fill and
+  // the shared-memory reduction, small enough that the grid still covers the 148 SMs.  Measured on B200 (batch 16,
+  // tools/gn_bwd_grid.py): 128 Ki elements from 32 Mi-element tensors up, 64 Ki at 8 Mi; knob > 0 overrides.
+  long long elems = g_bwd_block_elems;
+  if (elems <= 0) {
+    const long long total = static_cast<long long>(n) * hw * c;
+    elems = 16384;
+    while (elems < 131072 && elems * 2 * 128 <= total) elems *= 2;
+  }
+  long long per = elems / c;
   if (per < rows) per = rows;
   per = (per + rows - 1) / rows * rows;
   if (per > hw) per = (hw + rows - 1) / rows * rows;
@@ -403,6 +411,265 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int bl
 #pragma unroll
     for (int y = 0; y < 32; ++y) t += red[y][threadIdx.x];
     out[ch] = (accumulate ? out[ch] : 0.f) + static_cast<float>(t);
+  }
+}
+
+// ------------------------------------------------------------------------------------ bulk-async staged GroupNorm backward
+// Same two passes, but x and g reach the SM through cp.async.bulk (TMA, 1-D) into a shared-memory ring instead of register
+// loads: the bytes in flight per SM no longer depend on the register allocator (at 80 registers / thread ptxas serialised
+// the loads of the register version down to two 16-byte requests per thread = 24 KB / SM - long-scoreboard bound at 3.5 of
+// 6.5 TB/s; the ring keeps 128-192 KB / SM outstanding).  A block owns the contiguous pixel range [p0, p1) of one image =
+// one contiguous byte range of each NHWC tensor, walked in stages of kThreads * VEC 16-byte vectors; thread t owns vectors
+// t, t + 256, ... of a stage, which all belong to the same 8 channels because (C / 8) divides 256.
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(s_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 21)) __trap();  // a protocol bug traps instead of hanging the device
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
+               "l"(src), "r"(bytes), "r"(s_u32(bar))
+               : "memory");
+}
+
+// ring of STAGES slots, each NT tensors x (kThreads * VEC) uint4
+template <int NT, int VEC, int STAGES>
+struct BulkRing {
+  static constexpr int kSlotVecs = kThreads * VEC;
+  static constexpr uint32_t kSlotBytes = kSlotVecs * 16;
+  static constexpr size_t kSmemBytes = static_cast<size_t>(STAGES) * NT * kSlotBytes + 128;
+  uint4* slots;
+  uint64_t* full;
+  const char* src[NT];
+  long long total_bytes;  // of this block's range, per tensor
+  int nchunks;
+  __device__ __forceinline__ void init(unsigned char* smem, long long total) {
+    slots = reinterpret_cast<uint4*>(smem);
+    full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(STAGES) * NT * kSlotBytes);
+    total_bytes = total;
+    nchunks = static_cast<int>((total + kSlotBytes - 1) / kSlotBytes);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < STAGES; ++i) bar_init(&full[i], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int i = 0; i < STAGES && i < nchunks; ++i) issue(i);
+  }
+  __device__ __forceinline__ void issue(int chunk) {  // one thread
+    const int s = chunk % STAGES;
+    const long long off = static_cast<long long>(chunk) * kSlotBytes;
+    const long long left = total_bytes - off;
+    const uint32_t bytes = left < static_cast<long long>(kSlotBytes) ? static_cast<uint32_t>(left) : kSlotBytes;
+    bar_expect_tx(&full[s], bytes * NT);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) bulk_g2s(slot(s, t), src[t] + off, bytes, &full[s]);
+  }
+  __device__ __forceinline__ uint4* slot(int s, int t) { return slots + (static_cast<size_t>(s) * NT + t) * kSlotVecs; }
+  __device__ __forceinline__ void wait(int chunk) { bar_wait(&full[chunk % STAGES], (chunk / STAGES) & 1); }
+  // every thread has copied its vectors of `chunk` to registers: hand the slot back to the copy engine
+  __device__ __forceinline__ void release(int chunk) {
+    __syncthreads();
+    if (threadIdx.x == 0 && chunk + STAGES < nchunks) issue(chunk + STAGES);
+  }
+  // vectors of the chunk that hold data (the last chunk of a block may be short)
+  __device__ __forceinline__ int valid_vecs(int chunk) const {
+    const long long left = total_bytes - static_cast<long long>(chunk) * kSlotBytes;
+    return left >= static_cast<long long>(kSlotBytes) ? kSlotVecs : static_cast<int>(left >> 4);
+  }
+};
+
+template <typename T, typename TG, bool SILU, int VEC, int STAGES>
+__global__ void __launch_bounds__(kThreads, 2) gn_bwd_reduce_bulk_kernel(const T* __restrict__ x, const TG* __restrict__ g,
+                                                                         const float* __restrict__ stats,
+                                                                         const float* __restrict__ gamma,
+                                                                         const float* __restrict__ beta, long long hw, int c,
+                                                                         int groups, float* __restrict__ partial,
+                                                                         int pix_per_block) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using Ring = BulkRing<2, VEC, STAGES>;
+  Ring ring;
+  const int vpp = c >> 3;
+  const int rows = kThreads / vpp;
+  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
+  const int n = blockIdx.y;
+  const int cpg = c / groups;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > hw) p1 = hw;
+  const long long base = (static_cast<long long>(n) * hw + p0) * c;
+  ring.src[0] = reinterpret_cast<const char*>(x + base);
+  ring.src[1] = reinterpret_cast<const char*>(g + base);
+  ring.init(smem_raw, (p1 - p0) * c * 2);
+  float sa[8], sb[8], rs[8], nm[8], za[8], zb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = v * 8 + j, gi = ch / cpg;
+    const float mean = stats[(n * groups + gi) * 2], rstd = stats[(n * groups + gi) * 2 + 1];
+    sa[j] = sb[j] = 0.f;
+    rs[j] = rstd;
+    nm[j] = -mean * rstd;
+    za[j] = rstd * gamma[ch];
+    zb[j] = fmaf(-mean, za[j], beta[ch]);
+  }
+  auto accum = [&](const uint4& ux, const uint4& ug) {
+    const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fx = T16<T>::to_f2(wx[j]), fg = T16<TG>::to_f2(wg[j]);
+      const float xh0 = fmaf(fx.x, rs[2 * j], nm[2 * j]), xh1 = fmaf(fx.y, rs[2 * j + 1], nm[2 * j + 1]);
+      float d0 = fg.x, d1 = fg.y;
+      if (SILU) {
+        d0 *= silu_grad2(fmaf(fx.x, za[2 * j], zb[2 * j]));
+        d1 *= silu_grad2(fmaf(fx.y, za[2 * j + 1], zb[2 * j + 1]));
+      }
+      sa[2 * j] += d0; sb[2 * j] = fmaf(d0, xh0, sb[2 * j]);
+      sa[2 * j + 1] += d1; sb[2 * j + 1] = fmaf(d1, xh1, sb[2 * j + 1]);
+    }
+  };
+  for (int i = 0; i < ring.nchunks; ++i) {
+    const int s = i % STAGES;
+    ring.wait(i);
+    uint4 ux[VEC], ug[VEC];
+    const uint4 *sx = ring.slot(s, 0), *sg = ring.slot(s, 1);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      ux[k] = sx[threadIdx.x + k * kThreads];
+      ug[k] = sg[threadIdx.x + k * kThreads];
+    }
+    const int valid = ring.valid_vecs(i);
+    ring.release(i);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (static_cast<int>(threadIdx.x) + k * kThreads < valid) accum(ux[k], ug[k]);
+  }
+  __syncthreads();  // the ring is idle (every issued chunk was consumed): reuse it for the block reduction
+  float* sm = reinterpret_cast<float*>(smem_raw);  // [rows][2][c]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sm[(r * 2) * c + v * 8 + j] = sa[j];
+    sm[(r * 2 + 1) * c + v * 8 + j] = sb[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; ++rr) {
+      a += sm[(rr * 2) * c + ch];
+      b += sm[(rr * 2 + 1) * c + ch];
+    }
+    float* o = partial + ((static_cast<long long>(n) * gridDim.x + blockIdx.x) * c + ch) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+}
+
+template <typename T, typename TG, bool SILU, bool ADD, int VEC, int STAGES>
+__global__ void __launch_bounds__(kThreads, 2) gn_bwd_apply_bulk_kernel(const T* __restrict__ x, const TG* __restrict__ g,
+                                                                        const float* __restrict__ stats,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta,
+                                                                        const float* __restrict__ gsum,
+                                                                        const TG* __restrict__ add, TG* __restrict__ dx,
+                                                                        long long hw, int c, int groups, int pix_per_block,
+                                                                        float* __restrict__ colpart) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NT = ADD ? 3 : 2;
+  using Ring = BulkRing<NT, VEC, STAGES>;
+  Ring ring;
+  const int vpp = c >> 3;
+  const int rows = kThreads / vpp;
+  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
+  const int n = blockIdx.y;
+  const int cpg = c / groups;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > hw) p1 = hw;
+  const long long base = (static_cast<long long>(n) * hw + p0) * c;
+  ring.src[0] = reinterpret_cast<const char*>(x + base);
+  ring.src[1] = reinterpret_cast<const char*>(g + base);
+  if (ADD) ring.src[NT - 1] = reinterpret_cast<const char*>(add + base);
+  ring.init(smem_raw, (p1 - p0) * c * 2);
+  const float inv_m = 1.0f / (static_cast<float>(hw) * cpg);
+  // z = x * za + zb;  dx = dz * za - c1 - xhat * c2 = dz * za + x * xa + xb  (see gn_bwd_apply_kernel)
+  float cs[8], za[8], zb[8], xa[8], xb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = v * 8 + j, gi = ch / cpg;
+    const float mean = stats[(n * groups + gi) * 2], rstd = stats[(n * groups + gi) * 2 + 1];
+    cs[j] = 0.f;
+    za[j] = rstd * gamma[ch];
+    zb[j] = fmaf(-mean, za[j], beta[ch]);
+    const float c1 = rstd * gsum[(n * groups + gi) * 2] * inv_m;
+    const float c2 = rstd * gsum[(n * groups + gi) * 2 + 1] * inv_m;
+    xa[j] = -rstd * c2;
+    xb[j] = fmaf(mean * rstd, c2, -c1);
+  }
+  auto compute = [&](const uint4& ux, const uint4& ug, const uint4& ua) {
+    const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w}, wa[4] = {ua.x, ua.y, ua.z, ua.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fx = T16<T>::to_f2(wx[j]), fg = T16<TG>::to_f2(wg[j]);
+      float2 fa = make_float2(0.f, 0.f);
+      if (ADD) fa = T16<TG>::to_f2(wa[j]);
+      float d0 = fg.x, d1 = fg.y;
+      if (SILU) {
+        d0 *= silu_grad2(fmaf(fx.x, za[2 * j], zb[2 * j]));
+        d1 *= silu_grad2(fmaf(fx.y, za[2 * j + 1], zb[2 * j + 1]));
+      }
+      const float r0 = fmaf(fx.x, xa[2 * j], fmaf(d0, za[2 * j], fa.x + xb[2 * j]));
+      const float r1 = fmaf(fx.y, xa[2 * j + 1], fmaf(d1, za[2 * j + 1], fa.y + xb[2 * j + 1]));
+      cs[2 * j] += r0;
+      cs[2 * j + 1] += r1;
+      o[j] = T16<TG>::from_f2(r0, r1);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  uint4* out = reinterpret_cast<uint4*>(dx + base);
+  for (int i = 0; i < ring.nchunks; ++i) {
+    const int s = i % STAGES;
+    ring.wait(i);
+    uint4 ux[VEC], ug[VEC], ua[VEC];
+    const uint4 *sx = ring.slot(s, 0), *sg = ring.slot(s, 1), *sa = ring.slot(s, NT - 1);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      ux[k] = sx[threadIdx.x + k * kThreads];
+      ug[k] = sg[threadIdx.x + k * kThreads];
+      ua[k] = ADD ? sa[threadIdx.x + k * kThreads] : make_uint4(0, 0, 0, 0);
+    }
+    const int valid = ring.valid_vecs(i);
+    ring.release(i);
+    uint4* o = out + static_cast<long long>(i) * Ring::kSlotVecs;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (static_cast<int>(threadIdx.x) + k * kThreads < valid) o[threadIdx.x + k * kThreads] = compute(ux[k], ug[k], ua[k]);
+  }
+  if (colpart == nullptr) return;
+  __syncthreads();
+  float* sm_cs = reinterpret_cast<float*>(smem_raw);  // [rows][c]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm_cs[r * c + v * 8 + j] = cs[j];
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += sm_cs[rr * c + ch];
+    colpart[(static_cast<long long>(n) * gridDim.x + blockIdx.x) * c + ch] = a;
   }
 }
 
@@ -576,7 +843,7 @@ size_t eovae_gn_backward_workspace_bytes(int n, long long hw, int c, int groups)
   const int threads = block_threads(c);
   if (threads <= 0) return 0;
   int bpi, ppb;
-  bwd_grid(hw, c, threads / (c / 8), &bpi, &ppb);
+  bwd_grid(n, hw, c, threads / (c / 8), &bpi, &ppb);
   return sizeof(float) * (2 * static_cast<size_t>(n) * bpi * c + 2 * static_cast<size_t>(n) * groups +
                           2 * static_cast<size_t>(n) * c + 64);
 }
@@ -594,7 +861,7 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
   EOVAE_CHECK(workspace_bytes >= eovae_gn_backward_workspace_bytes(n, hw, c, groups), "gn_backward: workspace too small");
   const int rows = threads / (c / 8);
   int bpi, ppb;
-  bwd_grid(hw, c, rows, &bpi, &ppb);
+  bwd_grid(n, hw, c, rows, &bpi, &ppb);
   float* partial = static_cast<float*>(workspace);
   float* gsum = partial + 2 * static_cast<size_t>(n) * bpi * c;
   float* chsum = gsum + 2 * static_cast<size_t>(n) * groups;
@@ -607,6 +874,34 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
   gn_bwd_apply_kernel<T, TG, S><<<grid, threads, grad_x_colsum ? sizeof(float) * c * rows : 0, stream>>>(                \
       static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, gsum, static_cast<const TG*>(grad_add), \
       static_cast<TG*>(grad_x), hw, c, groups, ppb, grad_x_colsum ? partial : nullptr)
+  // bulk-async staged variants (see BulkRing): channel-vector count must divide the block
+  const bool bulk = g_gn_bwd_bulk != 0 && threads == kThreads && kThreads % (c / 8) == 0;
+#define EOVAE_GNB_LAUNCH_BULK(KERNEL, BYTES, ...)                                                                    \
+  do {                                                                                                                \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      EOVAE_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(BYTES))); \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    KERNEL<<<grid, kThreads, BYTES, stream>>>(__VA_ARGS__);                                                           \
+  } while (0)
+#define EOVAE_GNB_RB(T, TG, S)                                                                                        \
+  EOVAE_GNB_LAUNCH_BULK((gn_bwd_reduce_bulk_kernel<T, TG, S, 4, 3>), (BulkRing<2, 4, 3>::kSmemBytes),                  \
+                        static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, hw, c, groups, \
+                        partial, ppb)
+#define EOVAE_GNB_AB(T, TG, S)                                                                                        \
+  do {                                                                                                                \
+    if (grad_add != nullptr)                                                                                          \
+      EOVAE_GNB_LAUNCH_BULK((gn_bwd_apply_bulk_kernel<T, TG, S, true, 2, 4>), (BulkRing<3, 2, 4>::kSmemBytes),         \
+                            static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, gsum,     \
+                            static_cast<const TG*>(grad_add), static_cast<TG*>(grad_x), hw, c, groups, ppb,           \
+                            grad_x_colsum ? partial : nullptr);                                                       \
+    else                                                                                                              \
+      EOVAE_GNB_LAUNCH_BULK((gn_bwd_apply_bulk_kernel<T, TG, S, false, 4, 3>), (BulkRing<2, 4, 3>::kSmemBytes),        \
+                            static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, gsum,     \
+                            static_cast<const TG*>(grad_add), static_cast<TG*>(grad_x), hw, c, groups, ppb,           \
+                            grad_x_colsum ? partial : nullptr);                                                       \
+  } while (0)
   // (activation type, gradient type): bf16/bf16, f16/f16 and the default training mix f16 activations / bf16 gradients
 #define EOVAE_GNB_DISPATCH(M)                                                                                  \
   do {                                                                                                         \
@@ -620,7 +915,7 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
       EOVAE_CHECK(false, "gn_backward: unsupported (activation, gradient) dtype pair (%d, %d)", dtype, grad_dtype); \
     }                                                                                                          \
   } while (0)
-  EOVAE_GNB_DISPATCH(EOVAE_GNB_R);
+  if (bulk) EOVAE_GNB_DISPATCH(EOVAE_GNB_RB); else EOVAE_GNB_DISPATCH(EOVAE_GNB_R);
   EOVAE_LAUNCH_CHECK();
   {
     const int fthreads = 1024;
@@ -633,7 +928,7 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
     EOVAE_LAUNCH_CHECK();
   }
   if (grad_x != nullptr) {
-    EOVAE_GNB_DISPATCH(EOVAE_GNB_A);
+    if (bulk) EOVAE_GNB_DISPATCH(EOVAE_GNB_AB); else EOVAE_GNB_DISPATCH(EOVAE_GNB_A);
     EOVAE_LAUNCH_CHECK();
     if (grad_x_colsum != nullptr) {  // the reduce partials are dead by now: their buffer carried the column-sum slots
       colsum_finalize_kernel<<<ceil_div(c, 32), dim3(32, 32), 0, stream>>>(partial, n * bpi, c, grad_x_colsum, 0);
@@ -641,6 +936,9 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
     }
   }
 #undef EOVAE_GNB_R
+#undef EOVAE_GNB_RB
+#undef EOVAE_GNB_AB
+#undef EOVAE_GNB_LAUNCH_BULK
 #undef EOVAE_GNB_A
 #undef EOVAE_GNB_DISPATCH
   return 0;

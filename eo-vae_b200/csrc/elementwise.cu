@@ -582,6 +582,10 @@ __global__ void preprocess_kernel(const TIn* __restrict__ in, int c, int hi, int
 
 }  // namespace
 
+// launch-shape knobs of backward.cu, set through eovae_set_tuning
+extern long long g_bwd_block_elems;
+extern int g_gn_bwd_bulk;
+
 extern "C" {
 
 size_t eovae_gn_stats_workspace_bytes(int n, long long hw, int c, int groups) {
@@ -624,6 +628,8 @@ int eovae_gn_stats(const void* x, int x_dtype, int n, long long hw, int c, long 
 
 void eovae_set_tuning(int key, int value) {
   if (key == EOVAE_TUNE_GN_APPLY_CORESIDENT) g_gn_apply_coresident = value;
+  if (key == EOVAE_TUNE_GN_BWD_BLOCK_ELEMS && (value == 0 || value >= 4096)) g_bwd_block_elems = value;
+  if (key == EOVAE_TUNE_GN_BWD_BULK) g_gn_bwd_bulk = value;
 }
 
 int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const float* stats, const float* gamma,

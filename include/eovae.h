@@ -51,6 +51,11 @@ void eovae_set_debug_mode(int mode);
  * launches 128-thread CTAs with 8 loads in flight and <= 80 registers, a shape that fits on an SM beside a resident
  * implicit-GEMM CTA, so that the pass overlaps a convolution running on another stream (the dual-stream encode). */
 #define EOVAE_TUNE_GN_APPLY_CORESIDENT 1
+/* EOVAE_TUNE_GN_BWD_BLOCK_ELEMS: elements (pixels x channels) handled by one block of the GroupNorm backward kernels;
+   0 (default) = chosen from the tensor size */
+#define EOVAE_TUNE_GN_BWD_BLOCK_ELEMS 3
+/* EOVAE_TUNE_GN_BWD_BULK: 1 (default) = cp.async.bulk shared-memory ring in the GroupNorm backward kernels, 0 = register loads */
+#define EOVAE_TUNE_GN_BWD_BULK 4
 void eovae_set_tuning(int key, int value);
 
 /* ---- weight packing (derived, non-persistent caches of the OIHW fp32 master parameters) -------------------- */

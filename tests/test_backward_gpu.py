@@ -92,6 +92,37 @@ def test_group_norm_backward(cuda, n, c, h, w, silu):
     assert _rel(gx2, xf.grad + add.float()) < 6e-3
 
 
+@pytest.mark.parametrize("n,c,h,w", [(2, 128, 64, 64), (1, 64, 37, 29), (3, 512, 24, 24), (2, 256, 128, 128), (1, 8, 5, 7)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_group_norm_backward_staged_equals_register_path(cuda, n, c, h, w, dtype):
+    """The cp.async.bulk staged kernels (default) and the register-load kernels walk every thread's pixels in the same
+    order: identical bits, over block sizes that give short last stages, one-stage blocks and ragged last blocks."""
+    from eo_vae import ops
+    x = (_act(n, c, h, w, cuda, seed=11, scale=2.0).float() + 0.25).to(dtype).contiguous(memory_format=torch.channels_last)
+    g = _act(n, c, h, w, cuda, seed=12).to(dtype)
+    add = _act(n, c, h, w, cuda, seed=13).to(dtype)
+    groups = min(32, c // 8) if c < 32 else 32
+    gamma, beta = (1 + 0.2 * torch.randn(c)).to(cuda), (0.2 * torch.randn(c)).to(cuda)
+    stats = ops.gn_stats(x, groups)
+    try:
+        for elems in (0, 4096, 40960, 131072):
+            ops.set_tuning(ops.TUNE_GN_BWD_BLOCK_ELEMS, elems)
+            outs = []
+            for bulk in (0, 1):
+                ops.set_tuning(ops.TUNE_GN_BWD_BULK, bulk)
+                for silu in (True, False):
+                    outs.append((bulk, ops.gn_backward(x, g, stats, gamma, beta, silu, groups=groups),
+                                 ops.gn_backward(x, g, stats, gamma, beta, silu, groups=groups, grad_add=add)))
+            half = len(outs) // 2
+            for (_, a0, a1), (_, b0, b1) in zip(outs[:half], outs[half:]):
+                for t0, t1 in zip(a0 + a1, b0 + b1):
+                    assert torch.isfinite(t1.float()).all()
+                    assert torch.equal(t0, t1)
+    finally:
+        ops.set_tuning(ops.TUNE_GN_BWD_BLOCK_ELEMS, 0)
+        ops.set_tuning(ops.TUNE_GN_BWD_BULK, 1)
+
+
 def test_upsample_adjoint(cuda):
     from eo_vae import ops
     x = _act(2, 64, 6, 10, cuda, seed=11).float().requires_grad_(True)

@@ -13,6 +13,8 @@ namespace {
 int g_debug_mode = 0;
 int g_force_ctas = 0;  // 0 = auto, 1 / 2 = forced (tests, tools/igemm_bench.py)
 int g_force_kch1 = 0;  // 1 = always one K-chunk per stage
+int g_no_wide_store = 0;  // 1 = 64-byte-row output boxes everywhere
+int g_no_kch9 = 0;     // 1 = narrow-channel 3x3 convs stage three taps (not all nine) per pipeline stage
 int g_no_tma_store = 0;  // 1 = epilogue writes with per-thread 16-byte stores instead of bulk tensor stores
 int g_no_halo = 0;       // 1 = never use the halo-reuse mainloop
 
@@ -119,34 +121,44 @@ int pick_block_n(int cout_pad) {
   return 16;
 }
 
-// stats[n][g] = (mean, rstd) from the per-tile partial sums written by the igemm epilogue; one warp per (n, g),
-// fixed summation order (deterministic).
-__global__ void gn_tiles_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int pairs, int groups,
-                                         int slots_per_img, double count, float eps, int regions, long long region_stride) {
-  const int pair = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (pair >= pairs) return;
-  const int n = pair / groups, g = pair % groups;
-  double s = 0.0, q = 0.0;
-  for (int r = 0; r < regions; ++r) {  // one region per sub-pixel phase (1 for an ordinary convolution)
-    const float* base = partial + r * region_stride + (static_cast<long long>(n) * slots_per_img * groups + g) * 2;
-    for (int t = lane; t < slots_per_img; t += 32) {
-      const float2 v = *reinterpret_cast<const float2*>(base + static_cast<long long>(t) * groups * 2);
-      s += v.x;
-      q += v.y;
+// stats[n][g] = (mean, rstd) from the per-tile partial sums written by the igemm epilogue ([image][slot][group][2] floats).
+// One block per image; thread (slot lane, group) walks the slots with a stride of `lanes`, so a warp reads 256 contiguous
+// bytes per slot (the one-warp-per-(n, g) version read one 8-byte pair per 32-byte sector and took 10 us on the 2048-slot
+// level-0 tensors).  Fixed summation order (deterministic), double accumulation.
+__global__ void __launch_bounds__(1024) gn_tiles_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats,
+                                                                 int groups, int slots_per_img, double count, float eps,
+                                                                 int regions, long long region_stride) {
+  extern __shared__ double fin_sm[];  // [2][lanes][groups]
+  const int n = blockIdx.x;
+  const int lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups, sl = threadIdx.x / groups;
+  if (sl < lanes) {
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < regions; ++r) {  // one region per sub-pixel phase (1 for an ordinary convolution)
+      const float2* base = reinterpret_cast<const float2*>(partial + r * region_stride) +
+                           static_cast<long long>(n) * slots_per_img * groups + g;
+#pragma unroll 4
+      for (int t = sl; t < slots_per_img; t += lanes) {
+        const float2 v = base[static_cast<long long>(t) * groups];
+        s += v.x;
+        q += v.y;
+      }
     }
+    fin_sm[sl * groups + g] = s;
+    fin_sm[(lanes + sl) * groups + g] = q;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
-  if (lane == 0) {
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    double s = 0.0, q = 0.0;
+    for (int l = 0; l < lanes; ++l) {
+      s += fin_sm[l * groups + g];
+      q += fin_sm[(lanes + l) * groups + g];
+    }
     const double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
-    stats[2 * pair] = static_cast<float>(mean);
-    stats[2 * pair + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    stats[2 * (n * groups + g)] = static_cast<float>(mean);
+    stats[2 * (n * groups + g) + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
 }
 
@@ -382,11 +394,14 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     if (sw > 0) {
       uint64_t odims[4] = {static_cast<uint64_t>(cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
                            static_cast<uint64_t>(a.N)};
-      const uint32_t obox[4] = {32u, static_cast<uint32_t>(sw), static_cast<uint32_t>(sh), static_cast<uint32_t>(sn)};
+      // BLOCK_N = 128: every epilogue warp owns 64 columns -> one 128-byte-row box per warp and tile
+      const bool wide = block_n == 128 && cout % 64 == 0 && !g_no_wide_store;
+      const uint32_t obox[4] = {wide ? 64u : 32u, static_cast<uint32_t>(sw), static_cast<uint32_t>(sh), static_cast<uint32_t>(sn)};
+      const int osw = wide ? 128 : 64;
       if (p.phases == 1) {
         uint64_t ostr[3] = {static_cast<uint64_t>(out_pix_stride) * es, static_cast<uint64_t>(Wo) * out_pix_stride * es,
                             static_cast<uint64_t>(Ho) * Wo * out_pix_stride * es};
-        int rc0 = encode_map(&p.out_map, out_dtype, 4, out, odims, ostr, obox, 64, false);
+        int rc0 = encode_map(&p.out_map, out_dtype, 4, out, odims, ostr, obox, osw, false);
         if (rc0) return rc0;
       } else {
         // phase (py, px) stores the parity sub-lattice out[:, py::2, px::2, :] of the (2 Ho) x (2 Wo) output
@@ -394,14 +409,14 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
         uint64_t ostr[3] = {2ull * out_pix_stride * es, 2ull * W2 * out_pix_stride * es, H2 * W2 * out_pix_stride * es};
         for (int q = 0; q < 4; ++q) {
           uint8_t* base = reinterpret_cast<uint8_t*>(out) + (static_cast<uint64_t>(q >> 1) * W2 + (q & 1)) * out_pix_stride * es;
-          int rc0 = encode_map(q == 0 ? &p.out_map : &p.out_map_ph[q - 1], out_dtype, 4, base, odims, ostr, obox, 64, false);
+          int rc0 = encode_map(q == 0 ? &p.out_map : &p.out_map_ph[q - 1], out_dtype, 4, base, odims, ostr, obox, osw, false);
           if (rc0) return rc0;
         }
       }
-      p.out_tma = 1;
+      p.out_tma = wide ? 2 : 1;
     }
   }
-  EOVAE_CHECK(p.phases == 1 || (p.out_tma == 1 && res == nullptr && p.box_n == 1),
+  EOVAE_CHECK(p.phases == 1 || (p.out_tma != 0 && res == nullptr && p.box_n == 1),
               "igemm: the sub-pixel upsample convolution needs the TMA-store epilogue (16-bit output, Cout >= 32, whole warps "
               "inside the pixel box), one image per tile and no residual");
   const int total_tiles = ceil_div(m_tiles_total, ctas) * p.n_tiles * p.phases;  // work items
@@ -425,6 +440,8 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
                     (block_n == 128 || (block_n == 256 && ctas == 2));
   // narrow-channel inputs (the dynamic input conv: 16 channels = one 32-byte chunk per tap): three taps per stage
   const bool kch3 = chunk_bytes == 32 && k_items % 3 == 0 && !g_force_kch1 && block_n == 128 && ctas == 2;
+  // ... all nine taps of a 3x3 kernel in ONE stage (one producer / MMA handshake per tile; 3 stages of 54 KB)
+  const bool kch9 = kch3 && k_items == 9 && !g_no_kch9;
   // halo reuse of the A tile across the three horizontal taps: m-tile = 128 consecutive pixels of one image row
   const bool halo = mode == EOVAE_CONV_3X3 && chunk_bytes == 128 && ctas == 2 && p.extra_chunks == 0 && p.box_w == 128 &&
                     p.box_h == 1 && p.box_n == 1 && (block_n == 16 || block_n == 128 || block_n == 256) && !g_no_halo;
@@ -455,6 +472,8 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     else if (block_n == 128) rc = launch_t<128, 128, 2, 1, true>(p, total_tiles, stream);
     else if (block_n == 16) rc = launch_t<16, 128, 2, 1, true>(p, total_tiles, stream);  // skinny-N: dynamic output conv
     else rc = launch_t<256, 128, 2, 1, true>(p, total_tiles, stream);
+  } else if (kch9) {
+    rc = launch_t<128, 32, 2, 9>(p, total_tiles, stream);
   } else if (kch3) {
     rc = launch_t<128, 32, 2, 3>(p, total_tiles, stream);
   } else if (kch2) {
@@ -475,11 +494,16 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     }
   }
   if (rc != 0 || gn_stats == nullptr) return rc;
-  const int pairs = p.Nimg * gn_groups;
-  gn_tiles_finalize_kernel<<<ceil_div(pairs, 4), 128, 0, stream>>>(p.gn_partial, gn_stats, pairs, gn_groups,
-                                                                   p.tiles_w * p.tiles_h * 4,
-                                                                   static_cast<double>(Ho) * Wo * p.gn_cpg * p.phases, gn_eps,
-                                                                   p.phases, p.gn_phase_stride);
+  {
+    const int slots = p.tiles_w * p.tiles_h * 4;
+    int lanes = slots < 32 ? slots : 32;
+    while (lanes > 1 && lanes * gn_groups > 1024) lanes >>= 1;
+    const int threads = round_up(lanes * gn_groups, 32);
+    EOVAE_CHECK(threads <= 1024, "igemm: too many GroupNorm groups (%d)", gn_groups);
+    gn_tiles_finalize_kernel<<<p.Nimg, threads, sizeof(double) * 2 * lanes * gn_groups, stream>>>(
+        p.gn_partial, gn_stats, gn_groups, slots, static_cast<double>(Ho) * Wo * p.gn_cpg * p.phases, gn_eps, p.phases,
+        p.gn_phase_stride);
+  }
   EOVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -504,6 +528,8 @@ void eovae_set_debug_mode(int mode) {
   g_force_kch1 = (mode >> 10) & 1;  // bit 10: force 64-channel pipeline stages
   g_no_tma_store = (mode >> 11) & 1;  // bit 11: disable the TMA-store epilogue
   g_no_halo = (mode >> 12) & 1;       // bit 12: disable the halo-reuse mainloop
+  g_no_kch9 = (mode >> 13) & 1;       // bit 13: three (not nine) taps per stage in the narrow-channel 3x3 conv
+  g_no_wide_store = (mode >> 14) & 1; // bit 14: 64-byte-row output boxes in the BLOCK_N = 128 kernels too
 }
 
 int eovae_conv_chunk_bytes(int cin) {

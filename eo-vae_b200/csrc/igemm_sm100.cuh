@@ -62,14 +62,15 @@ struct Params {
   float* gn_partial;
   int gn_cpg;                     // channels per group (1, 2, 4, 8, 16 or 32)
   int gn_groups;                  // Cout / gn_cpg
-  int debug_mode;                 // bit mask: 1 no epilogue work | 2 no MMA issue | 4 no TMA (tools/igemm_bench.py)
+  int debug_mode;                 // bit mask: 1 no epilogue work | 2 no MMA issue | 4 no TMA loads | 32 no bulk store issue | 64 no tcgen05.ld (tools/igemm_bench.py, epilogue_probe.py)
   // fused GroupNorm + SiLU of the INPUT (GNP kernels): A operand = silu(x * a[n][c] + b[n][c]), zero outside the image
   const float2* gnp_ab;           // [Nimg][Cin] (gamma * rstd, beta - mean * gamma * rstd)
   int gnp_cin;                    // channels of the input tensor
   int gnp_h, gnp_w;               // input extent (padding mask)
   int gnp_bf16;                   // activation element type of the A operand
   CUtensorMap out_map;            // 16-bit output, box = (32 channels, the 32 pixels of one epilogue warp), 64 B swizzle
-  int out_tma;                    // 1: epilogue stores through out_map (shared-memory staging + bulk tensor store)
+  int out_tma;                    // 1: epilogue stores through out_map (shared-memory staging + bulk tensor store);
+                                  // 2: the same with 64-channel boxes / 128-byte swizzle (BLOCK_N = 128 kernels)
   // Sub-pixel phases (nearest-x2 upsample + 3x3 conv as four 2x2 convs on the LOW-resolution input, layers.py:47-50): the
   // work item gains a phase index; phase q reads the taps shifted by (phase_dx, phase_dy)[q], uses the weight rows
   // [q * b_phase_rows, ...) of the packed matrix, stores through the q-th output map (the parity sub-lattice
@@ -677,6 +678,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
     const bool res16 = has_res && p.res_dtype != EOVAE_F32;
     const bool res_bf16 = p.res_dtype == EOVAE_BF16;
     const bool use_tma_store = (CW == 32) && p.out_tma != 0;
+    const bool wide_store = (HALF_N == 64) && p.out_tma == 2;  // out_map boxes are 64 channels wide, 128-byte swizzle
     uint8_t* stage_buf = epi_smem + ew * (2 * EPI_BUF_BYTES);  // two 32-row x 32-column 16-bit buffers per warp
     int sbuf = 0;
     int it = 0;
@@ -722,8 +724,13 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
       if (has_cols && !(p.debug_mode & 1)) {
         auto process = [&](const int c, uint4 (&r16)[4]) {
           uint32_t raw[32];
-          tc_ld16(taddr + c, raw);
-          if constexpr (CW == 32) tc_ld16(taddr + c + 16, raw + 16);
+          if (p.debug_mode & 64) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = 0u;
+          } else {
+            tc_ld16(taddr + c, raw);
+            if constexpr (CW == 32) tc_ld16(taddr + c + 16, raw + 16);
+          }
           const int n0 = n_tile0 + c;
           const bool full = n0 + CW <= p.Cout;
           // bias: warp-uniform 16-byte loads (one L1 line per instruction), in flight together with the TMEM load
@@ -794,7 +801,38 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
 #pragma unroll
                 for (int j = 0; j < CW / 2; ++j) pk[j] = T16<__half>::from_f2(v[2 * j], v[2 * j + 1]);
               }
-              if (use_tma_store) {
+              if (use_tma_store && wide_store) {
+                if constexpr (CW == 32 && HALF_N == 64) {
+                  // the warp's 64 columns leave as ONE 32-row x 128-byte box (128-byte swizzle: 16-byte piece j of row r at
+                  // piece j ^ (r & 7)): the bulk-store engine's cost is per ROW, so 128-byte rows halve it (measured on
+                  // the 16 -> 128 input conv, which is bound by it)
+                  const int q = (c - col_begin) / CW;  // which 64-byte half of the rows this chunk fills
+                  if (q == 0) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous tile's store drained
+                    __syncwarp();
+                  }
+                  const uint32_t rbase = smem_u32(stage_buf) + lane * 128;
+                  const int sw = lane & 7;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((q * 4 + j) ^ sw) << 4)),
+                                 "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                                 : "memory");
+                  if (q == 1) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && mt < m_tiles && sub * 32 < box_pix && !(p.debug_mode & 32)) {
+                      asm volatile(
+                          "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                              reinterpret_cast<uint64_t>(omap)),
+                          "r"(smem_u32(stage_buf)), "r"(n_tile0 + col_begin), "r"(tw * p.box_w + w_wi),
+                          "r"(th * p.box_h + w_hi), "r"(tn * p.box_n + w_ni)
+                          : "memory");
+                    }
+                    if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                  }
+                }
+              } else if (use_tma_store) {
                 if constexpr (CW == 32) {
                   // 32 rows x 64 bytes, 64-byte swizzle (16-byte piece j of row r lives at piece j ^ ((r >> 1) & 3)):
                   // conflict-free st.shared, then ONE bulk tensor store per warp and chunk - coalesced by the TMA

@@ -34,11 +34,12 @@ for cin, cout, label in ((16, 128, "dyn conv-in 16->128"), (128, 128, "L0 128->1
     wp = ops.pack_conv_weight(w, dt)
     bias = torch.zeros((cout,), device=dev)
     res = torch.randn((n, 256, 256, cout), device=dev, dtype=dt).permute(0, 3, 1, 2)
-    for name, mode, kw in (("stats + bias, TMA store", 0, dict(gn_groups=32)), ("no stats", 0, dict()),
-                           ("no stats, no bias", 0, dict(nobias=True)), ("stats, per-thread stores", 1 << 11, dict(gn_groups=32)),
-                           ("no stats, per-thread stores", 1 << 11, dict()), ("stats + residual", 0, dict(gn_groups=32, residual=res)),
-                           ("epilogue work off (garbage)", 1, dict(gn_groups=32)), ("MMA off (garbage)", 2, dict(gn_groups=32)),
-                           ("TMA loads off (garbage)", 4, dict(gn_groups=32))):
+    for name, mode, kw in (("stats + bias", 0, dict(gn_groups=32)), ("no stats", 0, dict()),
+                           ("loads+MMA off, no stats", 6, dict()), ("loads+MMA off, no stats, no store issue", 6 | 32, dict()),
+                           ("loads+MMA off, no stats, no tcgen05.ld", 6 | 64, dict()),
+                           ("loads+MMA off, no stats, no store, no tcgen05.ld", 6 | 32 | 64, dict()),
+                           ("loads+MMA off, stats", 6, dict(gn_groups=32)), ("loads+MMA off, stats, no store issue", 6 | 32, dict(gn_groups=32)),
+                           ("all actors off", 7, dict())):
         ops._C.lib().eovae_set_debug_mode(mode)
         nobias = kw.pop("nobias", False)
         ms = timeit(lambda: ops.conv2d(x, wp, None if nobias else bias, cout, ops.CONV_3X3, **kw))

@@ -13,6 +13,7 @@ namespace {
 int g_debug_mode = 0;
 int g_force_ctas = 0;  // 0 = auto, 1 / 2 = forced (tests, tools/igemm_bench.py)
 int g_force_kch1 = 0;  // 1 = always one K-chunk per stage
+int g_no_res_tma = 0;     // 1 = residual rows through registers even where the TMA path applies
 int g_no_wide_store = 0;  // 1 = 64-byte-row output boxes everywhere
 int g_no_kch9 = 0;     // 1 = narrow-channel 3x3 convs stage three taps (not all nine) per pipeline stage
 int g_no_tma_store = 0;  // 1 = epilogue writes with per-thread 16-byte stores instead of bulk tensor stores
@@ -414,6 +415,14 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
         }
       }
       p.out_tma = wide ? 2 : 1;
+      // residual of the same geometry: pulled by TMA into the store staging buffer (coalesced) instead of per-thread rows
+      if (wide && res != nullptr && res_dtype != EOVAE_F32 && p.phases == 1 && !g_no_res_tma) {
+        uint64_t rstr[3] = {static_cast<uint64_t>(res_pix_stride) * es, static_cast<uint64_t>(Wo) * res_pix_stride * es,
+                            static_cast<uint64_t>(Ho) * Wo * res_pix_stride * es};
+        int rc0 = encode_map(&p.res_map, res_dtype, 4, res, odims, rstr, obox, 128, false);
+        if (rc0) return rc0;
+        p.res_tma = 1;
+      }
     }
   }
   EOVAE_CHECK(p.phases == 1 || (p.out_tma != 0 && res == nullptr && p.box_n == 1),
@@ -530,6 +539,7 @@ void eovae_set_debug_mode(int mode) {
   g_no_halo = (mode >> 12) & 1;       // bit 12: disable the halo-reuse mainloop
   g_no_kch9 = (mode >> 13) & 1;       // bit 13: three (not nine) taps per stage in the narrow-channel 3x3 conv
   g_no_wide_store = (mode >> 14) & 1; // bit 14: 64-byte-row output boxes in the BLOCK_N = 128 kernels too
+  g_no_res_tma = (mode >> 15) & 1;    // bit 15: residual through per-thread loads even where the TMA path applies
 }
 
 int eovae_conv_chunk_bytes(int cin) {

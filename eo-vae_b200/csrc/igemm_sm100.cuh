@@ -80,6 +80,8 @@ struct Params {
   int b_phase_rows;
   long long gn_phase_stride;      // floats between the phases' regions of gn_partial
   CUtensorMap out_map_ph[3];      // output maps of phases 1..3 (phase 0 = out_map)
+  CUtensorMap res_map;            // residual with the geometry of the wide out_map (res_tma = 1)
+  int res_tma;                    // 1: the epilogue warps pull their residual box into the store staging buffer by TMA
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint64_t* a_full = bars + 2 * STAGES + 6;       // GNP: this CTA's raw A tile has landed (local)
   uint64_t* ready_bar = bars + 3 * STAGES + 6;    // GNP: A tiles of the whole group are transformed (leader's copy)
+  uint64_t* res_bar = bars + 4 * STAGES + 6;      // per epilogue warp: its residual box has landed in its staging buffer
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 1024;  // TMA-store staging: 8 warps x 2 x 2 KB, 1 KB aligned
   constexpr int EPI_BUF_BYTES = 32 * 64;
   uint8_t* coef_smem = epi_smem + Cfg::EPI_BYTES;  // GNP only (the launch adds GNP_COEF_BYTES)
@@ -355,6 +358,8 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
       mbar_init(&full_bar[i], CTAS);   // one producer arrive per CTA of the group (the leader's copy is the live one)
       mbar_init(&empty_bar[i], 1);
     }
+    for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
+    if (p.res_tma) prefetch_tmap(&p.res_map);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], NUM_EPI_WARPS * CTAS);  // one arrive per epilogue warp of every CTA of the group
@@ -674,11 +679,15 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
     const int w_wi = (sub * 32) % p.box_w, w_hi = ((sub * 32) / p.box_w) % p.box_h, w_ni = (sub * 32) / (p.box_w * p.box_h);
     const bool out16 = p.out_dtype != EOVAE_F32;
     const bool out_bf16 = p.out_dtype == EOVAE_BF16;
-    const bool has_res = p.res != nullptr;
-    const bool res16 = has_res && p.res_dtype != EOVAE_F32;
-    const bool res_bf16 = p.res_dtype == EOVAE_BF16;
     const bool use_tma_store = (CW == 32) && p.out_tma != 0;
     const bool wide_store = (HALF_N == 64) && p.out_tma == 2;  // out_map boxes are 64 channels wide, 128-byte swizzle
+    // residual: either the warp's 32-pixel x 64-channel box arrives by TMA in the store staging buffer (coalesced,
+    // asynchronous, under the mainloop of the tile), or every thread reads its own pixel row through registers
+    const bool res_tma = wide_store && p.res_tma != 0;
+    const bool has_res = p.res != nullptr && !res_tma;
+    const bool res16 = has_res && p.res_dtype != EOVAE_F32;
+    const bool res_bf16 = p.res_dtype == EOVAE_BF16;
+    uint32_t res_phase = 0;
     uint8_t* stage_buf = epi_smem + ew * (2 * EPI_BUF_BYTES);  // two 32-row x 32-column 16-bit buffers per warp
     int sbuf = 0;
     int it = 0;
@@ -697,6 +706,18 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
       const bool valid = mt < m_tiles && row < box_pix && ox < p.Wo && oy < p.Ho && on < p.Nimg;
       const long long pix = (static_cast<long long>(on) * p.Ho + oy) * p.Wo + ox;
       const int n_tile0 = nt * BLOCK_N;
+      if constexpr (CW == 32 && HALF_N == 64) {
+        if (res_tma && lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the buffer's previous store has been read out
+          if (mt < m_tiles && sub * 32 < box_pix && n_tile0 + col_begin < p.Cout) {
+            mbar_expect_tx(&res_bar[ew], 32 * 128);
+            tma_load_4d(&p.res_map, &res_bar[ew], stage_buf, n_tile0 + col_begin, tw * p.box_w + w_wi, th * p.box_h + w_hi,
+                        tn * p.box_n + w_ni);
+          } else {
+            mbar_arrive(&res_bar[ew]);  // keeps the phase in step with the tile count
+          }
+        }
+      }
       // pull this thread's residual row segment into L2 while the mainloop of this tile is still running
       if (has_res && valid && has_cols) {
         const int esz = p.res_dtype == EOVAE_F32 ? 4 : 2;
@@ -813,6 +834,32 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
                   }
                   const uint32_t rbase = smem_u32(stage_buf) + lane * 128;
                   const int sw = lane & 7;
+                  if (res_tma) {
+                    // this lane's residual row pieces sit where its output pieces go (same box, same swizzle): add in
+                    // fp32, round once, write back in place
+                    if (q == 0) mbar_wait(&res_bar[ew], res_phase);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      uint32_t rr[4];
+                      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                   : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3])
+                                   : "r"(rbase + (((q * 4 + j) ^ sw) << 4))
+                                   : "memory");
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        const float2 f = p.res_dtype == EOVAE_BF16 ? T16<__nv_bfloat16>::to_f2(rr[e]) : T16<__half>::to_f2(rr[e]);
+                        v[8 * j + 2 * e] += f.x;
+                        v[8 * j + 2 * e + 1] += f.y;
+                      }
+                    }
+                    if (out_bf16) {
+#pragma unroll
+                      for (int j = 0; j < CW / 2; ++j) pk[j] = T16<__nv_bfloat16>::from_f2(v[2 * j], v[2 * j + 1]);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < CW / 2; ++j) pk[j] = T16<__half>::from_f2(v[2 * j], v[2 * j + 1]);
+                    }
+                  }
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((q * 4 + j) ^ sw) << 4)),
@@ -912,6 +959,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
       if (lane == 0) {
         if (leader) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_leader(&tmem_empty[acc]);
       }
+      if (res_tma) res_phase ^= 1;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp complete
   }

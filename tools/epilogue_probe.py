@@ -28,20 +28,23 @@ def timeit(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
-for cin, cout, label in ((16, 128, "dyn conv-in 16->128"), (128, 128, "L0 128->128")):
-    x = torch.randn((n, 256, 256, cin), device=dev, dtype=dt).permute(0, 3, 1, 2)
+for cin, cout, label, hw in ((16, 128, "dyn conv-in 16->128", 256), (128, 128, "L0 128->128", 256), (256, 256, "L1 256->256", 128),
+                             (512, 512, "L2 512->512", 64)):
+    x = torch.randn((n, hw, hw, cin), device=dev, dtype=dt).permute(0, 3, 1, 2)
     w = torch.randn((cout, cin, 3, 3), device=dev) * 0.05
     wp = ops.pack_conv_weight(w, dt)
     bias = torch.zeros((cout,), device=dev)
-    res = torch.randn((n, 256, 256, cout), device=dev, dtype=dt).permute(0, 3, 1, 2)
+    res = torch.randn((n, hw, hw, cout), device=dev, dtype=dt).permute(0, 3, 1, 2)
     for name, mode, kw in (("stats + bias", 0, dict(gn_groups=32)), ("no stats", 0, dict()),
                            ("loads+MMA off, no stats", 6, dict()), ("loads+MMA off, no stats, no store issue", 6 | 32, dict()),
                            ("loads+MMA off, no stats, no tcgen05.ld", 6 | 64, dict()),
                            ("loads+MMA off, no stats, no store, no tcgen05.ld", 6 | 32 | 64, dict()),
                            ("loads+MMA off, stats", 6, dict(gn_groups=32)), ("loads+MMA off, stats, no store issue", 6 | 32, dict(gn_groups=32)),
+                           ("stats + residual (TMA)", 0, dict(gn_groups=32, residual=res)),
+                           ("stats + residual (registers)", 1 << 15, dict(gn_groups=32, residual=res)),
                            ("all actors off", 7, dict())):
         ops._C.lib().eovae_set_debug_mode(mode)
         nobias = kw.pop("nobias", False)
         ms = timeit(lambda: ops.conv2d(x, wp, None if nobias else bias, cout, ops.CONV_3X3, **kw))
-        print(f"{label:22s} {name:32s} {ms:.3f} ms  ({n * 65536 * cout * 2 / ms / 1e6:.0f} GB/s written)", flush=True)
+        print(f"{label:22s} {name:32s} {ms:.3f} ms  ({n * hw * hw * cout * 2 / ms / 1e6:.0f} GB/s written)", flush=True)
     ops._C.lib().eovae_set_debug_mode(0)

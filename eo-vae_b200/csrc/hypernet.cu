@@ -242,6 +242,7 @@ __global__ void sgemm_reduce_kernel(const float* __restrict__ part, int splits, 
   const int batch = static_cast<int>(i / per);
   const long long r = i % per;
   float v = 0.f;
+#pragma unroll 8
   for (int z = 0; z < splits; ++z) v += part[(static_cast<long long>(z) * batches + batch) * per + r];
   float* o = c + batch * c_bs + (r / n) * ldc + (r % n);
   *o = (accumulate ? *o : 0.f) + v;
@@ -279,14 +280,27 @@ int sgemm(const float* a, long long a_rs, long long a_cs, const float* b, long l
   return sgemm_b(a, a_rs, a_cs, 0, b, b_rs, b_cs, 0, c, ldc, 0, 1, m, n, k, accumulate, g_sgemm_part, st);
 }
 
-// out[j] (+)= sum_r x[r][j]
-__global__ void colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out,
-                                  int accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= cols) return;
+// out[j] (+)= sum_r x[r][j].  Block = 32 columns x 8 row lanes (one thread per column walked the rows as one dependent
+// chain: 10-40 us per launch at the hypernetwork's 140 x 128..2048 shapes); fixed combination order (deterministic).
+constexpr int COLSUM_LANES = 8;
+__global__ void __launch_bounds__(32 * COLSUM_LANES) colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows,
+                                                                       int cols, float* __restrict__ out, int accumulate) {
+  __shared__ float part[COLSUM_LANES][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cx;
   float a = 0.f;
-  for (int r = 0; r < rows; ++r) a += x[r * ld + j];
-  out[j] = (accumulate ? out[j] : 0.f) + a;
+  if (j < cols) {
+#pragma unroll 4
+    for (int r = ry; r < rows; r += COLSUM_LANES) a += x[r * ld + j];
+  }
+  part[ry][cx] = a;
+  __syncthreads();
+  if (ry == 0 && j < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < COLSUM_LANES; ++l) t += part[l][cx];
+    out[j] = (accumulate ? out[j] : 0.f) + t;
+  }
 }
 
 // y[i] = act(z[i]) (forward with a saved pre-activation) / dz[i] = dy[i] * act'(z[i])
@@ -350,19 +364,36 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
     rowstat[2 * row + 1] = rstd;
   }
 }
-__global__ void layernorm_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                           const float* __restrict__ rowstat, float* __restrict__ dg, float* __restrict__ db,
-                                           int rows, int d) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= d) return;
+__global__ void __launch_bounds__(32 * COLSUM_LANES) layernorm_bwd_param_kernel(const float* __restrict__ x,
+                                                                                const float* __restrict__ dy,
+                                                                                const float* __restrict__ rowstat,
+                                                                                float* __restrict__ dg, float* __restrict__ db,
+                                                                                int rows, int d) {
+  __shared__ float pa[COLSUM_LANES][32], pb[COLSUM_LANES][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cx;
   float a = 0.f, b = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    const float g = dy[static_cast<long long>(r) * d + j];
-    a += g * (x[static_cast<long long>(r) * d + j] - rowstat[2 * r]) * rowstat[2 * r + 1];
-    b += g;
+  if (j < d) {
+#pragma unroll 4
+    for (int r = ry; r < rows; r += COLSUM_LANES) {
+      const float g = dy[static_cast<long long>(r) * d + j];
+      a += g * (x[static_cast<long long>(r) * d + j] - rowstat[2 * r]) * rowstat[2 * r + 1];
+      b += g;
+    }
   }
-  dg[j] = a;
-  db[j] = b;
+  pa[ry][cx] = a;
+  pb[ry][cx] = b;
+  __syncthreads();
+  if (ry == 0 && j < d) {
+    float ta = 0.f, tb = 0.f;
+#pragma unroll
+    for (int l = 0; l < COLSUM_LANES; ++l) {
+      ta += pa[l][cx];
+      tb += pb[l][cx];
+    }
+    dg[j] = ta;
+    db[j] = tb;
+  }
 }
 
 // attention backward, pass 1: one warp per (head, query): recompute the probability row, dP = dO V^T,
@@ -668,7 +699,7 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
   float* dwaves = da;  // [c][d]
   // wk = headin Wfw^T + bfw
   if (sgemm(dwk, 1, ne, headin, d, 1, grads[7], d, ne, d, c, 0, st)) return -1;            // dWfw [9E][d] = dwk^T headin
-  colsum_f32_kernel<<<ceil_div(ne, 128), 128, 0, st>>>(dwk, ne, c, ne, grads[8], 0);
+  colsum_f32_kernel<<<ceil_div(ne, 32), 32 * COLSUM_LANES, 0, st>>>(dwk, ne, c, ne, grads[8], 0);
   EOVAE_LAUNCH_CHECK();
   if (sgemm(dwk, ne, 1, params[7], d, 1, dwaves, d, c, d, ne, 0, st)) return -1;            // dheadin [c][d] = dwk Wfw
   axpy_kernel<<<blocks_for(cd), 256, 0, st>>>(dwaves, 1.f, dx + 128 * d, cd, 1);
@@ -679,12 +710,12 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
     axpy_kernel<<<blocks_for(c), 256, 0, st>>>(dbias, bias_scale, rowstat, c, 0);           // d(bias_raw) [c]
     EOVAE_LAUNCH_CHECK();
     if (sgemm(rowstat, 0, 1, headin2, d, 1, grads[9], d, 1, d, c, 0, st)) return -1;        // dwfb [1][d]
-    colsum_f32_kernel<<<1, 32, 0, st>>>(rowstat, 1, c, 1, grads[10], 0);
+    colsum_f32_kernel<<<1, 32 * COLSUM_LANES, 0, st>>>(rowstat, 1, c, 1, grads[10], 0);
     EOVAE_LAUNCH_CHECK();
     if (sgemm(rowstat, 1, 0, params[9], 0, 1, db_, d, c, d, 1, 0, st)) return -1;           // dheadin2 [c][d] = db (x) wfb
     axpy_kernel<<<blocks_for(cd), 256, 0, st>>>(db_, 1.f, dx + 128 * d, cd, 1);
     EOVAE_LAUNCH_CHECK();
-    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(db_, d, c, d, grads[2], 1);         // bias_token (broadcast add)
+    colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(db_, d, c, d, grads[2], 1);         // bias_token (broadcast add)
     EOVAE_LAUNCH_CHECK();
   } else {
     // bias[E] = bias_scale * (x_last Wfb^T + bfb), Wfb [E][d]
@@ -702,12 +733,12 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
     float* dtmp2 = db_;
     layernorm_bwd_kernel<<<ceil_div(s, 4), 128, 0, st>>>(L[l].tmp2, lp[10], dx, dtmp2, rowstat, s, d, 1e-5f);
     EOVAE_LAUNCH_CHECK();
-    layernorm_bwd_param_kernel<<<ceil_div(d, 128), 128, 0, st>>>(L[l].tmp2, dx, rowstat, lg[10], lg[11], s, d);
+    layernorm_bwd_param_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(L[l].tmp2, dx, rowstat, lg[10], lg[11], s, d);
     EOVAE_LAUNCH_CHECK();
     // tmp2 = ffh W2^T + b2 + x1
     if (sgemm(dtmp2, d, 1, lp[6], ff, 1, dffh, ff, s, ff, d, 0, st)) return -1;             // dffh = dtmp2 W2
     if (sgemm(dtmp2, 1, d, L[l].ffh, ff, 1, lg[6], ff, d, ff, s, 0, st)) return -1;          // dW2 [d][ff]
-    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dtmp2, d, s, d, lg[7], 0);
+    colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(dtmp2, d, s, d, lg[7], 0);
     EOVAE_LAUNCH_CHECK();
     gelu_bwd_kernel<<<blocks_for(sf), 256, 0, st>>>(L[l].z, dffh, dz, sf);
     EOVAE_LAUNCH_CHECK();
@@ -716,18 +747,18 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
     EOVAE_CUDA(cudaMemcpyAsync(dx1, dtmp2, sizeof(float) * sd, cudaMemcpyDeviceToDevice, st));
     if (sgemm(dz, ff, 1, lp[4], d, 1, dx1, d, s, d, ff, 1, st)) return -1;
     if (sgemm(dz, 1, ff, L[l].x1, d, 1, lg[4], d, ff, d, s, 0, st)) return -1;               // dW1 [ff][d]
-    colsum_f32_kernel<<<ceil_div(ff, 128), 128, 0, st>>>(dz, ff, s, ff, lg[5], 0);
+    colsum_f32_kernel<<<ceil_div(ff, 32), 32 * COLSUM_LANES, 0, st>>>(dz, ff, s, ff, lg[5], 0);
     EOVAE_LAUNCH_CHECK();
     float* dtmp1 = db_;
     layernorm_bwd_kernel<<<ceil_div(s, 4), 128, 0, st>>>(L[l].tmp1, lp[8], dx1, dtmp1, rowstat, s, d, 1e-5f);
     EOVAE_LAUNCH_CHECK();
-    layernorm_bwd_param_kernel<<<ceil_div(d, 128), 128, 0, st>>>(L[l].tmp1, dx1, rowstat, lg[8], lg[9], s, d);
+    layernorm_bwd_param_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(L[l].tmp1, dx1, rowstat, lg[8], lg[9], s, d);
     EOVAE_LAUNCH_CHECK();
     // tmp1 = att Wo^T + bo + xin
     float* datt = dc;
     if (sgemm(dtmp1, d, 1, lp[2], d, 1, datt, d, s, d, d, 0, st)) return -1;
     if (sgemm(dtmp1, 1, d, L[l].att, d, 1, lg[2], d, d, d, s, 0, st)) return -1;             // dWo [d][d]
-    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dtmp1, d, s, d, lg[3], 0);
+    colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(dtmp1, d, s, d, lg[3], 0);
     EOVAE_LAUNCH_CHECK();
     mha_bwd_q_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(L[l].qkv, datt, pbuf, dsbuf, dqkv, s, d, heads);
     EOVAE_LAUNCH_CHECK();
@@ -740,7 +771,7 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
     EOVAE_CUDA(cudaMemcpyAsync(dx, dtmp1, sizeof(float) * sd, cudaMemcpyDeviceToDevice, st));
     if (sgemm(dqkv, 3 * d, 1, lp[0], d, 1, dx, d, s, d, 3 * d, 1, st)) return -1;
     if (sgemm(dqkv, 1, 3 * d, lin, d, 1, lg[0], d, 3 * d, d, s, 0, st)) return -1;           // dWin [3d][d]
-    colsum_f32_kernel<<<ceil_div(3 * d, 128), 128, 0, st>>>(dqkv, 3 * d, s, 3 * d, lg[1], 0);
+    colsum_f32_kernel<<<ceil_div(3 * d, 32), 32 * COLSUM_LANES, 0, st>>>(dqkv, 3 * d, s, 3 * d, lg[1], 0);
     EOVAE_LAUNCH_CHECK();
   }
 
@@ -755,14 +786,14 @@ int eovae_hypernet_backward(const float* wvs_um, int c, const float* const* para
   relu_bwd_kernel<<<blocks_for(cd), 256, 0, st>>>(waves, emb, dwaves, du2, cd);
   EOVAE_LAUNCH_CHECK();
   if (sgemm(du2, 1, d, t1, d, 1, grads[5], d, d, d, c, 0, st)) return -1;
-  colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(du2, d, c, d, grads[6], 0);
+  colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(du2, d, c, d, grads[6], 0);
   EOVAE_LAUNCH_CHECK();
   float* dt1 = dc;
   if (sgemm(du2, d, 1, params[5], d, 1, dt1, d, c, d, d, 0, st)) return -1;
   relu_bwd_kernel<<<blocks_for(cd), 256, 0, st>>>(t1, nullptr, dt1, dt1, cd);
   EOVAE_LAUNCH_CHECK();
   if (sgemm(dt1, 1, d, emb, d, 1, grads[3], d, d, d, c, 0, st)) return -1;
-  colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dt1, d, c, d, grads[4], 0);
+  colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(dt1, d, c, d, grads[4], 0);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -928,13 +959,13 @@ int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* 
   EOVAE_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * sd, st));
   // wk = hg W2h^T + b2h
   if (sgemm(t.dwk, 1, ne, t.hg, rank, 1, grads[9], rank, ne, rank, c, 0, st)) return -1;      // dW2h [9E][rank]
-  colsum_f32_kernel<<<ceil_div(ne, 128), 128, 0, st>>>(t.dwk, ne, c, ne, grads[10], 0);
+  colsum_f32_kernel<<<ceil_div(ne, 32), 32 * COLSUM_LANES, 0, st>>>(t.dwk, ne, c, ne, grads[10], 0);
   EOVAE_LAUNCH_CHECK();
   if (sgemm(t.dwk, ne, 1, params[9], rank, 1, t.dhg, rank, c, rank, ne, 0, st)) return -1;    // dhg [c][rank]
   gelu_bwd_kernel<<<blocks_for(cr), 256, 0, st>>>(t.hr, t.dhg, t.dhr, cr);
   EOVAE_LAUNCH_CHECK();
   if (sgemm(t.dhr, 1, rank, t.headin, d, 1, grads[7], d, rank, d, c, 0, st)) return -1;       // dW0 [rank][d]
-  colsum_f32_kernel<<<ceil_div(rank, 128), 128, 0, st>>>(t.dhr, rank, c, rank, grads[8], 0);
+  colsum_f32_kernel<<<ceil_div(rank, 32), 32 * COLSUM_LANES, 0, st>>>(t.dhr, rank, c, rank, grads[8], 0);
   EOVAE_LAUNCH_CHECK();
   float* dfeat = da;  // [c][d] gradient of features = T[128:128+C] + waves
   if (sgemm(t.dhr, rank, 1, params[7], d, 1, dfeat, d, c, d, rank, 0, st)) return -1;
@@ -943,12 +974,12 @@ int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* 
     axpy_kernel<<<blocks_for(c), 256, 0, st>>>(dbias, bias_scale, rowstat, c, 0);             // d(bias_raw) [c]
     EOVAE_LAUNCH_CHECK();
     if (sgemm(rowstat, 0, 1, t.headin2, d, 1, grads[11], d, 1, d, c, 0, st)) return -1;       // dwfb [1][d]
-    colsum_f32_kernel<<<1, 32, 0, st>>>(rowstat, 1, c, 1, grads[12], 0);
+    colsum_f32_kernel<<<1, 32 * COLSUM_LANES, 0, st>>>(rowstat, 1, c, 1, grads[12], 0);
     EOVAE_LAUNCH_CHECK();
     if (sgemm(rowstat, 1, 0, params[11], 0, 1, db_, d, c, d, 1, 0, st)) return -1;            // dheadin2 [c][d]
     axpy_kernel<<<blocks_for(cd), 256, 0, st>>>(db_, 1.f, dfeat, cd, 1);                      // headin2 = features + btok
     EOVAE_LAUNCH_CHECK();
-    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(db_, d, c, d, grads[2], 1);
+    colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(db_, d, c, d, grads[2], 1);
     EOVAE_LAUNCH_CHECK();
   } else {
     axpy_kernel<<<blocks_for(embed), 256, 0, st>>>(dbias, bias_scale, grads[12], embed, 0);
@@ -969,7 +1000,7 @@ int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* 
     // xout = x1 + ffh W2^T + b2
     if (sgemm(dx, d, 1, lp[6], ff, 1, dffh, ff, s, ff, d, 0, st)) return -1;                  // dffh = dx W2
     if (sgemm(dx, 1, d, L.ffh, ff, 1, lg[6], ff, d, ff, s, 0, st)) return -1;                 // dW2 [d][ff]
-    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dx, d, s, d, lg[7], 0);
+    colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(dx, d, s, d, lg[7], 0);
     EOVAE_LAUNCH_CHECK();
     gelu_bwd_kernel<<<blocks_for(sf), 256, 0, st>>>(L.z, dffh, dz, sf);
     EOVAE_LAUNCH_CHECK();
@@ -977,13 +1008,13 @@ int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* 
     float* dln2 = db_;
     if (sgemm(dz, ff, 1, lp[4], d, 1, dln2, d, s, d, ff, 0, st)) return -1;
     if (sgemm(dz, 1, ff, L.ln2, d, 1, lg[4], d, ff, d, s, 0, st)) return -1;                  // dW1 [ff][d]
-    colsum_f32_kernel<<<ceil_div(ff, 128), 128, 0, st>>>(dz, ff, s, ff, lg[5], 0);
+    colsum_f32_kernel<<<ceil_div(ff, 32), 32 * COLSUM_LANES, 0, st>>>(dz, ff, s, ff, lg[5], 0);
     EOVAE_LAUNCH_CHECK();
     // ln2 = LN(x1; norm2): dx1 = dx + LN'(dln2)
     float* dx1 = dc;
     layernorm_bwd_kernel<<<ceil_div(s, 4), 128, 0, st>>>(L.x1, lp[10], dln2, dx1, rowstat, s, d, 1e-5f);
     EOVAE_LAUNCH_CHECK();
-    layernorm_bwd_param_kernel<<<ceil_div(d, 128), 128, 0, st>>>(L.x1, dln2, rowstat, lg[10], lg[11], s, d);
+    layernorm_bwd_param_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(L.x1, dln2, rowstat, lg[10], lg[11], s, d);
     EOVAE_LAUNCH_CHECK();
     axpy_kernel<<<blocks_for(sd), 256, 0, st>>>(dx, 1.f, dx1, sd, 1);
     EOVAE_LAUNCH_CHECK();
@@ -991,7 +1022,7 @@ int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* 
     float* datt = db_;
     if (sgemm(dx1, d, 1, lp[2], d, 1, datt, d, s, d, d, 0, st)) return -1;
     if (sgemm(dx1, 1, d, L.att, d, 1, lg[2], d, d, d, s, 0, st)) return -1;                   // dWo [d][d]
-    colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dx1, d, s, d, lg[3], 0);
+    colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(dx1, d, s, d, lg[3], 0);
     EOVAE_LAUNCH_CHECK();
     mha_bwd_q_kernel<<<ceil_div(s * heads, 4), 128, 0, st>>>(L.qkv, datt, t.pbuf, t.dsbuf, dqkv, s, d, heads);
     EOVAE_LAUNCH_CHECK();
@@ -1004,11 +1035,11 @@ int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* 
     float* dln1 = db_;
     if (sgemm(dqkv, 3 * d, 1, lp[0], d, 1, dln1, d, s, d, 3 * d, 0, st)) return -1;
     if (sgemm(dqkv, 1, 3 * d, L.ln1, d, 1, lg[0], d, 3 * d, d, s, 0, st)) return -1;           // dWin [3d][d]
-    colsum_f32_kernel<<<ceil_div(3 * d, 128), 128, 0, st>>>(dqkv, 3 * d, s, 3 * d, lg[1], 0);
+    colsum_f32_kernel<<<ceil_div(3 * d, 32), 32 * COLSUM_LANES, 0, st>>>(dqkv, 3 * d, s, 3 * d, lg[1], 0);
     EOVAE_LAUNCH_CHECK();
     layernorm_bwd_kernel<<<ceil_div(s, 4), 128, 0, st>>>(lin, lp[8], dln1, dx, rowstat, s, d, 1e-5f);
     EOVAE_LAUNCH_CHECK();
-    layernorm_bwd_param_kernel<<<ceil_div(d, 128), 128, 0, st>>>(lin, dln1, rowstat, lg[8], lg[9], s, d);
+    layernorm_bwd_param_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(lin, dln1, rowstat, lg[8], lg[9], s, d);
     EOVAE_LAUNCH_CHECK();
     axpy_kernel<<<blocks_for(sd), 256, 0, st>>>(dx1, 1.f, dx, sd, 1);
     EOVAE_LAUNCH_CHECK();
@@ -1024,14 +1055,14 @@ int eovae_hypernet_factorized_backward(const float* wvs_um, int c, const float* 
   relu_bwd_kernel<<<blocks_for(cd), 256, 0, st>>>(t.waves, t.emb, dwaves, du2, cd);
   EOVAE_LAUNCH_CHECK();
   if (sgemm(du2, 1, d, t.t1, d, 1, grads[5], d, d, d, c, 0, st)) return -1;
-  colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(du2, d, c, d, grads[6], 0);
+  colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(du2, d, c, d, grads[6], 0);
   EOVAE_LAUNCH_CHECK();
   float* dt1 = dc;
   if (sgemm(du2, d, 1, params[5], d, 1, dt1, d, c, d, d, 0, st)) return -1;
   relu_bwd_kernel<<<blocks_for(cd), 256, 0, st>>>(t.t1, nullptr, dt1, dt1, cd);
   EOVAE_LAUNCH_CHECK();
   if (sgemm(dt1, 1, d, t.emb, d, 1, grads[3], d, d, d, c, 0, st)) return -1;
-  colsum_f32_kernel<<<ceil_div(d, 128), 128, 0, st>>>(dt1, d, c, d, grads[4], 0);
+  colsum_f32_kernel<<<ceil_div(d, 32), 32 * COLSUM_LANES, 0, st>>>(dt1, d, c, d, grads[4], 0);
   EOVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -443,7 +443,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   const int co = static_cast<int>(t % cout);
   const int tap = static_cast<int>(t / cout);
   double acc = 0.0;
-  for (int k = 0; k < ksplit; ++k) acc += partial[static_cast<long long>(k) * total + i];
+#pragma unroll 8
+  for (int k = 0; k < ksplit; ++k) acc += partial[static_cast<long long>(k) * total + i];  // unrolled: loads issued in batches
   float* o = dw + (static_cast<long long>(co) * cin + ci) * taps + tap;
   *o = (accumulate ? *o : 0.f) + static_cast<float>(acc);
 }

@@ -35,17 +35,22 @@ __global__ void __launch_bounds__(256) linear_partial_kernel(const float* __rest
   const int kb = blockIdx.z * k_per_split;
   const int ke = min(k, kb + k_per_split);
   float acc[4][4] = {};
+  // 64 rows x 16 k per operand and step: one float4 per thread each, fetched one step ahead into registers so the
+  // global-load latency hides behind the previous step's FMAs (these GEMMs run 10-30 blocks: latency, not throughput)
+  const int rr = threadIdx.x / 4, kk4 = (threadIdx.x % 4) * 4;
+  auto fetch = [&](int k0, float4& v, float4& u) {
+    v = make_float4(0.f, 0.f, 0.f, 0.f);
+    u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + rr < s && k0 + kk4 < ke) v = *reinterpret_cast<const float4*>(&x[static_cast<long long>(row0 + rr) * ldx + k0 + kk4]);
+    if (col0 + rr < n && k0 + kk4 < ke) u = __ldg(reinterpret_cast<const float4*>(&w[static_cast<long long>(col0 + rr) * k + k0 + kk4]));
+  };
+  float4 v, u;
+  if (kb < ke) fetch(kb, v, u);
   for (int k0 = kb; k0 < ke; k0 += LBK) {
-    {  // 64 rows x 16 k: one float4 per thread for each operand
-      const int rr = threadIdx.x / 4, kk = (threadIdx.x % 4) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + rr < s && k0 + kk < ke) v = *reinterpret_cast<const float4*>(&x[static_cast<long long>(row0 + rr) * ldx + k0 + kk]);
-      xs[kk][rr] = v.x; xs[kk + 1][rr] = v.y; xs[kk + 2][rr] = v.z; xs[kk + 3][rr] = v.w;
-      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col0 + rr < n && k0 + kk < ke) u = __ldg(reinterpret_cast<const float4*>(&w[static_cast<long long>(col0 + rr) * k + k0 + kk]));
-      ws[kk][rr] = u.x; ws[kk + 1][rr] = u.y; ws[kk + 2][rr] = u.z; ws[kk + 3][rr] = u.w;
-    }
+    xs[kk4][rr] = v.x; xs[kk4 + 1][rr] = v.y; xs[kk4 + 2][rr] = v.z; xs[kk4 + 3][rr] = v.w;
+    ws[kk4][rr] = u.x; ws[kk4 + 1][rr] = u.y; ws[kk4 + 2][rr] = u.z; ws[kk4 + 3][rr] = u.w;
     __syncthreads();
+    if (k0 + LBK < ke) fetch(k0 + LBK, v, u);
 #pragma unroll
     for (int kk = 0; kk < LBK; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(&xs[kk][ty * 4]);
@@ -197,15 +202,30 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
   const int kb = split * k_per_split;
   const int ke = min(k, kb + k_per_split);
   float acc[4][4] = {};
-  for (int k0 = kb; k0 < ke; k0 += LBK) {
-    for (int e = threadIdx.x; e < LBM * LBK; e += 256) {
+  // every thread owns 4 elements of each 64 x 16 operand tile, fetched one k-step ahead into registers
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + q * 256;
       // consecutive threads walk the unit-stride direction of A (rows when A is read transposed, a_rs == 1)
       const int kk = a_rs == 1 ? e / LBM : e % LBK, rr = a_rs == 1 ? e % LBM : e / LBK;
-      as[kk][rr] = (row0 + rr < m && k0 + kk < ke) ? a[(row0 + rr) * a_rs + (k0 + kk) * a_cs] : 0.f;
+      ra[q] = (row0 + rr < m && k0 + kk < ke) ? a[(row0 + rr) * a_rs + (k0 + kk) * a_cs] : 0.f;
       const int cc = e % LBN, k2 = e / LBN;
-      bs[k2][cc] = (col0 + cc < n && k0 + k2 < ke) ? b[(k0 + k2) * b_rs + (col0 + cc) * b_cs] : 0.f;
+      rb[q] = (col0 + cc < n && k0 + k2 < ke) ? b[(k0 + k2) * b_rs + (col0 + cc) * b_cs] : 0.f;
+    }
+  };
+  if (kb < ke) fetch(kb);
+  for (int k0 = kb; k0 < ke; k0 += LBK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + q * 256;
+      const int kk = a_rs == 1 ? e / LBM : e % LBK, rr = a_rs == 1 ? e % LBM : e / LBK;
+      as[kk][rr] = ra[q];
+      bs[e / LBN][e % LBN] = rb[q];
     }
     __syncthreads();
+    if (k0 + LBK < ke) fetch(k0 + LBK);
 #pragma unroll
     for (int kk = 0; kk < LBK; ++kk) {
       const float4 av4 = *reinterpret_cast<const float4*>(&as[kk][ty * 4]);

@@ -4,6 +4,7 @@
 // (eovae_pack_conv_weight_dgrad); weight gradients are in wgrad_sm100.cu.
 #include "../../include/eovae.h"
 #include "common.cuh"
+#include "bulk_ring.cuh"
 
 int g_gn_bwd_bulk = 1;                // eovae_set_tuning(EOVAE_TUNE_GN_BWD_BULK, 0/1): cp.async.bulk staged kernels
 long long g_bwd_block_elems = 0;      // eovae_set_tuning(EOVAE_TUNE_GN_BWD_BLOCK_ELEMS, n): pixels x channels per block, 0 = auto
@@ -421,80 +422,6 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int bl
 // 6.5 TB/s; the ring keeps 128-192 KB / SM outstanding).  A block owns the contiguous pixel range [p0, p1) of one image =
 // one contiguous byte range of each NHWC tensor, walked in stages of kThreads * VEC 16-byte vectors; thread t owns vectors
 // t, t + 256, ... of a stage, which all belong to the same 8 channels because (C / 8) divides 256.
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(s_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (++spins > (1u << 21)) __trap();  // a protocol bug traps instead of hanging the device
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
-               "l"(src), "r"(bytes), "r"(s_u32(bar))
-               : "memory");
-}
-
-// ring of STAGES slots, each NT tensors x (kThreads * VEC) uint4
-template <int NT, int VEC, int STAGES>
-struct BulkRing {
-  static constexpr int kSlotVecs = kThreads * VEC;
-  static constexpr uint32_t kSlotBytes = kSlotVecs * 16;
-  static constexpr size_t kSmemBytes = static_cast<size_t>(STAGES) * NT * kSlotBytes + 128;
-  uint4* slots;
-  uint64_t* full;
-  const char* src[NT];
-  long long total_bytes;  // of this block's range, per tensor
-  int nchunks;
-  __device__ __forceinline__ void init(unsigned char* smem, long long total) {
-    slots = reinterpret_cast<uint4*>(smem);
-    full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(STAGES) * NT * kSlotBytes);
-    total_bytes = total;
-    nchunks = static_cast<int>((total + kSlotBytes - 1) / kSlotBytes);
-    if (threadIdx.x == 0) {
-      for (int i = 0; i < STAGES; ++i) bar_init(&full[i], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-      for (int i = 0; i < STAGES && i < nchunks; ++i) issue(i);
-  }
-  __device__ __forceinline__ void issue(int chunk) {  // one thread
-    const int s = chunk % STAGES;
-    const long long off = static_cast<long long>(chunk) * kSlotBytes;
-    const long long left = total_bytes - off;
-    const uint32_t bytes = left < static_cast<long long>(kSlotBytes) ? static_cast<uint32_t>(left) : kSlotBytes;
-    bar_expect_tx(&full[s], bytes * NT);
-#pragma unroll
-    for (int t = 0; t < NT; ++t) bulk_g2s(slot(s, t), src[t] + off, bytes, &full[s]);
-  }
-  __device__ __forceinline__ uint4* slot(int s, int t) { return slots + (static_cast<size_t>(s) * NT + t) * kSlotVecs; }
-  __device__ __forceinline__ void wait(int chunk) { bar_wait(&full[chunk % STAGES], (chunk / STAGES) & 1); }
-  // every thread has copied its vectors of `chunk` to registers: hand the slot back to the copy engine
-  __device__ __forceinline__ void release(int chunk) {
-    __syncthreads();
-    if (threadIdx.x == 0 && chunk + STAGES < nchunks) issue(chunk + STAGES);
-  }
-  // vectors of the chunk that hold data (the last chunk of a block may be short)
-  __device__ __forceinline__ int valid_vecs(int chunk) const {
-    const long long left = total_bytes - static_cast<long long>(chunk) * kSlotBytes;
-    return left >= static_cast<long long>(kSlotBytes) ? kSlotVecs : static_cast<int>(left >> 4);
-  }
-};
-
 template <typename T, typename TG, bool SILU, int VEC, int STAGES>
 __global__ void __launch_bounds__(kThreads, 2) gn_bwd_reduce_bulk_kernel(const T* __restrict__ x, const TG* __restrict__ g,
                                                                          const float* __restrict__ stats,
@@ -503,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_reduce_bulk_kernel(const T
                                                                          int groups, float* __restrict__ partial,
                                                                          int pix_per_block) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  using Ring = BulkRing<2, VEC, STAGES>;
+  using Ring = eovae::BulkRing<2, VEC, STAGES>;
   Ring ring;
   const int vpp = c >> 3;
   const int rows = kThreads / vpp;
@@ -590,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_apply_bulk_kernel(const T*
                                                                         float* __restrict__ colpart) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NT = ADD ? 3 : 2;
-  using Ring = BulkRing<NT, VEC, STAGES>;
+  using Ring = eovae::BulkRing<NT, VEC, STAGES>;
   Ring ring;
   const int vpp = c >> 3;
   const int rows = kThreads / vpp;
@@ -886,18 +813,18 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
     KERNEL<<<grid, kThreads, BYTES, stream>>>(__VA_ARGS__);                                                           \
   } while (0)
 #define EOVAE_GNB_RB(T, TG, S)                                                                                        \
-  EOVAE_GNB_LAUNCH_BULK((gn_bwd_reduce_bulk_kernel<T, TG, S, 4, 3>), (BulkRing<2, 4, 3>::kSmemBytes),                  \
+  EOVAE_GNB_LAUNCH_BULK((gn_bwd_reduce_bulk_kernel<T, TG, S, 4, 3>), (eovae::BulkRing<2, 4, 3>::kSmemBytes),                  \
                         static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, hw, c, groups, \
                         partial, ppb)
 #define EOVAE_GNB_AB(T, TG, S)                                                                                        \
   do {                                                                                                                \
     if (grad_add != nullptr)                                                                                          \
-      EOVAE_GNB_LAUNCH_BULK((gn_bwd_apply_bulk_kernel<T, TG, S, true, 2, 4>), (BulkRing<3, 2, 4>::kSmemBytes),         \
+      EOVAE_GNB_LAUNCH_BULK((gn_bwd_apply_bulk_kernel<T, TG, S, true, 2, 4>), (eovae::BulkRing<3, 2, 4>::kSmemBytes),         \
                             static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, gsum,     \
                             static_cast<const TG*>(grad_add), static_cast<TG*>(grad_x), hw, c, groups, ppb,           \
                             grad_x_colsum ? partial : nullptr);                                                       \
     else                                                                                                              \
-      EOVAE_GNB_LAUNCH_BULK((gn_bwd_apply_bulk_kernel<T, TG, S, false, 4, 3>), (BulkRing<2, 4, 3>::kSmemBytes),        \
+      EOVAE_GNB_LAUNCH_BULK((gn_bwd_apply_bulk_kernel<T, TG, S, false, 4, 3>), (eovae::BulkRing<2, 4, 3>::kSmemBytes),        \
                             static_cast<const T*>(x), static_cast<const TG*>(grad_out), stats, gamma, beta, gsum,     \
                             static_cast<const TG*>(grad_add), static_cast<TG*>(grad_x), hw, c, groups, ppb,           \
                             grad_x_colsum ? partial : nullptr);                                                       \

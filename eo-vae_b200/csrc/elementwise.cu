@@ -3,6 +3,7 @@
 // NHWC channel axis; reductions use warp shuffles + a few fp64 atomics per block.
 #include "../../include/eovae.h"
 #include "common.cuh"
+#include "bulk_ring.cuh"
 #include "fp32_path.cuh"
 
 #include <type_traits>
@@ -164,6 +165,75 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const TI* __restri
 
 // co-resident launch shape: the same body at 128 threads x 8 loads, registers capped so that one CTA fits in the ~11.7 K
 // registers a resident implicit-GEMM CTA leaves free on the SM
+// Bulk-ring variant (dense input): x streams through a cp.async.bulk shared-memory ring (bulk_ring.cuh: the bytes in flight
+// per SM are set by the ring - 3 blocks x 3 outstanding 16 KB slots - not by the loads a thread can keep in registers),
+// results leave as coalesced 16-byte stores (y may be a channel slice of a wider tensor).  Measured on B200 (batch 64,
+// tools/gn_apply_shapes.py): 6.66 vs 5.65 TB/s on the level-0 tensor, 18-22 % less time on every encoder shape.
+// grid (blocks_per_image, n), 256 threads.
+template <typename TI, typename TO, bool SILU, int VEC, int STAGES>
+__global__ void __launch_bounds__(eovae::kRingThreads, 3) gn_apply_bulk_kernel(const TI* __restrict__ x,
+                                                                               const float* __restrict__ stats,
+                                                                               const float* __restrict__ gamma,
+                                                                               const float* __restrict__ beta,
+                                                                               TO* __restrict__ y, long long y_pix_stride,
+                                                                               long long hw, int c, int groups,
+                                                                               int pix_per_block) {
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  using Ring = eovae::BulkRing<1, VEC, STAGES>;
+  Ring ring;
+  const int vpp = c >> 3;
+  const int rows = eovae::kRingThreads / vpp;
+  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
+  const int n = blockIdx.y;
+  const int cpg = c / groups;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > hw) p1 = hw;
+  ring.src[0] = reinterpret_cast<const char*>(x + (static_cast<long long>(n) * hw + p0) * c);
+  ring.init(ring_smem, (p1 - p0) * c * 2);
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = v * 8 + j;
+    const int g = ch / cpg;
+    const float mean = stats[(n * groups + g) * 2], rstd = stats[(n * groups + g) * 2 + 1];
+    const float ga = gamma[ch] * rstd;
+    a[j] = ga;
+    b[j] = beta[ch] - mean * ga;
+  }
+  // vector t + k * 256 of a slot = pixel r + k * rows of the slot, channels [8 v, 8 v + 8)
+  TO* yb = y + (static_cast<long long>(n) * hw + p0 + r) * y_pix_stride + v * 8;
+  const long long slot_pix = Ring::kSlotVecs / vpp;
+  for (int i = 0; i < ring.nchunks; ++i) {
+    ring.wait(i);
+    uint4 u[VEC];
+    const uint4* sx = ring.slot(i % STAGES, 0);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) u[k] = sx[threadIdx.x + k * eovae::kRingThreads];
+    const int valid = ring.valid_vecs(i);
+    ring.release(i);
+    TO* o = yb + i * slot_pix * y_pix_stride;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      if (static_cast<int>(threadIdx.x) + k * eovae::kRingThreads >= valid) break;
+      const uint32_t w4[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      uint32_t q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = T16<TI>::to_f2(w4[j]);
+        float h0 = fmaf(f.x, a[2 * j], b[2 * j]);
+        float h1 = fmaf(f.y, a[2 * j + 1], b[2 * j + 1]);
+        if (SILU) {
+          h0 = silu_f(h0);
+          h1 = silu_f(h1);
+        }
+        q[j] = T16<TO>::from_f2(h0, h1);
+      }
+      *reinterpret_cast<uint4*>(o + static_cast<long long>(k) * rows * y_pix_stride) = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+  }
+}
+
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(128, 6) gn_apply_co_kernel(const T* __restrict__ x, long long x_pix_stride,
                                                                            const float* __restrict__ stats,
@@ -174,7 +244,8 @@ __global__ void __launch_bounds__(128, 6) gn_apply_co_kernel(const T* __restrict
   gn_apply_body<T, T, SILU, 8>(x, x_pix_stride, stats, gamma, beta, y, y_pix_stride, hw, c, groups, pix_per_block);
 }
 
-int g_gn_apply_coresident = 0;  // eovae_set_tuning(EOVAE_TUNE_GN_APPLY_CORESIDENT, 1)
+int g_gn_apply_coresident = 0;  // eovae_set_tuning(EOVAE_TUNE_GN_APPLY_CORESIDENT, mode): see include/eovae.h
+long long g_gn_apply_block_elems = 0;  // eovae_set_tuning(EOVAE_TUNE_GN_APPLY_BLOCK_ELEMS, n): bulk-ring kernel, 0 = auto
 
 int gn_block_threads(int c) {
   const int vpp = c / 8;
@@ -628,6 +699,7 @@ int eovae_gn_stats(const void* x, int x_dtype, int n, long long hw, int c, long 
 
 void eovae_set_tuning(int key, int value) {
   if (key == EOVAE_TUNE_GN_APPLY_CORESIDENT) g_gn_apply_coresident = value;
+  if (key == EOVAE_TUNE_GN_APPLY_BLOCK_ELEMS && (value == 0 || value >= 2048)) g_gn_apply_block_elems = value;
   if (key == EOVAE_TUNE_GN_BWD_BLOCK_ELEMS && (value == 0 || value >= 4096)) g_bwd_block_elems = value;
   if (key == EOVAE_TUNE_GN_BWD_BULK) g_gn_bwd_bulk = value;
 }
@@ -654,7 +726,48 @@ int eovae_gn_apply(const void* x, int x_dtype, long long x_pix_stride, const flo
   // 128 threads x 8 loads in flight measures 5.66 vs 5.28 TB/s on the large tensors (tools/gn_apply_shapes.py) and loses on
   // the small ones: taken from 32 M elements up, or always when the co-resident shape is requested
   const bool big = static_cast<long long>(n) * hw * c >= (32LL << 20);
-  if ((g_gn_apply_coresident || big) && x_dtype == y_dtype && c <= 1024) {
+  // default: bulk-ring kernel wherever the input is dense and its 16-byte vectors per pixel divide the block
+  if ((g_gn_apply_coresident == 0 || g_gn_apply_coresident == 3) && x_pix_stride == c &&
+      eovae::kRingThreads % (c / 8) == 0) {
+    const long long total = static_cast<long long>(n) * hw * c;
+    long long elems = g_gn_apply_block_elems;
+    if (elems <= 0) {  // ~8 slots per block on the large tensors, at least ~256 blocks on the small ones
+      elems = 8192;
+      while (elems < 65536 && elems * 2 * 256 <= total) elems *= 2;
+    }
+    long long per = elems / c;
+    if (per < 1) per = 1;
+    if (per > hw) per = hw;
+    dim3 g3(static_cast<unsigned>((hw + per - 1) / per), n);
+    using Ring = eovae::BulkRing<1, 4, 4>;
+#define EOVAE_GN_APPLY_BULK(TI, TO, S)                                                                                 \
+  do {                                                                                                                 \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      EOVAE_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<TI, TO, S, 4, 4>,                                           \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Ring::kSmemBytes))); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    gn_apply_bulk_kernel<TI, TO, S, 4, 4><<<g3, eovae::kRingThreads, Ring::kSmemBytes, stream>>>(                      \
+        static_cast<const TI*>(x), stats, gamma, beta, static_cast<TO*>(y), y_pix_stride, hw, c, groups,               \
+        static_cast<int>(per));                                                                                        \
+  } while (0)
+    const int bkey = (x_dtype << 2) | (y_dtype << 1) | (apply_silu ? 1 : 0);
+    switch (bkey) {
+      case 0: EOVAE_GN_APPLY_BULK(__nv_bfloat16, __nv_bfloat16, false); break;
+      case 1: EOVAE_GN_APPLY_BULK(__nv_bfloat16, __nv_bfloat16, true); break;
+      case 2: EOVAE_GN_APPLY_BULK(__nv_bfloat16, __half, false); break;
+      case 3: EOVAE_GN_APPLY_BULK(__nv_bfloat16, __half, true); break;
+      case 4: EOVAE_GN_APPLY_BULK(__half, __nv_bfloat16, false); break;
+      case 5: EOVAE_GN_APPLY_BULK(__half, __nv_bfloat16, true); break;
+      case 6: EOVAE_GN_APPLY_BULK(__half, __half, false); break;
+      default: EOVAE_GN_APPLY_BULK(__half, __half, true); break;
+    }
+#undef EOVAE_GN_APPLY_BULK
+    EOVAE_LAUNCH_CHECK();
+    return 0;
+  }
+  if ((g_gn_apply_coresident == 1 || g_gn_apply_coresident == 2 || big) && x_dtype == y_dtype && c <= 1024) {
     // co-resident launch shape (see the kernel comment): 128 threads, 8 loads in flight, capped registers
     const int vpp = c / 8;
     const int thr = (128 / vpp) * vpp;

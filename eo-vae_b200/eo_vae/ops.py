@@ -39,6 +39,7 @@ def set_tuning(key: int, value: int) -> None:
 TUNE_GN_APPLY_CORESIDENT = 1
 TUNE_GN_BWD_BLOCK_ELEMS = 3
 TUNE_GN_BWD_BULK = 4
+TUNE_GN_APPLY_BLOCK_ELEMS = 5
 
 
 def launch_count() -> int:

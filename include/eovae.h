@@ -44,18 +44,25 @@ int eovae_num_sms(void);
 unsigned long long eovae_launch_count(void);
 /* test / profiling aid: low byte = bit mask 1 skip epilogue work | 2 skip MMA issue | 4 skip TMA loads (these produce
  * garbage by design, tools/igemm_bench.py only); bits 8-9: 0 automatic | 1 force single-CTA | 2 force CTA-pair
- * (cta_group::2) implicit GEMM; bit 10: force one K-chunk per stage; bit 11: per-thread stores instead of the TMA-store epilogue (tests run all).
+ * (cta_group::2) implicit GEMM; bit 10: force one K-chunk per stage; bit 11: per-thread stores instead of the TMA-store epilogue (tests run all);
+ * bit 12: no halo mainloop; bit 13: three taps per stage in the 16-channel conv; bit 14: 64-byte store rows everywhere;
+ * bit 15: residual through registers; low byte also 32 = no bulk store issue, 64 = no tcgen05.ld (tools/epilogue_probe.py).
  * The product path never sets it.                         */
 void eovae_set_debug_mode(int mode);
-/* launch-shape knobs (process-wide; results never depend on them).  EOVAE_TUNE_GN_APPLY_CORESIDENT = 1: eovae_gn_apply
- * launches 128-thread CTAs with 8 loads in flight and <= 80 registers, a shape that fits on an SM beside a resident
- * implicit-GEMM CTA, so that the pass overlaps a convolution running on another stream (the dual-stream encode). */
+/* launch-shape knobs (process-wide; results never depend on them).
+ * EOVAE_TUNE_GN_APPLY_CORESIDENT selects the kernel of eovae_gn_apply: 0 (default) = cp.async.bulk shared-memory ring
+ * wherever the input is dense (else the register-load kernels); 1 = 128-thread CTAs with 8 loads in flight, <= 80 registers
+ * and the maximum shared-memory carve-out, a shape that fits on an SM beside a resident implicit-GEMM CTA, so that the pass
+ * overlaps a convolution running on another stream (the dual-stream encode); 2 = that launch shape, default carve-out;
+ * 4 = register-load kernels with the size heuristic of round 1 (128 x 8 from 32 Mi elements up, else 256 x 4). */
 #define EOVAE_TUNE_GN_APPLY_CORESIDENT 1
 /* EOVAE_TUNE_GN_BWD_BLOCK_ELEMS: elements (pixels x channels) handled by one block of the GroupNorm backward kernels;
    0 (default) = chosen from the tensor size */
 #define EOVAE_TUNE_GN_BWD_BLOCK_ELEMS 3
 /* EOVAE_TUNE_GN_BWD_BULK: 1 (default) = cp.async.bulk shared-memory ring in the GroupNorm backward kernels, 0 = register loads */
 #define EOVAE_TUNE_GN_BWD_BULK 4
+/* EOVAE_TUNE_GN_APPLY_BLOCK_ELEMS: elements per block of the bulk-ring eovae_gn_apply kernel; 0 (default) = from the size */
+#define EOVAE_TUNE_GN_APPLY_BLOCK_ELEMS 5
 void eovae_set_tuning(int key, int value);
 
 /* ---- weight packing (derived, non-persistent caches of the OIHW fp32 master parameters) -------------------- */

@@ -213,6 +213,41 @@ def test_group_norm(cuda, n, c, h, w):
         assert _rel(y, ref) < 4e-3
 
 
+@pytest.mark.parametrize("n,c,h,w", [(2, 128, 64, 64), (1, 64, 37, 29), (3, 512, 24, 24), (1, 8, 5, 7), (2, 256, 16, 16)])
+@pytest.mark.parametrize("dt_in,dt_out", [(torch.bfloat16, torch.bfloat16), (torch.float16, torch.float16),
+                                          (torch.float16, torch.bfloat16)])
+def test_gn_apply_ring_equals_register_path(cuda, n, c, h, w, dt_in, dt_out):
+    """The cp.async.bulk ring kernel (default) and the register-load kernels compute every element with the same
+    instructions: identical bits, over block sizes that give one-slot blocks, short last slots and ragged last blocks; also
+    with the output written as a channel slice of a wider tensor (through the C ABI)."""
+    from eo_vae import _C, ops
+    from eo_vae.ops import DT, _ptr, _stream
+    groups = 32 if c >= 32 else c // 8
+    x = (_act(n, c, h, w, cuda, seed=21).float() * 2 + 0.5).to(dt_in).contiguous(memory_format=torch.channels_last)
+    gamma, beta = (1 + 0.1 * torch.randn(c)).to(cuda), (0.1 * torch.randn(c)).to(cuda)
+    stats = ops.gn_stats(x, groups)
+    try:
+        ops.set_tuning(ops.TUNE_GN_APPLY_CORESIDENT, 4)
+        ref = {silu: ops.gn_apply(x, stats, gamma, beta, silu, groups, out_dtype=dt_out) for silu in (False, True)}
+        ops.set_tuning(ops.TUNE_GN_APPLY_CORESIDENT, 0)
+        for elems in (0, 2048, 40960):
+            ops.set_tuning(ops.TUNE_GN_APPLY_BLOCK_ELEMS, elems)
+            for silu in (False, True):
+                y = ops.gn_apply(x, stats, gamma, beta, silu, groups, out_dtype=dt_out)
+                assert torch.isfinite(y.float()).all() and torch.equal(y, ref[silu])
+        # output = channels [c, 2c) of a (n, h, w, 3c) tensor
+        wide = torch.zeros((n, h, w, 3 * c), dtype=dt_out, device=cuda)
+        ysl = wide[..., c:2 * c]
+        rc = _C.lib().eovae_gn_apply(_ptr(x), DT[x.dtype], c, _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(ysl), DT[dt_out], 3 * c,
+                                    n, h * w, c, groups, 1, _stream())
+        _C.check(rc, "eovae_gn_apply")
+        assert torch.equal(ysl.permute(0, 3, 1, 2), ref[True])
+        assert float(wide[..., :c].abs().max()) == 0.0 and float(wide[..., 2 * c:].abs().max()) == 0.0
+    finally:
+        ops.set_tuning(ops.TUNE_GN_APPLY_CORESIDENT, 0)
+        ops.set_tuning(ops.TUNE_GN_APPLY_BLOCK_ELEMS, 0)
+
+
 def test_softmax_transpose_upsample(cuda):
     from eo_vae import ops
     s = torch.randn(3, 200, 1024, device=cuda) * 4

@@ -1,5 +1,5 @@
-"""GroupNorm-apply launch shapes on the encoder's tensors (batch 64, fp16): default 256 threads x 4 loads vs 128 threads x 8
-loads (with / without the max-shared carve-out)."""
+"""GroupNorm-apply launch shapes on the encoder's tensors (batch 64, fp16): mode 0 = cp.async.bulk ring (default), 4 = the register-load kernels
+(128 threads x 8 loads from 32 Mi elements up, else 256 x 4), 2 = 128 x 8 always."""
 import os
 import sys
 
@@ -33,8 +33,24 @@ for name, n, c, h, w in (("L0 128ch@256", 64, 128, 256, 256), ("L1 256ch@128", 6
     gamma, beta = torch.ones(c, device=dev), torch.zeros(c, device=dev)
     stats = ops.gn_stats(x)
     out = []
-    for mode in (0, 2, 1, 0, 2):
+    for mode in (0, 4, 2, 0, 4):
         ops.set_tuning(ops.TUNE_GN_APPLY_CORESIDENT, mode)
         ms = timeit(lambda: ops.gn_apply(x, stats, gamma, beta, True))
         out.append(f"mode {mode}: {ms:.3f} ms {2 * x.numel() * 2 / ms / 1e6:6.0f} GB/s")
     print(f"{name:26s} " + " | ".join(out), flush=True)
+
+# block size of the ring kernel
+x = torch.randn((64, 256, 256, 128), device=dev).half().permute(0, 3, 1, 2)
+x2 = torch.randn((64, 32, 32, 512), device=dev).half().permute(0, 3, 1, 2)
+ops.set_tuning(ops.TUNE_GN_APPLY_CORESIDENT, 0)
+for xx, name in ((x, "L0 128ch@256"), (x2, "L3 512ch@32")):
+    c = xx.shape[1]
+    gamma, beta = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    stats = ops.gn_stats(xx)
+    out = []
+    for elems in (0, 8192, 16384, 32768, 65536, 131072, 262144):
+        ops.set_tuning(ops.TUNE_GN_APPLY_BLOCK_ELEMS, elems)
+        ms = timeit(lambda: ops.gn_apply(xx, stats, gamma, beta, True))
+        out.append(f"{elems}: {ms:.3f} ms")
+    print(f"{name:26s} block elems " + " | ".join(out), flush=True)
+ops.set_tuning(ops.TUNE_GN_APPLY_BLOCK_ELEMS, 0)

@@ -135,51 +135,54 @@ __global__ void __launch_bounds__(kThreads, 3) gn_bwd_reduce_kernel(const T* __r
 // Pass 2 (tiny): per (image, channel) totals -> per-(image, group) s1 = sum dz*gamma, s2 = sum dz*gamma*xhat and the
 // parameter gradients dgamma[c] += sum_n B, dbeta[c] += sum_n A.   One block per image for the group sums.
 __global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma, int n_img, int bpi,
-                                       int c, int groups, float* __restrict__ gsum /*[n][groups][2]*/,
+                                       int c, int groups, int cw, float* __restrict__ gsum /*[n][groups][2]*/,
                                        float* __restrict__ chsum /*[n][c][2]*/) {
-  const int n = blockIdx.x;
-  extern __shared__ float tot[];  // [c][2] totals, then [slices][c][2] slice sums
+  // grid (c / cw, images): a block owns the channel window [c0, c0 + cw) of one image - whole groups (the host picks cw = 32
+  // channels when the groups tile it, else cw = c) - so that a batch-16 step launches 64-256 blocks instead of 16
+  const int n = blockIdx.y;
+  const int c0 = blockIdx.x * cw;
+  extern __shared__ float tot[];  // [cw][2] totals, then [slices][cw][2] slice sums
   // the bpi partial rows of a channel are split over `slices` threads (fixed assignment), combined in slice order
-  const int slices = c <= static_cast<int>(blockDim.x) ? static_cast<int>(blockDim.x) / c : 1;
-  float* slice_sum = tot + 2 * c;
-  for (int t = threadIdx.x; t < c * slices; t += blockDim.x) {
-    const int ch = t % c, sl = t / c;
+  const int slices = cw <= static_cast<int>(blockDim.x) ? static_cast<int>(blockDim.x) / cw : 1;
+  float* slice_sum = tot + 2 * cw;
+  for (int t = threadIdx.x; t < cw * slices; t += blockDim.x) {
+    const int chl = t % cw, sl = t / cw;
     double a = 0.0, b = 0.0;
 #pragma unroll 8
     for (int k = sl; k < bpi; k += slices) {  // unrolled: the loads of a batch of rows are issued together
-      const float2 o = *reinterpret_cast<const float2*>(partial + ((static_cast<long long>(n) * bpi + k) * c + ch) * 2);
+      const float2 o = *reinterpret_cast<const float2*>(partial + ((static_cast<long long>(n) * bpi + k) * c + c0 + chl) * 2);
       a += o.x;
       b += o.y;
     }
-    slice_sum[(sl * c + ch) * 2] = static_cast<float>(a);
-    slice_sum[(sl * c + ch) * 2 + 1] = static_cast<float>(b);
+    slice_sum[(sl * cw + chl) * 2] = static_cast<float>(a);
+    slice_sum[(sl * cw + chl) * 2 + 1] = static_cast<float>(b);
   }
   __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+  for (int chl = threadIdx.x; chl < cw; chl += blockDim.x) {
     double a = 0.0, b = 0.0;
     for (int sl = 0; sl < slices; ++sl) {
-      a += slice_sum[(sl * c + ch) * 2];
-      b += slice_sum[(sl * c + ch) * 2 + 1];
+      a += slice_sum[(sl * cw + chl) * 2];
+      b += slice_sum[(sl * cw + chl) * 2 + 1];
     }
-    tot[2 * ch] = static_cast<float>(a);
-    tot[2 * ch + 1] = static_cast<float>(b);
-    chsum[(static_cast<long long>(n) * c + ch) * 2] = static_cast<float>(a);
-    chsum[(static_cast<long long>(n) * c + ch) * 2 + 1] = static_cast<float>(b);
+    tot[2 * chl] = static_cast<float>(a);
+    tot[2 * chl + 1] = static_cast<float>(b);
+    chsum[(static_cast<long long>(n) * c + c0 + chl) * 2] = static_cast<float>(a);
+    chsum[(static_cast<long long>(n) * c + c0 + chl) * 2 + 1] = static_cast<float>(b);
   }
   __syncthreads();
   const int cpg = c / groups;
-  for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+  for (int gl = threadIdx.x; gl < cw / cpg; gl += blockDim.x) {
     double s1 = 0.0, s2 = 0.0;
     for (int j = 0; j < cpg; ++j) {
-      const int ch = gi * cpg + j;
-      s1 += static_cast<double>(tot[2 * ch]) * gamma[ch];
-      s2 += static_cast<double>(tot[2 * ch + 1]) * gamma[ch];
+      const int chl = gl * cpg + j;
+      s1 += static_cast<double>(tot[2 * chl]) * gamma[c0 + chl];
+      s2 += static_cast<double>(tot[2 * chl + 1]) * gamma[c0 + chl];
     }
+    const int gi = c0 / cpg + gl;
     gsum[(n * groups + gi) * 2] = static_cast<float>(s1);
     gsum[(n * groups + gi) * 2 + 1] = static_cast<float>(s2);
   }
 }
-
 __global__ void gn_bwd_param_kernel(const float* __restrict__ chsum, int n_img, int c, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, int accumulate) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
@@ -845,9 +848,13 @@ int eovae_gn_backward(const void* x, const void* grad_out, int dtype, int grad_d
   if (bulk) EOVAE_GNB_DISPATCH(EOVAE_GNB_RB); else EOVAE_GNB_DISPATCH(EOVAE_GNB_R);
   EOVAE_LAUNCH_CHECK();
   {
-    const int fthreads = 1024;
-    const int slices = c <= fthreads ? fthreads / c : 1;
-    gn_bwd_finalize_kernel<<<n, fthreads, sizeof(float) * 2 * c * (1 + slices), stream>>>(partial, gamma, n, bpi, c, groups, gsum, chsum);
+    const int cpg = c / groups;
+    const bool window = c % 32 == 0 && cpg <= 32 && 32 % cpg == 0;  // 32-channel windows hold whole groups
+    const int cw = window ? 32 : c;
+    const int fthreads = window ? 256 : 1024;
+    const int slices = cw <= fthreads ? fthreads / cw : 1;
+    gn_bwd_finalize_kernel<<<dim3(c / cw, n), fthreads, sizeof(float) * 2 * cw * (1 + slices), stream>>>(partial, gamma, n, bpi, c, groups, cw,
+                                                                                                       gsum, chsum);
   }
   EOVAE_LAUNCH_CHECK();
   if (dgamma != nullptr && dbeta != nullptr) {

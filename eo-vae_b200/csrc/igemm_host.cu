@@ -123,18 +123,20 @@ int pick_block_n(int cout_pad) {
 }
 
 // stats[n][g] = (mean, rstd) from the per-tile partial sums written by the igemm epilogue ([image][slot][group][2] floats).
-// One block per image; thread (slot lane, group) walks the slots with a stride of `lanes`, so a warp reads 256 contiguous
-// bytes per slot (the one-warp-per-(n, g) version read one 8-byte pair per 32-byte sector and took 10 us on the 2048-slot
-// level-0 tensors).  Fixed summation order (deterministic), double accumulation.
-__global__ void __launch_bounds__(1024) gn_tiles_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats,
-                                                                 int groups, int slots_per_img, double count, float eps,
-                                                                 int regions, long long region_stride) {
-  extern __shared__ double fin_sm[];  // [2][lanes][groups]
-  const int n = blockIdx.x;
-  const int lanes = blockDim.x / groups;
-  const int g = threadIdx.x % groups, sl = threadIdx.x / groups;
+// grid (groups / gsub, images): a block owns `gsub` (<= 4) adjacent groups of one image = one 32-byte sector per slot;
+// thread (slot lane, group) walks the slots with a stride of `lanes`.  (One warp per (n, g) read one 8-byte pair per sector
+// and took 10 us on the 2048-slot level-0 tensors; one block per image left a batch-16 training step with 16 blocks.)
+// Fixed summation order (deterministic), double accumulation.
+__global__ void __launch_bounds__(256) gn_tiles_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats,
+                                                                int groups, int gsub, int slots_per_img, double count,
+                                                                float eps, int regions, long long region_stride) {
+  __shared__ double fin_s[256], fin_q[256];
+  const int n = blockIdx.y;
+  const int lanes = blockDim.x / gsub;
+  const int gl = threadIdx.x % gsub, sl = threadIdx.x / gsub;
+  const int g = blockIdx.x * gsub + gl;
+  double s = 0.0, q = 0.0;
   if (sl < lanes) {
-    double s = 0.0, q = 0.0;
     for (int r = 0; r < regions; ++r) {  // one region per sub-pixel phase (1 for an ordinary convolution)
       const float2* base = reinterpret_cast<const float2*>(partial + r * region_stride) +
                            static_cast<long long>(n) * slots_per_img * groups + g;
@@ -145,15 +147,16 @@ __global__ void __launch_bounds__(1024) gn_tiles_finalize_kernel(const float* __
         q += v.y;
       }
     }
-    fin_sm[sl * groups + g] = s;
-    fin_sm[(lanes + sl) * groups + g] = q;
   }
+  fin_s[threadIdx.x] = s;
+  fin_q[threadIdx.x] = q;
   __syncthreads();
-  if (threadIdx.x < groups) {
-    double s = 0.0, q = 0.0;
+  if (threadIdx.x < gsub) {
+    s = 0.0;
+    q = 0.0;
     for (int l = 0; l < lanes; ++l) {
-      s += fin_sm[l * groups + g];
-      q += fin_sm[(lanes + l) * groups + g];
+      s += fin_s[l * gsub + gl];
+      q += fin_q[l * gsub + gl];
     }
     const double mean = s / count;
     double var = q / count - mean * mean;
@@ -505,12 +508,11 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
   if (rc != 0 || gn_stats == nullptr) return rc;
   {
     const int slots = p.tiles_w * p.tiles_h * 4;
-    int lanes = slots < 32 ? slots : 32;
-    while (lanes > 1 && lanes * gn_groups > 1024) lanes >>= 1;
-    const int threads = round_up(lanes * gn_groups, 32);
-    EOVAE_CHECK(threads <= 1024, "igemm: too many GroupNorm groups (%d)", gn_groups);
-    gn_tiles_finalize_kernel<<<p.Nimg, threads, sizeof(double) * 2 * lanes * gn_groups, stream>>>(
-        p.gn_partial, gn_stats, gn_groups, slots, static_cast<double>(Ho) * Wo * p.gn_cpg * p.phases, gn_eps, p.phases,
+    const int gsub = gn_groups % 4 == 0 ? 4 : (gn_groups % 2 == 0 ? 2 : 1);
+    int threads = 256;
+    while (threads > 32 && threads / gsub >= 2 * slots) threads >>= 1;  // few slots: fewer idle lanes
+    gn_tiles_finalize_kernel<<<dim3(gn_groups / gsub, p.Nimg), threads, 0, stream>>>(
+        p.gn_partial, gn_stats, gn_groups, gsub, slots, static_cast<double>(Ho) * Wo * p.gn_cpg * p.phases, gn_eps, p.phases,
         p.gn_phase_stride);
   }
   EOVAE_LAUNCH_CHECK();

@@ -77,36 +77,40 @@ __global__ void __launch_bounds__(256) pack_conv_weight_tiled_kernel(const float
   __syncthreads();
   const int half = kpt >> 1;
   uint32_t* orow = reinterpret_cast<uint32_t*>(out + static_cast<long long>(o) * taps * kpt);
-  for (int i = threadIdx.x; i < taps * half; i += 256) {
-    const int tap = i / half, c = 2 * (i % half);
-    const float v0 = (o < cout && c < cin) ? sm[c * taps + tap] : 0.f;
-    const float v1 = (o < cout && c + 1 < cin) ? sm[(c + 1) * taps + tap] : 0.f;
-    orow[i] = T16<T>::from_f2(v0, v1);
+  for (int tap = 0; tap < taps; ++tap) {  // nested loops: no per-element division by the runtime extents
+    for (int h = threadIdx.x; h < half; h += 256) {
+      const int c = 2 * h;
+      const float v0 = (o < cout && c < cin) ? sm[c * taps + tap] : 0.f;
+      const float v1 = (o < cout && c + 1 < cin) ? sm[(c + 1) * taps + tap] : 0.f;
+      orow[tap * half + h] = T16<T>::from_f2(v0, v1);
+    }
   }
 }
 
 // Data-gradient operand out[ci][tap][co] = w[co][ci][taps-1-tap]: a (64 co) x (16 ci) tile goes through shared memory so that
 // both the fp32 reads (16 * taps contiguous floats per co) and the 16-bit writes (64 contiguous co per (ci, tap)) coalesce.
 constexpr int PD_CO = 64, PD_CI = 16;
-template <typename T>
+template <typename T, int TAPS>
 __global__ void __launch_bounds__(256) pack_conv_weight_dgrad_tiled_kernel(const float* __restrict__ w, T* __restrict__ out,
-                                                                           int cout, int cin, int cin_pad, int taps, int kpt) {
-  __shared__ float sm[PD_CO][PD_CI * 9 + 1];
+                                                                           int cout, int cin, int cin_pad, int kpt) {
+  // TAPS is a template parameter: the index arithmetic below divides by it per element (runtime divisions made this
+  // kernel 5x slower than its 14 MB of traffic)
+  __shared__ float sm[PD_CO][PD_CI * TAPS + 1];
   const int ci0 = blockIdx.x * PD_CI, co0 = blockIdx.y * PD_CO;
-  const int seg = PD_CI * taps;
+  constexpr int seg = PD_CI * TAPS;
   for (int i = threadIdx.x; i < PD_CO * seg; i += 256) {
     const int r = i / seg, j = i % seg;
-    const int co = co0 + r, ci = ci0 + j / taps;
-    sm[r][j] = (co < cout && ci < cin) ? w[(static_cast<long long>(co) * cin + ci0) * taps + j] : 0.f;
+    const int co = co0 + r, ci = ci0 + j / TAPS;
+    sm[r][j] = (co < cout && ci < cin) ? w[(static_cast<long long>(co) * cin + ci0) * TAPS + j] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < seg * (PD_CO / 2); i += 256) {
     const int pair = i % (PD_CO / 2), t = i / (PD_CO / 2);
-    const int tap = t % taps, cil = t / taps;
+    const int tap = t % TAPS, cil = t / TAPS;
     const int ci = ci0 + cil, co = co0 + 2 * pair;
     if (ci < cin_pad && co < kpt) {
-      const int src = cil * taps + (taps - 1 - tap);
-      *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(ci) * taps + tap) * kpt + co) =
+      const int src = cil * TAPS + (TAPS - 1 - tap);
+      *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(ci) * TAPS + tap) * kpt + co) =
           T16<T>::from_f2(sm[2 * pair][src], sm[2 * pair + 1][src]);
     }
   }
@@ -188,10 +192,13 @@ int eovae_pack_conv_weight_dgrad(const float* w_oihw, void* out, int cout, int c
   if (dtype == EOVAE_BF16 || dtype == EOVAE_F16) {  // coalesced path: (64 co) x (16 ci) tiles through shared memory
     const int cin_pad = round_up(cin, 16);
     dim3 tg(cin_pad / PD_CI, ceil_div(kpt, PD_CO));
-    if (dtype == EOVAE_BF16)
-      pack_conv_weight_dgrad_tiled_kernel<__nv_bfloat16><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, cin_pad, taps, kpt);
-    else
-      pack_conv_weight_dgrad_tiled_kernel<__half><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, cin_pad, taps, kpt);
+    if (dtype == EOVAE_BF16) {
+      if (taps == 9) pack_conv_weight_dgrad_tiled_kernel<__nv_bfloat16, 9><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, cin_pad, kpt);
+      else pack_conv_weight_dgrad_tiled_kernel<__nv_bfloat16, 1><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, cin_pad, kpt);
+    } else {
+      if (taps == 9) pack_conv_weight_dgrad_tiled_kernel<__half, 9><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, cin_pad, kpt);
+      else pack_conv_weight_dgrad_tiled_kernel<__half, 1><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, cin_pad, kpt);
+    }
     EOVAE_LAUNCH_CHECK();
     return 0;
   }

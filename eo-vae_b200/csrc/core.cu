@@ -66,45 +66,74 @@ __global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, T* __
 // Coalesced versions of the two packs (every conv weight is re-packed twice per training step: forward operand and data-
 // gradient operand).  Forward: one block per output channel stages w[o] ([cin][taps] fp32, contiguous) in shared memory and
 // writes out[o][tap][0..kpt) as 32-bit pairs.
+constexpr int PF_THREADS = 512;
 template <typename T>
-__global__ void __launch_bounds__(256) pack_conv_weight_tiled_kernel(const float* __restrict__ w, T* __restrict__ out, int cout,
+__global__ void __launch_bounds__(PF_THREADS) pack_conv_weight_tiled_kernel(const float* __restrict__ w, T* __restrict__ out, int cout,
                                                                      int cin, int taps, int kpt) {
   extern __shared__ float sm[];
   const int o = blockIdx.x;
   const int n = cin * taps;
-  if (o < cout)
-    for (int i = threadIdx.x; i < n; i += 256) sm[i] = w[static_cast<long long>(o) * n + i];
+  if (o < cout) {
+    constexpr int LB = 9;  // loads in batches (see the data-gradient pack): 512 x 9 = one batch for a 512-channel 3x3 row
+    for (int i0 = threadIdx.x; i0 < n; i0 += PF_THREADS * LB) {
+      float v[LB];
+#pragma unroll
+      for (int u = 0; u < LB; ++u) v[u] = i0 + u * PF_THREADS < n ? __ldg(&w[static_cast<long long>(o) * n + i0 + u * PF_THREADS]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < LB; ++u)
+        if (i0 + u * PF_THREADS < n) sm[i0 + u * PF_THREADS] = v[u];
+    }
+  }
   __syncthreads();
   const int half = kpt >> 1;
   uint32_t* orow = reinterpret_cast<uint32_t*>(out + static_cast<long long>(o) * taps * kpt);
-  for (int tap = 0; tap < taps; ++tap) {  // nested loops: no per-element division by the runtime extents
-    for (int h = threadIdx.x; h < half; h += 256) {
-      const int c = 2 * h;
-      const float v0 = (o < cout && c < cin) ? sm[c * taps + tap] : 0.f;
-      const float v1 = (o < cout && c + 1 < cin) ? sm[(c + 1) * taps + tap] : 0.f;
-      orow[tap * half + h] = T16<T>::from_f2(v0, v1);
+  // thread -> (tap lane, channel pair) once, then strided loops: no per-element division by the runtime extents
+  const int hw_ = half < PF_THREADS ? half : PF_THREADS;  // channel pairs covered per pass
+  const int tstep = PF_THREADS / hw_;                     // taps covered per pass
+  const int h0 = threadIdx.x % hw_, t0 = threadIdx.x / hw_;
+  if (t0 < tstep) {
+    for (int tap = t0; tap < taps; tap += tstep) {
+      for (int h = h0; h < half; h += hw_) {
+        const int c = 2 * h;
+        const float v0 = (o < cout && c < cin) ? sm[c * taps + tap] : 0.f;
+        const float v1 = (o < cout && c + 1 < cin) ? sm[(c + 1) * taps + tap] : 0.f;
+        orow[tap * half + h] = T16<T>::from_f2(v0, v1);
+      }
     }
   }
 }
 
 // Data-gradient operand out[ci][tap][co] = w[co][ci][taps-1-tap]: a (64 co) x (16 ci) tile goes through shared memory so that
 // both the fp32 reads (16 * taps contiguous floats per co) and the 16-bit writes (64 contiguous co per (ci, tap)) coalesce.
-constexpr int PD_CO = 64, PD_CI = 16;
+constexpr int PD_CO = 64, PD_CI = 16, PD_THREADS = 1024;
 template <typename T, int TAPS>
-__global__ void __launch_bounds__(256) pack_conv_weight_dgrad_tiled_kernel(const float* __restrict__ w, T* __restrict__ out,
+__global__ void __launch_bounds__(PD_THREADS) pack_conv_weight_dgrad_tiled_kernel(const float* __restrict__ w, T* __restrict__ out,
                                                                            int cout, int cin, int cin_pad, int kpt) {
   // TAPS is a template parameter: the index arithmetic below divides by it per element (runtime divisions made this
   // kernel 5x slower than its 14 MB of traffic)
   __shared__ float sm[PD_CO][PD_CI * TAPS + 1];
   const int ci0 = blockIdx.x * PD_CI, co0 = blockIdx.y * PD_CO;
   constexpr int seg = PD_CI * TAPS;
-  for (int i = threadIdx.x; i < PD_CO * seg; i += 256) {
-    const int r = i / seg, j = i % seg;
-    const int co = co0 + r, ci = ci0 + j / TAPS;
-    sm[r][j] = (co < cout && ci < cin) ? w[(static_cast<long long>(co) * cin + ci0) * TAPS + j] : 0.f;
+  // all loads of a thread in ONE batch (in-order issue: a load consumed by the next instruction serialises the loop at the
+  // memory latency - it was 36 round trips per block): 1024 threads x 9 elements cover the 64 x 144 tile
+  constexpr int LB = (PD_CO * seg + PD_THREADS - 1) / PD_THREADS;
+  for (int i0 = threadIdx.x; i0 < PD_CO * seg; i0 += PD_THREADS * LB) {
+    float v[LB];
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int i = i0 + u * PD_THREADS;
+      const int r = i / seg, j = i % seg;
+      const int co = co0 + r, ci = ci0 + j / TAPS;
+      v[u] = (i < PD_CO * seg && co < cout && ci < cin) ? __ldg(&w[(static_cast<long long>(co) * cin + ci0) * TAPS + j]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int i = i0 + u * PD_THREADS;
+      if (i < PD_CO * seg) sm[i / seg][i % seg] = v[u];
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < seg * (PD_CO / 2); i += 256) {
+  for (int i = threadIdx.x; i < seg * (PD_CO / 2); i += PD_THREADS) {
     const int pair = i % (PD_CO / 2), t = i / (PD_CO / 2);
     const int tap = t % TAPS, cil = t / TAPS;
     const int ci = ci0 + cil, co = co0 + 2 * pair;
@@ -163,9 +192,9 @@ int eovae_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, in
   if (stage <= 40 * 1024 && (dtype == EOVAE_BF16 || dtype == EOVAE_F16)) {  // coalesced path: one block per output channel
     const int rows = round_up(cout, 16);
     if (dtype == EOVAE_BF16)
-      pack_conv_weight_tiled_kernel<__nv_bfloat16><<<rows, 256, stage, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, taps, kpt);
+      pack_conv_weight_tiled_kernel<__nv_bfloat16><<<rows, PF_THREADS, stage, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, taps, kpt);
     else
-      pack_conv_weight_tiled_kernel<__half><<<rows, 256, stage, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, taps, kpt);
+      pack_conv_weight_tiled_kernel<__half><<<rows, PF_THREADS, stage, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, taps, kpt);
     EOVAE_LAUNCH_CHECK();
     return 0;
   }
@@ -193,11 +222,11 @@ int eovae_pack_conv_weight_dgrad(const float* w_oihw, void* out, int cout, int c
     const int cin_pad = round_up(cin, 16);
     dim3 tg(cin_pad / PD_CI, ceil_div(kpt, PD_CO));
     if (dtype == EOVAE_BF16) {
-      if (taps == 9) pack_conv_weight_dgrad_tiled_kernel<__nv_bfloat16, 9><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, cin_pad, kpt);
-      else pack_conv_weight_dgrad_tiled_kernel<__nv_bfloat16, 1><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, cin_pad, kpt);
+      if (taps == 9) pack_conv_weight_dgrad_tiled_kernel<__nv_bfloat16, 9><<<tg, PD_THREADS, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, cin_pad, kpt);
+      else pack_conv_weight_dgrad_tiled_kernel<__nv_bfloat16, 1><<<tg, PD_THREADS, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(out), cout, cin, cin_pad, kpt);
     } else {
-      if (taps == 9) pack_conv_weight_dgrad_tiled_kernel<__half, 9><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, cin_pad, kpt);
-      else pack_conv_weight_dgrad_tiled_kernel<__half, 1><<<tg, 256, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, cin_pad, kpt);
+      if (taps == 9) pack_conv_weight_dgrad_tiled_kernel<__half, 9><<<tg, PD_THREADS, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, cin_pad, kpt);
+      else pack_conv_weight_dgrad_tiled_kernel<__half, 1><<<tg, PD_THREADS, 0, stream>>>(w_oihw, static_cast<__half*>(out), cout, cin, cin_pad, kpt);
     }
     EOVAE_LAUNCH_CHECK();
     return 0;

@@ -432,6 +432,10 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
               "igemm: the sub-pixel upsample convolution needs the TMA-store epilogue (16-bit output, Cout >= 32, whole warps "
               "inside the pixel box), one image per tile and no residual");
   const int total_tiles = ceil_div(m_tiles_total, ctas) * p.n_tiles * p.phases;  // work items
+  p.fd_phases.set(p.phases);
+  p.fd_ntiles.set(p.n_tiles);
+  p.fd_tw.set(p.tiles_w);
+  p.fd_th.set(p.tiles_h);
   if (total_tiles == 0) return 0;
   if (gn_stats != nullptr) {
     EOVAE_CHECK(p.box_n == 1 && cout % 32 == 0 && gn_groups > 0 && cout % gn_groups == 0 && 32 % (cout / gn_groups) == 0 &&

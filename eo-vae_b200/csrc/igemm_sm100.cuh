@@ -34,6 +34,27 @@ constexpr int NUM_THREADS_GNP = 128 + 32 * NUM_EPI_WARPS + 32 * NUM_XF_WARPS;
 constexpr int GNP_COEF_BYTES = 4096;  // GroupNorm-prologue kernels: per-image coefficient table [Cin <= 512][8 bytes] in shared memory
 constexpr int MAX_TAPS = 16;  // 9 for a 3x3 kernel; 16 = 4 sub-pixel phases x 2x2 taps (data gradient of the upsample conv)
 
+// Division by a launch-time constant: q = umulhi(n, mul) >> (shift - 1), exact for 0 <= n < 2^31 with
+// shift = ceil(log2 d), mul = ceil(2^(31 + shift) / d) (mul == 0 encodes d == 1).  The persistent kernels decode a work
+// index with seven divisions per tile in every epilogue warp (~25 instructions each as runtime divisions).
+struct FastDiv {
+  uint32_t mul, shift, d;
+  __host__ void set(int div) {
+    d = static_cast<uint32_t>(div);
+    if (div <= 1) { mul = 0; shift = 0; return; }
+    shift = 0;
+    while ((1u << shift) < d) ++shift;
+    mul = static_cast<uint32_t>(((1ull << (31 + shift)) + d - 1) / d);
+  }
+  __device__ __forceinline__ int div(int n) const {
+    return mul == 0 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> (shift - 1));
+  }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+    q = div(n);
+    r = n - q * static_cast<int>(d);
+  }
+};
+
 struct Params {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
@@ -62,6 +83,7 @@ struct Params {
   float* gn_partial;
   int gn_cpg;                     // channels per group (1, 2, 4, 8, 16 or 32)
   int gn_groups;                  // Cout / gn_cpg
+  FastDiv fd_phases, fd_ntiles, fd_tw, fd_th;  // work index -> (phase, n-tile, tile x, tile y, tile image)
   int debug_mode;                 // bit mask: 1 no epilogue work | 2 no MMA issue | 4 no TMA loads | 32 no bulk store issue | 64 no tcgen05.ld (tools/igemm_bench.py, epilogue_probe.py)
   // fused GroupNorm + SiLU of the INPUT (GNP kernels): A operand = silu(x * a[n][c] + b[n][c]), zero outside the image
   const float2* gnp_ab;           // [Nimg][Cin] (gamma * rstd, beta - mean * gamma * rstd)
@@ -309,6 +331,20 @@ __device__ __forceinline__ void gn_chunk(const float (&v)[32], int lane, float* 
   }
 }
 
+// work index -> (phase, n-tile, m-tile of this CTA, tile x / y / image)
+struct WorkItem { int ph, nt, mt, tw, th, tn; };
+__device__ __forceinline__ WorkItem decode_work(const Params& p, int work, int ctas, int cta_rank) {
+  WorkItem w;
+  int wk, q;
+  p.fd_phases.divmod(work, wk, w.ph);
+  p.fd_ntiles.divmod(wk, q, w.nt);
+  w.mt = q * ctas + cta_rank;
+  int t;
+  p.fd_tw.divmod(w.mt, t, w.tw);
+  p.fd_th.divmod(t, w.tn, w.th);
+  return w;
+}
+
 template <int BLOCK_N, int CHUNK_BYTES, int CTAS, int KCH, bool HALO = false, bool GNP = false>
 __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_kernel(const __grid_constant__ Params p) {
   static_assert(!GNP || (HALO && CTAS == 2), "the GroupNorm prologue lives in the CTA-pair halo mainloop");
@@ -405,16 +441,13 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
       int stage = 0;
       uint32_t phase = 0;
       for (int work = group_id; work < total_work; work += num_groups) {
-        const int ph = work % p.phases;
-        const int wk = work / p.phases;
-        const int nt = wk % p.n_tiles;
-        const int mt = (wk / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tn = mt / (p.tiles_w * p.tiles_h);  // == tiles_n for the padding tile of an odd tail: fully OOB -> zeros
+        const WorkItem wi_ = decode_work(p, work, CTAS, static_cast<int>(cta_rank));
+        const int ph = wi_.ph, nt = wi_.nt, mt = wi_.mt, tw = wi_.tw, th = wi_.th;
+        const int tn = wi_.tn;  // == tiles_n for the padding tile of an odd tail: fully OOB -> zeros
         const int x0 = tw * p.box_w + p.phase_dx[ph], y0 = th * p.box_h + p.phase_dy[ph], img0 = tn * p.box_n;
         const int bb = p.b_batched ? img0 : 0;
         const int b_row0 = nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS + ph * p.b_phase_rows;
+        int h_kh = 0, h_cc = 0;  // K item -> (kernel row | tap, channel chunk) by increments, no division per stage
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p.debug_mode & 4) {
@@ -434,8 +467,9 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
             mbar_expect_tx(&full_bar[stage], tx_bytes);
           }
           if constexpr (HALO) {
-            const int kh = kb / p.chunks_per_tap;
-            const int c0 = (kb - kh * p.chunks_per_tap) * CH_ELEMS;
+            const int kh = h_kh;
+            const int c0 = h_cc * CH_ELEMS;
+            if (++h_cc == p.chunks_per_tap) { h_cc = 0; ++h_kh; }
             // one input row segment with its halo: pixels [x0 - 1, x0 + 128], row y0 + kh - 1 (OOB -> zeros)
             if constexpr (GNP) tma_load_4d(&p.a_map[3], &a_full[stage], sa, c0, x0 - 1, y0 + kh - 1, img0);
             else tma2_load_4d(&p.a_map[3], &full_bar[stage], sa, c0, x0 - 1, y0 + kh - 1, img0);
@@ -453,8 +487,9 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
             const CUtensorMap* amap;
             int ax, ay, c0, k0;
             if (item < main_items) {
-              const int tap = item / p.chunks_per_tap;
-              c0 = (item - tap * p.chunks_per_tap) * CH_ELEMS;
+              const int tap = h_kh;  // item -> (tap, channel chunk) by increments
+              c0 = h_cc * CH_ELEMS;
+              if (++h_cc == p.chunks_per_tap) { h_cc = 0; ++h_kh; }
               amap = &p.a_map[p.tap_map[tap]];
               ax = x0 + p.tap_dx[tap];
               ay = y0 + p.tap_dy[tap];
@@ -554,10 +589,8 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
       uint32_t phase = 0;
       int coef_img = -1;  // image whose coefficients sit in coef_smem
       for (int work = group_id; work < total_work; work += num_groups) {
-        const int mt = (work / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tn = mt / (p.tiles_w * p.tiles_h);
+        const WorkItem wi_ = decode_work(p, work, CTAS, static_cast<int>(cta_rank));  // phases == 1 here
+        const int mt = wi_.mt, tw = wi_.tw, th = wi_.th, tn = wi_.tn;
         const int x0 = tw * p.box_w, y0 = th * p.box_h;
         if (tn != coef_img && mt < m_tiles) {
           // The per-(image, channel) coefficients come from global memory once per IMAGE, not once per stage: a stage gives a
@@ -569,9 +602,11 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
           asm volatile("bar.sync 1, %0;" ::"n"(NUM_XF_WARPS * 32) : "memory");
           coef_img = tn;
         }
+        int x_kh = 0, x_cc = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int kh = kb / p.chunks_per_tap;
-          const int c0 = (kb - kh * p.chunks_per_tap) * CH_ELEMS + j * 8;
+          const int kh = x_kh;
+          const int c0 = x_cc * CH_ELEMS + j * 8;
+          if (++x_cc == p.chunks_per_tap) { x_cc = 0; ++x_kh; }
           const int y = y0 + kh - 1;
           mbar_wait(&a_full[stage], phase);
           if (mt < m_tiles && y >= 0 && y < p.gnp_h && !(p.debug_mode & 16)) {
@@ -694,13 +729,8 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
     for (int work = group_id; work < total_work; work += num_groups, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int ph = work % p.phases;
-      const int wk = work / p.phases;
-      const int nt = wk % p.n_tiles;
-      const int mt = (wk / p.n_tiles) * CTAS + static_cast<int>(cta_rank);
-      const int tw = mt % p.tiles_w;
-      const int th = (mt / p.tiles_w) % p.tiles_h;
-      const int tn = mt / (p.tiles_w * p.tiles_h);
+      const WorkItem wi_ = decode_work(p, work, CTAS, static_cast<int>(cta_rank));
+      const int ph = wi_.ph, nt = wi_.nt, mt = wi_.mt, tw = wi_.tw, th = wi_.th, tn = wi_.tn;
       const CUtensorMap* omap = ph == 0 ? &p.out_map : &p.out_map_ph[ph - 1];
       const int ox = tw * p.box_w + wi, oy = th * p.box_h + hi, on = tn * p.box_n + ni;
       const bool valid = mt < m_tiles && row < box_pix && ox < p.Wo && oy < p.Ho && on < p.Nimg;

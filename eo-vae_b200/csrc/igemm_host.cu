@@ -448,6 +448,8 @@ int launch_igemm(const ASpec& a, int mode, const void* w, int k_per_tap, int chu
     p.gn_phase_stride = static_cast<long long>(region);
     p.gn_groups = gn_groups;
     p.gn_cpg = cout / gn_groups;
+    p.gn_cpg_log2 = 0;
+    while ((1 << p.gn_cpg_log2) < p.gn_cpg) ++p.gn_cpg_log2;
   }
   int rc;
   // two K-chunks (128 channels) per pipeline stage where the shapes allow >= 3 stages of shared memory

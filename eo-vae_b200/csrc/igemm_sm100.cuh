@@ -83,6 +83,7 @@ struct Params {
   float* gn_partial;
   int gn_cpg;                     // channels per group (1, 2, 4, 8, 16 or 32)
   int gn_groups;                  // Cout / gn_cpg
+  int gn_cpg_log2;                // log2(gn_cpg) (the supported group widths are powers of two)
   FastDiv fd_phases, fd_ntiles, fd_tw, fd_th;  // work index -> (phase, n-tile, tile x, tile y, tile image)
   int debug_mode;                 // bit mask: 1 no epilogue work | 2 no MMA issue | 4 no TMA loads | 32 no bulk store issue | 64 no tcgen05.ld (tools/igemm_bench.py, epilogue_probe.py)
   // fused GroupNorm + SiLU of the INPUT (GNP kernels): A operand = silu(x * a[n][c] + b[n][c]), zero outside the image
@@ -328,6 +329,44 @@ __device__ __forceinline__ void gn_chunk(const float (&v)[32], int lane, float* 
   } else {  // NV == 64: five halvings leave two consecutive indices per lane
     put(2 * lane, vals[0]);
     put(2 * lane + 1, vals[1]);
+  }
+}
+
+// Two adjacent 32-column chunks of a warp reduced TOGETHER: the shuffle tree of a chunk is a dependent chain of five
+// exchange levels (~150 cycles of latency for ~50 instructions) and the epilogue warps have little else to overlap it with,
+// so the per-thread sums of the first chunk wait in registers and one reduce-scatter over both chunks' values runs the two
+// trees side by side.  Every value still follows the same butterfly (lane l with l ^ 16, ^ 8, ...): bit-identical sums.
+template <int CPG>
+__device__ __forceinline__ void gn_thread_sums(const float (&v)[32], float* vals /* [2 * 32 / CPG]: sums, then squares */) {
+  constexpr int G = 32 / CPG;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) {
+      const float t = v[g * CPG + j];
+      s += t;
+      q = fmaf(t, t, q);
+    }
+    vals[g] = s;
+    vals[G + g] = q;
+  }
+}
+template <int CPG>
+__device__ __forceinline__ void gn_pair_finish(const float* lo /* stashed sums of the first chunk */, const float (&v)[32],
+                                               int lane, float* dst /* of the FIRST chunk: [2 * 32 / CPG groups][2] */) {
+  constexpr int G = 32 / CPG;
+  constexpr int NV = 4 * G;  // <= 32 for CPG >= 4
+  float vals[NV];
+#pragma unroll
+  for (int i = 0; i < 2 * G; ++i) vals[i] = lo[i];
+  gn_thread_sums<CPG>(v, vals + 2 * G);
+  reduce_scatter<NV>(vals, lane);
+  constexpr int LOG = (NV == 32) ? 5 : (NV == 16) ? 4 : (NV == 8) ? 3 : 2;
+  if ((lane & ((1 << (5 - LOG)) - 1)) == 0) {
+    const int idx = lane >> (5 - LOG);         // chunk * 2G + stat * G + g
+    const int chunk = idx / (2 * G), r = idx % (2 * G);
+    dst[((chunk * G) + (r % G)) * 2 + r / G] = vals[0];
   }
 }
 
@@ -773,6 +812,8 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
       if (has_cols && !(p.debug_mode & 1)) {
+        float gn_stash[16];            // per-thread statistics sums of the first chunk of a pair (see gn_pair_finish)
+        float* gn_stash_dst = nullptr;
         auto process = [&](const int c, uint4 (&r16)[4]) {
           uint32_t raw[32];
           if (p.debug_mode & 64) {
@@ -965,14 +1006,34 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
               }
               float* dst = p.gn_partial + ph * p.gn_phase_stride +
-                           ((static_cast<long long>(mt) * 4 + sub) * p.gn_groups + n0 / p.gn_cpg) * 2;
-              switch (p.gn_cpg) {
-                case 1: gn_chunk<1>(v, lane, dst); break;
-                case 2: gn_chunk<2>(v, lane, dst); break;
-                case 4: gn_chunk<4>(v, lane, dst); break;
-                case 8: gn_chunk<8>(v, lane, dst); break;
-                case 16: gn_chunk<16>(v, lane, dst); break;
-                default: gn_chunk<32>(v, lane, dst); break;
+                           ((static_cast<long long>(mt) * 4 + sub) * p.gn_groups + (n0 >> p.gn_cpg_log2)) * 2;
+              const bool lo_chunk = ((c - col_begin) & CW) == 0;
+              if (lo_chunk && p.gn_cpg >= 4 && c + CW < col_begin + HALF_N && n0 + 2 * CW <= p.Cout) {
+                // first chunk of a pair: keep the per-thread sums, the partner chunk reduces both
+                switch (p.gn_cpg) {
+                  case 4: gn_thread_sums<4>(v, gn_stash); break;
+                  case 8: gn_thread_sums<8>(v, gn_stash); break;
+                  case 16: gn_thread_sums<16>(v, gn_stash); break;
+                  default: gn_thread_sums<32>(v, gn_stash); break;
+                }
+                gn_stash_dst = dst;
+              } else if (!lo_chunk && gn_stash_dst != nullptr) {
+                switch (p.gn_cpg) {
+                  case 4: gn_pair_finish<4>(gn_stash, v, lane, gn_stash_dst); break;
+                  case 8: gn_pair_finish<8>(gn_stash, v, lane, gn_stash_dst); break;
+                  case 16: gn_pair_finish<16>(gn_stash, v, lane, gn_stash_dst); break;
+                  default: gn_pair_finish<32>(gn_stash, v, lane, gn_stash_dst); break;
+                }
+                gn_stash_dst = nullptr;
+              } else {
+                switch (p.gn_cpg) {
+                  case 1: gn_chunk<1>(v, lane, dst); break;
+                  case 2: gn_chunk<2>(v, lane, dst); break;
+                  case 4: gn_chunk<4>(v, lane, dst); break;
+                  case 8: gn_chunk<8>(v, lane, dst); break;
+                  case 16: gn_chunk<16>(v, lane, dst); break;
+                  default: gn_chunk<32>(v, lane, dst); break;
+                }
               }
             }
           }

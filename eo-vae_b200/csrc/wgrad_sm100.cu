@@ -233,22 +233,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // chunk -> (x box, y box, image): decoded once, then advanced by increments (three runtime divisions per chunk in
+      // this single thread were a third of its per-chunk latency budget)
+      int bx = chunk0 % chunks_w, by = (chunk0 / chunks_w) % chunks_h, n = chunk0 / (chunks_w * chunks_h);
       for (int c = 0; c < nchunks; ++c) {
-        const int chunk = chunk0 + c;
-        const int x0 = (chunk % chunks_w) * p.bw;
-        const int y0 = ((chunk / chunks_w) % chunks_h) * p.bh;
-        const int n = chunk / (chunks_w * chunks_h);
+        const int x0 = bx * p.bw;
+        const int y0 = by * p.bh;
+        const int n_cur = n;
+        if (++bx == chunks_w) { bx = 0; if (++by == chunks_h) { by = 0; ++n; } }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], A_BYTES + ntaps * BN * 128);
         uint8_t* sa = smem + stage * STAGE;
 #pragma unroll
-        for (int a = 0; a < 2; ++a) tma_load_4d(&p.a_map, &full_bar[stage], sa + a * 8192, cot * 128 + a * 64, x0, y0, n);
+        for (int a = 0; a < 2; ++a) tma_load_4d(&p.a_map, &full_bar[stage], sa + a * 8192, cot * 128 + a * 64, x0, y0, n_cur);
         for (int j = 0; j < ntaps; ++j) {
           const int tap = tap0 + j;
           const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
 #pragma unroll
           for (int b = 0; b < BN / 64; ++b)
-            tma_load_4d(&p.b_map, &full_bar[stage], sa + A_BYTES + (j * (BN / 64) + b) * 8192, cit * BN + b * 64, x0 + dx, y0 + dy, n);
+            tma_load_4d(&p.b_map, &full_bar[stage], sa + A_BYTES + (j * (BN / 64) + b) * 8192, cit * BN + b * 64, x0 + dx, y0 + dy, n_cur);
         }
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -364,15 +367,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc2_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // chunk -> (x box, y box, image): decoded once, then advanced by increments (no division per chunk in this thread)
+      int bx = chunk0 % chunks_w, by = (chunk0 / chunks_w) % chunks_h, bn = chunk0 / (chunks_w * chunks_h);
       for (int c = 0; c < nchunks; c += WG2_KC) {
         const int nck = nchunks - c < WG2_KC ? nchunks - c : WG2_KC;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) mbar_expect_tx(&full_bar[stage], 2 * nck * CHUNK); else mbar_arrive_leader(&full_bar[stage]);
         for (int q = 0; q < nck; ++q) {
-          const int chunk = chunk0 + c + q;
-          const int x0 = (chunk % chunks_w) * p.bw;
-          const int y0 = ((chunk / chunks_w) % chunks_h) * p.bh;
-          const int n = chunk / (chunks_w * chunks_h);
+          const int x0 = bx * p.bw;
+          const int y0 = by * p.bh;
+          const int n = bn;
+          if (++bx == chunks_w) { bx = 0; if (++by == chunks_h) { by = 0; ++bn; } }
           uint8_t* sa = smem + stage * STAGE + q * CHUNK;
 #pragma unroll
           for (int a = 0; a < 2; ++a) tma2_load_4d(&p.a_map, &full_bar[stage], sa + a * 8192, co_base + a * 64, x0, y0, n);

@@ -280,16 +280,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
 #pragma unroll 1
-    for (int cc = 0; cc < NT; cc += 16) {
+    for (int cc = 0; cc < NT; cc += 64) {  // BN is a multiple of 64: a 64-column step stays inside one tap slot
       const int jt = cc / BN, c = cc % BN;  // tap slot, channel inside the Cin tile
       if (jt >= ntaps) break;
-      uint32_t raw[16];
-      tc_ld16(taddr + cc, raw);
+      uint32_t raw[64];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tc_ld16(taddr + cc + 16 * q, raw + 16 * q);  // four TMEM loads in flight per wait
       tc_wait_ld();
       if (co >= p.cout) continue;
       float* dst = p.partial + ((static_cast<long long>(ks) * p.taps + tap0 + jt) * p.cout + co) * p.cin + cit * BN;
 #pragma unroll
-      for (int j = 0; j < 16; j += 4)
+      for (int j = 0; j < 64; j += 4)
         if (cit * BN + c + j < p.cin)
           *reinterpret_cast<float4*>(dst + c + j) =
               nchunks > 0 ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]),
@@ -416,14 +417,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc2_kernel(const __grid
     float* dst = p.partial + ((static_cast<long long>(ks) * p.taps + tap) * p.cout + co) * p.cin + cit * 256;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < 256; c += 16) {
-      uint32_t raw[16];
+    for (int c = 0; c < 256; c += 64) {  // four TMEM loads in flight per wait (one per wait cost 16 load latencies per item)
+      uint32_t raw[64];
       if (nchunks > 0) {
-        tc_ld16(taddr + c, raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tc_ld16(taddr + c + 16 * q, raw + 16 * q);
         tc_wait_ld();
       }
 #pragma unroll
-      for (int j = 0; j < 16; j += 4)
+      for (int j = 0; j < 64; j += 4)
         *reinterpret_cast<float4*>(dst + c + j) =
             nchunks > 0 ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]),
                                       __uint_as_float(raw[j + 3]))

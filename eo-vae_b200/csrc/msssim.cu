@@ -139,32 +139,62 @@ __global__ void __launch_bounds__(256) ssim_scale_kernel(const float* __restrict
 struct ScaleInfo { long long offset; int slots_per_sample; double count; };
 struct Scales { ScaleInfo s[NSCALES]; float beta[NSCALES]; };
 
-// one block: per sample, per scale: mean ssim / cs (fixed order), relu, weighted product; then the batch mean
-__global__ void msssim_finalize_kernel(const float* __restrict__ partial, Scales sc, int b, float* __restrict__ per_sample,
-                                       float* __restrict__ out) {
-  __shared__ double acc[256];
-  double local = 0.0;
-  for (int n = threadIdx.x; n < b; n += blockDim.x) {
-    double prod = 1.0;
-    for (int s = 0; s < NSCALES; ++s) {
-      const float* base = partial + sc.s[s].offset + static_cast<long long>(n) * sc.s[s].slots_per_sample * 2;
-      double a = 0.0, c = 0.0;
-      for (int i = 0; i < sc.s[s].slots_per_sample; ++i) {
-        a += base[2 * i];
-        c += base[2 * i + 1];
-      }
+// Per-(sample, scale) mean of the ssim / cs partial sums: ONE WARP per pair (lanes stride the slots, double accumulation,
+// shuffle tree - a fixed order), results in shared memory.  (One thread per sample walked 768 + 192 + ... slots as a single
+// dependent chain: 80 us per launch for 16 samples.)
+constexpr int MS_CHUNK = 64;  // samples per pass of a 256-thread block
+__device__ __forceinline__ void msssim_scale_means(const float* __restrict__ partial, const Scales& sc, int b, int n0,
+                                                   double (*vs)[NSCALES] /* [MS_CHUNK][NSCALES] shared */) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int nloc = min(MS_CHUNK, b - n0);
+  for (int item = wid; item < nloc * NSCALES; item += nwarps) {
+    const int nl = item / NSCALES, s = item % NSCALES;
+    const int slots = sc.s[s].slots_per_sample;
+    const float2* base = reinterpret_cast<const float2*>(partial + sc.s[s].offset) + static_cast<long long>(n0 + nl) * slots;
+    double a = 0.0, c = 0.0;
+#pragma unroll 4
+    for (int i = lane; i < slots; i += 32) {
+      const float2 v = base[i];
+      a += v.x;
+      c += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
       double v = (s == NSCALES - 1 ? a : c) / sc.s[s].count;
       if (v < 0.0) v = 0.0;  // normalize='relu'
-      prod *= pow(v, static_cast<double>(sc.beta[s]));
+      vs[nl][s] = v;
     }
-    if (per_sample != nullptr) per_sample[n] = static_cast<float>(prod);
-    local += prod;
+  }
+}
+
+// one block: per sample the weighted product of the scale means; then the batch mean
+__global__ void __launch_bounds__(256) msssim_finalize_kernel(const float* __restrict__ partial, Scales sc, int b,
+                                                              float* __restrict__ per_sample, float* __restrict__ out) {
+  __shared__ double acc[256];
+  __shared__ double vs[MS_CHUNK][NSCALES];
+  double local = 0.0;
+  for (int n0 = 0; n0 < b; n0 += MS_CHUNK) {
+    __syncthreads();  // the previous chunk's means have been consumed
+    msssim_scale_means(partial, sc, b, n0, vs);
+    __syncthreads();
+    const int n = n0 + static_cast<int>(threadIdx.x);
+    if (threadIdx.x < MS_CHUNK && n < b) {
+      double prod = 1.0;
+      for (int s = 0; s < NSCALES; ++s) prod *= pow(vs[threadIdx.x][s], static_cast<double>(sc.beta[s]));
+      if (per_sample != nullptr) per_sample[n] = static_cast<float>(prod);
+      local += prod;
+    }
   }
   acc[threadIdx.x] = local;
   __syncthreads();
   if (threadIdx.x == 0) {
+    // sample order: thread t holds samples t, t + 64, ... - summed thread by thread (fixed order)
     double tot = 0.0;
-    for (int i = 0; i < static_cast<int>(blockDim.x); ++i) tot += acc[i];
+    for (int i = 0; i < MS_CHUNK; ++i) tot += acc[i];
     out[0] = static_cast<float>(tot / b);
   }
 }
@@ -313,24 +343,20 @@ __global__ void __launch_bounds__(256) ssim_scale_bwd_kernel(const float* __rest
 }
 
 // coef[s][n] = gscale / B * beta_s * prod_n / v_{n,s} / count_s   (0 where the relu clipped v)
-__global__ void msssim_coef_kernel(const float* __restrict__ partial, Scales sc, int b, const float* __restrict__ gscale,
-                                   float* __restrict__ coef) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= b) return;
-  double v[NSCALES], prod = 1.0;
+__global__ void __launch_bounds__(256) msssim_coef_kernel(const float* __restrict__ partial, Scales sc, int b,
+                                                          const float* __restrict__ gscale, float* __restrict__ coef) {
+  __shared__ double vs[MS_CHUNK][NSCALES];
+  const int n0 = blockIdx.x * MS_CHUNK;
+  msssim_scale_means(partial, sc, b, n0, vs);
+  __syncthreads();
+  const int n = n0 + static_cast<int>(threadIdx.x);
+  if (threadIdx.x >= MS_CHUNK || n >= b) return;
+  double prod = 1.0;
+  for (int s = 0; s < NSCALES; ++s) prod *= pow(vs[threadIdx.x][s], static_cast<double>(sc.beta[s]));
   for (int s = 0; s < NSCALES; ++s) {
-    const float* base = partial + sc.s[s].offset + static_cast<long long>(n) * sc.s[s].slots_per_sample * 2;
-    double a = 0.0, cc = 0.0;
-    for (int i = 0; i < sc.s[s].slots_per_sample; ++i) {
-      a += base[2 * i];
-      cc += base[2 * i + 1];
-    }
-    v[s] = (s == NSCALES - 1 ? a : cc) / sc.s[s].count;
-    if (v[s] < 0.0) v[s] = 0.0;
-    prod *= pow(v[s], static_cast<double>(sc.beta[s]));
+    const double v = vs[threadIdx.x][s];
+    coef[s * b + n] = v > 0.0 ? static_cast<float>(gscale[0] / b * sc.beta[s] * prod / v / sc.s[s].count) : 0.f;
   }
-  for (int s = 0; s < NSCALES; ++s)
-    coef[s * b + n] = v[s] > 0.0 ? static_cast<float>(gscale[0] / b * sc.beta[s] * prod / v[s] / sc.s[s].count) : 0.f;
 }
 
 void make_gauss(Gauss* g) {
@@ -460,7 +486,7 @@ int eovae_msssim_backward(const float* pred, const float* target, int b, int c, 
       ww /= 2;
     }
   }
-  msssim_coef_kernel<<<ceil_div(b, 64), 64, 0, stream>>>(partial, sc, b, grad_scale, coef);
+  msssim_coef_kernel<<<ceil_div(b, MS_CHUNK), 256, 0, stream>>>(partial, sc, b, grad_scale, coef);
   EOVAE_LAUNCH_CHECK();
   static bool attr = false;
   const size_t smem = kBwdSmemFloats * sizeof(float);

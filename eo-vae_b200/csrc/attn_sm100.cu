@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nblocks; ++j) {
       const int b = j & 1;
-      mbar_wait(&s_full[b], (j >> 1) & 1);
+      mbar_wait_long(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
       float s[KB];
 #pragma unroll
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     }
     const float inv_l = 1.f / l;
     // ---- epilogue: O / l -> 16-bit rows of the output
-    mbar_wait(o_full, 0);
+    mbar_wait_long(o_full, 0);
     tc_fence_after();
     uint16_t* orow = static_cast<uint16_t*>(p.out) + (static_cast<long long>(img) * p.L + q) * p.out_ld + dhalf * p.npv;
 #pragma unroll 1

@@ -121,22 +121,50 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// HINT_NS > 0: the thread may be suspended up to that long while the phase is pending (it is woken when the barrier
+// completes) instead of re-polling at once.  Measured on B200, sustained (power-capped) runs, two boxes, builds compared in one
+// job: every wait hinted with 500 / 2000 / 20000 ns = encode step -1.4 ... -2.5 %, training step -0.3 ... -1.8 %; hinting
+// only the long epilogue-side waits = no change.  The default hints every wait with 1000 ns.
+template <uint32_t HINT_NS = 0>
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+  if constexpr (HINT_NS > 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(HINT_NS)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
   return ok != 0;
 }
+#ifndef EOVAE_WAIT_HINT_NS
+#define EOVAE_WAIT_HINT_NS 1000
+#endif
+#ifndef EOVAE_LONG_WAIT_HINT_NS
+#define EOVAE_LONG_WAIT_HINT_NS 0
+#endif
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait<EOVAE_WAIT_HINT_NS>(bar, parity)) {
     if (++spins > (1u << 21)) __trap();  // ~10 s of polling: far beyond any legitimate wait
+  }
+}
+// waits of many threads for a whole mainloop (epilogue side); EOVAE_LONG_WAIT_HINT_NS gives them a longer hint
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait<(EOVAE_LONG_WAIT_HINT_NS > EOVAE_WAIT_HINT_NS ? EOVAE_LONG_WAIT_HINT_NS : EOVAE_WAIT_HINT_NS)>(bar, parity)) {
+    if (++spins > (1u << 21)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
@@ -808,7 +836,7 @@ __global__ void __launch_bounds__(GNP ? NUM_THREADS_GNP : NUM_THREADS, 1) igemm_
         res_fetch(rbuf_a, col_begin);
         res_fetch(rbuf_b, col_begin + CW);
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_long(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
       if (has_cols && !(p.debug_mode & 1)) {

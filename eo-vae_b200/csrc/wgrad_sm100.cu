@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   } else {
     const int sub = warp & 3;
     const int co = cot * 128 + sub * 32 + lane;
-    mbar_wait(done_bar, 0);
+    mbar_wait_long(done_bar, 0);
     tc_fence_after();
     float* dst = p.partial + ((static_cast<long long>(ks) * p.taps + tap) * p.cout + co) * p.cin + cit * BN;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc_kernel(const __grid_
   } else {
     const int sub = warp & 3;
     const int co = cot * 128 + sub * 32 + lane;
-    mbar_wait(done_bar, 0);
+    mbar_wait_long(done_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
 #pragma unroll 1
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_nhwc2_kernel(const __grid
   } else {
     const int sub = warp & 3;
     const int co = co_base + sub * 32 + lane;
-    if (nchunks > 0) mbar_wait(done_bar, 0);
+    if (nchunks > 0) mbar_wait_long(done_bar, 0);
     tc_fence_after();
     float* dst = p.partial + ((static_cast<long long>(ks) * p.taps + tap) * p.cout + co) * p.cin + cit * 256;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);

@@ -338,6 +338,25 @@ def test_msssim_and_consistency_loss(cuda, b, c, h, w):
     assert "train/loss_msssim" not in logs
 
 
+def test_msssim_large_batch_value_and_gradient(cuda):
+    """More samples than one pass of the finalize / coefficient kernels takes (64): per-sample values, their mean and the
+    gradient against autograd over the CPU oracle."""
+    from eo_vae import ops
+    from oracle import eovae_oracle as O
+    b, c, h, w = 70, 1, 176, 176
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((b, c, h, w), generator=g).clamp_(-2, 6)
+    r = (x + (0.1 + 0.4 * torch.rand((b, 1, 1, 1), generator=g)) * torch.randn((b, c, h, w), generator=g)).requires_grad_(True)
+    ref = O.ms_ssim(r, x)
+    ref.backward()
+    out, per = ops.msssim(r.detach().to(cuda), x.to(cuda))
+    assert abs(float(out) - float(ref)) / float(ref) < 1e-4
+    per_ref = torch.stack([O.ms_ssim(r.detach()[i:i + 1], x[i:i + 1]) for i in range(b)])
+    assert torch.allclose(per.cpu(), per_ref.float(), rtol=1e-4, atol=1e-6)
+    gr = ops.msssim_backward(r.detach().to(cuda), x.to(cuda), 6.0, torch.ones(1, device=cuda))
+    assert _rel(gr.cpu(), r.grad) < 1e-3
+
+
 @pytest.mark.parametrize("modality", ["S2RGB", "S1RTC", "S2L2A", "S2L1C"])
 @pytest.mark.parametrize("cfg_name", ["tiny", "full"])
 def test_hypernet(cuda, modality, cfg_name):

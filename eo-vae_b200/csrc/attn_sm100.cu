@@ -200,8 +200,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
         if (c >= valid) s[c] = -INFINITY;
         bm = fmaxf(bm, s[c]);
       }
-      const float mn = fmaxf(m, bm);
-      const float alpha = ex2f((m - mn) * p.scale_log2e);   // 0 on the first block (m = -inf), 1 when the maximum stays
+      // LAZY reference maximum: the exponent reference only moves when the block maximum exceeds it by more than 8 in the
+      // log2 domain (always on the first block, m = -inf).  Probabilities then reach at most 2^8 instead of 1 - exact in
+      // fp32 / 16-bit floating point, O and l carry the same factor and it cancels in O / l - and the O rows in TMEM are
+      // rescaled on a few blocks instead of whenever any of a warp's 32 rows sees a new maximum (most blocks).
+      const bool upd = (bm - m) * p.scale_log2e > 8.0f;
+      const float mn = upd ? bm : m;
+      const float alpha = upd ? ex2f((m - mn) * p.scale_log2e) : 1.f;   // 0 on the first block
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < KB; ++c) {
@@ -215,13 +220,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.f)) {   // some row of this warp moved its maximum: rescale the warp's O rows
 #pragma unroll 1
-          for (int c = 0; c < p.npv; c += 16) {
-            uint32_t raw[16];
-            tc_ld16(tmem_o + lane_addr + c, raw);
+          for (int c = 0; c < p.npv; c += 64) {   // npv is a multiple of 64: four TMEM loads in flight per wait
+            uint32_t raw[64];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tc_ld16(tmem_o + lane_addr + c + 16 * u, raw + 16 * u);
             tc_wait_ld();
 #pragma unroll
-            for (int h = 0; h < 16; ++h) raw[h] = __float_as_uint(__uint_as_float(raw[h]) * alpha);
-            tc_st16(tmem_o + lane_addr + c, raw);
+            for (int h = 0; h < 64; ++h) raw[h] = __float_as_uint(__uint_as_float(raw[h]) * alpha);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tc_st16(tmem_o + lane_addr + c + 16 * u, raw + 16 * u);
           }
           tc_wait_st();
         }
@@ -245,17 +252,21 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     tc_fence_after();
     uint16_t* orow = static_cast<uint16_t*>(p.out) + (static_cast<long long>(img) * p.L + q) * p.out_ld + dhalf * p.npv;
 #pragma unroll 1
-    for (int c = 0; c < p.npv; c += 16) {
-      uint32_t raw[16];
-      tc_ld16(tmem_o + lane_addr + c, raw);
+    for (int c = 0; c < p.npv; c += 64) {   // four TMEM loads in flight per wait
+      uint32_t raw[64];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) tc_ld16(tmem_o + lane_addr + c + 16 * u, raw + 16 * u);
       tc_wait_ld();
       if (q < p.L) {
-        uint32_t w[8];
 #pragma unroll
-        for (int h = 0; h < 8; ++h)
-          w[h] = pack16(__uint_as_float(raw[2 * h]) * inv_l, __uint_as_float(raw[2 * h + 1]) * inv_l, p.bf16 ? EOVAE_BF16 : EOVAE_F16);
-        *reinterpret_cast<uint4*>(orow + c) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        for (int u = 0; u < 8; ++u) {
+          uint32_t w[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            w[h] = pack16(__uint_as_float(raw[8 * u + 2 * h]) * inv_l, __uint_as_float(raw[8 * u + 2 * h + 1]) * inv_l,
+                          p.bf16 ? EOVAE_BF16 : EOVAE_F16);
+          *reinterpret_cast<uint4*>(orow + c + 8 * u) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
     }
   }
